@@ -1,0 +1,25 @@
+// Error reporting and device queries for the C ABI (include/fplplus_b200.h).
+#include <stdarg.h>
+
+#include "common.cuh"
+#include "../../include/fplplus_b200.h"
+
+static thread_local char g_err[1024] = "";
+
+void fpl_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* fpl_last_error(void) { return g_err; }
+
+extern "C" int fpl_version(void) { return 100; }
+
+extern "C" int fpl_device_is_sm100(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10 ? 1 : 0;
+}

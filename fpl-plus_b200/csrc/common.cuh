@@ -1,0 +1,118 @@
+// Shared helpers for the fplplus_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define FPL_NUM_SMS 148
+
+void fpl_set_error(const char* fmt, ...);
+
+#define FPL_CHECK_CUDA(expr)                                                              \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            fpl_set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr,           \
+                          cudaGetErrorString(_e));                                        \
+            return 1;                                                                     \
+        }                                                                                 \
+    } while (0)
+
+#define FPL_REQUIRE(cond, ...)                                                            \
+    do {                                                                                  \
+        if (!(cond)) {                                                                    \
+            fpl_set_error(__VA_ARGS__);                                                   \
+            return 2;                                                                     \
+        }                                                                                 \
+    } while (0)
+
+#define FPL_LAUNCH_CHECK() FPL_CHECK_CUDA(cudaGetLastError())
+
+// ---- 16-byte bf16x8 vectors ----------------------------------------------------------
+struct __align__(16) bf16x8 {
+    __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ void bf16x8_to_float(const bf16x8& a, float* f) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 t = __bfloat1622float2(a.v[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+
+__device__ __forceinline__ bf16x8 float_to_bf16x8(const float* f) {
+    bf16x8 r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return r;
+}
+
+__device__ __forceinline__ bf16x8 ldg_bf16x8(const void* p) {
+    int4 t = __ldg(reinterpret_cast<const int4*>(p));
+    return *reinterpret_cast<bf16x8*>(&t);
+}
+
+// streaming (read-once) 16-byte load / store: keep L1 for data with reuse
+__device__ __forceinline__ int4 ld_stream16(const void* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ld_stream_f4(const void* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// C8-planar addressing: element-vector index of (n,d,c8,h,w) in a buffer with c8tot groups
+__device__ __forceinline__ int64_t c8_index(int n, int d, int c8, int h, int w, int D, int C8tot, int H, int W) {
+    return ((((int64_t)n * D + d) * C8tot + c8) * H + h) * (int64_t)W + w;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- Philox4x32-10 (counter based; the same stream is regenerated in backward) ------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+
+// keep-mask bits for the 8 channels of element-vector `vec_index` (dense C8-planar order)
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t offset, uint64_t vec_index, float p) {
+    uint64_t c = vec_index * 2 + offset;
+    uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    uint4 a = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), key);
+    uint4 b = philox4x32_10(make_uint4((uint32_t)(c + 1), (uint32_t)((c + 1) >> 32), 0u, 0u), key);
+    uint32_t r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t bits = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float u = (float)(r[i] >> 8) * (1.0f / 16777216.0f);  // [0,1)
+        bits |= (u >= p ? 1u : 0u) << i;
+    }
+    return bits;
+}

@@ -1,0 +1,465 @@
+// Implicit-GEMM 3-D convolution on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM),
+// operands staged by TMA.  Forward and dgrad of nn.Conv3d k(kd,3,3) stride 1 "same" padding
+// (PyMIC/pymic/net/net3d/unet2d5_dsbn.py:75,79 and their autograd), bf16 in / fp32 accumulate.
+//
+// GEMM view per tile:  D[128 voxels x NB] += A[128 x 16] * B[16 x NB]   for every tap and 16-channel slice
+//   * tile = 16(H) x 8(W) output voxels of one (n, d) plane; M row r <-> (h0 + r/8, w0 + r%8).
+//   * activations are C8-planar ([N][D][C/8][H][W][8] bf16).  One TMA box {80 elem, 18 rows, KC/8 planes}
+//     lands a halo'd plane chunk in shared memory as [c8][18][10][8]: that is simultaneously the
+//     canonical no-swizzle K-major UMMA layout (8 voxels x 16 B core matrices; SBO = one tile row =
+//     160 B, LBO = one channel-group plane = 2880 B), so each of the 9 in-plane taps is the SAME
+//     buffer read through a descriptor whose start address is shifted by (kh*10 + kw)*16 B.
+//     Zero padding in H/W comes from TMA out-of-bounds fill; out-of-range depth planes are skipped.
+//   * weights are pre-staged (fpl_conv3d_prep_weight) as [slice][cin chunk][kd][tap 9][KC/8][NB][8] bf16,
+//     i.e. each pipeline stage's B operand is one contiguous chunk fetched with cp.async.bulk.
+//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue
+//     (tcgen05.ld -> +bias -> per-channel sum / sum^2 for BatchNorm -> bf16 -> coalesced 16 B stores).
+//     Two TMEM accumulator stages overlap the epilogue of tile i with the MMAs of tile i+1.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "../../include/fplplus_b200.h"
+
+namespace {
+
+constexpr int kTileH = 16, kTileW = 8;
+constexpr int kBoxH = kTileH + 2, kBoxW = kTileW + 2;
+constexpr int kPlaneBytes = kBoxH * kBoxW * 16;       // one channel-group (8 ch) halo plane: 2880 B
+constexpr int kMaxStages = 8;
+constexpr int kNumThreads = 192;
+constexpr int kSmemBudget = 200 * 1024;
+
+struct TcConfig {
+    int nb;        // output channels per CTA tile (UMMA N)
+    int kc;        // input channels per pipeline stage
+    int nslices, nchunks;
+    int a_bytes, b_bytes, stage_bytes, stages;
+    int tmem_cols;
+    int smem_bytes;
+};
+
+bool make_config(int cin, int cout, TcConfig& c) {
+    if (cin % 16 != 0 || cout % 16 != 0 || cin <= 0 || cout <= 0) return false;
+    c.nb = cout;
+    if (c.nb > 128) {
+        if (cout % 128 == 0) c.nb = 128;
+        else if (cout % 64 == 0) c.nb = 64;
+        else if (cout % 32 == 0) c.nb = 32;
+        else c.nb = 16;
+    }
+    c.kc = 64;
+    while (c.kc > 16 && (c.kc * c.nb > 4096 || cin % c.kc != 0)) c.kc /= 2;
+    if (cin % c.kc != 0) return false;
+    c.nslices = cout / c.nb;
+    c.nchunks = cin / c.kc;
+    c.a_bytes = (c.kc / 8) * kPlaneBytes;
+    c.b_bytes = 9 * c.kc * c.nb * 2;
+    c.stage_bytes = c.a_bytes + c.b_bytes;
+    c.stages = kSmemBudget / c.stage_bytes;
+    if (c.stages > kMaxStages) c.stages = kMaxStages;
+    if (c.stages < 2) return false;
+    // small stages: cap at ~100 KB so two CTAs fit on one SM
+    while (c.stages > 3 && c.stages * c.stage_bytes > 100 * 1024) --c.stages;
+    int cols = 2 * c.nb;
+    c.tmem_cols = 32;
+    while (c.tmem_cols < cols) c.tmem_cols *= 2;
+    c.smem_bytes = c.stages * c.stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + 2 * 2 * c.nb * (int)sizeof(float);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// no-swizzle K-major shared memory matrix descriptor (SM100 format, version field = 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+struct TcParams {
+    const __nv_bfloat16* image;
+    const float* bias;
+    bf16x8* y;
+    int y_c8tot, y_c8off;
+    double* stats;
+    int N, D, H, W, cin, cout, kd;
+    int x_c8tot, x_c8off;
+    int nb, kc, nslices, nchunks, a_bytes, b_bytes, stages, tmem_cols;
+    int tiles_h, tiles_w, total_tiles;
+    int dbg_swap_lbo_sbo;
+};
+
+struct TileCoord {
+    int n, d, h0, w0, slice;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int t) {
+    TileCoord c;
+    int tw = t % P.tiles_w; t /= P.tiles_w;
+    int th = t % P.tiles_h; t /= P.tiles_h;
+    c.d = t % P.D; t /= P.D;
+    c.n = t % P.N;
+    c.slice = t / P.N;
+    c.h0 = th * kTileH;
+    c.w0 = tw * kTileW;
+    return c;
+}
+
+__global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, TcParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    // stage ring at 1024-byte alignment, then barriers, the TMEM base slot and the BN partial sums
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stage_bytes = P.a_bytes + P.b_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kMaxStages;
+    uint64_t* tmem_full = bars + 2 * kMaxStages;
+    uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+    float* stat_sm = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);   // [2][nb] (sum, sumsq)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pad_d = P.kd / 2;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+        for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+    for (int i = threadIdx.x; i < 2 * P.nb; i += kNumThreads) stat_sm[i] = 0.0f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+                TileCoord c = decode_tile(P, t);
+                for (int q = 0; q < P.nchunks; ++q) {
+                    for (int kdi = 0; kdi < P.kd; ++kdi) {
+                        int dz = c.d + kdi - pad_d;
+                        if (dz < 0 || dz >= P.D) continue;
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
+                        uint8_t* b_dst = a_dst + P.a_bytes;
+                        mbar_expect_tx(&full_bar[stage], (uint32_t)(P.a_bytes + P.b_bytes));
+                        tma_load_3d(a_dst, &xmap, &full_bar[stage], (c.w0 - 1) * 8, c.h0 - 1,
+                                    (c.n * P.D + dz) * P.x_c8tot + P.x_c8off + q * (P.kc / 8));
+                        const uint8_t* b_src = reinterpret_cast<const uint8_t*>(P.image) +
+                                               ((size_t)(c.slice * P.nchunks + q) * P.kd + kdi) * P.b_bytes;
+                        bulk_load(b_dst, b_src, (uint32_t)P.b_bytes, &full_bar[stage]);
+                        if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.nb >> 3) << 17) | (8u << 24);
+            const uint32_t a_lbo = P.dbg_swap_lbo_sbo ? kBoxW * 16 : kPlaneBytes;
+            const uint32_t a_sbo = P.dbg_swap_lbo_sbo ? kPlaneBytes : kBoxW * 16;
+            const uint32_t b_lbo = P.dbg_swap_lbo_sbo ? 128 : P.nb * 16;
+            const uint32_t b_sbo = P.dbg_swap_lbo_sbo ? P.nb * 16 : 128;
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+                TileCoord c = decode_tile(P, t);
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.nb);
+                uint32_t accumulate = 0;
+                for (int q = 0; q < P.nchunks; ++q) {
+                    for (int kdi = 0; kdi < P.kd; ++kdi) {
+                        int dz = c.d + kdi - pad_d;
+                        if (dz < 0 || dz >= P.D) continue;
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_base = smem_u32(smem + (size_t)stage * stage_bytes);
+                        const uint32_t b_base = a_base + P.a_bytes;
+                        const int ksteps = P.kc / 16;
+#pragma unroll 1
+                        for (int t9 = 0; t9 < 9; ++t9) {
+                            const uint32_t a_tap = a_base + (uint32_t)(((t9 / 3) * kBoxW + (t9 % 3)) * 16);
+                            const uint32_t b_tap = b_base + (uint32_t)(t9 * (P.kc / 8) * P.nb * 16);
+                            for (int j = 0; j < ksteps; ++j) {
+                                uint64_t adesc = make_desc(a_tap + (uint32_t)(j * 2 * kPlaneBytes), a_lbo, a_sbo);
+                                uint64_t bdesc = make_desc(b_tap + (uint32_t)(j * 2 * P.nb * 16), b_lbo, b_sbo);
+                                umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+                                accumulate = 1;
+                            }
+                        }
+                        umma_commit(&empty_bar[stage]);      // smem slot reusable once these MMAs retire
+                        if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+                umma_commit(&tmem_full[acc]);                // accumulator ready for the epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;
+        const int hl = row / kTileW, wl = row % kTileW;
+        int acc = 0; uint32_t acc_phase = 0;
+        int cur_slice = -1;
+        for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+            TileCoord c = decode_tile(P, t);
+            if (P.stats != nullptr && c.slice != cur_slice) {
+                if (cur_slice >= 0) {
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    for (int i = threadIdx.x - 64; i < 2 * P.nb; i += 128) {
+                        int ch = i % P.nb, which = i / P.nb;
+                        atomicAdd(P.stats + which * P.cout + cur_slice * P.nb + ch, (double)stat_sm[i]);
+                        stat_sm[i] = 0.0f;
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                cur_slice = c.slice;
+            }
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int h = c.h0 + hl, w = c.w0 + wl;
+            const bool valid = h < P.H && w < P.W;
+            const int64_t HW = (int64_t)P.H * P.W;
+            const int64_t out_base = (((int64_t)c.n * P.D + c.d) * P.y_c8tot + P.y_c8off + (c.slice * P.nb) / 8) * HW +
+                                     (int64_t)h * P.W + w;
+            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P.nb);
+            for (int c0 = 0; c0 < P.nb; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(t_row + (uint32_t)c0, r);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    v[i] = __uint_as_float(r[i]);
+                    if (P.bias != nullptr) v[i] += __ldg(P.bias + c.slice * P.nb + c0 + i);
+                }
+                if (valid) {
+                    P.y[out_base + (int64_t)(c0 / 8) * HW] = float_to_bf16x8(v);
+                    P.y[out_base + (int64_t)(c0 / 8 + 1) * HW] = float_to_bf16x8(v + 8);
+                }
+                if (P.stats != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float s = valid ? v[i] : 0.0f;
+                        float q2 = s * s;
+                        s = warp_sum(s);
+                        q2 = warp_sum(q2);
+                        if (lane == 0) {
+                            atomicAdd(&stat_sm[c0 + i], s);
+                            atomicAdd(&stat_sm[P.nb + c0 + i], q2);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (P.stats != nullptr && cur_slice >= 0) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = threadIdx.x - 64; i < 2 * P.nb; i += 128) {
+                int ch = i % P.nb, which = i / P.nb;
+                atomicAdd(P.stats + which * P.cout + cur_slice * P.nb + ch, (double)stat_sm[i]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight staging: fp32 [Cout][Cin][T] -> bf16 [slice][chunk][kd][tap9][KC/8][NB][8]
+// ---------------------------------------------------------------------------------------------
+__global__ void prep_weight_kernel(const float* __restrict__ w, __nv_bfloat16* image, int cin_eff, int cout_eff, int kd,
+                                   int transpose_flip, int nb, int kc, int64_t total) {
+    const int T = kd * 9;
+    const int nchunks = cin_eff / kc;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t t = i;
+        int e = (int)(t % 8); t /= 8;
+        int nrow = (int)(t % nb); t /= nb;
+        int k8 = (int)(t % (kc / 8)); t /= (kc / 8);
+        int t9 = (int)(t % 9); t /= 9;
+        int kdi = (int)(t % kd); t /= kd;
+        int q = (int)(t % nchunks);
+        int s = (int)(t / nchunks);
+        int out = s * nb + nrow, in = q * kc + k8 * 8 + e, tap = kdi * 9 + t9;
+        float v;
+        if (!transpose_flip) v = w[((int64_t)out * cin_eff + in) * T + tap];
+        else v = w[((int64_t)in * cout_eff + out) * T + (T - 1 - tap)];   // w is [Cout_fwd = cin_eff][Cin_fwd = cout_eff][T]
+        image[i] = __float2bfloat16_rn(v);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+}  // namespace
+
+extern "C" int64_t fpl_conv3d_weight_image_bytes(int cin, int cout, int kd) {
+    TcConfig c;
+    if (!make_config(cin, cout, c)) return -1;
+    return (int64_t)c.nslices * c.nchunks * kd * c.b_bytes;
+}
+
+extern "C" int fpl_conv3d_prep_weight(const float* w, int cin, int cout, int kd, int transpose_flip, void* image,
+                                      void* stream) {
+    const int cin_eff = transpose_flip ? cout : cin, cout_eff = transpose_flip ? cin : cout;
+    TcConfig c;
+    FPL_REQUIRE(make_config(cin_eff, cout_eff, c), "fpl_conv3d_prep_weight: unsupported channels (%d -> %d)", cin_eff, cout_eff);
+    FPL_REQUIRE(kd == 1 || kd == 3, "fpl_conv3d_prep_weight: kd=%d must be 1 or 3", kd);
+    int64_t total = (int64_t)c.nslices * c.nchunks * kd * c.b_bytes / 2;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > FPL_NUM_SMS * 8) blocks = FPL_NUM_SMS * 8;
+    prep_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)image, cin_eff, cout_eff, kd,
+                                                                 transpose_flip, c.nb, c.kc, total);
+    FPL_LAUNCH_CHECK();
+    return 0;
+}
+
+static int g_dbg_swap = 0;
+extern "C" void fpl_debug_set(int key, int value) {
+    if (key == 0) g_dbg_swap = value;
+}
+
+extern "C" int fpl_conv3d_tc(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias, void* y,
+                             int y_c8tot, int y_c8off, double* stats, int n, int d, int h, int w, int cin, int cout,
+                             int kd, void* stream) {
+    TcConfig c;
+    FPL_REQUIRE(make_config(cin, cout, c), "fpl_conv3d_tc: unsupported channels (%d -> %d); need multiples of 16", cin, cout);
+    FPL_REQUIRE(kd == 1 || kd == 3, "fpl_conv3d_tc: kd=%d must be 1 or 3", kd);
+    FPL_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(image) & 15) == 0,
+                "fpl_conv3d_tc: x/image must be 16-byte aligned");
+    EncodeTiledFn encode = get_encode_fn();
+    FPL_REQUIRE(encode != nullptr, "fpl_conv3d_tc: cuTensorMapEncodeTiled not available from the driver");
+    CUtensorMap xmap;
+    cuuint64_t gdim[3] = {(cuuint64_t)w * 8, (cuuint64_t)h, (cuuint64_t)n * d * x_c8tot};
+    cuuint64_t gstride[2] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16};
+    cuuint32_t box[3] = {(cuuint32_t)kBoxW * 8, (cuuint32_t)kBoxH, (cuuint32_t)(c.kc / 8)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(x), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FPL_REQUIRE(r == CUDA_SUCCESS, "fpl_conv3d_tc: cuTensorMapEncodeTiled failed (%d) for dims [%d,%d,%d] c8tot=%d", (int)r,
+                w * 8, h, n * d * x_c8tot, x_c8tot);
+    TcParams P;
+    P.image = (const __nv_bfloat16*)image; P.bias = bias; P.y = (bf16x8*)y; P.y_c8tot = y_c8tot; P.y_c8off = y_c8off;
+    P.stats = stats; P.N = n; P.D = d; P.H = h; P.W = w; P.cin = cin; P.cout = cout; P.kd = kd;
+    P.x_c8tot = x_c8tot; P.x_c8off = x_c8off;
+    P.nb = c.nb; P.kc = c.kc; P.nslices = c.nslices; P.nchunks = c.nchunks; P.a_bytes = c.a_bytes; P.b_bytes = c.b_bytes;
+    P.stages = c.stages; P.tmem_cols = c.tmem_cols;
+    P.tiles_h = (h + kTileH - 1) / kTileH; P.tiles_w = (w + kTileW - 1) / kTileW;
+    int64_t total = (int64_t)P.tiles_h * P.tiles_w * d * n * c.nslices;
+    FPL_REQUIRE(total < (1ll << 30), "fpl_conv3d_tc: too many tiles");
+    P.total_tiles = (int)total;
+    P.dbg_swap_lbo_sbo = g_dbg_swap;
+    FPL_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
+    int ctas_per_sm = c.smem_bytes <= 110 * 1024 ? 2 : 1;
+    int grid = FPL_NUM_SMS * ctas_per_sm;
+    if (grid > P.total_tiles) grid = P.total_tiles;
+    conv3d_tc_kernel<<<grid, kNumThreads, c.smem_bytes, (cudaStream_t)stream>>>(xmap, P);
+    FPL_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,459 @@
+// DSBN BatchNorm3d + PReLU + Dropout + MaxPool, forward and backward, on C8-planar bf16.
+// Replaces nn.BatchNorm3d (selected domain, net_run_dsbn/dsbn.py:54-57), nn.PReLU,
+// nn.Dropout and nn.MaxPool3d of PyMIC/pymic/net/net3d/unet2d5_dsbn.py:75-81,104-117.
+// All kernels are HBM-streaming: one 16-byte vector (8 channels of one voxel) per access,
+// consecutive threads on consecutive voxels of one (n, d, channel-group) plane.
+#include "common.cuh"
+#include "../../include/fplplus_b200.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// ------------------------------------------------------------------------------------
+// finalize: batch statistics -> scale/shift, running statistics update
+// ------------------------------------------------------------------------------------
+__global__ void dsbn_finalize_kernel(const double* __restrict__ stats, double inv_count, double unbias,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     float* running_mean, float* running_var, long long* nbt,
+                                     float momentum, float eps, int training,
+                                     float* scale, float* shift, float* save_mean, float* save_invstd, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) {
+        float mean, invstd;
+        if (training) {
+            double m = stats[c] * inv_count;
+            double var = stats[C + c] * inv_count - m * m;
+            if (var < 0.0) var = 0.0;
+            mean = (float)m;
+            invstd = (float)(1.0 / sqrt(var + (double)eps));
+            if (running_mean != nullptr) {
+                running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * mean;
+                running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)(var * unbias);
+            }
+        } else {
+            mean = running_mean[c];
+            invstd = rsqrtf(running_var[c] + eps);
+            invstd = 1.0f / sqrtf(running_var[c] + eps);
+        }
+        float g = gamma[c] * invstd;
+        scale[c] = g;
+        shift[c] = beta[c] - mean * g;
+        save_mean[c] = mean;
+        save_invstd[c] = invstd;
+    }
+    if (training && nbt != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *nbt += 1;
+}
+
+// ------------------------------------------------------------------------------------
+// forward: a = dropout(prelu(y*scale+shift)), optional fused max-pool
+// ------------------------------------------------------------------------------------
+struct ActParams {
+    const bf16x8* y;            // dense [N][D][C8][H][W]
+    const float* scale;
+    const float* shift;
+    const float* slope;
+    bf16x8* a;
+    int a_c8tot, a_c8off;
+    bf16x8* pooled;
+    int p_c8tot, p_c8off;
+    uint2* pool_idx;            // 8 x uint8 per pooled vector
+    int pool_kd;
+    float drop_p;
+    const uint2* drop_mask;     // 8 x uint8 per vector, dense order
+    uint64_t seed, offset;
+    int N, D, C8, H, W;
+};
+
+__device__ __forceinline__ void load_affine(const float* scale, const float* shift, int c8, float* sc, float* sh) {
+    const float4* s4 = reinterpret_cast<const float4*>(scale + c8 * 8);
+    const float4* h4 = reinterpret_cast<const float4*>(shift + c8 * 8);
+    float4 a = __ldg(s4), b = __ldg(s4 + 1), c = __ldg(h4), d = __ldg(h4 + 1);
+    sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; sc[4] = b.x; sc[5] = b.y; sc[6] = b.z; sc[7] = b.w;
+    sh[0] = c.x; sh[1] = c.y; sh[2] = c.z; sh[3] = c.w; sh[4] = d.x; sh[5] = d.y; sh[6] = d.z; sh[7] = d.w;
+}
+
+__device__ __forceinline__ uint32_t keep_bits(const uint2* mask, uint64_t seed, uint64_t offset, int64_t vec, float p) {
+    if (mask != nullptr) {
+        uint2 m = __ldg(mask + vec);
+        uint32_t bits = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            bits |= (((m.x >> (8 * i)) & 0xffu) ? 1u : 0u) << i;
+            bits |= (((m.y >> (8 * i)) & 0xffu) ? 1u : 0u) << (4 + i);
+        }
+        return bits;
+    }
+    return dropout_keep8(seed, offset, (uint64_t)vec, p);
+}
+
+__global__ void __launch_bounds__(kThreads) dsbn_act_fwd_kernel(ActParams P) {
+    const int64_t HW = (int64_t)P.H * P.W;
+    const int64_t total = (int64_t)P.N * P.D * P.C8 * HW;
+    const float slope = __ldg(P.slope);
+    const bool drop = P.drop_p > 0.0f;
+    const float keep_scale = drop ? 1.0f / (1.0f - P.drop_p) : 1.0f;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
+        int64_t plane = v / HW;
+        int64_t hw = v - plane * HW;
+        int c8 = (int)(plane % P.C8);
+        int64_t nd = plane / P.C8;
+        float sc[8], sh[8], f[8];
+        load_affine(P.scale, P.shift, c8, sc, sh);
+        int4 raw = ld_stream16(P.y + v);
+        bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw), f);
+        uint32_t keep = drop ? keep_bits(P.drop_mask, P.seed, P.offset, v, P.drop_p) : 0xffu;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float z = fmaf(f[i], sc[i], sh[i]);
+            float a = z > 0.0f ? z : slope * z;
+            f[i] = ((keep >> i) & 1u) ? a * keep_scale : 0.0f;
+        }
+        int64_t o = (nd * P.a_c8tot + P.a_c8off + c8) * HW + hw;
+        P.a[o] = float_to_bf16x8(f);
+    }
+}
+
+// one thread per pooled output vector; reads the 2x2x2 (or 1x2x2) window, writes the full
+// resolution activations, the pooled max and the 3-bit argmax code (first max wins, scan
+// order d,h,w as in torch's max_pool3d).
+__global__ void __launch_bounds__(kThreads) dsbn_act_pool_fwd_kernel(ActParams P) {
+    const int kd = P.pool_kd;
+    const int D2 = P.D / kd, H2 = P.H / 2, W2 = P.W / 2;
+    const int64_t HW = (int64_t)P.H * P.W, HW2 = (int64_t)H2 * W2;
+    const int64_t total = (int64_t)P.N * D2 * P.C8 * HW2;
+    const float slope = __ldg(P.slope);
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
+        int w2 = (int)(v % W2);
+        int64_t t = v / W2;
+        int h2 = (int)(t % H2); t /= H2;
+        int c8 = (int)(t % P.C8); t /= P.C8;
+        int d2 = (int)(t % D2);
+        int n = (int)(t / D2);
+        float sc[8], sh[8], best[8];
+        uint32_t code[8];
+        load_affine(P.scale, P.shift, c8, sc, sh);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; code[i] = 0; }
+        for (int dd = 0; dd < kd; ++dd) {
+            int d = d2 * kd + dd;
+            int64_t nd = (int64_t)n * P.D + d;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                int64_t row = (int64_t)(h2 * 2 + hh) * P.W + w2 * 2;
+                int64_t src = (nd * P.C8 + c8) * HW + row;
+                int64_t dst = (nd * P.a_c8tot + P.a_c8off + c8) * HW + row;
+#pragma unroll
+                for (int ww = 0; ww < 2; ++ww) {
+                    float f[8];
+                    int4 raw = ld_stream16(P.y + src + ww);
+                    bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw), f);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float z = fmaf(f[i], sc[i], sh[i]);
+                        f[i] = z > 0.0f ? z : slope * z;
+                    }
+                    bf16x8 outv = float_to_bf16x8(f);
+                    P.a[dst + ww] = outv;
+                    // compare on the bf16-rounded values (what backward and the next layer see)
+                    bf16x8_to_float(outv, f);
+                    uint32_t k = (uint32_t)((dd * 2 + hh) * 2 + ww);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (f[i] > best[i]) { best[i] = f[i]; code[i] = k; }
+                    }
+                }
+            }
+        }
+        int64_t po = (((int64_t)n * D2 + d2) * P.p_c8tot + P.p_c8off + c8) * HW2 + (int64_t)h2 * W2 + w2;
+        P.pooled[po] = float_to_bf16x8(best);
+        uint2 packed;
+        packed.x = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+        packed.y = code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24);
+        P.pool_idx[v] = packed;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------
+struct ActBwdParams {
+    const bf16x8* y;
+    const bf16x8* g1;
+    int g1_c8tot, g1_c8off;
+    const bf16x8* g_pool;
+    int gp_c8tot, gp_c8off;
+    const uint2* pool_idx;
+    int pool_kd;
+    const float* scale;
+    const float* shift;
+    const float* mean;
+    const float* invstd;
+    const float* slope;
+    float drop_p;
+    const uint2* drop_mask;
+    uint64_t seed, offset;
+    double* red;                // [2C+1]: sum dz, sum dz*xhat, dslope
+    bf16x8* dy;
+    int training;
+    double inv_count;
+    int N, D, C8, H, W;
+};
+
+// gradient wrt the BN output (dz[8]) of vector (nd, c8, hw); also returns z*g for dslope
+__device__ __forceinline__ void act_bwd_vec(const ActBwdParams& P, int64_t v, int64_t nd, int c8, int h, int w,
+                                            const float* sc, const float* sh, float slope, float keep_scale,
+                                            float* yf, float* dz, float& dslope) {
+    const int64_t HW = (int64_t)P.H * P.W;
+    float g[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = 0.0f;
+    if (P.g1 != nullptr) {
+        int4 raw = ld_stream16(P.g1 + (nd * P.g1_c8tot + P.g1_c8off + c8) * HW + (int64_t)h * P.W + w);
+        bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw), g);
+    }
+    if (P.g_pool != nullptr) {
+        const int kd = P.pool_kd;
+        const int D2 = P.D / kd, H2 = P.H / 2, W2 = P.W / 2;
+        int n = (int)(nd / P.D), d = (int)(nd % P.D);
+        int d2 = d / kd, h2 = h >> 1, w2 = w >> 1;
+        uint32_t mycode = (uint32_t)((((d - d2 * kd) * 2) + (h & 1)) * 2 + (w & 1));
+        int64_t pnd = (int64_t)n * D2 + d2;
+        int64_t pix = (int64_t)h2 * W2 + w2;
+        uint2 codes = __ldg(P.pool_idx + (pnd * P.C8 + c8) * ((int64_t)H2 * W2) + pix);
+        bf16x8 gp = ldg_bf16x8(P.g_pool + (pnd * P.gp_c8tot + P.gp_c8off + c8) * ((int64_t)H2 * W2) + pix);
+        float gpf[8];
+        bf16x8_to_float(gp, gpf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint32_t cd = ((i < 4 ? codes.x : codes.y) >> (8 * (i & 3))) & 0xffu;
+            if (cd == mycode) g[i] += gpf[i];
+        }
+    }
+    int4 raw = ld_stream16(P.y + v);
+    bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw), yf);
+    uint32_t keep = P.drop_p > 0.0f ? keep_bits(P.drop_mask, P.seed, P.offset, v, P.drop_p) : 0xffu;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float z = fmaf(yf[i], sc[i], sh[i]);
+        float ga = ((keep >> i) & 1u) ? g[i] * keep_scale : 0.0f;
+        if (z > 0.0f) {
+            dz[i] = ga;
+        } else {
+            dz[i] = ga * slope;
+            dslope += z * ga;
+        }
+    }
+}
+
+// grid: (chunks of H*W, N*D*C8 planes) so a block stays inside one channel group
+template <bool APPLY>
+__global__ void __launch_bounds__(kThreads) dsbn_act_bwd_kernel(ActBwdParams P) {
+    const int64_t HW = (int64_t)P.H * P.W;
+    const int64_t plane = blockIdx.y;
+    const int c8 = (int)(plane % P.C8);
+    const int64_t nd = plane / P.C8;
+    const float slope = __ldg(P.slope);
+    const float keep_scale = P.drop_p > 0.0f ? 1.0f / (1.0f - P.drop_p) : 1.0f;
+    float sc[8], sh[8], mean[8], invstd[8];
+    load_affine(P.scale, P.shift, c8, sc, sh);
+    load_affine(P.mean, P.invstd, c8, mean, invstd);
+    float s1[8], s2[8], dsl = 0.0f;
+    float m1[8], m2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s1[i] = 0.0f; s2[i] = 0.0f; m1[i] = 0.0f; m2[i] = 0.0f; }
+    if (APPLY && P.training) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            m1[i] = (float)(P.red[c8 * 8 + i] * P.inv_count);
+            m2[i] = (float)(P.red[P.C8 * 8 + c8 * 8 + i] * P.inv_count);
+        }
+    }
+    for (int64_t hw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; hw < HW; hw += (int64_t)gridDim.x * blockDim.x) {
+        int h = (int)(hw / P.W), w = (int)(hw - (int64_t)h * P.W);
+        int64_t v = plane * HW + hw;
+        float yf[8], dz[8];
+        act_bwd_vec(P, v, nd, c8, h, w, sc, sh, slope, keep_scale, yf, dz, dsl);
+        if (!APPLY) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float xhat = (yf[i] - mean[i]) * invstd[i];
+                s1[i] += dz[i];
+                s2[i] = fmaf(dz[i], xhat, s2[i]);
+            }
+        } else {
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (P.training) {
+                    float xhat = (yf[i] - mean[i]) * invstd[i];
+                    o[i] = sc[i] * (dz[i] - m1[i] - xhat * m2[i]);
+                } else {
+                    o[i] = sc[i] * dz[i];
+                }
+            }
+            P.dy[v] = float_to_bf16x8(o);
+        }
+    }
+    if (!APPLY) {
+        __shared__ float sm[kThreads / 32][17];
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float a = warp_sum(s1[i]), b = warp_sum(s2[i]);
+            if (lane == 0) { sm[wid][i] = a; sm[wid][8 + i] = b; }
+        }
+        float c = warp_sum(dsl);
+        if (lane == 0) sm[wid][16] = c;
+        __syncthreads();
+        if (threadIdx.x < 17) {
+            float t = 0.0f;
+#pragma unroll
+            for (int k = 0; k < kThreads / 32; ++k) t += sm[k][threadIdx.x];
+            int i = threadIdx.x;
+            if (i < 8) atomicAdd(P.red + c8 * 8 + i, (double)t);
+            else if (i < 16) atomicAdd(P.red + P.C8 * 8 + c8 * 8 + (i - 8), (double)t);
+            else atomicAdd(P.red + 2 * P.C8 * 8, (double)t);
+        }
+    }
+}
+
+__global__ void dsbn_bwd_finalize_kernel(const double* __restrict__ red, const float* __restrict__ scale, int training,
+                                         float* dgamma, float* dbeta, float* dslope, float* dbias_conv,
+                                         const float* __restrict__ invstd, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) {
+        // dz is the gradient wrt the BN output: dbeta = sum dz, dgamma = sum dz*xhat
+        if (dbeta != nullptr) dbeta[c] += (float)red[c];
+        if (dgamma != nullptr) dgamma[c] += (float)red[C + c];
+        // the conv bias feeds straight into BN: in training mode its gradient is identically 0
+        // (sum_v dy = 0), in eval mode it is scale * sum dz
+        if (dbias_conv != nullptr && !training) dbias_conv[c] += scale[c] * (float)red[c];
+    }
+    if (c == 0 && dslope != nullptr) dslope[0] += (float)red[2 * C];
+}
+
+int grid_for(int64_t work_items, int per_thread) {
+    int64_t blocks = (work_items + (int64_t)kThreads * per_thread - 1) / ((int64_t)kThreads * per_thread);
+    int64_t cap = (int64_t)FPL_NUM_SMS * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace
+
+extern "C" int fpl_dsbn_finalize(const double* stats, int64_t count, const float* gamma, const float* beta,
+                                 float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                                 float momentum, float eps, int training, float* scale, float* shift,
+                                 float* save_mean, float* save_invstd, int c, void* stream) {
+    FPL_REQUIRE(c > 0 && c % 8 == 0, "fpl_dsbn_finalize: channels (%d) must be a positive multiple of 8", c);
+    FPL_REQUIRE(training ? (stats != nullptr && count > 0) : (running_mean != nullptr && running_var != nullptr),
+                "fpl_dsbn_finalize: missing statistics for training=%d", training);
+    double unbias = count > 1 ? (double)count / (double)(count - 1) : 1.0;
+    dsbn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        stats, 1.0 / (double)(count > 0 ? count : 1), unbias, gamma, beta, running_mean, running_var,
+        (long long*)num_batches_tracked, momentum, eps, training, scale, shift, save_mean, save_invstd, c);
+    FPL_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int fpl_dsbn_act_fwd(const void* y, const float* scale, const float* shift, const float* slope,
+                                void* a, int a_c8tot, int a_c8off, void* pooled, int p_c8tot, int p_c8off,
+                                uint8_t* pool_idx, int pool_kd, float drop_p, const uint8_t* drop_mask,
+                                uint64_t seed, uint64_t offset, int n, int d, int h, int w, int c, void* stream) {
+    FPL_REQUIRE(c > 0 && c % 8 == 0, "fpl_dsbn_act_fwd: channels (%d) must be a multiple of 8", c);
+    FPL_REQUIRE(drop_p >= 0.0f && drop_p < 1.0f, "fpl_dsbn_act_fwd: dropout p=%f out of [0,1)", drop_p);
+    ActParams P;
+    P.y = (const bf16x8*)y; P.scale = scale; P.shift = shift; P.slope = slope;
+    P.a = (bf16x8*)a; P.a_c8tot = a_c8tot; P.a_c8off = a_c8off;
+    P.pooled = (bf16x8*)pooled; P.p_c8tot = p_c8tot; P.p_c8off = p_c8off; P.pool_idx = (uint2*)pool_idx;
+    P.pool_kd = pool_kd; P.drop_p = drop_p; P.drop_mask = (const uint2*)drop_mask; P.seed = seed; P.offset = offset;
+    P.N = n; P.D = d; P.C8 = c / 8; P.H = h; P.W = w;
+    if (pooled != nullptr) {
+        FPL_REQUIRE(pool_kd == 1 || pool_kd == 2, "fpl_dsbn_act_fwd: pool_kd must be 1 or 2");
+        FPL_REQUIRE(h % 2 == 0 && w % 2 == 0 && d % pool_kd == 0, "fpl_dsbn_act_fwd: pooled dims must be even");
+        FPL_REQUIRE(drop_p == 0.0f, "fpl_dsbn_act_fwd: dropout is not combined with pooling");
+        FPL_REQUIRE(pool_idx != nullptr, "fpl_dsbn_act_fwd: pool_idx required");
+        int64_t total = (int64_t)n * (d / pool_kd) * (c / 8) * (h / 2) * (w / 2);
+        dsbn_act_pool_fwd_kernel<<<grid_for(total, 1), kThreads, 0, (cudaStream_t)stream>>>(P);
+    } else {
+        int64_t total = (int64_t)n * d * (c / 8) * h * w;
+        dsbn_act_fwd_kernel<<<grid_for(total, 4), kThreads, 0, (cudaStream_t)stream>>>(P);
+    }
+    FPL_LAUNCH_CHECK();
+    return 0;
+}
+
+static int fill_bwd(ActBwdParams& P, const void* y, const void* g1, int g1_c8tot, int g1_c8off, const void* g_pool,
+                    int gp_c8tot, int gp_c8off, const uint8_t* pool_idx, int pool_kd, const float* scale,
+                    const float* shift, const float* save_mean, const float* save_invstd, const float* slope,
+                    float drop_p, const uint8_t* drop_mask, uint64_t seed, uint64_t offset, int n, int d, int h,
+                    int w, int c) {
+    FPL_REQUIRE(c > 0 && c % 8 == 0, "dsbn bwd: channels (%d) must be a multiple of 8", c);
+    FPL_REQUIRE(g1 != nullptr || g_pool != nullptr, "dsbn bwd: no incoming gradient");
+    if (g_pool != nullptr) {
+        FPL_REQUIRE(pool_idx != nullptr && (pool_kd == 1 || pool_kd == 2), "dsbn bwd: pool_idx/pool_kd invalid");
+        FPL_REQUIRE(h % 2 == 0 && w % 2 == 0 && d % pool_kd == 0, "dsbn bwd: pooled dims must be even");
+    }
+    P.y = (const bf16x8*)y; P.g1 = (const bf16x8*)g1; P.g1_c8tot = g1_c8tot; P.g1_c8off = g1_c8off;
+    P.g_pool = (const bf16x8*)g_pool; P.gp_c8tot = gp_c8tot; P.gp_c8off = gp_c8off;
+    P.pool_idx = (const uint2*)pool_idx; P.pool_kd = pool_kd > 0 ? pool_kd : 2;
+    P.scale = scale; P.shift = shift; P.mean = save_mean; P.invstd = save_invstd; P.slope = slope;
+    P.drop_p = drop_p; P.drop_mask = (const uint2*)drop_mask; P.seed = seed; P.offset = offset;
+    P.red = nullptr; P.dy = nullptr; P.training = 1; P.inv_count = 1.0 / ((double)n * d * h * w);
+    P.N = n; P.D = d; P.C8 = c / 8; P.H = h; P.W = w;
+    return 0;
+}
+
+static dim3 bwd_grid(int n, int d, int h, int w, int c) {
+    int64_t hw = (int64_t)h * w;
+    int chunks = (int)((hw + kThreads * 4 - 1) / (kThreads * 4));
+    if (chunks < 1) chunks = 1;
+    return dim3(chunks, n * d * (c / 8));
+}
+
+extern "C" int fpl_dsbn_act_bwd_reduce(const void* y, const void* g1, int g1_c8tot, int g1_c8off, const void* g_pool,
+                                       int gp_c8tot, int gp_c8off, const uint8_t* pool_idx, int pool_kd,
+                                       const float* scale, const float* shift, const float* save_mean,
+                                       const float* save_invstd, const float* slope, float drop_p,
+                                       const uint8_t* drop_mask, uint64_t seed, uint64_t offset, double* red, int n,
+                                       int d, int h, int w, int c, void* stream) {
+    ActBwdParams P;
+    int rc = fill_bwd(P, y, g1, g1_c8tot, g1_c8off, g_pool, gp_c8tot, gp_c8off, pool_idx, pool_kd, scale, shift,
+                      save_mean, save_invstd, slope, drop_p, drop_mask, seed, offset, n, d, h, w, c);
+    if (rc) return rc;
+    FPL_REQUIRE((int64_t)n * d * (c / 8) <= 65535, "dsbn bwd: too many planes (%lld)", (long long)n * d * (c / 8));
+    P.red = red;
+    dsbn_act_bwd_kernel<false><<<bwd_grid(n, d, h, w, c), kThreads, 0, (cudaStream_t)stream>>>(P);
+    FPL_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int fpl_dsbn_act_bwd_apply(const void* y, const void* g1, int g1_c8tot, int g1_c8off, const void* g_pool,
+                                      int gp_c8tot, int gp_c8off, const uint8_t* pool_idx, int pool_kd,
+                                      const float* scale, const float* shift, const float* save_mean,
+                                      const float* save_invstd, const float* slope, float drop_p,
+                                      const uint8_t* drop_mask, uint64_t seed, uint64_t offset, const double* red,
+                                      int training, void* dy, int n, int d, int h, int w, int c, void* stream) {
+    ActBwdParams P;
+    int rc = fill_bwd(P, y, g1, g1_c8tot, g1_c8off, g_pool, gp_c8tot, gp_c8off, pool_idx, pool_kd, scale, shift,
+                      save_mean, save_invstd, slope, drop_p, drop_mask, seed, offset, n, d, h, w, c);
+    if (rc) return rc;
+    FPL_REQUIRE((int64_t)n * d * (c / 8) <= 65535, "dsbn bwd: too many planes (%lld)", (long long)n * d * (c / 8));
+    P.red = const_cast<double*>(red);
+    P.dy = (bf16x8*)dy;
+    P.training = training;
+    dsbn_act_bwd_kernel<true><<<bwd_grid(n, d, h, w, c), kThreads, 0, (cudaStream_t)stream>>>(P);
+    FPL_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int fpl_dsbn_bwd_finalize(const double* red, const float* scale, const float* save_invstd, int training,
+                                     float* dgamma, float* dbeta, float* dslope, float* dbias_conv, int c,
+                                     void* stream) {
+    dsbn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(red, scale, training, dgamma, dbeta,
+                                                                                dslope, dbias_conv, save_invstd, c);
+    FPL_LAUNCH_CHECK();
+    return 0;
+}

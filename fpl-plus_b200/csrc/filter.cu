@@ -1,0 +1,263 @@
+// Pseudo-label filter and sliding-window stitching kernels (HBM streaming, fp32 NCDHW logits).
+//   argmax labels        : net_run_dsbn/agent_seg.py:1049-1050
+//   MC-dropout statistics: agent_seg.py:911-929
+//   agreement weight     : data/get_pixel_weight.py:21-26 (+ io/nifty_dataset.py:165-168 folding)
+//   window accumulate    : net_run_dsbn/infer_func.py:96-112, 202-219
+#include "common.cuh"
+#include "../../include/fplplus_b200.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxK = 8;
+
+int grid_for(int64_t items) {
+    int64_t blocks = (items + kThreads - 1) / kThreads;
+    int64_t cap = (int64_t)FPL_NUM_SMS * 8;
+    if (blocks > cap) blocks = cap;
+    return (int)(blocks < 1 ? 1 : blocks);
+}
+
+template <int C>
+__device__ __forceinline__ int argmax_c(const float* z) {
+    int am = 0;
+    float best = z[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c)
+        if (z[c] > best) { best = z[c]; am = c; }
+    return am;
+}
+
+template <int C>
+__global__ void __launch_bounds__(kThreads) argmax_label_kernel(const float* __restrict__ logits, uint8_t* label, int B,
+                                                               int64_t S4) {
+    const int64_t total = (int64_t)B * S4;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        int64_t b = g / S4, s4 = g - b * S4;
+        float4 zv[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) zv[c] = ld_stream_f4(reinterpret_cast<const float4*>(logits) + (b * C + c) * S4 + s4);
+        uint32_t packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float z[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) z[c] = reinterpret_cast<const float*>(&zv[c])[j];
+            packed |= (uint32_t)argmax_c<C>(z) << (8 * j);
+        }
+        reinterpret_cast<uint32_t*>(label)[g] = packed;
+    }
+}
+
+struct PassPtrs {
+    const float* p[kMaxK];
+};
+
+// out[0] += sum over classes and voxels of the population variance across the K passes of the
+// softmax probabilities; out[1] += #voxels with -m*ln(m+1e-6) > 0.01, m = mean class-1 probability.
+template <int C>
+__global__ void __launch_bounds__(kThreads) mc_uncertainty_kernel(PassPtrs ptrs, int K, int64_t S4, double* out,
+                                                                 float* umap) {
+    float var_acc = 0.0f;
+    unsigned int cnt = 0;
+    const float invK = 1.0f / (float)K;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < S4; g += (int64_t)gridDim.x * blockDim.x) {
+        float prob[kMaxK][C][4];
+#pragma unroll
+        for (int k = 0; k < kMaxK; ++k) {
+            if (k < K) {
+                float4 zv[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) zv[c] = ld_stream_f4(reinterpret_cast<const float4*>(ptrs.p[k]) + c * S4 + g);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float m = reinterpret_cast<const float*>(&zv[0])[j];
+#pragma unroll
+                    for (int c = 1; c < C; ++c) m = fmaxf(m, reinterpret_cast<const float*>(&zv[c])[j]);
+                    float s = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        float e = expf(reinterpret_cast<const float*>(&zv[c])[j] - m);
+                        prob[k][c][j] = e;
+                        s += e;
+                    }
+#pragma unroll
+                    for (int c = 0; c < C; ++c) prob[k][c][j] = prob[k][c][j] / s;
+                }
+            }
+        }
+        float4 uo;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float mean1 = 0.0f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float mean = 0.0f;
+#pragma unroll
+                for (int k = 0; k < kMaxK; ++k)
+                    if (k < K) mean += prob[k][c][j];
+                mean *= invK;
+                float m2 = 0.0f;
+#pragma unroll
+                for (int k = 0; k < kMaxK; ++k)
+                    if (k < K) { float dlt = prob[k][c][j] - mean; m2 = fmaf(dlt, dlt, m2); }
+                var_acc += m2 * invK;
+                if (c == 1) mean1 = mean;
+            }
+            float u = -1.0f * (mean1 * logf(mean1 + 1e-6f));
+            cnt += (u > 0.01f) ? 1u : 0u;
+            reinterpret_cast<float*>(&uo)[j] = u;
+        }
+        if (umap != nullptr) reinterpret_cast<float4*>(umap)[g] = uo;
+    }
+    __shared__ float sv[kThreads / 32];
+    __shared__ unsigned int sc[kThreads / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float v = warp_sum(var_acc);
+    unsigned int c = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) { sv[wid] = v; sc[wid] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tv = 0.0, tc = 0.0;
+        for (int k = 0; k < kThreads / 32; ++k) { tv += (double)sv[k]; tc += (double)sc[k]; }
+        atomicAdd(out, tv);
+        atomicAdd(out + 1, tc);
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kThreads) agree_weight_kernel(const float* __restrict__ lt, const float* __restrict__ ls,
+                                                               uint8_t* lab_t, uint8_t* lab_s, float* weight, int fold,
+                                                               float image_weight, unsigned long long* out_count,
+                                                               int64_t S4) {
+    unsigned int diff = 0;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < S4; g += (int64_t)gridDim.x * blockDim.x) {
+        float4 a[C], b[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            a[c] = ld_stream_f4(reinterpret_cast<const float4*>(lt) + c * S4 + g);
+            b[c] = ld_stream_f4(reinterpret_cast<const float4*>(ls) + c * S4 + g);
+        }
+        uint32_t pa = 0, pb = 0;
+        float4 wv;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float za[C], zb[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                za[c] = reinterpret_cast<const float*>(&a[c])[j];
+                zb[c] = reinterpret_cast<const float*>(&b[c])[j];
+            }
+            int la = argmax_c<C>(za), lb = argmax_c<C>(zb);
+            pa |= (uint32_t)la << (8 * j);
+            pb |= (uint32_t)lb << (8 * j);
+            float w = (la == lb) ? 1.0f : 0.5f;
+            diff += (la != lb) ? 1u : 0u;
+            if (fold) w = (w < 1.0f ? 0.0f : w) * image_weight;
+            reinterpret_cast<float*>(&wv)[j] = w;
+        }
+        if (lab_t != nullptr) reinterpret_cast<uint32_t*>(lab_t)[g] = pa;
+        if (lab_s != nullptr) reinterpret_cast<uint32_t*>(lab_s)[g] = pb;
+        if (weight != nullptr) reinterpret_cast<float4*>(weight)[g] = wv;
+    }
+    if (out_count != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) diff += __shfl_xor_sync(0xffffffffu, diff, o);
+        if ((threadIdx.x & 31) == 0 && diff) atomicAdd(out_count, (unsigned long long)diff);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) window_accumulate_kernel(const float* __restrict__ patch, float* out,
+                                                                    float* count, int BC, int vd, int vh, int vw, int d0,
+                                                                    int h0, int w0, int pd, int ph, int pw, int flip_h,
+                                                                    int flip_w, float scale) {
+    const int64_t total = (int64_t)BC * pd * ph * pw;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int k = (int)(i % pw);
+        int64_t t = i / pw;
+        int j = (int)(t % ph); t /= ph;
+        int ii = (int)(t % pd);
+        int64_t bc = t / pd;
+        int jj = flip_h ? ph - 1 - j : j;
+        int kk = flip_w ? pw - 1 - k : k;
+        int64_t o = ((bc * vd + d0 + ii) * vh + h0 + jj) * (int64_t)vw + w0 + kk;
+        out[o] += scale * __ldg(patch + i);
+        if (count != nullptr) count[o] += 1.0f;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) window_normalize_kernel(float* out, const float* __restrict__ count,
+                                                                   float scale, int64_t numel) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = out[i];
+        if (count != nullptr) v = v / count[i];
+        out[i] = v * scale;
+    }
+}
+
+}  // namespace
+
+#define FPL_DISPATCH_C(C_, ...)                                                     \
+    switch (C_) {                                                                   \
+        case 2: { constexpr int CC = 2; __VA_ARGS__; } break;                       \
+        case 3: { constexpr int CC = 3; __VA_ARGS__; } break;                       \
+        case 4: { constexpr int CC = 4; __VA_ARGS__; } break;                       \
+        case 5: { constexpr int CC = 5; __VA_ARGS__; } break;                       \
+        case 6: { constexpr int CC = 6; __VA_ARGS__; } break;                       \
+        case 7: { constexpr int CC = 7; __VA_ARGS__; } break;                       \
+        case 8: { constexpr int CC = 8; __VA_ARGS__; } break;                       \
+        default: fpl_set_error("class_num %d not in [2,8]", C_); return 2;          \
+    }
+
+extern "C" int fpl_argmax_label(const float* logits, uint8_t* label, int b, int c, int64_t spatial, void* stream) {
+    FPL_REQUIRE(spatial % 4 == 0, "fpl_argmax_label: spatial size %lld must be a multiple of 4", (long long)spatial);
+    int64_t s4 = spatial / 4;
+    FPL_DISPATCH_C(c, (argmax_label_kernel<CC><<<grid_for((int64_t)b * s4), kThreads, 0, (cudaStream_t)stream>>>(logits, label, b, s4)));
+    FPL_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int fpl_mc_uncertainty(const float* const* h_logits_k, int k, int c, int64_t spatial, double* out,
+                                  float* uncertainty_map, void* stream) {
+    FPL_REQUIRE(k >= 1 && k <= kMaxK, "fpl_mc_uncertainty: K=%d passes not in [1,%d]", k, kMaxK);
+    FPL_REQUIRE(spatial % 4 == 0, "fpl_mc_uncertainty: spatial size %lld must be a multiple of 4", (long long)spatial);
+    PassPtrs ptrs;
+    for (int i = 0; i < kMaxK; ++i) ptrs.p[i] = i < k ? h_logits_k[i] : nullptr;
+    int64_t s4 = spatial / 4;
+    FPL_DISPATCH_C(c, (mc_uncertainty_kernel<CC><<<grid_for(s4), kThreads, 0, (cudaStream_t)stream>>>(ptrs, k, s4, out, uncertainty_map)));
+    FPL_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int fpl_agree_weight(const float* logits_tgt, const float* logits_src, uint8_t* label_tgt,
+                                uint8_t* label_src, float* weight, int fold_image_weight, float image_weight,
+                                long long* out_count, int c, int64_t spatial, void* stream) {
+    FPL_REQUIRE(spatial % 4 == 0, "fpl_agree_weight: spatial size %lld must be a multiple of 4", (long long)spatial);
+    int64_t s4 = spatial / 4;
+    FPL_DISPATCH_C(c, (agree_weight_kernel<CC><<<grid_for(s4), kThreads, 0, (cudaStream_t)stream>>>(
+                          logits_tgt, logits_src, label_tgt, label_src, weight, fold_image_weight, image_weight,
+                          (unsigned long long*)out_count, s4)));
+    FPL_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int fpl_window_accumulate(const float* patch, float* out, float* count, int b, int c, int vd, int vh,
+                                     int vw, int d0, int h0, int w0, int pd, int ph, int pw, int flip_h, int flip_w,
+                                     float scale, void* stream) {
+    FPL_REQUIRE(d0 >= 0 && h0 >= 0 && w0 >= 0 && d0 + pd <= vd && h0 + ph <= vh && w0 + pw <= vw,
+                "fpl_window_accumulate: window [%d+%d,%d+%d,%d+%d] outside volume [%d,%d,%d]", d0, pd, h0, ph, w0, pw,
+                vd, vh, vw);
+    int64_t total = (int64_t)b * c * pd * ph * pw;
+    window_accumulate_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(
+        patch, out, count, b * c, vd, vh, vw, d0, h0, w0, pd, ph, pw, flip_h, flip_w, scale);
+    FPL_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int fpl_window_normalize(float* out, const float* count, float scale, int64_t numel, void* stream) {
+    window_normalize_kernel<<<grid_for(numel), kThreads, 0, (cudaStream_t)stream>>>(out, count, scale, numel);
+    FPL_LAUNCH_CHECK();
+    return 0;
+}

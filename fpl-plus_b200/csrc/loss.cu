@@ -1,0 +1,207 @@
+// Fused pixel/image-weighted Dice + cross-entropy: reduction pass and gradient pass.
+// Replaces DiceLoss (PyMIC/pymic/loss/seg/dice.py:20-57), get_classwise_dice
+// (loss/seg/util.py:85-107), CrossEntropyLoss (loss/seg/ce.py:23-44), CombinedLoss
+// (loss/seg/combined.py:34-39) and the training-time hard-Dice metric
+// (net_run_dsbn/agent_seg.py:472-476).  Pure HBM streaming over NCDHW fp32 (the layout the
+// PyMIC loss API hands over): 8C+4 bytes/voxel in the reduce pass, 12C+4 in the grad pass.
+#include "common.cuh"
+#include "../../include/fplplus_b200.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <int C>
+__device__ __forceinline__ void softmax_c(const float* z, float* p) {
+    float m = z[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c) m = fmaxf(m, z[c]);
+    float s = 0.0f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { p[c] = expf(z[c] - m); s += p[c]; }
+    float inv = 1.0f / s;
+#pragma unroll
+    for (int c = 0; c < C; ++c) p[c] *= inv;
+}
+
+// sums layout (double): I[C], Y[C], P[C], sum_w, sum_w_ce, HI[C], HY[C], HP[C]
+template <int C>
+__global__ void __launch_bounds__(kThreads) dice_ce_reduce_kernel(const float* __restrict__ logits,
+                                                                 const float* __restrict__ soft_y,
+                                                                 const float* __restrict__ weight, double* sums,
+                                                                 int N, int64_t S4) {
+    constexpr int NV = 6 * C + 2;
+    float acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.0f;
+    const int64_t total = (int64_t)N * S4;   // float4 groups
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        int64_t n = g / S4, s4 = g - n * S4;
+        float4 zv[C], yv[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            zv[c] = ld_stream_f4(reinterpret_cast<const float4*>(logits) + (n * C + c) * S4 + s4);
+            yv[c] = ld_stream_f4(reinterpret_cast<const float4*>(soft_y) + (n * C + c) * S4 + s4);
+        }
+        float4 wv = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (weight != nullptr) wv = ld_stream_f4(reinterpret_cast<const float4*>(weight) + n * S4 + s4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float z[C], y[C], p[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                z[c] = reinterpret_cast<const float*>(&zv[c])[j];
+                y[c] = reinterpret_cast<const float*>(&yv[c])[j];
+            }
+            float w = reinterpret_cast<const float*>(&wv)[j];
+            softmax_c<C>(z, p);
+            int am = 0;
+            float best = z[0];
+            float ce = 0.0f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                if (c > 0 && z[c] > best) { best = z[c]; am = c; }
+                acc[c] = fmaf(w * y[c], p[c], acc[c]);
+                acc[C + c] = fmaf(w, y[c], acc[C + c]);
+                acc[2 * C + c] = fmaf(w, p[c], acc[2 * C + c]);
+                ce -= y[c] * logf(p[c] * 0.999f + 5e-4f);
+                acc[3 * C + 2 + C + c] += y[c];
+            }
+            acc[3 * C] += w;
+            acc[3 * C + 1] = fmaf(w, ce, acc[3 * C + 1]);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                if (c == am) {
+                    acc[3 * C + 2 + c] += y[c];
+                    acc[3 * C + 2 + 2 * C + c] += 1.0f;
+                }
+            }
+        }
+    }
+    __shared__ float sm[kThreads / 32][NV];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float t = warp_sum(acc[i]);
+        if (lane == 0) sm[wid][i] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < kThreads / 32; ++k) t += (double)sm[k][threadIdx.x];
+        atomicAdd(sums + threadIdx.x, t);
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kThreads) dice_ce_grad_kernel(const float* __restrict__ logits,
+                                                               const float* __restrict__ soft_y,
+                                                               const float* __restrict__ weight,
+                                                               const double* __restrict__ sums, float w_dice,
+                                                               float w_ce, float grad_scale,
+                                                               const float* __restrict__ grad_scale_dev, float* loss,
+                                                               float* dlogits, int N, int64_t S4) {
+    if (grad_scale_dev != nullptr) grad_scale *= __ldg(grad_scale_dev);
+    // per-class constants of dDice/dp:  g_c = -(1/C) * w * (2*y*den - num) / den^2
+    float a_c[C], b_c[C];
+    double dice_mean = 0.0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        double I = sums[c], Y = sums[C + c], Pp = sums[2 * C + c];
+        double den = Y + Pp + 1e-5, num = 2.0 * I + 1e-5;
+        dice_mean += num / den;
+        a_c[c] = (float)(-(double)w_dice * 2.0 / (C * den));          // * w * y
+        b_c[c] = (float)((double)w_dice * num / (C * den * den));     // * w
+    }
+    dice_mean /= C;
+    const double sum_w = sums[3 * C], sum_wce = sums[3 * C + 1];
+    const double V = (double)N * (double)S4 * 4.0;
+    const double ce_den = weight != nullptr ? sum_w + 1e-5 : V;
+    if (loss != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+        double l = 0.0;
+        if (w_dice != 0.0f) l += (double)w_dice * (1.0 - dice_mean);
+        if (w_ce != 0.0f) l += (double)w_ce * (sum_wce / ce_den);
+        loss[0] = (float)l;
+    }
+    if (dlogits == nullptr) return;
+    const float ce_k = (float)(-(double)w_ce * 0.999 / ce_den);
+    const int64_t total = (int64_t)N * S4;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        int64_t n = g / S4, s4 = g - n * S4;
+        float4 zv[C], yv[C], ov[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            zv[c] = ld_stream_f4(reinterpret_cast<const float4*>(logits) + (n * C + c) * S4 + s4);
+            yv[c] = ld_stream_f4(reinterpret_cast<const float4*>(soft_y) + (n * C + c) * S4 + s4);
+        }
+        float4 wv = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (weight != nullptr) wv = ld_stream_f4(reinterpret_cast<const float4*>(weight) + n * S4 + s4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float z[C], y[C], p[C], gp[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                z[c] = reinterpret_cast<const float*>(&zv[c])[j];
+                y[c] = reinterpret_cast<const float*>(&yv[c])[j];
+            }
+            float w = reinterpret_cast<const float*>(&wv)[j];
+            softmax_c<C>(z, p);
+            float dot = 0.0f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float gc = w * fmaf(a_c[c], y[c], b_c[c]);
+                if (w_ce != 0.0f) gc += ce_k * w * y[c] / (p[c] * 0.999f + 5e-4f);
+                gp[c] = gc;
+                dot = fmaf(gc, p[c], dot);
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) reinterpret_cast<float*>(&ov[c])[j] = grad_scale * p[c] * (gp[c] - dot);
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) reinterpret_cast<float4*>(dlogits)[(n * C + c) * S4 + s4] = ov[c];
+    }
+}
+
+int grid_for(int64_t groups) {
+    int64_t blocks = (groups + kThreads - 1) / kThreads;
+    int64_t cap = (int64_t)FPL_NUM_SMS * 8;
+    if (blocks > cap) blocks = cap;
+    return (int)(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace
+
+#define FPL_DISPATCH_C(C_, ...)                                                     \
+    switch (C_) {                                                                   \
+        case 2: { constexpr int CC = 2; __VA_ARGS__; } break;                       \
+        case 3: { constexpr int CC = 3; __VA_ARGS__; } break;                       \
+        case 4: { constexpr int CC = 4; __VA_ARGS__; } break;                       \
+        case 5: { constexpr int CC = 5; __VA_ARGS__; } break;                       \
+        case 6: { constexpr int CC = 6; __VA_ARGS__; } break;                       \
+        case 7: { constexpr int CC = 7; __VA_ARGS__; } break;                       \
+        case 8: { constexpr int CC = 8; __VA_ARGS__; } break;                       \
+        default: fpl_set_error("class_num %d not in [2,8]", C_); return 2;          \
+    }
+
+extern "C" int fpl_dice_ce_reduce(const float* logits, const float* soft_y, const float* weight, double* sums, int n,
+                                  int c, int64_t spatial, void* stream) {
+    FPL_REQUIRE(spatial % 4 == 0, "fpl_dice_ce_reduce: spatial size %lld must be a multiple of 4", (long long)spatial);
+    int64_t s4 = spatial / 4;
+    FPL_DISPATCH_C(c, (dice_ce_reduce_kernel<CC><<<grid_for((int64_t)n * s4), kThreads, 0, (cudaStream_t)stream>>>(
+                          logits, soft_y, weight, sums, n, s4)));
+    FPL_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int fpl_dice_ce_grad(const float* logits, const float* soft_y, const float* weight, const double* sums,
+                                float w_dice, float w_ce, float grad_scale, const float* grad_scale_dev, float* loss,
+                                float* dlogits, int n, int c, int64_t spatial, void* stream) {
+    FPL_REQUIRE(spatial % 4 == 0, "fpl_dice_ce_grad: spatial size %lld must be a multiple of 4", (long long)spatial);
+    int64_t s4 = spatial / 4;
+    int grid = dlogits != nullptr ? grid_for((int64_t)n * s4) : 1;
+    FPL_DISPATCH_C(c, (dice_ce_grad_kernel<CC><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+                          logits, soft_y, weight, sums, w_dice, w_ce, grad_scale, grad_scale_dev, loss, dlogits, n, s4)));
+    FPL_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,104 @@
+"""Drop-in ``Inferer`` (reference: PyMIC/pymic/net_run_dsbn/infer_func.py:6-222): sliding-window
+inference with overlap averaging and 4-flip test-time augmentation, same config keys
+(``sliding_window_enable/size/stride``, ``tta_mode``, ``class_num``) and the same
+``run(model, image, domain_label)`` call.
+
+B200 re-design: all windows of a pass are stacked into ONE batched network call (exact for a
+network in eval mode, where BatchNorm uses running statistics), window results are scattered
+into the volume by a fused accumulate kernel and normalised by the visit count on the device;
+the un-flip of TTA passes is folded into the accumulate kernel.  The reference's probe forward
+on a ones tensor (infer_func.py:92-93) is not issued: it only counts outputs.
+"""
+import torch
+
+from .ops import call, ptr, stream_ptr
+
+
+def _bn_in_eval(model):
+    for m in model.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm) and m.training:
+            return False
+    return True
+
+
+class Inferer(object):
+    def __init__(self, config):
+        self.config = config
+        self.max_batch = config.get('window_batch', 8)
+
+    # window enumeration: infer_func.py:55-85 (w outer, h, d inner; last window clamped)
+    def _windows(self, img_shape):
+        win = [x for x in self.config['sliding_window_size']]
+        stride = [x for x in self.config['sliding_window_stride']]
+        if len(img_shape) != 3:
+            raise ValueError("Inference using sliding window only supports 3D images here")
+        for d in range(3):
+            if win[d] is None or win[d] > img_shape[d]:
+                win[d] = img_shape[d]
+            if stride[d] is None or stride[d] > win[d]:
+                stride[d] = win[d]
+        if all(win[d] >= img_shape[d] for d in range(3)):
+            return None, win
+        starts = []
+        for w in range(0, img_shape[2], stride[2]):
+            w0 = min(w, img_shape[2] - win[2])
+            for h in range(0, img_shape[1], stride[1]):
+                h0 = min(h, img_shape[1] - win[1])
+                for d in range(0, img_shape[0], stride[0]):
+                    starts.append((min(d, img_shape[0] - win[0]), h0, w0))
+        return starts, win
+
+    def _model(self, x, domain_label):
+        out = self.model(x, domain_label=domain_label)
+        if isinstance(out, (tuple, list)):
+            out = out[0]
+        return out
+
+    def _infer(self, image, domain_label, result, scale, flip_h, flip_w):
+        """result += scale * unflip(sliding_window(model, image))."""
+        b, _cin, vd, vh, vw = image.shape
+        class_num = self.config['class_num']
+        st = stream_ptr()
+        starts = None
+        if self.config.get('sliding_window_enable', False):
+            starts, win = self._windows([vd, vh, vw])
+        if starts is None:
+            out = self._model(image, domain_label).float().contiguous()
+            call("fpl_window_accumulate", ptr(out), ptr(result), None, b, out.shape[1], vd, vh, vw, 0, 0, 0,
+                 vd, vh, vw, flip_h, flip_w, scale, st)
+            return
+        acc = torch.zeros((b, class_num, vd, vh, vw), dtype=torch.float32, device=image.device)
+        cnt = torch.zeros_like(acc)
+        batched = _bn_in_eval(self.model)
+        group = max(1, self.max_batch // b) if batched else 1
+        for g0 in range(0, len(starts), group):
+            chunk = starts[g0:g0 + group]
+            patches = [image[:, :, d0:d0 + win[0], h0:h0 + win[1], w0:w0 + win[2]] for d0, h0, w0 in chunk]
+            x = torch.cat(patches, 0).contiguous() if len(patches) > 1 else patches[0].contiguous()
+            dl = domain_label if len(chunk) == 1 else domain_label.repeat(len(chunk))
+            out = self._model(x, dl).float().contiguous()
+            for j, (d0, h0, w0) in enumerate(chunk):
+                call("fpl_window_accumulate", ptr(out[j * b:(j + 1) * b]), ptr(acc), ptr(cnt), b, class_num, vd, vh, vw,
+                     d0, h0, w0, win[0], win[1], win[2], 0, 0, 1.0, st)
+        call("fpl_window_normalize", ptr(acc), ptr(cnt), 1.0, acc.numel(), st)
+        call("fpl_window_accumulate", ptr(acc), ptr(result), None, b, class_num, vd, vh, vw, 0, 0, 0, vd, vh, vw,
+             flip_h, flip_w, scale, st)
+
+    def run(self, model, image, domain_label):
+        """Logits [B,class_num,D,H,W] on ``image.device`` (infer_func.py:188-222)."""
+        self.model = model
+        tta_mode = self.config.get('tta_mode', 0)
+        if tta_mode not in (0, 1):
+            raise ValueError("Undefined tta_mode {0:}".format(tta_mode))
+        image = image.float()
+        b, _c, vd, vh, vw = image.shape
+        class_num = self.config['class_num']
+        result = torch.zeros((b, class_num, vd, vh, vw), dtype=torch.float32, device=image.device)
+        if tta_mode == 0:
+            self._infer(image, domain_label, result, 1.0, 0, 0)
+        else:
+            self._infer(image, domain_label, result, 0.25, 0, 0)
+            self._infer(torch.flip(image, [-2]), domain_label, result, 0.25, 1, 0)
+            self._infer(torch.flip(image, [-1]), domain_label, result, 0.25, 0, 1)
+            self._infer(torch.flip(image, [-2, -1]), domain_label, result, 0.25, 1, 1)
+        return result

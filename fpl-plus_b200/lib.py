@@ -1,0 +1,78 @@
+"""ctypes binding of libfplplus_b200.so (the C ABI declared in include/fplplus_b200.h).
+
+There is deliberately no fallback: if the library is missing it is built with nvcc, and if
+that is impossible the import fails loudly.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_longlong, c_uint64, c_void_p
+
+from . import build as _build
+
+_P = c_void_p
+_I = c_int
+_L = c_int64
+_F = c_float
+_U = c_uint64
+
+_SIGNATURES = {
+    "fpl_last_error": (c_char_p, []),
+    "fpl_version": (_I, []),
+    "fpl_device_is_sm100": (_I, []),
+    "fpl_debug_set": (None, [_I, _I]),
+    "fpl_conv3d_weight_image_bytes": (_L, [_I, _I, _I]),
+    "fpl_conv3d_prep_weight": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "fpl_conv3d_tc": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _P] + [_I] * 7 + [_P]),
+    "fpl_conv3d_direct": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _P] + [_I] * 9 + [_P]),
+    "fpl_conv3d_wgrad": (_I, [_P, _I, _I, _P, _I, _I, _P] + [_I] * 7 + [_P]),
+    "fpl_stem_conv_fwd": (_I, [_P, _P, _P, _P, _I, _I, _P] + [_I] * 7 + [_P]),
+    "fpl_stem_conv_wgrad": (_I, [_P, _P, _I, _I, _P] + [_I] * 7 + [_P]),
+    "fpl_head_conv_fwd": (_I, [_P, _I, _I, _P, _P, _P] + [_I] * 6 + [_P]),
+    "fpl_head_conv_bwd": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _P, _P] + [_I] * 6 + [_P]),
+    "fpl_convt_k2s2_fwd": (_I, [_P, _I, _I, _P, _P, _P, _I, _I] + [_I] * 7 + [_P]),
+    "fpl_convt_k2s2_bwd": (_I, [_P, _I, _I, _P, _P, _I, _I, _P, _I, _I, _P, _P] + [_I] * 7 + [_P]),
+    "fpl_dsbn_finalize": (_I, [_P, _L, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _I, _P]),
+    "fpl_dsbn_act_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _F, _P, _U, _U] + [_I] * 5 + [_P]),
+    "fpl_dsbn_act_bwd_reduce": (_I, [_P, _P, _I, _I, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _F, _P, _U, _U, _P]
+                                + [_I] * 5 + [_P]),
+    "fpl_dsbn_act_bwd_apply": (_I, [_P, _P, _I, _I, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _F, _P, _U, _U, _P, _I, _P]
+                               + [_I] * 5 + [_P]),
+    "fpl_dsbn_bwd_finalize": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _I, _P]),
+    "fpl_dice_ce_reduce": (_I, [_P, _P, _P, _P, _I, _I, _L, _P]),
+    "fpl_dice_ce_grad": (_I, [_P, _P, _P, _P, _F, _F, _F, _P, _P, _P, _I, _I, _L, _P]),
+    "fpl_argmax_label": (_I, [_P, _P, _I, _I, _L, _P]),
+    "fpl_mc_uncertainty": (_I, [ctypes.POINTER(c_void_p), _I, _I, _L, _P, _P, _P]),
+    "fpl_agree_weight": (_I, [_P, _P, _P, _P, _P, _I, _F, _P, _I, _L, _P]),
+    "fpl_window_accumulate": (_I, [_P, _P, _P] + [_I] * 13 + [_F, _P]),
+    "fpl_window_normalize": (_I, [_P, _P, _F, _L, _P]),
+}
+
+#: every symbol include/fplplus_b200.h declares (tests check the .so exports them all)
+EXPORTED = [k for k in _SIGNATURES if k != "fpl_debug_set"]
+
+_lib = None
+
+
+class FplError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is None:
+        path = _build.build()
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def call(name, *args):
+    """Invoke a C-ABI function; a non-zero status raises FplError with the library's message."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise FplError("%s failed (%d): %s" % (name, rc, lib.fpl_last_error().decode()))

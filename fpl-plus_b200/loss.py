@@ -1,0 +1,135 @@
+"""Drop-in ``loss_dict`` entries: pixel/image-weighted Dice, cross entropy and their weighted sum,
+computed by one fused reduction kernel + one gradient kernel (csrc/loss.cu).
+
+API mirrors PyMIC (PyMIC/pymic/loss/seg/abstract.py:16-21, dice.py:20-57, ce.py:23-44,
+combined.py:21-39): ``cls(params)`` reads ``loss_softmax`` (default True); ``forward(dict)`` takes
+``prediction`` (tensor or list/tuple -> [0]), ``ground_truth`` [N,C,D,H,W] float one-hot/soft,
+optional ``pixel_weight`` [N,1,D,H,W]; ``image_weight`` is accepted and ignored exactly as the
+reference's DiceLoss/CrossEntropyLoss ignore it (image weights enter through
+NiftyDataset.set_weight_, io/nifty_dataset.py:165-168).  Returns a 0-dim tensor attached to autograd.
+"""
+import torch
+import torch.nn as nn
+
+from .ops import call, ptr, stream_ptr
+
+
+def _prep(loss_input_dict):
+    predict = loss_input_dict['prediction']
+    soft_y = loss_input_dict['ground_truth']
+    pix_w = loss_input_dict.get('pixel_weight', None)
+    if isinstance(predict, (list, tuple)):
+        predict = predict[0]
+    if not predict.is_cuda:
+        raise RuntimeError("fplplus_b200 losses run on CUDA only")
+    if predict.dim() != 5:
+        raise ValueError("{0:}D tensor not supported".format(predict.dim()))
+    soft_y = soft_y.to(device=predict.device, dtype=torch.float32).contiguous()
+    if soft_y.shape != predict.shape:
+        raise ValueError("prediction %s and ground_truth %s differ in shape" % (tuple(predict.shape), tuple(soft_y.shape)))
+    if pix_w is not None:
+        pix_w = pix_w.to(device=predict.device, dtype=torch.float32).contiguous()
+        if pix_w.numel() != predict.numel() // predict.shape[1]:
+            raise ValueError("pixel_weight must be [N,1,D,H,W]")
+    return predict, soft_y, pix_w
+
+
+def n_sums(c):
+    return 6 * c + 2
+
+
+class _DiceCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, soft_y, weight, w_dice, w_ce, holder):
+        logits = logits.float().contiguous()
+        n, c = logits.shape[:2]
+        spatial = logits.numel() // (n * c)
+        sums = torch.zeros(n_sums(c), dtype=torch.float64, device=logits.device)
+        st = stream_ptr()
+        call("fpl_dice_ce_reduce", ptr(logits), ptr(soft_y), ptr(weight), ptr(sums), n, c, spatial, st)
+        loss = torch.empty((), dtype=torch.float32, device=logits.device)
+        call("fpl_dice_ce_grad", ptr(logits), ptr(soft_y), ptr(weight), ptr(sums), w_dice, w_ce, 1.0, None, ptr(loss),
+             None, n, c, spatial, st)
+        ctx.save_for_backward(logits, soft_y, sums) if weight is None else ctx.save_for_backward(logits, soft_y, sums, weight)
+        ctx.w = (w_dice, w_ce)
+        if holder is not None:
+            holder["sums"] = sums
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        saved = ctx.saved_tensors
+        logits, soft_y, sums = saved[:3]
+        weight = saved[3] if len(saved) > 3 else None
+        n, c = logits.shape[:2]
+        spatial = logits.numel() // (n * c)
+        dlogits = torch.empty_like(logits)
+        g = grad_out.float().contiguous()
+        call("fpl_dice_ce_grad", ptr(logits), ptr(soft_y), ptr(weight), ptr(sums), ctx.w[0], ctx.w[1], 1.0, ptr(g),
+             None, ptr(dlogits), n, c, spatial, stream_ptr())
+        return dlogits, None, None, None, None, None
+
+
+def hard_dice_from_sums(sums, c):
+    """Class-wise Dice of argmax one-hot vs ground truth (agent_seg.py:472-476) from the fused
+    kernel's counters; returns a float64 CUDA tensor [C] (no sync)."""
+    base = 3 * c + 2
+    hi, hy, hp = sums[base:base + c], sums[base + c:base + 2 * c], sums[base + 2 * c:base + 3 * c]
+    return (2.0 * hi + 1e-5) / (hy + hp + 1e-5)
+
+
+class _FusedSegLoss(nn.Module):
+    w_dice, w_ce = 1.0, 0.0
+
+    def __init__(self, params=None):
+        super().__init__()
+        self.softmax = True if params is None else params.get('loss_softmax', True)
+        self.last = {}
+
+    def forward(self, loss_input_dict):
+        if not self.softmax:
+            raise NotImplementedError("loss_softmax=False is not supported by the fused Dice/CE kernel")
+        predict, soft_y, pix_w = _prep(loss_input_dict)
+        return _DiceCE.apply(predict, soft_y, pix_w, float(self.w_dice), float(self.w_ce), self.last)
+
+    def last_hard_dice(self):
+        s = self.last.get("sums")
+        return None if s is None else hard_dice_from_sums(s, (s.numel() - 2) // 6)
+
+
+class DiceLoss(_FusedSegLoss):
+    w_dice, w_ce = 1.0, 0.0
+
+
+class CrossEntropyLoss(_FusedSegLoss):
+    w_dice, w_ce = 0.0, 1.0
+
+
+class CombinedLoss(_FusedSegLoss):
+    """sum_i loss_weight[i] * loss_i for ``loss_type = [..]`` (combined.py:21-39); when every term is
+    a fused Dice/CE entry the sum is evaluated by ONE kernel pair."""
+
+    def __init__(self, params, loss_dict):
+        super().__init__(params)
+        names = params['loss_type']
+        self.loss_weight = params['loss_weight']
+        assert len(names) == len(self.loss_weight)
+        self.loss_list = []
+        for name in names:
+            if name in loss_dict:
+                self.loss_list.append(loss_dict[name](params))
+            else:
+                raise ValueError("{0:} is not defined, or has not been added to the \
+                    loss dictionary".format(name))
+        self.fused = all(isinstance(l, _FusedSegLoss) and not isinstance(l, CombinedLoss) for l in self.loss_list)
+        if self.fused:
+            self.w_dice = sum(w * l.w_dice for w, l in zip(self.loss_weight, self.loss_list))
+            self.w_ce = sum(w * l.w_ce for w, l in zip(self.loss_weight, self.loss_list))
+
+    def forward(self, loss_input_dict):
+        if self.fused:
+            return super().forward(loss_input_dict)
+        loss_value = 0.0
+        for w, l in zip(self.loss_weight, self.loss_list):
+            loss_value = loss_value + w * l(loss_input_dict)
+        return loss_value

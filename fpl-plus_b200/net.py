@@ -1,0 +1,515 @@
+"""Drop-in ``UNet2D5_dsbn`` for PyMIC's ``net_dict`` (reference:
+PyMIC/pymic/net/net3d/unet2d5_dsbn.py:239-309, net_run_dsbn/dsbn.py:35-64).
+
+Same constructor (``params`` dict), same ``forward(x, domain_label)``, same 484-entry
+``state_dict`` (the torch ``nn`` modules below are used purely as parameter containers, created
+in the reference's order so default initialisation under a given seed is identical), same
+``nn.Dropout`` children for the agent's test-time-dropout hook (agent_seg.py:845-852).
+
+The arithmetic is NOT torch: ``forward`` runs the whole network as one autograd node whose
+forward/backward are sequences of sm_100a kernels behind the C ABI (tcgen05 implicit-GEMM convs,
+fused DSBN+PReLU+dropout+pool kernels, skip/up tensors written straight into shared concat
+buffers).  Activations live in bf16 C8-planar layout; images/logits stay NCDHW fp32.
+"""
+import ctypes
+import os
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import C8, call, ptr, stream_ptr
+
+
+# ------------------------------------------------------------------------------------------
+# parameter containers (state_dict compatible with the reference)
+# ------------------------------------------------------------------------------------------
+class DomainSpecificBatchNorm2d(nn.Module):
+    def __init__(self, num_features, num_domains):
+        super().__init__()
+        self.bns = nn.ModuleList([nn.BatchNorm2d(num_features) for _ in range(num_domains)])
+
+
+class DomainSpecificBatchNorm3d(nn.Module):
+    def __init__(self, num_features, num_domains):
+        super().__init__()
+        self.bns = nn.ModuleList([nn.BatchNorm3d(num_features) for _ in range(num_domains)])
+
+
+class ConvBlockND(nn.Module):
+    """conv -> DSBN -> PReLU -> Dropout -> conv -> DSBN -> PReLU (unet2d5_dsbn.py:48-83)."""
+
+    def __init__(self, in_channels, out_channels, num_domains=None, dim=2, dropout_p=0.5):
+        super().__init__()
+        self.conv2d_1 = nn.Conv2d(in_channels, out_channels, kernel_size=3, padding=1)
+        self.conv2d_2 = nn.Conv2d(out_channels, out_channels, kernel_size=3, padding=1)
+        self.conv3d_1 = nn.Conv3d(in_channels, out_channels, kernel_size=3, padding=1)
+        self.conv3d_2 = nn.Conv3d(out_channels, out_channels, kernel_size=3, padding=1)
+        self.bn2d1 = DomainSpecificBatchNorm2d(out_channels, num_domains)
+        self.bn2d2 = DomainSpecificBatchNorm2d(out_channels, num_domains)
+        self.bn3d1 = DomainSpecificBatchNorm3d(out_channels, num_domains)
+        self.bn3d2 = DomainSpecificBatchNorm3d(out_channels, num_domains)
+        self.dropout_p = dropout_p
+        self.dropout = nn.Dropout(dropout_p)
+        self.relu_1 = nn.PReLU()
+        self.relu_2 = nn.PReLU()
+        self.dim = dim
+        self.in_channels, self.out_channels = in_channels, out_channels
+
+    def units(self):
+        """(conv, dsbn, prelu, dropout-or-None) for the two conv units in use."""
+        if self.dim == 2:
+            return ((self.conv2d_1, self.bn2d1, self.relu_1, self.dropout),
+                    (self.conv2d_2, self.bn2d2, self.relu_2, None))
+        return ((self.conv3d_1, self.bn3d1, self.relu_1, self.dropout),
+                (self.conv3d_2, self.bn3d2, self.relu_2, None))
+
+
+class DownBlock(nn.Module):
+    def __init__(self, in_channels, out_channels, num_domains=None, dim=2, dropout_p=0.0, downsample=True):
+        super().__init__()
+        self.downsample, self.dim = downsample, dim
+        self.conv = ConvBlockND(in_channels, out_channels, num_domains, dim, dropout_p)
+
+
+class UpBlock(nn.Module):
+    def __init__(self, in_channels1, in_channels2, out_channels, num_domains=None, dim=2, dropout_p=0.0,
+                 bilinear=True):
+        super().__init__()
+        self.bilinear, self.dim = bilinear, dim
+        self.conv2d = nn.Conv2d(in_channels1, in_channels2, kernel_size=1)
+        self.conv3d = nn.Conv3d(in_channels1, in_channels2, kernel_size=1)
+        self.trans2d = nn.ConvTranspose2d(in_channels1, in_channels2, kernel_size=2, stride=2)
+        self.trans3d = nn.ConvTranspose3d(in_channels1, in_channels2, kernel_size=2, stride=2)
+        self.conv = ConvBlockND(in_channels2 * 2, out_channels, num_domains, dim, dropout_p)
+
+
+# ------------------------------------------------------------------------------------------
+# execution engine
+# ------------------------------------------------------------------------------------------
+class _Unit(object):
+    """One conv + DSBN + PReLU (+dropout) stage and where its tensors live."""
+
+    def __init__(self, name, conv, dsbn, prelu, dropout, kd, is_stem=False):
+        self.name, self.conv, self.dsbn, self.prelu, self.dropout = name, conv, dsbn, prelu, dropout
+        self.kd, self.is_stem = kd, is_stem
+        self.cin, self.cout = conv.in_channels, conv.out_channels
+
+
+class _Workspace(object):
+    def __init__(self, device):
+        self.device = device
+        self.t = {}
+
+    def get(self, name, shape, dtype):
+        t = self.t.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self.t[name] = t
+        return t
+
+    def c8(self, name, n, d, c, h, w):
+        return self.get(name, (n, d, c // 8, h, w, 8), torch.bfloat16)
+
+
+class _Lease(object):
+    """Returns a workspace to the pool when the autograd node that used it is freed."""
+
+    def __init__(self, pool, ws):
+        self.pool, self.ws = pool, ws
+
+    def __del__(self):
+        try:
+            self.pool.append(self.ws)
+        except Exception:
+            pass
+
+
+def _conv_impl():
+    return os.environ.get("FPL_CONV_IMPL", "tc")
+
+
+class UNet2D5_dsbn(nn.Module):
+    """DSBN 2.5D/3D U-Net; see module docstring.  ``params`` keys: in_chns, feature_chns[5],
+    dropout[5], conv_dims[5] (2 or 3), class_num, bilinear, num_domains (extra keys ignored)."""
+
+    def __init__(self, params):
+        super().__init__()
+        self.params = params
+        self.in_chns = params['in_chns']
+        self.ft_chns = list(params['feature_chns'])
+        self.dropout = list(params['dropout'])
+        self.dims = list(params['conv_dims'])
+        self.n_class = params['class_num']
+        self.bilinear = params['bilinear']
+        self.num_domains = params['num_domains']
+        assert len(self.ft_chns) == 5
+        ft, nd, dm, dp = self.ft_chns, self.num_domains, self.dims, self.dropout
+        self.block0 = DownBlock(self.in_chns, ft[0], nd, dm[0], dp[0], True)
+        self.block1 = DownBlock(ft[0], ft[1], nd, dm[1], dp[1], True)
+        self.block2 = DownBlock(ft[1], ft[2], nd, dm[2], dp[2], True)
+        self.block3 = DownBlock(ft[2], ft[3], nd, dm[3], dp[3], True)
+        self.block4 = DownBlock(ft[3], ft[4], nd, dm[4], dp[4], False)
+        self.up1 = UpBlock(ft[4], ft[3], ft[3], nd, dm[3], dropout_p=dp[3], bilinear=self.bilinear)
+        self.up2 = UpBlock(ft[3], ft[2], ft[2], nd, dm[2], dropout_p=dp[2], bilinear=self.bilinear)
+        self.up3 = UpBlock(ft[2], ft[1], ft[1], nd, dm[1], dropout_p=dp[1], bilinear=self.bilinear)
+        self.up4 = UpBlock(ft[1], ft[0], ft[0], nd, dm[0], dropout_p=dp[0], bilinear=self.bilinear)
+        self.out_conv = nn.Conv3d(ft[0], self.n_class, kernel_size=(1, 3, 3), padding=(0, 1, 1))
+        # engine state (not part of state_dict)
+        self._pool = []
+        self._infer_ws = None
+        self._img_cache = {}
+        self._dropout_masks = None      # {unit name: uint8 keep mask, dense C8-planar order} (parity tests)
+        self._rng_offset = 0
+        self.grad_ready_hook = None     # callable(flat_grad, start, end) fired as buckets complete (DDP)
+        self._build_plan()
+
+    # -- plan -------------------------------------------------------------------------------
+    def _build_plan(self):
+        for c in self.ft_chns:
+            if c % 8 != 0:
+                raise ValueError("feature_chns must be multiples of 8, got {0:}".format(self.ft_chns))
+        blocks = [self.block0, self.block1, self.block2, self.block3, self.block4]
+        ups = [self.up1, self.up2, self.up3, self.up4]
+        self._down_units, self._up_units = [], []
+        for i, b in enumerate(blocks):
+            kd = 3 if b.dim == 3 else 1
+            (c1, n1, r1, d1), (c2, n2, r2, _d2) = b.conv.units()
+            self._down_units.append((_Unit("block%d.conv#1" % i, c1, n1, r1, d1, kd, is_stem=(i == 0)),
+                                     _Unit("block%d.conv#2" % i, c2, n2, r2, None, kd)))
+        for k, u in enumerate(ups, start=1):
+            kd = 3 if u.dim == 3 else 1
+            (c1, n1, r1, d1), (c2, n2, r2, _d2) = u.conv.units()
+            self._up_units.append((_Unit("up%d.conv#1" % k, c1, n1, r1, d1, kd),
+                                   _Unit("up%d.conv#2" % k, c2, n2, r2, None, kd)))
+
+    def _grad_params(self, domain):
+        """Parameters that receive gradients, in the order backward completes them."""
+        out = [self.out_conv.weight, self.out_conv.bias]
+        ups = [self.up1, self.up2, self.up3, self.up4]
+
+        def unit_params(u):
+            bn = u.dsbn.bns[domain]
+            return [u.conv.weight, u.conv.bias, bn.weight, bn.bias, u.prelu.weight]
+
+        for k in (3, 2, 1, 0):
+            u1, u2 = self._up_units[k]
+            out += unit_params(u2) + unit_params(u1)
+            t = ups[k].trans3d if ups[k].dim == 3 else ups[k].trans2d
+            out += [t.weight, t.bias]
+        for i in (4, 3, 2, 1, 0):
+            u1, u2 = self._down_units[i]
+            out += unit_params(u2) + unit_params(u1)
+        return out
+
+    # -- public forward ---------------------------------------------------------------------
+    def forward(self, x, domain_label=None):
+        if domain_label is None:
+            raise ValueError("UNet2D5_dsbn.forward needs domain_label")
+        if x.dim() != 5:
+            raise ValueError('expected 5D input (got {}D input)'.format(x.dim()))
+        if not x.is_cuda:
+            raise RuntimeError("fplplus_b200.UNet2D5_dsbn runs on CUDA (sm_100a) only; got a %s tensor" % x.device)
+        if self.bilinear:
+            raise NotImplementedError("bilinear=True up-sampling is not built yet (SURVEY.md §8f-1)")
+        domain = int(domain_label[0])
+        if not 0 <= domain < self.num_domains:
+            raise IndexError("domain_label %d out of range" % domain)
+        x = x.float().contiguous()
+        params = self._grad_params(domain)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        if need_grad:
+            return _UNetFunction.apply(self, domain, x, *params)
+        ws = self._infer_ws
+        if ws is None or ws.device != x.device:
+            ws = self._infer_ws = _Workspace(x.device)
+        logits, _ = self._run_forward(x, domain, ws)
+        return logits
+
+    # -- helpers ----------------------------------------------------------------------------
+    def _geometry(self, shape):
+        n, c, d, h, w = shape
+        if c != self.in_chns:
+            raise ValueError("expected %d input channels, got %d" % (self.in_chns, c))
+        geo = [(d, h, w)]
+        for i in range(4):
+            d, h, w = geo[-1]
+            kd = 2 if self.dims[i] == 3 else 1
+            if d % kd or h % 2 or w % 2:
+                raise ValueError("input size %s is not divisible by the down-sampling factors" % (tuple(shape[2:]),))
+            geo.append((d // kd, h // 2, w // 2))
+        return geo
+
+    def _use_tc(self, cin, cout):
+        return _conv_impl() == "tc" and cin % 16 == 0 and cout % 16 == 0 and ops.is_sm100()
+
+    def _weight_image(self, conv, kd, transpose, ws):
+        w = conv.weight
+        cin, cout = conv.in_channels, conv.out_channels
+        key = (id(w), transpose)
+        ent = self._img_cache.get(key)
+        if ent is not None and ent[0] == w._version and ent[1].device == w.device:
+            return ent[1]
+        nbytes = ops._lib.load().fpl_conv3d_weight_image_bytes(cout if transpose else cin, cin if transpose else cout, kd)
+        img = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
+        call("fpl_conv3d_prep_weight", ptr(w), cin, cout, kd, 1 if transpose else 0, ptr(img), stream_ptr())
+        self._img_cache[key] = (w._version, img)
+        return img
+
+    def _conv_fwd(self, u, xin, x_img, y, stats, n, geo, ws):
+        d, h, w = geo
+        st = stream_ptr()
+        if u.is_stem:
+            call("fpl_stem_conv_fwd", ptr(x_img), ptr(u.conv.weight), ptr(u.conv.bias), ptr(y), y.shape[2], 0,
+                 ptr(stats), n, u.cin, d, h, w, u.cout, u.kd, st)
+        elif self._use_tc(u.cin, u.cout):
+            img = self._weight_image(u.conv, u.kd, False, ws)
+            call("fpl_conv3d_tc", *xin.args(), ptr(img), ptr(u.conv.bias), ptr(y), y.shape[2], 0, ptr(stats),
+                 n, d, h, w, u.cin, u.cout, u.kd, st)
+        else:
+            call("fpl_conv3d_direct", *xin.args(), ptr(u.conv.weight), ptr(u.conv.bias), ptr(y), y.shape[2], 0,
+                 ptr(stats), n, d, h, w, u.cin, u.cout, u.kd, 0, 0, st)
+
+    def _unit_fwd(self, u, domain, xin, x_img, out, pooled, pool_idx, pool_kd, n, geo, ws, small, rec):
+        """conv -> finalize -> act.  ``out``/``pooled`` are C8 views."""
+        d, h, w = geo
+        c = u.cout
+        y = ws.c8("Y:" + u.name, n, d, c, h, w)
+        stats = small.f64(2 * c)
+        self._conv_fwd(u, xin, x_img, y, stats, n, geo, ws)
+        bn = u.dsbn.bns[domain]
+        if bn.weight.dtype != torch.float32:
+            raise RuntimeError("fplplus_b200 supports tensor_type=float only")
+        scale, shift, mean, invstd = small.f32(c), small.f32(c), small.f32(c), small.f32(c)
+        training = 1 if bn.training else 0
+        call("fpl_dsbn_finalize", ptr(stats), n * d * h * w, ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean),
+             ptr(bn.running_var), ptr(bn.num_batches_tracked), float(bn.momentum), float(bn.eps), training,
+             ptr(scale), ptr(shift), ptr(mean), ptr(invstd), c, stream_ptr())
+        p, mask, seed, offset = 0.0, None, 0, 0
+        if u.dropout is not None and u.dropout.training and u.dropout.p > 0.0:
+            p = float(u.dropout.p)
+            if self._dropout_masks is not None and u.name in self._dropout_masks:
+                mask = self._dropout_masks[u.name]
+            else:
+                seed, offset = rec["seed"], rec["next_offset"]
+                rec["next_offset"] += 2 * n * d * (c // 8) * h * w
+        pv = pooled.args() if pooled is not None else (None, 0, 0)
+        call("fpl_dsbn_act_fwd", ptr(y), ptr(scale), ptr(shift), ptr(u.prelu.weight), *out.args(), *pv,
+             ptr(pool_idx), pool_kd, p, ptr(mask), seed, offset, n, d, h, w, c, stream_ptr())
+        rec[u.name] = dict(y=y, xin=xin, scale=scale, shift=shift, mean=mean, invstd=invstd, training=training,
+                           p=p, mask=mask, seed=seed, offset=offset, geo=geo, bn=bn)
+
+    # -- whole-network forward --------------------------------------------------------------
+    def _run_forward(self, x, domain, ws):
+        n = x.shape[0]
+        geo = self._geometry(x.shape)
+        ft = self.ft_chns
+        small = _SmallPool(ws, "fwd", x.device)
+        # dropout stream: (seed, per-layer offset) drawn from torch's CPU generator, so torch.manual_seed
+        # makes MC-dropout passes reproducible; backward regenerates the same Philox stream
+        rec = {"seed": int(torch.empty((), dtype=torch.int64).random_().item()),
+               "next_offset": 0, "geo": geo, "n": n, "x": x}
+        cur = None
+        for i in range(5):
+            u1, u2 = self._down_units[i]
+            d, h, w = geo[i]
+            c = ft[i]
+            a1 = C8(ws.c8("A1:block%d" % i, n, d, c, h, w))
+            self._unit_fwd(u1, domain, cur, x, a1, None, None, 0, n, geo[i], ws, small, rec)
+            if i < 4:
+                cat = ws.c8("cat%d" % i, n, d, 2 * c, h, w)
+                d2, h2, w2 = geo[i + 1]
+                pooled = C8(ws.c8("P%d" % i, n, d2, c, h2, w2))
+                idx = ws.get("idx%d" % i, (n, d2, c // 8, h2, w2, 8), torch.uint8)
+                pool_kd = 2 if self.dims[i] == 3 else 1
+                self._unit_fwd(u2, domain, a1, None, C8(cat, 0, c), pooled, idx, pool_kd, n, geo[i], ws, small, rec)
+                rec["idx%d" % i] = (idx, pool_kd)
+                cur = pooled
+            else:
+                a2 = C8(ws.c8("A2:block4", n, d, c, h, w))
+                self._unit_fwd(u2, domain, a1, None, a2, None, None, 0, n, geo[i], ws, small, rec)
+                cur = a2
+        low = cur
+        ups = [self.up1, self.up2, self.up3, self.up4]
+        for k, lvl in zip(range(4), (3, 2, 1, 0)):
+            up = ups[k]
+            u1, u2 = self._up_units[k]
+            d, h, w = geo[lvl]
+            dl, hl, wl = geo[lvl + 1]
+            c, c_low = ft[lvl], ft[lvl + 1]
+            cat = ws.t["cat%d" % lvl]
+            trans = up.trans3d if up.dim == 3 else up.trans2d
+            kd2 = 2 if up.dim == 3 else 1
+            call("fpl_convt_k2s2_fwd", *low.args(), ptr(trans.weight), ptr(trans.bias), ptr(cat), 2 * c // 8, c // 8,
+                 n, dl, hl, wl, c_low, c, kd2, stream_ptr())
+            rec["up%d.low" % (k + 1)] = low
+            a1 = C8(ws.c8("A1:up%d" % (k + 1), n, d, c, h, w))
+            self._unit_fwd(u1, domain, C8(cat, 0, 2 * c), None, a1, None, None, 0, n, geo[lvl], ws, small, rec)
+            a2 = C8(ws.c8("A2:up%d" % (k + 1), n, d, c, h, w))
+            self._unit_fwd(u2, domain, a1, None, a2, None, None, 0, n, geo[lvl], ws, small, rec)
+            low = a2
+        d, h, w = geo[0]
+        logits = torch.empty((n, self.n_class, d, h, w), dtype=torch.float32, device=x.device)
+        call("fpl_head_conv_fwd", *low.args(), ptr(self.out_conv.weight), ptr(self.out_conv.bias), ptr(logits),
+             n, d, h, w, ft[0], self.n_class, stream_ptr())
+        rec["head_in"] = low
+        return logits, rec
+
+    # -- whole-network backward -------------------------------------------------------------
+    def _unit_bwd(self, u, r, g1, g_pool, pool_idx, pool_kd, n, ws, small, grads, need_dx):
+        """Backward of one conv unit.  Returns the C8 gradient wrt the unit's input (or None)."""
+        d, h, w = r["geo"]
+        c = u.cout
+        st = stream_ptr()
+        red = small.f64(2 * c + 1)
+        g1a = g1.args() if g1 is not None else (None, 0, 0)
+        gpa = g_pool.args() if g_pool is not None else (None, 0, 0)
+        common = (ptr(r["y"]), *g1a, *gpa, ptr(pool_idx), pool_kd, ptr(r["scale"]), ptr(r["shift"]), ptr(r["mean"]),
+                  ptr(r["invstd"]), ptr(u.prelu.weight), r["p"], ptr(r["mask"]), r["seed"], r["offset"])
+        call("fpl_dsbn_act_bwd_reduce", *common, ptr(red), n, d, h, w, c, st)
+        dy = ws.c8("dY:%dx%dx%dx%d" % (c, d, h, w), n, d, c, h, w)
+        call("fpl_dsbn_act_bwd_apply", *common, ptr(red), r["training"], ptr(dy), n, d, h, w, c, st)
+        bn = r["bn"]
+        call("fpl_dsbn_bwd_finalize", ptr(red), ptr(r["scale"]), ptr(r["invstd"]), r["training"],
+             ptr(grads[bn.weight]), ptr(grads[bn.bias]), ptr(grads[u.prelu.weight]), ptr(grads[u.conv.bias]), c, st)
+        dw = grads[u.conv.weight]
+        if u.is_stem:
+            call("fpl_stem_conv_wgrad", ptr(r["x_img"]), ptr(dy), c // 8, 0, ptr(dw), n, u.cin, d, h, w, c, u.kd, st)
+            return None
+        xin = r["xin"]
+        self._wgrad(u, xin, dy, dw, n, d, h, w)
+        if not need_dx:
+            return None
+        dx = ws.c8("dX:" + u.name, n, d, u.cin, h, w)
+        if self._use_tc(u.cout, u.cin):
+            img = self._weight_image(u.conv, u.kd, True, ws)
+            call("fpl_conv3d_tc", ptr(dy), c // 8, 0, ptr(img), None, ptr(dx), u.cin // 8, 0, None,
+                 n, d, h, w, c, u.cin, u.kd, st)
+        else:
+            call("fpl_conv3d_direct", ptr(dy), c // 8, 0, ptr(u.conv.weight), None, ptr(dx), u.cin // 8, 0, None,
+                 n, d, h, w, c, u.cin, u.kd, 1, 0, st)
+        return C8(dx)
+
+    def _wgrad(self, u, xin, dy, dw, n, d, h, w):
+        impl = os.environ.get("FPL_WGRAD_IMPL", "mma")
+        lib = ops._lib.load()
+        if impl == "mma" and hasattr(lib, "fpl_conv3d_wgrad_mma") and u.cin % 16 == 0 and u.cout % 16 == 0:
+            call("fpl_conv3d_wgrad_mma", *xin.args(), ptr(dy), u.cout // 8, 0, ptr(dw), n, d, h, w, u.cin, u.cout,
+                 u.kd, stream_ptr())
+        else:
+            call("fpl_conv3d_wgrad", *xin.args(), ptr(dy), u.cout // 8, 0, ptr(dw), n, d, h, w, u.cin, u.cout, u.kd,
+                 stream_ptr())
+
+    def _run_backward(self, rec, dlogits, domain, ws):
+        n, geo, ft = rec["n"], rec["geo"], self.ft_chns
+        params = self._grad_params(domain)
+        sizes = [(p.numel() + 3) // 4 * 4 for p in params]
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dlogits.device)
+        grads, offs, o = {}, [], 0
+        for p, s in zip(params, sizes):
+            grads[p] = flat[o:o + p.numel()]
+            offs.append(o)
+            o += s
+        fired = [0]
+
+        def fire(n_params_done):
+            # gradients of params[:n_params_done] are final: hand the new flat range to the hook (DDP all-reduce)
+            if self.grad_ready_hook is not None:
+                end = offs[n_params_done - 1] + sizes[n_params_done - 1]
+                if end > fired[0]:
+                    self.grad_ready_hook(flat, fired[0], end)
+                    fired[0] = end
+
+        small = _SmallPool(ws, "bwd", dlogits.device)
+        st = stream_ptr()
+        d, h, w = geo[0]
+        head_in = rec["head_in"]
+        g = C8(ws.c8("dX:head", n, d, ft[0], h, w))
+        call("fpl_head_conv_bwd", *head_in.args(), ptr(self.out_conv.weight), ptr(dlogits.contiguous()), *g.args(),
+             ptr(grads[self.out_conv.weight]), ptr(grads[self.out_conv.bias]), n, d, h, w, ft[0], self.n_class, st)
+        ups = [self.up1, self.up2, self.up3, self.up4]
+        skip_grads = {}
+        done = 2
+        fire(done)
+        for k, lvl in zip((3, 2, 1, 0), (0, 1, 2, 3)):
+            u1, u2 = self._up_units[k]
+            up = ups[k]
+            c, c_low = ft[lvl], ft[lvl + 1]
+            g = self._unit_bwd(u2, rec[u2.name], g, None, None, 0, n, ws, small, grads, True)
+            # dgrad of unit 1 produces the gradient of the whole concat buffer; keep it alive per level
+            r1 = rec[u1.name]
+            dcat = self._unit_bwd(u1, r1, g, None, None, 0, n, ws, small, grads, True)
+            skip_grads[lvl] = C8(dcat.buf, 0, c)
+            trans = up.trans3d if up.dim == 3 else up.trans2d
+            kd2 = 2 if up.dim == 3 else 1
+            dl, hl, wl = geo[lvl + 1]
+            low = rec["up%d.low" % (k + 1)]
+            glow = C8(ws.c8("dlow%d" % lvl, n, dl, c_low, hl, wl))
+            call("fpl_convt_k2s2_bwd", *low.args(), ptr(trans.weight), ptr(dcat.buf), 2 * c // 8, c // 8, *glow.args(),
+                 ptr(grads[trans.weight]), ptr(grads[trans.bias]), n, dl, hl, wl, c_low, c, kd2, st)
+            g = glow
+            done += 12
+            fire(done)
+        g_pool = None
+        for i in (4, 3, 2, 1, 0):
+            u1, u2 = self._down_units[i]
+            if i == 4:
+                g = self._unit_bwd(u2, rec[u2.name], g, None, None, 0, n, ws, small, grads, True)
+            else:
+                idx, pool_kd = rec["idx%d" % i]
+                g = self._unit_bwd(u2, rec[u2.name], skip_grads[i], g_pool, idx, pool_kd, n, ws, small, grads, True)
+            r1 = rec[u1.name]
+            r1["x_img"] = rec["x"]
+            if i > 0:
+                g_pool = self._unit_bwd(u1, r1, g, None, None, 0, n, ws, small, grads, True)
+            else:
+                self._unit_bwd(u1, r1, g, None, None, 0, n, ws, small, grads, False)
+            done += 10
+            fire(done)
+        assert done == len(params)
+        return [grads[p] for p in params]
+
+
+class _SmallPool(object):
+    """Bump allocator for per-layer fp32/fp64 scratch (statistics, scale/shift, reductions): one
+    zero-fill per pass instead of one per layer."""
+
+    def __init__(self, ws, tag, device, n32=1 << 16, n64=1 << 15):
+        self.b32 = ws.get("small32:" + tag, (n32,), torch.float32)
+        self.b64 = ws.get("small64:" + tag, (n64,), torch.float64)
+        self.b32.zero_()
+        self.b64.zero_()
+        self.o32 = self.o64 = 0
+
+    def f32(self, n):
+        n4 = (n + 3) // 4 * 4
+        t = self.b32[self.o32:self.o32 + n]
+        self.o32 += n4
+        assert self.o32 <= self.b32.numel()
+        return t
+
+    def f64(self, n):
+        n2 = (n + 1) // 2 * 2
+        t = self.b64[self.o64:self.o64 + n]
+        self.o64 += n2
+        assert self.o64 <= self.b64.numel()
+        return t
+
+
+class _UNetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, net, domain, x, *params):
+        ws = net._pool.pop() if net._pool else _Workspace(x.device)
+        if ws.device != x.device:
+            ws = _Workspace(x.device)
+        logits, rec = net._run_forward(x, domain, ws)
+        ctx.net, ctx.domain, ctx.rec = net, domain, rec
+        ctx.lease = _Lease(net._pool, ws)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        net = ctx.net
+        grads = net._run_backward(ctx.rec, dlogits, ctx.domain, ctx.lease.ws)
+        ctx.rec = None
+        return (None, None, None) + tuple(grads)

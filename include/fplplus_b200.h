@@ -1,0 +1,179 @@
+/*
+ * fplplus_b200 -- C ABI of the B200-native FPL+ hot path (sm_100a).
+ *
+ * The reference (HiLab-git/FPL-plus) is pure Python and has no FFI; every entry
+ * point below replaces the torch/NumPy call sequence named in its comment
+ * (paths relative to the reference tree).  INTEGRATION.md shows the ctypes
+ * binding a PyMIC maintainer would add.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless named h_*; the caller owns them.
+ *   - `stream` is a cudaStream_t passed as void*.
+ *   - every function returns 0 on success, non-zero on error; fpl_last_error()
+ *     returns a thread-local message.  Nothing here falls back to the CPU.
+ *   - activations use the "C8-planar" layout  [N][D][C/8][H][W][8]  in bf16
+ *     (channel groups of 8 are 16-byte vectors; a tensor that is a channel slice
+ *     of a wider buffer -- e.g. one half of a skip/up concat buffer -- is
+ *     addressed by (base, c8_total, c8_offset)).  Images/logits at the PyMIC
+ *     boundary stay NCDHW fp32.
+ */
+#ifndef FPLPLUS_B200_H
+#define FPLPLUS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* fpl_last_error(void);
+int fpl_version(void);
+/* 1 when the running device is sm_100 (tcgen05 kernels usable), else 0. */
+int fpl_device_is_sm100(void);
+/* debugging knobs of the tensor-core conv (key 0: swap LBO/SBO of the UMMA descriptors). */
+void fpl_debug_set(int key, int value);
+
+/* ---- (a) conv3d: PyMIC/pymic/net/net3d/unet2d5_dsbn.py:75,79 (nn.Conv3d k3 p1 / k(1,3,3) p(0,1,1)) ---- */
+
+/* Bytes of the staged bf16 weight image fpl_conv3d_prep_weight writes. */
+int64_t fpl_conv3d_weight_image_bytes(int cin, int cout, int kd);
+/* fp32 [Cout][Cin][kd][3][3] -> staged bf16 image for the tcgen05 kernel.
+ * transpose_flip=0: forward operand.  =1: dgrad operand (taps flipped, Cin/Cout
+ * swapped; `cin`/`cout` are still those of the FORWARD conv). */
+int fpl_conv3d_prep_weight(const float* w, int cin, int cout, int kd, int transpose_flip,
+                           void* image, void* stream);
+/* Implicit-GEMM conv on tcgen05/TMEM fed by TMA.  x: C8-planar bf16 with
+ * `cin` channels at (x_c8tot, x_c8off); y likewise with `cout` channels.
+ * bias may be NULL.  stats (double[2*cout]: sum, sum of squares of the fp32
+ * results incl. bias) may be NULL; it is ACCUMULATED into (caller zeroes).
+ * `image` must have been prepared for (cin, cout) of THIS call (for dgrad call
+ * with cin=Cout_fwd, cout=Cin_fwd and the transpose_flip image). */
+int fpl_conv3d_tc(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias,
+                  void* y, int y_c8tot, int y_c8off, double* stats,
+                  int n, int d, int h, int w, int cin, int cout, int kd, void* stream);
+/* CUDA-core conv with the same contract (used for shapes the tensor kernel does
+ * not cover and as the on-device cross-check).  w is fp32 [Cout][Cin][kd][3][3];
+ * transpose_flip as above; round_w_bf16!=0 rounds weights to bf16 first. */
+int fpl_conv3d_direct(const void* x, int x_c8tot, int x_c8off, const float* w, const float* bias,
+                      void* y, int y_c8tot, int y_c8off, double* stats,
+                      int n, int d, int h, int w_, int cin, int cout, int kd,
+                      int transpose_flip, int round_w_bf16, void* stream);
+/* wgrad: dW[Cout][Cin][kd][3][3] (fp32, ACCUMULATED into) = sum_v dy[v] (x) x[v+tap]. */
+int fpl_conv3d_wgrad(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
+                     float* dw, int n, int d, int h, int w, int cin, int cout, int kd, void* stream);
+
+/* stem: image fp32 NCDHW (in_chns <= 8) -> C8-planar bf16, conv k3 p1 + bias + stats. */
+int fpl_stem_conv_fwd(const float* x, const float* w, const float* bias, void* y, int y_c8tot, int y_c8off,
+                      double* stats, int n, int cin, int d, int h, int w_, int cout, int kd, void* stream);
+int fpl_stem_conv_wgrad(const float* x, const void* dy, int dy_c8tot, int dy_c8off, float* dw,
+                        int n, int cin, int d, int h, int w_, int cout, int kd, void* stream);
+/* head: unet2d5_dsbn.py:293-294, nn.Conv3d(C0, classes, (1,3,3), padding (0,1,1)); logits fp32 NCDHW. */
+int fpl_head_conv_fwd(const void* x, int x_c8tot, int x_c8off, const float* w, const float* bias,
+                      float* logits, int n, int d, int h, int w_, int cin, int classes, void* stream);
+/* dlogits fp32 NCDHW -> dx C8-planar bf16; dw[classes][cin][1][3][3], db[classes] accumulated. */
+int fpl_head_conv_bwd(const void* x, int x_c8tot, int x_c8off, const float* w, const float* dlogits,
+                      void* dx, int dx_c8tot, int dx_c8off, float* dw, float* db,
+                      int n, int d, int h, int w_, int cin, int classes, void* stream);
+
+/* ---- (a') ConvTranspose3d k2 s2: unet2d5_dsbn.py:152,181 (w fp32 [Cin][Cout][2][2][2]) ---- */
+int fpl_convt_k2s2_fwd(const void* x, int x_c8tot, int x_c8off, const float* w, const float* bias,
+                       void* y, int y_c8tot, int y_c8off, int n, int d, int h, int w_, int cin, int cout,
+                       int kd2, void* stream);   /* kd2 = 2 (3-D) or 1 ((1,2,2), 2.5-D levels) */
+/* dy at the up-sampled resolution; dx (may be NULL) at the input resolution;
+ * dw/db accumulated. */
+int fpl_convt_k2s2_bwd(const void* x, int x_c8tot, int x_c8off, const float* w,
+                       const void* dy, int dy_c8tot, int dy_c8off,
+                       void* dx, int dx_c8tot, int dx_c8off, float* dw, float* db,
+                       int n, int d, int h, int w_, int cin, int cout, int kd2, void* stream);
+
+/* ---- (b) DSBN BatchNorm3d + PReLU + Dropout + MaxPool: net_run_dsbn/dsbn.py:54-57,
+ *          unet2d5_dsbn.py:76-81,104-106 ---- */
+
+/* stats(double[2C]) -> scale/shift (fp32[C]) and save_mean/save_invstd (fp32[C]).
+ * training!=0: batch statistics; running_mean/var updated with momentum (unbiased
+ * var), num_batches_tracked (int64) += 1 -- pass the SELECTED domain's buffers.
+ * training==0: scale/shift from the running statistics; stats unused. */
+int fpl_dsbn_finalize(const double* stats, int64_t count, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                      float momentum, float eps, int training,
+                      float* scale, float* shift, float* save_mean, float* save_invstd, int c, void* stream);
+/* a = dropout(prelu(y*scale+shift)); optional fused 2x2x2 (pool_kd=2) or 1x2x2
+ * (pool_kd=1) max-pool writing `pooled` and the argmax code `pool_idx` (uint8).
+ * Dropout: p in [0,1); mask (uint8 keep flags, same C8-planar element order as a
+ * dense [N][D][C/8][H][W][8] tensor) if non-NULL, else Philox4x32-10(seed, offset). */
+int fpl_dsbn_act_fwd(const void* y, const float* scale, const float* shift, const float* slope,
+                     void* a, int a_c8tot, int a_c8off,
+                     void* pooled, int p_c8tot, int p_c8off, uint8_t* pool_idx, int pool_kd,
+                     float drop_p, const uint8_t* drop_mask, uint64_t seed, uint64_t offset,
+                     int n, int d, int h, int w, int c, void* stream);
+/* Backward.  Gradient wrt the activated output = g1 (C8-planar slice, may be NULL)
+ * + max-pool scatter of g_pool through pool_idx (may be NULL).  With dz the gradient
+ * wrt the BN output and xhat = (y-mean)*invstd:
+ *   pass 1 (reduce) ACCUMULATES red = double[2C+1] {sum dz [C], sum dz*xhat [C], dslope};
+ *   pass 2 (apply) writes dy (bf16, dense C8-planar) = scale*(dz - mean(dz) - xhat*mean(dz*xhat))
+ *                  (training) or scale*dz (training==0, BN is a fixed affine map);
+ *   finalize ACCUMULATES dgamma/dbeta/dslope/dbias_conv (fp32; any may be NULL) from red.
+ * The dropout mask is regenerated from (seed, offset) or read from drop_mask. */
+int fpl_dsbn_act_bwd_reduce(const void* y, const void* g1, int g1_c8tot, int g1_c8off,
+                            const void* g_pool, int gp_c8tot, int gp_c8off, const uint8_t* pool_idx, int pool_kd,
+                            const float* scale, const float* shift, const float* save_mean,
+                            const float* save_invstd, const float* slope,
+                            float drop_p, const uint8_t* drop_mask, uint64_t seed, uint64_t offset,
+                            double* red, int n, int d, int h, int w, int c, void* stream);
+int fpl_dsbn_act_bwd_apply(const void* y, const void* g1, int g1_c8tot, int g1_c8off,
+                           const void* g_pool, int gp_c8tot, int gp_c8off, const uint8_t* pool_idx, int pool_kd,
+                           const float* scale, const float* shift, const float* save_mean,
+                           const float* save_invstd, const float* slope,
+                           float drop_p, const uint8_t* drop_mask, uint64_t seed, uint64_t offset,
+                           const double* red, int training, void* dy,
+                           int n, int d, int h, int w, int c, void* stream);
+int fpl_dsbn_bwd_finalize(const double* red, const float* scale, const float* save_invstd, int training,
+                          float* dgamma, float* dbeta, float* dslope, float* dbias_conv, int c, void* stream);
+
+/* ---- (d) pixel/image-weighted Dice + CE: loss/seg/dice.py:20-57, ce.py:23-44, util.py:85-107 ---- */
+
+/* sums = double[3C+2+3C]: I_c, Y_c, P_c, sum_w, sum_w_ce, then the hard-Dice
+ * counters of agent_seg.py:472-476 (sum onehot(argmax)*y, sum y, sum onehot(argmax)) -- ACCUMULATED into.
+ * logits/soft_y fp32 NCDHW, weight fp32 [N,1,D,H,W] or NULL. */
+int fpl_dice_ce_reduce(const float* logits, const float* soft_y, const float* weight,
+                       double* sums, int n, int c, int64_t spatial, void* stream);
+/* loss (fp32[1], may be NULL) and dlogits (fp32 NCDHW, may be NULL) from the sums; dlogits =
+ * grad_scale * (*grad_scale_dev if non-NULL) * d(w_dice*Dice + w_ce*CE)/dlogits, so the upstream
+ * gradient of autograd can stay on the device. */
+int fpl_dice_ce_grad(const float* logits, const float* soft_y, const float* weight,
+                     const double* sums, float w_dice, float w_ce, float grad_scale,
+                     const float* grad_scale_dev, float* loss, float* dlogits,
+                     int n, int c, int64_t spatial, void* stream);
+
+/* ---- (c) pseudo-label filter: agent_seg.py:897-931,1045-1050; data/get_pixel_weight.py:21-26;
+ *          io/nifty_dataset.py:165-168 ---- */
+
+/* logits fp32 [B,C,spatial] -> uint8 argmax labels (first max wins). */
+int fpl_argmax_label(const float* logits, uint8_t* label, int b, int c, int64_t spatial, void* stream);
+/* K MC-dropout logits maps of ONE volume ([K][C][spatial], passes may live in
+ * separate buffers: logits_k[k]) -> out (double[2]: sum of per-voxel population
+ * variance over classes, boundary voxel count), optional uncertainty map fp32[spatial]. */
+int fpl_mc_uncertainty(const float* const* h_logits_k, int k, int c, int64_t spatial,
+                       double* out, float* uncertainty_map, void* stream);
+/* Two logits maps (target pass, fake-source pass) -> two uint8 label maps and the
+ * agreement weight 1 - 0.5*[a != b]; if fold_image_weight != 0 the weight is folded
+ * as set_weight_ does: (w < 1 ? 0 : w) * image_weight.  out_count (int64[1], may be
+ * NULL) accumulates the number of disagreeing voxels. */
+int fpl_agree_weight(const float* logits_tgt, const float* logits_src, uint8_t* label_tgt, uint8_t* label_src,
+                     float* weight, int fold_image_weight, float image_weight, long long* out_count,
+                     int c, int64_t spatial, void* stream);
+
+/* ---- (c') sliding window: net_run_dsbn/infer_func.py:96-112, 202-219 ---- */
+
+/* out[b,c, d0+i, h0+j', w0+k'] += scale * patch[b,c,i,j,k] with j' = ph-1-j when
+ * flip_h (k' likewise for flip_w); count (may be NULL) += 1 on the same voxels. */
+int fpl_window_accumulate(const float* patch, float* out, float* count, int b, int c,
+                          int vd, int vh, int vw, int d0, int h0, int w0, int pd, int ph, int pw,
+                          int flip_h, int flip_w, float scale, void* stream);
+/* out = out / count * scale (count may be NULL). */
+int fpl_window_normalize(float* out, const float* count, float scale, int64_t numel, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

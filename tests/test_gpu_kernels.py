@@ -1,0 +1,455 @@
+"""GPU: every C-ABI kernel against a plain torch fp32 CPU reference of the same op (run on the
+bf16-rounded inputs the kernel sees) -- the per-kernel parity layer under the network tests."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests._util import bf16_round, from_c8, max_rel, randn, rel_l2, to_c8
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _ops():
+    from fplplus_b200 import ops
+    return ops
+
+
+def _call(name, *a):
+    _ops().call(name, *a)
+
+
+def _p(t):
+    return _ops().ptr(t)
+
+
+def _st():
+    return _ops().stream_ptr()
+
+
+def _conv_ref(x, w, b, kd):
+    return F.conv3d(x, w, b, padding=(kd // 2, 1, 1))
+
+
+# ------------------------------------------------------------------------------------------
+# convolution: direct kernel vs torch, tensor-core kernel vs direct kernel
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cin,cout,kd,shape", [(16, 16, 3, (2, 4, 20, 12)), (32, 16, 3, (1, 3, 16, 8)),
+                                               (8, 24, 1, (1, 2, 9, 10)), (64, 32, 3, (1, 2, 8, 8))])
+def test_conv3d_direct_fwd_and_stats(cin, cout, kd, shape):
+    n, d, h, w = shape
+    x = bf16_round(randn(1, n, cin, d, h, w))
+    wt = randn(2, cout, cin, kd, 3, 3, scale=0.1)
+    b = randn(3, cout, scale=0.1)
+    ref = _conv_ref(x, wt, b, kd)
+    xb = to_c8(x.to(DEV))
+    y = torch.empty((n, d, cout // 8, h, w, 8), dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
+    _call("fpl_conv3d_direct", _p(xb), cin // 8, 0, _p(wt.to(DEV)), _p(b.to(DEV)), _p(y), cout // 8, 0, _p(stats),
+          n, d, h, w, cin, cout, kd, 0, 0, _st())
+    out = from_c8(y).cpu()
+    assert max_rel(out, ref) < 6e-3          # bf16 output rounding only
+    s = stats.cpu()
+    np.testing.assert_allclose(s[:cout], ref.double().sum((0, 2, 3, 4)), rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(s[cout:], (ref.double() ** 2).sum((0, 2, 3, 4)), rtol=1e-4, atol=1e-3)
+
+
+TC_CASES = [
+    (16, 16, 3, (2, 4, 32, 16)), (32, 16, 3, (1, 3, 20, 12)), (16, 32, 3, (1, 2, 16, 8)),
+    (32, 32, 3, (1, 5, 24, 24)), (64, 32, 3, (1, 2, 16, 16)), (64, 64, 3, (2, 3, 16, 8)),
+    (128, 128, 3, (1, 2, 8, 8)), (256, 128, 3, (1, 2, 4, 4)), (256, 256, 3, (2, 1, 2, 2)),
+    (16, 16, 1, (1, 3, 18, 10)), (64, 64, 1, (1, 2, 16, 16)), (48, 80, 3, (1, 2, 10, 9)),
+]
+
+
+@pytest.mark.parametrize("cin,cout,kd,shape", TC_CASES)
+def test_conv3d_tc_matches_direct_and_torch(cin, cout, kd, shape):
+    from fplplus_b200 import lib as L
+    n, d, h, w = shape
+    x = bf16_round(randn(11, n, cin, d, h, w))
+    wt = bf16_round(randn(12, cout, cin, kd, 3, 3, scale=0.1))
+    b = randn(13, cout, scale=0.1)
+    ref = _conv_ref(x, wt, b, kd)
+    xb = to_c8(x.to(DEV))
+    nbytes = L.load().fpl_conv3d_weight_image_bytes(cin, cout, kd)
+    assert nbytes == cin * cout * kd * 9 * 2
+    img = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=DEV)
+    wd, bd = wt.to(DEV), b.to(DEV)
+    _call("fpl_conv3d_prep_weight", _p(wd), cin, cout, kd, 0, _p(img), _st())
+    y = torch.zeros((n, d, cout // 8, h, w, 8), dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
+    _call("fpl_conv3d_tc", _p(xb), cin // 8, 0, _p(img), _p(bd), _p(y), cout // 8, 0, _p(stats), n, d, h, w, cin, cout,
+          kd, _st())
+    torch.cuda.synchronize()
+    out = from_c8(y).cpu()
+    assert max_rel(out, ref) < 6e-3, (max_rel(out, ref), rel_l2(out, ref))
+    y2 = torch.zeros_like(y)
+    _call("fpl_conv3d_direct", _p(xb), cin // 8, 0, _p(wd), _p(bd), _p(y2), cout // 8, 0, None, n, d, h, w, cin, cout,
+          kd, 0, 1, _st())
+    out2 = from_c8(y2).cpu()
+    # same bf16 operands, fp32 accumulation in a different order: at most 1 bf16 ulp apart
+    assert max_rel(out, out2) < 5e-3
+    assert (out != out2).float().mean() < 0.05
+    s = stats.cpu()
+    np.testing.assert_allclose(s[:cout], ref.double().sum((0, 2, 3, 4)), rtol=1e-4, atol=2e-3)
+    np.testing.assert_allclose(s[cout:], (ref.double() ** 2).sum((0, 2, 3, 4)), rtol=1e-4, atol=2e-3)
+
+
+def test_conv3d_tc_reads_and_writes_channel_slices():
+    """x is the second half of a 2C concat buffer, y the first half of another."""
+    from fplplus_b200 import lib as L
+    n, d, h, w, c = 1, 2, 16, 16, 16
+    full = bf16_round(randn(21, n, 2 * c, d, h, w))
+    wt = bf16_round(randn(22, c, c, 3, 3, 3, scale=0.1))
+    ref = _conv_ref(full[:, c:], wt, None, 3)
+    xb = to_c8(full.to(DEV))
+    img = torch.empty(c * c * 27, dtype=torch.bfloat16, device=DEV)
+    _call("fpl_conv3d_prep_weight", _p(wt.to(DEV)), c, c, 3, 0, _p(img), _st())
+    y = torch.full((n, d, 2 * c // 8, h, w, 8), 7.0, dtype=torch.bfloat16, device=DEV)
+    _call("fpl_conv3d_tc", _p(xb), 2 * c // 8, c // 8, _p(img), None, _p(y), 2 * c // 8, 0, None, n, d, h, w, c, c, 3, _st())
+    out = from_c8(y).cpu()
+    assert max_rel(out[:, :c], ref) < 6e-3
+    assert torch.all(out[:, c:] == 7.0)
+
+
+@pytest.mark.parametrize("impl", ["direct", "tc"])
+@pytest.mark.parametrize("cin,cout,kd,shape", [(32, 16, 3, (1, 3, 16, 8)), (16, 32, 1, (1, 2, 16, 16)),
+                                               (64, 64, 3, (1, 2, 8, 8))])
+def test_conv3d_dgrad(impl, cin, cout, kd, shape):
+    n, d, h, w = shape
+    wt = bf16_round(randn(31, cout, cin, kd, 3, 3, scale=0.1))
+    dy = bf16_round(randn(32, n, cout, d, h, w))
+    x = torch.zeros(n, cin, d, h, w, requires_grad=True)
+    _conv_ref(x, wt, None, kd).backward(dy)
+    ref = x.grad
+    dyb = to_c8(dy.to(DEV))
+    dx = torch.empty((n, d, cin // 8, h, w, 8), dtype=torch.bfloat16, device=DEV)
+    if impl == "direct":
+        _call("fpl_conv3d_direct", _p(dyb), cout // 8, 0, _p(wt.to(DEV)), None, _p(dx), cin // 8, 0, None, n, d, h, w,
+              cout, cin, kd, 1, 0, _st())
+    else:
+        img = torch.empty(cin * cout * kd * 9, dtype=torch.bfloat16, device=DEV)
+        _call("fpl_conv3d_prep_weight", _p(wt.to(DEV)), cin, cout, kd, 1, _p(img), _st())
+        _call("fpl_conv3d_tc", _p(dyb), cout // 8, 0, _p(img), None, _p(dx), cin // 8, 0, None, n, d, h, w, cout, cin, kd, _st())
+    assert max_rel(from_c8(dx).cpu(), ref) < 6e-3
+
+
+@pytest.mark.parametrize("name", ["fpl_conv3d_wgrad", "fpl_conv3d_wgrad_mma"])
+@pytest.mark.parametrize("cin,cout,kd,shape", [(16, 16, 3, (2, 3, 16, 12)), (32, 16, 3, (1, 2, 8, 8)),
+                                               (16, 32, 1, (1, 2, 16, 16)), (64, 48, 3, (1, 2, 6, 10))])
+def test_conv3d_wgrad(name, cin, cout, kd, shape):
+    from fplplus_b200 import lib as L
+    if not hasattr(L.load(), name):
+        pytest.skip(name + " not built")
+    n, d, h, w = shape
+    x = bf16_round(randn(41, n, cin, d, h, w))
+    dy = bf16_round(randn(42, n, cout, d, h, w))
+    wt = torch.zeros(cout, cin, kd, 3, 3, requires_grad=True)
+    _conv_ref(x, wt, None, kd).backward(dy)
+    ref = wt.grad
+    dw = torch.zeros_like(ref, device=DEV)
+    _call(name, _p(to_c8(x.to(DEV))), cin // 8, 0, _p(to_c8(dy.to(DEV))), cout // 8, 0, _p(dw), n, d, h, w, cin, cout,
+          kd, _st())
+    assert max_rel(dw.cpu(), ref) < 1e-4
+    # accumulates
+    _call(name, _p(to_c8(x.to(DEV))), cin // 8, 0, _p(to_c8(dy.to(DEV))), cout // 8, 0, _p(dw), n, d, h, w, cin, cout,
+          kd, _st())
+    assert max_rel(dw.cpu(), 2 * ref) < 1e-4
+
+
+@pytest.mark.parametrize("cin,kd", [(1, 3), (3, 3), (1, 1)])
+def test_stem_conv_fwd_and_wgrad(cin, kd):
+    n, d, h, w, cout = 2, 3, 12, 20, 16
+    x = randn(51, n, cin, d, h, w)
+    wt = randn(52, cout, cin, kd, 3, 3, scale=0.2).requires_grad_(True)
+    b = randn(53, cout, scale=0.1)
+    ref = _conv_ref(x, wt, b, kd)
+    y = torch.empty((n, d, cout // 8, h, w, 8), dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
+    _call("fpl_stem_conv_fwd", _p(x.to(DEV)), _p(wt.detach().to(DEV)), _p(b.to(DEV)), _p(y), cout // 8, 0, _p(stats),
+          n, cin, d, h, w, cout, kd, _st())
+    assert max_rel(from_c8(y).cpu(), ref.detach()) < 6e-3
+    np.testing.assert_allclose(stats.cpu()[:cout], ref.detach().double().sum((0, 2, 3, 4)), rtol=1e-5, atol=1e-3)
+    dy = bf16_round(randn(54, n, cout, d, h, w))
+    ref.backward(dy)
+    dw = torch.zeros(cout, cin, kd, 3, 3, device=DEV)
+    _call("fpl_stem_conv_wgrad", _p(x.to(DEV)), _p(to_c8(dy.to(DEV))), cout // 8, 0, _p(dw), n, cin, d, h, w, cout, kd, _st())
+    assert max_rel(dw.cpu(), wt.grad) < 1e-4
+
+
+@pytest.mark.parametrize("classes", [2, 5])
+def test_head_conv_fwd_bwd(classes):
+    n, d, h, w, cin = 2, 3, 12, 16, 16
+    x = bf16_round(randn(61, n, cin, d, h, w)).requires_grad_(True)
+    wt = randn(62, classes, cin, 1, 3, 3, scale=0.2).requires_grad_(True)
+    b = randn(63, classes, scale=0.1).requires_grad_(True)
+    ref = F.conv3d(x, wt, b, padding=(0, 1, 1))
+    xb = to_c8(x.detach().to(DEV))
+    logits = torch.empty((n, classes, d, h, w), device=DEV)
+    _call("fpl_head_conv_fwd", _p(xb), cin // 8, 0, _p(wt.detach().to(DEV)), _p(b.detach().to(DEV)), _p(logits), n, d, h,
+          w, cin, classes, _st())
+    assert max_rel(logits.cpu(), ref.detach()) < 1e-5
+    g = randn(64, n, classes, d, h, w)
+    ref.backward(g)
+    dx = torch.empty((n, d, cin // 8, h, w, 8), dtype=torch.bfloat16, device=DEV)
+    dw = torch.zeros(classes, cin, 1, 3, 3, device=DEV)
+    db = torch.zeros(classes, device=DEV)
+    _call("fpl_head_conv_bwd", _p(xb), cin // 8, 0, _p(wt.detach().to(DEV)), _p(g.to(DEV)), _p(dx), cin // 8, 0, _p(dw),
+          _p(db), n, d, h, w, cin, classes, _st())
+    assert max_rel(from_c8(dx).cpu(), x.grad) < 6e-3
+    assert max_rel(dw.cpu(), wt.grad) < 1e-4
+    assert max_rel(db.cpu(), b.grad) < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,kd2", [(32, 16, 2), (64, 32, 1), (256, 128, 2)])
+def test_convt_k2s2_fwd_bwd(cin, cout, kd2):
+    n, d, h, w = 2, 2, 4, 6
+    x = bf16_round(randn(71, n, cin, d, h, w)).requires_grad_(True)
+    wt = randn(72, cin, cout, kd2, 2, 2, scale=0.2).requires_grad_(True)
+    b = randn(73, cout, scale=0.1).requires_grad_(True)
+    ref = F.conv_transpose3d(x, wt, b, stride=(kd2, 2, 2))
+    xb = to_c8(x.detach().to(DEV))
+    do, ho, wo = d * kd2, h * 2, w * 2
+    # written into the second half of a concat buffer
+    cat = torch.zeros((n, do, 2 * cout // 8, ho, wo, 8), dtype=torch.bfloat16, device=DEV)
+    _call("fpl_convt_k2s2_fwd", _p(xb), cin // 8, 0, _p(wt.detach().to(DEV)), _p(b.detach().to(DEV)), _p(cat),
+          2 * cout // 8, cout // 8, n, d, h, w, cin, cout, kd2, _st())
+    out = from_c8(cat).cpu()
+    assert max_rel(out[:, cout:], ref.detach()) < 6e-3
+    assert torch.all(out[:, :cout] == 0)
+    g = bf16_round(randn(74, n, cout, do, ho, wo))
+    ref.backward(g)
+    gcat = torch.cat([torch.zeros_like(g), g], 1)
+    dx = torch.empty((n, d, cin // 8, h, w, 8), dtype=torch.bfloat16, device=DEV)
+    dw = torch.zeros(cin, cout, kd2, 2, 2, device=DEV)
+    db = torch.zeros(cout, device=DEV)
+    _call("fpl_convt_k2s2_bwd", _p(xb), cin // 8, 0, _p(wt.detach().to(DEV)), _p(to_c8(gcat.to(DEV))), 2 * cout // 8,
+          cout // 8, _p(dx), cin // 8, 0, _p(dw), _p(db), n, d, h, w, cin, cout, kd2, _st())
+    assert max_rel(from_c8(dx).cpu(), x.grad) < 6e-3
+    assert max_rel(dw.cpu(), wt.grad) < 1e-4
+    assert max_rel(db.cpu(), b.grad) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------
+# DSBN + PReLU + dropout + pool
+# ------------------------------------------------------------------------------------------
+def _dense_mask_c8(mask_ncdhw):
+    """bool [N,C,D,H,W] -> uint8 in dense C8-planar element order."""
+    n, c, d, h, w = mask_ncdhw.shape
+    return mask_ncdhw.reshape(n, c // 8, 8, d, h, w).permute(0, 3, 1, 4, 5, 2).contiguous().to(torch.uint8)
+
+
+@pytest.mark.parametrize("training", [1, 0])
+@pytest.mark.parametrize("pool_kd,drop_p", [(0, 0.0), (2, 0.0), (1, 0.0), (0, 0.4)])
+def test_dsbn_act_fwd_bwd(training, pool_kd, drop_p):
+    n, c, d, h, w = 2, 16, 4, 8, 12
+    y = bf16_round(randn(81, n, c, d, h, w, scale=2.0) + 0.5).requires_grad_(True)
+    gamma = (randn(82, c, scale=0.3) + 1.0).requires_grad_(True)
+    beta = randn(83, c, scale=0.2).requires_grad_(True)
+    slope = torch.tensor([0.2], requires_grad=True)
+    rm, rv = randn(84, c, scale=0.1), randn(85, c, scale=0.1).abs() + 0.8
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    keep = torch.from_numpy(np.random.Generator(np.random.PCG64(86)).random((n, c, d, h, w)) >= drop_p)
+    z = F.batch_norm(y, rm_ref, rv_ref, gamma, beta, training=bool(training), momentum=0.1, eps=1e-5)
+    a = F.prelu(z, slope)
+    if drop_p > 0:
+        a = a * keep.float() / (1 - drop_p)
+    outs = [a]
+    if pool_kd:
+        outs.append(F.max_pool3d(bf16_round(a.detach()) + (a - a.detach()), (pool_kd, 2, 2), (pool_kd, 2, 2)))
+
+    yb = to_c8(y.detach().to(DEV))
+    stats = torch.stack([y.detach().double().sum((0, 2, 3, 4)), (y.detach().double() ** 2).sum((0, 2, 3, 4))]).flatten().to(DEV)
+    f32 = lambda: torch.zeros(c, device=DEV)
+    scale, shift, mean, invstd = f32(), f32(), f32(), f32()
+    rmd, rvd = rm.to(DEV), rv.to(DEV)
+    nbt = torch.zeros((), dtype=torch.int64, device=DEV)
+    cnt = n * d * h * w
+    _call("fpl_dsbn_finalize", _p(stats), cnt, _p(gamma.detach().to(DEV)), _p(beta.detach().to(DEV)), _p(rmd), _p(rvd),
+          _p(nbt), 0.1, 1e-5, training, _p(scale), _p(shift), _p(mean), _p(invstd), c, _st())
+    if training:
+        np.testing.assert_allclose(rmd.cpu(), rm_ref, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(rvd.cpu(), rv_ref, rtol=1e-5, atol=1e-6)
+        assert int(nbt) == 1
+    else:
+        assert int(nbt) == 0
+    act = torch.zeros((n, d, 2 * c // 8, h, w, 8), dtype=torch.bfloat16, device=DEV)   # first half of a concat buffer
+    mask = _dense_mask_c8(keep).to(DEV) if drop_p > 0 else None
+    pooled = idx = None
+    if pool_kd:
+        pooled = torch.empty((n, d // pool_kd, c // 8, h // 2, w // 2, 8), dtype=torch.bfloat16, device=DEV)
+        idx = torch.empty((n, d // pool_kd, c // 8, h // 2, w // 2, 8), dtype=torch.uint8, device=DEV)
+    sl = slope.detach().to(DEV)
+    _call("fpl_dsbn_act_fwd", _p(yb), _p(scale), _p(shift), _p(sl), _p(act), 2 * c // 8, 0, _p(pooled), c // 8, 0, _p(idx),
+          pool_kd, drop_p, _p(mask), 0, 0, n, d, h, w, c, _st())
+    got = from_c8(act).cpu()
+    assert max_rel(got[:, :c], a.detach()) < 6e-3
+    if pool_kd:
+        assert max_rel(from_c8(pooled).cpu(), outs[1].detach()) < 6e-3
+
+    # backward: gradient arrives through the activation (g1) and, when pooled, through the pool
+    g1 = bf16_round(randn(87, n, c, d, h, w))
+    loss = (a * g1).sum()
+    gp = None
+    if pool_kd:
+        gp = bf16_round(randn(88, *outs[1].shape))
+        loss = loss + (outs[1] * gp).sum()
+    loss.backward()
+    g1b = to_c8(torch.cat([g1, torch.zeros_like(g1)], 1).to(DEV))
+    gpb = to_c8(gp.to(DEV)) if pool_kd else None
+    red = torch.zeros(2 * c + 1, dtype=torch.float64, device=DEV)
+    common = (_p(yb), _p(g1b), 2 * c // 8, 0, _p(gpb), c // 8, 0, _p(idx), pool_kd, _p(scale), _p(shift), _p(mean),
+              _p(invstd), _p(sl), drop_p, _p(mask), 0, 0)
+    _call("fpl_dsbn_act_bwd_reduce", *common, _p(red), n, d, h, w, c, _st())
+    dy = torch.empty((n, d, c // 8, h, w, 8), dtype=torch.bfloat16, device=DEV)
+    _call("fpl_dsbn_act_bwd_apply", *common, _p(red), training, _p(dy), n, d, h, w, c, _st())
+    dgamma, dbeta, dslope, dbias = f32(), f32(), torch.zeros(1, device=DEV), f32()
+    _call("fpl_dsbn_bwd_finalize", _p(red), _p(scale), _p(invstd), training, _p(dgamma), _p(dbeta), _p(dslope), _p(dbias),
+          c, _st())
+    assert max_rel(from_c8(dy).cpu(), y.grad) < 1e-2
+    assert max_rel(dgamma.cpu(), gamma.grad) < 2e-3
+    assert max_rel(dbeta.cpu(), beta.grad) < 2e-3
+    assert max_rel(dslope.cpu(), slope.grad) < 2e-3
+
+
+def test_philox_dropout_statistics_and_backward_consistency():
+    n, c, d, h, w = 1, 32, 4, 16, 16
+    p = 0.3
+    yb = to_c8(torch.ones(n, c, d, h, w, device=DEV))
+    one, zero = torch.ones(c, device=DEV), torch.zeros(c, device=DEV)
+    sl = torch.tensor([0.25], device=DEV)
+    outs = []
+    for seed in (123, 123, 124):
+        act = torch.empty((n, d, c // 8, h, w, 8), dtype=torch.bfloat16, device=DEV)
+        _call("fpl_dsbn_act_fwd", _p(yb), _p(one), _p(zero), _p(sl), _p(act), c // 8, 0, None, 0, 0, None, 0, p, None,
+              seed, 16, n, d, h, w, c, _st())
+        outs.append(from_c8(act).cpu())
+    assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
+    kept = outs[0] != 0
+    assert abs(kept.float().mean().item() - (1 - p)) < 0.02
+    assert torch.allclose(outs[0][kept], torch.tensor(1 / (1 - p)), rtol=1e-2)
+    # per-channel keep rate is uniform too
+    assert (kept.float().mean((0, 2, 3, 4)) - (1 - p)).abs().max() < 0.06
+    # backward regenerates the same mask: dy is non-zero exactly where the forward kept the unit
+    g1 = to_c8(torch.ones(n, c, d, h, w, device=DEV))
+    red = torch.zeros(2 * c + 1, dtype=torch.float64, device=DEV)
+    dy = torch.empty((n, d, c // 8, h, w, 8), dtype=torch.bfloat16, device=DEV)
+    _call("fpl_dsbn_act_bwd_apply", _p(yb), _p(g1), c // 8, 0, None, 0, 0, None, 0, _p(one), _p(zero), _p(zero), _p(one),
+          _p(sl), p, None, 123, 16, _p(red), 0, _p(dy), n, d, h, w, c, _st())
+    assert torch.equal(from_c8(dy).cpu() != 0, kept)
+
+
+# ------------------------------------------------------------------------------------------
+# loss, filter, window kernels
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["c2", "c5"])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_dice_ce_against_golden_and_closed_form(golden_dir, tag, weighted):
+    import os
+    from oracle import losses
+    from fplplus_b200.loss import CrossEntropyLoss, DiceLoss, CombinedLoss
+    from fplplus_b200.registry import loss_dict
+    g = np.load(os.path.join(golden_dir, "loss.npz"))
+    z, y, pw = g[f"{tag}_logits"], g[f"{tag}_onehot"], g[f"{tag}_pw"]
+    wt = "w" if weighted else "u"
+    for name, cls in (("dice", DiceLoss), ("ce", CrossEntropyLoss)):
+        zt = torch.from_numpy(z).to(DEV).requires_grad_(True)
+        d = {"prediction": zt, "ground_truth": torch.from_numpy(y).to(DEV)}
+        if weighted:
+            d["pixel_weight"] = torch.from_numpy(pw).to(DEV)
+            d["image_weight"] = torch.ones(z.shape[0], dtype=torch.float64)
+        val = cls({})(d)
+        (val * 0.5).backward()
+        np.testing.assert_allclose(val.item(), float(g[f"{tag}_{name}_{wt}_loss"]), rtol=1e-5)
+        ref = g[f"{tag}_{name}_{wt}_grad"] * 0.5
+        np.testing.assert_allclose(zt.grad.cpu().numpy(), ref, rtol=2e-3, atol=1e-5 * np.abs(ref).max())
+    # combined 0.3*Dice + 0.7*CE through the CombinedLoss entry, against the float64 closed form
+    zt = torch.from_numpy(z).to(DEV).requires_grad_(True)
+    d = {"prediction": [zt], "ground_truth": torch.from_numpy(y).to(DEV)}
+    if weighted:
+        d["pixel_weight"] = torch.from_numpy(pw).to(DEV)
+    comb = CombinedLoss({"loss_type": ["DiceLoss", "CrossEntropyLoss"], "loss_weight": [0.3, 0.7]}, loss_dict)
+    val = comb(d)
+    val.backward()
+    lv, dz, _ = losses.dice_ce_closed_form(z, y, pw if weighted else None, 0.3, 0.7)
+    np.testing.assert_allclose(val.item(), lv, rtol=1e-5)
+    np.testing.assert_allclose(zt.grad.cpu().numpy(), dz, rtol=2e-3, atol=1e-5 * np.abs(dz).max())
+    hd = comb.last_hard_dice().cpu().numpy()
+    ref_hd = losses.hard_dice(torch.from_numpy(z), torch.from_numpy(y)).numpy()
+    np.testing.assert_allclose(hd, ref_hd, rtol=1e-6)
+
+
+def test_argmax_agreement_and_weight_folding_bit_exact():
+    from oracle import fpl_filter
+    from fplplus_b200 import fpl
+    r = np.random.Generator(np.random.PCG64(5))
+    for c in (2, 5):
+        za = (r.standard_normal((1, c, 6, 12, 20)) * 2).astype(np.float32)
+        zb = (za + r.standard_normal(za.shape) * 0.8).astype(np.float32)
+        za[0, :, 0, 0, :4] = 1.0                      # exact ties -> first index wins
+        la, lb, w, cnt = fpl.agreement_weight(torch.from_numpy(za).to(DEV), torch.from_numpy(zb).to(DEV))
+        ra, rb = fpl_filter.pseudo_label(za)[0], fpl_filter.pseudo_label(zb)[0]
+        np.testing.assert_array_equal(la.cpu().numpy(), ra)
+        np.testing.assert_array_equal(lb.cpu().numpy(), rb)
+        np.testing.assert_array_equal(fpl.pseudo_label(torch.from_numpy(za).to(DEV)).cpu().numpy()[0], ra)
+        ref_w = fpl_filter.agreement_weight_multiclass(ra, rb)
+        if c == 2:
+            np.testing.assert_array_equal(ref_w, fpl_filter.agreement_weight(ra, rb))
+        np.testing.assert_array_equal(w.cpu().numpy().astype(np.float64), ref_w)
+        assert int(cnt) == int((ra != rb).sum())
+        _, _, wf, _ = fpl.agreement_weight(torch.from_numpy(za).to(DEV), torch.from_numpy(zb).to(DEV), image_weight=0.37)
+        np.testing.assert_array_equal(wf.cpu().numpy(), fpl_filter.set_weight_(np.float32(0.37), ref_w.astype(np.float32)))
+
+
+def test_mc_uncertainty_against_reference_agent_golden(golden_dir):
+    """Same prepared MC logits as oracle/gen_golden_fpl.py fed the reference agent's infer()."""
+    import os
+    from oracle import fpl_filter
+    from oracle.gen_golden_fpl import CASES, fpl_case_logits
+    from fplplus_b200 import fpl
+    g = np.load(os.path.join(golden_dir, "fpl_infer.npz"))
+    table = {}
+    for name, seed, conf in CASES:
+        passes = fpl_case_logits(seed, confident=conf)
+        stats, umap = fpl.mc_uncertainty([torch.from_numpy(p).to(DEV) for p in passes], want_map=True)
+        ref = fpl_filter.mc_uncertainty(passes)
+        v, b = stats.tolist()
+        near = int((np.abs(ref["uncertainty_map"] - 0.01) < 1e-6).sum())
+        assert abs(int(b) - ref["boundary"]) <= near
+        np.testing.assert_allclose(v, float(ref["vars"]), rtol=1e-5)
+        np.testing.assert_allclose(umap.cpu().numpy(), ref["uncertainty_map"][0] if ref["uncertainty_map"].ndim == 4
+                                   else ref["uncertainty_map"], rtol=1e-4, atol=1e-7)
+        table[name] = [fpl.finish_uncertainty(stats)]
+    srt = fpl.sort_uncertainty(table)
+    assert [n for _v, n in srt] == [str(n) for n in g["names"]]                 # order incl. sentinel name ties
+    np.testing.assert_allclose([float(v[0]) for v, _n in srt], g["values"], rtol=1e-5)
+    assert [isinstance(v[0], int) for v, _n in srt] == list(g["is_sentinel"])
+
+
+def test_window_accumulate_flips_and_normalize():
+    b, c, vd, vh, vw = 1, 2, 6, 10, 12
+    out = torch.zeros(b, c, vd, vh, vw, device=DEV)
+    cnt = torch.zeros_like(out)
+    patch = randn(91, b, c, 4, 6, 8).to(DEV)
+    ref = torch.zeros(b, c, vd, vh, vw)
+    rc = torch.zeros_like(ref)
+    for (d0, h0, w0, fh, fw, s) in ((0, 0, 0, 0, 0, 1.0), (2, 4, 4, 1, 0, 0.5), (1, 2, 3, 1, 1, 2.0), (2, 0, 4, 0, 1, 1.0)):
+        _call("fpl_window_accumulate", _p(patch), _p(out), _p(cnt), b, c, vd, vh, vw, d0, h0, w0, 4, 6, 8, fh, fw, s, _st())
+        pp = patch.cpu()
+        dims = [d for d, f in ((-2, fh), (-1, fw)) if f]
+        if dims:
+            pp = torch.flip(pp, dims)
+        ref[:, :, d0:d0 + 4, h0:h0 + 6, w0:w0 + 8] += s * pp
+        rc[:, :, d0:d0 + 4, h0:h0 + 6, w0:w0 + 8] += 1
+    torch.testing.assert_close(out.cpu(), ref)
+    torch.testing.assert_close(cnt.cpu(), rc)
+    cnt.clamp_(min=1)
+    _call("fpl_window_normalize", _p(out), _p(cnt), 0.25, out.numel(), _st())
+    torch.testing.assert_close(out.cpu(), ref / rc.clamp(min=1) * 0.25)
+    from fplplus_b200 import lib as L
+    with pytest.raises(L.FplError):
+        _call("fpl_window_accumulate", _p(patch), _p(out), None, b, c, vd, vh, vw, 4, 0, 0, 4, 6, 8, 0, 0, 1.0, _st())
