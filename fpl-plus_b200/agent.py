@@ -1,0 +1,659 @@
+"""Host-side train/test agent of the hot path, mirroring PyMIC's ``net_run_dsbn`` plugin surface
+(reference: PyMIC/pymic/net_run_dsbn/agent_abstract.py:28-357, agent_seg.py:35-1065,
+util/parse_config.py:70-111, net_run/get_optimizer.py:9-57).
+
+Same names, same ``.cfg`` keys, same call order:
+
+* ``parse_config`` / ``synchronize_config``                      (util/parse_config.py:86-111)
+* ``SegmentationAgent(config, stage)`` with the plugin setters ``set_net_dict / set_loss_dict /
+  set_network / set_inferer / set_optimizer / set_scheduler / set_datasets``
+  (agent_abstract.py:67-134), ``create_network`` (agent_seg.py:82-105), ``create_optimizer``
+  (agent_abstract.py:320-337), ``create_loss_calculator`` (agent_seg.py:113-132),
+  ``get_loss_value`` (:134-142), ``training_all`` (:415-508), ``validation`` (:509-604),
+  ``train_valid`` (:689-831, same checkpoint dict / ``_latest.txt`` / ``_best.txt``), ``infer``
+  (:834-964, plain pseudo-label branch and the FPL branch with K=6 MC-dropout passes) and ``run``.
+
+What is different underneath (B200-first):
+
+* one process per GPU (``torchrun``): gradients of each backward are all-reduced over NCCL in
+  buckets that overlap the rest of the backward (``GradAllReducer``); inference shards volumes
+  round-robin over ranks with no communication except the final gather of ~100 scalars;
+* the train loop never synchronises per step: loss and hard-Dice counters accumulate on the
+  device and are read once per ``training_all`` round (the reference does 2 ``.item()``/``.cpu()``
+  syncs per step, agent_seg.py:476,495);
+* the FPL statistics / pseudo labels / agreement weights stay on the device (csrc/filter.cu); only
+  the uint8 label volume or two scalars per volume come back to the host;
+* file I/O (NIfTI through SimpleITK) and the CPU transform pipeline are out of scope: loaders are
+  any iterables of batch dicts (``set_loaders`` / ``set_datasets``); ``NpyVolumeDataset`` is the
+  minimal built-in for ``.npy`` volumes.
+
+As in the reference only ``training_all`` semantics train (``training()`` of the shipped
+``dual=False`` cfgs has no ``backward()``): ``dual`` is accepted and both values
+run the optimiser step.
+"""
+import configparser
+import copy
+import logging
+import os
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.optim import lr_scheduler
+
+from . import fpl
+from .inferer import Inferer
+from .loss import CombinedLoss, hard_dice_from_sums
+from .registry import loss_dict as _default_loss_dict
+from .registry import net_dict as _default_net_dict
+
+
+# ------------------------------------------------------------------------------------------
+# .cfg parsing (util/parse_config.py:7-111): INI, keys lower-cased, values type-sniffed
+# ------------------------------------------------------------------------------------------
+def _is_int(s):
+    body = s[1:] if s[:1] == '-' else s
+    return all('0' <= ch <= '9' for ch in body)
+
+
+def _is_float(s):
+    for sep in ('.', 'e'):
+        if sep in s:
+            parts = s.split(sep)
+            if sep == '.' and './' in s:
+                return False
+            if sep == 'e' and s[0] == 'e':
+                continue
+            return len(parts) == 2 and _is_int(parts[0]) and _is_int(parts[1])
+    return False
+
+
+def _scalar(s):
+    if _is_int(s):
+        return int(s)
+    if _is_float(s):
+        return float(s)
+    if s.lower() in ('true', 'false'):
+        return s.lower() == 'true'
+    if s.lower() == 'none':
+        return None
+    return s
+
+
+def parse_value_from_string(val_str):
+    if _is_int(val_str):
+        return int(val_str)
+    if _is_float(val_str):
+        return float(val_str)
+    if val_str[0] == '[' and val_str[-1] == ']':
+        return [_scalar(item.strip()) for item in val_str[1:-1].split(',')]
+    return _scalar(val_str)
+
+
+def parse_config(filename):
+    cp = configparser.ConfigParser()
+    cp.read(filename)
+    out = {}
+    for section in cp.sections():
+        out[section] = {}
+        for key in cp[section]:
+            val = str(cp[section][key])
+            if len(val) > 0:
+                out[section][key] = parse_value_from_string(val)
+    return out
+
+
+def synchronize_config(config):
+    config['dataset']['labeltoprobability_class_num'] = config['network']['class_num']
+    if 'PartialLabelToProbability' in (config['dataset'].get('train_transform') or []):
+        config['dataset']['partiallabeltoprobability_class_num'] = config['network']['class_num']
+    return config
+
+
+def seed_torch(seed=1):
+    """agent_abstract.py:13-26 (cudnn flags are irrelevant here: no cuDNN on the path)."""
+    import random
+    random.seed(seed)
+    os.environ['PYTHONHASHSEED'] = str(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed(seed)
+
+
+def keyword_match(a, b):
+    return a.lower() == b.lower()
+
+
+def get_optimizer(name, net_params, optim_params):
+    """net_run/get_optimizer.py:9-36 (the optimisers FPL+ configs select; coupled-L2 Adam)."""
+    lr = optim_params['learning_rate']
+    momentum = optim_params.get('momentum', 0.9)
+    weight_decay = optim_params.get('weight_decay', 0.0)
+    if keyword_match(name, "SGD"):
+        return torch.optim.SGD(net_params, lr, momentum=momentum, weight_decay=weight_decay)
+    if keyword_match(name, "Adam"):
+        return torch.optim.Adam(net_params, lr, weight_decay=weight_decay)
+    if keyword_match(name, "RMSprop"):
+        return torch.optim.RMSprop(net_params, lr, momentum=momentum, weight_decay=weight_decay)
+    raise ValueError("unsupported optimizer {0:}".format(name))
+
+
+def get_lr_scheduler(optimizer, sched_params):
+    """net_run/get_optimizer.py:39-57."""
+    name = sched_params.get("lr_scheduler")
+    if name is None:
+        return None
+    lr_gamma = sched_params["lr_gamma"]
+    if keyword_match(name, "ReduceLROnPlateau"):
+        patience = sched_params["reducelronplateau_patience"] / sched_params["iter_valid"]
+        return lr_scheduler.ReduceLROnPlateau(optimizer, mode="max", factor=lr_gamma, patience=patience)
+    if keyword_match(name, "MultiStepLR"):
+        return lr_scheduler.MultiStepLR(optimizer, sched_params["lr_milestones"], lr_gamma,
+                                        sched_params.get("last_iter", -1))
+    raise ValueError("unsupported lr scheduler {0:}".format(name))
+
+
+# ------------------------------------------------------------------------------------------
+# multi-GPU plumbing: one process per GPU, NCCL (gloo on CPU tests)
+# ------------------------------------------------------------------------------------------
+def dist_info():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+class GradAllReducer(object):
+    """Averages gradients over ranks while backward is still running.
+
+    ``UNet2D5_dsbn`` writes all gradients of one backward into ONE flat fp32 buffer in the order
+    backward completes them and calls ``grad_ready_hook(flat, start, end)`` whenever a further
+    prefix is final.  Ranges are coalesced into buckets of >= ``bucket_bytes`` and all-reduced
+    asynchronously (NCCL runs them on its own stream, NVLS over NVSwitch when available), so the
+    22.6 MB of gradients travel under the remaining backward kernels; ``finish`` waits for the
+    outstanding handles and applies the 1/world scale.  Parameters without gradients (2-D twins,
+    1x1 convs, the other domain's BN) are never touched: no unused-parameter search."""
+
+    def __init__(self, bucket_bytes=4 << 20, group=None):
+        self.bucket_bytes = bucket_bytes
+        self.group = group
+        self._pending = []
+        self._start = None
+
+    def hook(self, flat, start, end, last=False):
+        import torch.distributed as dist
+        if self._start is None:
+            self._start = start
+        if (end - self._start) * 4 >= self.bucket_bytes or last:
+            seg = flat[self._start:end]
+            seg.mul_(1.0 / dist.get_world_size(self.group))
+            self._pending.append(dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self._start = None
+
+    def finish(self):
+        for h in self._pending:
+            h.wait()
+        self._pending = []
+        self._start = None
+
+
+def shard_round_robin(items, rank, world):
+    """Volumes are independent (agent_seg.py:881 loop): rank r takes items r, r+world, ..."""
+    return [it for i, it in enumerate(items) if i % world == rank]
+
+
+# ------------------------------------------------------------------------------------------
+# minimal built-in dataset (file formats are out of scope; this covers .npy volumes)
+# ------------------------------------------------------------------------------------------
+class NpyVolumeDataset(torch.utils.data.Dataset):
+    """Rows of (image.npy[, label.npy[, pixel_weight.npy[, image_weight]]]) -> the batch-dict keys
+    the agent consumes (io/nifty_dataset.py:171-218): 'image' [C,D,H,W] fp32, 'label_prob'
+    [class,D,H,W] fp32, 'pixel_weight' [1,D,H,W] folded by set_weight_ (:165-168), 'image_weight',
+    'names'."""
+
+    def __init__(self, rows, class_num, root_dir=""):
+        self.rows, self.class_num, self.root = rows, class_num, root_dir
+
+    def __len__(self):
+        return len(self.rows)
+
+    def __getitem__(self, i):
+        row = self.rows[i]
+        img = np.load(os.path.join(self.root, row[0])).astype(np.float32)
+        if img.ndim == 3:
+            img = img[None]
+        sample = {'image': torch.from_numpy(img), 'names': row[0]}
+        if len(row) > 1 and row[1]:
+            lab = np.load(os.path.join(self.root, row[1]))
+            sample['label_prob'] = torch.from_numpy(
+                np.stack([lab == c for c in range(self.class_num)], 0).astype(np.float32))
+        if len(row) > 2 and row[2]:
+            w = np.load(os.path.join(self.root, row[2])).astype(np.float32)[None]
+            iw = float(row[3]) if len(row) > 3 else 1.0
+            w = np.where(w < 1, 0, w).astype(np.float32) * np.float32(iw)      # set_weight_
+            sample['pixel_weight'] = torch.from_numpy(w)
+            sample['image_weight'] = iw
+        return sample
+
+
+# ------------------------------------------------------------------------------------------
+# the agent
+# ------------------------------------------------------------------------------------------
+class SegmentationAgent(object):
+    def __init__(self, config, stage='train'):
+        assert stage in ['train', 'inference', 'test']
+        self.config = config
+        self.stage = 'test' if stage == 'inference' else stage
+        self.train_set = self.valid_set = self.test_set = None
+        self.net = self.optimizer = self.scheduler = None
+        self.net_dict, self.loss_dict = _default_net_dict, _default_loss_dict
+        self.inferer = None
+        self.loss_calculator = None
+        self.train_loaders = [None, None]
+        self.valid_loaders = [None, None]
+        self.test_loader = None
+        self.tensor_type = config.get('dataset', {}).get('tensor_type', 'float')
+        self.deterministic = config.get('training', {}).get('deterministic', True)
+        self.random_seed = config.get('training', {}).get('random_seed', 1)
+        if self.deterministic:
+            seed_torch(self.random_seed)
+        if self.tensor_type != 'float':
+            raise ValueError("fplplus_b200 supports tensor_type = float only (bf16 tensor-core path)")
+        self.rank, self.world = dist_info()
+        self.device = None
+        self.reducer = None
+        self.fpl_uda = config.get('training', {}).get('train_fpl_uda', False)
+        self.glob_it = 0
+        self.last_outputs = {}
+
+    # -- plugin setters (agent_abstract.py:67-134) -------------------------------------------
+    def set_datasets(self, train_set, valid_set, test_set):
+        self.train_set, self.valid_set, self.test_set = train_set, valid_set, test_set
+
+    def set_loaders(self, train=None, valid=None, test=None):
+        """train / valid: a loader or a [domain-1 loader, domain-2 loader] pair."""
+        def pair(x):
+            if x is None:
+                return [None, None]
+            return list(x) if isinstance(x, (list, tuple)) else [x, None]
+        if train is not None:
+            self.train_loaders = pair(train)
+        if valid is not None:
+            self.valid_loaders = pair(valid)
+        if test is not None:
+            self.test_loader = test
+
+    def set_network(self, net):
+        self.net = net
+
+    def set_net_dict(self, net_dict):
+        self.net_dict = net_dict
+
+    def set_loss_dict(self, loss_dict):
+        self.loss_dict = loss_dict
+
+    def set_optimizer(self, optimizer):
+        self.optimizer = optimizer
+
+    def set_scheduler(self, scheduler):
+        self.scheduler = scheduler
+
+    def set_inferer(self, inferer):
+        self.inferer = inferer
+
+    # -- construction --------------------------------------------------------------------------
+    def _pick_device(self, section):
+        if not torch.cuda.is_available():
+            raise RuntimeError("fplplus_b200 runs on CUDA (sm_100a) only: no GPU visible")
+        if self.world > 1:
+            dev = int(os.environ.get("LOCAL_RANK", self.rank))
+        else:
+            gpus = self.config.get(section, {}).get('gpus', [0])
+            dev = gpus[0] if isinstance(gpus, (list, tuple)) else int(gpus)
+        torch.cuda.set_device(dev)
+        self.device = torch.device("cuda:{0:}".format(dev))
+        return self.device
+
+    def create_dataset(self):
+        """agent_abstract.py:241-318: loaders come from set_loaders(), or are wrapped around the
+        datasets given to set_datasets() with the cfg's batch sizes."""
+        bs = self.config.get('dataset', {}).get('train_batch_size', 1)
+        if self.stage == 'train':
+            if self.train_loaders[0] is None and self.train_set is not None:
+                sets = self.train_set if isinstance(self.train_set, (list, tuple)) else [self.train_set]
+                self.train_loaders = [torch.utils.data.DataLoader(s, batch_size=bs, shuffle=True, drop_last=True)
+                                      for s in sets] + [None] * (2 - len(sets))
+            if self.valid_loaders[0] is None and self.valid_set is not None:
+                sets = self.valid_set if isinstance(self.valid_set, (list, tuple)) else [self.valid_set]
+                self.valid_loaders = [torch.utils.data.DataLoader(s, batch_size=1, shuffle=False) for s in sets] \
+                    + [None] * (2 - len(sets))
+        elif self.test_loader is None and self.test_set is not None:
+            self.test_loader = torch.utils.data.DataLoader(self.test_set, batch_size=1, shuffle=False)
+
+    def create_network(self):
+        if self.net is None:
+            net_name = self.config['network']['net_type']
+            if net_name not in self.net_dict:
+                raise ValueError("Undefined network {0:}".format(net_name))
+            self.net = self.net_dict[net_name](self.config['network'])
+        self.net.float()
+        n = sum(p.numel() for p in self.net.parameters() if p.requires_grad)
+        logging.info('parameter number {0:}'.format(n))
+
+    def get_parameters_to_update(self):
+        return self.net.parameters()
+
+    def create_optimizer(self, params):
+        opt_params = self.config['training']
+        if self.optimizer is None:
+            self.optimizer = get_optimizer(opt_params['optimizer'], params, opt_params)
+        last_iter = -1
+        if getattr(self, 'checkpoint', None) is not None:
+            self.optimizer.load_state_dict(self.checkpoint['optimizer_state_dict'])
+            last_iter = self.checkpoint['iteration'] - 1
+        if self.scheduler is None:
+            opt_params["last_iter"] = last_iter
+            self.scheduler = get_lr_scheduler(self.optimizer, opt_params)
+
+    def create_loss_calculator(self):
+        loss_name = self.config['training']['loss_type']
+        if isinstance(loss_name, (list, tuple)):
+            self.loss_calculator = CombinedLoss(self.config['training'], self.loss_dict)
+        elif loss_name not in self.loss_dict:
+            raise ValueError("Undefined loss function {0:}".format(loss_name))
+        else:
+            self.loss_calculator = self.loss_dict[loss_name](self.config['training'])
+
+    def get_loss_value(self, data, pred, gt, fpl_uda=False):
+        loss_input_dict = {'prediction': pred, 'ground_truth': gt}
+        if fpl_uda and data.get('pixel_weight', None) is not None:
+            loss_input_dict['pixel_weight'] = data['pixel_weight'].to(pred.device, non_blocking=True)
+            if data.get('image_weight', None) is not None:
+                loss_input_dict['image_weight'] = data['image_weight']
+        return self.loss_calculator(loss_input_dict)
+
+    # -- one optimiser step (agent_seg.py:459-495) -------------------------------------------
+    def _to_device(self, t):
+        return t.to(self.device, dtype=torch.float32, non_blocking=True)
+
+    def train_step(self, batches):
+        """zero_grad; for each domain d present: L_d = loss(net(x_d, d), y_d[, w_d]); L = mean_d L_d;
+        backward (gradient all-reduce overlapped when world > 1); optimizer.step; scheduler.step.
+        ``batches``: list indexed by domain of batch dicts (host or device tensors) or None.
+        Returns (loss tensor on the device, [hard-Dice tensor per domain]) -- no host sync."""
+        self.optimizer.zero_grad(set_to_none=True)
+        total, n_dom, dices = None, 0, []
+        for d, data in enumerate(batches):
+            if data is None:
+                continue
+            x = self._to_device(data['image'])
+            y = self._to_device(data['label_prob'])
+            out = self.net(x, domain_label=d * torch.ones(x.shape[0], dtype=torch.long))
+            loss_d = self.get_loss_value(data, out, y, self.fpl_uda)
+            total = loss_d if total is None else total + loss_d
+            n_dom += 1
+            hd = getattr(self.loss_calculator, "last_hard_dice", None)
+            dices.append(hd() if hd is not None else None)
+        loss = total / n_dom if n_dom > 1 else total
+        loss.backward()
+        if self.reducer is not None:
+            self.reducer.finish()
+        self.optimizer.step()
+        if self.scheduler is not None and not isinstance(self.scheduler, lr_scheduler.ReduceLROnPlateau):
+            self.scheduler.step()
+        return loss.detach(), dices
+
+    def _next(self, d, iters):
+        try:
+            return next(iters[d])
+        except StopIteration:
+            iters[d] = iter(self.train_loaders[d])
+            return next(iters[d])
+
+    def training_all(self):
+        iter_valid = self.config['training']['iter_valid']
+        n_dom = self.config['network']['num_domains']
+        self.net.train()
+        iters = [iter(self.train_loaders[d]) if self.train_loaders[d] is not None else None for d in range(2)]
+        loss_acc = torch.zeros((), dtype=torch.float32, device=self.device)
+        dice_acc = [None] * n_dom
+        for _it in range(iter_valid):
+            batches = [self._next(d, iters) if (d < n_dom and iters[d] is not None) else None for d in range(2)]
+            loss, dices = self.train_step(batches)
+            loss_acc += loss
+            k = 0
+            for d, b in enumerate(batches):
+                if b is None:
+                    continue
+                if dices[k] is not None:
+                    dice_acc[d] = dices[k] if dice_acc[d] is None else dice_acc[d] + dices[k]
+                k += 1
+        # ONE device->host read per round
+        train_avg_loss = float(loss_acc) / iter_valid / int(n_dom)
+        cls = [(a / iter_valid).cpu().numpy() for a in dice_acc if a is not None]
+        cls_dice = np.mean(np.stack(cls, 0), 0) if cls else np.zeros(self.config['network']['class_num'])
+        return {'loss': train_avg_loss, 'avg_dice': float(cls_dice.mean()), 'class_dice': cls_dice}
+
+    training = training_all     # the shipped training() never calls backward()
+
+    def validation(self):
+        class_num = self.config['network']['class_num']
+        n_dom = self.config['network']['num_domains']
+        if self.inferer is None:
+            infer_cfg = dict(self.config.get('testing', {}))
+            infer_cfg['class_num'] = class_num
+            self.inferer = Inferer(infer_cfg)
+        res = []
+        self.net.eval()
+        with torch.no_grad():
+            for d in range(n_dom):
+                losses, dices = [], []
+                loader = self.valid_loaders[d]
+                for data in (loader if loader is not None else []):
+                    x, y = self._to_device(data['image']), self._to_device(data['label_prob'])
+                    out = self.inferer.run(self.net, x, domain_label=d * torch.ones(x.shape[0], dtype=torch.long))
+                    losses.append(self.get_loss_value(data, out, y))
+                    for i in range(x.shape[0]):        # per-volume hard Dice (agent_seg.py:541-545)
+                        self.get_loss_value(data, out[i:i + 1].contiguous(), y[i:i + 1].contiguous())
+                        dices.append(self.loss_calculator.last_hard_dice())
+                if losses:
+                    res.append((torch.stack(losses).mean(), torch.stack(dices).mean(0)))
+        self.net.train()
+        if not res:
+            return {'loss': 0.0, 'avg_dice': 0.0, 'class_dice': np.zeros(class_num)}
+        host = [(float(l), c.cpu().numpy()) for l, c in res]
+        tr = self.config['training']
+        if tr.get('val_t2', False) and len(host) > 1:
+            pick = [host[1]]
+        elif tr.get('val_t1', False):
+            pick = [host[0]]
+        else:
+            pick = host
+        loss = float(np.mean([h[0] for h in pick]))
+        cls = np.mean(np.stack([h[1] for h in pick], 0), 0)
+        scal = {'loss': loss, 'avg_dice': float(cls.mean()), 'class_dice': cls}
+        if isinstance(self.scheduler, lr_scheduler.ReduceLROnPlateau):
+            self.scheduler.step(scal['avg_dice'])
+        return scal
+
+    # -- train/valid driver with the reference's checkpoint protocol (agent_seg.py:689-831) ----
+    def _ckpt_names(self):
+        ckpt_dir = self.config['training']['ckpt_save_dir']
+        prefix = self.config['training'].get('ckpt_prefix', None)
+        if prefix is None:
+            prefix = ckpt_dir.split('/')[-1]
+        return ckpt_dir, prefix
+
+    def train_valid(self):
+        tr = self.config['training']
+        self.dual = tr.get('dual', True)
+        self.fpl_uda = tr.get('train_fpl_uda', False)
+        self._pick_device('training')
+        self.net.to(self.device)
+        if self.world > 1:
+            self.reducer = GradAllReducer()
+            self.net.grad_ready_hook = self.reducer.hook
+        ckpt_dir, prefix = self._ckpt_names()
+        iter_start, iter_max, iter_valid = tr['iter_start'], tr['iter_max'], tr['iter_valid']
+        iter_save = tr.get('iter_save', None)
+        early_stop_it = tr.get('early_stop_patience', None)
+        if iter_save is None:
+            iter_save_list = [iter_max]
+        elif isinstance(iter_save, (tuple, list)):
+            iter_save_list = iter_save
+        else:
+            iter_save_list = range(0, iter_max + 1, iter_save)
+        self.max_val_dice, self.max_val_it, self.best_model_wts, self.checkpoint = 0.0, 0, None, None
+        if iter_start > 0:
+            name = "{0:}/{1:}_{2:}.pt".format(ckpt_dir, prefix, iter_start)
+            self.checkpoint = torch.load(name, map_location=self.device, weights_only=False)
+            self.checkpoint['valid_pred'] = 0
+            self.net.load_state_dict(self.checkpoint['model_state_dict'])
+            self.max_val_it = iter_start
+            self.best_model_wts = self.checkpoint['model_state_dict']
+        self.create_optimizer(self.get_parameters_to_update())
+        self.create_loss_calculator()
+        if self.rank == 0:
+            os.makedirs(ckpt_dir, exist_ok=True)
+        self.glob_it = iter_start
+        history = []
+        for it in range(iter_start, iter_max, iter_valid):
+            lr_value = self.optimizer.param_groups[0]['lr']
+            t0 = time.time()
+            train_scalars = self.training_all()
+            t1 = time.time()
+            valid_scalars = self.validation()
+            t2 = time.time()
+            self.glob_it = it + iter_valid
+            logging.info("it {0:} lr {1:} train loss {2:.4f} dice {3:.4f} | valid loss {4:.4f} dice {5:.4f} | "
+                         "{6:.2f}s/{7:.2f}s".format(self.glob_it, lr_value, train_scalars['loss'],
+                                                    train_scalars['avg_dice'], valid_scalars['loss'],
+                                                    valid_scalars['avg_dice'], t1 - t0, t2 - t1))
+            history.append((self.glob_it, train_scalars, valid_scalars))
+            if valid_scalars['avg_dice'] > self.max_val_dice or self.best_model_wts is None:
+                self.max_val_dice = valid_scalars['avg_dice']
+                self.max_val_it = self.glob_it
+                self.best_model_wts = copy.deepcopy(self.net.state_dict())
+            stop_now = early_stop_it is not None and self.glob_it - self.max_val_it > early_stop_it
+            if (self.glob_it in iter_save_list or stop_now) and self.rank == 0:
+                torch.save({'iteration': self.glob_it, 'valid_pred': valid_scalars['avg_dice'],
+                            'model_state_dict': self.net.state_dict(),
+                            'optimizer_state_dict': self.optimizer.state_dict()},
+                           "{0:}/{1:}_{2:}.pt".format(ckpt_dir, prefix, self.glob_it))
+                with open("{0:}/{1:}_latest.txt".format(ckpt_dir, prefix), 'wt') as f:
+                    f.write(str(self.glob_it))
+            if stop_now:
+                logging.info("The training is early stopped")
+                break
+        if self.rank == 0:
+            torch.save({'iteration': self.max_val_it, 'valid_pred': self.max_val_dice,
+                        'model_state_dict': self.best_model_wts,
+                        'optimizer_state_dict': self.optimizer.state_dict()},
+                       "{0:}/{1:}_{2:}.pt".format(ckpt_dir, prefix, self.max_val_it))
+            with open("{0:}/{1:}_best.txt".format(ckpt_dir, prefix), 'wt') as f:
+                f.write(str(self.max_val_it))
+        return history
+
+    def get_checkpoint_name(self):
+        ckpt_mode = self.config['testing']['ckpt_mode']
+        if ckpt_mode in (0, 1):
+            ckpt_dir, prefix = self._ckpt_names()
+            txt = ckpt_dir + '/' + prefix + ("_latest.txt" if ckpt_mode == 0 else "_best.txt")
+            with open(txt, 'r') as f:
+                it_num = f.read().replace('\n', '')
+            return "{0:}/{1:}_{2:}.pt".format(ckpt_dir, prefix, it_num)
+        return self.config['testing']['ckpt_name']
+
+    # -- inference / pseudo labels / FPL image weights (agent_seg.py:834-964) -------------------
+    def infer(self, load_checkpoint=True):
+        te = self.config['testing']
+        domain = te['domian_label']                 # (sic) the reference's key
+        self.FPL = te.get('fpl', False)
+        device = self._pick_device('testing')
+        self.net.to(device)
+        if te.get('evaluation_mode', True):
+            self.net.eval()
+            if te.get('test_time_dropout', False) or self.FPL:
+                def test_time_dropout(m):
+                    if type(m) == nn.Dropout:
+                        m.train()
+                self.net.apply(test_time_dropout)
+        if load_checkpoint:
+            ckpt_name = self.get_checkpoint_name()
+            if isinstance(ckpt_name, (tuple, list)):
+                raise ValueError("ckpt_mode 3 (multi-checkpoint ensemble) is outside the hot path")
+            checkpoint = torch.load(ckpt_name, map_location=device, weights_only=False)
+            self.net.load_state_dict(checkpoint['model_state_dict'])
+        if self.inferer is None:
+            infer_cfg = dict(te)
+            infer_cfg['class_num'] = self.config['network']['class_num']
+            self.inferer = Inferer(infer_cfg)
+        k_passes = te.get('fpl_mc_passes', 6)       # hard-coded 6 in the reference (:898)
+        uncertainty_list, pending = {}, []
+        outputs = {}
+        volumes = list(self.test_loader)
+        with torch.no_grad():
+            for data in shard_round_robin(volumes, self.rank, self.world):
+                images = self._to_device(data['image'])
+                names = data['names']
+                name = names[0] if isinstance(names, (list, tuple)) else names
+                dl = domain * torch.ones(images.shape[0], dtype=torch.long)
+                if self.FPL:
+                    passes = [self.inferer.run(self.net, images, domain_label=dl) for _ in range(k_passes)]
+                    stats, _ = fpl.mc_uncertainty(passes)
+                    pending.append((name, stats))          # stays on the device until the loop ends
+                else:
+                    pred = self.inferer.run(self.net, images, domain_label=dl)
+                    outputs[name] = fpl.pseudo_label(pred)
+        if self.FPL:
+            for name, stats in pending:
+                uncertainty_list[name] = [fpl.finish_uncertainty(stats)]
+            uncertainty_list = self._gather_dict(uncertainty_list)
+            srt = fpl.sort_uncertainty(uncertainty_list)
+            path = te.get('fpl_uncertainty_sorted', None)
+            if path and self.rank == 0:
+                np.save(path, np.asarray(srt, dtype=object))
+            self.last_outputs = {'uncertainty_sorted': srt}
+            return srt
+        self.last_outputs = {k: v.cpu().numpy() for k, v in outputs.items()}
+        self.save_outputs(self.last_outputs)
+        return self.last_outputs
+
+    def _gather_dict(self, d):
+        if self.world == 1:
+            return d
+        import torch.distributed as dist
+        parts = [None] * self.world
+        dist.all_gather_object(parts, d)
+        merged = {}
+        for p in parts:
+            merged.update(p)
+        return merged
+
+    def save_outputs(self, outputs):
+        """uint8 label volumes -> ``output_dir/<name>.npy`` (NIfTI writing needs SimpleITK: out of scope)."""
+        out_dir = self.config['testing'].get('output_dir', None)
+        if not out_dir:
+            return
+        os.makedirs(out_dir, exist_ok=True)
+        for name, lab in outputs.items():
+            base = os.path.basename(str(name))
+            for ext in ('.nii.gz', '.nii', '.npy'):
+                if base.endswith(ext):
+                    base = base[:-len(ext)]
+            np.save(os.path.join(out_dir, base + '.npy'), lab)
+
+    def run(self):
+        self.create_dataset()
+        self.create_network()
+        if self.stage == 'train':
+            return self.train_valid()
+        return self.infer()
+
+
+def pixel_weights_from_pseudo_labels(logits_tgt, logits_src, image_weight=None):
+    """Stage 3 of the FPL+ recipe on the device (data/get_pixel_weight.py:12-28 on the two
+    Inferer outputs of one target volume): labels of both passes, agreement weight, count."""
+    return fpl.agreement_weight(logits_tgt, logits_src, image_weight=image_weight)

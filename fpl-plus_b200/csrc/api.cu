@@ -15,6 +15,14 @@ void fpl_set_error(const char* fmt, ...) {
 
 extern "C" const char* fpl_last_error(void) { return g_err; }
 
+unsigned long long g_fpl_launches = 0;
+
+extern "C" long long fpl_launch_count(int reset) {
+    unsigned long long v = __atomic_load_n(&g_fpl_launches, __ATOMIC_RELAXED);
+    if (reset) __atomic_store_n(&g_fpl_launches, 0ull, __ATOMIC_RELAXED);
+    return (long long)v;
+}
+
 extern "C" int fpl_version(void) { return 100; }
 
 extern "C" int fpl_device_is_sm100(void) {

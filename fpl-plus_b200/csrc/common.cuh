@@ -27,7 +27,14 @@ void fpl_set_error(const char* fmt, ...);
         }                                                                                 \
     } while (0)
 
-#define FPL_LAUNCH_CHECK() FPL_CHECK_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this macro: it bumps the launch counter that
+// fpl_launch_count() reports (bench.py's "gpu_launches") and surfaces launch errors
+extern unsigned long long g_fpl_launches;
+#define FPL_LAUNCH_CHECK()                                                                \
+    do {                                                                                  \
+        __atomic_fetch_add(&g_fpl_launches, 1ull, __ATOMIC_RELAXED);                      \
+        FPL_CHECK_CUDA(cudaGetLastError());                                               \
+    } while (0)
 
 // ---- 16-byte bf16x8 vectors ----------------------------------------------------------
 struct __align__(16) bf16x8 {

@@ -18,6 +18,7 @@ _U = c_uint64
 _SIGNATURES = {
     "fpl_last_error": (c_char_p, []),
     "fpl_version": (_I, []),
+    "fpl_launch_count": (c_longlong, [_I]),
     "fpl_device_is_sm100": (_I, []),
     "fpl_debug_set": (None, [_I, _I]),
     "fpl_conv3d_weight_image_bytes": (_L, [_I, _I, _I]),
@@ -70,9 +71,26 @@ def load():
     return _lib
 
 
+#: optional per-call instrumentation: a callable(name, args) -> context token with .stop(); bench.py
+#: installs one that brackets selected entry points with CUDA events on the launching stream
+_call_timer = None
+
+
+def set_call_timer(fn):
+    global _call_timer
+    _call_timer = fn
+
+
 def call(name, *args):
     """Invoke a C-ABI function; a non-zero status raises FplError with the library's message."""
     lib = load()
+    tok = _call_timer(name, args) if _call_timer is not None else None
     rc = getattr(lib, name)(*args)
+    if tok is not None:
+        tok.stop()
     if rc != 0:
         raise FplError("%s failed (%d): %s" % (name, rc, lib.fpl_last_error().decode()))
+
+
+def launch_count(reset=False):
+    return int(load().fpl_launch_count(1 if reset else 0))

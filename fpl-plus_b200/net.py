@@ -161,7 +161,7 @@ class UNet2D5_dsbn(nn.Module):
         self._img_cache = {}
         self._dropout_masks = None      # {unit name: uint8 keep mask, dense C8-planar order} (parity tests)
         self._rng_offset = 0
-        self.grad_ready_hook = None     # callable(flat_grad, start, end) fired as buckets complete (DDP)
+        self.grad_ready_hook = None     # callable(flat_grad, start, end, last) fired as buckets complete (DDP)
         self._build_plan()
 
     # -- plan -------------------------------------------------------------------------------
@@ -417,7 +417,7 @@ class UNet2D5_dsbn(nn.Module):
             if self.grad_ready_hook is not None:
                 end = offs[n_params_done - 1] + sizes[n_params_done - 1]
                 if end > fired[0]:
-                    self.grad_ready_hook(flat, fired[0], end)
+                    self.grad_ready_hook(flat, fired[0], end, n_params_done == len(params))
                     fired[0] = end
 
         small = _SmallPool(ws, "bwd", dlogits.device)
@@ -467,7 +467,7 @@ class UNet2D5_dsbn(nn.Module):
             done += 10
             fire(done)
         assert done == len(params)
-        return [grads[p] for p in params]
+        return [grads[p].view(p.shape) for p in params]
 
 
 class _SmallPool(object):

@@ -28,6 +28,9 @@ extern "C" {
 
 const char* fpl_last_error(void);
 int fpl_version(void);
+/* Number of kernels this library has launched in the process so far (reset != 0 zeroes it).
+ * Instrumentation only (bench.py reports it as "gpu_launches"); no reference counterpart. */
+long long fpl_launch_count(int reset);
 /* 1 when the running device is sm_100 (tcgen05 kernels usable), else 0. */
 int fpl_device_is_sm100(void);
 /* debugging knobs of the tensor-core conv (key 0: swap LBO/SBO of the UMMA descriptors). */
