@@ -57,6 +57,31 @@ __device__ __forceinline__ bf16x8 float_to_bf16x8(const float* f) {
     return r;
 }
 
+// one 128-bit store of 8 floats rounded to bf16 (the struct assignment above compiles to four
+// 32-bit stores; the epilogues and streaming kernels want a single STG.128)
+__device__ __forceinline__ void st_bf16x8(void* p, const float* f) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(f[4], f[5]), d = __floats2bfloat162_rn(f[6], f[7]);
+    uint4 v = make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b),
+                         *reinterpret_cast<uint32_t*>(&c), *reinterpret_cast<uint32_t*>(&d));
+    *reinterpret_cast<uint4*>(p) = v;
+}
+
+// Transposing butterfly: every lane enters with 32 values w[0..31] (static indexing); on return
+// lane L holds in w[0] the sum over the 32 lanes of w[L].  31 shuffles instead of 32 x 5.
+__device__ __forceinline__ void warp_transpose_sum32(float* w, int lane) {
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            float send = upper ? w[i] : w[i + half];
+            float keep = upper ? w[i + half] : w[i];
+            w[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+}
+
 __device__ __forceinline__ bf16x8 ldg_bf16x8(const void* p) {
     int4 t = __ldg(reinterpret_cast<const int4*>(p));
     return *reinterpret_cast<bf16x8*>(&t);

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(128) conv3d_direct_kernel(ConvP P) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] += P.bias[co8 * 8 + i];
     }
-    if (active) P.y[(((int64_t)n * P.D + d) * P.y_c8tot + P.y_c8off + co8) * HW + hw] = float_to_bf16x8(acc);
+    if (active) st_bf16x8(&P.y[(((int64_t)n * P.D + d) * P.y_c8tot + P.y_c8off + co8) * HW + hw], acc);
     if (P.stats != nullptr) {
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(128) stem_conv_fwd_kernel(StemP P) {
                 }
             }
         }
-        P.y[(((int64_t)n * P.D + d) * P.y_c8tot + P.y_c8off + co8) * HW + hw] = float_to_bf16x8(acc);
+        st_bf16x8(&P.y[(((int64_t)n * P.D + d) * P.y_c8tot + P.y_c8off + co8) * HW + hw], acc);
     }
     if (P.stats != nullptr) {
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(128) head_conv_dgrad_kernel(HeadP P) {
             }
         }
     }
-    P.dx[((int64_t)nd * P.dx_c8tot + P.dx_c8off + ci8) * HW + hw] = float_to_bf16x8(acc);
+    st_bf16x8(&P.dx[((int64_t)nd * P.dx_c8tot + P.dx_c8off + ci8) * HW + hw], acc);
 }
 
 // wgrad + bias grad: block = (row group, plane); thread = (cls, ci, tap) element
@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(128) convt_fwd_kernel(ConvTP P) {
             for (int i = 0; i < 8; ++i) acc[i] = fmaf(xf[ci], wp[i], acc[i]);
         }
     }
-    P.y[(((int64_t)n * Do + dq) * P.y_c8tot + P.y_c8off + co8) * ((int64_t)Ho * Wo) + (int64_t)ho * Wo + wo] = float_to_bf16x8(acc);
+    st_bf16x8(&P.y[(((int64_t)n * Do + dq) * P.y_c8tot + P.y_c8off + co8) * ((int64_t)Ho * Wo) + (int64_t)ho * Wo + wo], acc);
 }
 
 // dgrad: thread = low-res voxel x 8 ci; loops the kd2*4 positions and all co
@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(128) convt_dgrad_kernel(ConvTP P) {
             }
         }
     }
-    P.dx[((int64_t)nd * P.dx_c8tot + P.dx_c8off + ci8) * HW + hw] = float_to_bf16x8(acc);
+    st_bf16x8(&P.dx[((int64_t)nd * P.dx_c8tot + P.dx_c8off + ci8) * HW + hw], acc);
 }
 
 }  // namespace

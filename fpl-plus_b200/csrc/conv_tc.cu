@@ -18,6 +18,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 #include "../../include/fplplus_b200.h"
 
 namespace {
@@ -63,93 +64,8 @@ bool make_config(int cin, int cout, TcConfig& c) {
     int cols = 2 * c.nb;
     c.tmem_cols = 32;
     while (c.tmem_cols < cols) c.tmem_cols *= 2;
-    c.smem_bytes = c.stages * c.stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + 2 * 2 * c.nb * (int)sizeof(float);
+    c.smem_bytes = c.stages * c.stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + cout * (int)sizeof(float) + 16;
     return true;
-}
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// no-swizzle K-major shared memory matrix descriptor (SM100 format, version field = 1)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
 }
 
 struct TcParams {
@@ -192,7 +108,7 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
     uint64_t* tmem_full = bars + 2 * kMaxStages;
     uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
-    float* stat_sm = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);   // [2][nb] (sum, sumsq)
+    float* bias_sm = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);   // [cout], 16-byte aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pad_d = P.kd / 2;
@@ -204,7 +120,7 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
-    for (int i = threadIdx.x; i < 2 * P.nb; i += kNumThreads) stat_sm[i] = 0.0f;
+    for (int i = threadIdx.x; i < P.cout; i += kNumThreads) bias_sm[i] = P.bias != nullptr ? P.bias[i] : 0.0f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -235,67 +151,83 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.nb >> 3) << 17) | (8u << 24);
-            const uint32_t a_lbo = P.dbg_swap_lbo_sbo ? kBoxW * 16 : kPlaneBytes;
-            const uint32_t a_sbo = P.dbg_swap_lbo_sbo ? kPlaneBytes : kBoxW * 16;
-            const uint32_t b_lbo = P.dbg_swap_lbo_sbo ? 128 : P.nb * 16;
-            const uint32_t b_sbo = P.dbg_swap_lbo_sbo ? P.nb * 16 : 128;
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
-                TileCoord c = decode_tile(P, t);
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.nb);
-                uint32_t accumulate = 0;
-                for (int q = 0; q < P.nchunks; ++q) {
-                    for (int kdi = 0; kdi < P.kd; ++kdi) {
-                        int dz = c.d + kdi - pad_d;
-                        if (dz < 0 || dz >= P.D) continue;
-                        mbar_wait(&full_bar[stage], phase);
-                        tc_fence_after();
-                        const uint32_t a_base = smem_u32(smem + (size_t)stage * stage_bytes);
-                        const uint32_t b_base = a_base + P.a_bytes;
-                        const int ksteps = P.kc / 16;
-#pragma unroll 1
+        // ===================== MMA issuer: the whole warp runs the loop (uniform), one lane issues =====================
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.nb >> 3) << 17) | (8u << 24);
+        const uint32_t a_lbo = P.dbg_swap_lbo_sbo ? kBoxW * 16 : kPlaneBytes;
+        const uint32_t a_sbo = P.dbg_swap_lbo_sbo ? kPlaneBytes : kBoxW * 16;
+        const uint32_t b_lbo = P.dbg_swap_lbo_sbo ? 128 : P.nb * 16;
+        const uint32_t b_sbo = P.dbg_swap_lbo_sbo ? P.nb * 16 : 128;
+        // descriptors = constant high part + (smem byte address >> 4) in the low 14 bits
+        const uint64_t a_hi = make_desc(0, a_lbo, a_sbo), b_hi = make_desc(0, b_lbo, b_sbo);
+        const uint32_t smem_u = smem_u32(smem) >> 4;
+        const uint32_t b_tap_step = (uint32_t)((P.kc / 8) * P.nb);        // 16-byte units between taps of B
+        const uint32_t b_k_step = (uint32_t)(2 * P.nb);                   // ... between 16-channel K steps
+        const int ksteps = P.kc / 16;
+        const bool leader = elect_one();
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+            TileCoord c = decode_tile(P, t);
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.nb);
+            uint32_t accumulate = 0;
+            for (int q = 0; q < P.nchunks; ++q) {
+                for (int kdi = 0; kdi < P.kd; ++kdi) {
+                    int dz = c.d + kdi - pad_d;
+                    if (dz < 0 || dz >= P.D) continue;
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u + (uint32_t)(((size_t)stage * stage_bytes) >> 4);
+                    const uint32_t b_base = a_base + (uint32_t)(P.a_bytes >> 4);
+                    for (int j = 0; j < ksteps; ++j) {
+                        const uint32_t a_j = a_base + (uint32_t)j * (2 * kPlaneBytes / 16);
+                        const uint32_t b_j = b_base + (uint32_t)j * b_k_step;
+#pragma unroll
                         for (int t9 = 0; t9 < 9; ++t9) {
-                            const uint32_t a_tap = a_base + (uint32_t)(((t9 / 3) * kBoxW + (t9 % 3)) * 16);
-                            const uint32_t b_tap = b_base + (uint32_t)(t9 * (P.kc / 8) * P.nb * 16);
-                            for (int j = 0; j < ksteps; ++j) {
-                                uint64_t adesc = make_desc(a_tap + (uint32_t)(j * 2 * kPlaneBytes), a_lbo, a_sbo);
-                                uint64_t bdesc = make_desc(b_tap + (uint32_t)(j * 2 * P.nb * 16), b_lbo, b_sbo);
-                                umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
-                                accumulate = 1;
-                            }
+                            const uint64_t adesc = a_hi | (uint64_t)(a_j + (uint32_t)((t9 / 3) * kBoxW + (t9 % 3)));
+                            const uint64_t bdesc = b_hi | (uint64_t)(b_j + (uint32_t)t9 * b_tap_step);
+                            if (leader) umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+                            accumulate = 1;
                         }
-                        umma_commit(&empty_bar[stage]);      // smem slot reusable once these MMAs retire
-                        if (++stage == P.stages) { stage = 0; phase ^= 1; }
                     }
+                    if (leader) umma_commit(&empty_bar[stage]);      // smem slot reusable once these MMAs retire
+                    __syncwarp();
+                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full[acc]);                // accumulator ready for the epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
+            if (leader) umma_commit(&tmem_full[acc]);                // accumulator ready for the epilogue
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
+        // thread = one output voxel (TMEM lane); per 16-channel chunk: +bias, one 2 x 128-bit bf16 store,
+        // and the BatchNorm partial sums through a transposing butterfly (lane L ends up owning channel
+        // L of the sum, lane 16+L of the sum of squares).  The per-lane totals stay in registers across
+        // all tiles of a slice and reach global memory once per slice (double atomics).
         const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;
         const int hl = row / kTileW, wl = row % kTileW;
         int acc = 0; uint32_t acc_phase = 0;
         int cur_slice = -1;
+        constexpr int kMaxChunks = 8;                        // nb <= 128
+        float run[kMaxChunks];
+#pragma unroll
+        for (int k = 0; k < kMaxChunks; ++k) run[k] = 0.0f;
+        const bool want_stats = P.stats != nullptr;
+        const int nchunk16 = P.nb / 16;
         for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
             TileCoord c = decode_tile(P, t);
-            if (P.stats != nullptr && c.slice != cur_slice) {
+            if (want_stats && c.slice != cur_slice) {
                 if (cur_slice >= 0) {
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    for (int i = threadIdx.x - 64; i < 2 * P.nb; i += 128) {
-                        int ch = i % P.nb, which = i / P.nb;
-                        atomicAdd(P.stats + which * P.cout + cur_slice * P.nb + ch, (double)stat_sm[i]);
-                        stat_sm[i] = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < kMaxChunks; ++k) {
+                        if (k < nchunk16) {
+                            atomicAdd(P.stats + (lane >> 4) * P.cout + cur_slice * P.nb + k * 16 + (lane & 15), (double)run[k]);
+                            run[k] = 0.0f;
+                        }
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
                 }
                 cur_slice = c.slice;
             }
@@ -307,31 +239,35 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
             const int64_t out_base = (((int64_t)c.n * P.D + c.d) * P.y_c8tot + P.y_c8off + (c.slice * P.nb) / 8) * HW +
                                      (int64_t)h * P.W + w;
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P.nb);
-            for (int c0 = 0; c0 < P.nb; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(t_row + (uint32_t)c0, r);
-                tmem_ld_wait();
-                float v[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    v[i] = __uint_as_float(r[i]);
-                    if (P.bias != nullptr) v[i] += __ldg(P.bias + c.slice * P.nb + c0 + i);
-                }
-                if (valid) {
-                    P.y[out_base + (int64_t)(c0 / 8) * HW] = float_to_bf16x8(v);
-                    P.y[out_base + (int64_t)(c0 / 8 + 1) * HW] = float_to_bf16x8(v + 8);
-                }
-                if (P.stats != nullptr) {
+            for (int k = 0; k < kMaxChunks; ++k) {
+                if (k < nchunk16) {
+                    const int c0 = k * 16;
+                    uint32_t r[16];
+                    tmem_ld16(t_row + (uint32_t)c0, r);
+                    tmem_ld_wait();
+                    float v[32];
+                    const float4* b4 = reinterpret_cast<const float4*>(bias_sm + c.slice * P.nb + c0);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float s = valid ? v[i] : 0.0f;
-                        float q2 = s * s;
-                        s = warp_sum(s);
-                        q2 = warp_sum(q2);
-                        if (lane == 0) {
-                            atomicAdd(&stat_sm[c0 + i], s);
-                            atomicAdd(&stat_sm[P.nb + c0 + i], q2);
+                    for (int i = 0; i < 4; ++i) {
+                        float4 bb = b4[i];
+                        v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bb.x;
+                        v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
+                        v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z;
+                        v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
+                    }
+                    if (valid) {
+                        st_bf16x8(P.y + out_base + (int64_t)(c0 / 8) * HW, v);
+                        st_bf16x8(P.y + out_base + (int64_t)(c0 / 8 + 1) * HW, v + 8);
+                    }
+                    if (want_stats) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            v[i] = valid ? v[i] : 0.0f;
+                            v[16 + i] = v[i] * v[i];
                         }
+                        warp_transpose_sum32(v, lane);
+                        run[k] += v[0];
                     }
                 }
             }
@@ -340,12 +276,11 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (P.stats != nullptr && cur_slice >= 0) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int i = threadIdx.x - 64; i < 2 * P.nb; i += 128) {
-                int ch = i % P.nb, which = i / P.nb;
-                atomicAdd(P.stats + which * P.cout + cur_slice * P.nb + ch, (double)stat_sm[i]);
-            }
+        if (want_stats && cur_slice >= 0) {
+#pragma unroll
+            for (int k = 0; k < kMaxChunks; ++k)
+                if (k < nchunk16)
+                    atomicAdd(P.stats + (lane >> 4) * P.cout + cur_slice * P.nb + k * 16 + (lane & 15), (double)run[k]);
         }
     }
     tc_fence_before();
@@ -380,22 +315,6 @@ __global__ void prep_weight_kernel(const float* __restrict__ w, __nv_bfloat16* i
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (fn == nullptr) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
 }  // namespace
 
 extern "C" int64_t fpl_conv3d_weight_image_bytes(int cin, int cout, int kd) {
@@ -420,8 +339,10 @@ extern "C" int fpl_conv3d_prep_weight(const float* w, int cin, int cout, int kd,
 }
 
 static int g_dbg_swap = 0;
-extern "C" void fpl_debug_set(int key, int value) {
-    if (key == 0) g_dbg_swap = value;
+void fpl_wgrad_debug_set(int key, long long value);
+extern "C" void fpl_debug_set(int key, long long value) {
+    if (key == 0) g_dbg_swap = (int)value;
+    if (key >= 10) fpl_wgrad_debug_set(key, value);
 }
 
 extern "C" int fpl_conv3d_tc(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias, void* y,

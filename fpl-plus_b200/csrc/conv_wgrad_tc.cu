@@ -1,0 +1,310 @@
+// Weight gradient of nn.Conv3d k(kd,3,3) "same" (autograd of PyMIC/pymic/net/net3d/unet2d5_dsbn.py:75,79)
+// on the 5th-gen tensor cores:  dW[co][ci][kd][kh][kw] += sum_v dy[v][co] * x[v + tap][ci].
+//
+// GEMM view (the reduction runs over VOXELS, so both operands are MN-major):
+//   D[(kd,ci)][co] (+)= A[(kd,ci)][16 voxels] * B[16 voxels][co]          one tcgen05.mma per (kh,kw) tap
+//   * the C8-planar activation layout ([..][C/8][H][W][8] bf16) is exactly the canonical no-swizzle
+//     MN-major UMMA core matrix: 8 consecutive voxels of a W row x 8 channels = 128 contiguous bytes.
+//     One K step = two such row segments one tile row apart (LBO = row pitch); channel groups (and the
+//     kd depth planes, landed back to back by ONE 5-D TMA box with zero fill outside the volume) are the
+//     M groups at a uniform stride (SBO = halo'd plane bytes).
+//   * the 9 in-plane taps are the SAME shared-memory tile read through descriptors whose start address is
+//     shifted by (kh*pitch + kw*16) bytes; each tap owns its own TMEM accumulator (9*N columns).
+//   * a CTA keeps its accumulators in TMEM across ALL the voxel tiles of its split-K slice and touches
+//     global memory once at the end (fp32 atomics into dW).
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2..5 epilogue.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "../../include/fplplus_b200.h"
+
+namespace {
+
+constexpr int kThreadsW = 192;
+constexpr int kMaxStagesW = 8;
+constexpr int kSmemBudgetW = 220 * 1024;
+
+struct WgCfg {
+    int th, tw;            // tile rows (even) / cols (multiple of 8)
+    int nkd;               // depth taps per M tile (kd or 1)
+    int c8chunk;           // channel groups per M tile and depth tap
+    int mtiles_c, mtiles_kd;
+    int m;                 // UMMA M (64 or 128)
+    int nb, nchunks;       // UMMA N, number of N chunks
+    int plane_x, plane_dy; // bytes of one channel-group plane in the x / dy tile
+    int dy_off;            // offset of the dy tile inside a stage (x bytes rounded up to 128)
+    int x_bytes, dy_bytes, stage_bytes, stages, pad_bytes, smem_bytes;
+    int tmem_cols;
+};
+
+bool make_wg_cfg(int h, int w, int cin, int cout, int kd, int allow_m64, WgCfg& c) {
+    if (cin % 8 != 0 || cout % 16 != 0 || cin <= 0 || cout <= 0) return false;
+    c.tw = w >= 32 ? 32 : (w >= 16 ? 16 : 8);
+    c.th = h >= 8 ? 8 : ((h + 1) / 2) * 2;
+    const int g_all = cin / 8;
+    if (kd * g_all <= 16) { c.nkd = kd; c.c8chunk = g_all; c.mtiles_kd = 1; c.mtiles_c = 1; }
+    else {
+        c.nkd = 1; c.mtiles_kd = kd;
+        c.c8chunk = g_all < 16 ? g_all : 16;
+        if (g_all % c.c8chunk != 0) return false;
+        c.mtiles_c = g_all / c.c8chunk;
+    }
+    const int groups = c.nkd * c.c8chunk;
+    c.m = (groups <= 8 && allow_m64) ? 64 : 128;
+    c.nb = cout % 32 == 0 ? 32 : 16;
+    c.nchunks = cout / c.nb;
+    if (groups > 8 && c.tw == 32 && cin >= 32 && h * w >= 128 * 128) c.tw = 16;   // keep >= 3 stages at full resolution
+    c.plane_x = (c.th + 2) * (c.tw + 2) * 16;
+    c.plane_dy = c.th * c.tw * 16;
+    c.x_bytes = groups * c.plane_x;
+    c.dy_bytes = (c.nb / 8) * c.plane_dy;
+    c.dy_off = ((c.x_bytes + 127) / 128) * 128;
+    c.stage_bytes = ((c.dy_off + c.dy_bytes + 127) / 128) * 128;
+    // the M=64/128 operand reads 8/16 channel-group planes from the tile start: keep that window inside the allocation
+    int over = (c.m / 8 + 1) * c.plane_x - c.stage_bytes;
+    c.pad_bytes = over > 0 ? ((over + 127) / 128) * 128 : 0;
+    c.stages = (kSmemBudgetW - c.pad_bytes - 2048) / c.stage_bytes;
+    if (c.stages > kMaxStagesW) c.stages = kMaxStagesW;
+    if (c.stages < 2) return false;
+    c.smem_bytes = c.stages * c.stage_bytes + c.pad_bytes + 1024 + 256;
+    int cols = 9 * c.nb;
+    c.tmem_cols = 32;
+    while (c.tmem_cols < cols) c.tmem_cols *= 2;
+    return c.tmem_cols <= 512;
+}
+
+struct WgParams {
+    float* dw;
+    float* dump;           // debug: raw accumulators [9][128 lanes][nb] of CTA 0 (may be NULL)
+    int N, D, H, W, cin, cout, kd;
+    int x_c8off, dy_c8off;
+    int th, tw, nkd, c8chunk, mtiles_c, mtiles_kd, m, nb, nchunks;
+    int plane_x, plane_dy, x_bytes, dy_off, stage_bytes, stages, tmem_cols;
+    int tiles_h, tiles_w, tiles_total, split;
+    int swap_lbo_sbo, m64_quadrant_layout;
+};
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+
+struct WgWork {
+    int mt_kd, mt_c, nc, slice;
+};
+
+__device__ __forceinline__ WgWork decode_work(const WgParams& P, int b) {
+    WgWork w;
+    w.slice = b % P.split; b /= P.split;
+    w.nc = b % P.nchunks; b /= P.nchunks;
+    w.mt_c = b % P.mtiles_c;
+    w.mt_kd = b / P.mtiles_c;
+    return w;
+}
+
+__global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                                   const __grid_constant__ CUtensorMap dymap, WgParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // barriers live in front of the stage ring so that operand over-reads past the last stage stay in the pad
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kMaxStagesW;
+    uint64_t* done_bar = bars + 2 * kMaxStagesW;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStagesW + 1);
+    uint8_t* ring = smem + 256;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const WgWork wk = decode_work(P, blockIdx.x);
+    const int tile_begin = (int)(((int64_t)P.tiles_total * wk.slice) / P.split);
+    const int tile_end = (int)(((int64_t)P.tiles_total * (wk.slice + 1)) / P.split);
+    const int pad_d = P.kd / 2;
+    const int kd0 = P.mtiles_kd > 1 ? wk.mt_kd : 0;          // first depth tap of this M tile
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&dymap) : "memory");
+        for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(done_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = tile_begin; t < tile_end; ++t) {
+                int r = t;
+                const int tw_i = r % P.tiles_w; r /= P.tiles_w;
+                const int th_i = r % P.tiles_h; r /= P.tiles_h;
+                const int d = r % P.D;
+                const int n = r / P.D;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* x_dst = ring + (size_t)stage * P.stage_bytes;
+                uint8_t* dy_dst = x_dst + P.dy_off;
+                mbar_expect_tx(&full_bar[stage], (uint32_t)(P.x_bytes + (P.nb / 8) * P.plane_dy));
+                tma_load_5d(x_dst, &xmap, &full_bar[stage], 2 * (tw_i * P.tw - 1), th_i * P.th - 1,
+                            P.x_c8off + wk.mt_c * P.c8chunk, d + kd0 - pad_d, n);
+                tma_load_5d(dy_dst, &dymap, &full_bar[stage], 2 * (tw_i * P.tw), th_i * P.th,
+                            P.dy_c8off + wk.nc * (P.nb / 8), d, n);
+                if (++stage == P.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer: the whole warp runs the loop (uniform), one lane issues =====================
+        // kind::f16, bf16 x bf16 -> fp32, A and B both MN-major (bits 15, 16)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(P.nb >> 3) << 17) | ((uint32_t)(P.m >> 4) << 24);
+        const uint32_t pitch_x = (uint32_t)(P.tw + 2) * 16, pitch_dy = (uint32_t)P.tw * 16;
+        const uint32_t a_lbo = P.swap_lbo_sbo ? (uint32_t)P.plane_x : pitch_x;
+        const uint32_t a_sbo = P.swap_lbo_sbo ? pitch_x : (uint32_t)P.plane_x;
+        const uint32_t b_lbo = P.swap_lbo_sbo ? (uint32_t)P.plane_dy : pitch_dy;
+        const uint32_t b_sbo = P.swap_lbo_sbo ? pitch_dy : (uint32_t)P.plane_dy;
+        // descriptors = constant high part + (smem byte address >> 4) in the low 14 bits
+        const uint64_t a_hi = make_desc(0, a_lbo, a_sbo), b_hi = make_desc(0, b_lbo, b_sbo);
+        uint32_t tap_off[9];                                  // (kh*pitch + kw*16) >> 4
+#pragma unroll
+        for (int t9 = 0; t9 < 9; ++t9) tap_off[t9] = ((uint32_t)(t9 / 3) * pitch_x + (uint32_t)(t9 % 3) * 16) >> 4;
+        const uint32_t ring_u = smem_u32(ring);
+        const bool leader = elect_one();
+        int stage = 0; uint32_t phase = 0;
+        uint32_t accumulate = 0;
+        for (int t = tile_begin; t < tile_end; ++t) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t x_base = (ring_u + (uint32_t)stage * (uint32_t)P.stage_bytes) >> 4;
+            const uint32_t dy_base = x_base + ((uint32_t)P.dy_off >> 4);
+            for (int hp = 0; hp < P.th / 2; ++hp) {
+                const uint32_t a_row = x_base + (((uint32_t)(2 * hp) * pitch_x) >> 4);
+                const uint32_t b_row = dy_base + (((uint32_t)(2 * hp) * pitch_dy) >> 4);
+                for (int j = 0; j < P.tw / 8; ++j) {
+                    const uint64_t bdesc = b_hi | (uint64_t)(b_row + (uint32_t)j * 8);
+                    const uint32_t a_col = a_row + (uint32_t)j * 8;
+#pragma unroll
+                    for (int t9 = 0; t9 < 9; ++t9) {
+                        const uint64_t adesc = a_hi | (uint64_t)(a_col + tap_off[t9]);
+                        if (leader) umma_bf16(tmem_base + (uint32_t)(t9 * P.nb), adesc, bdesc, idesc, accumulate);
+                    }
+                    accumulate = 1;
+                }
+            }
+            if (leader) umma_commit(&empty_bar[stage]);
+            __syncwarp();
+            if (++stage == P.stages) { stage = 0; phase ^= 1; }
+        }
+        if (leader) umma_commit(done_bar);
+        __syncwarp();
+    } else if (tile_end > tile_begin) {
+        // ===================== epilogue: TMEM -> fp32 atomics into dW =====================
+        const int quarter = warp & 3;
+        mbar_wait(done_bar, 0);
+        tc_fence_after();
+        const int T = P.kd * 9;
+        const int tlane = quarter * 32 + lane;               // TMEM lane this thread reads
+        int row;                                             // M row held by that lane
+        if (P.m == 128 || !P.m64_quadrant_layout) row = tlane;
+        else row = (lane < 16) ? quarter * 16 + lane : -1;   // M=64: 16 rows per 32-lane quadrant
+        bool valid = row >= 0 && row < P.m;
+        int kdi = 0, ci = 0;
+        if (valid) {
+            const int g = row >> 3;
+            valid = g < P.nkd * P.c8chunk;
+            kdi = kd0 + g / P.c8chunk;
+            ci = (wk.mt_c * P.c8chunk + g % P.c8chunk) * 8 + (row & 7);
+        }
+        for (int t9 = 0; t9 < 9; ++t9) {
+            for (int c0 = 0; c0 < P.nb; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t9 * P.nb + c0), r);
+                tmem_ld_wait();
+                if (P.dump != nullptr && blockIdx.x == 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) P.dump[((int64_t)t9 * 128 + tlane) * P.nb + c0 + i] = __uint_as_float(r[i]);
+                }
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int co = wk.nc * P.nb + c0 + i;
+                        atomicAdd(P.dw + ((int64_t)co * P.cin + ci) * T + kdi * 9 + t9, __uint_as_float(r[i]));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+    }
+}
+
+int g_wg_swap = 0, g_wg_allow_m64 = 1, g_wg_m64_quadrant = 1;
+float* g_wg_dump = nullptr;
+
+CUresult encode_5d(EncodeTiledFn encode, CUtensorMap* map, const void* base, int n, int d, int c8tot, int h, int w,
+                   int box_w, int box_h, int box_c8, int box_d) {
+    // 8-byte elements (4 bf16 channels) so that a 34-voxel halo row fits the 256-element box limit
+    cuuint64_t gdim[5] = {(cuuint64_t)w * 2, (cuuint64_t)h, (cuuint64_t)c8tot, (cuuint64_t)d, (cuuint64_t)n};
+    cuuint64_t gstr[4] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16, (cuuint64_t)c8tot * h * w * 16,
+                          (cuuint64_t)d * c8tot * h * w * 16};
+    cuuint32_t box[5] = {(cuuint32_t)box_w * 2, (cuuint32_t)box_h, (cuuint32_t)box_c8, (cuuint32_t)box_d, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+}  // namespace
+
+// debug knobs (keys 10..13), see fpl_debug_set
+void fpl_wgrad_debug_set(int key, long long value) {
+    if (key == 10) g_wg_swap = (int)value;
+    if (key == 11) g_wg_allow_m64 = (int)value;
+    if (key == 12) g_wg_m64_quadrant = (int)value;
+    if (key == 13) g_wg_dump = reinterpret_cast<float*>(value);
+}
+
+extern "C" int fpl_conv3d_wgrad_tc(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
+                                   float* dw, int n, int d, int h, int w, int cin, int cout, int kd, void* stream) {
+    FPL_REQUIRE(kd == 1 || kd == 3, "fpl_conv3d_wgrad_tc: kd=%d must be 1 or 3", kd);
+    WgCfg c;
+    FPL_REQUIRE(make_wg_cfg(h, w, cin, cout, kd, g_wg_allow_m64, c),
+                "fpl_conv3d_wgrad_tc: unsupported shape (cin %d, cout %d, %dx%d)", cin, cout, h, w);
+    FPL_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0,
+                "fpl_conv3d_wgrad_tc: x/dy must be 16-byte aligned");
+    EncodeTiledFn encode = get_encode_fn();
+    FPL_REQUIRE(encode != nullptr, "fpl_conv3d_wgrad_tc: cuTensorMapEncodeTiled not available from the driver");
+    CUtensorMap xmap, dymap;
+    CUresult r = encode_5d(encode, &xmap, x, n, d, x_c8tot, h, w, c.tw + 2, c.th + 2, c.c8chunk, c.nkd);
+    FPL_REQUIRE(r == CUDA_SUCCESS, "fpl_conv3d_wgrad_tc: tensor map (x) failed (%d)", (int)r);
+    r = encode_5d(encode, &dymap, dy, n, d, dy_c8tot, h, w, c.tw, c.th, c.nb / 8, 1);
+    FPL_REQUIRE(r == CUDA_SUCCESS, "fpl_conv3d_wgrad_tc: tensor map (dy) failed (%d)", (int)r);
+    WgParams P;
+    P.dw = dw; P.dump = g_wg_dump;
+    P.N = n; P.D = d; P.H = h; P.W = w; P.cin = cin; P.cout = cout; P.kd = kd;
+    P.x_c8off = x_c8off; P.dy_c8off = dy_c8off;
+    P.th = c.th; P.tw = c.tw; P.nkd = c.nkd; P.c8chunk = c.c8chunk; P.mtiles_c = c.mtiles_c; P.mtiles_kd = c.mtiles_kd;
+    P.m = c.m; P.nb = c.nb; P.nchunks = c.nchunks; P.plane_x = c.plane_x; P.plane_dy = c.plane_dy; P.x_bytes = c.x_bytes; P.dy_off = c.dy_off;
+    P.stage_bytes = c.stage_bytes; P.stages = c.stages; P.tmem_cols = c.tmem_cols;
+    P.tiles_h = (h + c.th - 1) / c.th; P.tiles_w = (w + c.tw - 1) / c.tw;
+    int64_t tiles = (int64_t)P.tiles_h * P.tiles_w * d * n;
+    FPL_REQUIRE(tiles < (1ll << 30), "fpl_conv3d_wgrad_tc: too many tiles");
+    P.tiles_total = (int)tiles;
+    const int pairs = c.mtiles_kd * c.mtiles_c * c.nchunks;
+    int split = FPL_NUM_SMS / pairs;
+    if (split < 1) split = 1;
+    if (split > P.tiles_total) split = P.tiles_total;
+    P.split = split;
+    P.swap_lbo_sbo = g_wg_swap; P.m64_quadrant_layout = g_wg_m64_quadrant;
+    FPL_CHECK_CUDA(cudaFuncSetAttribute(conv3d_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
+    conv3d_wgrad_tc_kernel<<<pairs * split, kThreadsW, c.smem_bytes, (cudaStream_t)stream>>>(xmap, dymap, P);
+    FPL_LAUNCH_CHECK();
+    return 0;
+}

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kThreads) dsbn_act_fwd_kernel(ActParams P) {
             f[i] = ((keep >> i) & 1u) ? a * keep_scale : 0.0f;
         }
         int64_t o = (nd * P.a_c8tot + P.a_c8off + c8) * HW + hw;
-        P.a[o] = float_to_bf16x8(f);
+        st_bf16x8(&P.a[o], f);
     }
 }
 
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kThreads) dsbn_act_pool_fwd_kernel(ActParams P
                         f[i] = z > 0.0f ? z : slope * z;
                     }
                     bf16x8 outv = float_to_bf16x8(f);
-                    P.a[dst + ww] = outv;
+                    st_bf16x8(&P.a[dst + ww], f);
                     // compare on the bf16-rounded values (what backward and the next layer see)
                     bf16x8_to_float(outv, f);
                     uint32_t k = (uint32_t)((dd * 2 + hh) * 2 + ww);
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kThreads) dsbn_act_pool_fwd_kernel(ActParams P
             }
         }
         int64_t po = (((int64_t)n * D2 + d2) * P.p_c8tot + P.p_c8off + c8) * HW2 + (int64_t)h2 * W2 + w2;
-        P.pooled[po] = float_to_bf16x8(best);
+        st_bf16x8(&P.pooled[po], best);
         uint2 packed;
         packed.x = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
         packed.y = code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24);
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(kThreads) dsbn_act_bwd_kernel(ActBwdParams P) 
                     o[i] = sc[i] * dz[i];
                 }
             }
-            P.dy[v] = float_to_bf16x8(o);
+            st_bf16x8(&P.dy[v], o);
         }
     }
     if (!APPLY) {

@@ -20,12 +20,13 @@ _SIGNATURES = {
     "fpl_version": (_I, []),
     "fpl_launch_count": (c_longlong, [_I]),
     "fpl_device_is_sm100": (_I, []),
-    "fpl_debug_set": (None, [_I, _I]),
+    "fpl_debug_set": (None, [_I, c_longlong]),
     "fpl_conv3d_weight_image_bytes": (_L, [_I, _I, _I]),
     "fpl_conv3d_prep_weight": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "fpl_conv3d_tc": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _P] + [_I] * 7 + [_P]),
     "fpl_conv3d_direct": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _P] + [_I] * 9 + [_P]),
     "fpl_conv3d_wgrad": (_I, [_P, _I, _I, _P, _I, _I, _P] + [_I] * 7 + [_P]),
+    "fpl_conv3d_wgrad_tc": (_I, [_P, _I, _I, _P, _I, _I, _P] + [_I] * 7 + [_P]),
     "fpl_stem_conv_fwd": (_I, [_P, _P, _P, _P, _I, _I, _P] + [_I] * 7 + [_P]),
     "fpl_stem_conv_wgrad": (_I, [_P, _P, _I, _I, _P] + [_I] * 7 + [_P]),
     "fpl_head_conv_fwd": (_I, [_P, _I, _I, _P, _P, _P] + [_I] * 6 + [_P]),

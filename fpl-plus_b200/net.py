@@ -391,10 +391,9 @@ class UNet2D5_dsbn(nn.Module):
         return C8(dx)
 
     def _wgrad(self, u, xin, dy, dw, n, d, h, w):
-        impl = os.environ.get("FPL_WGRAD_IMPL", "mma")
-        lib = ops._lib.load()
-        if impl == "mma" and hasattr(lib, "fpl_conv3d_wgrad_mma") and u.cin % 16 == 0 and u.cout % 16 == 0:
-            call("fpl_conv3d_wgrad_mma", *xin.args(), ptr(dy), u.cout // 8, 0, ptr(dw), n, d, h, w, u.cin, u.cout,
+        impl = os.environ.get("FPL_WGRAD_IMPL", "tc")
+        if impl == "tc" and u.cin % 8 == 0 and u.cout % 16 == 0 and ops.is_sm100():
+            call("fpl_conv3d_wgrad_tc", *xin.args(), ptr(dy), u.cout // 8, 0, ptr(dw), n, d, h, w, u.cin, u.cout,
                  u.kd, stream_ptr())
         else:
             call("fpl_conv3d_wgrad", *xin.args(), ptr(dy), u.cout // 8, 0, ptr(dw), n, d, h, w, u.cin, u.cout, u.kd,

@@ -33,8 +33,9 @@ int fpl_version(void);
 long long fpl_launch_count(int reset);
 /* 1 when the running device is sm_100 (tcgen05 kernels usable), else 0. */
 int fpl_device_is_sm100(void);
-/* debugging knobs of the tensor-core conv (key 0: swap LBO/SBO of the UMMA descriptors). */
-void fpl_debug_set(int key, int value);
+/* debugging knobs of the tensor-core kernels (key 0: swap LBO/SBO of the fwd UMMA descriptors;
+ * 10: same for wgrad; 11: allow UMMA M=64 in wgrad; 12: M=64 TMEM lane layout; 13: raw-accumulator dump pointer). */
+void fpl_debug_set(int key, long long value);
 
 /* ---- (a) conv3d: PyMIC/pymic/net/net3d/unet2d5_dsbn.py:75,79 (nn.Conv3d k3 p1 / k(1,3,3) p(0,1,1)) ---- */
 
@@ -64,6 +65,12 @@ int fpl_conv3d_direct(const void* x, int x_c8tot, int x_c8off, const float* w, c
 /* wgrad: dW[Cout][Cin][kd][3][3] (fp32, ACCUMULATED into) = sum_v dy[v] (x) x[v+tap]. */
 int fpl_conv3d_wgrad(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
                      float* dw, int n, int d, int h, int w, int cin, int cout, int kd, void* stream);
+
+/* The same contract on tcgen05 (both operands MN-major straight from the C8-planar layout, the 9
+ * in-plane taps as shifted descriptors of one TMA-staged halo tile, accumulators resident in TMEM over
+ * the CTA's whole split-K slice).  Needs cin % 8 == 0 and cout % 16 == 0. */
+int fpl_conv3d_wgrad_tc(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
+                        float* dw, int n, int d, int h, int w, int cin, int cout, int kd, void* stream);
 
 /* stem: image fp32 NCDHW (in_chns <= 8) -> C8-planar bf16, conv k3 p1 + bias + stats. */
 int fpl_stem_conv_fwd(const float* x, const float* w, const float* bias, void* y, int y_c8tot, int y_c8off,

@@ -152,7 +152,7 @@ def test_conv3d_dgrad(impl, cin, cout, kd, shape):
     assert max_rel(from_c8(dx).cpu(), ref) < 6e-3
 
 
-@pytest.mark.parametrize("name", ["fpl_conv3d_wgrad", "fpl_conv3d_wgrad_mma"])
+@pytest.mark.parametrize("name", ["fpl_conv3d_wgrad", "fpl_conv3d_wgrad_tc"])
 @pytest.mark.parametrize("cin,cout,kd,shape", [(16, 16, 3, (2, 3, 16, 12)), (32, 16, 3, (1, 2, 8, 8)),
                                                (16, 32, 1, (1, 2, 16, 16)), (64, 48, 3, (1, 2, 6, 10))])
 def test_conv3d_wgrad(name, cin, cout, kd, shape):
