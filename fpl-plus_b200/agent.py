@@ -126,15 +126,23 @@ def keyword_match(a, b):
     return a.lower() == b.lower()
 
 
-def get_optimizer(name, net_params, optim_params):
-    """net_run/get_optimizer.py:9-36 (the optimisers FPL+ configs select; coupled-L2 Adam)."""
+def get_optimizer(name, net_params, optim_params, capturable=False):
+    """net_run/get_optimizer.py:9-36 (the optimisers FPL+ configs select; coupled-L2 Adam).
+    ``capturable``: Adam keeps its step counter and learning rate on the device so that the whole
+    optimiser step can live inside a CUDA graph."""
     lr = optim_params['learning_rate']
     momentum = optim_params.get('momentum', 0.9)
     weight_decay = optim_params.get('weight_decay', 0.0)
     if keyword_match(name, "SGD"):
         return torch.optim.SGD(net_params, lr, momentum=momentum, weight_decay=weight_decay)
     if keyword_match(name, "Adam"):
-        return torch.optim.Adam(net_params, lr, weight_decay=weight_decay)
+        params = list(net_params)
+        # same update rule (coupled L2); on CUDA use torch's single-launch multi-tensor implementation
+        fused = len(params) > 0 and all(p.is_cuda for p in params)
+        if fused and capturable:
+            lr = torch.tensor(float(lr), dtype=torch.float32, device=params[0].device)
+            return torch.optim.Adam(params, lr, weight_decay=weight_decay, fused=True, capturable=True)
+        return torch.optim.Adam(params, lr, weight_decay=weight_decay, fused=fused)
     if keyword_match(name, "RMSprop"):
         return torch.optim.RMSprop(net_params, lr, momentum=momentum, weight_decay=weight_decay)
     raise ValueError("unsupported optimizer {0:}".format(name))
@@ -267,6 +275,11 @@ class SegmentationAgent(object):
         self.fpl_uda = config.get('training', {}).get('train_fpl_uda', False)
         self.glob_it = 0
         self.last_outputs = {}
+        # B200-first: the whole optimiser step (both forwards, loss, backward, gradient all-reduce, Adam)
+        # is captured once per batch signature into a CUDA graph and replayed ([training] cuda_graph, default on)
+        self.use_cuda_graph = bool(config.get('training', {}).get('cuda_graph', True))
+        self._graphs = {}
+        self._host_it = 0
 
     # -- plugin setters (agent_abstract.py:67-134) -------------------------------------------
     def set_datasets(self, train_set, valid_set, test_set):
@@ -348,14 +361,25 @@ class SegmentationAgent(object):
     def create_optimizer(self, params):
         opt_params = self.config['training']
         if self.optimizer is None:
-            self.optimizer = get_optimizer(opt_params['optimizer'], params, opt_params)
+            self._graph_capable = (self.use_cuda_graph and keyword_match(opt_params['optimizer'], "Adam")
+                                   and opt_params.get("lr_scheduler") in (None, "MultiStepLR"))
+            self.optimizer = get_optimizer(opt_params['optimizer'], params, opt_params, capturable=self._graph_capable)
         last_iter = -1
         if getattr(self, 'checkpoint', None) is not None:
             self.optimizer.load_state_dict(self.checkpoint['optimizer_state_dict'])
             last_iter = self.checkpoint['iteration'] - 1
+        self._host_it = last_iter + 1
         if self.scheduler is None:
             opt_params["last_iter"] = last_iter
-            self.scheduler = get_lr_scheduler(self.optimizer, opt_params)
+            if getattr(self, "_graph_capable", False):
+                # the learning rate lives in a device tensor read by the captured Adam: MultiStepLR is evaluated
+                # in closed form on the host (get_optimizer.py:50-54) and written into that tensor when it changes
+                self.scheduler = None
+                self._lr_base = float(opt_params['learning_rate'])
+                self._lr_now = None
+                self._set_lr(self._lr_at(self._host_it))
+            else:
+                self.scheduler = get_lr_scheduler(self.optimizer, opt_params)
 
     def create_loss_calculator(self):
         loss_name = self.config['training']['loss_type']
@@ -378,12 +402,31 @@ class SegmentationAgent(object):
     def _to_device(self, t):
         return t.to(self.device, dtype=torch.float32, non_blocking=True)
 
-    def train_step(self, batches):
-        """zero_grad; for each domain d present: L_d = loss(net(x_d, d), y_d[, w_d]); L = mean_d L_d;
-        backward (gradient all-reduce overlapped when world > 1); optimizer.step; scheduler.step.
-        ``batches``: list indexed by domain of batch dicts (host or device tensors) or None.
-        Returns (loss tensor on the device, [hard-Dice tensor per domain]) -- no host sync."""
-        self.optimizer.zero_grad(set_to_none=True)
+    def _lr_at(self, it):
+        tr = self.config['training']
+        if tr.get("lr_scheduler") is None:
+            return self._lr_base
+        n = sum(1 for m in tr["lr_milestones"] if m <= it)
+        return self._lr_base * (tr["lr_gamma"] ** n)
+
+    def _set_lr(self, lr):
+        if self._lr_now is None or lr != self._lr_now:
+            for gph in self.optimizer.param_groups:
+                if torch.is_tensor(gph['lr']):
+                    gph['lr'].fill_(lr)
+                else:
+                    gph['lr'] = lr
+            self._lr_now = lr
+
+    def current_lr(self):
+        lr = self.optimizer.param_groups[0]['lr']
+        return self._lr_now if torch.is_tensor(lr) else lr
+
+    def _step_body(self, batches):
+        """forward(s) + loss + backward (+ overlapped gradient all-reduce) + optimiser update; device work only."""
+        inval = getattr(self.net, "invalidate_weight_images", None)
+        if inval is not None:
+            inval()                 # fused optimisers do not bump tensor versions (see UNet2D5_dsbn)
         total, n_dom, dices = None, 0, []
         for d, data in enumerate(batches):
             if data is None:
@@ -401,9 +444,78 @@ class SegmentationAgent(object):
         if self.reducer is not None:
             self.reducer.finish()
         self.optimizer.step()
+        return loss.detach(), dices
+
+    def train_step(self, batches):
+        """zero_grad; for each domain d present: L_d = loss(net(x_d, d), y_d[, w_d]); L = mean_d L_d;
+        backward (gradient all-reduce overlapped when world > 1); optimizer.step; scheduler.step.
+        ``batches``: list indexed by domain of batch dicts (host or device tensors) or None.
+        Returns (loss tensor on the device, [hard-Dice tensor per domain]) -- no host sync.
+        With ``cuda_graph`` the device work of the step is replayed from a captured graph; the returned
+        tensors are then static buffers that the next step overwrites."""
+        if getattr(self, "_graph_capable", False) and self.use_cuda_graph:
+            out = self._train_step_graphed(batches)
+            self._host_it += 1
+            self._set_lr(self._lr_at(self._host_it))
+            return out
+        self.optimizer.zero_grad(set_to_none=True)
+        out = self._step_body(batches)
+        self._host_it += 1
         if self.scheduler is not None and not isinstance(self.scheduler, lr_scheduler.ReduceLROnPlateau):
             self.scheduler.step()
-        return loss.detach(), dices
+        elif getattr(self, "_graph_capable", False):
+            self._set_lr(self._lr_at(self._host_it))
+        return out
+
+    _TENSOR_KEYS = ('image', 'label_prob', 'pixel_weight')
+
+    def _train_step_graphed(self, batches):
+        key = tuple(None if b is None else tuple((k, tuple(b[k].shape)) for k in self._TENSOR_KEYS
+                                                 if b.get(k, None) is not None and (k != 'pixel_weight' or self.fpl_uda))
+                    for b in batches)
+        ent = self._graphs.get(key)
+        if ent is None:
+            ent = self._graphs[key] = {"graph": None, "calls": 0}
+        ent["calls"] += 1
+        if ent["graph"] is None and ent["calls"] <= 3:
+            # eager warm-up steps: optimiser state, workspaces, lazy driver state
+            self.optimizer.zero_grad(set_to_none=True)
+            return self._step_body(batches)
+        if ent["graph"] is None:
+            static = []
+            for b in batches:
+                if b is None:
+                    static.append(None)
+                    continue
+                sb = {k: self._to_device(b[k]).clone() for k in self._TENSOR_KEYS
+                      if b.get(k, None) is not None and (k != 'pixel_weight' or self.fpl_uda)}
+                if b.get('image_weight', None) is not None:
+                    sb['image_weight'] = b['image_weight']
+                static.append(sb)
+            ent["static"] = static
+            if hasattr(self.net, "ensure_rng"):
+                self.net.ensure_rng(self.device)
+            self.net._seed_from_device = True
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            self.optimizer.zero_grad(set_to_none=True)
+            try:
+                with torch.cuda.graph(g):
+                    ent["out"] = self._step_body(static)
+            finally:
+                self.net._seed_from_device = False
+            ent["graph"] = g
+            # the capture itself does not execute: fall through to the first replay with this step's data
+        for b, sb in zip(batches, ent["static"]):
+            if b is None:
+                continue
+            for k in self._TENSOR_KEYS:
+                if k in sb:
+                    sb[k].copy_(b[k], non_blocking=True)
+        if getattr(self.net, "_rng_dev", None) is not None:
+            self.net._rng_dev.fill_(self.net._draw_seed())
+        ent["graph"].replay()
+        return ent["out"]
 
     def _next(self, d, iters):
         try:
@@ -520,7 +632,7 @@ class SegmentationAgent(object):
         self.glob_it = iter_start
         history = []
         for it in range(iter_start, iter_max, iter_valid):
-            lr_value = self.optimizer.param_groups[0]['lr']
+            lr_value = self.current_lr() if hasattr(self, '_lr_now') else self.optimizer.param_groups[0]['lr']
             t0 = time.time()
             train_scalars = self.training_all()
             t1 = time.time()

@@ -338,6 +338,67 @@ extern "C" int fpl_conv3d_prep_weight(const float* w, int cin, int cout, int kd,
     return 0;
 }
 
+// all weight images of a network in ONE launch (blockIdx.y = conv): the per-step refresh after the
+// optimiser update costs one launch instead of one per conv and direction
+constexpr int kMaxPrepBatch = 80;
+struct PrepBatch {
+    const float* w[kMaxPrepBatch];
+    __nv_bfloat16* image[kMaxPrepBatch];
+    int cin_eff[kMaxPrepBatch], cout_eff[kMaxPrepBatch];
+    unsigned char kd[kMaxPrepBatch], tf[kMaxPrepBatch];
+    short nb[kMaxPrepBatch], kc[kMaxPrepBatch];
+    int total[kMaxPrepBatch];
+};
+
+namespace {
+__global__ void prep_weight_batch_kernel(const __grid_constant__ PrepBatch B) {
+    const int e = blockIdx.y;
+    const float* __restrict__ w = B.w[e];
+    __nv_bfloat16* image = B.image[e];
+    const int cin_eff = B.cin_eff[e], cout_eff = B.cout_eff[e], kd = B.kd[e], nb = B.nb[e], kc = B.kc[e];
+    const int T = kd * 9, nchunks = cin_eff / kc, total = B.total[e];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int t = i;
+        int el = t % 8; t /= 8;
+        int nrow = t % nb; t /= nb;
+        int k8 = t % (kc / 8); t /= (kc / 8);
+        int t9 = t % 9; t /= 9;
+        int kdi = t % kd; t /= kd;
+        int q = t % nchunks;
+        int sl = t / nchunks;
+        int out = sl * nb + nrow, in = q * kc + k8 * 8 + el, tap = kdi * 9 + t9;
+        float v = B.tf[e] ? w[((int64_t)in * cout_eff + out) * T + (T - 1 - tap)] : w[((int64_t)out * cin_eff + in) * T + tap];
+        image[i] = __float2bfloat16_rn(v);
+    }
+}
+}  // namespace
+
+extern "C" int fpl_conv3d_prep_weight_batch(int count, const float* const* h_w, const int* h_cin, const int* h_cout,
+                                            const int* h_kd, const int* h_transpose_flip, void* const* h_images,
+                                            void* stream) {
+    FPL_REQUIRE(count >= 0 && count <= kMaxPrepBatch, "fpl_conv3d_prep_weight_batch: count %d not in [0,%d]", count, kMaxPrepBatch);
+    if (count == 0) return 0;
+    PrepBatch B;
+    int max_total = 0;
+    for (int e = 0; e < count; ++e) {
+        const int tf = h_transpose_flip[e];
+        const int cin_eff = tf ? h_cout[e] : h_cin[e], cout_eff = tf ? h_cin[e] : h_cout[e];
+        TcConfig c;
+        FPL_REQUIRE(make_config(cin_eff, cout_eff, c), "fpl_conv3d_prep_weight_batch: unsupported channels (%d -> %d)", cin_eff, cout_eff);
+        FPL_REQUIRE(h_kd[e] == 1 || h_kd[e] == 3, "fpl_conv3d_prep_weight_batch: kd=%d must be 1 or 3", h_kd[e]);
+        B.w[e] = h_w[e]; B.image[e] = (__nv_bfloat16*)h_images[e];
+        B.cin_eff[e] = cin_eff; B.cout_eff[e] = cout_eff; B.kd[e] = (unsigned char)h_kd[e]; B.tf[e] = (unsigned char)tf;
+        B.nb[e] = (short)c.nb; B.kc[e] = (short)c.kc;
+        B.total[e] = c.nslices * c.nchunks * h_kd[e] * c.b_bytes / 2;
+        if (B.total[e] > max_total) max_total = B.total[e];
+    }
+    int bx = (max_total + 255) / 256;
+    if (bx > 64) bx = 64;
+    prep_weight_batch_kernel<<<dim3(bx, count), 256, 0, (cudaStream_t)stream>>>(B);
+    FPL_LAUNCH_CHECK();
+    return 0;
+}
+
 static int g_dbg_swap = 0;
 void fpl_wgrad_debug_set(int key, long long value);
 extern "C" void fpl_debug_set(int key, long long value) {

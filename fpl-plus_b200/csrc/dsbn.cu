@@ -62,6 +62,7 @@ struct ActParams {
     float drop_p;
     const uint2* drop_mask;     // 8 x uint8 per vector, dense order
     uint64_t seed, offset;
+    const unsigned long long* seed_dev;   // optional device-side addend to the seed (CUDA-graph replays)
     int N, D, C8, H, W;
 };
 
@@ -87,90 +88,103 @@ __device__ __forceinline__ uint32_t keep_bits(const uint2* mask, uint64_t seed, 
     return dropout_keep8(seed, offset, (uint64_t)vec, p);
 }
 
+// grid: (chunks of H*W, N*D*C8 planes): a block stays inside one channel group, so the affine
+// parameters are loaded once and the index math is 32-bit
 __global__ void __launch_bounds__(kThreads) dsbn_act_fwd_kernel(ActParams P) {
-    const int64_t HW = (int64_t)P.H * P.W;
-    const int64_t total = (int64_t)P.N * P.D * P.C8 * HW;
+    const int HW = P.H * P.W;
+    const int plane = blockIdx.y;
+    const int c8 = plane % P.C8;
+    const int nd = plane / P.C8;
     const float slope = __ldg(P.slope);
     const bool drop = P.drop_p > 0.0f;
     const float keep_scale = drop ? 1.0f / (1.0f - P.drop_p) : 1.0f;
-    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
-        int64_t plane = v / HW;
-        int64_t hw = v - plane * HW;
-        int c8 = (int)(plane % P.C8);
-        int64_t nd = plane / P.C8;
-        float sc[8], sh[8], f[8];
-        load_affine(P.scale, P.shift, c8, sc, sh);
-        int4 raw = ld_stream16(P.y + v);
-        bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw), f);
-        uint32_t keep = drop ? keep_bits(P.drop_mask, P.seed, P.offset, v, P.drop_p) : 0xffu;
+    const uint64_t seed = P.seed + (P.seed_dev != nullptr ? (uint64_t)__ldg(P.seed_dev) : 0ull);
+    float sc[8], sh[8];
+    load_affine(P.scale, P.shift, c8, sc, sh);
+    const bf16x8* src = P.y + (int64_t)plane * HW;
+    bf16x8* dst = P.a + ((int64_t)nd * P.a_c8tot + P.a_c8off + c8) * HW;
+    const int stride = gridDim.x * blockDim.x;
+    for (int hw = blockIdx.x * blockDim.x + threadIdx.x; hw < HW; hw += 2 * stride) {
+        const int hw2 = hw + stride;
+        const bool two = hw2 < HW;
+        int4 r0 = ld_stream16(src + hw), r1 = make_int4(0, 0, 0, 0);
+        if (two) r1 = ld_stream16(src + hw2);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float z = fmaf(f[i], sc[i], sh[i]);
-            float a = z > 0.0f ? z : slope * z;
-            f[i] = ((keep >> i) & 1u) ? a * keep_scale : 0.0f;
+        for (int k = 0; k < 2; ++k) {
+            if (k == 1 && !two) break;
+            const int h = k == 0 ? hw : hw2;
+            float f[8];
+            bf16x8_to_float(*reinterpret_cast<bf16x8*>(k == 0 ? &r0 : &r1), f);
+            uint32_t keep = drop ? keep_bits(P.drop_mask, seed, P.offset, (int64_t)plane * HW + h, P.drop_p) : 0xffu;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float z = fmaf(f[i], sc[i], sh[i]);
+                float a = z > 0.0f ? z : slope * z;
+                f[i] = ((keep >> i) & 1u) ? a * keep_scale : 0.0f;
+            }
+            st_bf16x8(dst + h, f);
         }
-        int64_t o = (nd * P.a_c8tot + P.a_c8off + c8) * HW + hw;
-        st_bf16x8(&P.a[o], f);
     }
 }
 
 // one thread per pooled output vector; reads the 2x2x2 (or 1x2x2) window, writes the full
 // resolution activations, the pooled max and the 3-bit argmax code (first max wins, scan
 // order d,h,w as in torch's max_pool3d).
+// grid: (chunks of H2*W2, N*D2*C8 pooled planes)
 __global__ void __launch_bounds__(kThreads) dsbn_act_pool_fwd_kernel(ActParams P) {
     const int kd = P.pool_kd;
     const int D2 = P.D / kd, H2 = P.H / 2, W2 = P.W / 2;
-    const int64_t HW = (int64_t)P.H * P.W, HW2 = (int64_t)H2 * W2;
-    const int64_t total = (int64_t)P.N * D2 * P.C8 * HW2;
+    const int HW = P.H * P.W, HW2 = H2 * W2;
+    const int pplane = blockIdx.y;
+    const int c8 = pplane % P.C8;
+    const int nd2 = pplane / P.C8;
+    const int d2 = nd2 % D2, n = nd2 / D2;
     const float slope = __ldg(P.slope);
-    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
-        int w2 = (int)(v % W2);
-        int64_t t = v / W2;
-        int h2 = (int)(t % H2); t /= H2;
-        int c8 = (int)(t % P.C8); t /= P.C8;
-        int d2 = (int)(t % D2);
-        int n = (int)(t / D2);
-        float sc[8], sh[8], best[8];
+    float sc[8], sh[8];
+    load_affine(P.scale, P.shift, c8, sc, sh);
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < HW2; v += gridDim.x * blockDim.x) {
+        const int h2 = v / W2, w2 = v - h2 * W2;
+        float best[8];
         uint32_t code[8];
-        load_affine(P.scale, P.shift, c8, sc, sh);
 #pragma unroll
         for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; code[i] = 0; }
-        for (int dd = 0; dd < kd; ++dd) {
-            int d = d2 * kd + dd;
-            int64_t nd = (int64_t)n * P.D + d;
+        int4 raw[8];
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                int64_t row = (int64_t)(h2 * 2 + hh) * P.W + w2 * 2;
-                int64_t src = (nd * P.C8 + c8) * HW + row;
-                int64_t dst = (nd * P.a_c8tot + P.a_c8off + c8) * HW + row;
+        for (int q = 0; q < 8; ++q) {                      // all loads of the 2x2x2 window first
+            const int dd = q >> 2, hh = (q >> 1) & 1, ww = q & 1;
+            if (dd < kd) {
+                const int64_t nd = (int64_t)n * P.D + d2 * kd + dd;
+                raw[q] = ld_stream16(P.y + (nd * P.C8 + c8) * HW + (h2 * 2 + hh) * P.W + w2 * 2 + ww);
+            }
+        }
 #pragma unroll
-                for (int ww = 0; ww < 2; ++ww) {
-                    float f[8];
-                    int4 raw = ld_stream16(P.y + src + ww);
-                    bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw), f);
+        for (int q = 0; q < 8; ++q) {
+            const int dd = q >> 2, hh = (q >> 1) & 1, ww = q & 1;
+            if (dd < kd) {
+                const int64_t nd = (int64_t)n * P.D + d2 * kd + dd;
+                float f[8];
+                bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw[q]), f);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float z = fmaf(f[i], sc[i], sh[i]);
-                        f[i] = z > 0.0f ? z : slope * z;
-                    }
-                    bf16x8 outv = float_to_bf16x8(f);
-                    st_bf16x8(&P.a[dst + ww], f);
-                    // compare on the bf16-rounded values (what backward and the next layer see)
-                    bf16x8_to_float(outv, f);
-                    uint32_t k = (uint32_t)((dd * 2 + hh) * 2 + ww);
+                for (int i = 0; i < 8; ++i) {
+                    float z = fmaf(f[i], sc[i], sh[i]);
+                    f[i] = z > 0.0f ? z : slope * z;
+                }
+                bf16x8 outv = float_to_bf16x8(f);
+                st_bf16x8(P.a + (nd * P.a_c8tot + P.a_c8off + c8) * HW + (h2 * 2 + hh) * P.W + w2 * 2 + ww, f);
+                // compare on the bf16-rounded values (what backward and the next layer see); first max wins
+                bf16x8_to_float(outv, f);
+                const uint32_t k = (uint32_t)((dd * 2 + hh) * 2 + ww);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (f[i] > best[i]) { best[i] = f[i]; code[i] = k; }
-                    }
+                for (int i = 0; i < 8; ++i) {
+                    if (f[i] > best[i]) { best[i] = f[i]; code[i] = k; }
                 }
             }
         }
-        int64_t po = (((int64_t)n * D2 + d2) * P.p_c8tot + P.p_c8off + c8) * HW2 + (int64_t)h2 * W2 + w2;
-        st_bf16x8(&P.pooled[po], best);
+        st_bf16x8(P.pooled + ((int64_t)nd2 * P.p_c8tot + P.p_c8off + c8) * HW2 + v, best);
         uint2 packed;
         packed.x = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
         packed.y = code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24);
-        P.pool_idx[v] = packed;
+        P.pool_idx[(int64_t)pplane * HW2 + v] = packed;
     }
 }
 
@@ -193,6 +207,7 @@ struct ActBwdParams {
     float drop_p;
     const uint2* drop_mask;
     uint64_t seed, offset;
+    const unsigned long long* seed_dev;
     double* red;                // [2C+1]: sum dz, sum dz*xhat, dslope
     bf16x8* dy;
     int training;
@@ -200,99 +215,100 @@ struct ActBwdParams {
     int N, D, C8, H, W;
 };
 
-// gradient wrt the BN output (dz[8]) of vector (nd, c8, hw); also returns z*g for dslope
-__device__ __forceinline__ void act_bwd_vec(const ActBwdParams& P, int64_t v, int64_t nd, int c8, int h, int w,
-                                            const float* sc, const float* sh, float slope, float keep_scale,
-                                            float* yf, float* dz, float& dslope) {
-    const int64_t HW = (int64_t)P.H * P.W;
-    float g[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) g[i] = 0.0f;
-    if (P.g1 != nullptr) {
-        int4 raw = ld_stream16(P.g1 + (nd * P.g1_c8tot + P.g1_c8off + c8) * HW + (int64_t)h * P.W + w);
-        bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw), g);
-    }
-    if (P.g_pool != nullptr) {
-        const int kd = P.pool_kd;
-        const int D2 = P.D / kd, H2 = P.H / 2, W2 = P.W / 2;
-        int n = (int)(nd / P.D), d = (int)(nd % P.D);
-        int d2 = d / kd, h2 = h >> 1, w2 = w >> 1;
-        uint32_t mycode = (uint32_t)((((d - d2 * kd) * 2) + (h & 1)) * 2 + (w & 1));
-        int64_t pnd = (int64_t)n * D2 + d2;
-        int64_t pix = (int64_t)h2 * W2 + w2;
-        uint2 codes = __ldg(P.pool_idx + (pnd * P.C8 + c8) * ((int64_t)H2 * W2) + pix);
-        bf16x8 gp = ldg_bf16x8(P.g_pool + (pnd * P.gp_c8tot + P.gp_c8off + c8) * ((int64_t)H2 * W2) + pix);
-        float gpf[8];
-        bf16x8_to_float(gp, gpf);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            uint32_t cd = ((i < 4 ? codes.x : codes.y) >> (8 * (i & 3))) & 0xffu;
-            if (cd == mycode) g[i] += gpf[i];
-        }
-    }
-    int4 raw = ld_stream16(P.y + v);
-    bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw), yf);
-    uint32_t keep = P.drop_p > 0.0f ? keep_bits(P.drop_mask, P.seed, P.offset, v, P.drop_p) : 0xffu;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        float z = fmaf(yf[i], sc[i], sh[i]);
-        float ga = ((keep >> i) & 1u) ? g[i] * keep_scale : 0.0f;
-        if (z > 0.0f) {
-            dz[i] = ga;
-        } else {
-            dz[i] = ga * slope;
-            dslope += z * ga;
-        }
-    }
-}
-
-// grid: (chunks of H*W, N*D*C8 planes) so a block stays inside one channel group
+// grid: (chunks of H*W, N*D*C8 planes) so a block stays inside one channel group.  Two vectors per
+// thread are in flight (all loads issued before any arithmetic); xhat = y*k1 + k0.
 template <bool APPLY>
 __global__ void __launch_bounds__(kThreads) dsbn_act_bwd_kernel(ActBwdParams P) {
-    const int64_t HW = (int64_t)P.H * P.W;
-    const int64_t plane = blockIdx.y;
-    const int c8 = (int)(plane % P.C8);
-    const int64_t nd = plane / P.C8;
+    const int HW = P.H * P.W;
+    const int plane = blockIdx.y;
+    const int c8 = plane % P.C8;
+    const int nd = plane / P.C8;
     const float slope = __ldg(P.slope);
-    const float keep_scale = P.drop_p > 0.0f ? 1.0f / (1.0f - P.drop_p) : 1.0f;
-    float sc[8], sh[8], mean[8], invstd[8];
+    const bool drop = P.drop_p > 0.0f;
+    const float keep_scale = drop ? 1.0f / (1.0f - P.drop_p) : 1.0f;
+    const uint64_t seed = P.seed + (P.seed_dev != nullptr ? (uint64_t)__ldg(P.seed_dev) : 0ull);
+    float sc[8], sh[8], k1[8], k0[8];
     load_affine(P.scale, P.shift, c8, sc, sh);
-    load_affine(P.mean, P.invstd, c8, mean, invstd);
-    float s1[8], s2[8], dsl = 0.0f;
-    float m1[8], m2[8];
+    load_affine(P.mean, P.invstd, c8, k0, k1);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s1[i] = 0.0f; s2[i] = 0.0f; m1[i] = 0.0f; m2[i] = 0.0f; }
+    for (int i = 0; i < 8; ++i) k0[i] = -k0[i] * k1[i];
+    float s1[8], s2[8], dsl = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s1[i] = 0.0f; s2[i] = 0.0f; }
     if (APPLY && P.training) {
+        // fold the batch means into the apply constants: dy = sc*(dz - m1 - xhat*m2)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            m1[i] = (float)(P.red[c8 * 8 + i] * P.inv_count);
-            m2[i] = (float)(P.red[P.C8 * 8 + c8 * 8 + i] * P.inv_count);
+            s1[i] = (float)(P.red[c8 * 8 + i] * P.inv_count);                 // m1
+            s2[i] = (float)(P.red[P.C8 * 8 + c8 * 8 + i] * P.inv_count);      // m2
         }
     }
-    for (int64_t hw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; hw < HW; hw += (int64_t)gridDim.x * blockDim.x) {
-        int h = (int)(hw / P.W), w = (int)(hw - (int64_t)h * P.W);
-        int64_t v = plane * HW + hw;
-        float yf[8], dz[8];
-        act_bwd_vec(P, v, nd, c8, h, w, sc, sh, slope, keep_scale, yf, dz, dsl);
-        if (!APPLY) {
+    const bf16x8* yp = P.y + (int64_t)plane * HW;
+    const bf16x8* g1p = P.g1 != nullptr ? P.g1 + ((int64_t)nd * P.g1_c8tot + P.g1_c8off + c8) * HW : nullptr;
+    // pooled-path pointers (2x2 in-plane window; kd = 1 or 2 planes per pooled plane)
+    const int W2 = P.W >> 1, HW2 = (P.H >> 1) * W2;
+    const bf16x8* gpp = nullptr;
+    const uint2* idxp = nullptr;
+    uint32_t code_d = 0;
+    if (P.g_pool != nullptr) {
+        const int kd = P.pool_kd, D2 = P.D / kd;
+        const int n = nd / P.D, d = nd - n * P.D, d2 = d / kd;
+        const int64_t pnd = (int64_t)n * D2 + d2;
+        gpp = P.g_pool + (pnd * P.gp_c8tot + P.gp_c8off + c8) * HW2;
+        idxp = P.pool_idx + (pnd * P.C8 + c8) * HW2;
+        code_d = (uint32_t)(d - d2 * kd) * 4u;
+    }
+    bf16x8* dyp = APPLY ? P.dy + (int64_t)plane * HW : nullptr;
+    const int stride = gridDim.x * blockDim.x;
+    for (int hw0 = blockIdx.x * blockDim.x + threadIdx.x; hw0 < HW; hw0 += 2 * stride) {
+        int hwk[2] = {hw0, hw0 + stride};
+        const bool act[2] = {true, hwk[1] < HW};
+        int4 ry[2], rg[2], rp[2];
+        uint2 rc[2];
+        uint32_t mycode[2];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float xhat = (yf[i] - mean[i]) * invstd[i];
-                s1[i] += dz[i];
-                s2[i] = fmaf(dz[i], xhat, s2[i]);
+        for (int k = 0; k < 2; ++k) {
+            ry[k] = rg[k] = rp[k] = make_int4(0, 0, 0, 0);
+            rc[k] = make_uint2(0, 0);
+            mycode[k] = 0xffu;
+            if (act[k]) {
+                ry[k] = ld_stream16(yp + hwk[k]);
+                if (g1p != nullptr) rg[k] = ld_stream16(g1p + hwk[k]);
+                if (gpp != nullptr) {
+                    const int h = hwk[k] / P.W, w = hwk[k] - h * P.W;
+                    const int pix = (h >> 1) * W2 + (w >> 1);
+                    mycode[k] = code_d + (uint32_t)((h & 1) * 2 + (w & 1));
+                    rc[k] = __ldg(idxp + pix);
+                    rp[k] = __ldg(reinterpret_cast<const int4*>(gpp + pix));
+                }
             }
-        } else {
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (!act[k]) continue;
+            float yf[8], g[8], gp[8];
+            bf16x8_to_float(*reinterpret_cast<bf16x8*>(&ry[k]), yf);
+            bf16x8_to_float(*reinterpret_cast<bf16x8*>(&rg[k]), g);
+            bf16x8_to_float(*reinterpret_cast<bf16x8*>(&rp[k]), gp);
+            const uint32_t keep = drop ? keep_bits(P.drop_mask, seed, P.offset, (int64_t)plane * HW + hwk[k], P.drop_p) : 0xffu;
             float o[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                if (P.training) {
-                    float xhat = (yf[i] - mean[i]) * invstd[i];
-                    o[i] = sc[i] * (dz[i] - m1[i] - xhat * m2[i]);
+                const uint32_t cd = ((i < 4 ? rc[k].x : rc[k].y) >> (8 * (i & 3))) & 0xffu;
+                float gi = g[i] + (cd == mycode[k] ? gp[i] : 0.0f);
+                gi = ((keep >> i) & 1u) ? gi * keep_scale : 0.0f;
+                const float z = fmaf(yf[i], sc[i], sh[i]);
+                const float dz = z > 0.0f ? gi : gi * slope;
+                const float xhat = fmaf(yf[i], k1[i], k0[i]);
+                if (!APPLY) {
+                    dsl += z > 0.0f ? 0.0f : z * gi;
+                    s1[i] += dz;
+                    s2[i] = fmaf(dz, xhat, s2[i]);
                 } else {
-                    o[i] = sc[i] * dz[i];
+                    o[i] = P.training ? sc[i] * (dz - s1[i] - xhat * s2[i]) : sc[i] * dz;
                 }
             }
-            st_bf16x8(&P.dy[v], o);
+            if (APPLY) st_bf16x8(dyp + hwk[k], o);
         }
     }
     if (!APPLY) {
@@ -361,7 +377,8 @@ extern "C" int fpl_dsbn_finalize(const double* stats, int64_t count, const float
 extern "C" int fpl_dsbn_act_fwd(const void* y, const float* scale, const float* shift, const float* slope,
                                 void* a, int a_c8tot, int a_c8off, void* pooled, int p_c8tot, int p_c8off,
                                 uint8_t* pool_idx, int pool_kd, float drop_p, const uint8_t* drop_mask,
-                                uint64_t seed, uint64_t offset, int n, int d, int h, int w, int c, void* stream) {
+                                uint64_t seed, uint64_t offset, const uint64_t* seed_dev, int n, int d, int h, int w, int c,
+                                void* stream) {
     FPL_REQUIRE(c > 0 && c % 8 == 0, "fpl_dsbn_act_fwd: channels (%d) must be a multiple of 8", c);
     FPL_REQUIRE(drop_p >= 0.0f && drop_p < 1.0f, "fpl_dsbn_act_fwd: dropout p=%f out of [0,1)", drop_p);
     ActParams P;
@@ -369,17 +386,24 @@ extern "C" int fpl_dsbn_act_fwd(const void* y, const float* scale, const float* 
     P.a = (bf16x8*)a; P.a_c8tot = a_c8tot; P.a_c8off = a_c8off;
     P.pooled = (bf16x8*)pooled; P.p_c8tot = p_c8tot; P.p_c8off = p_c8off; P.pool_idx = (uint2*)pool_idx;
     P.pool_kd = pool_kd; P.drop_p = drop_p; P.drop_mask = (const uint2*)drop_mask; P.seed = seed; P.offset = offset;
+    P.seed_dev = (const unsigned long long*)seed_dev;
     P.N = n; P.D = d; P.C8 = c / 8; P.H = h; P.W = w;
     if (pooled != nullptr) {
         FPL_REQUIRE(pool_kd == 1 || pool_kd == 2, "fpl_dsbn_act_fwd: pool_kd must be 1 or 2");
         FPL_REQUIRE(h % 2 == 0 && w % 2 == 0 && d % pool_kd == 0, "fpl_dsbn_act_fwd: pooled dims must be even");
         FPL_REQUIRE(drop_p == 0.0f, "fpl_dsbn_act_fwd: dropout is not combined with pooling");
         FPL_REQUIRE(pool_idx != nullptr, "fpl_dsbn_act_fwd: pool_idx required");
-        int64_t total = (int64_t)n * (d / pool_kd) * (c / 8) * (h / 2) * (w / 2);
-        dsbn_act_pool_fwd_kernel<<<grid_for(total, 1), kThreads, 0, (cudaStream_t)stream>>>(P);
+        int64_t planes = (int64_t)n * (d / pool_kd) * (c / 8);
+        FPL_REQUIRE(planes <= 65535, "fpl_dsbn_act_fwd: too many planes (%lld)", (long long)planes);
+        int hw2 = (h / 2) * (w / 2);
+        dim3 grid((hw2 + kThreads - 1) / kThreads, (unsigned)planes);
+        dsbn_act_pool_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(P);
     } else {
-        int64_t total = (int64_t)n * d * (c / 8) * h * w;
-        dsbn_act_fwd_kernel<<<grid_for(total, 4), kThreads, 0, (cudaStream_t)stream>>>(P);
+        int64_t planes = (int64_t)n * d * (c / 8);
+        FPL_REQUIRE(planes <= 65535, "fpl_dsbn_act_fwd: too many planes (%lld)", (long long)planes);
+        int chunks = (h * w + kThreads * 4 - 1) / (kThreads * 4);
+        dim3 grid(chunks < 1 ? 1 : chunks, (unsigned)planes);
+        dsbn_act_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(P);
     }
     FPL_LAUNCH_CHECK();
     return 0;
@@ -388,8 +412,8 @@ extern "C" int fpl_dsbn_act_fwd(const void* y, const float* scale, const float* 
 static int fill_bwd(ActBwdParams& P, const void* y, const void* g1, int g1_c8tot, int g1_c8off, const void* g_pool,
                     int gp_c8tot, int gp_c8off, const uint8_t* pool_idx, int pool_kd, const float* scale,
                     const float* shift, const float* save_mean, const float* save_invstd, const float* slope,
-                    float drop_p, const uint8_t* drop_mask, uint64_t seed, uint64_t offset, int n, int d, int h,
-                    int w, int c) {
+                    float drop_p, const uint8_t* drop_mask, uint64_t seed, uint64_t offset, const uint64_t* seed_dev,
+                    int n, int d, int h, int w, int c) {
     FPL_REQUIRE(c > 0 && c % 8 == 0, "dsbn bwd: channels (%d) must be a multiple of 8", c);
     FPL_REQUIRE(g1 != nullptr || g_pool != nullptr, "dsbn bwd: no incoming gradient");
     if (g_pool != nullptr) {
@@ -401,6 +425,7 @@ static int fill_bwd(ActBwdParams& P, const void* y, const void* g1, int g1_c8tot
     P.pool_idx = (const uint2*)pool_idx; P.pool_kd = pool_kd > 0 ? pool_kd : 2;
     P.scale = scale; P.shift = shift; P.mean = save_mean; P.invstd = save_invstd; P.slope = slope;
     P.drop_p = drop_p; P.drop_mask = (const uint2*)drop_mask; P.seed = seed; P.offset = offset;
+    P.seed_dev = (const unsigned long long*)seed_dev;
     P.red = nullptr; P.dy = nullptr; P.training = 1; P.inv_count = 1.0 / ((double)n * d * h * w);
     P.N = n; P.D = d; P.C8 = c / 8; P.H = h; P.W = w;
     return 0;
@@ -417,11 +442,12 @@ extern "C" int fpl_dsbn_act_bwd_reduce(const void* y, const void* g1, int g1_c8t
                                        int gp_c8tot, int gp_c8off, const uint8_t* pool_idx, int pool_kd,
                                        const float* scale, const float* shift, const float* save_mean,
                                        const float* save_invstd, const float* slope, float drop_p,
-                                       const uint8_t* drop_mask, uint64_t seed, uint64_t offset, double* red, int n,
-                                       int d, int h, int w, int c, void* stream) {
+                                       const uint8_t* drop_mask, uint64_t seed, uint64_t offset,
+                                       const uint64_t* seed_dev, double* red, int n, int d, int h, int w, int c,
+                                       void* stream) {
     ActBwdParams P;
     int rc = fill_bwd(P, y, g1, g1_c8tot, g1_c8off, g_pool, gp_c8tot, gp_c8off, pool_idx, pool_kd, scale, shift,
-                      save_mean, save_invstd, slope, drop_p, drop_mask, seed, offset, n, d, h, w, c);
+                      save_mean, save_invstd, slope, drop_p, drop_mask, seed, offset, seed_dev, n, d, h, w, c);
     if (rc) return rc;
     FPL_REQUIRE((int64_t)n * d * (c / 8) <= 65535, "dsbn bwd: too many planes (%lld)", (long long)n * d * (c / 8));
     P.red = red;
@@ -434,11 +460,12 @@ extern "C" int fpl_dsbn_act_bwd_apply(const void* y, const void* g1, int g1_c8to
                                       int gp_c8tot, int gp_c8off, const uint8_t* pool_idx, int pool_kd,
                                       const float* scale, const float* shift, const float* save_mean,
                                       const float* save_invstd, const float* slope, float drop_p,
-                                      const uint8_t* drop_mask, uint64_t seed, uint64_t offset, const double* red,
-                                      int training, void* dy, int n, int d, int h, int w, int c, void* stream) {
+                                      const uint8_t* drop_mask, uint64_t seed, uint64_t offset,
+                                      const uint64_t* seed_dev, const double* red, int training, void* dy, int n, int d,
+                                      int h, int w, int c, void* stream) {
     ActBwdParams P;
     int rc = fill_bwd(P, y, g1, g1_c8tot, g1_c8off, g_pool, gp_c8tot, gp_c8off, pool_idx, pool_kd, scale, shift,
-                      save_mean, save_invstd, slope, drop_p, drop_mask, seed, offset, n, d, h, w, c);
+                      save_mean, save_invstd, slope, drop_p, drop_mask, seed, offset, seed_dev, n, d, h, w, c);
     if (rc) return rc;
     FPL_REQUIRE((int64_t)n * d * (c / 8) <= 65535, "dsbn bwd: too many planes (%lld)", (long long)n * d * (c / 8));
     P.red = const_cast<double*>(red);

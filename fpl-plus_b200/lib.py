@@ -23,6 +23,8 @@ _SIGNATURES = {
     "fpl_debug_set": (None, [_I, c_longlong]),
     "fpl_conv3d_weight_image_bytes": (_L, [_I, _I, _I]),
     "fpl_conv3d_prep_weight": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "fpl_conv3d_prep_weight_batch": (_I, [_I, ctypes.POINTER(c_void_p), ctypes.POINTER(_I), ctypes.POINTER(_I),
+                                          ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(c_void_p), _P]),
     "fpl_conv3d_tc": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _P] + [_I] * 7 + [_P]),
     "fpl_conv3d_direct": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _P] + [_I] * 9 + [_P]),
     "fpl_conv3d_wgrad": (_I, [_P, _I, _I, _P, _I, _I, _P] + [_I] * 7 + [_P]),
@@ -34,10 +36,10 @@ _SIGNATURES = {
     "fpl_convt_k2s2_fwd": (_I, [_P, _I, _I, _P, _P, _P, _I, _I] + [_I] * 7 + [_P]),
     "fpl_convt_k2s2_bwd": (_I, [_P, _I, _I, _P, _P, _I, _I, _P, _I, _I, _P, _P] + [_I] * 7 + [_P]),
     "fpl_dsbn_finalize": (_I, [_P, _L, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _I, _P]),
-    "fpl_dsbn_act_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _F, _P, _U, _U] + [_I] * 5 + [_P]),
-    "fpl_dsbn_act_bwd_reduce": (_I, [_P, _P, _I, _I, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _F, _P, _U, _U, _P]
+    "fpl_dsbn_act_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _F, _P, _U, _U, _P] + [_I] * 5 + [_P]),
+    "fpl_dsbn_act_bwd_reduce": (_I, [_P, _P, _I, _I, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _F, _P, _U, _U, _P, _P]
                                 + [_I] * 5 + [_P]),
-    "fpl_dsbn_act_bwd_apply": (_I, [_P, _P, _I, _I, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _F, _P, _U, _U, _P, _I, _P]
+    "fpl_dsbn_act_bwd_apply": (_I, [_P, _P, _I, _I, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _F, _P, _U, _U, _P, _P, _I, _P]
                                + [_I] * 5 + [_P]),
     "fpl_dsbn_bwd_finalize": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _I, _P]),
     "fpl_dice_ce_reduce": (_I, [_P, _P, _P, _P, _I, _I, _L, _P]),

@@ -160,7 +160,11 @@ class UNet2D5_dsbn(nn.Module):
         self._infer_ws = None
         self._img_cache = {}
         self._dropout_masks = None      # {unit name: uint8 keep mask, dense C8-planar order} (parity tests)
-        self._rng_offset = 0
+        self._rng_dev = None            # int64[1] device seed read by the dropout kernels inside CUDA graphs
+        self._seed_from_device = False
+        self._graphs = {}               # (shape, domain, mode) -> _GraphedForward (no-grad forwards)
+        self._graph_ws_keep = []        # workspaces baked into captured graphs: never recycled
+        self.cuda_graphs = os.environ.get("FPL_CUDA_GRAPH", "1") != "0"
         self.grad_ready_hook = None     # callable(flat_grad, start, end, last) fired as buckets complete (DDP)
         self._build_plan()
 
@@ -220,11 +224,69 @@ class UNet2D5_dsbn(nn.Module):
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         if need_grad:
             return _UNetFunction.apply(self, domain, x, *params)
+        if self.cuda_graphs and not torch.cuda.is_current_stream_capturing():
+            return self._forward_graphed(x, domain)
         ws = self._infer_ws
         if ws is None or ws.device != x.device:
             ws = self._infer_ws = _Workspace(x.device)
         logits, _ = self._run_forward(x, domain, ws)
         return logits
+
+    # -- no-grad forwards replayed from CUDA graphs (sliding-window inference: 256 forwards / volume) --
+    def _mode_signature(self, domain):
+        sig = [self.training]
+        for u1, u2 in self._down_units + self._up_units:
+            for u in (u1, u2):
+                sig.append(u.dsbn.bns[domain].training)
+                if u.dropout is not None:
+                    sig.append(u.dropout.training and u.dropout.p > 0.0)
+        return tuple(sig)
+
+    def ensure_rng(self, device):
+        """The device-side dropout seed (must exist BEFORE a capture so that no allocation/zero-fill of it
+        is recorded into the graph)."""
+        if self._rng_dev is None or self._rng_dev.device != torch.device(device):
+            self._rng_dev = torch.zeros(1, dtype=torch.int64, device=device)
+        return self._rng_dev
+
+    def _draw_seed(self):
+        # torch's CPU generator, so torch.manual_seed makes MC-dropout passes reproducible
+        return int(torch.empty((), dtype=torch.int64).random_().item()) & ((1 << 62) - 1)
+
+    def _forward_graphed(self, x, domain):
+        key = (tuple(x.shape), domain, x.device.index, self._mode_signature(domain))
+        ent = self._graphs.get(key)
+        if ent is None:
+            # first sight of this (shape, domain, mode): run eagerly (also warms lazy driver state), capture next time
+            self._graphs[key] = ent = {"graph": None, "calls": 0}
+        ent["calls"] += 1
+        if ent["graph"] is None and ent["calls"] < 2:
+            ws = self._infer_ws
+            if ws is None or ws.device != x.device:
+                ws = self._infer_ws = _Workspace(x.device)
+            logits, _ = self._run_forward(x, domain, ws)
+            return logits
+        self.ensure_rng(x.device)
+        self._refresh_weight_images(with_dgrad=False)      # eager: a captured graph never restages weights
+        if ent["graph"] is None:
+            if len(self._graphs) > 16:                     # bound the memory held by stale shapes
+                for k in [k for k in self._graphs if k != key][:8]:
+                    del self._graphs[k]
+            ent["x"] = x.clone()
+            ent["ws"] = _Workspace(x.device)
+            g = torch.cuda.CUDAGraph()
+            self._seed_from_device = True
+            try:
+                with torch.cuda.graph(g):
+                    ent["out"], _ = self._run_forward(ent["x"], domain, ent["ws"])
+            finally:
+                self._seed_from_device = False
+            ent["graph"] = g
+        ent["x"].copy_(x, non_blocking=True)
+        if any(key[3][1:]) and self._dropout_masks is None:
+            self._rng_dev.fill_(self._draw_seed())
+        ent["graph"].replay()
+        return ent["out"].clone()
 
     # -- helpers ----------------------------------------------------------------------------
     def _geometry(self, shape):
@@ -243,18 +305,55 @@ class UNet2D5_dsbn(nn.Module):
     def _use_tc(self, cin, cout):
         return _conv_impl() == "tc" and cin % 16 == 0 and cout % 16 == 0 and ops.is_sm100()
 
+    def invalidate_weight_images(self):
+        """Forget the staged bf16 weight images.  They are keyed on ``weight._version``, which every
+        ordinary in-place update bumps (torch.optim's default implementations, ``load_state_dict``);
+        optimisers that write through fused multi-tensor kernels (``Adam(fused=True)``) do not, so the
+        agent calls this after ``optimizer.step()``."""
+        for ent in self._img_cache.values():
+            ent[0] = -1
+
+    def _tc_convs(self):
+        out = []
+        for u1, u2 in self._down_units + self._up_units:
+            for u in (u1, u2):
+                if not u.is_stem and self._use_tc(u.cin, u.cout):
+                    out.append(u)
+        return out
+
+    def _refresh_weight_images(self, with_dgrad):
+        """(Re)stage every stale weight image with ONE batched launch."""
+        lib = ops._lib.load()
+        todo = []
+        for u in self._tc_convs():
+            w = u.conv.weight
+            for transpose in ((False, True) if with_dgrad else (False,)):
+                if transpose and not self._use_tc(u.cout, u.cin):
+                    continue
+                key = (id(w), transpose)
+                ent = self._img_cache.get(key)
+                if ent is None or ent[1].device != w.device:
+                    nbytes = lib.fpl_conv3d_weight_image_bytes(u.cout if transpose else u.cin,
+                                                               u.cin if transpose else u.cout, u.kd)
+                    ent = self._img_cache[key] = [-1, torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)]
+                if ent[0] != w._version:
+                    todo.append((w, u.cin, u.cout, u.kd, 1 if transpose else 0, ent))
+        for i in range(0, len(todo), 80):
+            part = todo[i:i + 80]
+            n = len(part)
+            arr_w = (ctypes.c_void_p * n)(*[t[0].data_ptr() for t in part])
+            arr_img = (ctypes.c_void_p * n)(*[t[5][1].data_ptr() for t in part])
+            ints = [(ctypes.c_int * n)(*[t[k] for t in part]) for k in (1, 2, 3, 4)]
+            call("fpl_conv3d_prep_weight_batch", n, arr_w, ints[0], ints[1], ints[2], ints[3], arr_img, stream_ptr())
+            for t in part:
+                t[5][0] = t[0]._version
+
     def _weight_image(self, conv, kd, transpose, ws):
-        w = conv.weight
-        cin, cout = conv.in_channels, conv.out_channels
-        key = (id(w), transpose)
-        ent = self._img_cache.get(key)
-        if ent is not None and ent[0] == w._version and ent[1].device == w.device:
-            return ent[1]
-        nbytes = ops._lib.load().fpl_conv3d_weight_image_bytes(cout if transpose else cin, cin if transpose else cout, kd)
-        img = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
-        call("fpl_conv3d_prep_weight", ptr(w), cin, cout, kd, 1 if transpose else 0, ptr(img), stream_ptr())
-        self._img_cache[key] = (w._version, img)
-        return img
+        ent = self._img_cache.get((id(conv.weight), transpose))
+        if ent is None or ent[0] != conv.weight._version:
+            self._refresh_weight_images(with_dgrad=transpose)
+            ent = self._img_cache[(id(conv.weight), transpose)]
+        return ent[1]
 
     def _conv_fwd(self, u, xin, x_img, y, stats, n, geo, ws):
         d, h, w = geo
@@ -295,9 +394,11 @@ class UNet2D5_dsbn(nn.Module):
                 rec["next_offset"] += 2 * n * d * (c // 8) * h * w
         pv = pooled.args() if pooled is not None else (None, 0, 0)
         call("fpl_dsbn_act_fwd", ptr(y), ptr(scale), ptr(shift), ptr(u.prelu.weight), *out.args(), *pv,
-             ptr(pool_idx), pool_kd, p, ptr(mask), seed, offset, n, d, h, w, c, stream_ptr())
+             ptr(pool_idx), pool_kd, p, ptr(mask), seed, offset, ptr(rec["seed_dev"]) if p > 0.0 and mask is None else None,
+             n, d, h, w, c, stream_ptr())
         rec[u.name] = dict(y=y, xin=xin, scale=scale, shift=shift, mean=mean, invstd=invstd, training=training,
-                           p=p, mask=mask, seed=seed, offset=offset, geo=geo, bn=bn)
+                           p=p, mask=mask, seed=seed, offset=offset, geo=geo, bn=bn,
+                           seed_dev=rec["seed_dev"] if p > 0.0 and mask is None else None)
 
     # -- whole-network forward --------------------------------------------------------------
     def _run_forward(self, x, domain, ws):
@@ -305,10 +406,14 @@ class UNet2D5_dsbn(nn.Module):
         geo = self._geometry(x.shape)
         ft = self.ft_chns
         small = _SmallPool(ws, "fwd", x.device)
+        self._refresh_weight_images(with_dgrad=torch.is_grad_enabled())
         # dropout stream: (seed, per-layer offset) drawn from torch's CPU generator, so torch.manual_seed
         # makes MC-dropout passes reproducible; backward regenerates the same Philox stream
-        rec = {"seed": int(torch.empty((), dtype=torch.int64).random_().item()),
-               "next_offset": 0, "geo": geo, "n": n, "x": x}
+        if self._seed_from_device:
+            seed, seed_dev = 0, self.ensure_rng(x.device)
+        else:
+            seed, seed_dev = self._draw_seed(), None
+        rec = {"seed": seed, "seed_dev": seed_dev, "next_offset": 0, "geo": geo, "n": n, "x": x}
         cur = None
         for i in range(5):
             u1, u2 = self._down_units[i]
@@ -365,7 +470,7 @@ class UNet2D5_dsbn(nn.Module):
         g1a = g1.args() if g1 is not None else (None, 0, 0)
         gpa = g_pool.args() if g_pool is not None else (None, 0, 0)
         common = (ptr(r["y"]), *g1a, *gpa, ptr(pool_idx), pool_kd, ptr(r["scale"]), ptr(r["shift"]), ptr(r["mean"]),
-                  ptr(r["invstd"]), ptr(u.prelu.weight), r["p"], ptr(r["mask"]), r["seed"], r["offset"])
+                  ptr(r["invstd"]), ptr(u.prelu.weight), r["p"], ptr(r["mask"]), r["seed"], r["offset"], ptr(r["seed_dev"]))
         call("fpl_dsbn_act_bwd_reduce", *common, ptr(red), n, d, h, w, c, st)
         dy = ws.c8("dY:%dx%dx%dx%d" % (c, d, h, w), n, d, c, h, w)
         call("fpl_dsbn_act_bwd_apply", *common, ptr(red), r["training"], ptr(dy), n, d, h, w, c, st)
@@ -498,12 +603,17 @@ class _SmallPool(object):
 class _UNetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, domain, x, *params):
-        ws = net._pool.pop() if net._pool else _Workspace(x.device)
-        if ws.device != x.device:
-            ws = _Workspace(x.device)
+        if torch.cuda.is_current_stream_capturing():
+            # buffers baked into a CUDA graph: a private workspace (allocated from the graph's pool) that is
+            # parked in _graph_ws_keep instead of going back to the recycling pool
+            ws, home = _Workspace(x.device), net._graph_ws_keep
+        else:
+            ws, home = (net._pool.pop() if net._pool else _Workspace(x.device)), net._pool
+            if ws.device != x.device:
+                ws = _Workspace(x.device)
         logits, rec = net._run_forward(x, domain, ws)
         ctx.net, ctx.domain, ctx.rec = net, domain, rec
-        ctx.lease = _Lease(net._pool, ws)
+        ctx.lease = _Lease(home, ws)
         return logits
 
     @staticmethod

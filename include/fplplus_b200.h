@@ -46,6 +46,10 @@ int64_t fpl_conv3d_weight_image_bytes(int cin, int cout, int kd);
  * swapped; `cin`/`cout` are still those of the FORWARD conv). */
 int fpl_conv3d_prep_weight(const float* w, int cin, int cout, int kd, int transpose_flip,
                            void* image, void* stream);
+/* The same for `count` (<= 80) convolutions in ONE launch; all arrays are HOST arrays of length count
+ * (w / images hold device pointers). */
+int fpl_conv3d_prep_weight_batch(int count, const float* const* h_w, const int* h_cin, const int* h_cout,
+                                 const int* h_kd, const int* h_transpose_flip, void* const* h_images, void* stream);
 /* Implicit-GEMM conv on tcgen05/TMEM fed by TMA.  x: C8-planar bf16 with
  * `cin` channels at (x_c8tot, x_c8off); y likewise with `cout` channels.
  * bias may be NULL.  stats (double[2*cout]: sum, sum of squares of the fp32
@@ -110,11 +114,12 @@ int fpl_dsbn_finalize(const double* stats, int64_t count, const float* gamma, co
 /* a = dropout(prelu(y*scale+shift)); optional fused 2x2x2 (pool_kd=2) or 1x2x2
  * (pool_kd=1) max-pool writing `pooled` and the argmax code `pool_idx` (uint8).
  * Dropout: p in [0,1); mask (uint8 keep flags, same C8-planar element order as a
- * dense [N][D][C/8][H][W][8] tensor) if non-NULL, else Philox4x32-10(seed, offset). */
+ * dense [N][D][C/8][H][W][8] tensor) if non-NULL, else Philox4x32-10(seed + *seed_dev, offset);
+ * seed_dev (device uint64, may be NULL) lets a captured CUDA graph draw a fresh mask per replay. */
 int fpl_dsbn_act_fwd(const void* y, const float* scale, const float* shift, const float* slope,
                      void* a, int a_c8tot, int a_c8off,
                      void* pooled, int p_c8tot, int p_c8off, uint8_t* pool_idx, int pool_kd,
-                     float drop_p, const uint8_t* drop_mask, uint64_t seed, uint64_t offset,
+                     float drop_p, const uint8_t* drop_mask, uint64_t seed, uint64_t offset, const uint64_t* seed_dev,
                      int n, int d, int h, int w, int c, void* stream);
 /* Backward.  Gradient wrt the activated output = g1 (C8-planar slice, may be NULL)
  * + max-pool scatter of g_pool through pool_idx (may be NULL).  With dz the gradient
@@ -129,13 +134,13 @@ int fpl_dsbn_act_bwd_reduce(const void* y, const void* g1, int g1_c8tot, int g1_
                             const float* scale, const float* shift, const float* save_mean,
                             const float* save_invstd, const float* slope,
                             float drop_p, const uint8_t* drop_mask, uint64_t seed, uint64_t offset,
-                            double* red, int n, int d, int h, int w, int c, void* stream);
+                            const uint64_t* seed_dev, double* red, int n, int d, int h, int w, int c, void* stream);
 int fpl_dsbn_act_bwd_apply(const void* y, const void* g1, int g1_c8tot, int g1_c8off,
                            const void* g_pool, int gp_c8tot, int gp_c8off, const uint8_t* pool_idx, int pool_kd,
                            const float* scale, const float* shift, const float* save_mean,
                            const float* save_invstd, const float* slope,
                            float drop_p, const uint8_t* drop_mask, uint64_t seed, uint64_t offset,
-                           const double* red, int training, void* dy,
+                           const uint64_t* seed_dev, const double* red, int training, void* dy,
                            int n, int d, int h, int w, int c, void* stream);
 int fpl_dsbn_bwd_finalize(const double* red, const float* scale, const float* save_invstd, int training,
                           float* dgamma, float* dbeta, float* dslope, float* dbias_conv, int c, void* stream);

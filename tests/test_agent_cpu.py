@@ -1,0 +1,83 @@
+"""CPU: host logic of the agent -- .cfg parsing against the reference parser's output (golden made by
+oracle/gen_golden_cfg.py from the reference's own util/parse_config.py), optimiser/scheduler factory,
+round-robin sharding, image-weight map, plugin errors."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from fplplus_b200 import agent as A
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_parse_config_matches_reference_parser(tmp_path):
+    with open(os.path.join(HERE, "golden", "cfg_parse.json")) as f:
+        g = json.load(f)
+    p = tmp_path / "x.cfg"
+    p.write_text(g["text"])
+    cfg = A.synchronize_config(A.parse_config(str(p)))
+    assert json.loads(json.dumps(cfg)) == g["parsed"]
+    # keys are lower-cased, values type-sniffed exactly like the reference
+    assert cfg["testing"]["domian_label"] == 1 and cfg["network"]["feature_chns"] == [16, 32, 64, 128, 256]
+    assert cfg["dataset"]["labeltoprobability_class_num"] == 2
+
+
+def test_value_sniffing_edge_cases():
+    f = A.parse_value_from_string
+    assert f("-5") == -5 and f("1e-4") == 1e-4 and f("0.5") == 0.5
+    assert f("./data/x.csv") == "./data/x.csv"
+    assert f("[1, 2.5, True, None, abc]") == [1, 2.5, True, None, "abc"]
+    assert f("None") is None and f("false") is False and f("DiceLoss") == "DiceLoss"
+
+
+def test_optimizer_and_scheduler_factory():
+    w = [torch.nn.Parameter(torch.zeros(3))]
+    opt = A.get_optimizer("Adam", w, {"learning_rate": 1e-3, "momentum": 0.9, "weight_decay": 1e-5})
+    assert isinstance(opt, torch.optim.Adam) and opt.param_groups[0]["weight_decay"] == 1e-5
+    sch = A.get_lr_scheduler(opt, {"lr_scheduler": "MultiStepLR", "lr_gamma": 0.5, "lr_milestones": [2, 4], "last_iter": -1})
+    lrs = []
+    for _ in range(5):
+        opt.step()
+        sch.step()
+        lrs.append(opt.param_groups[0]["lr"])
+    assert np.allclose(lrs, [1e-3, 5e-4, 5e-4, 2.5e-4, 2.5e-4])
+    assert A.get_lr_scheduler(opt, {"lr_scheduler": None}) is None
+    with pytest.raises(ValueError):
+        A.get_optimizer("LBFGS2", w, {"learning_rate": 1.0})
+
+
+def test_round_robin_sharding_covers_everything_once():
+    items = list(range(11))
+    for world in (1, 2, 4, 8):
+        parts = [A.shard_round_robin(items, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == items
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_undefined_network_and_loss_raise_like_the_reference():
+    cfg = {"dataset": {"tensor_type": "float"}, "network": {"net_type": "Nope", "class_num": 2, "num_domains": 2},
+           "training": {"loss_type": "NoLoss"}, "testing": {}}
+    ag = A.SegmentationAgent(cfg, "train")
+    with pytest.raises(ValueError, match="Undefined network"):
+        ag.create_network()
+    with pytest.raises(ValueError, match="Undefined loss"):
+        ag.create_loss_calculator()
+    with pytest.raises(ValueError):
+        A.SegmentationAgent({"dataset": {"tensor_type": "double"}, "training": {}, "network": {}}, "train")
+
+
+def test_npy_dataset_folds_image_weight_like_set_weight(tmp_path):
+    rng = np.random.default_rng(0)
+    img = rng.standard_normal((4, 6, 8)).astype(np.float32)
+    lab = rng.integers(0, 2, (4, 6, 8)).astype(np.uint8)
+    w = np.where(rng.random((4, 6, 8)) < 0.3, 0.5, 1.0)
+    for n, a in (("i", img), ("l", lab), ("w", w)):
+        np.save(tmp_path / (n + ".npy"), a)
+    ds = A.NpyVolumeDataset([("i.npy", "l.npy", "w.npy", 0.37)], class_num=2, root_dir=str(tmp_path))
+    s = ds[0]
+    assert s["image"].shape == (1, 4, 6, 8) and s["label_prob"].shape == (2, 4, 6, 8)
+    from oracle import fpl_filter
+    np.testing.assert_array_equal(s["pixel_weight"][0].numpy(), fpl_filter.set_weight_(np.float32(0.37), w.astype(np.float32)))

@@ -1,0 +1,71 @@
+"""CPU, world size 2 over gloo: the host-side multi-GPU logic (gradient bucket all-reduce driven by the
+network's grad_ready_hook protocol, volume sharding + final gather/sort of the FPL uncertainties)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fplplus_b200 import agent as A, fpl
+        # ---- gradient reducer: the hook protocol of UNet2D5_dsbn._run_backward (flat, start, end, last) ----
+        g = torch.Generator().manual_seed(100 + rank)
+        n = 3_000_000                                        # 12 MB of fp32 "gradients"
+        flat = torch.randn(n, generator=g)
+        mine = flat.clone()
+        red = A.GradAllReducer(bucket_bytes=4 << 20)
+        cuts = [0, 10, 700_000, 700_100, 1_900_000, 2_999_990, n]       # irregular completion order
+        for i in range(len(cuts) - 1):
+            red.hook(flat, cuts[i], cuts[i + 1], i == len(cuts) - 2)
+        n_buckets = len(red._pending)
+        red.finish()
+        others = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(others, mine)
+        ref = torch.stack(others).mean(0)
+        ok_avg = bool(torch.allclose(flat, ref, rtol=1e-6, atol=1e-7))
+        # ---- inference: volumes round-robin, gather of (value, name) pairs, host sort ----
+        cfg = {"dataset": {"tensor_type": "float"}, "network": {}, "training": {}, "testing": {}}
+        ag = A.SegmentationAgent(cfg, "test")
+        names = ["vol_%02d.nii.gz" % i for i in range(7)]
+        table = {nm: [1 if i == 3 else 0.01 * (7 - i)] for i, nm in enumerate(names)}
+        local = {nm: table[nm] for nm in A.shard_round_robin(names, ag.rank, ag.world)}
+        merged = ag._gather_dict(local)
+        srt = fpl.sort_uncertainty(merged)
+        q.put((rank, ok_avg, n_buckets, len(local), [nm for _v, nm in srt], ag.world))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gradient_average_and_sharded_inference():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    names = ["vol_%02d.nii.gz" % i for i in range(7)]
+    expected = [names[i] for i in (6, 5, 4, 2, 1, 0, 3)]        # ascending uncertainty, the sentinel (1) last
+    for rank, ok_avg, n_buckets, n_local, order, w in res:
+        assert ok_avg, "rank %d: all-reduced buckets != mean over ranks" % rank
+        assert n_buckets == 3                                    # 12 MB in >= 4 MB buckets + the tail flush
+        assert w == 2 and n_local == (4 if rank == 0 else 3)
+        assert order == expected

@@ -299,7 +299,7 @@ def test_dsbn_act_fwd_bwd(training, pool_kd, drop_p):
         idx = torch.empty((n, d // pool_kd, c // 8, h // 2, w // 2, 8), dtype=torch.uint8, device=DEV)
     sl = slope.detach().to(DEV)
     _call("fpl_dsbn_act_fwd", _p(yb), _p(scale), _p(shift), _p(sl), _p(act), 2 * c // 8, 0, _p(pooled), c // 8, 0, _p(idx),
-          pool_kd, drop_p, _p(mask), 0, 0, n, d, h, w, c, _st())
+          pool_kd, drop_p, _p(mask), 0, 0, None, n, d, h, w, c, _st())
     got = from_c8(act).cpu()
     assert max_rel(got[:, :c], a.detach()) < 6e-3
     if pool_kd:
@@ -317,7 +317,7 @@ def test_dsbn_act_fwd_bwd(training, pool_kd, drop_p):
     gpb = to_c8(gp.to(DEV)) if pool_kd else None
     red = torch.zeros(2 * c + 1, dtype=torch.float64, device=DEV)
     common = (_p(yb), _p(g1b), 2 * c // 8, 0, _p(gpb), c // 8, 0, _p(idx), pool_kd, _p(scale), _p(shift), _p(mean),
-              _p(invstd), _p(sl), drop_p, _p(mask), 0, 0)
+              _p(invstd), _p(sl), drop_p, _p(mask), 0, 0, None)
     _call("fpl_dsbn_act_bwd_reduce", *common, _p(red), n, d, h, w, c, _st())
     dy = torch.empty((n, d, c // 8, h, w, 8), dtype=torch.bfloat16, device=DEV)
     _call("fpl_dsbn_act_bwd_apply", *common, _p(red), training, _p(dy), n, d, h, w, c, _st())
@@ -340,7 +340,7 @@ def test_philox_dropout_statistics_and_backward_consistency():
     for seed in (123, 123, 124):
         act = torch.empty((n, d, c // 8, h, w, 8), dtype=torch.bfloat16, device=DEV)
         _call("fpl_dsbn_act_fwd", _p(yb), _p(one), _p(zero), _p(sl), _p(act), c // 8, 0, None, 0, 0, None, 0, p, None,
-              seed, 16, n, d, h, w, c, _st())
+              seed, 16, None, n, d, h, w, c, _st())
         outs.append(from_c8(act).cpu())
     assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
     kept = outs[0] != 0
@@ -353,7 +353,7 @@ def test_philox_dropout_statistics_and_backward_consistency():
     red = torch.zeros(2 * c + 1, dtype=torch.float64, device=DEV)
     dy = torch.empty((n, d, c // 8, h, w, 8), dtype=torch.bfloat16, device=DEV)
     _call("fpl_dsbn_act_bwd_apply", _p(yb), _p(g1), c // 8, 0, None, 0, 0, None, 0, _p(one), _p(zero), _p(zero), _p(one),
-          _p(sl), p, None, 123, 16, _p(red), 0, _p(dy), n, d, h, w, c, _st())
+          _p(sl), p, None, 123, 16, None, _p(red), 0, _p(dy), n, d, h, w, c, _st())
     assert torch.equal(from_c8(dy).cpu() != 0, kept)
 
 

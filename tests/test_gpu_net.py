@@ -219,13 +219,16 @@ def test_dropout_mask_injection_matches_oracle():
     _check_labels(out, ref, overall=0.99)
 
 
-def test_two_domain_step_like_training_all():
-    """zero_grad; L=(L0+L1)/2 over two forwards; backward; Adam step -- vs the oracle trainer."""
+@pytest.mark.parametrize("fused", [False, True])
+def test_two_domain_step_like_training_all(fused):
+    """zero_grad; L=(L0+L1)/2 over two forwards; backward; Adam step -- vs the oracle trainer.
+    ``fused=True``: torch's multi-tensor Adam does not bump tensor versions, the staged bf16 weight
+    images must be invalidated explicitly (what the agent does) or step 2 would run on stale weights."""
     from oracle.train_step import OracleTrainer
     from fplplus_b200.loss import DiceLoss
     params = dict(NET_PARAMS, dropout=[0.0] * 5)
     net = _net(params).train()
-    opt = torch.optim.Adam(net.parameters(), 1e-3, weight_decay=1e-5)
+    opt = torch.optim.Adam(net.parameters(), 1e-3, weight_decay=1e-5, fused=fused)
     oracle = OracleTrainer(synth.synth_state_dict(), params, lr=1e-3, weight_decay=1e-5)
     crit = DiceLoss({})
     batches = []
@@ -233,7 +236,8 @@ def test_two_domain_step_like_training_all():
         x = synth.synth_image(2, 1, SHAPE, seed=10 + dmn)
         lab = synth.synth_label(2, 2, SHAPE, seed=10 + dmn)
         batches.append((torch.from_numpy(x), torch.from_numpy(synth.one_hot(lab, 2)), None))
-    for step in range(2):
+    trace = []
+    for step in range(3):
         opt.zero_grad()
         total = 0.0
         for dmn, (x, y, _w) in enumerate(batches):
@@ -242,9 +246,15 @@ def test_two_domain_step_like_training_all():
         loss = total / 2
         loss.backward()
         opt.step()
+        if fused:
+            net.invalidate_weight_images()
         ref_loss, _m, ref_logits = oracle.step(batches)
         print("step", step, "loss", loss.item(), "oracle", ref_loss)
         np.testing.assert_allclose(loss.item(), ref_loss, rtol=1e-2)
+        trace.append((loss.item(), ref_loss))
+    # the loss moves from step to step as the oracle's does (stale weights would freeze it)
+    for (a0, r0), (a1, r1) in zip(trace[:-1], trace[1:]):
+        assert abs((a1 - a0) - (r1 - r0)) <= 0.3 * abs(r1 - r0) + 1e-4, trace
     # after two Adam steps the weights still track the oracle's
     named = dict(net.named_parameters())
     for key in ("out_conv.weight", "up4.conv.conv3d_2.weight", "block0.conv.conv3d_1.weight", "up4.conv.relu_1.weight"):
