@@ -336,11 +336,17 @@ def run_ours(args):
                "pl_filter": pl}
         if not args.skip_cpu:
             out["cpu_baseline"] = cpu_baseline(bounded_steps=2)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     if out is not None:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        # captured graphs hold NCCL work: drop them before the communicator, and do not let a wedged
+        # communicator teardown turn a finished measurement into a hang
+        dist.barrier()
+        torch.cuda.synchronize()
+        agent._graphs.clear()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def bench_filter(agent, rank, world, barrier, max_over_ranks, args):
@@ -464,6 +470,10 @@ def run_reference(args):
 
 
 def main():
+    wd = int(os.environ.get("FPL_BENCH_WATCHDOG", "0"))
+    if wd > 0:                       # debugging aid: dump every thread's stack and exit if the run wedges
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

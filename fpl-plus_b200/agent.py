@@ -277,7 +277,8 @@ class SegmentationAgent(object):
         self.last_outputs = {}
         # B200-first: the whole optimiser step (both forwards, loss, backward, gradient all-reduce, Adam)
         # is captured once per batch signature into a CUDA graph and replayed ([training] cuda_graph, default on)
-        self.use_cuda_graph = bool(config.get('training', {}).get('cuda_graph', True))
+        self.use_cuda_graph = (bool(config.get('training', {}).get('cuda_graph', True))
+                               and os.environ.get("FPL_CUDA_GRAPH", "1") != "0")
         self._graphs = {}
         self._host_it = 0
 
