@@ -571,11 +571,60 @@ __global__ void __launch_bounds__(128) convt_dgrad_kernel(ConvTP P) {
     st_bf16x8(&P.dx[((int64_t)nd * P.dx_c8tot + P.dx_c8off + ci8) * HW + hw], acc);
 }
 
+// fp32 NCDHW [N][C][D][H][W] -> C8-planar bf16 channel groups (zero padded to a multiple of 8 channels),
+// optional per-channel sums (the bias gradient when the tensor is dlogits).  grid: (chunks of H*W, N*D)
+__global__ void __launch_bounds__(256) pack_ncdhw_c8_kernel(const float* __restrict__ x, int C, bf16x8* out, int c8tot,
+                                                            int c8off, int groups, float* chan_sum, int D, int HW) {
+    const int nd = blockIdx.y, n = nd / D, d = nd - n * D;
+    float s[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s[i] = 0.f;
+    for (int hw = blockIdx.x * blockDim.x + threadIdx.x; hw < HW; hw += gridDim.x * blockDim.x) {
+        for (int g = 0; g < groups; ++g) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c = g * 8 + i;
+                f[i] = c < C ? __ldg(x + (((int64_t)n * C + c) * D + d) * HW + hw) : 0.f;
+                if (g < 2) s[g * 8 + i] += f[i];
+            }
+            st_bf16x8(out + ((int64_t)nd * c8tot + c8off + g) * HW + hw, f);
+        }
+    }
+    if (chan_sum != nullptr) {
+        __shared__ float sm[8][16];
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            float t = warp_sum(s[i]);
+            if (lane == 0) sm[wid][i] = t;
+        }
+        __syncthreads();
+        if (threadIdx.x < 16 && threadIdx.x < C) {
+            float t = 0.f;
+            for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x];
+            atomicAdd(chan_sum + threadIdx.x, t);
+        }
+    }
+}
+
 }  // namespace
 
 // ======================================================================================
 // C ABI
 // ======================================================================================
+extern "C" int fpl_pack_ncdhw_to_c8(const float* x, int c, void* out, int out_c8tot, int out_c8off, int groups,
+                                    float* chan_sum, int n, int d, int h, int w, void* stream) {
+    FPL_REQUIRE(c >= 1 && groups >= 1 && c <= groups * 8, "fpl_pack_ncdhw_to_c8: %d channels do not fit %d groups", c, groups);
+    FPL_REQUIRE(chan_sum == nullptr || c <= 16, "fpl_pack_ncdhw_to_c8: channel sums need c <= 16");
+    FPL_REQUIRE((int64_t)n * d <= 65535, "fpl_pack_ncdhw_to_c8: too many planes");
+    int chunks = (h * w + 1023) / 1024;
+    pack_ncdhw_c8_kernel<<<dim3(chunks, n * d), 256, 0, (cudaStream_t)stream>>>(x, c, (bf16x8*)out, out_c8tot, out_c8off,
+                                                                               groups, chan_sum, d, h * w);
+    FPL_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int fpl_conv3d_direct(const void* x, int x_c8tot, int x_c8off, const float* w, const float* bias, void* y,
                                  int y_c8tot, int y_c8off, double* stats, int n, int d, int h, int w_, int cin,
                                  int cout, int kd, int transpose_flip, int round_w_bf16, void* stream) {

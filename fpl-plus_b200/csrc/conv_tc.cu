@@ -79,6 +79,8 @@ struct TcParams {
     int nb, kc, nslices, nchunks, a_bytes, b_bytes, stages, tmem_cols;
     int tiles_h, tiles_w, total_tiles;
     int dbg_swap_lbo_sbo;
+    float* logits;        // head mode: fp32 NCDHW output of the first `classes` channels instead of bf16 C8-planar
+    int classes;
 };
 
 struct TileCoord {
@@ -256,7 +258,14 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
                         v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z;
                         v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
                     }
-                    if (valid) {
+                    if (P.logits != nullptr) {
+                        if (valid && k == 0) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                if (i < P.classes)
+                                    P.logits[(((int64_t)c.n * P.classes + i) * P.D + c.d) * HW + (int64_t)h * P.W + w] = v[i];
+                        }
+                    } else if (valid) {
                         st_bf16x8(P.y + out_base + (int64_t)(c0 / 8) * HW, v);
                         st_bf16x8(P.y + out_base + (int64_t)(c0 / 8 + 1) * HW, v + 8);
                     }
@@ -406,9 +415,9 @@ extern "C" void fpl_debug_set(int key, long long value) {
     if (key >= 10) fpl_wgrad_debug_set(key, value);
 }
 
-extern "C" int fpl_conv3d_tc(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias, void* y,
-                             int y_c8tot, int y_c8off, double* stats, int n, int d, int h, int w, int cin, int cout,
-                             int kd, void* stream) {
+static int conv3d_tc_launch(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias, void* y,
+                            int y_c8tot, int y_c8off, double* stats, int n, int d, int h, int w, int cin, int cout,
+                            int kd, float* logits, int classes, void* stream) {
     TcConfig c;
     FPL_REQUIRE(make_config(cin, cout, c), "fpl_conv3d_tc: unsupported channels (%d -> %d); need multiples of 16", cin, cout);
     FPL_REQUIRE(kd == 1 || kd == 3, "fpl_conv3d_tc: kd=%d must be 1 or 3", kd);
@@ -437,6 +446,7 @@ extern "C" int fpl_conv3d_tc(const void* x, int x_c8tot, int x_c8off, const void
     FPL_REQUIRE(total < (1ll << 30), "fpl_conv3d_tc: too many tiles");
     P.total_tiles = (int)total;
     P.dbg_swap_lbo_sbo = g_dbg_swap;
+    P.logits = logits; P.classes = classes;
     FPL_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
     int ctas_per_sm = c.smem_bytes <= 110 * 1024 ? 2 : 1;
     int grid = FPL_NUM_SMS * ctas_per_sm;
@@ -444,4 +454,19 @@ extern "C" int fpl_conv3d_tc(const void* x, int x_c8tot, int x_c8off, const void
     conv3d_tc_kernel<<<grid, kNumThreads, c.smem_bytes, (cudaStream_t)stream>>>(xmap, P);
     FPL_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int fpl_conv3d_tc(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias, void* y,
+                             int y_c8tot, int y_c8off, double* stats, int n, int d, int h, int w, int cin, int cout,
+                             int kd, void* stream) {
+    return conv3d_tc_launch(x, x_c8tot, x_c8off, image, bias, y, y_c8tot, y_c8off, stats, n, d, h, w, cin, cout, kd,
+                            nullptr, 0, stream);
+}
+
+extern "C" int fpl_head_conv_tc(const void* x, int x_c8tot, int x_c8off, const void* image16, const float* bias16,
+                                float* logits, int n, int d, int h, int w, int cin, int classes, void* stream) {
+    FPL_REQUIRE(classes >= 1 && classes <= 8, "fpl_head_conv_tc: class_num=%d not in [1,8]", classes);
+    FPL_REQUIRE(logits != nullptr, "fpl_head_conv_tc: logits required");
+    return conv3d_tc_launch(x, x_c8tot, x_c8off, image16, bias16, nullptr, 0, 0, nullptr, n, d, h, w, cin, 16, 1, logits,
+                            classes, stream);
 }

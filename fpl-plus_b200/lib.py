@@ -32,6 +32,8 @@ _SIGNATURES = {
     "fpl_stem_conv_fwd": (_I, [_P, _P, _P, _P, _I, _I, _P] + [_I] * 7 + [_P]),
     "fpl_stem_conv_wgrad": (_I, [_P, _P, _I, _I, _P] + [_I] * 7 + [_P]),
     "fpl_head_conv_fwd": (_I, [_P, _I, _I, _P, _P, _P] + [_I] * 6 + [_P]),
+    "fpl_head_conv_tc": (_I, [_P, _I, _I, _P, _P, _P] + [_I] * 6 + [_P]),
+    "fpl_pack_ncdhw_to_c8": (_I, [_P, _I, _P, _I, _I, _I, _P] + [_I] * 4 + [_P]),
     "fpl_head_conv_bwd": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _P, _P] + [_I] * 6 + [_P]),
     "fpl_convt_k2s2_fwd": (_I, [_P, _I, _I, _P, _P, _P, _I, _I] + [_I] * 7 + [_P]),
     "fpl_convt_k2s2_bwd": (_I, [_P, _I, _I, _P, _P, _I, _I, _P, _I, _I, _P, _P] + [_I] * 7 + [_P]),

@@ -166,6 +166,9 @@ class UNet2D5_dsbn(nn.Module):
         self._graph_ws_keep = []        # workspaces baked into captured graphs: never recycled
         self.cuda_graphs = os.environ.get("FPL_CUDA_GRAPH", "1") != "0"
         self.grad_ready_hook = None     # callable(flat_grad, start, end, last) fired as buckets complete (DDP)
+        self._head = UNet2D5_dsbn._HeadConv(self.out_conv)
+        self._head_unit = None
+        self._head_dirty = True
         self._build_plan()
 
     # -- plan -------------------------------------------------------------------------------
@@ -186,6 +189,33 @@ class UNet2D5_dsbn(nn.Module):
             (c1, n1, r1, d1), (c2, n2, r2, _d2) = u.conv.units()
             self._up_units.append((_Unit("up%d.conv#1" % k, c1, n1, r1, d1, kd),
                                    _Unit("up%d.conv#2" % k, c2, n2, r2, None, kd)))
+
+    class _HeadConv(object):
+        """The head's weights zero-padded to 16 output channels (a plain tensor whose ``_version`` drives the
+        weight-image cache), so that the (1,3,3) head runs through the same tensor-core kernels."""
+
+        def __init__(self, out_conv):
+            self.src = out_conv
+            self.weight = None
+            self.bias = None
+            self.in_channels, self.out_channels = out_conv.in_channels, 16
+            self.seen = None
+
+        def sync(self, force):
+            w = self.src.weight
+            if self.weight is None or self.weight.device != w.device:
+                self.weight = torch.zeros((16,) + tuple(w.shape[1:]), dtype=torch.float32, device=w.device)
+                self.bias = torch.zeros(16, dtype=torch.float32, device=w.device)
+                force = True
+            ver = (w._version, self.src.bias._version)
+            if force or ver != self.seen:
+                k = w.shape[0]
+                self.weight[:k].copy_(w.detach())
+                self.bias[:k].copy_(self.src.bias.detach())
+                self.seen = ver
+
+    def _head_tc(self):
+        return self._use_tc(self.ft_chns[0], 16) and self.n_class <= 8 and os.environ.get("FPL_HEAD_IMPL", "tc") == "tc"
 
     def _grad_params(self, domain):
         """Parameters that receive gradients, in the order backward completes them."""
@@ -312,6 +342,7 @@ class UNet2D5_dsbn(nn.Module):
         agent calls this after ``optimizer.step()``."""
         for ent in self._img_cache.values():
             ent[0] = -1
+        self._head_dirty = True
 
     def _tc_convs(self):
         out = []
@@ -319,6 +350,12 @@ class UNet2D5_dsbn(nn.Module):
             for u in (u1, u2):
                 if not u.is_stem and self._use_tc(u.cin, u.cout):
                     out.append(u)
+        if self._head_tc():
+            if self._head_unit is None:
+                self._head_unit = _Unit("head", self._head, None, None, None, 1)
+            self._head.sync(self._head_dirty)
+            self._head_dirty = False
+            out.append(self._head_unit)
         return out
 
     def _refresh_weight_images(self, with_dgrad):
@@ -455,8 +492,13 @@ class UNet2D5_dsbn(nn.Module):
             low = a2
         d, h, w = geo[0]
         logits = torch.empty((n, self.n_class, d, h, w), dtype=torch.float32, device=x.device)
-        call("fpl_head_conv_fwd", *low.args(), ptr(self.out_conv.weight), ptr(self.out_conv.bias), ptr(logits),
-             n, d, h, w, ft[0], self.n_class, stream_ptr())
+        if self._head_tc():
+            img = self._weight_image(self._head, 1, False, ws)
+            call("fpl_head_conv_tc", *low.args(), ptr(img), ptr(self._head.bias), ptr(logits), n, d, h, w, ft[0],
+                 self.n_class, stream_ptr())
+        else:
+            call("fpl_head_conv_fwd", *low.args(), ptr(self.out_conv.weight), ptr(self.out_conv.bias), ptr(logits),
+                 n, d, h, w, ft[0], self.n_class, stream_ptr())
         rec["head_in"] = low
         return logits, rec
 
@@ -479,7 +521,16 @@ class UNet2D5_dsbn(nn.Module):
              ptr(grads[bn.weight]), ptr(grads[bn.bias]), ptr(grads[u.prelu.weight]), ptr(grads[u.conv.bias]), c, st)
         dw = grads[u.conv.weight]
         if u.is_stem:
-            call("fpl_stem_conv_wgrad", ptr(r["x_img"]), ptr(dy), c // 8, 0, ptr(dw), n, u.cin, d, h, w, c, u.kd, st)
+            if self._use_tc(16, c) and u.cin <= 8 and os.environ.get("FPL_WGRAD_IMPL", "tc") == "tc":
+                # image -> one bf16 channel group (zero padded), then the tensor-core wgrad with Cin = 8
+                x8 = ws.c8("X8", n, d, 8, h, w)
+                call("fpl_pack_ncdhw_to_c8", ptr(r["x_img"]), u.cin, ptr(x8), 1, 0, 1, None, n, d, h, w, st)
+                dw8 = ws.get("dW8", (c, 8, u.kd, 3, 3), torch.float32)
+                dw8.zero_()
+                call("fpl_conv3d_wgrad_tc", ptr(x8), 1, 0, ptr(dy), c // 8, 0, ptr(dw8), n, d, h, w, 8, c, u.kd, st)
+                dw.view(c, u.cin, u.kd, 3, 3).add_(dw8[:, :u.cin])
+            else:
+                call("fpl_stem_conv_wgrad", ptr(r["x_img"]), ptr(dy), c // 8, 0, ptr(dw), n, u.cin, d, h, w, c, u.kd, st)
             return None
         xin = r["xin"]
         self._wgrad(u, xin, dy, dw, n, d, h, w)
@@ -529,8 +580,22 @@ class UNet2D5_dsbn(nn.Module):
         d, h, w = geo[0]
         head_in = rec["head_in"]
         g = C8(ws.c8("dX:head", n, d, ft[0], h, w))
-        call("fpl_head_conv_bwd", *head_in.args(), ptr(self.out_conv.weight), ptr(dlogits.contiguous()), *g.args(),
-             ptr(grads[self.out_conv.weight]), ptr(grads[self.out_conv.bias]), n, d, h, w, ft[0], self.n_class, st)
+        dlogits = dlogits.contiguous()
+        if self._head_tc():
+            # dlogits -> bf16 C8-planar (zero padded to 16 channels) + the bias gradient; then the ordinary
+            # tensor-core dgrad / wgrad with the padded head weights
+            k = self.n_class
+            dl16 = ws.c8("dL16", n, d, 16, h, w)
+            call("fpl_pack_ncdhw_to_c8", ptr(dlogits), k, ptr(dl16), 2, 0, 2, ptr(grads[self.out_conv.bias]), n, d, h, w, st)
+            img_t = self._weight_image(self._head, 1, True, ws)
+            call("fpl_conv3d_tc", ptr(dl16), 2, 0, ptr(img_t), None, *g.args(), None, n, d, h, w, 16, ft[0], 1, st)
+            dw16 = ws.get("dW16", (16, ft[0], 1, 3, 3), torch.float32)
+            dw16.zero_()
+            call("fpl_conv3d_wgrad_tc", *head_in.args(), ptr(dl16), 2, 0, ptr(dw16), n, d, h, w, ft[0], 16, 1, st)
+            grads[self.out_conv.weight].view(k, ft[0], 1, 3, 3).add_(dw16[:k])
+        else:
+            call("fpl_head_conv_bwd", *head_in.args(), ptr(self.out_conv.weight), ptr(dlogits), *g.args(),
+                 ptr(grads[self.out_conv.weight]), ptr(grads[self.out_conv.bias]), n, d, h, w, ft[0], self.n_class, st)
         ups = [self.up1, self.up2, self.up3, self.up4]
         skip_grads = {}
         done = 2

@@ -84,6 +84,15 @@ int fpl_stem_conv_wgrad(const float* x, const void* dy, int dy_c8tot, int dy_c8o
 /* head: unet2d5_dsbn.py:293-294, nn.Conv3d(C0, classes, (1,3,3), padding (0,1,1)); logits fp32 NCDHW. */
 int fpl_head_conv_fwd(const void* x, int x_c8tot, int x_c8off, const float* w, const float* bias,
                       float* logits, int n, int d, int h, int w_, int cin, int classes, void* stream);
+/* The head on tcgen05: `image16` / `bias16` are the staged image / bias of the head weights zero-padded to
+ * 16 output channels ((1,3,3) taps, kd = 1); the epilogue writes the first `classes` channels as fp32 NCDHW. */
+int fpl_head_conv_tc(const void* x, int x_c8tot, int x_c8off, const void* image16, const float* bias16,
+                     float* logits, int n, int d, int h, int w, int cin, int classes, void* stream);
+/* fp32 NCDHW [N,c,D,H,W] -> C8-planar bf16 channel groups (`groups` x 8 channels, zero padded) at
+ * (out_c8tot, out_c8off); chan_sum (fp32[c], may be NULL, c <= 16) ACCUMULATES the per-channel sums (the
+ * head's bias gradient when x is dlogits).  Feeds dlogits / the image to the tensor-core dgrad / wgrad. */
+int fpl_pack_ncdhw_to_c8(const float* x, int c, void* out, int out_c8tot, int out_c8off, int groups,
+                         float* chan_sum, int n, int d, int h, int w, void* stream);
 /* dlogits fp32 NCDHW -> dx C8-planar bf16; dw[classes][cin][1][3][3], db[classes] accumulated. */
 int fpl_head_conv_bwd(const void* x, int x_c8tot, int x_c8off, const float* w, const float* dlogits,
                       void* dx, int dx_c8tot, int dx_c8off, float* dw, float* db,

@@ -209,8 +209,10 @@ def forward(state, x, domain, params, bn_training=False, drop_training=None, mas
                 h = _RoundFwd.apply(h) if bf16 else h
             cat = torch.cat([skip, h], dim=1)
             h = conv_block(state, pre + ".conv", cat, domain, 3, drop[lvl], bn_training, drop_training, masks, bf16)
-    return F.conv3d(_RoundBwd.apply(h) if bf16 else h, state["out_conv.weight"], state["out_conv.bias"],
-                    padding=(0, 1, 1))
+    if bf16:     # the head runs on the tensor cores too: bf16 weights, dlogits stored in bf16 for dgrad / wgrad
+        return _RoundBwd.apply(F.conv3d(_RoundBwd.apply(h), _wq(state["out_conv.weight"]), state["out_conv.bias"],
+                                        padding=(0, 1, 1)))
+    return F.conv3d(h, state["out_conv.weight"], state["out_conv.bias"], padding=(0, 1, 1))
 
 
 def to_torch_state(np_state, requires_grad=False):
