@@ -281,6 +281,15 @@ class SegmentationAgent(object):
                                and os.environ.get("FPL_CUDA_GRAPH", "1") != "0")
         self._graphs = {}
         self._host_it = 0
+        self.dual_stream = (bool(config.get('training', {}).get('dual_stream', True))
+                            and os.environ.get("FPL_DUAL_STREAM", "1") != "0")
+        self._side_stream = None
+        self._copy_stream = None
+        if self.dual_stream:
+            try:
+                torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+            except Exception:
+                pass
 
     # -- plugin setters (agent_abstract.py:67-134) -------------------------------------------
     def set_datasets(self, train_set, valid_set, test_set):
@@ -428,20 +437,38 @@ class SegmentationAgent(object):
         inval = getattr(self.net, "invalidate_weight_images", None)
         if inval is not None:
             inval()                 # fused optimisers do not bump tensor versions (see UNet2D5_dsbn)
+        present = [d for d, b in enumerate(batches) if b is not None]
+        main = torch.cuda.current_stream()
+        fork = self.dual_stream and len(present) == 2
+        if fork:
+            # the two domain passes are independent until the optimiser: run them on two streams so that the
+            # tensor-pipe-bound convolutions of one overlap the HBM-bound BatchNorm/activation kernels of the other
+            # (autograd replays each backward on the stream its forward ran on)
+            refresh = getattr(self.net, "_refresh_weight_images", None)
+            if refresh is not None:
+                refresh(with_dgrad=True)               # staged once, before the fork
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream()
+            self._side_stream.wait_stream(main)
         total, n_dom, dices = None, 0, []
-        for d, data in enumerate(batches):
-            if data is None:
-                continue
-            x = self._to_device(data['image'])
-            y = self._to_device(data['label_prob'])
-            out = self.net(x, domain_label=d * torch.ones(x.shape[0], dtype=torch.long))
-            loss_d = self.get_loss_value(data, out, y, self.fpl_uda)
+        for d in present:
+            data = batches[d]
+            stream = self._side_stream if (fork and d == present[1]) else main
+            with torch.cuda.stream(stream):
+                x = self._to_device(data['image'])
+                y = self._to_device(data['label_prob'])
+                out = self.net(x, domain_label=d * torch.ones(x.shape[0], dtype=torch.long))
+                loss_d = self.get_loss_value(data, out, y, self.fpl_uda)
+                hd = getattr(self.loss_calculator, "last_hard_dice", None)
+                dices.append(hd() if hd is not None else None)
+            if fork and stream is not main:
+                main.wait_stream(stream)
             total = loss_d if total is None else total + loss_d
             n_dom += 1
-            hd = getattr(self.loss_calculator, "last_hard_dice", None)
-            dices.append(hd() if hd is not None else None)
         loss = total / n_dom if n_dom > 1 else total
         loss.backward()
+        if fork:
+            main.wait_stream(self._side_stream)
         if self.reducer is not None:
             self.reducer.finish()
         self.optimizer.step()
@@ -507,12 +534,49 @@ class SegmentationAgent(object):
                 self.net._seed_from_device = False
             ent["graph"] = g
             # the capture itself does not execute: fall through to the first replay with this step's data
-        for b, sb in zip(batches, ent["static"]):
-            if b is None:
-                continue
-            for k in self._TENSOR_KEYS:
-                if k in sb:
-                    sb[k].copy_(b[k], non_blocking=True)
+        # inputs -> the graph's static buffers.  Host batches go through a double-buffered staging area filled by
+        # a copy stream, so the H2D transfer of step i runs under the replay of step i-1; the hand-over into the
+        # static buffers is a device-to-device copy on the compute stream.
+        main = torch.cuda.current_stream()
+        on_host = any(b is not None and any(not b[k].is_cuda for k in self._TENSOR_KEYS if k in sb)
+                      for b, sb in zip(batches, ent["static"]))
+        if on_host:
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream()
+            if "staging" not in ent:
+                ent["staging"] = [[None if sb is None else {k: torch.empty_like(v) for k, v in sb.items() if torch.is_tensor(v)}
+                                   for sb in ent["static"]] for _ in range(2)]
+                ent["stg_free"] = [torch.cuda.Event(), torch.cuda.Event()]
+                for ev in ent["stg_free"]:
+                    ev.record(main)
+            slot = ent["calls"] & 1
+            stg = ent["staging"][slot]
+            cs = self._copy_stream
+            cs.wait_event(ent["stg_free"][slot])
+            with torch.cuda.stream(cs):
+                for b, st_ in zip(batches, stg):
+                    if b is None:
+                        continue
+                    for k in self._TENSOR_KEYS:
+                        if k in st_:
+                            st_[k].copy_(b[k], non_blocking=True)
+                arrived = torch.cuda.Event()
+                arrived.record(cs)
+            main.wait_event(arrived)
+            for st_, sb in zip(stg, ent["static"]):
+                if sb is None:
+                    continue
+                for k in self._TENSOR_KEYS:
+                    if k in sb:
+                        sb[k].copy_(st_[k], non_blocking=True)
+            ent["stg_free"][slot].record(main)
+        else:
+            for b, sb in zip(batches, ent["static"]):
+                if b is None:
+                    continue
+                for k in self._TENSOR_KEYS:
+                    if k in sb:
+                        sb[k].copy_(b[k], non_blocking=True)
         if getattr(self.net, "_rng_dev", None) is not None:
             self.net._rng_dev.fill_(self.net._draw_seed())
         ent["graph"].replay()

@@ -48,7 +48,27 @@ __global__ void dsbn_finalize_kernel(const double* __restrict__ stats, double in
 // ------------------------------------------------------------------------------------
 // forward: a = dropout(prelu(y*scale+shift)), optional fused max-pool
 // ------------------------------------------------------------------------------------
+// optional fused "finalize" (statistics -> scale/shift, running-stat update) executed in the prologue of
+// the activation kernels: every block derives the affine map of ITS 8 channels, one block per channel
+// group publishes it (for backward) and updates the selected domain's running statistics
+struct BnFinalize {
+    const double* stats;        // non-NULL (training) or running_mean non-NULL (eval) enables the fused path
+    double inv_count, unbias;
+    const float* gamma;
+    const float* beta;
+    float* running_mean;
+    float* running_var;
+    long long* nbt;
+    float momentum, eps;
+    int training, enabled;
+    float* scale;
+    float* shift;
+    float* save_mean;
+    float* save_invstd;
+};
+
 struct ActParams {
+    BnFinalize fin;
     const bf16x8* y;            // dense [N][D][C8][H][W]
     const float* scale;
     const float* shift;
@@ -72,6 +92,41 @@ __device__ __forceinline__ void load_affine(const float* scale, const float* shi
     float4 a = __ldg(s4), b = __ldg(s4 + 1), c = __ldg(h4), d = __ldg(h4 + 1);
     sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; sc[4] = b.x; sc[5] = b.y; sc[6] = b.z; sc[7] = b.w;
     sh[0] = c.x; sh[1] = c.y; sh[2] = c.z; sh[3] = c.w; sh[4] = d.x; sh[5] = d.y; sh[6] = d.z; sh[7] = d.w;
+}
+
+__device__ __forceinline__ void bn_prologue(const BnFinalize& F, int C, int c8, bool writer, float* sc, float* sh) {
+    __shared__ float s_aff[16];
+    if (threadIdx.x < 8) {
+        const int c = c8 * 8 + threadIdx.x;
+        float mean, invstd;
+        if (F.training) {
+            double m = F.stats[c] * F.inv_count;
+            double var = F.stats[C + c] * F.inv_count - m * m;
+            if (var < 0.0) var = 0.0;
+            mean = (float)m;
+            invstd = (float)(1.0 / sqrt(var + (double)F.eps));
+            if (writer && F.running_mean != nullptr) {
+                F.running_mean[c] = (1.0f - F.momentum) * F.running_mean[c] + F.momentum * mean;
+                F.running_var[c] = (1.0f - F.momentum) * F.running_var[c] + F.momentum * (float)(var * F.unbias);
+            }
+        } else {
+            mean = F.running_mean[c];
+            invstd = 1.0f / sqrtf(F.running_var[c] + F.eps);
+        }
+        const float g = F.gamma[c] * invstd;
+        s_aff[threadIdx.x] = g;
+        s_aff[8 + threadIdx.x] = F.beta[c] - mean * g;
+        if (writer) {
+            F.scale[c] = g;
+            F.shift[c] = F.beta[c] - mean * g;
+            F.save_mean[c] = mean;
+            F.save_invstd[c] = invstd;
+            if (c == 0 && F.training && F.nbt != nullptr) *F.nbt += 1;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sc[i] = s_aff[i]; sh[i] = s_aff[8 + i]; }
 }
 
 __device__ __forceinline__ uint32_t keep_bits(const uint2* mask, uint64_t seed, uint64_t offset, int64_t vec, float p) {
@@ -100,7 +155,8 @@ __global__ void __launch_bounds__(kThreads) dsbn_act_fwd_kernel(ActParams P) {
     const float keep_scale = drop ? 1.0f / (1.0f - P.drop_p) : 1.0f;
     const uint64_t seed = P.seed + (P.seed_dev != nullptr ? (uint64_t)__ldg(P.seed_dev) : 0ull);
     float sc[8], sh[8];
-    load_affine(P.scale, P.shift, c8, sc, sh);
+    if (P.fin.enabled) bn_prologue(P.fin, P.C8 * 8, c8, blockIdx.x == 0 && nd == 0, sc, sh);
+    else load_affine(P.scale, P.shift, c8, sc, sh);
     const bf16x8* src = P.y + (int64_t)plane * HW;
     bf16x8* dst = P.a + ((int64_t)nd * P.a_c8tot + P.a_c8off + c8) * HW;
     const int stride = gridDim.x * blockDim.x;
@@ -141,7 +197,8 @@ __global__ void __launch_bounds__(kThreads) dsbn_act_pool_fwd_kernel(ActParams P
     const int d2 = nd2 % D2, n = nd2 / D2;
     const float slope = __ldg(P.slope);
     float sc[8], sh[8];
-    load_affine(P.scale, P.shift, c8, sc, sh);
+    if (P.fin.enabled) bn_prologue(P.fin, P.C8 * 8, c8, blockIdx.x == 0 && nd2 == 0, sc, sh);
+    else load_affine(P.scale, P.shift, c8, sc, sh);
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < HW2; v += gridDim.x * blockDim.x) {
         const int h2 = v / W2, w2 = v - h2 * W2;
         float best[8];
@@ -209,6 +266,10 @@ struct ActBwdParams {
     uint64_t seed, offset;
     const unsigned long long* seed_dev;
     double* red;                // [2C+1]: sum dz, sum dz*xhat, dslope
+    float* fin_dgamma;          // optional fused finalize of the apply pass (all may be NULL)
+    float* fin_dbeta;
+    float* fin_dslope;
+    float* fin_dbias;
     bf16x8* dy;
     int training;
     double inv_count;
@@ -235,6 +296,14 @@ __global__ void __launch_bounds__(kThreads) dsbn_act_bwd_kernel(ActBwdParams P) 
     float s1[8], s2[8], dsl = 0.0f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s1[i] = 0.0f; s2[i] = 0.0f; }
+    if (APPLY && blockIdx.x == 0 && nd == 0 && threadIdx.x < 8) {
+        // one block per channel group publishes the parameter gradients (what fpl_dsbn_bwd_finalize does)
+        const int c = c8 * 8 + threadIdx.x, C = P.C8 * 8;
+        if (P.fin_dbeta != nullptr) P.fin_dbeta[c] += (float)P.red[c];
+        if (P.fin_dgamma != nullptr) P.fin_dgamma[c] += (float)P.red[C + c];
+        if (P.fin_dbias != nullptr && !P.training) P.fin_dbias[c] += __ldg(P.scale + c) * (float)P.red[c];
+        if (c == 0 && P.fin_dslope != nullptr) P.fin_dslope[0] += (float)P.red[2 * C];
+    }
     if (APPLY && P.training) {
         // fold the batch means into the apply constants: dy = sc*(dz - m1 - xhat*m2)
 #pragma unroll
@@ -374,7 +443,7 @@ extern "C" int fpl_dsbn_finalize(const double* stats, int64_t count, const float
     return 0;
 }
 
-extern "C" int fpl_dsbn_act_fwd(const void* y, const float* scale, const float* shift, const float* slope,
+static int act_fwd_launch(const BnFinalize* fin, const void* y, const float* scale, const float* shift, const float* slope,
                                 void* a, int a_c8tot, int a_c8off, void* pooled, int p_c8tot, int p_c8off,
                                 uint8_t* pool_idx, int pool_kd, float drop_p, const uint8_t* drop_mask,
                                 uint64_t seed, uint64_t offset, const uint64_t* seed_dev, int n, int d, int h, int w, int c,
@@ -382,6 +451,7 @@ extern "C" int fpl_dsbn_act_fwd(const void* y, const float* scale, const float* 
     FPL_REQUIRE(c > 0 && c % 8 == 0, "fpl_dsbn_act_fwd: channels (%d) must be a multiple of 8", c);
     FPL_REQUIRE(drop_p >= 0.0f && drop_p < 1.0f, "fpl_dsbn_act_fwd: dropout p=%f out of [0,1)", drop_p);
     ActParams P;
+    if (fin != nullptr) { P.fin = *fin; P.fin.enabled = 1; } else P.fin.enabled = 0;
     P.y = (const bf16x8*)y; P.scale = scale; P.shift = shift; P.slope = slope;
     P.a = (bf16x8*)a; P.a_c8tot = a_c8tot; P.a_c8off = a_c8off;
     P.pooled = (bf16x8*)pooled; P.p_c8tot = p_c8tot; P.p_c8off = p_c8off; P.pool_idx = (uint2*)pool_idx;
@@ -409,6 +479,35 @@ extern "C" int fpl_dsbn_act_fwd(const void* y, const float* scale, const float* 
     return 0;
 }
 
+extern "C" int fpl_dsbn_act_fwd(const void* y, const float* scale, const float* shift, const float* slope,
+                                void* a, int a_c8tot, int a_c8off, void* pooled, int p_c8tot, int p_c8off,
+                                uint8_t* pool_idx, int pool_kd, float drop_p, const uint8_t* drop_mask,
+                                uint64_t seed, uint64_t offset, const uint64_t* seed_dev, int n, int d, int h, int w, int c,
+                                void* stream) {
+    return act_fwd_launch(nullptr, y, scale, shift, slope, a, a_c8tot, a_c8off, pooled, p_c8tot, p_c8off, pool_idx, pool_kd,
+                          drop_p, drop_mask, seed, offset, seed_dev, n, d, h, w, c, stream);
+}
+
+extern "C" int fpl_dsbn_bn_act_fwd(const void* y, const double* stats, int64_t count, const float* gamma, const float* beta,
+                                   float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
+                                   float eps, int training, float* scale, float* shift, float* save_mean,
+                                   float* save_invstd, const float* slope, void* a, int a_c8tot, int a_c8off, void* pooled,
+                                   int p_c8tot, int p_c8off, uint8_t* pool_idx, int pool_kd, float drop_p,
+                                   const uint8_t* drop_mask, uint64_t seed, uint64_t offset, const uint64_t* seed_dev,
+                                   int n, int d, int h, int w, int c, void* stream) {
+    FPL_REQUIRE(training ? (stats != nullptr && count > 0) : (running_mean != nullptr && running_var != nullptr),
+                "fpl_dsbn_bn_act_fwd: missing statistics for training=%d", training);
+    FPL_REQUIRE(scale && shift && save_mean && save_invstd && gamma && beta, "fpl_dsbn_bn_act_fwd: NULL parameter arrays");
+    BnFinalize F;
+    F.stats = stats; F.inv_count = 1.0 / (double)(count > 0 ? count : 1);
+    F.unbias = count > 1 ? (double)count / (double)(count - 1) : 1.0;
+    F.gamma = gamma; F.beta = beta; F.running_mean = running_mean; F.running_var = running_var;
+    F.nbt = (long long*)num_batches_tracked; F.momentum = momentum; F.eps = eps; F.training = training; F.enabled = 1;
+    F.scale = scale; F.shift = shift; F.save_mean = save_mean; F.save_invstd = save_invstd;
+    return act_fwd_launch(&F, y, scale, shift, slope, a, a_c8tot, a_c8off, pooled, p_c8tot, p_c8off, pool_idx, pool_kd,
+                          drop_p, drop_mask, seed, offset, seed_dev, n, d, h, w, c, stream);
+}
+
 static int fill_bwd(ActBwdParams& P, const void* y, const void* g1, int g1_c8tot, int g1_c8off, const void* g_pool,
                     int gp_c8tot, int gp_c8off, const uint8_t* pool_idx, int pool_kd, const float* scale,
                     const float* shift, const float* save_mean, const float* save_invstd, const float* slope,
@@ -426,7 +525,8 @@ static int fill_bwd(ActBwdParams& P, const void* y, const void* g1, int g1_c8tot
     P.scale = scale; P.shift = shift; P.mean = save_mean; P.invstd = save_invstd; P.slope = slope;
     P.drop_p = drop_p; P.drop_mask = (const uint2*)drop_mask; P.seed = seed; P.offset = offset;
     P.seed_dev = (const unsigned long long*)seed_dev;
-    P.red = nullptr; P.dy = nullptr; P.training = 1; P.inv_count = 1.0 / ((double)n * d * h * w);
+    P.red = nullptr; P.dy = nullptr; P.training = 1;
+    P.fin_dgamma = P.fin_dbeta = P.fin_dslope = P.fin_dbias = nullptr; P.inv_count = 1.0 / ((double)n * d * h * w);
     P.N = n; P.D = d; P.C8 = c / 8; P.H = h; P.W = w;
     return 0;
 }
@@ -456,7 +556,7 @@ extern "C" int fpl_dsbn_act_bwd_reduce(const void* y, const void* g1, int g1_c8t
     return 0;
 }
 
-extern "C" int fpl_dsbn_act_bwd_apply(const void* y, const void* g1, int g1_c8tot, int g1_c8off, const void* g_pool,
+static int act_bwd_apply_launch(float* dgamma, float* dbeta, float* dslope, float* dbias_conv, const void* y, const void* g1, int g1_c8tot, int g1_c8off, const void* g_pool,
                                       int gp_c8tot, int gp_c8off, const uint8_t* pool_idx, int pool_kd,
                                       const float* scale, const float* shift, const float* save_mean,
                                       const float* save_invstd, const float* slope, float drop_p,
@@ -471,9 +571,30 @@ extern "C" int fpl_dsbn_act_bwd_apply(const void* y, const void* g1, int g1_c8to
     P.red = const_cast<double*>(red);
     P.dy = (bf16x8*)dy;
     P.training = training;
+    P.fin_dgamma = dgamma; P.fin_dbeta = dbeta; P.fin_dslope = dslope; P.fin_dbias = dbias_conv;
     dsbn_act_bwd_kernel<true><<<bwd_grid(n, d, h, w, c), kThreads, 0, (cudaStream_t)stream>>>(P);
     FPL_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int fpl_dsbn_act_bwd_apply(const void* y, const void* g1, int g1_c8tot, int g1_c8off, const void* g_pool,
+                                      int gp_c8tot, int gp_c8off, const uint8_t* pool_idx, int pool_kd,
+                                      const float* scale, const float* shift, const float* save_mean,
+                                      const float* save_invstd, const float* slope, float drop_p,
+                                      const uint8_t* drop_mask, uint64_t seed, uint64_t offset,
+                                      const uint64_t* seed_dev, const double* red, int training, void* dy, int n, int d,
+                                      int h, int w, int c, void* stream) {
+    return act_bwd_apply_launch(nullptr, nullptr, nullptr, nullptr, y, g1, g1_c8tot, g1_c8off, g_pool, gp_c8tot, gp_c8off, pool_idx, pool_kd, scale, shift, save_mean, save_invstd, slope, drop_p, drop_mask, seed, offset, seed_dev, red, training, dy, n, d, h, w, c, stream);
+}
+
+extern "C" int fpl_dsbn_act_bwd_apply_fin(const void* y, const void* g1, int g1_c8tot, int g1_c8off, const void* g_pool,
+                                      int gp_c8tot, int gp_c8off, const uint8_t* pool_idx, int pool_kd,
+                                      const float* scale, const float* shift, const float* save_mean,
+                                      const float* save_invstd, const float* slope, float drop_p,
+                                      const uint8_t* drop_mask, uint64_t seed, uint64_t offset,
+                                      const uint64_t* seed_dev, const double* red, int training, void* dy, int n, int d,
+                                      int h, int w, int c, void* stream, float* dgamma, float* dbeta, float* dslope, float* dbias_conv) {
+    return act_bwd_apply_launch(dgamma, dbeta, dslope, dbias_conv, y, g1, g1_c8tot, g1_c8off, g_pool, gp_c8tot, gp_c8off, pool_idx, pool_kd, scale, shift, save_mean, save_invstd, slope, drop_p, drop_mask, seed, offset, seed_dev, red, training, dy, n, d, h, w, c, stream);
 }
 
 extern "C" int fpl_dsbn_bwd_finalize(const double* red, const float* scale, const float* save_invstd, int training,

@@ -39,6 +39,10 @@ _SIGNATURES = {
     "fpl_convt_k2s2_bwd": (_I, [_P, _I, _I, _P, _P, _I, _I, _P, _I, _I, _P, _P] + [_I] * 7 + [_P]),
     "fpl_dsbn_finalize": (_I, [_P, _L, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _I, _P]),
     "fpl_dsbn_act_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _F, _P, _U, _U, _P] + [_I] * 5 + [_P]),
+    "fpl_dsbn_bn_act_fwd": (_I, [_P, _P, _L, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P,
+                                 _P, _I, _I, _P, _I, _I, _P, _I, _F, _P, _U, _U, _P] + [_I] * 5 + [_P]),
+    "fpl_dsbn_act_bwd_apply_fin": (_I, [_P, _P, _I, _I, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _F, _P, _U, _U, _P, _P, _I, _P]
+                                   + [_I] * 5 + [_P, _P, _P, _P, _P]),
     "fpl_dsbn_act_bwd_reduce": (_I, [_P, _P, _I, _I, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _F, _P, _U, _U, _P, _P]
                                 + [_I] * 5 + [_P]),
     "fpl_dsbn_act_bwd_apply": (_I, [_P, _P, _I, _I, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _F, _P, _U, _U, _P, _P, _I, _P]

@@ -165,6 +165,8 @@ class UNet2D5_dsbn(nn.Module):
         self._graphs = {}               # (shape, domain, mode) -> _GraphedForward (no-grad forwards)
         self._graph_ws_keep = []        # workspaces baked into captured graphs: never recycled
         self.cuda_graphs = os.environ.get("FPL_CUDA_GRAPH", "1") != "0"
+        self.wgrad_side_stream = os.environ.get("FPL_WGRAD_STREAM", "0") != "0"   # measured: no gain on top of the dual-domain streams
+        self._aux_streams = {}
         self.grad_ready_hook = None     # callable(flat_grad, start, end, last) fired as buckets complete (DDP)
         self._head = UNet2D5_dsbn._HeadConv(self.out_conv)
         self._head_unit = None
@@ -418,9 +420,6 @@ class UNet2D5_dsbn(nn.Module):
             raise RuntimeError("fplplus_b200 supports tensor_type=float only")
         scale, shift, mean, invstd = small.f32(c), small.f32(c), small.f32(c), small.f32(c)
         training = 1 if bn.training else 0
-        call("fpl_dsbn_finalize", ptr(stats), n * d * h * w, ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean),
-             ptr(bn.running_var), ptr(bn.num_batches_tracked), float(bn.momentum), float(bn.eps), training,
-             ptr(scale), ptr(shift), ptr(mean), ptr(invstd), c, stream_ptr())
         p, mask, seed, offset = 0.0, None, 0, 0
         if u.dropout is not None and u.dropout.training and u.dropout.p > 0.0:
             p = float(u.dropout.p)
@@ -430,7 +429,10 @@ class UNet2D5_dsbn(nn.Module):
                 seed, offset = rec["seed"], rec["next_offset"]
                 rec["next_offset"] += 2 * n * d * (c // 8) * h * w
         pv = pooled.args() if pooled is not None else (None, 0, 0)
-        call("fpl_dsbn_act_fwd", ptr(y), ptr(scale), ptr(shift), ptr(u.prelu.weight), *out.args(), *pv,
+        # statistics -> affine map (+ running statistics) in the prologue of the activation kernel
+        call("fpl_dsbn_bn_act_fwd", ptr(y), ptr(stats), n * d * h * w, ptr(bn.weight), ptr(bn.bias),
+             ptr(bn.running_mean), ptr(bn.running_var), ptr(bn.num_batches_tracked), float(bn.momentum), float(bn.eps),
+             training, ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(u.prelu.weight), *out.args(), *pv,
              ptr(pool_idx), pool_kd, p, ptr(mask), seed, offset, ptr(rec["seed_dev"]) if p > 0.0 and mask is None else None,
              n, d, h, w, c, stream_ptr())
         rec[u.name] = dict(y=y, xin=xin, scale=scale, shift=shift, mean=mean, invstd=invstd, training=training,
@@ -514,11 +516,10 @@ class UNet2D5_dsbn(nn.Module):
         common = (ptr(r["y"]), *g1a, *gpa, ptr(pool_idx), pool_kd, ptr(r["scale"]), ptr(r["shift"]), ptr(r["mean"]),
                   ptr(r["invstd"]), ptr(u.prelu.weight), r["p"], ptr(r["mask"]), r["seed"], r["offset"], ptr(r["seed_dev"]))
         call("fpl_dsbn_act_bwd_reduce", *common, ptr(red), n, d, h, w, c, st)
-        dy = ws.c8("dY:%dx%dx%dx%d" % (c, d, h, w), n, d, c, h, w)
-        call("fpl_dsbn_act_bwd_apply", *common, ptr(red), r["training"], ptr(dy), n, d, h, w, c, st)
+        dy = ws.c8("dY:" + u.name, n, d, c, h, w)       # per unit: the side-stream wgrad may still be reading it
         bn = r["bn"]
-        call("fpl_dsbn_bwd_finalize", ptr(red), ptr(r["scale"]), ptr(r["invstd"]), r["training"],
-             ptr(grads[bn.weight]), ptr(grads[bn.bias]), ptr(grads[u.prelu.weight]), ptr(grads[u.conv.bias]), c, st)
+        call("fpl_dsbn_act_bwd_apply_fin", *common, ptr(red), r["training"], ptr(dy), n, d, h, w, c, st,
+             ptr(grads[bn.weight]), ptr(grads[bn.bias]), ptr(grads[u.prelu.weight]), ptr(grads[u.conv.bias]))
         dw = grads[u.conv.weight]
         if u.is_stem:
             if self._use_tc(16, c) and u.cin <= 8 and os.environ.get("FPL_WGRAD_IMPL", "tc") == "tc":
@@ -533,7 +534,18 @@ class UNet2D5_dsbn(nn.Module):
                 call("fpl_stem_conv_wgrad", ptr(r["x_img"]), ptr(dy), c // 8, 0, ptr(dw), n, u.cin, d, h, w, c, u.kd, st)
             return None
         xin = r["xin"]
-        self._wgrad(u, xin, dy, dw, n, d, h, w)
+        aux = self._aux_stream()
+        if aux is not None:
+            # dW does not feed the rest of backward: issue it on a side stream so that it fills the tensor pipe
+            # while the main stream runs the HBM-bound BatchNorm kernels of the next unit
+            cur = torch.cuda.current_stream()
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            aux.wait_event(ready)
+            with torch.cuda.stream(aux):
+                self._wgrad(u, xin, dy, dw, n, d, h, w)
+        else:
+            self._wgrad(u, xin, dy, dw, n, d, h, w)
         if not need_dx:
             return None
         dx = ws.c8("dX:" + u.name, n, d, u.cin, h, w)
@@ -545,6 +557,22 @@ class UNet2D5_dsbn(nn.Module):
             call("fpl_conv3d_direct", ptr(dy), c // 8, 0, ptr(u.conv.weight), None, ptr(dx), u.cin // 8, 0, None,
                  n, d, h, w, c, u.cin, u.kd, 1, 0, st)
         return C8(dx)
+
+    def _aux_stream(self):
+        """The wgrad side stream paired with the current stream (None when disabled)."""
+        if not self.wgrad_side_stream:
+            return None
+        cur = torch.cuda.current_stream()
+        key = cur.cuda_stream
+        st = self._aux_streams.get(key)
+        if st is None:
+            st = self._aux_streams[key] = torch.cuda.Stream(device=cur.device)
+        return st
+
+    def _join_aux(self):
+        aux = self._aux_stream()
+        if aux is not None:
+            torch.cuda.current_stream().wait_stream(aux)
 
     def _wgrad(self, u, xin, dy, dw, n, d, h, w):
         impl = os.environ.get("FPL_WGRAD_IMPL", "tc")
@@ -572,6 +600,7 @@ class UNet2D5_dsbn(nn.Module):
             if self.grad_ready_hook is not None:
                 end = offs[n_params_done - 1] + sizes[n_params_done - 1]
                 if end > fired[0]:
+                    self._join_aux()
                     self.grad_ready_hook(flat, fired[0], end, n_params_done == len(params))
                     fired[0] = end
 
@@ -636,6 +665,7 @@ class UNet2D5_dsbn(nn.Module):
             done += 10
             fire(done)
         assert done == len(params)
+        self._join_aux()
         return [grads[p].view(p.shape) for p in params]
 
 

@@ -130,6 +130,15 @@ int fpl_dsbn_act_fwd(const void* y, const float* scale, const float* shift, cons
                      void* pooled, int p_c8tot, int p_c8off, uint8_t* pool_idx, int pool_kd,
                      float drop_p, const uint8_t* drop_mask, uint64_t seed, uint64_t offset, const uint64_t* seed_dev,
                      int n, int d, int h, int w, int c, void* stream);
+/* fpl_dsbn_finalize fused into the prologue of fpl_dsbn_act_fwd (one launch per layer instead of two):
+ * every block derives the affine map of its 8 channels from `stats`, one block per channel group
+ * publishes scale/shift/save_mean/save_invstd and updates the running statistics. */
+int fpl_dsbn_bn_act_fwd(const void* y, const double* stats, int64_t count, const float* gamma, const float* beta,
+                        float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
+                        float eps, int training, float* scale, float* shift, float* save_mean, float* save_invstd,
+                        const float* slope, void* a, int a_c8tot, int a_c8off, void* pooled, int p_c8tot, int p_c8off,
+                        uint8_t* pool_idx, int pool_kd, float drop_p, const uint8_t* drop_mask, uint64_t seed,
+                        uint64_t offset, const uint64_t* seed_dev, int n, int d, int h, int w, int c, void* stream);
 /* Backward.  Gradient wrt the activated output = g1 (C8-planar slice, may be NULL)
  * + max-pool scatter of g_pool through pool_idx (may be NULL).  With dz the gradient
  * wrt the BN output and xhat = (y-mean)*invstd:
@@ -151,6 +160,15 @@ int fpl_dsbn_act_bwd_apply(const void* y, const void* g1, int g1_c8tot, int g1_c
                            float drop_p, const uint8_t* drop_mask, uint64_t seed, uint64_t offset,
                            const uint64_t* seed_dev, const double* red, int training, void* dy,
                            int n, int d, int h, int w, int c, void* stream);
+/* fpl_dsbn_act_bwd_apply with fpl_dsbn_bwd_finalize fused in (same accumulate semantics, any pointer may be NULL). */
+int fpl_dsbn_act_bwd_apply_fin(const void* y, const void* g1, int g1_c8tot, int g1_c8off,
+                               const void* g_pool, int gp_c8tot, int gp_c8off, const uint8_t* pool_idx, int pool_kd,
+                               const float* scale, const float* shift, const float* save_mean,
+                               const float* save_invstd, const float* slope,
+                               float drop_p, const uint8_t* drop_mask, uint64_t seed, uint64_t offset,
+                               const uint64_t* seed_dev, const double* red, int training, void* dy,
+                               int n, int d, int h, int w, int c, void* stream,
+                               float* dgamma, float* dbeta, float* dslope, float* dbias_conv);
 int fpl_dsbn_bwd_finalize(const double* red, const float* scale, const float* save_invstd, int training,
                           float* dgamma, float* dbeta, float* dslope, float* dbias_conv, int c, void* stream);
 

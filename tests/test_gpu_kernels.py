@@ -468,3 +468,64 @@ def test_window_accumulate_flips_and_normalize():
     from fplplus_b200 import lib as L
     with pytest.raises(L.FplError):
         _call("fpl_window_accumulate", _p(patch), _p(out), None, b, c, vd, vh, vw, 4, 0, 0, 4, 6, 8, 0, 0, 1.0, _st())
+
+
+@pytest.mark.parametrize("training", [1, 0])
+@pytest.mark.parametrize("pool_kd", [0, 2])
+def test_dsbn_fused_finalize_entry_points_equal_the_two_step_ones(training, pool_kd):
+    """fpl_dsbn_bn_act_fwd == fpl_dsbn_finalize + fpl_dsbn_act_fwd and fpl_dsbn_act_bwd_apply_fin ==
+    fpl_dsbn_act_bwd_apply + fpl_dsbn_bwd_finalize, bit for bit (same arithmetic, one launch each)."""
+    n, c, d, h, w = 2, 32, 4, 8, 12
+    yb = to_c8((randn(181, n, c, d, h, w, scale=2.0) + 0.5).to(DEV))
+    yf = from_c8(yb).double()
+    stats = torch.stack([yf.sum((0, 2, 3, 4)), (yf ** 2).sum((0, 2, 3, 4))]).flatten().contiguous()
+    gamma, beta = (randn(182, c, scale=0.3) + 1.0).to(DEV), randn(183, c, scale=0.2).to(DEV)
+    sl = torch.tensor([0.2], device=DEV)
+    cnt = n * d * h * w
+    res = []
+    for fused in (0, 1):
+        rm, rv = randn(184, c, scale=0.1).to(DEV), (randn(185, c, scale=0.1).abs() + 0.8).to(DEV)
+        nbt = torch.zeros((), dtype=torch.int64, device=DEV)
+        scale, shift, mean, invstd = (torch.zeros(c, device=DEV) for _ in range(4))
+        act = torch.zeros((n, d, c // 8, h, w, 8), dtype=torch.bfloat16, device=DEV)
+        pooled = idx = None
+        if pool_kd:
+            pooled = torch.zeros((n, d // pool_kd, c // 8, h // 2, w // 2, 8), dtype=torch.bfloat16, device=DEV)
+            idx = torch.zeros((n, d // pool_kd, c // 8, h // 2, w // 2, 8), dtype=torch.uint8, device=DEV)
+        tail = (_p(sl), _p(act), c // 8, 0, _p(pooled), c // 8, 0, _p(idx), pool_kd, 0.0, None, 0, 0, None, n, d, h, w, c, _st())
+        if fused:
+            _call("fpl_dsbn_bn_act_fwd", _p(yb), _p(stats), cnt, _p(gamma), _p(beta), _p(rm), _p(rv), _p(nbt), 0.1, 1e-5,
+                  training, _p(scale), _p(shift), _p(mean), _p(invstd), *tail)
+        else:
+            _call("fpl_dsbn_finalize", _p(stats), cnt, _p(gamma), _p(beta), _p(rm), _p(rv), _p(nbt), 0.1, 1e-5, training,
+                  _p(scale), _p(shift), _p(mean), _p(invstd), c, _st())
+            _call("fpl_dsbn_act_fwd", _p(yb), _p(scale), _p(shift), *tail)
+        g1 = to_c8(bf16_round(randn(187, n, c, d, h, w)).to(DEV))
+        gp = to_c8(bf16_round(randn(188, n, c, d // 2, h // 2, w // 2)).to(DEV)) if pool_kd else None
+        red = torch.zeros(2 * c + 1, dtype=torch.float64, device=DEV)
+        common = (_p(yb), _p(g1), c // 8, 0, _p(gp), c // 8, 0, _p(idx), pool_kd, _p(scale), _p(shift), _p(mean), _p(invstd),
+                  _p(sl), 0.0, None, 0, 0, None)
+        _call("fpl_dsbn_act_bwd_reduce", *common, _p(red), n, d, h, w, c, _st())
+        dy = torch.zeros((n, d, c // 8, h, w, 8), dtype=torch.bfloat16, device=DEV)
+        dg, db, dsl, dbias = torch.zeros(c, device=DEV), torch.zeros(c, device=DEV), torch.zeros(1, device=DEV), torch.zeros(c, device=DEV)
+        if fused:
+            _call("fpl_dsbn_act_bwd_apply_fin", *common, _p(red), training, _p(dy), n, d, h, w, c, _st(), _p(dg), _p(db),
+                  _p(dsl), _p(dbias))
+        else:
+            _call("fpl_dsbn_act_bwd_apply", *common, _p(red), training, _p(dy), n, d, h, w, c, _st())
+            _call("fpl_dsbn_bwd_finalize", _p(red), _p(scale), _p(invstd), training, _p(dg), _p(db), _p(dsl), _p(dbias), c, _st())
+        torch.cuda.synchronize()
+        res.append([t.clone() for t in (act, scale, shift, mean, invstd, rm, rv, nbt, dy, dg, db, dsl, dbias)]
+                   + ([pooled.clone(), idx.clone()] if pool_kd else []))
+    # same arithmetic up to fp32 contraction (fma vs mul+add): fp32 vectors agree to ~1 ulp, the bf16 tensors
+    # except for rare 1-ulp rounding flips, the argmax codes except on exact ties
+    for a, b in zip(*res):
+        if a.dtype == torch.float32:
+            torch.testing.assert_close(a, b, rtol=2e-5, atol=1e-6)
+        elif a.dtype == torch.bfloat16:
+            assert max_rel(a.float().cpu(), b.float().cpu()) < 1e-2
+            assert float((a != b).float().mean()) < 2e-3
+        elif a.dtype == torch.uint8:
+            assert float((a != b).float().mean()) < 2e-3
+        else:
+            assert torch.equal(a, b)
