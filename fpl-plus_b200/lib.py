@@ -37,6 +37,11 @@ _SIGNATURES = {
     "fpl_head_conv_bwd": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _P, _P] + [_I] * 6 + [_P]),
     "fpl_convt_k2s2_fwd": (_I, [_P, _I, _I, _P, _P, _P, _I, _I] + [_I] * 7 + [_P]),
     "fpl_convt_k2s2_bwd": (_I, [_P, _I, _I, _P, _P, _I, _I, _P, _I, _I, _P, _P] + [_I] * 7 + [_P]),
+    "fpl_convt_weight_image_bytes": (_L, [_I, _I, _I]),
+    "fpl_convt_prep_weight": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "fpl_convt_k2s2_fwd_tc": (_I, [_P, _I, _I, _P, _P, _P, _I, _I] + [_I] * 7 + [_P]),
+    "fpl_convt_k2s2_dgrad_tc": (_I, [_P, _I, _I, _P, _P, _I, _I] + [_I] * 7 + [_P]),
+    "fpl_convt_k2s2_wgrad_tc": (_I, [_P, _I, _I, _P, _I, _I, _P] + [_I] * 7 + [_P]),
     "fpl_dsbn_finalize": (_I, [_P, _L, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _I, _P]),
     "fpl_dsbn_act_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _F, _P, _U, _U, _P] + [_I] * 5 + [_P]),
     "fpl_dsbn_bn_act_fwd": (_I, [_P, _P, _L, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P,

@@ -377,6 +377,14 @@ class UNet2D5_dsbn(nn.Module):
                     ent = self._img_cache[key] = [-1, torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)]
                 if ent[0] != w._version:
                     todo.append((w, u.cin, u.cout, u.kd, 1 if transpose else 0, ent))
+        if os.environ.get("FPL_CONVT_IMPL", "tc") == "tc":
+            for up in (self.up1, self.up2, self.up3, self.up4):
+                trans = up.trans3d if up.dim == 3 else up.trans2d
+                if self._use_tc(trans.weight.shape[0], trans.weight.shape[1]):
+                    kd2 = 2 if up.dim == 3 else 1
+                    self._convt_image(trans, kd2, 0)
+                    if with_dgrad:
+                        self._convt_image(trans, kd2, 1)
         for i in range(0, len(todo), 80):
             part = todo[i:i + 80]
             n = len(part)
@@ -386,6 +394,22 @@ class UNet2D5_dsbn(nn.Module):
             call("fpl_conv3d_prep_weight_batch", n, arr_w, ints[0], ints[1], ints[2], ints[3], arr_img, stream_ptr())
             for t in part:
                 t[5][0] = t[0]._version
+
+    def _convt_tc(self, cin, cout):
+        return (self._use_tc(cin, cout) and os.environ.get("FPL_CONVT_IMPL", "tc") == "tc")
+
+    def _convt_image(self, trans, kd2, mode):
+        """Staged bf16 GEMM operand of a transposed conv (mode 0 forward, 1 dgrad), cached on the weight version."""
+        w = trans.weight
+        key = (id(w), "ct%d" % mode)
+        ent = self._img_cache.get(key)
+        if ent is None or ent[1].device != w.device:
+            nbytes = ops._lib.load().fpl_convt_weight_image_bytes(w.shape[0], w.shape[1], kd2)
+            ent = self._img_cache[key] = [-1, torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)]
+        if ent[0] != w._version:
+            call("fpl_convt_prep_weight", ptr(w), w.shape[0], w.shape[1], kd2, mode, ptr(ent[1]), stream_ptr())
+            ent[0] = w._version
+        return ent[1]
 
     def _weight_image(self, conv, kd, transpose, ws):
         ent = self._img_cache.get((id(conv.weight), transpose))
@@ -484,8 +508,12 @@ class UNet2D5_dsbn(nn.Module):
             cat = ws.t["cat%d" % lvl]
             trans = up.trans3d if up.dim == 3 else up.trans2d
             kd2 = 2 if up.dim == 3 else 1
-            call("fpl_convt_k2s2_fwd", *low.args(), ptr(trans.weight), ptr(trans.bias), ptr(cat), 2 * c // 8, c // 8,
-                 n, dl, hl, wl, c_low, c, kd2, stream_ptr())
+            if self._convt_tc(c_low, c):
+                call("fpl_convt_k2s2_fwd_tc", *low.args(), ptr(self._convt_image(trans, kd2, 0)), ptr(trans.bias), ptr(cat),
+                     2 * c // 8, c // 8, n, dl, hl, wl, c_low, c, kd2, stream_ptr())
+            else:
+                call("fpl_convt_k2s2_fwd", *low.args(), ptr(trans.weight), ptr(trans.bias), ptr(cat), 2 * c // 8, c // 8,
+                     n, dl, hl, wl, c_low, c, kd2, stream_ptr())
             rec["up%d.low" % (k + 1)] = low
             a1 = C8(ws.c8("A1:up%d" % (k + 1), n, d, c, h, w))
             self._unit_fwd(u1, domain, C8(cat, 0, 2 * c), None, a1, None, None, 0, n, geo[lvl], ws, small, rec)
@@ -643,8 +671,16 @@ class UNet2D5_dsbn(nn.Module):
             dl, hl, wl = geo[lvl + 1]
             low = rec["up%d.low" % (k + 1)]
             glow = C8(ws.c8("dlow%d" % lvl, n, dl, c_low, hl, wl))
-            call("fpl_convt_k2s2_bwd", *low.args(), ptr(trans.weight), ptr(dcat.buf), 2 * c // 8, c // 8, *glow.args(),
-                 ptr(grads[trans.weight]), ptr(grads[trans.bias]), n, dl, hl, wl, c_low, c, kd2, st)
+            if self._convt_tc(c_low, c):
+                call("fpl_convt_k2s2_dgrad_tc", ptr(dcat.buf), 2 * c // 8, c // 8, ptr(self._convt_image(trans, kd2, 1)),
+                     *glow.args(), n, dl, hl, wl, c_low, c, kd2, st)
+                call("fpl_convt_k2s2_wgrad_tc", *low.args(), ptr(dcat.buf), 2 * c // 8, c // 8, ptr(grads[trans.weight]),
+                     n, dl, hl, wl, c_low, c, kd2, st)
+                call("fpl_convt_k2s2_bwd", *low.args(), ptr(trans.weight), ptr(dcat.buf), 2 * c // 8, c // 8, None, 0, 0,
+                     None, ptr(grads[trans.bias]), n, dl, hl, wl, c_low, c, kd2, st)       # bias gradient only
+            else:
+                call("fpl_convt_k2s2_bwd", *low.args(), ptr(trans.weight), ptr(dcat.buf), 2 * c // 8, c // 8, *glow.args(),
+                     ptr(grads[trans.weight]), ptr(grads[trans.bias]), n, dl, hl, wl, c_low, c, kd2, st)
             g = glow
             done += 12
             fire(done)

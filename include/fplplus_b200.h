@@ -109,6 +109,19 @@ int fpl_convt_k2s2_bwd(const void* x, int x_c8tot, int x_c8off, const float* w,
                        void* dx, int dx_c8tot, int dx_c8off, float* dw, float* db,
                        int n, int d, int h, int w_, int cin, int cout, int kd2, void* stream);
 
+/* The same three operations on tcgen05 (csrc/convt_tc.cu): the stride-2 sub-lattice of one tap is fetched by TMA
+ * with elementStrides = 2, fwd scatters its epilogue into (y_c8tot, y_c8off).  Images come from
+ * fpl_convt_prep_weight (mode 0: forward operand, mode 1: dgrad operand); need cin % 16 == 0, cout % 16 == 0. */
+int64_t fpl_convt_weight_image_bytes(int cin, int cout, int kd2);
+int fpl_convt_prep_weight(const float* w, int cin, int cout, int kd2, int mode, void* image, void* stream);
+int fpl_convt_k2s2_fwd_tc(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias, void* y,
+                          int y_c8tot, int y_c8off, int n, int d, int h, int w, int cin, int cout, int kd2, void* stream);
+int fpl_convt_k2s2_dgrad_tc(const void* dy, int dy_c8tot, int dy_c8off, const void* image_t, void* dx, int dx_c8tot,
+                            int dx_c8off, int n, int d, int h, int w, int cin, int cout, int kd2, void* stream);
+/* dW[cin][cout][kd2][2][2] (fp32) ACCUMULATED into. */
+int fpl_convt_k2s2_wgrad_tc(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
+                            float* dw, int n, int d, int h, int w, int cin, int cout, int kd2, void* stream);
+
 /* ---- (b) DSBN BatchNorm3d + PReLU + Dropout + MaxPool: net_run_dsbn/dsbn.py:54-57,
  *          unet2d5_dsbn.py:76-81,104-106 ---- */
 

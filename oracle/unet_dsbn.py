@@ -193,7 +193,8 @@ def forward(state, x, domain, params, bn_training=False, drop_training=None, mas
                 h2 = F.conv2d(h2, state[pre + ".conv2d.weight"], state[pre + ".conv2d.bias"])
                 h2 = F.interpolate(h2, scale_factor=2, mode="bilinear", align_corners=True)
             else:
-                h2 = F.conv_transpose2d(_RoundBwd.apply(h2) if bf16 else h2, state[pre + ".trans2d.weight"],
+                h2 = F.conv_transpose2d(_RoundBwd.apply(h2) if bf16 else h2,
+                                        _wq(state[pre + ".trans2d.weight"]) if bf16 else state[pre + ".trans2d.weight"],
                                         state[pre + ".trans2d.bias"], stride=2)
                 h2 = _RoundFwd.apply(h2) if bf16 else h2
             cat = torch.cat([s2, h2], dim=1)
@@ -204,7 +205,8 @@ def forward(state, x, domain, params, bn_training=False, drop_training=None, mas
                 h = F.conv3d(h, state[pre + ".conv3d.weight"], state[pre + ".conv3d.bias"])
                 h = F.interpolate(h, scale_factor=2, mode="trilinear", align_corners=True)
             else:
-                h = F.conv_transpose3d(_RoundBwd.apply(h) if bf16 else h, state[pre + ".trans3d.weight"],
+                h = F.conv_transpose3d(_RoundBwd.apply(h) if bf16 else h,
+                                       _wq(state[pre + ".trans3d.weight"]) if bf16 else state[pre + ".trans3d.weight"],
                                        state[pre + ".trans3d.bias"], stride=2)
                 h = _RoundFwd.apply(h) if bf16 else h
             cat = torch.cat([skip, h], dim=1)

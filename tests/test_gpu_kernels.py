@@ -529,3 +529,41 @@ def test_dsbn_fused_finalize_entry_points_equal_the_two_step_ones(training, pool
             assert float((a != b).float().mean()) < 2e-3
         else:
             assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("cin,cout,kd2,shape", [(32, 16, 2, (2, 2, 16, 8)), (64, 32, 1, (1, 3, 20, 12)),
+                                                (256, 128, 2, (1, 1, 4, 6)), (128, 64, 2, (1, 2, 8, 8))])
+def test_convt_k2s2_tensor_core_fwd_dgrad_wgrad(cin, cout, kd2, shape):
+    """ConvTranspose3d k2 s2 on tcgen05 (strided TMA sub-lattices) against torch on bf16-rounded operands."""
+    from fplplus_b200 import lib as L
+    n, d, h, w = shape
+    x = bf16_round(randn(71, n, cin, d, h, w)).requires_grad_(True)
+    wt = bf16_round(randn(72, cin, cout, kd2, 2, 2, scale=0.2)).requires_grad_(True)
+    b = randn(73, cout, scale=0.1)
+    ref = F.conv_transpose3d(x, wt, b, stride=(kd2, 2, 2))
+    g = bf16_round(randn(74, *ref.shape))
+    ref.backward(g)
+    xb = to_c8(x.detach().to(DEV))
+    wd, bd = wt.detach().to(DEV), b.to(DEV)
+    nbytes = L.load().fpl_convt_weight_image_bytes(cin, cout, kd2)
+    img = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=DEV)
+    img_t = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=DEV)
+    _call("fpl_convt_prep_weight", _p(wd), cin, cout, kd2, 0, _p(img), _st())
+    _call("fpl_convt_prep_weight", _p(wd), cin, cout, kd2, 1, _p(img_t), _st())
+    do, ho, wo = d * kd2, 2 * h, 2 * w
+    cat = torch.zeros((n, do, 2 * cout // 8, ho, wo, 8), dtype=torch.bfloat16, device=DEV)
+    _call("fpl_convt_k2s2_fwd_tc", _p(xb), cin // 8, 0, _p(img), _p(bd), _p(cat), 2 * cout // 8, cout // 8, n, d, h, w, cin,
+          cout, kd2, _st())
+    out = from_c8(cat).cpu()
+    assert max_rel(out[:, cout:], ref.detach()) < 6e-3
+    assert torch.all(out[:, :cout] == 0)                      # the skip half of the concat buffer is untouched
+    gcat = to_c8(torch.cat([torch.zeros_like(g), g], 1).to(DEV))
+    dx = torch.zeros((n, d, cin // 8, h, w, 8), dtype=torch.bfloat16, device=DEV)
+    _call("fpl_convt_k2s2_dgrad_tc", _p(gcat), 2 * cout // 8, cout // 8, _p(img_t), _p(dx), cin // 8, 0, n, d, h, w, cin, cout,
+          kd2, _st())
+    dw = torch.zeros(cin, cout, kd2, 2, 2, device=DEV)
+    for _ in range(2):                                         # accumulates
+        _call("fpl_convt_k2s2_wgrad_tc", _p(xb), cin // 8, 0, _p(gcat), 2 * cout // 8, cout // 8, _p(dw), n, d, h, w, cin, cout,
+              kd2, _st())
+    assert max_rel(from_c8(dx).cpu(), x.grad) < 6e-3
+    assert max_rel(dw.cpu(), 2 * wt.grad) < 1e-4
