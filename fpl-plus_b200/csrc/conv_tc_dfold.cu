@@ -1,0 +1,395 @@
+// Depth-folded implicit-GEMM conv3d (k 3x3x3, "same") for the SMALL-channel layers, where a tcgen05.mma
+// M=128 x N=Cout x K=16 is paced by the shared-memory feed of its A operand (4 KB per instruction), not by the math:
+// instead of 27 MMAs (N = Cout) per OUTPUT plane, every INPUT plane tile issues 9 MMAs whose N spans the three
+// output planes it contributes to,  D[z-1 | z | z+1] += A(z) * [W_kd=2 | W_kd=1 | W_kd=0]   (N = 3*Cout),
+// so the A tile is fetched from shared memory 9 times instead of 27 and from L2 once instead of three times.
+//   * a CTA owns a (n, 16x8 tile, depth chunk of DC planes) column: TMEM holds DC accumulators side by side
+//     (DC*Cout columns); the first / last input planes of a chunk use N = Cout or 2*Cout sub-ranges of B;
+//   * all 27 taps of the layer's weights stay RESIDENT in shared memory (<= 110 KB) for the kernel's lifetime;
+//   * accumulators are kept zeroed by the epilogue (tcgen05.st after each read), every MMA accumulates;
+//   * output plane p is complete once input plane p+1 has been issued: its epilogue (bias, bf16 store, BatchNorm
+//     partial sums) runs under the MMAs of the following planes.
+// Same operands, contract and epilogue as conv3d_tc_kernel (conv_tc.cu); forward and dgrad.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "../../include/fplplus_b200.h"
+
+namespace {
+
+constexpr int kTileH = 16, kTileW = 8;
+constexpr int kBoxH = kTileH + 2, kBoxW = kTileW + 2;
+constexpr int kPlaneBytes = kBoxH * kBoxW * 16;
+constexpr int kThreadsD = 192;
+constexpr int kMaxStagesD = 8;
+constexpr int kMaxDC = 16;
+
+struct DfParams {
+    const __nv_bfloat16* image;      // [slice][tap9][cin/16][2][3*nb][8]
+    const float* bias;
+    bf16x8* y;
+    int y_c8tot, y_c8off;
+    double* stats;
+    int N, D, H, W, cin, cout;
+    int x_c8tot, x_c8off;
+    int nb, nslices, dc, ndc;        // dc: output planes per depth chunk; ndc = ceil(D/dc)
+    int a_bytes, b_bytes, stages, tmem_cols;
+    int tiles_h, tiles_w, total_items;
+};
+
+__device__ __forceinline__ void tmem_st_zero16(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+        ::"r"(taddr), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+struct DfItem {
+    int n, d0, h0, w0, slice, dcount;
+};
+
+__device__ __forceinline__ DfItem decode_item(const DfParams& P, int t) {
+    DfItem c;
+    int tw = t % P.tiles_w; t /= P.tiles_w;
+    int th = t % P.tiles_h; t /= P.tiles_h;
+    int ch = t % P.ndc; t /= P.ndc;
+    c.n = t % P.N;
+    c.slice = t / P.N;
+    c.h0 = th * kTileH;
+    c.w0 = tw * kTileW;
+    c.d0 = ch * P.dc;
+    c.dcount = min(P.dc, P.D - c.d0);
+    return c;
+}
+
+__global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid_constant__ CUtensorMap xmap, DfParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // [resident weights of this CTA's slice][A stage ring][barriers][bias]
+    uint8_t* b_sm = smem;
+    uint8_t* ring = smem + P.b_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)P.stages * P.a_bytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kMaxStagesD;
+    uint64_t* done_bar = bars + 2 * kMaxStagesD;                  // [kMaxDC] output plane complete
+    uint64_t* acc_free = bars + 2 * kMaxStagesD + kMaxDC;         // all accumulators drained and zeroed
+    uint64_t* w_bar = bars + 2 * kMaxStagesD + kMaxDC + 1;        // resident weights landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStagesD + kMaxDC + 2);
+    float* bias_sm = reinterpret_cast<float*>(bars + 2 * kMaxStagesD + kMaxDC + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+        for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int p = 0; p < kMaxDC; ++p) mbar_init(&done_bar[p], 1);
+        mbar_init(acc_free, 4);
+        mbar_init(w_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+    for (int i = threadIdx.x; i < P.cout; i += kThreadsD) bias_sm[i] = P.bias != nullptr ? P.bias[i] : 0.0f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int cur_slice = -1;
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < P.total_items; t += gridDim.x) {
+                const DfItem c = decode_item(P, t);
+                if (c.slice != cur_slice) {
+                    // items are ordered slice-major, so a CTA (re)loads the resident weights at most nslices times;
+                    // the MMA warp has drained every earlier stage before it waits on w_bar again (see below)
+                    cur_slice = c.slice;
+                    mbar_expect_tx(w_bar, (uint32_t)P.b_bytes);
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(P.image) + (size_t)c.slice * P.b_bytes;
+                    for (int off = 0; off < P.b_bytes; off += 32768) {
+                        const int nbytes = min(32768, P.b_bytes - off);
+                        bulk_load(b_sm + off, src + off, (uint32_t)nbytes, w_bar);
+                    }
+                }
+                for (int z = c.d0 - 1; z <= c.d0 + c.dcount; ++z) {
+                    if (z < 0 || z >= P.D) continue;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], (uint32_t)P.a_bytes);
+                    tma_load_3d(ring + (size_t)stage * P.a_bytes, &xmap, &full_bar[stage], (c.w0 - 1) * 8, c.h0 - 1,
+                                (c.n * P.D + z) * P.x_c8tot + P.x_c8off);
+                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+        const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (8u << 24);
+        const uint64_t a_hi = make_desc(0, kPlaneBytes, kBoxW * 16);
+        const uint64_t b_hi = make_desc(0, (uint32_t)(3 * P.nb) * 16, 128);
+        const uint32_t b_u = smem_u32(b_sm) >> 4, ring_u = smem_u32(ring) >> 4;
+        const int ksteps = P.cin / 16;
+        const uint32_t b_kstep = (uint32_t)(2 * 3 * P.nb);             // 16-byte units per 16-channel K step
+        const uint32_t b_tap = (uint32_t)ksteps * b_kstep;
+        const bool leader = elect_one();
+        int stage = 0; uint32_t phase = 0;
+        uint32_t item_phase = 0, w_phase = 0;
+        int cur_slice = -1;
+        for (int t = blockIdx.x; t < P.total_items; t += gridDim.x) {
+            const DfItem c = decode_item(P, t);
+            if (c.slice != cur_slice) {
+                cur_slice = c.slice;
+                mbar_wait(w_bar, w_phase);
+                w_phase ^= 1;
+            }
+            mbar_wait(acc_free, item_phase);                            // accumulators drained + zeroed
+            tc_fence_after();
+            for (int r = -1; r <= c.dcount; ++r) {                      // input plane z = d0 + r
+                const int z = c.d0 + r;
+                if (z >= 0 && z < P.D) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    // output planes r-1+j, j in [jlo, jhi], clipped to the chunk
+                    const int jlo = r < 1 ? 1 - r : 0;
+                    const int jhi = r > c.dcount - 2 ? c.dcount - r : 2;
+                    const uint32_t ncols = (uint32_t)(jhi - jlo + 1) * (uint32_t)P.nb;
+                    const uint32_t idesc = idesc0 | ((ncols >> 3) << 17);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(r - 1 + jlo) * (uint32_t)P.nb;
+                    const uint32_t a_base = ring_u + (uint32_t)(((size_t)stage * P.a_bytes) >> 4);
+                    const uint32_t b_base = b_u + (uint32_t)(jlo * P.nb);
+                    for (int j = 0; j < ksteps; ++j) {
+                        const uint32_t a_j = a_base + (uint32_t)j * (2 * kPlaneBytes / 16);
+                        const uint32_t b_j = b_base + (uint32_t)j * b_kstep;
+#pragma unroll
+                        for (int t9 = 0; t9 < 9; ++t9) {
+                            const uint64_t adesc = a_hi | (uint64_t)(a_j + (uint32_t)((t9 / 3) * kBoxW + (t9 % 3)));
+                            const uint64_t bdesc = b_hi | (uint64_t)(b_j + (uint32_t)t9 * b_tap);
+                            if (leader) umma_bf16(d_tmem, adesc, bdesc, idesc, 1u);
+                        }
+                    }
+                    if (leader) umma_commit(&empty_bar[stage]);
+                    __syncwarp();
+                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                }
+                if (r >= 1) {                                           // output plane r-1 has all its contributions
+                    if (leader) umma_commit(&done_bar[r - 1]);
+                    __syncwarp();
+                }
+            }
+            // a short last chunk: complete the unused plane barriers too, so that every barrier flips once per item
+            for (int p = c.dcount; p < P.dc; ++p) {
+                if (leader) umma_commit(&done_bar[p]);
+                __syncwarp();
+            }
+            item_phase ^= 1;
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int hl = row / kTileW, wl = row % kTileW;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        constexpr int kMaxChunks = 4;                                   // nb <= 64
+        float run[kMaxChunks];
+#pragma unroll
+        for (int k = 0; k < kMaxChunks; ++k) run[k] = 0.0f;
+        const bool want_stats = P.stats != nullptr;
+        const int nchunk16 = P.nb / 16;
+        // zero every accumulator once, then hand them to the MMA warp
+        for (int col = 0; col < P.dc * P.nb; col += 16) tmem_st_zero16(lane_base + (uint32_t)col);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_free);
+        uint32_t item_phase = 0;
+        int cur_slice = -1;
+        for (int t = blockIdx.x; t < P.total_items; t += gridDim.x) {
+            const DfItem c = decode_item(P, t);
+            if (want_stats && c.slice != cur_slice) {
+                if (cur_slice >= 0) {
+#pragma unroll
+                    for (int k = 0; k < kMaxChunks; ++k)
+                        if (k < nchunk16) {
+                            atomicAdd(P.stats + (lane >> 4) * P.cout + cur_slice * P.nb + k * 16 + (lane & 15), (double)run[k]);
+                            run[k] = 0.0f;
+                        }
+                }
+                cur_slice = c.slice;
+            }
+            const int h = c.h0 + hl, w = c.w0 + wl;
+            const bool valid = h < P.H && w < P.W;
+            const int64_t HW = (int64_t)P.H * P.W;
+            for (int p = 0; p < c.dcount; ++p) {
+                mbar_wait(&done_bar[p], item_phase);
+                tc_fence_after();
+                const int64_t out_base = (((int64_t)c.n * P.D + c.d0 + p) * P.y_c8tot + P.y_c8off + (c.slice * P.nb) / 8) * HW +
+                                         (int64_t)h * P.W + w;
+#pragma unroll
+                for (int k = 0; k < kMaxChunks; ++k) {
+                    if (k < nchunk16) {
+                        const int c0 = k * 16;
+                        const uint32_t taddr = lane_base + (uint32_t)(p * P.nb + c0);
+                        uint32_t r[16];
+                        tmem_ld16(taddr, r);
+                        tmem_ld_wait();
+                        tmem_st_zero16(taddr);                          // leave the slot clean for the next item
+                        float v[32];
+                        const float4* b4 = reinterpret_cast<const float4*>(bias_sm + c.slice * P.nb + c0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float4 bb = b4[i];
+                            v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bb.x;
+                            v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
+                            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z;
+                            v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
+                        }
+                        if (valid) {
+                            st_bf16x8(P.y + out_base + (int64_t)(c0 / 8) * HW, v);
+                            st_bf16x8(P.y + out_base + (int64_t)(c0 / 8 + 1) * HW, v + 8);
+                        }
+                        if (want_stats) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                v[i] = valid ? v[i] : 0.0f;
+                                v[16 + i] = v[i] * v[i];
+                            }
+                            warp_transpose_sum32(v, lane);
+                            run[k] += v[0];
+                        }
+                    }
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_free);
+            item_phase ^= 1;
+        }
+        if (want_stats && cur_slice >= 0) {
+#pragma unroll
+            for (int k = 0; k < kMaxChunks; ++k)
+                if (k < nchunk16)
+                    atomicAdd(P.stats + (lane >> 4) * P.cout + cur_slice * P.nb + k * 16 + (lane & 15), (double)run[k]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+    }
+}
+
+// weights: fp32 [Cout][Cin][27] -> bf16 [slice][tap9][cin/16][2][3*nb][8]; column block jj of B feeds output plane
+// z-1+jj of input plane z, i.e. depth tap kd = 2 - jj.  transpose_flip as in fpl_conv3d_prep_weight.
+__global__ void dfold_prep_kernel(const float* __restrict__ w, __nv_bfloat16* image, int cin_eff, int cout_eff, int transpose_flip,
+                                  int nb, int total) {
+    const int ksteps = cin_eff / 16, n3 = 3 * nb;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int t = i;
+        const int el = t % 8; t /= 8;
+        const int nn = t % n3; t /= n3;
+        const int k8 = t % 2; t /= 2;
+        const int j = t % ksteps; t /= ksteps;
+        const int t9 = t % 9;
+        const int sl = t / 9;
+        const int in = j * 16 + k8 * 8 + el;
+        const int jj = nn / nb, out = sl * nb + nn % nb;
+        const int tap = (2 - jj) * 9 + t9;
+        float v;
+        if (!transpose_flip) v = w[((int64_t)out * cin_eff + in) * 27 + tap];
+        else v = w[((int64_t)in * cout_eff + out) * 27 + (26 - tap)];
+        image[i] = __float2bfloat16_rn(v);
+    }
+}
+
+struct DfCfg {
+    int nb, nslices, dc, stages, a_bytes, b_bytes, tmem_cols, smem_bytes, ctas_per_sm;
+};
+
+bool make_df_cfg(int cin, int cout, int d, DfCfg& c) {
+    if (cin % 16 || cout % 16 || cin > 64) return false;
+    c.nb = cout <= 64 ? cout : (cout % 64 == 0 ? 64 : (cout % 32 == 0 ? 32 : 16));
+    if (c.nb != 16 && c.nb != 32 && c.nb != 64) return false;
+    c.nslices = cout / c.nb;
+    if (c.nslices != 1) return false;          // resident weights are loaded once per CTA
+    c.b_bytes = 9 * cin * 3 * c.nb * 2;
+    if (c.b_bytes > 112 * 1024) return false;
+    c.a_bytes = (cin / 8) * kPlaneBytes;
+    c.dc = c.nb == 16 ? 16 : 8;
+    if (c.dc > d) c.dc = d;
+    if (c.dc < 2) return false;
+    int cols = c.dc * c.nb;
+    c.tmem_cols = 32;
+    while (c.tmem_cols < cols) c.tmem_cols *= 2;
+    if (c.tmem_cols > 512) return false;
+    c.stages = c.b_bytes <= 32 * 1024 ? 6 : 4;
+    c.smem_bytes = c.b_bytes + c.stages * c.a_bytes + 1024 + 512 + cout * (int)sizeof(float) + 16;
+    if (c.smem_bytes > 220 * 1024) return false;
+    c.ctas_per_sm = (c.smem_bytes <= 110 * 1024 && c.tmem_cols <= 256) ? 2 : 1;
+    return true;
+}
+
+int g_dfold_enable = 1;
+
+}  // namespace
+
+void fpl_dfold_debug_set(int value) { g_dfold_enable = value; }
+
+bool fpl_dfold_eligible(int cin, int cout, int kd, int d) {
+    DfCfg c;
+    return g_dfold_enable && kd == 3 && make_df_cfg(cin, cout, d, c);
+}
+
+extern "C" int64_t fpl_conv3d_dfold_image_bytes(int cin, int cout) {
+    DfCfg c;
+    if (!make_df_cfg(cin, cout, 16, c)) return -1;
+    return (int64_t)c.nslices * c.b_bytes;
+}
+
+extern "C" int fpl_conv3d_dfold_prep_weight(const float* w, int cin, int cout, int transpose_flip, void* image, void* stream) {
+    const int cin_eff = transpose_flip ? cout : cin, cout_eff = transpose_flip ? cin : cout;
+    DfCfg c;
+    FPL_REQUIRE(make_df_cfg(cin_eff, cout_eff, 16, c), "fpl_conv3d_dfold_prep_weight: unsupported channels (%d -> %d)", cin_eff, cout_eff);
+    const int total = c.nslices * c.b_bytes / 2;
+    int blocks = (total + 255) / 256;
+    if (blocks > FPL_NUM_SMS * 4) blocks = FPL_NUM_SMS * 4;
+    dfold_prep_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)image, cin_eff, cout_eff, transpose_flip, c.nb, total);
+    FPL_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int fpl_conv3d_tc_dfold(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias, void* y,
+                                   int y_c8tot, int y_c8off, double* stats, int n, int d, int h, int w, int cin, int cout,
+                                   void* stream) {
+    DfCfg c;
+    FPL_REQUIRE(make_df_cfg(cin, cout, d, c), "fpl_conv3d_tc_dfold: unsupported shape (%d -> %d, depth %d)", cin, cout, d);
+    FPL_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(image) & 15) == 0,
+                "fpl_conv3d_tc_dfold: x/image must be 16-byte aligned");
+    EncodeTiledFn encode = get_encode_fn();
+    FPL_REQUIRE(encode != nullptr, "fpl_conv3d_tc_dfold: cuTensorMapEncodeTiled not available from the driver");
+    CUtensorMap xmap;
+    cuuint64_t gdim[3] = {(cuuint64_t)w * 8, (cuuint64_t)h, (cuuint64_t)n * d * x_c8tot};
+    cuuint64_t gstride[2] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16};
+    cuuint32_t box[3] = {(cuuint32_t)kBoxW * 8, (cuuint32_t)kBoxH, (cuuint32_t)(cin / 8)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(x), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FPL_REQUIRE(r == CUDA_SUCCESS, "fpl_conv3d_tc_dfold: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    DfParams P;
+    P.image = (const __nv_bfloat16*)image; P.bias = bias; P.y = (bf16x8*)y; P.y_c8tot = y_c8tot; P.y_c8off = y_c8off;
+    P.stats = stats; P.N = n; P.D = d; P.H = h; P.W = w; P.cin = cin; P.cout = cout;
+    P.x_c8tot = x_c8tot; P.x_c8off = x_c8off;
+    P.nb = c.nb; P.nslices = c.nslices; P.dc = c.dc; P.ndc = (d + c.dc - 1) / c.dc;
+    P.a_bytes = c.a_bytes; P.b_bytes = c.b_bytes; P.stages = c.stages; P.tmem_cols = c.tmem_cols;
+    P.tiles_h = (h + kTileH - 1) / kTileH; P.tiles_w = (w + kTileW - 1) / kTileW;
+    int64_t total = (int64_t)P.tiles_h * P.tiles_w * P.ndc * n * c.nslices;
+    FPL_REQUIRE(total < (1ll << 30), "fpl_conv3d_tc_dfold: too many items");
+    P.total_items = (int)total;
+    FPL_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_dfold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
+    int grid = FPL_NUM_SMS * c.ctas_per_sm;
+    if (grid > P.total_items) grid = P.total_items;
+    conv3d_tc_dfold_kernel<<<grid, kThreadsD, c.smem_bytes, (cudaStream_t)stream>>>(xmap, P);
+    FPL_LAUNCH_CHECK();
+    return 0;
+}

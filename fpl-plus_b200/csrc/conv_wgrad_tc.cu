@@ -298,9 +298,11 @@ extern "C" int fpl_conv3d_wgrad_tc(const void* x, int x_c8tot, int x_c8off, cons
     FPL_REQUIRE(tiles < (1ll << 30), "fpl_conv3d_wgrad_tc: too many tiles");
     P.tiles_total = (int)tiles;
     const int pairs = c.mtiles_kd * c.mtiles_c * c.nchunks;
+    // split-K over voxel tiles: every CTA ends with 9*128*N atomics into dW, so a slice should own >= 8 tiles
+    // (deep levels: few tiles, many (M,N) pairs -> split 1; full resolution: one CTA per SM)
     int split = FPL_NUM_SMS / pairs;
+    if (split > P.tiles_total / 8) split = P.tiles_total / 8;
     if (split < 1) split = 1;
-    if (split > P.tiles_total) split = P.tiles_total;
     P.split = split;
     P.swap_lbo_sbo = g_wg_swap; P.m64_quadrant_layout = g_wg_m64_quadrant;
     FPL_CHECK_CUDA(cudaFuncSetAttribute(conv3d_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));

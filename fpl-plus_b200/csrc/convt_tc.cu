@@ -491,8 +491,8 @@ extern "C" int fpl_convt_k2s2_wgrad_tc(const void* x, int x_c8tot, int x_c8off, 
     P.tiles_total = (int)tiles;
     const int pairs = P.mtiles * P.nchunks;
     int split = FPL_NUM_SMS / pairs;
+    if (split > P.tiles_total / 4) split = P.tiles_total / 4;      // amortise the per-CTA atomics epilogue
     if (split < 1) split = 1;
-    if (split > P.tiles_total) split = P.tiles_total;
     P.split = split;
     const int smem_bytes = P.stages * P.stage_bytes + (P.m / 8) * kPlane + 1024 + 256;
     FPL_CHECK_CUDA(cudaFuncSetAttribute(convt_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));

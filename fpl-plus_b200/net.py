@@ -167,6 +167,8 @@ class UNet2D5_dsbn(nn.Module):
         self.cuda_graphs = os.environ.get("FPL_CUDA_GRAPH", "1") != "0"
         self.wgrad_side_stream = os.environ.get("FPL_WGRAD_STREAM", "0") != "0"   # measured: no gain on top of the dual-domain streams
         self._aux_streams = {}
+        self._dfold_cache = {}
+        self._unit_depth = {}
         self.grad_ready_hook = None     # callable(flat_grad, start, end, last) fired as buckets complete (DDP)
         self._head = UNet2D5_dsbn._HeadConv(self.out_conv)
         self._head_unit = None
@@ -299,6 +301,7 @@ class UNet2D5_dsbn(nn.Module):
             logits, _ = self._run_forward(x, domain, ws)
             return logits
         self.ensure_rng(x.device)
+        self._note_depths(self._geometry(x.shape))
         self._refresh_weight_images(with_dgrad=False)      # eager: a captured graph never restages weights
         if ent["graph"] is None:
             if len(self._graphs) > 16:                     # bound the memory held by stale shapes
@@ -366,8 +369,14 @@ class UNet2D5_dsbn(nn.Module):
         todo = []
         for u in self._tc_convs():
             w = u.conv.weight
+            depth = self._unit_depth.get(u.name, 0)
             for transpose in ((False, True) if with_dgrad else (False,)):
                 if transpose and not self._use_tc(u.cout, u.cin):
+                    continue
+                if u.name != "head" and self._dfold_ok(u.cout if transpose else u.cin, u.cin if transpose else u.cout,
+                                                       u.kd, depth):
+                    if not (transpose and u.name == "block0.conv#1"):
+                        self._dfold_image(u.conv, transpose)       # depth-folded kernel: its own image layout
                     continue
                 key = (id(w), transpose)
                 ent = self._img_cache.get(key)
@@ -394,6 +403,38 @@ class UNet2D5_dsbn(nn.Module):
             call("fpl_conv3d_prep_weight_batch", n, arr_w, ints[0], ints[1], ints[2], ints[3], arr_img, stream_ptr())
             for t in part:
                 t[5][0] = t[0]._version
+
+    def _note_depths(self, geo):
+        """Depth of every conv unit for the current input geometry (kernel selection of the weight staging)."""
+        for i in range(5):
+            for u in self._down_units[i]:
+                self._unit_depth[u.name] = geo[i][0]
+        for k, lvl in zip(range(4), (3, 2, 1, 0)):
+            for u in self._up_units[k]:
+                self._unit_depth[u.name] = geo[lvl][0]
+
+    def _dfold_ok(self, cin, cout, kd, depth):
+        """Depth-folded tensor-core kernel (csrc/conv_tc_dfold.cu) for the small-channel k3 layers."""
+        if kd != 3 or depth < 2 or not self._use_tc(cin, cout) or os.environ.get("FPL_DFOLD", "1") == "0":
+            return False
+        key = (cin, cout)
+        ok = self._dfold_cache.get(key)
+        if ok is None:
+            ok = self._dfold_cache[key] = ops._lib.load().fpl_conv3d_dfold_image_bytes(cin, cout) > 0
+        return ok
+
+    def _dfold_image(self, conv, transpose):
+        w = conv.weight
+        key = (id(w), "df%d" % (1 if transpose else 0))
+        ent = self._img_cache.get(key)
+        cin, cout = conv.in_channels, conv.out_channels
+        if ent is None or ent[1].device != w.device:
+            nbytes = ops._lib.load().fpl_conv3d_dfold_image_bytes(cout if transpose else cin, cin if transpose else cout)
+            ent = self._img_cache[key] = [-1, torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)]
+        if ent[0] != w._version:
+            call("fpl_conv3d_dfold_prep_weight", ptr(w), cin, cout, 1 if transpose else 0, ptr(ent[1]), stream_ptr())
+            ent[0] = w._version
+        return ent[1]
 
     def _convt_tc(self, cin, cout):
         return (self._use_tc(cin, cout) and os.environ.get("FPL_CONVT_IMPL", "tc") == "tc")
@@ -424,6 +465,9 @@ class UNet2D5_dsbn(nn.Module):
         if u.is_stem:
             call("fpl_stem_conv_fwd", ptr(x_img), ptr(u.conv.weight), ptr(u.conv.bias), ptr(y), y.shape[2], 0,
                  ptr(stats), n, u.cin, d, h, w, u.cout, u.kd, st)
+        elif self._dfold_ok(u.cin, u.cout, u.kd, d):
+            call("fpl_conv3d_tc_dfold", *xin.args(), ptr(self._dfold_image(u.conv, False)), ptr(u.conv.bias), ptr(y),
+                 y.shape[2], 0, ptr(stats), n, d, h, w, u.cin, u.cout, st)
         elif self._use_tc(u.cin, u.cout):
             img = self._weight_image(u.conv, u.kd, False, ws)
             call("fpl_conv3d_tc", *xin.args(), ptr(img), ptr(u.conv.bias), ptr(y), y.shape[2], 0, ptr(stats),
@@ -469,6 +513,7 @@ class UNet2D5_dsbn(nn.Module):
         geo = self._geometry(x.shape)
         ft = self.ft_chns
         small = _SmallPool(ws, "fwd", x.device)
+        self._note_depths(geo)
         self._refresh_weight_images(with_dgrad=torch.is_grad_enabled())
         # dropout stream: (seed, per-layer offset) drawn from torch's CPU generator, so torch.manual_seed
         # makes MC-dropout passes reproducible; backward regenerates the same Philox stream
@@ -577,7 +622,10 @@ class UNet2D5_dsbn(nn.Module):
         if not need_dx:
             return None
         dx = ws.c8("dX:" + u.name, n, d, u.cin, h, w)
-        if self._use_tc(u.cout, u.cin):
+        if self._dfold_ok(u.cout, u.cin, u.kd, d):
+            call("fpl_conv3d_tc_dfold", ptr(dy), c // 8, 0, ptr(self._dfold_image(u.conv, True)), None, ptr(dx),
+                 u.cin // 8, 0, None, n, d, h, w, c, u.cin, st)
+        elif self._use_tc(u.cout, u.cin):
             img = self._weight_image(u.conv, u.kd, True, ws)
             call("fpl_conv3d_tc", ptr(dy), c // 8, 0, ptr(img), None, ptr(dx), u.cin // 8, 0, None,
                  n, d, h, w, c, u.cin, u.kd, st)

@@ -59,6 +59,15 @@ int fpl_conv3d_prep_weight_batch(int count, const float* const* h_w, const int* 
 int fpl_conv3d_tc(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias,
                   void* y, int y_c8tot, int y_c8off, double* stats,
                   int n, int d, int h, int w, int cin, int cout, int kd, void* stream);
+/* Depth-folded variant for the small-channel k3 layers (csrc/conv_tc_dfold.cu): every input plane tile issues 9 MMAs
+ * of N = 3*Cout into the accumulators of the three output planes it feeds, with all 27 weight taps resident in
+ * shared memory.  Same contract as fpl_conv3d_tc (kd = 3 only); its own staged image.  image_bytes returns -1 when
+ * (cin, cout) is not eligible (needs cin <= 64, cout in {16,32,64}, 27*cin*cout*2 B <= 112 KB). */
+int64_t fpl_conv3d_dfold_image_bytes(int cin, int cout);
+int fpl_conv3d_dfold_prep_weight(const float* w, int cin, int cout, int transpose_flip, void* image, void* stream);
+int fpl_conv3d_tc_dfold(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias,
+                        void* y, int y_c8tot, int y_c8off, double* stats,
+                        int n, int d, int h, int w, int cin, int cout, void* stream);
 /* CUDA-core conv with the same contract (used for shapes the tensor kernel does
  * not cover and as the on-device cross-check).  w is fp32 [Cout][Cin][kd][3][3];
  * transpose_flip as above; round_w_bf16!=0 rounds weights to bf16 first. */

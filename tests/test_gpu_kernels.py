@@ -567,3 +567,48 @@ def test_convt_k2s2_tensor_core_fwd_dgrad_wgrad(cin, cout, kd2, shape):
               kd2, _st())
     assert max_rel(from_c8(dx).cpu(), x.grad) < 6e-3
     assert max_rel(dw.cpu(), 2 * wt.grad) < 1e-4
+
+
+@pytest.mark.parametrize("transpose", [0, 1])
+@pytest.mark.parametrize("cin,cout,shape", [(16, 16, (2, 4, 32, 16)), (32, 16, (1, 3, 20, 12)), (16, 32, (1, 17, 16, 8)),
+                                            (64, 32, (1, 2, 16, 16)), (32, 64, (1, 9, 10, 9)), (16, 16, (1, 20, 16, 16))])
+def test_conv3d_depth_folded_tensor_core_kernel(cin, cout, shape, transpose):
+    """Depth-folded tcgen05 conv (N spans the 3 output planes an input plane feeds; resident weights; TMEM
+    accumulators zeroed by the epilogue) against torch on bf16-rounded operands, forward and dgrad, incl.
+    ragged tiles, odd depths and a short last depth chunk; and bit-compatible with fpl_conv3d_tc up to 1 ulp."""
+    from fplplus_b200 import lib as L
+    n, d, h, w = shape
+    wt = bf16_round(randn(12, cout, cin, 3, 3, 3, scale=0.1))
+    if not transpose:
+        x = bf16_round(randn(11, n, cin, d, h, w))
+        b = randn(13, cout, scale=0.1)
+        ref = F.conv3d(x, wt, b, padding=1)
+        xin, ci, co, bias = x, cin, cout, b.to(DEV)
+    else:
+        dy = bf16_round(randn(14, n, cout, d, h, w))
+        xx = torch.zeros(n, cin, d, h, w, requires_grad=True)
+        F.conv3d(xx, wt, None, padding=1).backward(dy)
+        ref, xin, ci, co, bias = xx.grad, dy, cout, cin, None
+    nbytes = L.load().fpl_conv3d_dfold_image_bytes(ci, co)
+    assert nbytes == 27 * ci * co * 2
+    xb, wd = to_c8(xin.to(DEV)), wt.to(DEV)
+    img = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=DEV)
+    _call("fpl_conv3d_dfold_prep_weight", _p(wd), cin, cout, transpose, _p(img), _st())
+    y = torch.zeros((n, d, co // 8, h, w, 8), dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros(2 * co, dtype=torch.float64, device=DEV)
+    for _ in range(2):           # twice: the second launch must find nothing stale (accumulators are re-zeroed per launch)
+        stats.zero_()
+        _call("fpl_conv3d_tc_dfold", _p(xb), ci // 8, 0, _p(img), _p(bias), _p(y), co // 8, 0, _p(stats), n, d, h, w, ci, co, _st())
+    out = from_c8(y).cpu()
+    rd = ref.detach()
+    assert max_rel(out, rd) < 6e-3
+    s = stats.cpu()
+    np.testing.assert_allclose(s[:co], rd.double().sum((0, 2, 3, 4)), rtol=1e-4, atol=2e-3)
+    np.testing.assert_allclose(s[co:], (rd.double() ** 2).sum((0, 2, 3, 4)), rtol=1e-4, atol=2e-3)
+    img2 = torch.empty(L.load().fpl_conv3d_weight_image_bytes(ci, co, 3) // 2, dtype=torch.bfloat16, device=DEV)
+    _call("fpl_conv3d_prep_weight", _p(wd), cin, cout, 3, transpose, _p(img2), _st())
+    y2 = torch.zeros_like(y)
+    _call("fpl_conv3d_tc", _p(xb), ci // 8, 0, _p(img2), _p(bias), _p(y2), co // 8, 0, None, n, d, h, w, ci, co, 3, _st())
+    out2 = from_c8(y2).cpu()
+    assert max_rel(out, out2) < 5e-3 and float((out != out2).float().mean()) < 0.05
+    assert L.load().fpl_conv3d_dfold_image_bytes(128, 128) == -1         # large layers stay on fpl_conv3d_tc
