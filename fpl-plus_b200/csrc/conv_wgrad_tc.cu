@@ -34,14 +34,18 @@ struct WgCfg {
     int dy_off;            // offset of the dy tile inside a stage (x bytes rounded up to 128)
     int x_bytes, dy_bytes, stage_bytes, stages, pad_bytes, smem_bytes;
     int tmem_cols;
+    int pair;              // depth-paired mode: 2 dy planes x (2+2) x planes per tile (see the kernel)
+    int ncols;             // UMMA N = nb * (pair ? 2 : 1)
 };
 
-bool make_wg_cfg(int h, int w, int cin, int cout, int kd, int allow_m64, WgCfg& c) {
+bool make_wg_cfg(int h, int w, int cin, int cout, int kd, int allow_m64, int allow_pair, WgCfg& c) {
     if (cin % 8 != 0 || cout % 16 != 0 || cin <= 0 || cout <= 0) return false;
     c.tw = w >= 32 ? 32 : (w >= 16 ? 16 : 8);
     c.th = h >= 8 ? 8 : ((h + 1) / 2) * 2;
     const int g_all = cin / 8;
-    if (kd * g_all <= 16) { c.nkd = kd; c.c8chunk = g_all; c.mtiles_kd = 1; c.mtiles_c = 1; }
+    c.pair = (allow_pair && kd == 3 && g_all <= 4) ? 1 : 0;
+    if (c.pair) { c.nkd = 4; c.c8chunk = g_all; c.mtiles_kd = 1; c.mtiles_c = 1; }
+    else if (kd * g_all <= 16) { c.nkd = kd; c.c8chunk = g_all; c.mtiles_kd = 1; c.mtiles_c = 1; }
     else {
         c.nkd = 1; c.mtiles_kd = kd;
         c.c8chunk = g_all < 16 ? g_all : 16;
@@ -50,13 +54,14 @@ bool make_wg_cfg(int h, int w, int cin, int cout, int kd, int allow_m64, WgCfg& 
     }
     const int groups = c.nkd * c.c8chunk;
     c.m = (groups <= 8 && allow_m64) ? 64 : 128;
-    c.nb = cout % 32 == 0 ? 32 : 16;
+    c.nb = (cout % 32 == 0 && !c.pair) ? 32 : 16;
+    c.ncols = c.pair ? 2 * c.nb : c.nb;
     c.nchunks = cout / c.nb;
     if (groups > 8 && c.tw == 32 && cin >= 32 && h * w >= 128 * 128) c.tw = 16;   // keep >= 3 stages at full resolution
     c.plane_x = (c.th + 2) * (c.tw + 2) * 16;
     c.plane_dy = c.th * c.tw * 16;
     c.x_bytes = groups * c.plane_x;
-    c.dy_bytes = (c.nb / 8) * c.plane_dy;
+    c.dy_bytes = (c.ncols / 8) * c.plane_dy;
     c.dy_off = ((c.x_bytes + 127) / 128) * 128;
     c.stage_bytes = ((c.dy_off + c.dy_bytes + 127) / 128) * 128;
     // the M=64/128 operand reads 8/16 channel-group planes from the tile start: keep that window inside the allocation
@@ -66,7 +71,7 @@ bool make_wg_cfg(int h, int w, int cin, int cout, int kd, int allow_m64, WgCfg& 
     if (c.stages > kMaxStagesW) c.stages = kMaxStagesW;
     if (c.stages < 2) return false;
     c.smem_bytes = c.stages * c.stage_bytes + c.pad_bytes + 1024 + 256;
-    int cols = 9 * c.nb;
+    int cols = 9 * c.ncols;
     c.tmem_cols = 32;
     while (c.tmem_cols < cols) c.tmem_cols *= 2;
     return c.tmem_cols <= 512;
@@ -81,6 +86,7 @@ struct WgParams {
     int plane_x, plane_dy, x_bytes, dy_off, stage_bytes, stages, tmem_cols;
     int tiles_h, tiles_w, tiles_total, split;
     int swap_lbo_sbo, m64_quadrant_layout;
+    int pair, ncols, dplanes;      // dplanes: tile index range along depth (D, or ceil(D/2) in pair mode)
 };
 
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
@@ -143,12 +149,14 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
                 int r = t;
                 const int tw_i = r % P.tiles_w; r /= P.tiles_w;
                 const int th_i = r % P.tiles_h; r /= P.tiles_h;
-                const int d = r % P.D;
-                const int n = r / P.D;
+                const int dp = r % P.dplanes;
+                const int n = r / P.dplanes;
+                // pair mode: dy planes (2dp, 2dp+1) against x planes 2dp-1 .. 2dp+2 (planes outside the volume: TMA zero fill)
+                const int d = P.pair ? 2 * dp : dp;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* x_dst = ring + (size_t)stage * P.stage_bytes;
                 uint8_t* dy_dst = x_dst + P.dy_off;
-                mbar_expect_tx(&full_bar[stage], (uint32_t)(P.x_bytes + (P.nb / 8) * P.plane_dy));
+                mbar_expect_tx(&full_bar[stage], (uint32_t)(P.x_bytes + (P.ncols / 8) * P.plane_dy));
                 tma_load_5d(x_dst, &xmap, &full_bar[stage], 2 * (tw_i * P.tw - 1), th_i * P.th - 1,
                             P.x_c8off + wk.mt_c * P.c8chunk, d + kd0 - pad_d, n);
                 tma_load_5d(dy_dst, &dymap, &full_bar[stage], 2 * (tw_i * P.tw), th_i * P.th,
@@ -160,7 +168,7 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
         // ===================== MMA issuer: the whole warp runs the loop (uniform), one lane issues =====================
         // kind::f16, bf16 x bf16 -> fp32, A and B both MN-major (bits 15, 16)
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                               ((uint32_t)(P.nb >> 3) << 17) | ((uint32_t)(P.m >> 4) << 24);
+                               ((uint32_t)(P.ncols >> 3) << 17) | ((uint32_t)(P.m >> 4) << 24);
         const uint32_t pitch_x = (uint32_t)(P.tw + 2) * 16, pitch_dy = (uint32_t)P.tw * 16;
         const uint32_t a_lbo = P.swap_lbo_sbo ? (uint32_t)P.plane_x : pitch_x;
         const uint32_t a_sbo = P.swap_lbo_sbo ? pitch_x : (uint32_t)P.plane_x;
@@ -189,7 +197,7 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
 #pragma unroll
                     for (int t9 = 0; t9 < 9; ++t9) {
                         const uint64_t adesc = a_hi | (uint64_t)(a_col + tap_off[t9]);
-                        if (leader) umma_bf16(tmem_base + (uint32_t)(t9 * P.nb), adesc, bdesc, idesc, accumulate);
+                        if (leader) umma_bf16(tmem_base + (uint32_t)(t9 * P.ncols), adesc, bdesc, idesc, accumulate);
                     }
                     accumulate = 1;
                 }
@@ -215,23 +223,27 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
         if (valid) {
             const int g = row >> 3;
             valid = g < P.nkd * P.c8chunk;
-            kdi = kd0 + g / P.c8chunk;
+            kdi = kd0 + g / P.c8chunk;                       // pair mode: index of the x plane (0..3) inside the tile
             ci = (wk.mt_c * P.c8chunk + g % P.c8chunk) * 8 + (row & 7);
         }
         for (int t9 = 0; t9 < 9; ++t9) {
-            for (int c0 = 0; c0 < P.nb; c0 += 16) {
+            for (int c0 = 0; c0 < P.ncols; c0 += 16) {
                 uint32_t r[16];
-                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t9 * P.nb + c0), r);
+                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t9 * P.ncols + c0), r);
                 tmem_ld_wait();
                 if (P.dump != nullptr && blockIdx.x == 0) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) P.dump[((int64_t)t9 * 128 + tlane) * P.nb + c0 + i] = __uint_as_float(r[i]);
+                    for (int i = 0; i < 16; ++i) P.dump[((int64_t)t9 * 128 + tlane) * P.ncols + c0 + i] = __uint_as_float(r[i]);
                 }
-                if (valid) {
+                // pair mode: column block dd = c0 / nb is dy plane 2dp+dd, row block kdi is x plane 2dp-1+kdi:
+                // depth tap kd = kdi - dd (the two (kdi, dd) blocks of one tap are summed by the atomics)
+                const int dd = P.pair ? c0 / P.nb : 0;
+                const int kd_tap = P.pair ? kdi - dd : kdi;
+                if (valid && kd_tap >= 0 && kd_tap < P.kd) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const int co = wk.nc * P.nb + c0 + i;
-                        atomicAdd(P.dw + ((int64_t)co * P.cin + ci) * T + kdi * 9 + t9, __uint_as_float(r[i]));
+                        const int co = wk.nc * P.nb + (c0 - dd * P.nb) + i;
+                        atomicAdd(P.dw + ((int64_t)co * P.cin + ci) * T + kd_tap * 9 + t9, __uint_as_float(r[i]));
                     }
                 }
             }
@@ -245,7 +257,7 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
     }
 }
 
-int g_wg_swap = 0, g_wg_allow_m64 = 1, g_wg_m64_quadrant = 1;
+int g_wg_swap = 0, g_wg_allow_m64 = 1, g_wg_m64_quadrant = 1, g_wg_allow_pair = 1;
 float* g_wg_dump = nullptr;
 
 CUresult encode_5d(EncodeTiledFn encode, CUtensorMap* map, const void* base, int n, int d, int c8tot, int h, int w,
@@ -269,13 +281,14 @@ void fpl_wgrad_debug_set(int key, long long value) {
     if (key == 11) g_wg_allow_m64 = (int)value;
     if (key == 12) g_wg_m64_quadrant = (int)value;
     if (key == 13) g_wg_dump = reinterpret_cast<float*>(value);
+    if (key == 14) g_wg_allow_pair = (int)value;
 }
 
 extern "C" int fpl_conv3d_wgrad_tc(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
                                    float* dw, int n, int d, int h, int w, int cin, int cout, int kd, void* stream) {
     FPL_REQUIRE(kd == 1 || kd == 3, "fpl_conv3d_wgrad_tc: kd=%d must be 1 or 3", kd);
     WgCfg c;
-    FPL_REQUIRE(make_wg_cfg(h, w, cin, cout, kd, g_wg_allow_m64, c),
+    FPL_REQUIRE(make_wg_cfg(h, w, cin, cout, kd, g_wg_allow_m64, g_wg_allow_pair && d >= 2, c),
                 "fpl_conv3d_wgrad_tc: unsupported shape (cin %d, cout %d, %dx%d)", cin, cout, h, w);
     FPL_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0,
                 "fpl_conv3d_wgrad_tc: x/dy must be 16-byte aligned");
@@ -284,7 +297,7 @@ extern "C" int fpl_conv3d_wgrad_tc(const void* x, int x_c8tot, int x_c8off, cons
     CUtensorMap xmap, dymap;
     CUresult r = encode_5d(encode, &xmap, x, n, d, x_c8tot, h, w, c.tw + 2, c.th + 2, c.c8chunk, c.nkd);
     FPL_REQUIRE(r == CUDA_SUCCESS, "fpl_conv3d_wgrad_tc: tensor map (x) failed (%d)", (int)r);
-    r = encode_5d(encode, &dymap, dy, n, d, dy_c8tot, h, w, c.tw, c.th, c.nb / 8, 1);
+    r = encode_5d(encode, &dymap, dy, n, d, dy_c8tot, h, w, c.tw, c.th, c.nb / 8, c.pair ? 2 : 1);
     FPL_REQUIRE(r == CUDA_SUCCESS, "fpl_conv3d_wgrad_tc: tensor map (dy) failed (%d)", (int)r);
     WgParams P;
     P.dw = dw; P.dump = g_wg_dump;
@@ -294,7 +307,8 @@ extern "C" int fpl_conv3d_wgrad_tc(const void* x, int x_c8tot, int x_c8off, cons
     P.m = c.m; P.nb = c.nb; P.nchunks = c.nchunks; P.plane_x = c.plane_x; P.plane_dy = c.plane_dy; P.x_bytes = c.x_bytes; P.dy_off = c.dy_off;
     P.stage_bytes = c.stage_bytes; P.stages = c.stages; P.tmem_cols = c.tmem_cols;
     P.tiles_h = (h + c.th - 1) / c.th; P.tiles_w = (w + c.tw - 1) / c.tw;
-    int64_t tiles = (int64_t)P.tiles_h * P.tiles_w * d * n;
+    P.pair = c.pair; P.ncols = c.ncols; P.dplanes = c.pair ? (d + 1) / 2 : d;
+    int64_t tiles = (int64_t)P.tiles_h * P.tiles_w * P.dplanes * n;
     FPL_REQUIRE(tiles < (1ll << 30), "fpl_conv3d_wgrad_tc: too many tiles");
     P.tiles_total = (int)tiles;
     const int pairs = c.mtiles_kd * c.mtiles_c * c.nchunks;
