@@ -608,11 +608,46 @@ __global__ void __launch_bounds__(256) pack_ncdhw_c8_kernel(const float* __restr
     }
 }
 
+// 1-channel fp32 image [N][1][D][H][W] -> C8-planar bf16 with 16 channels: channel t9 = kh*3+kw holds the in-plane
+// neighbour x[d][h+kh-1][w+kw-1] (zero outside the plane), channels 9..15 are zero.  The stem conv k(3,3,3) then is a
+// k(3,1,1) conv over these 16 channels, which the tensor-core kernels run with ONE in-plane tap.
+__global__ void __launch_bounds__(256) patch9_kernel(const float* __restrict__ x, bf16x8* out, int D, int H, int W) {
+    const int nd = blockIdx.y;
+    const int HW = H * W;
+    const float* plane = x + (int64_t)nd * HW;
+    for (int hw = blockIdx.x * blockDim.x + threadIdx.x; hw < HW; hw += gridDim.x * blockDim.x) {
+        const int h = hw / W, w = hw - h * W;
+        float f[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) f[t] = 0.f;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int hy = h + kh - 1;
+            if (hy < 0 || hy >= H) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int wx = w + kw - 1;
+                if (wx >= 0 && wx < W) f[kh * 3 + kw] = __ldg(plane + hy * W + wx);
+            }
+        }
+        st_bf16x8(out + ((int64_t)nd * 2 + 0) * HW + hw, f);
+        st_bf16x8(out + ((int64_t)nd * 2 + 1) * HW + hw, f + 8);
+    }
+}
+
 }  // namespace
 
 // ======================================================================================
 // C ABI
 // ======================================================================================
+extern "C" int fpl_patch9_c8(const float* x, void* out16, int n, int d, int h, int w, void* stream) {
+    FPL_REQUIRE((int64_t)n * d <= 65535, "fpl_patch9_c8: too many planes");
+    int chunks = (h * w + 1023) / 1024;
+    patch9_kernel<<<dim3(chunks, n * d), 256, 0, (cudaStream_t)stream>>>(x, (bf16x8*)out16, d, h, w);
+    FPL_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int fpl_pack_ncdhw_to_c8(const float* x, int c, void* out, int out_c8tot, int out_c8off, int groups,
                                     float* chan_sum, int n, int d, int h, int w, void* stream) {
     FPL_REQUIRE(c >= 1 && groups >= 1 && c <= groups * 8, "fpl_pack_ncdhw_to_c8: %d channels do not fit %d groups", c, groups);

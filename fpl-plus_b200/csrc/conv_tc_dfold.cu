@@ -34,6 +34,7 @@ struct DfParams {
     int nb, nslices, dc, ndc;        // dc: output planes per depth chunk; ndc = ceil(D/dc)
     int a_bytes, b_bytes, stages, tmem_cols;
     int tiles_h, tiles_w, total_items;
+    int taps;                        // 9 (k 3x3x3) or 1 (k 3x1x1: only the centre in-plane tap)
 };
 
 __device__ __forceinline__ void tmem_st_zero16(uint32_t taddr) {
@@ -161,8 +162,9 @@ __global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid
                         const uint32_t b_j = b_base + (uint32_t)j * b_kstep;
 #pragma unroll
                         for (int t9 = 0; t9 < 9; ++t9) {
+                            if (P.taps == 1 && t9 != 4) continue;
                             const uint64_t adesc = a_hi | (uint64_t)(a_j + (uint32_t)((t9 / 3) * kBoxW + (t9 % 3)));
-                            const uint64_t bdesc = b_hi | (uint64_t)(b_j + (uint32_t)t9 * b_tap);
+                            const uint64_t bdesc = b_hi | (uint64_t)(b_j + (uint32_t)(P.taps == 1 ? 0 : t9) * b_tap);
                             if (leader) umma_bf16(d_tmem, adesc, bdesc, idesc, 1u);
                         }
                     }
@@ -282,22 +284,22 @@ __global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid
 // weights: fp32 [Cout][Cin][27] -> bf16 [slice][tap9][cin/16][2][3*nb][8]; column block jj of B feeds output plane
 // z-1+jj of input plane z, i.e. depth tap kd = 2 - jj.  transpose_flip as in fpl_conv3d_prep_weight.
 __global__ void dfold_prep_kernel(const float* __restrict__ w, __nv_bfloat16* image, int cin_eff, int cout_eff, int transpose_flip,
-                                  int nb, int total) {
-    const int ksteps = cin_eff / 16, n3 = 3 * nb;
+                                  int nb, int total, int taps) {
+    const int ksteps = cin_eff / 16, n3 = 3 * nb, T = 3 * taps;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int t = i;
         const int el = t % 8; t /= 8;
         const int nn = t % n3; t /= n3;
         const int k8 = t % 2; t /= 2;
         const int j = t % ksteps; t /= ksteps;
-        const int t9 = t % 9;
-        const int sl = t / 9;
+        const int t9 = t % taps;
+        const int sl = t / taps;
         const int in = j * 16 + k8 * 8 + el;
         const int jj = nn / nb, out = sl * nb + nn % nb;
-        const int tap = (2 - jj) * 9 + t9;
+        const int tap = (2 - jj) * taps + t9;
         float v;
-        if (!transpose_flip) v = w[((int64_t)out * cin_eff + in) * 27 + tap];
-        else v = w[((int64_t)in * cout_eff + out) * 27 + (26 - tap)];
+        if (!transpose_flip) v = w[((int64_t)out * cin_eff + in) * T + tap];
+        else v = w[((int64_t)in * cout_eff + out) * T + (T - 1 - tap)];
         image[i] = __float2bfloat16_rn(v);
     }
 }
@@ -306,13 +308,13 @@ struct DfCfg {
     int nb, nslices, dc, stages, a_bytes, b_bytes, tmem_cols, smem_bytes, ctas_per_sm;
 };
 
-bool make_df_cfg(int cin, int cout, int d, DfCfg& c) {
+bool make_df_cfg(int cin, int cout, int d, DfCfg& c, int taps = 9) {
     if (cin % 16 || cout % 16 || cin > 64) return false;
     c.nb = cout <= 64 ? cout : (cout % 64 == 0 ? 64 : (cout % 32 == 0 ? 32 : 16));
     if (c.nb != 16 && c.nb != 32 && c.nb != 64) return false;
     c.nslices = cout / c.nb;
     if (c.nslices != 1) return false;          // resident weights are loaded once per CTA
-    c.b_bytes = 9 * cin * 3 * c.nb * 2;
+    c.b_bytes = taps * cin * 3 * c.nb * 2;
     if (c.b_bytes > 112 * 1024) return false;
     c.a_bytes = (cin / 8) * kPlaneBytes;
     c.dc = c.nb == 16 ? 16 : 8;
@@ -346,23 +348,86 @@ extern "C" int64_t fpl_conv3d_dfold_image_bytes(int cin, int cout) {
     return (int64_t)c.nslices * c.b_bytes;
 }
 
-extern "C" int fpl_conv3d_dfold_prep_weight(const float* w, int cin, int cout, int transpose_flip, void* image, void* stream) {
+static int dfold_prep(const float* w, int cin, int cout, int transpose_flip, int taps, void* image, void* stream) {
     const int cin_eff = transpose_flip ? cout : cin, cout_eff = transpose_flip ? cin : cout;
     DfCfg c;
-    FPL_REQUIRE(make_df_cfg(cin_eff, cout_eff, 16, c), "fpl_conv3d_dfold_prep_weight: unsupported channels (%d -> %d)", cin_eff, cout_eff);
+    FPL_REQUIRE(make_df_cfg(cin_eff, cout_eff, 16, c, taps), "fpl_conv3d_dfold_prep_weight: unsupported channels (%d -> %d)", cin_eff, cout_eff);
     const int total = c.nslices * c.b_bytes / 2;
     int blocks = (total + 255) / 256;
     if (blocks > FPL_NUM_SMS * 4) blocks = FPL_NUM_SMS * 4;
-    dfold_prep_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)image, cin_eff, cout_eff, transpose_flip, c.nb, total);
+    dfold_prep_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)image, cin_eff, cout_eff, transpose_flip, c.nb, total, taps);
     FPL_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int fpl_conv3d_tc_dfold(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias, void* y,
-                                   int y_c8tot, int y_c8off, double* stats, int n, int d, int h, int w, int cin, int cout,
-                                   void* stream) {
+extern "C" int fpl_conv3d_dfold_prep_weight(const float* w, int cin, int cout, int transpose_flip, void* image, void* stream) {
+    return dfold_prep(w, cin, cout, transpose_flip, 9, image, stream);
+}
+
+/* k = (3,1,1): w is fp32 [Cout][Cin][3] */
+extern "C" int fpl_conv3d_k311_prep_weight(const float* w, int cin, int cout, void* image, void* stream) {
+    return dfold_prep(w, cin, cout, 0, 1, image, stream);
+}
+
+// all depth-folded images of a network in ONE launch (blockIdx.y = entry); host arrays of length count
+namespace {
+constexpr int kMaxDfBatch = 64;
+struct DfPrepBatch {
+    const float* w[kMaxDfBatch];
+    __nv_bfloat16* image[kMaxDfBatch];
+    int cin_eff[kMaxDfBatch], cout_eff[kMaxDfBatch], total[kMaxDfBatch];
+    unsigned char tf[kMaxDfBatch], nb[kMaxDfBatch];
+};
+__global__ void dfold_prep_batch_kernel(const __grid_constant__ DfPrepBatch B) {
+    const int e = blockIdx.y;
+    const float* __restrict__ w = B.w[e];
+    __nv_bfloat16* image = B.image[e];
+    const int cin_eff = B.cin_eff[e], cout_eff = B.cout_eff[e], nb = B.nb[e], total = B.total[e], tf = B.tf[e];
+    const int ksteps = cin_eff / 16, n3 = 3 * nb;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int t = i;
+        const int el = t % 8; t /= 8;
+        const int nn = t % n3; t /= n3;
+        const int k8 = t % 2; t /= 2;
+        const int j = t % ksteps; t /= ksteps;
+        const int t9 = t % 9;
+        const int sl = t / 9;
+        const int in = j * 16 + k8 * 8 + el;
+        const int jj = nn / nb, out = sl * nb + nn % nb;
+        const int tap = (2 - jj) * 9 + t9;
+        const float v = tf ? w[((int64_t)in * cout_eff + out) * 27 + (26 - tap)] : w[((int64_t)out * cin_eff + in) * 27 + tap];
+        image[i] = __float2bfloat16_rn(v);
+    }
+}
+}  // namespace
+
+extern "C" int fpl_conv3d_dfold_prep_weight_batch(int count, const float* const* h_w, const int* h_cin, const int* h_cout,
+                                                  const int* h_transpose_flip, void* const* h_images, void* stream) {
+    FPL_REQUIRE(count >= 0 && count <= kMaxDfBatch, "fpl_conv3d_dfold_prep_weight_batch: count %d not in [0,%d]", count, kMaxDfBatch);
+    if (count == 0) return 0;
+    DfPrepBatch B;
+    int max_total = 0;
+    for (int e = 0; e < count; ++e) {
+        const int tf = h_transpose_flip[e];
+        const int cin_eff = tf ? h_cout[e] : h_cin[e], cout_eff = tf ? h_cin[e] : h_cout[e];
+        DfCfg c;
+        FPL_REQUIRE(make_df_cfg(cin_eff, cout_eff, 16, c), "fpl_conv3d_dfold_prep_weight_batch: unsupported channels (%d -> %d)", cin_eff, cout_eff);
+        B.w[e] = h_w[e]; B.image[e] = (__nv_bfloat16*)h_images[e]; B.cin_eff[e] = cin_eff; B.cout_eff[e] = cout_eff;
+        B.tf[e] = (unsigned char)tf; B.nb[e] = (unsigned char)c.nb; B.total[e] = c.nslices * c.b_bytes / 2;
+        if (B.total[e] > max_total) max_total = B.total[e];
+    }
+    int bx = (max_total + 255) / 256;
+    if (bx > 32) bx = 32;
+    dfold_prep_batch_kernel<<<dim3(bx, count), 256, 0, (cudaStream_t)stream>>>(B);
+    FPL_LAUNCH_CHECK();
+    return 0;
+}
+
+static int dfold_launch(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias, void* y,
+                        int y_c8tot, int y_c8off, double* stats, int n, int d, int h, int w, int cin, int cout, int taps,
+                        void* stream) {
     DfCfg c;
-    FPL_REQUIRE(make_df_cfg(cin, cout, d, c), "fpl_conv3d_tc_dfold: unsupported shape (%d -> %d, depth %d)", cin, cout, d);
+    FPL_REQUIRE(make_df_cfg(cin, cout, d, c, taps), "fpl_conv3d_tc_dfold: unsupported shape (%d -> %d, depth %d)", cin, cout, d);
     FPL_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(image) & 15) == 0,
                 "fpl_conv3d_tc_dfold: x/image must be 16-byte aligned");
     EncodeTiledFn encode = get_encode_fn();
@@ -386,10 +451,25 @@ extern "C" int fpl_conv3d_tc_dfold(const void* x, int x_c8tot, int x_c8off, cons
     int64_t total = (int64_t)P.tiles_h * P.tiles_w * P.ndc * n * c.nslices;
     FPL_REQUIRE(total < (1ll << 30), "fpl_conv3d_tc_dfold: too many items");
     P.total_items = (int)total;
+    P.taps = taps;
     FPL_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_dfold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
     int grid = FPL_NUM_SMS * c.ctas_per_sm;
     if (grid > P.total_items) grid = P.total_items;
     conv3d_tc_dfold_kernel<<<grid, kThreadsD, c.smem_bytes, (cudaStream_t)stream>>>(xmap, P);
     FPL_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int fpl_conv3d_tc_dfold(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias, void* y,
+                                   int y_c8tot, int y_c8off, double* stats, int n, int d, int h, int w, int cin, int cout,
+                                   void* stream) {
+    return dfold_launch(x, x_c8tot, x_c8off, image, bias, y, y_c8tot, y_c8off, stats, n, d, h, w, cin, cout, 9, stream);
+}
+
+/* k = (3,1,1) "same" conv (depth taps only) with the same machinery: 1 MMA (N = 3*Cout) per input plane and K step.
+ * Used for the stem after fpl_patch9_c8 has turned the 9 in-plane neighbours of the 1-channel image into channels. */
+extern "C" int fpl_conv3d_tc_k311(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias, void* y,
+                                  int y_c8tot, int y_c8off, double* stats, int n, int d, int h, int w, int cin, int cout,
+                                  void* stream) {
+    return dfold_launch(x, x_c8tot, x_c8off, image, bias, y, y_c8tot, y_c8off, stats, n, d, h, w, cin, cout, 1, stream);
 }

@@ -87,6 +87,7 @@ struct WgParams {
     int tiles_h, tiles_w, tiles_total, split;
     int swap_lbo_sbo, m64_quadrant_layout;
     int pair, ncols, dplanes;      // dplanes: tile index range along depth (D, or ceil(D/2) in pair mode)
+    int taps;                      // 9, or 1 = only the centre in-plane tap (k = (kd,1,1))
 };
 
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
@@ -196,8 +197,9 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
                     const uint32_t a_col = a_row + (uint32_t)j * 8;
 #pragma unroll
                     for (int t9 = 0; t9 < 9; ++t9) {
+                        if (P.taps == 1 && t9 != 4) continue;
                         const uint64_t adesc = a_hi | (uint64_t)(a_col + tap_off[t9]);
-                        if (leader) umma_bf16(tmem_base + (uint32_t)(t9 * P.ncols), adesc, bdesc, idesc, accumulate);
+                        if (leader) umma_bf16(tmem_base + (uint32_t)((P.taps == 1 ? 0 : t9) * P.ncols), adesc, bdesc, idesc, accumulate);
                     }
                     accumulate = 1;
                 }
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
         const int quarter = warp & 3;
         mbar_wait(done_bar, 0);
         tc_fence_after();
-        const int T = P.kd * 9;
+        const int T = P.kd * P.taps;
         const int tlane = quarter * 32 + lane;               // TMEM lane this thread reads
         int row;                                             // M row held by that lane
         if (P.m == 128 || !P.m64_quadrant_layout) row = tlane;
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
             kdi = kd0 + g / P.c8chunk;                       // pair mode: index of the x plane (0..3) inside the tile
             ci = (wk.mt_c * P.c8chunk + g % P.c8chunk) * 8 + (row & 7);
         }
-        for (int t9 = 0; t9 < 9; ++t9) {
+        for (int t9 = 0; t9 < P.taps; ++t9) {
             for (int c0 = 0; c0 < P.ncols; c0 += 16) {
                 uint32_t r[16];
                 tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t9 * P.ncols + c0), r);
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int co = wk.nc * P.nb + (c0 - dd * P.nb) + i;
-                        atomicAdd(P.dw + ((int64_t)co * P.cin + ci) * T + kd_tap * 9 + t9, __uint_as_float(r[i]));
+                        atomicAdd(P.dw + ((int64_t)co * P.cin + ci) * T + kd_tap * P.taps + t9, __uint_as_float(r[i]));
                     }
                 }
             }
@@ -284,8 +286,8 @@ void fpl_wgrad_debug_set(int key, long long value) {
     if (key == 14) g_wg_allow_pair = (int)value;
 }
 
-extern "C" int fpl_conv3d_wgrad_tc(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
-                                   float* dw, int n, int d, int h, int w, int cin, int cout, int kd, void* stream) {
+static int wgrad_tc_launch(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
+                           float* dw, int n, int d, int h, int w, int cin, int cout, int kd, int taps, void* stream) {
     FPL_REQUIRE(kd == 1 || kd == 3, "fpl_conv3d_wgrad_tc: kd=%d must be 1 or 3", kd);
     WgCfg c;
     FPL_REQUIRE(make_wg_cfg(h, w, cin, cout, kd, g_wg_allow_m64, g_wg_allow_pair && d >= 2, c),
@@ -319,8 +321,20 @@ extern "C" int fpl_conv3d_wgrad_tc(const void* x, int x_c8tot, int x_c8off, cons
     if (split < 1) split = 1;
     P.split = split;
     P.swap_lbo_sbo = g_wg_swap; P.m64_quadrant_layout = g_wg_m64_quadrant;
+    P.taps = taps;
     FPL_CHECK_CUDA(cudaFuncSetAttribute(conv3d_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
     conv3d_wgrad_tc_kernel<<<pairs * split, kThreadsW, c.smem_bytes, (cudaStream_t)stream>>>(xmap, dymap, P);
     FPL_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int fpl_conv3d_wgrad_tc(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
+                                   float* dw, int n, int d, int h, int w, int cin, int cout, int kd, void* stream) {
+    return wgrad_tc_launch(x, x_c8tot, x_c8off, dy, dy_c8tot, dy_c8off, dw, n, d, h, w, cin, cout, kd, 9, stream);
+}
+
+/* wgrad of a k = (3,1,1) conv: dW[cout][cin][3] (fp32, ACCUMULATED into); one MMA per K step instead of nine. */
+extern "C" int fpl_conv3d_wgrad_tc_k311(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
+                                        float* dw, int n, int d, int h, int w, int cin, int cout, void* stream) {
+    return wgrad_tc_launch(x, x_c8tot, x_c8off, dy, dy_c8tot, dy_c8off, dw, n, d, h, w, cin, cout, 3, 1, stream);
 }

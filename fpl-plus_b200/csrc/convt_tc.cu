@@ -406,6 +406,57 @@ extern "C" int fpl_convt_prep_weight(const float* w, int cin, int cout, int kd2,
     return 0;
 }
 
+namespace {
+constexpr int kMaxCtBatch = 16;
+struct CtPrepBatch {
+    const float* w[kMaxCtBatch];
+    __nv_bfloat16* image[kMaxCtBatch];
+    int cin[kMaxCtBatch], cout[kMaxCtBatch], ntaps[kMaxCtBatch], mode[kMaxCtBatch], nb[kMaxCtBatch], kc[kMaxCtBatch],
+        nchunks[kMaxCtBatch], total[kMaxCtBatch];
+};
+__global__ void convt_prep_batch_kernel(const __grid_constant__ CtPrepBatch B) {
+    const int e = blockIdx.y;
+    const float* __restrict__ w = B.w[e];
+    __nv_bfloat16* image = B.image[e];
+    const int cout = B.cout[e], ntaps = B.ntaps[e], mode = B.mode[e], nb = B.nb[e], kc = B.kc[e], nchunks = B.nchunks[e];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B.total[e]; i += gridDim.x * blockDim.x) {
+        int t = i;
+        const int el = t % 8; t /= 8;
+        const int nrow = t % nb; t /= nb;
+        const int k8 = t % (kc / 8); t /= (kc / 8);
+        const int q = t % nchunks;
+        const int sl = t / nchunks;
+        const int k = q * kc + k8 * 8 + el, nn = sl * nb + nrow;
+        int ci, co, tap;
+        if (mode == 0) { ci = k; tap = nn / cout; co = nn - tap * cout; }
+        else { tap = k / cout; co = k - tap * cout; ci = nn; }
+        image[i] = __float2bfloat16_rn(w[((int64_t)ci * cout + co) * ntaps + tap]);
+    }
+}
+}  // namespace
+
+extern "C" int fpl_convt_prep_weight_batch(int count, const float* const* h_w, const int* h_cin, const int* h_cout,
+                                           const int* h_kd2, const int* h_mode, void* const* h_images, void* stream) {
+    FPL_REQUIRE(count >= 0 && count <= kMaxCtBatch, "fpl_convt_prep_weight_batch: count %d not in [0,%d]", count, kMaxCtBatch);
+    if (count == 0) return 0;
+    CtPrepBatch B;
+    int max_total = 0;
+    for (int e = 0; e < count; ++e) {
+        const int ntaps = 4 * h_kd2[e], mode = h_mode[e], cin = h_cin[e], cout = h_cout[e];
+        const int kdim = mode == 0 ? cin : ntaps * cout, ndim = mode == 0 ? ntaps * cout : cin;
+        CtCfg c;
+        FPL_REQUIRE(make_ct_cfg(kdim, ndim, mode == 0 ? cin : cout, c), "fpl_convt_prep_weight_batch: unsupported channels (%d -> %d)", cin, cout);
+        B.w[e] = h_w[e]; B.image[e] = (__nv_bfloat16*)h_images[e]; B.cin[e] = cin; B.cout[e] = cout; B.ntaps[e] = ntaps;
+        B.mode[e] = mode; B.nb[e] = c.nb; B.kc[e] = c.kc; B.nchunks[e] = c.nchunks; B.total[e] = kdim * ndim;
+        if (B.total[e] > max_total) max_total = B.total[e];
+    }
+    int bx = (max_total + 255) / 256;
+    if (bx > 64) bx = 64;
+    convt_prep_batch_kernel<<<dim3(bx, count), 256, 0, (cudaStream_t)stream>>>(B);
+    FPL_LAUNCH_CHECK();
+    return 0;
+}
+
 static int convt_gemm_launch(int mode, const void* a, int a_c8tot, int a_c8off, const void* image, const float* bias, void* out,
                              int out_c8tot, int out_c8off, int n, int d, int h, int w, int cin, int cout, int kd2,
                              void* stream) {

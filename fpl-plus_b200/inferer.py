@@ -9,6 +9,8 @@ into the volume by a fused accumulate kernel and normalised by the visit count o
 the un-flip of TTA passes is folded into the accumulate kernel.  The reference's probe forward
 on a ones tensor (infer_func.py:92-93) is not issued: it only counts outputs.
 """
+import ctypes
+
 import torch
 
 from .ops import call, ptr, stream_ptr
@@ -25,6 +27,7 @@ class Inferer(object):
     def __init__(self, config):
         self.config = config
         self.max_batch = config.get('window_batch', 8)
+        self._side = None
 
     # window enumeration: infer_func.py:55-85 (w outer, h, d inner; last window clamped)
     def _windows(self, img_shape):
@@ -48,11 +51,19 @@ class Inferer(object):
                     starts.append((min(d, img_shape[0] - win[0]), h0, w0))
         return starts, win
 
-    def _model(self, x, domain_label):
-        out = self.model(x, domain_label=domain_label)
+    def _model(self, x, domain_label, lane=None):
+        if lane is None:
+            out = self.model(x, domain_label=domain_label)
+        else:
+            out = self.model(x, domain_label=domain_label, graph_lane=lane)
         if isinstance(out, (tuple, list)):
             out = out[0]
         return out
+
+    def _two_lanes(self, model):
+        """The fplplus_b200 network accepts ``graph_lane``: two half-batches of windows can then run concurrently
+        on two streams (tensor-pipe-bound convolutions of one under the HBM-bound BatchNorm kernels of the other)."""
+        return self.config.get('window_two_streams', True) and hasattr(model, "_forward_graphed") and model.cuda_graphs
 
     def _infer(self, image, domain_label, result, scale, flip_h, flip_w):
         """result += scale * unflip(sliding_window(model, image))."""
@@ -71,15 +82,35 @@ class Inferer(object):
         cnt = torch.zeros_like(acc)
         batched = _bn_in_eval(self.model)
         group = max(1, self.max_batch // b) if batched else 1
+        two = batched and self._two_lanes(self.model) and len(starts) >= 2
+        main = torch.cuda.current_stream()
+        if two:
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            # each lane accumulates into its own volume (windows of the two lanes may overlap): deterministic sums
+            acc1, cnt1 = torch.zeros_like(acc), torch.zeros_like(cnt)
+            self._side.wait_stream(main)
+            group = max(1, group // 2)
+        lane = 0
         for g0 in range(0, len(starts), group):
             chunk = starts[g0:g0 + group]
-            patches = [image[:, :, d0:d0 + win[0], h0:h0 + win[1], w0:w0 + win[2]] for d0, h0, w0 in chunk]
-            x = torch.cat(patches, 0).contiguous() if len(patches) > 1 else patches[0].contiguous()
-            dl = domain_label if len(chunk) == 1 else domain_label.repeat(len(chunk))
-            out = self._model(x, dl).float().contiguous()
-            for j, (d0, h0, w0) in enumerate(chunk):
-                call("fpl_window_accumulate", ptr(out[j * b:(j + 1) * b]), ptr(acc), ptr(cnt), b, class_num, vd, vh, vw,
-                     d0, h0, w0, win[0], win[1], win[2], 0, 0, 1.0, st)
+            stream = self._side if (two and lane == 1) else main
+            with torch.cuda.stream(stream):
+                patches = [image[:, :, d0:d0 + win[0], h0:h0 + win[1], w0:w0 + win[2]] for d0, h0, w0 in chunk]
+                x = torch.cat(patches, 0).contiguous() if len(patches) > 1 else patches[0].contiguous()
+                dl = domain_label if len(chunk) == 1 else domain_label.repeat(len(chunk))
+                out = self._model(x, dl, lane if two else None).float().contiguous()
+                sp = ctypes.c_void_p(stream.cuda_stream)
+                a_, c_ = (acc1, cnt1) if (two and lane == 1) else (acc, cnt)
+                for j, (d0, h0, w0) in enumerate(chunk):
+                    call("fpl_window_accumulate", ptr(out[j * b:(j + 1) * b]), ptr(a_), ptr(c_), b, class_num, vd, vh, vw,
+                         d0, h0, w0, win[0], win[1], win[2], 0, 0, 1.0, sp)
+            if two:
+                lane ^= 1
+        if two:
+            main.wait_stream(self._side)
+            acc.add_(acc1)
+            cnt.add_(cnt1)
         call("fpl_window_normalize", ptr(acc), ptr(cnt), 1.0, acc.numel(), st)
         call("fpl_window_accumulate", ptr(acc), ptr(result), None, b, class_num, vd, vh, vw, 0, 0, 0, vd, vh, vw,
              flip_h, flip_w, scale, st)

@@ -161,9 +161,12 @@ class UNet2D5_dsbn(nn.Module):
         self._img_cache = {}
         self._dropout_masks = None      # {unit name: uint8 keep mask, dense C8-planar order} (parity tests)
         self._rng_dev = None            # int64[1] device seed read by the dropout kernels inside CUDA graphs
+        self._rng_lanes = {}
+        self._cur_lane = 0
         self._seed_from_device = False
         self._graphs = {}               # (shape, domain, mode) -> _GraphedForward (no-grad forwards)
         self._graph_ws_keep = []        # workspaces baked into captured graphs: never recycled
+        self._infer_wss = {}            # eager no-grad workspaces per graph lane
         self.cuda_graphs = os.environ.get("FPL_CUDA_GRAPH", "1") != "0"
         self.wgrad_side_stream = os.environ.get("FPL_WGRAD_STREAM", "0") != "0"   # measured: no gain on top of the dual-domain streams
         self._aux_streams = {}
@@ -241,7 +244,9 @@ class UNet2D5_dsbn(nn.Module):
         return out
 
     # -- public forward ---------------------------------------------------------------------
-    def forward(self, x, domain_label=None):
+    def forward(self, x, domain_label=None, graph_lane=0):
+        """``graph_lane``: callers that run several no-grad forwards CONCURRENTLY on different streams (the
+        Inferer's two half-batches) give each its own lane, i.e. its own captured graph and static buffers."""
         if domain_label is None:
             raise ValueError("UNet2D5_dsbn.forward needs domain_label")
         if x.dim() != 5:
@@ -259,7 +264,7 @@ class UNet2D5_dsbn(nn.Module):
         if need_grad:
             return _UNetFunction.apply(self, domain, x, *params)
         if self.cuda_graphs and not torch.cuda.is_current_stream_capturing():
-            return self._forward_graphed(x, domain)
+            return self._forward_graphed(x, domain, graph_lane)
         ws = self._infer_ws
         if ws is None or ws.device != x.device:
             ws = self._infer_ws = _Workspace(x.device)
@@ -276,50 +281,53 @@ class UNet2D5_dsbn(nn.Module):
                     sig.append(u.dropout.training and u.dropout.p > 0.0)
         return tuple(sig)
 
-    def ensure_rng(self, device):
-        """The device-side dropout seed (must exist BEFORE a capture so that no allocation/zero-fill of it
-        is recorded into the graph)."""
-        if self._rng_dev is None or self._rng_dev.device != torch.device(device):
-            self._rng_dev = torch.zeros(1, dtype=torch.int64, device=device)
-        return self._rng_dev
+    def ensure_rng(self, device, lane=0):
+        """The device-side dropout seed of a graph lane (must exist BEFORE a capture so that no allocation /
+        zero-fill of it is recorded into the graph).  Lane 0 is also ``self._rng_dev`` (training graphs)."""
+        t = self._rng_lanes.get(lane)
+        if t is None or t.device != torch.device(device):
+            t = self._rng_lanes[lane] = torch.zeros(1, dtype=torch.int64, device=device)
+        if lane == 0:
+            self._rng_dev = t
+        return t
 
     def _draw_seed(self):
         # torch's CPU generator, so torch.manual_seed makes MC-dropout passes reproducible
         return int(torch.empty((), dtype=torch.int64).random_().item()) & ((1 << 62) - 1)
 
-    def _forward_graphed(self, x, domain):
-        key = (tuple(x.shape), domain, x.device.index, self._mode_signature(domain))
+    def _forward_graphed(self, x, domain, lane=0):
+        key = (tuple(x.shape), domain, x.device.index, self._mode_signature(domain), lane)
         ent = self._graphs.get(key)
         if ent is None:
             # first sight of this (shape, domain, mode): run eagerly (also warms lazy driver state), capture next time
             self._graphs[key] = ent = {"graph": None, "calls": 0}
         ent["calls"] += 1
         if ent["graph"] is None and ent["calls"] < 2:
-            ws = self._infer_ws
+            ws = self._infer_wss.get(lane)
             if ws is None or ws.device != x.device:
-                ws = self._infer_ws = _Workspace(x.device)
+                ws = self._infer_wss[lane] = _Workspace(x.device)
             logits, _ = self._run_forward(x, domain, ws)
             return logits
-        self.ensure_rng(x.device)
+        rng = self.ensure_rng(x.device, lane)
         self._note_depths(self._geometry(x.shape))
         self._refresh_weight_images(with_dgrad=False)      # eager: a captured graph never restages weights
         if ent["graph"] is None:
-            if len(self._graphs) > 16:                     # bound the memory held by stale shapes
+            if len(self._graphs) > 24:                     # bound the memory held by stale shapes
                 for k in [k for k in self._graphs if k != key][:8]:
                     del self._graphs[k]
             ent["x"] = x.clone()
             ent["ws"] = _Workspace(x.device)
             g = torch.cuda.CUDAGraph()
-            self._seed_from_device = True
+            self._seed_from_device, self._cur_lane = True, lane
             try:
                 with torch.cuda.graph(g):
                     ent["out"], _ = self._run_forward(ent["x"], domain, ent["ws"])
             finally:
-                self._seed_from_device = False
+                self._seed_from_device, self._cur_lane = False, 0
             ent["graph"] = g
         ent["x"].copy_(x, non_blocking=True)
         if any(key[3][1:]) and self._dropout_masks is None:
-            self._rng_dev.fill_(self._draw_seed())
+            rng.fill_(self._draw_seed())
         ent["graph"].replay()
         return ent["out"].clone()
 
@@ -366,7 +374,7 @@ class UNet2D5_dsbn(nn.Module):
     def _refresh_weight_images(self, with_dgrad):
         """(Re)stage every stale weight image with ONE batched launch."""
         lib = ops._lib.load()
-        todo = []
+        todo, todo_df, todo_ct = [], [], []
         for u in self._tc_convs():
             w = u.conv.weight
             depth = self._unit_depth.get(u.name, 0)
@@ -376,7 +384,7 @@ class UNet2D5_dsbn(nn.Module):
                 if u.name != "head" and self._dfold_ok(u.cout if transpose else u.cin, u.cin if transpose else u.cout,
                                                        u.kd, depth):
                     if not (transpose and u.name == "block0.conv#1"):
-                        self._dfold_image(u.conv, transpose)       # depth-folded kernel: its own image layout
+                        self._dfold_image(u.conv, transpose, todo_df)   # depth-folded kernel: its own image layout
                     continue
                 key = (id(w), transpose)
                 ent = self._img_cache.get(key)
@@ -391,9 +399,26 @@ class UNet2D5_dsbn(nn.Module):
                 trans = up.trans3d if up.dim == 3 else up.trans2d
                 if self._use_tc(trans.weight.shape[0], trans.weight.shape[1]):
                     kd2 = 2 if up.dim == 3 else 1
-                    self._convt_image(trans, kd2, 0)
+                    self._convt_image(trans, kd2, 0, todo_ct)
                     if with_dgrad:
-                        self._convt_image(trans, kd2, 1)
+                        self._convt_image(trans, kd2, 1, todo_ct)
+        for i in range(0, len(todo_df), 64):
+            part = todo_df[i:i + 64]
+            n = len(part)
+            arr_w = (ctypes.c_void_p * n)(*[t[0].data_ptr() for t in part])
+            arr_img = (ctypes.c_void_p * n)(*[t[4][1].data_ptr() for t in part])
+            ints = [(ctypes.c_int * n)(*[t[k] for t in part]) for k in (1, 2, 3)]
+            call("fpl_conv3d_dfold_prep_weight_batch", n, arr_w, ints[0], ints[1], ints[2], arr_img, stream_ptr())
+            for t in part:
+                t[4][0] = t[0]._version
+        if todo_ct:
+            n = len(todo_ct)
+            arr_w = (ctypes.c_void_p * n)(*[t[0].data_ptr() for t in todo_ct])
+            arr_img = (ctypes.c_void_p * n)(*[t[5][1].data_ptr() for t in todo_ct])
+            ints = [(ctypes.c_int * n)(*[t[k] for t in todo_ct]) for k in (1, 2, 3, 4)]
+            call("fpl_convt_prep_weight_batch", n, arr_w, ints[0], ints[1], ints[2], ints[3], arr_img, stream_ptr())
+            for t in todo_ct:
+                t[5][0] = t[0]._version
         for i in range(0, len(todo), 80):
             part = todo[i:i + 80]
             n = len(part)
@@ -423,7 +448,7 @@ class UNet2D5_dsbn(nn.Module):
             ok = self._dfold_cache[key] = ops._lib.load().fpl_conv3d_dfold_image_bytes(cin, cout) > 0
         return ok
 
-    def _dfold_image(self, conv, transpose):
+    def _dfold_image(self, conv, transpose, defer=None):
         w = conv.weight
         key = (id(w), "df%d" % (1 if transpose else 0))
         ent = self._img_cache.get(key)
@@ -432,14 +457,17 @@ class UNet2D5_dsbn(nn.Module):
             nbytes = ops._lib.load().fpl_conv3d_dfold_image_bytes(cout if transpose else cin, cin if transpose else cout)
             ent = self._img_cache[key] = [-1, torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)]
         if ent[0] != w._version:
-            call("fpl_conv3d_dfold_prep_weight", ptr(w), cin, cout, 1 if transpose else 0, ptr(ent[1]), stream_ptr())
-            ent[0] = w._version
+            if defer is not None:
+                defer.append((w, cin, cout, 1 if transpose else 0, ent))
+            else:
+                call("fpl_conv3d_dfold_prep_weight", ptr(w), cin, cout, 1 if transpose else 0, ptr(ent[1]), stream_ptr())
+                ent[0] = w._version
         return ent[1]
 
     def _convt_tc(self, cin, cout):
         return (self._use_tc(cin, cout) and os.environ.get("FPL_CONVT_IMPL", "tc") == "tc")
 
-    def _convt_image(self, trans, kd2, mode):
+    def _convt_image(self, trans, kd2, mode, defer=None):
         """Staged bf16 GEMM operand of a transposed conv (mode 0 forward, 1 dgrad), cached on the weight version."""
         w = trans.weight
         key = (id(w), "ct%d" % mode)
@@ -448,8 +476,11 @@ class UNet2D5_dsbn(nn.Module):
             nbytes = ops._lib.load().fpl_convt_weight_image_bytes(w.shape[0], w.shape[1], kd2)
             ent = self._img_cache[key] = [-1, torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)]
         if ent[0] != w._version:
-            call("fpl_convt_prep_weight", ptr(w), w.shape[0], w.shape[1], kd2, mode, ptr(ent[1]), stream_ptr())
-            ent[0] = w._version
+            if defer is not None:
+                defer.append((w, w.shape[0], w.shape[1], kd2, mode, ent))
+            else:
+                call("fpl_convt_prep_weight", ptr(w), w.shape[0], w.shape[1], kd2, mode, ptr(ent[1]), stream_ptr())
+                ent[0] = w._version
         return ent[1]
 
     def _weight_image(self, conv, kd, transpose, ws):
@@ -518,7 +549,7 @@ class UNet2D5_dsbn(nn.Module):
         # dropout stream: (seed, per-layer offset) drawn from torch's CPU generator, so torch.manual_seed
         # makes MC-dropout passes reproducible; backward regenerates the same Philox stream
         if self._seed_from_device:
-            seed, seed_dev = 0, self.ensure_rng(x.device)
+            seed, seed_dev = 0, self.ensure_rng(x.device, self._cur_lane)
         else:
             seed, seed_dev = self._draw_seed(), None
         rec = {"seed": seed, "seed_dev": seed_dev, "next_offset": 0, "geo": geo, "n": n, "x": x}

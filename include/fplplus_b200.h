@@ -65,9 +65,21 @@ int fpl_conv3d_tc(const void* x, int x_c8tot, int x_c8off, const void* image, co
  * (cin, cout) is not eligible (needs cin <= 64, cout in {16,32,64}, 27*cin*cout*2 B <= 112 KB). */
 int64_t fpl_conv3d_dfold_image_bytes(int cin, int cout);
 int fpl_conv3d_dfold_prep_weight(const float* w, int cin, int cout, int transpose_flip, void* image, void* stream);
+int fpl_conv3d_dfold_prep_weight_batch(int count, const float* const* h_w, const int* h_cin, const int* h_cout,
+                                       const int* h_transpose_flip, void* const* h_images, void* stream);
 int fpl_conv3d_tc_dfold(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias,
                         void* y, int y_c8tot, int y_c8off, double* stats,
                         int n, int d, int h, int w, int cin, int cout, void* stream);
+/* k = (3,1,1) conv (depth taps only) and its wgrad on the same kernels with ONE in-plane tap; w / dW are fp32
+ * [Cout][Cin][3].  With fpl_patch9_c8 (1-channel fp32 image -> 16 bf16 channels holding the 9 in-plane neighbours)
+ * they run the stem conv k(3,3,3), in_chns = 1 (unet2d5_dsbn.py:75, first conv3d_1) on the tensor cores. */
+int fpl_patch9_c8(const float* x, void* out16, int n, int d, int h, int w, void* stream);
+int fpl_conv3d_k311_prep_weight(const float* w, int cin, int cout, void* image, void* stream);
+int fpl_conv3d_tc_k311(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias,
+                       void* y, int y_c8tot, int y_c8off, double* stats,
+                       int n, int d, int h, int w, int cin, int cout, void* stream);
+int fpl_conv3d_wgrad_tc_k311(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
+                             float* dw, int n, int d, int h, int w, int cin, int cout, void* stream);
 /* CUDA-core conv with the same contract (used for shapes the tensor kernel does
  * not cover and as the on-device cross-check).  w is fp32 [Cout][Cin][kd][3][3];
  * transpose_flip as above; round_w_bf16!=0 rounds weights to bf16 first. */
@@ -123,6 +135,8 @@ int fpl_convt_k2s2_bwd(const void* x, int x_c8tot, int x_c8off, const float* w,
  * fpl_convt_prep_weight (mode 0: forward operand, mode 1: dgrad operand); need cin % 16 == 0, cout % 16 == 0. */
 int64_t fpl_convt_weight_image_bytes(int cin, int cout, int kd2);
 int fpl_convt_prep_weight(const float* w, int cin, int cout, int kd2, int mode, void* image, void* stream);
+int fpl_convt_prep_weight_batch(int count, const float* const* h_w, const int* h_cin, const int* h_cout,
+                                const int* h_kd2, const int* h_mode, void* const* h_images, void* stream);
 int fpl_convt_k2s2_fwd_tc(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias, void* y,
                           int y_c8tot, int y_c8off, int n, int d, int h, int w, int cin, int cout, int kd2, void* stream);
 int fpl_convt_k2s2_dgrad_tc(const void* dy, int dy_c8tot, int dy_c8off, const void* image_t, void* dx, int dx_c8tot,

@@ -166,3 +166,34 @@ def test_pseudo_label_is_argmax():
     rng = np.random.Generator(np.random.PCG64(5))
     z = rng.standard_normal((1, 5, 4, 6, 7)).astype(np.float32)
     np.testing.assert_array_equal(fpl_filter.pseudo_label(z), z.argmax(1).astype(np.uint8))
+
+
+def test_bf16_emulating_mode_tracks_the_fp32_oracle():
+    """oracle.unet_dsbn.forward(bf16=True) makes the CUDA path's storage roundings explicit (kernel parity is
+    asserted against it on the GPU); on CPU: it stays within the bf16 tolerance of the fp32 restatement, its
+    gradients exist for exactly the same parameters, and conv-bias gradients (biases feeding BatchNorm) vanish."""
+    from oracle import losses, synth, unet_dsbn
+    from oracle.gen_golden import NET_PARAMS
+    params = dict(NET_PARAMS, dropout=[0.0] * 5)
+    shape = (16, 32, 32)
+    x = torch.from_numpy(synth.synth_image(2, 1, shape, seed=5))
+    lab = synth.synth_label(2, 2, shape, seed=5)
+    y = torch.from_numpy(synth.one_hot(lab, 2))
+    res = {}
+    for bf in (False, True):
+        st = unet_dsbn.to_torch_state(synth.synth_state_dict(), requires_grad=True)
+        lg = unet_dsbn.forward(st, x, 0, params, bn_training=True, bf16=bf)
+        losses.combined_loss(lg, y, None, 0.5, 0.5).backward()
+        res[bf] = (lg.detach(), st)
+    a, b = res[True][0], res[False][0]
+    assert float((a - b).norm() / b.norm()) < 2e-2
+    g_emu = {k for k, v in res[True][1].items() if v.requires_grad and v.grad is not None and float(v.grad.abs().max()) > 0}
+    g_ref = {k for k, v in res[False][1].items() if v.requires_grad and v.grad is not None and float(v.grad.abs().max()) > 0}
+    bias_keys = {k for k in g_ref if k.endswith("conv3d_1.bias") or k.endswith("conv3d_2.bias")}
+    assert g_emu | bias_keys == g_ref | bias_keys
+    for k in bias_keys & set(res[True][1]):
+        gb = res[True][1][k].grad
+        assert gb is None or float(gb.abs().max()) < 1e-4
+    cos = torch.nn.functional.cosine_similarity(res[True][1]["up4.conv.conv3d_2.weight"].grad.flatten(),
+                                                res[False][1]["up4.conv.conv3d_2.weight"].grad.flatten(), dim=0)
+    assert float(cos) > 0.99
