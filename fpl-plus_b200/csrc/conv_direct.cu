@@ -611,7 +611,7 @@ __global__ void __launch_bounds__(256) pack_ncdhw_c8_kernel(const float* __restr
 // 1-channel fp32 image [N][1][D][H][W] -> C8-planar bf16 with 16 channels: channel t9 = kh*3+kw holds the in-plane
 // neighbour x[d][h+kh-1][w+kw-1] (zero outside the plane), channels 9..15 are zero.  The stem conv k(3,3,3) then is a
 // k(3,1,1) conv over these 16 channels, which the tensor-core kernels run with ONE in-plane tap.
-__global__ void __launch_bounds__(256) patch9_kernel(const float* __restrict__ x, bf16x8* out, int D, int H, int W) {
+__global__ void __launch_bounds__(256) patch9_kernel(const float* __restrict__ x, bf16x8* out, int D, int H, int W, int split) {
     const int nd = blockIdx.y;
     const int HW = H * W;
     const float* plane = x + (int64_t)nd * HW;
@@ -630,8 +630,16 @@ __global__ void __launch_bounds__(256) patch9_kernel(const float* __restrict__ x
                 if (wx >= 0 && wx < W) f[kh * 3 + kw] = __ldg(plane + hy * W + wx);
             }
         }
-        st_bf16x8(out + ((int64_t)nd * 2 + 0) * HW + hw, f);
-        st_bf16x8(out + ((int64_t)nd * 2 + 1) * HW + hw, f + 8);
+        const int groups = split ? 4 : 2;
+        st_bf16x8(out + ((int64_t)nd * groups + 0) * HW + hw, f);
+        st_bf16x8(out + ((int64_t)nd * groups + 1) * HW + hw, f + 8);
+        if (split) {
+            // second half: the bf16 rounding residual, so that hi + lo carries 16 mantissa bits of the image
+#pragma unroll
+            for (int t = 0; t < 16; ++t) f[t] -= __bfloat162float(__float2bfloat16_rn(f[t]));
+            st_bf16x8(out + ((int64_t)nd * 4 + 2) * HW + hw, f);
+            st_bf16x8(out + ((int64_t)nd * 4 + 3) * HW + hw, f + 8);
+        }
     }
 }
 
@@ -640,10 +648,10 @@ __global__ void __launch_bounds__(256) patch9_kernel(const float* __restrict__ x
 // ======================================================================================
 // C ABI
 // ======================================================================================
-extern "C" int fpl_patch9_c8(const float* x, void* out16, int n, int d, int h, int w, void* stream) {
+extern "C" int fpl_patch9_c8(const float* x, void* out, int split_hi_lo, int n, int d, int h, int w, void* stream) {
     FPL_REQUIRE((int64_t)n * d <= 65535, "fpl_patch9_c8: too many planes");
     int chunks = (h * w + 1023) / 1024;
-    patch9_kernel<<<dim3(chunks, n * d), 256, 0, (cudaStream_t)stream>>>(x, (bf16x8*)out16, d, h, w);
+    patch9_kernel<<<dim3(chunks, n * d), 256, 0, (cudaStream_t)stream>>>(x, (bf16x8*)out, d, h, w, split_hi_lo);
     FPL_LAUNCH_CHECK();
     return 0;
 }

@@ -35,6 +35,7 @@ struct DfParams {
     int a_bytes, b_bytes, stages, tmem_cols;
     int tiles_h, tiles_w, total_items;
     int taps;                        // 9 (k 3x3x3) or 1 (k 3x1x1: only the centre in-plane tap)
+    int a_ksteps;                    // distinct 16-channel K steps of A (B K step j reads A K step j % a_ksteps)
 };
 
 __device__ __forceinline__ void tmem_st_zero16(uint32_t taddr) {
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid
                     const uint32_t a_base = ring_u + (uint32_t)(((size_t)stage * P.a_bytes) >> 4);
                     const uint32_t b_base = b_u + (uint32_t)(jlo * P.nb);
                     for (int j = 0; j < ksteps; ++j) {
-                        const uint32_t a_j = a_base + (uint32_t)j * (2 * kPlaneBytes / 16);
+                        const uint32_t a_j = a_base + (uint32_t)(j % P.a_ksteps) * (2 * kPlaneBytes / 16);
                         const uint32_t b_j = b_base + (uint32_t)j * b_kstep;
 #pragma unroll
                         for (int t9 = 0; t9 < 9; ++t9) {
@@ -308,15 +309,16 @@ struct DfCfg {
     int nb, nslices, dc, stages, a_bytes, b_bytes, tmem_cols, smem_bytes, ctas_per_sm;
 };
 
-bool make_df_cfg(int cin, int cout, int d, DfCfg& c, int taps = 9) {
-    if (cin % 16 || cout % 16 || cin > 64) return false;
+bool make_df_cfg(int cin, int cout, int d, DfCfg& c, int taps = 9, int cin_a = 0) {
+    if (cin_a <= 0) cin_a = cin;
+    if (cin % 16 || cout % 16 || cin > 64 || cin_a % 16 || cin_a > cin) return false;
     c.nb = cout <= 64 ? cout : (cout % 64 == 0 ? 64 : (cout % 32 == 0 ? 32 : 16));
     if (c.nb != 16 && c.nb != 32 && c.nb != 64) return false;
     c.nslices = cout / c.nb;
     if (c.nslices != 1) return false;          // resident weights are loaded once per CTA
     c.b_bytes = taps * cin * 3 * c.nb * 2;
     if (c.b_bytes > 112 * 1024) return false;
-    c.a_bytes = (cin / 8) * kPlaneBytes;
+    c.a_bytes = (cin_a / 8) * kPlaneBytes;
     c.dc = c.nb == 16 ? 16 : 8;
     if (c.dc > d) c.dc = d;
     if (c.dc < 2) return false;
@@ -425,9 +427,10 @@ extern "C" int fpl_conv3d_dfold_prep_weight_batch(int count, const float* const*
 
 static int dfold_launch(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias, void* y,
                         int y_c8tot, int y_c8off, double* stats, int n, int d, int h, int w, int cin, int cout, int taps,
-                        void* stream) {
+                        int cin_a, void* stream) {
+    if (cin_a <= 0) cin_a = cin;
     DfCfg c;
-    FPL_REQUIRE(make_df_cfg(cin, cout, d, c, taps), "fpl_conv3d_tc_dfold: unsupported shape (%d -> %d, depth %d)", cin, cout, d);
+    FPL_REQUIRE(make_df_cfg(cin, cout, d, c, taps, cin_a), "fpl_conv3d_tc_dfold: unsupported shape (%d -> %d, depth %d)", cin, cout, d);
     FPL_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(image) & 15) == 0,
                 "fpl_conv3d_tc_dfold: x/image must be 16-byte aligned");
     EncodeTiledFn encode = get_encode_fn();
@@ -435,7 +438,7 @@ static int dfold_launch(const void* x, int x_c8tot, int x_c8off, const void* ima
     CUtensorMap xmap;
     cuuint64_t gdim[3] = {(cuuint64_t)w * 8, (cuuint64_t)h, (cuuint64_t)n * d * x_c8tot};
     cuuint64_t gstride[2] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16};
-    cuuint32_t box[3] = {(cuuint32_t)kBoxW * 8, (cuuint32_t)kBoxH, (cuuint32_t)(cin / 8)};
+    cuuint32_t box[3] = {(cuuint32_t)kBoxW * 8, (cuuint32_t)kBoxH, (cuuint32_t)(cin_a / 8)};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(x), gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -451,7 +454,7 @@ static int dfold_launch(const void* x, int x_c8tot, int x_c8off, const void* ima
     int64_t total = (int64_t)P.tiles_h * P.tiles_w * P.ndc * n * c.nslices;
     FPL_REQUIRE(total < (1ll << 30), "fpl_conv3d_tc_dfold: too many items");
     P.total_items = (int)total;
-    P.taps = taps;
+    P.taps = taps; P.a_ksteps = cin_a / 16;
     FPL_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_dfold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
     int grid = FPL_NUM_SMS * c.ctas_per_sm;
     if (grid > P.total_items) grid = P.total_items;
@@ -463,13 +466,14 @@ static int dfold_launch(const void* x, int x_c8tot, int x_c8off, const void* ima
 extern "C" int fpl_conv3d_tc_dfold(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias, void* y,
                                    int y_c8tot, int y_c8off, double* stats, int n, int d, int h, int w, int cin, int cout,
                                    void* stream) {
-    return dfold_launch(x, x_c8tot, x_c8off, image, bias, y, y_c8tot, y_c8off, stats, n, d, h, w, cin, cout, 9, stream);
+    return dfold_launch(x, x_c8tot, x_c8off, image, bias, y, y_c8tot, y_c8off, stats, n, d, h, w, cin, cout, 9, 0, stream);
 }
 
 /* k = (3,1,1) "same" conv (depth taps only) with the same machinery: 1 MMA (N = 3*Cout) per input plane and K step.
  * Used for the stem after fpl_patch9_c8 has turned the 9 in-plane neighbours of the 1-channel image into channels. */
 extern "C" int fpl_conv3d_tc_k311(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias, void* y,
                                   int y_c8tot, int y_c8off, double* stats, int n, int d, int h, int w, int cin, int cout,
-                                  void* stream) {
-    return dfold_launch(x, x_c8tot, x_c8off, image, bias, y, y_c8tot, y_c8off, stats, n, d, h, w, cin, cout, 1, stream);
+                                  int a_channels, void* stream) {
+    return dfold_launch(x, x_c8tot, x_c8off, image, bias, y, y_c8tot, y_c8off, stats, n, d, h, w, cin, cout, 1, a_channels,
+                        stream);
 }

@@ -31,9 +31,9 @@ _SIGNATURES = {
     "fpl_conv3d_dfold_prep_weight_batch": (_I, [_I, ctypes.POINTER(c_void_p), ctypes.POINTER(_I), ctypes.POINTER(_I),
                                                 ctypes.POINTER(_I), ctypes.POINTER(c_void_p), _P]),
     "fpl_conv3d_tc_dfold": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _P] + [_I] * 6 + [_P]),
-    "fpl_patch9_c8": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "fpl_patch9_c8": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "fpl_conv3d_k311_prep_weight": (_I, [_P, _I, _I, _P, _P]),
-    "fpl_conv3d_tc_k311": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _P] + [_I] * 6 + [_P]),
+    "fpl_conv3d_tc_k311": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _P] + [_I] * 7 + [_P]),
     "fpl_conv3d_wgrad_tc_k311": (_I, [_P, _I, _I, _P, _I, _I, _P] + [_I] * 6 + [_P]),
     "fpl_conv3d_direct": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _P] + [_I] * 9 + [_P]),
     "fpl_conv3d_wgrad": (_I, [_P, _I, _I, _P, _I, _I, _P] + [_I] * 7 + [_P]),

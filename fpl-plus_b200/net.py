@@ -174,6 +174,7 @@ class UNet2D5_dsbn(nn.Module):
         self._unit_depth = {}
         self.grad_ready_hook = None     # callable(flat_grad, start, end, last) fired as buckets complete (DDP)
         self._head = UNet2D5_dsbn._HeadConv(self.out_conv)
+        self._stem = None
         self._head_unit = None
         self._head_dirty = True
         self._build_plan()
@@ -220,6 +221,39 @@ class UNet2D5_dsbn(nn.Module):
                 self.weight[:k].copy_(w.detach())
                 self.bias[:k].copy_(self.src.bias.detach())
                 self.seen = ver
+
+    class _StemConv(object):
+        """The 1-channel stem conv k(3,3,3) as a k(3,1,1) conv over the 16 "patch" channels written by
+        fpl_patch9_c8 (channel kh*3+kw = in-plane neighbour): weight [Cout][16][3] kept in sync with the module."""
+
+        def __init__(self, conv):
+            self.src = conv
+            self.weight = None
+            self.seen = None
+            self.image = None
+
+        def sync(self, force):
+            # K blocks [w_hi | w_hi | w_lo] against the A blocks [x_hi | x_lo | x_hi] of fpl_patch9_c8(split): the
+            # stem stays fp32-accurate (x*w to ~2^-16) although every tensor-core operand is bf16
+            w = self.src.weight
+            co = w.shape[0]
+            if self.weight is None or self.weight.device != w.device:
+                self.weight = torch.zeros((co, 48, 3), dtype=torch.float32, device=w.device)
+                self.image = torch.empty(48 * 3 * co, dtype=torch.bfloat16, device=w.device)
+                force = True
+            if force or w._version != self.seen:
+                wk = w.detach()[:, 0].reshape(co, 3, 9).permute(0, 2, 1)
+                hi = wk.to(torch.bfloat16).float()
+                self.weight[:, 0:9, :].copy_(hi)
+                self.weight[:, 16:25, :].copy_(hi)
+                self.weight[:, 32:41, :].copy_(wk - hi)
+                call("fpl_conv3d_k311_prep_weight", ptr(self.weight), 48, co, ptr(self.image), stream_ptr())
+                self.seen = w._version
+
+    def _stem_tc(self, depth):
+        u = self._down_units[0][0]
+        return (u.cin == 1 and u.kd == 3 and depth >= 2 and u.cout in (16, 32, 64) and ops.is_sm100()
+                and _conv_impl() == "tc" and os.environ.get("FPL_STEM_IMPL", "tc") == "tc")
 
     def _head_tc(self):
         return self._use_tc(self.ft_chns[0], 16) and self.n_class <= 8 and os.environ.get("FPL_HEAD_IMPL", "tc") == "tc"
@@ -374,6 +408,10 @@ class UNet2D5_dsbn(nn.Module):
     def _refresh_weight_images(self, with_dgrad):
         """(Re)stage every stale weight image with ONE batched launch."""
         lib = ops._lib.load()
+        if self._stem_tc(self._unit_depth.get("block0.conv#1", 0)):
+            if self._stem is None:
+                self._stem = UNet2D5_dsbn._StemConv(self._down_units[0][0].conv)
+            self._stem.sync(self._head_dirty)
         todo, todo_df, todo_ct = [], [], []
         for u in self._tc_convs():
             w = u.conv.weight
@@ -493,7 +531,12 @@ class UNet2D5_dsbn(nn.Module):
     def _conv_fwd(self, u, xin, x_img, y, stats, n, geo, ws):
         d, h, w = geo
         st = stream_ptr()
-        if u.is_stem:
+        if u.is_stem and self._stem_tc(d):
+            xs = ws.c8("XS:stem", n, d, 32, h, w)
+            call("fpl_patch9_c8", ptr(x_img), ptr(xs), 1, n, d, h, w, st)
+            call("fpl_conv3d_tc_k311", ptr(xs), 4, 0, ptr(self._stem.image), ptr(u.conv.bias), ptr(y), y.shape[2], 0,
+                 ptr(stats), n, d, h, w, 48, u.cout, 32, st)
+        elif u.is_stem:
             call("fpl_stem_conv_fwd", ptr(x_img), ptr(u.conv.weight), ptr(u.conv.bias), ptr(y), y.shape[2], 0,
                  ptr(stats), n, u.cin, d, h, w, u.cout, u.kd, st)
         elif self._dfold_ok(u.cin, u.cout, u.kd, d):
@@ -625,6 +668,14 @@ class UNet2D5_dsbn(nn.Module):
         call("fpl_dsbn_act_bwd_apply_fin", *common, ptr(red), r["training"], ptr(dy), n, d, h, w, c, st,
              ptr(grads[bn.weight]), ptr(grads[bn.bias]), ptr(grads[u.prelu.weight]), ptr(grads[u.conv.bias]))
         dw = grads[u.conv.weight]
+        if u.is_stem and self._stem_tc(d):
+            # the patch tensor of the forward is still in the workspace: k(3,1,1) wgrad, one MMA per K step
+            xs = ws.c8("XS:stem", n, d, 32, h, w)
+            dw16 = ws.get("dW16s", (c, 16, 3), torch.float32)
+            dw16.zero_()
+            call("fpl_conv3d_wgrad_tc_k311", ptr(xs), 4, 0, ptr(dy), c // 8, 0, ptr(dw16), n, d, h, w, 16, c, st)   # hi half
+            dw.view(c, 1, 3, 3, 3).add_(dw16[:, :9, :].permute(0, 2, 1).reshape(c, 1, 3, 3, 3))
+            return None
         if u.is_stem:
             if self._use_tc(16, c) and u.cin <= 8 and os.environ.get("FPL_WGRAD_IMPL", "tc") == "tc":
                 # image -> one bf16 channel group (zero padded), then the tensor-core wgrad with Cin = 8

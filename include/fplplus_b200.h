@@ -73,11 +73,14 @@ int fpl_conv3d_tc_dfold(const void* x, int x_c8tot, int x_c8off, const void* ima
 /* k = (3,1,1) conv (depth taps only) and its wgrad on the same kernels with ONE in-plane tap; w / dW are fp32
  * [Cout][Cin][3].  With fpl_patch9_c8 (1-channel fp32 image -> 16 bf16 channels holding the 9 in-plane neighbours)
  * they run the stem conv k(3,3,3), in_chns = 1 (unet2d5_dsbn.py:75, first conv3d_1) on the tensor cores. */
-int fpl_patch9_c8(const float* x, void* out16, int n, int d, int h, int w, void* stream);
+/* split_hi_lo != 0: 32 channels, the second 16 hold the bf16 rounding residual x - bf16(x) (hi + lo = 16 mantissa
+ * bits); fpl_conv3d_tc_k311 with cin = 48 weights [w_hi | w_hi | w_lo] and a_channels = 32 (the third K block reads
+ * the hi channels again) then evaluates x*w to ~2^-16 although every operand is bf16. */
+int fpl_patch9_c8(const float* x, void* out, int split_hi_lo, int n, int d, int h, int w, void* stream);
 int fpl_conv3d_k311_prep_weight(const float* w, int cin, int cout, void* image, void* stream);
 int fpl_conv3d_tc_k311(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias,
                        void* y, int y_c8tot, int y_c8off, double* stats,
-                       int n, int d, int h, int w, int cin, int cout, void* stream);
+                       int n, int d, int h, int w, int cin, int cout, int a_channels, void* stream);
 int fpl_conv3d_wgrad_tc_k311(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
                              float* dw, int n, int d, int h, int w, int cin, int cout, void* stream);
 /* CUDA-core conv with the same contract (used for shapes the tensor kernel does

@@ -133,7 +133,7 @@ def conv_block(state, prefix, x, domain, dim, p_drop, bn_training, drop_training
     for k in (1, 2):
         w, b = state[f"{prefix}.{cn}_{k}.weight"], state[f"{prefix}.{cn}_{k}.bias"]
         if bf16:
-            # the stem (image input, in_chns < 8) runs on CUDA cores with fp32 weights and an fp32 image
+            # the stem is evaluated from hi/lo bf16 pairs of the image and of its weights: fp32-accurate
             first = stem and k == 1
             x = conv(x if first else _RoundBwd.apply(x), w if first else _wq(w), b, padding=1)
         else:

@@ -612,3 +612,53 @@ def test_conv3d_depth_folded_tensor_core_kernel(cin, cout, shape, transpose):
     out2 = from_c8(y2).cpu()
     assert max_rel(out, out2) < 5e-3 and float((out != out2).float().mean()) < 0.05
     assert L.load().fpl_conv3d_dfold_image_bytes(128, 128) == -1         # large layers stay on fpl_conv3d_tc
+
+
+@pytest.mark.parametrize("cout,shape", [(16, (2, 5, 20, 12)), (32, (1, 16, 16, 24))])
+def test_stem_on_tensor_cores_patch9_k311(cout, shape):
+    """Stem conv k(3,3,3), in_chns = 1: fpl_patch9_c8 turns the 9 in-plane neighbours into channels, then the conv and
+    its wgrad are k(3,1,1) tensor-core kernels with ONE in-plane tap.  Against torch on the bf16-rounded image."""
+    n, d, h, w = shape
+    x = bf16_round(randn(201, n, 1, d, h, w))
+    wt = bf16_round(randn(202, cout, 1, 3, 3, 3, scale=0.2)).requires_grad_(True)
+    b = randn(203, cout, scale=0.1)
+    ref = F.conv3d(x, wt, b, padding=1)
+    g = bf16_round(randn(204, *ref.shape))
+    ref.backward(g)
+    xs = torch.empty((n, d, 2, h, w, 8), dtype=torch.bfloat16, device=DEV)
+    _call("fpl_patch9_c8", _p(x.to(DEV)), _p(xs), 0, n, d, h, w, _st())
+    patch = from_c8(xs).cpu()
+    assert torch.equal(patch[:, 4], x[:, 0]) and torch.all(patch[:, 9:] == 0)       # centre tap = the image itself
+    assert torch.equal(patch[:, 0, :, 1:, 1:], x[:, 0, :, :-1, :-1]) and torch.all(patch[:, 0, :, 0, :] == 0)
+    w16 = torch.zeros(cout, 16, 3)
+    w16[:, :9, :] = wt.detach()[:, 0].reshape(cout, 3, 9).permute(0, 2, 1)
+    img = torch.empty(16 * 3 * cout, dtype=torch.bfloat16, device=DEV)
+    _call("fpl_conv3d_k311_prep_weight", _p(w16.to(DEV)), 16, cout, _p(img), _st())
+    y = torch.zeros((n, d, cout // 8, h, w, 8), dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
+    _call("fpl_conv3d_tc_k311", _p(xs), 2, 0, _p(img), _p(b.to(DEV)), _p(y), cout // 8, 0, _p(stats), n, d, h, w, 16, cout, 0, _st())
+    rd = ref.detach()
+    assert max_rel(from_c8(y).cpu(), rd) < 6e-3
+    np.testing.assert_allclose(stats.cpu()[:cout], rd.double().sum((0, 2, 3, 4)), rtol=1e-4, atol=2e-3)
+    dw16 = torch.zeros(cout, 16, 3, device=DEV)
+    _call("fpl_conv3d_wgrad_tc_k311", _p(xs), 2, 0, _p(to_c8(g.to(DEV))), cout // 8, 0, _p(dw16), n, d, h, w, 16, cout, _st())
+    dw = dw16.cpu()[:, :9, :].permute(0, 2, 1).reshape(cout, 1, 3, 3, 3)
+    assert max_rel(dw, wt.grad) < 1e-4
+    assert float(dw16.cpu()[:, 9:, :].abs().max()) == 0.0
+    # hi/lo split: an fp32 image and fp32 weights through bf16 operands, [x_hi | x_lo | x_hi] x [w_hi | w_hi | w_lo]
+    xf = randn(205, n, 1, d, h, w)
+    wf = randn(206, cout, 1, 3, 3, 3, scale=0.2)
+    ref32 = F.conv3d(xf, wf, b, padding=1)
+    xs4 = torch.empty((n, d, 4, h, w, 8), dtype=torch.bfloat16, device=DEV)
+    _call("fpl_patch9_c8", _p(xf.to(DEV)), _p(xs4), 1, n, d, h, w, _st())
+    wk = wf[:, 0].reshape(cout, 3, 9).permute(0, 2, 1)
+    hi = bf16_round(wk)
+    w48 = torch.zeros(cout, 48, 3)
+    w48[:, 0:9], w48[:, 16:25], w48[:, 32:41] = hi, hi, wk - hi
+    img48 = torch.empty(48 * 3 * cout, dtype=torch.bfloat16, device=DEV)
+    _call("fpl_conv3d_k311_prep_weight", _p(w48.to(DEV)), 48, cout, _p(img48), _st())
+    stats.zero_()
+    _call("fpl_conv3d_tc_k311", _p(xs4), 4, 0, _p(img48), _p(b.to(DEV)), _p(y), cout // 8, 0, _p(stats), n, d, h, w, 48, cout, 32, _st())
+    np.testing.assert_allclose(stats.cpu()[:cout], ref32.double().sum((0, 2, 3, 4)), rtol=2e-5, atol=2e-3)   # fp32-accurate sums
+    np.testing.assert_allclose(stats.cpu()[cout:], (ref32.double() ** 2).sum((0, 2, 3, 4)), rtol=2e-5, atol=2e-3)
+    assert max_rel(from_c8(y).cpu(), ref32) < 4e-3                                   # only the bf16 output rounding is left
