@@ -19,6 +19,9 @@
 
 namespace {
 
+// debug / tuning knobs (fpl_debug_set keys 10..16)
+int g_wg_swap = 0, g_wg_allow_m64 = 1, g_wg_m64_quadrant = 1, g_wg_allow_pair = 1, g_wg_force_tw = 0, g_wg_tiles_per_cta = 4, g_wg_skip_epilogue = 0;
+
 constexpr int kThreadsW = 192;
 constexpr int kMaxStagesW = 8;
 constexpr int kSmemBudgetW = 220 * 1024;
@@ -58,6 +61,7 @@ bool make_wg_cfg(int h, int w, int cin, int cout, int kd, int allow_m64, int all
     c.ncols = c.pair ? 2 * c.nb : c.nb;
     c.nchunks = cout / c.nb;
     if (groups > 8 && c.tw == 32 && cin >= 32 && h * w >= 128 * 128) c.tw = 16;   // keep >= 3 stages at full resolution
+    if (g_wg_force_tw > 0 && g_wg_force_tw <= w) c.tw = g_wg_force_tw;
     c.plane_x = (c.th + 2) * (c.tw + 2) * 16;
     c.plane_dy = c.th * c.tw * 16;
     c.x_bytes = groups * c.plane_x;
@@ -88,6 +92,8 @@ struct WgParams {
     int swap_lbo_sbo, m64_quadrant_layout;
     int pair, ncols, dplanes;      // dplanes: tile index range along depth (D, or ceil(D/2) in pair mode)
     int taps;                      // 9, or 1 = only the centre in-plane tap (k = (kd,1,1))
+    int skip_epilogue;             // timing experiments only
+    int tapmajor;                  // dW written as [tap][cout][cin] (coalesced atomics; see fpl_wgrad_tapmajor_to_dw_batch)
 };
 
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
@@ -241,11 +247,18 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
                 // depth tap kd = kdi - dd (the two (kdi, dd) blocks of one tap are summed by the atomics)
                 const int dd = P.pair ? c0 / P.nb : 0;
                 const int kd_tap = P.pair ? kdi - dd : kdi;
-                if (valid && kd_tap >= 0 && kd_tap < P.kd) {
+                if (valid && kd_tap >= 0 && kd_tap < P.kd && !P.skip_epilogue) {
+                    if (P.tapmajor) {
+                        // lanes = consecutive input channels: one 128-byte line per warp instruction
+                        float* base = P.dw + ((int64_t)(kd_tap * P.taps + t9) * P.cout + wk.nc * P.nb + (c0 - dd * P.nb)) * P.cin + ci;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int co = wk.nc * P.nb + (c0 - dd * P.nb) + i;
-                        atomicAdd(P.dw + ((int64_t)co * P.cin + ci) * T + kd_tap * P.taps + t9, __uint_as_float(r[i]));
+                        for (int i = 0; i < 16; ++i) atomicAdd(base + (int64_t)i * P.cin, __uint_as_float(r[i]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int co = wk.nc * P.nb + (c0 - dd * P.nb) + i;
+                            atomicAdd(P.dw + ((int64_t)co * P.cin + ci) * T + kd_tap * P.taps + t9, __uint_as_float(r[i]));
+                        }
                     }
                 }
             }
@@ -259,7 +272,6 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
     }
 }
 
-int g_wg_swap = 0, g_wg_allow_m64 = 1, g_wg_m64_quadrant = 1, g_wg_allow_pair = 1;
 float* g_wg_dump = nullptr;
 
 CUresult encode_5d(EncodeTiledFn encode, CUtensorMap* map, const void* base, int n, int d, int c8tot, int h, int w,
@@ -284,10 +296,14 @@ void fpl_wgrad_debug_set(int key, long long value) {
     if (key == 12) g_wg_m64_quadrant = (int)value;
     if (key == 13) g_wg_dump = reinterpret_cast<float*>(value);
     if (key == 14) g_wg_allow_pair = (int)value;
+    if (key == 15) g_wg_force_tw = (int)value;
+    if (key == 16) g_wg_tiles_per_cta = (int)value;
+    if (key == 17) g_wg_skip_epilogue = (int)value;
 }
 
 static int wgrad_tc_launch(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
-                           float* dw, int n, int d, int h, int w, int cin, int cout, int kd, int taps, void* stream) {
+                           float* dw, int n, int d, int h, int w, int cin, int cout, int kd, int taps, void* stream,
+                           int tapmajor = 0) {
     FPL_REQUIRE(kd == 1 || kd == 3, "fpl_conv3d_wgrad_tc: kd=%d must be 1 or 3", kd);
     WgCfg c;
     FPL_REQUIRE(make_wg_cfg(h, w, cin, cout, kd, g_wg_allow_m64, g_wg_allow_pair && d >= 2, c),
@@ -317,11 +333,11 @@ static int wgrad_tc_launch(const void* x, int x_c8tot, int x_c8off, const void* 
     // split-K over voxel tiles: every CTA ends with 9*128*N atomics into dW, so a slice should own >= 8 tiles
     // (deep levels: few tiles, many (M,N) pairs -> split 1; full resolution: one CTA per SM)
     int split = FPL_NUM_SMS / pairs;
-    if (split > P.tiles_total / 8) split = P.tiles_total / 8;
+    if (split > P.tiles_total / g_wg_tiles_per_cta) split = P.tiles_total / g_wg_tiles_per_cta;
     if (split < 1) split = 1;
     P.split = split;
     P.swap_lbo_sbo = g_wg_swap; P.m64_quadrant_layout = g_wg_m64_quadrant;
-    P.taps = taps;
+    P.taps = taps; P.skip_epilogue = g_wg_skip_epilogue; P.tapmajor = tapmajor;
     FPL_CHECK_CUDA(cudaFuncSetAttribute(conv3d_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
     conv3d_wgrad_tc_kernel<<<pairs * split, kThreadsW, c.smem_bytes, (cudaStream_t)stream>>>(xmap, dymap, P);
     FPL_LAUNCH_CHECK();
@@ -337,4 +353,53 @@ extern "C" int fpl_conv3d_wgrad_tc(const void* x, int x_c8tot, int x_c8off, cons
 extern "C" int fpl_conv3d_wgrad_tc_k311(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
                                         float* dw, int n, int d, int h, int w, int cin, int cout, void* stream) {
     return wgrad_tc_launch(x, x_c8tot, x_c8off, dy, dy_c8tot, dy_c8off, dw, n, d, h, w, cin, cout, 3, 1, stream);
+}
+
+/* fpl_conv3d_wgrad_tc writing a TAP-MAJOR scratch gradient  S[kd*9 + t9][cout][cin]  (fp32, ACCUMULATED into): the
+ * epilogue's atomics then hit consecutive addresses across a warp (input channels are the TMEM lanes).  The scratch
+ * of all layers is folded into the PyTorch layout by ONE fpl_wgrad_tapmajor_to_dw_batch launch. */
+extern "C" int fpl_conv3d_wgrad_tc_tapmajor(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
+                                            float* scratch, int n, int d, int h, int w, int cin, int cout, int kd,
+                                            void* stream) {
+    return wgrad_tc_launch(x, x_c8tot, x_c8off, dy, dy_c8tot, dy_c8off, scratch, n, d, h, w, cin, cout, kd, 9, stream, 1);
+}
+
+namespace {
+constexpr int kMaxFold = 64;
+struct FoldBatch {
+    const float* s[kMaxFold];
+    float* dw[kMaxFold];
+    int cout[kMaxFold], cin[kMaxFold], taps[kMaxFold];
+};
+// dW[co][ci][tap] += S[tap][co][ci]   (blockIdx.y = layer)
+__global__ void __launch_bounds__(256) fold_tapmajor_kernel(const __grid_constant__ FoldBatch B) {
+    const int e = blockIdx.y;
+    const float* __restrict__ s = B.s[e];
+    float* dw = B.dw[e];
+    const int cout = B.cout[e], cin = B.cin[e], T = B.taps[e];
+    const int total = cout * cin * T;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int tap = i % T;
+        const int rest = i / T;                 // co * cin + ci
+        dw[i] += __ldg(s + (int64_t)tap * cout * cin + rest);
+    }
+}
+}  // namespace
+
+extern "C" int fpl_wgrad_tapmajor_to_dw_batch(int count, const float* const* h_scratch, float* const* h_dw, const int* h_cout,
+                                              const int* h_cin, const int* h_taps, void* stream) {
+    FPL_REQUIRE(count >= 0 && count <= kMaxFold, "fpl_wgrad_tapmajor_to_dw_batch: count %d not in [0,%d]", count, kMaxFold);
+    if (count == 0) return 0;
+    FoldBatch B;
+    int max_total = 0;
+    for (int e = 0; e < count; ++e) {
+        B.s[e] = h_scratch[e]; B.dw[e] = h_dw[e]; B.cout[e] = h_cout[e]; B.cin[e] = h_cin[e]; B.taps[e] = h_taps[e];
+        const int total = h_cout[e] * h_cin[e] * h_taps[e];
+        if (total > max_total) max_total = total;
+    }
+    int bx = (max_total + 1023) / 1024;
+    if (bx > 128) bx = 128;
+    fold_tapmajor_kernel<<<dim3(bx, count), 256, 0, (cudaStream_t)stream>>>(B);
+    FPL_LAUNCH_CHECK();
+    return 0;
 }

@@ -652,7 +652,7 @@ class UNet2D5_dsbn(nn.Module):
         return logits, rec
 
     # -- whole-network backward -------------------------------------------------------------
-    def _unit_bwd(self, u, r, g1, g_pool, pool_idx, pool_kd, n, ws, small, grads, need_dx):
+    def _unit_bwd(self, u, r, g1, g_pool, pool_idx, pool_kd, n, ws, small, grads, need_dx, fold=None):
         """Backward of one conv unit.  Returns the C8 gradient wrt the unit's input (or None)."""
         d, h, w = r["geo"]
         c = u.cout
@@ -698,9 +698,9 @@ class UNet2D5_dsbn(nn.Module):
             ready.record(cur)
             aux.wait_event(ready)
             with torch.cuda.stream(aux):
-                self._wgrad(u, xin, dy, dw, n, d, h, w)
+                self._wgrad(u, xin, dy, dw, n, d, h, w, fold)
         else:
-            self._wgrad(u, xin, dy, dw, n, d, h, w)
+            self._wgrad(u, xin, dy, dw, n, d, h, w, fold)
         if not need_dx:
             return None
         dx = ws.c8("dX:" + u.name, n, d, u.cin, h, w)
@@ -732,9 +732,16 @@ class UNet2D5_dsbn(nn.Module):
         if aux is not None:
             torch.cuda.current_stream().wait_stream(aux)
 
-    def _wgrad(self, u, xin, dy, dw, n, d, h, w):
+    def _wgrad(self, u, xin, dy, dw, n, d, h, w, fold=None):
         impl = os.environ.get("FPL_WGRAD_IMPL", "tc")
         if impl == "tc" and u.cin % 8 == 0 and u.cout % 16 == 0 and ops.is_sm100():
+            if fold is not None:
+                # tap-major scratch (coalesced epilogue atomics); folded into dw by one batched launch later
+                scr = fold["alloc"](u.cout * u.cin * u.kd * 9)
+                call("fpl_conv3d_wgrad_tc_tapmajor", *xin.args(), ptr(dy), u.cout // 8, 0, ptr(scr), n, d, h, w, u.cin,
+                     u.cout, u.kd, stream_ptr())
+                fold["pending"].append((scr, dw, u.cout, u.cin, u.kd * 9))
+                return
             call("fpl_conv3d_wgrad_tc", *xin.args(), ptr(dy), u.cout // 8, 0, ptr(dw), n, d, h, w, u.cin, u.cout,
                  u.kd, stream_ptr())
         else:
@@ -752,12 +759,40 @@ class UNet2D5_dsbn(nn.Module):
             offs.append(o)
             o += s
         fired = [0]
+        # tap-major scratch of the conv weight gradients (one flat zeroed buffer per backward) + the list of layers
+        # whose scratch still has to be folded into the PyTorch layout
+        fold = None
+        if os.environ.get("FPL_WGRAD_TAPMAJOR", "1") != "0" and ops.is_sm100():
+            total = sum((u.conv.weight.numel() + 3) // 4 * 4 for pair in self._down_units + self._up_units for u in pair
+                        if not u.is_stem)
+            scratch = ws.get("wgrad_scratch", (total,), torch.float32)
+            scratch.zero_()
+            cursor = [0]
+
+            def alloc(numel):
+                t = scratch[cursor[0]:cursor[0] + numel]
+                cursor[0] += (numel + 3) // 4 * 4
+                return t
+            fold = {"alloc": alloc, "pending": []}
+
+        def flush_fold():
+            if fold is None or not fold["pending"]:
+                return
+            self._join_aux()
+            part = fold["pending"]
+            m = len(part)
+            arr_s = (ctypes.c_void_p * m)(*[t[0].data_ptr() for t in part])
+            arr_d = (ctypes.c_void_p * m)(*[t[1].data_ptr() for t in part])
+            ints = [(ctypes.c_int * m)(*[t[k] for t in part]) for k in (2, 3, 4)]
+            call("fpl_wgrad_tapmajor_to_dw_batch", m, arr_s, arr_d, ints[0], ints[1], ints[2], stream_ptr())
+            fold["pending"] = []
 
         def fire(n_params_done):
             # gradients of params[:n_params_done] are final: hand the new flat range to the hook (DDP all-reduce)
             if self.grad_ready_hook is not None:
                 end = offs[n_params_done - 1] + sizes[n_params_done - 1]
                 if end > fired[0]:
+                    flush_fold()
                     self._join_aux()
                     self.grad_ready_hook(flat, fired[0], end, n_params_done == len(params))
                     fired[0] = end
@@ -791,10 +826,10 @@ class UNet2D5_dsbn(nn.Module):
             u1, u2 = self._up_units[k]
             up = ups[k]
             c, c_low = ft[lvl], ft[lvl + 1]
-            g = self._unit_bwd(u2, rec[u2.name], g, None, None, 0, n, ws, small, grads, True)
+            g = self._unit_bwd(u2, rec[u2.name], g, None, None, 0, n, ws, small, grads, True, fold)
             # dgrad of unit 1 produces the gradient of the whole concat buffer; keep it alive per level
             r1 = rec[u1.name]
-            dcat = self._unit_bwd(u1, r1, g, None, None, 0, n, ws, small, grads, True)
+            dcat = self._unit_bwd(u1, r1, g, None, None, 0, n, ws, small, grads, True, fold)
             skip_grads[lvl] = C8(dcat.buf, 0, c)
             trans = up.trans3d if up.dim == 3 else up.trans2d
             kd2 = 2 if up.dim == 3 else 1
@@ -818,19 +853,20 @@ class UNet2D5_dsbn(nn.Module):
         for i in (4, 3, 2, 1, 0):
             u1, u2 = self._down_units[i]
             if i == 4:
-                g = self._unit_bwd(u2, rec[u2.name], g, None, None, 0, n, ws, small, grads, True)
+                g = self._unit_bwd(u2, rec[u2.name], g, None, None, 0, n, ws, small, grads, True, fold)
             else:
                 idx, pool_kd = rec["idx%d" % i]
-                g = self._unit_bwd(u2, rec[u2.name], skip_grads[i], g_pool, idx, pool_kd, n, ws, small, grads, True)
+                g = self._unit_bwd(u2, rec[u2.name], skip_grads[i], g_pool, idx, pool_kd, n, ws, small, grads, True, fold)
             r1 = rec[u1.name]
             r1["x_img"] = rec["x"]
             if i > 0:
-                g_pool = self._unit_bwd(u1, r1, g, None, None, 0, n, ws, small, grads, True)
+                g_pool = self._unit_bwd(u1, r1, g, None, None, 0, n, ws, small, grads, True, fold)
             else:
-                self._unit_bwd(u1, r1, g, None, None, 0, n, ws, small, grads, False)
+                self._unit_bwd(u1, r1, g, None, None, 0, n, ws, small, grads, False, fold)
             done += 10
             fire(done)
         assert done == len(params)
+        flush_fold()
         self._join_aux()
         return [grads[p].view(p.shape) for p in params]
 

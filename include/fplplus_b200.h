@@ -100,6 +100,14 @@ int fpl_conv3d_wgrad(const void* x, int x_c8tot, int x_c8off, const void* dy, in
 int fpl_conv3d_wgrad_tc(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
                         float* dw, int n, int d, int h, int w, int cin, int cout, int kd, void* stream);
 
+/* Tap-major variant: scratch S[kd*9+t9][cout][cin] (fp32, ACCUMULATED into) so that the epilogue's atomics are
+ * coalesced; fpl_wgrad_tapmajor_to_dw_batch then folds the scratch of up to 64 layers into the PyTorch layout
+ * (dW[co][ci][tap] += S[tap][co][ci]) in one launch; all arrays are HOST arrays of length count. */
+int fpl_conv3d_wgrad_tc_tapmajor(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
+                                 float* scratch, int n, int d, int h, int w, int cin, int cout, int kd, void* stream);
+int fpl_wgrad_tapmajor_to_dw_batch(int count, const float* const* h_scratch, float* const* h_dw, const int* h_cout,
+                                   const int* h_cin, const int* h_taps, void* stream);
+
 /* stem: image fp32 NCDHW (in_chns <= 8) -> C8-planar bf16, conv k3 p1 + bias + stats. */
 int fpl_stem_conv_fwd(const float* x, const float* w, const float* bias, void* y, int y_c8tot, int y_c8off,
                       double* stats, int n, int cin, int d, int h, int w_, int cout, int kd, void* stream);
