@@ -6,6 +6,11 @@
 #include "common.cuh"
 #include "../../include/fplplus_b200.h"
 
+#ifndef FPL_BWD_V
+#define FPL_BWD_V 2
+#define FPL_BWD_BLOCKS 4
+#endif
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -274,77 +279,101 @@ struct ActBwdParams {
     int training;
     double inv_count;
     int N, D, C8, H, W;
+    int w_shift;                // log2(W) when W is a power of two, else -1
 };
 
-// grid: (chunks of H*W, N*D*C8 planes) so a block stays inside one channel group.  Two vectors per
-// thread are in flight (all loads issued before any arithmetic); xhat = y*k1 + k0.
-template <bool APPLY>
-__global__ void __launch_bounds__(kThreads) dsbn_act_bwd_kernel(ActBwdParams P) {
+// grid: (blocks per channel group, C8).  A block stays inside one channel group (its per-channel constants live in
+// registers) and walks over work items = (plane (n,d), chunk of kBwdV*256 vectors of that plane), kBwdV vectors per thread
+// in flight.  The reduce pass ends with ONE block reduction + 17 double atomics per block (a few hundred blocks per
+// launch, not one per 1024 vectors: same-address atomics would otherwise serialise at L2).
+//   reduce: accumulates sum dz, sum dz*y (raw conv output; turned into sum dz*xhat per block in double) and dslope
+//   apply : dy = sc*(dz - m1 - xhat*m2)  rewritten as  sc*dz + cb + cy*y  (cb, cy per channel)
+// __launch_bounds__(256, 4): <= 64 registers, 1024 threads per SM keep >= 64 KB of loads in flight.
+constexpr int kBwdV = FPL_BWD_V;          // vectors per thread per work item
+constexpr int kBwdBlocks = FPL_BWD_BLOCKS; // resident blocks per SM the register budget is tuned for
+template <bool APPLY, bool POOL, bool DROP>
+__global__ void __launch_bounds__(kThreads, kBwdBlocks) dsbn_act_bwd_kernel(const __grid_constant__ ActBwdParams P) {
     const int HW = P.H * P.W;
-    const int plane = blockIdx.y;
-    const int c8 = plane % P.C8;
-    const int nd = plane / P.C8;
+    const int c8 = blockIdx.y;
+    const int C = P.C8 * 8;
     const float slope = __ldg(P.slope);
-    const bool drop = P.drop_p > 0.0f;
-    const float keep_scale = drop ? 1.0f / (1.0f - P.drop_p) : 1.0f;
-    const uint64_t seed = P.seed + (P.seed_dev != nullptr ? (uint64_t)__ldg(P.seed_dev) : 0ull);
-    float sc[8], sh[8], k1[8], k0[8];
+    const float keep_scale = DROP ? 1.0f / (1.0f - P.drop_p) : 1.0f;
+    uint64_t seed = 0;
+    if (DROP) seed = P.seed + (P.seed_dev != nullptr ? (uint64_t)__ldg(P.seed_dev) : 0ull);
+    float sc[8], sh[8];
     load_affine(P.scale, P.shift, c8, sc, sh);
-    load_affine(P.mean, P.invstd, c8, k0, k1);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) k0[i] = -k0[i] * k1[i];
-    float s1[8], s2[8], dsl = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { s1[i] = 0.0f; s2[i] = 0.0f; }
-    if (APPLY && blockIdx.x == 0 && nd == 0 && threadIdx.x < 8) {
-        // one block per channel group publishes the parameter gradients (what fpl_dsbn_bwd_finalize does)
-        const int c = c8 * 8 + threadIdx.x, C = P.C8 * 8;
-        if (P.fin_dbeta != nullptr) P.fin_dbeta[c] += (float)P.red[c];
-        if (P.fin_dgamma != nullptr) P.fin_dgamma[c] += (float)P.red[C + c];
-        if (P.fin_dbias != nullptr && !P.training) P.fin_dbias[c] += __ldg(P.scale + c) * (float)P.red[c];
-        if (c == 0 && P.fin_dslope != nullptr) P.fin_dslope[0] += (float)P.red[2 * C];
-    }
-    if (APPLY && P.training) {
-        // fold the batch means into the apply constants: dy = sc*(dz - m1 - xhat*m2)
+    float ka[8], kb[8];          // reduce: s1, s2 accumulators; apply: cb, cy
+    float dsl = 0.0f;
+    if (APPLY) {
+        if (blockIdx.x == 0 && threadIdx.x < 8) {
+            // one block per channel group publishes the parameter gradients (what fpl_dsbn_bwd_finalize does)
+            const int c = c8 * 8 + threadIdx.x;
+            if (P.fin_dbeta != nullptr) P.fin_dbeta[c] += (float)P.red[c];
+            if (P.fin_dgamma != nullptr) P.fin_dgamma[c] += (float)P.red[C + c];
+            if (P.fin_dbias != nullptr && !P.training) P.fin_dbias[c] += __ldg(P.scale + c) * (float)P.red[c];
+            if (c == 0 && P.fin_dslope != nullptr) P.fin_dslope[0] += (float)P.red[2 * C];
+        }
+        float mean[8], invstd[8];
+        load_affine(P.mean, P.invstd, c8, mean, invstd);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            s1[i] = (float)(P.red[c8 * 8 + i] * P.inv_count);                 // m1
-            s2[i] = (float)(P.red[P.C8 * 8 + c8 * 8 + i] * P.inv_count);      // m2
+            if (P.training) {
+                const float m1 = (float)(P.red[c8 * 8 + i] * P.inv_count);
+                const float m2 = (float)(P.red[C + c8 * 8 + i] * P.inv_count);
+                ka[i] = -sc[i] * (m1 - m2 * mean[i] * invstd[i]);
+                kb[i] = -sc[i] * m2 * invstd[i];
+            } else {
+                ka[i] = 0.0f; kb[i] = 0.0f;
+            }
         }
-    }
-    const bf16x8* yp = P.y + (int64_t)plane * HW;
-    const bf16x8* g1p = P.g1 != nullptr ? P.g1 + ((int64_t)nd * P.g1_c8tot + P.g1_c8off + c8) * HW : nullptr;
-    // pooled-path pointers (2x2 in-plane window; kd = 1 or 2 planes per pooled plane)
-    const int W2 = P.W >> 1, HW2 = (P.H >> 1) * W2;
-    const bf16x8* gpp = nullptr;
-    const uint2* idxp = nullptr;
-    uint32_t code_d = 0;
-    if (P.g_pool != nullptr) {
-        const int kd = P.pool_kd, D2 = P.D / kd;
-        const int n = nd / P.D, d = nd - n * P.D, d2 = d / kd;
-        const int64_t pnd = (int64_t)n * D2 + d2;
-        gpp = P.g_pool + (pnd * P.gp_c8tot + P.gp_c8off + c8) * HW2;
-        idxp = P.pool_idx + (pnd * P.C8 + c8) * HW2;
-        code_d = (uint32_t)(d - d2 * kd) * 4u;
-    }
-    bf16x8* dyp = APPLY ? P.dy + (int64_t)plane * HW : nullptr;
-    const int stride = gridDim.x * blockDim.x;
-    for (int hw0 = blockIdx.x * blockDim.x + threadIdx.x; hw0 < HW; hw0 += 2 * stride) {
-        int hwk[2] = {hw0, hw0 + stride};
-        const bool act[2] = {true, hwk[1] < HW};
-        int4 ry[2], rg[2], rp[2];
-        uint2 rc[2];
-        uint32_t mycode[2];
+    } else {
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int i = 0; i < 8; ++i) { ka[i] = 0.0f; kb[i] = 0.0f; }
+    }
+    const int chunks = (HW + kBwdV * kThreads - 1) / (kBwdV * kThreads);
+    const int items = P.N * P.D * chunks;
+    const int W2 = P.W >> 1, HW2 = (P.H >> 1) * W2;
+    // (nd, ch) = divmod(item, chunks) and the plane base pointers are stepped, not recomputed (no division and no
+    // 64-bit multiply chains in the loop)
+    const int step_nd = gridDim.x / chunks, step_ch = gridDim.x - step_nd * chunks;
+    int nd = blockIdx.x / chunks, ch = blockIdx.x - nd * chunks;
+    const int64_t y_stride = (int64_t)P.C8 * HW, g_stride = (int64_t)P.g1_c8tot * HW;
+    const bf16x8* yp = P.y + ((int64_t)nd * P.C8 + c8) * HW + threadIdx.x;
+    const bf16x8* g1p = P.g1 != nullptr ? P.g1 + ((int64_t)nd * P.g1_c8tot + P.g1_c8off + c8) * HW + threadIdx.x : nullptr;
+    const int64_t dy_off = APPLY ? reinterpret_cast<const char*>(P.dy) - reinterpret_cast<const char*>(P.y) : 0;
+    int pn = 0, pd = 0;          // POOL: (n, d) of plane nd
+    if (POOL) { pn = nd / P.D; pd = nd - pn * P.D; }
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const bf16x8* gpp = nullptr;
+        const uint2* idxp = nullptr;
+        uint32_t code_d = 0;
+        if (POOL) {
+            const int kd = P.pool_kd;
+            const int d2 = kd == 2 ? pd >> 1 : pd;
+            const int64_t pnd = (int64_t)pn * (kd == 2 ? P.D >> 1 : P.D) + d2;
+            gpp = P.g_pool + (pnd * P.gp_c8tot + P.gp_c8off + c8) * HW2;
+            idxp = P.pool_idx + (pnd * P.C8 + c8) * HW2;
+            code_d = (uint32_t)(pd - d2 * kd) * 4u;
+        }
+        const int voff = ch * (kBwdV * kThreads);
+        int hwk[kBwdV];
+        bool act[kBwdV];
+#pragma unroll
+        for (int k = 0; k < kBwdV; ++k) { hwk[k] = voff + (int)threadIdx.x + k * kThreads; act[k] = hwk[k] < HW; }
+        int4 ry[kBwdV], rg[kBwdV], rp[kBwdV];
+        uint2 rc[kBwdV];
+        uint32_t mycode[kBwdV];
+#pragma unroll
+        for (int k = 0; k < kBwdV; ++k) {
             ry[k] = rg[k] = rp[k] = make_int4(0, 0, 0, 0);
             rc[k] = make_uint2(0, 0);
             mycode[k] = 0xffu;
             if (act[k]) {
-                ry[k] = ld_stream16(yp + hwk[k]);
-                if (g1p != nullptr) rg[k] = ld_stream16(g1p + hwk[k]);
-                if (gpp != nullptr) {
-                    const int h = hwk[k] / P.W, w = hwk[k] - h * P.W;
+                ry[k] = ld_stream16(yp + voff + k * kThreads);
+                if (g1p != nullptr) rg[k] = ld_stream16(g1p + voff + k * kThreads);
+                if (POOL) {
+                    const int h = P.w_shift >= 0 ? hwk[k] >> P.w_shift : hwk[k] / P.W;
+                    const int w = hwk[k] - h * P.W;
                     const int pix = (h >> 1) * W2 + (w >> 1);
                     mycode[k] = code_d + (uint32_t)((h & 1) * 2 + (w & 1));
                     rc[k] = __ldg(idxp + pix);
@@ -353,31 +382,54 @@ __global__ void __launch_bounds__(kThreads) dsbn_act_bwd_kernel(ActBwdParams P) 
             }
         }
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < kBwdV; ++k) {
             if (!act[k]) continue;
-            float yf[8], g[8], gp[8];
+            float yf[8], g[8];
             bf16x8_to_float(*reinterpret_cast<bf16x8*>(&ry[k]), yf);
             bf16x8_to_float(*reinterpret_cast<bf16x8*>(&rg[k]), g);
-            bf16x8_to_float(*reinterpret_cast<bf16x8*>(&rp[k]), gp);
-            const uint32_t keep = drop ? keep_bits(P.drop_mask, seed, P.offset, (int64_t)plane * HW + hwk[k], P.drop_p) : 0xffu;
+            if (POOL) {
+                // byte-wise compare of the 8 argmax codes with this voxel's code, widened to bf16 masks: the pooled
+                // gradient is masked in its packed form (2 + 4 + 4 integer ops for 8 channels)
+                const uint32_t code4 = mycode[k] * 0x01010101u;
+                const uint32_t m0 = __vcmpeq4(rc[k].x, code4), m1 = __vcmpeq4(rc[k].y, code4);
+                rp[k].x &= (int)__byte_perm(m0, 0, 0x1100); rp[k].y &= (int)__byte_perm(m0, 0, 0x3322);
+                rp[k].z &= (int)__byte_perm(m1, 0, 0x1100); rp[k].w &= (int)__byte_perm(m1, 0, 0x3322);
+                float gp[8];
+                bf16x8_to_float(*reinterpret_cast<bf16x8*>(&rp[k]), gp);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g[i] += gp[i];
+            }
+            if (DROP) {
+                const uint32_t keep = keep_bits(P.drop_mask, seed, P.offset, (yp - P.y) + (hwk[k] - (int)threadIdx.x), P.drop_p);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g[i] = ((keep >> i) & 1u) ? g[i] * keep_scale : 0.0f;
+            }
             float o[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const uint32_t cd = ((i < 4 ? rc[k].x : rc[k].y) >> (8 * (i & 3))) & 0xffu;
-                float gi = g[i] + (cd == mycode[k] ? gp[i] : 0.0f);
-                gi = ((keep >> i) & 1u) ? gi * keep_scale : 0.0f;
                 const float z = fmaf(yf[i], sc[i], sh[i]);
-                const float dz = z > 0.0f ? gi : gi * slope;
-                const float xhat = fmaf(yf[i], k1[i], k0[i]);
+                const bool pos = z > 0.0f;
+                const float dz = pos ? g[i] : g[i] * slope;
                 if (!APPLY) {
-                    dsl += z > 0.0f ? 0.0f : z * gi;
-                    s1[i] += dz;
-                    s2[i] = fmaf(dz, xhat, s2[i]);
+                    dsl = fmaf(z, pos ? 0.0f : g[i], dsl);
+                    ka[i] += dz;
+                    kb[i] = fmaf(dz, yf[i], kb[i]);
                 } else {
-                    o[i] = P.training ? sc[i] * (dz - s1[i] - xhat * s2[i]) : sc[i] * dz;
+                    o[i] = fmaf(sc[i], dz, fmaf(kb[i], yf[i], ka[i]));
                 }
             }
-            if (APPLY) st_bf16x8(dyp + hwk[k], o);
+            if (APPLY)
+                st_bf16x8(const_cast<char*>(reinterpret_cast<const char*>(yp + voff + k * kThreads)) + dy_off, o);
+        }
+        // next item
+        int dnd = step_nd;
+        ch += step_ch;
+        if (ch >= chunks) { ch -= chunks; ++dnd; }
+        yp += dnd * y_stride;
+        if (g1p != nullptr) g1p += dnd * g_stride;
+        if (POOL) {
+            pd += dnd;
+            while (pd >= P.D) { pd -= P.D; ++pn; }
         }
     }
     if (!APPLY) {
@@ -385,7 +437,7 @@ __global__ void __launch_bounds__(kThreads) dsbn_act_bwd_kernel(ActBwdParams P) 
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            float a = warp_sum(s1[i]), b = warp_sum(s2[i]);
+            float a = warp_sum(ka[i]), b = warp_sum(kb[i]);
             if (lane == 0) { sm[wid][i] = a; sm[wid][8 + i] = b; }
         }
         float c = warp_sum(dsl);
@@ -395,10 +447,20 @@ __global__ void __launch_bounds__(kThreads) dsbn_act_bwd_kernel(ActBwdParams P) 
             float t = 0.0f;
 #pragma unroll
             for (int k = 0; k < kThreads / 32; ++k) t += sm[k][threadIdx.x];
-            int i = threadIdx.x;
-            if (i < 8) atomicAdd(P.red + c8 * 8 + i, (double)t);
-            else if (i < 16) atomicAdd(P.red + P.C8 * 8 + c8 * 8 + (i - 8), (double)t);
-            else atomicAdd(P.red + 2 * P.C8 * 8, (double)t);
+            const int i = threadIdx.x;
+            if (i < 8) {
+                atomicAdd(P.red + c8 * 8 + i, (double)t);
+            } else if (i < 16) {
+                // sum dz*xhat = invstd * (sum dz*y - mean * sum dz)
+                float t1 = 0.0f;
+#pragma unroll
+                for (int k = 0; k < kThreads / 32; ++k) t1 += sm[k][i - 8];
+                const int c = c8 * 8 + (i - 8);
+                const double v = (double)__ldg(P.invstd + c) * ((double)t - (double)__ldg(P.mean + c) * (double)t1);
+                atomicAdd(P.red + C + c, v);
+            } else {
+                atomicAdd(P.red + 2 * C, (double)t);
+            }
         }
     }
 }
@@ -418,15 +480,12 @@ __global__ void dsbn_bwd_finalize_kernel(const double* __restrict__ red, const f
     if (c == 0 && dslope != nullptr) dslope[0] += (float)red[2 * C];
 }
 
-int grid_for(int64_t work_items, int per_thread) {
-    int64_t blocks = (work_items + (int64_t)kThreads * per_thread - 1) / ((int64_t)kThreads * per_thread);
-    int64_t cap = (int64_t)FPL_NUM_SMS * 16;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    return (int)blocks;
-}
-
 }  // namespace
+
+static int g_bwd_blocks_per_sm = 8;   // tuning knob (fpl_debug_set key 30)
+void fpl_dsbn_debug_set(int key, long long value) {
+    if (key == 30 && value > 0) g_bwd_blocks_per_sm = (int)value;
+}
 
 extern "C" int fpl_dsbn_finalize(const double* stats, int64_t count, const float* gamma, const float* beta,
                                  float* running_mean, float* running_var, int64_t* num_batches_tracked,
@@ -528,14 +587,30 @@ static int fill_bwd(ActBwdParams& P, const void* y, const void* g1, int g1_c8tot
     P.red = nullptr; P.dy = nullptr; P.training = 1;
     P.fin_dgamma = P.fin_dbeta = P.fin_dslope = P.fin_dbias = nullptr; P.inv_count = 1.0 / ((double)n * d * h * w);
     P.N = n; P.D = d; P.C8 = c / 8; P.H = h; P.W = w;
+    P.w_shift = -1;
+    for (int s = 0; s < 16; ++s) if ((1 << s) == w) P.w_shift = s;
     return 0;
 }
 
+// blocks per channel group: enough blocks for ~8 per SM over the whole grid, at most one per work item
 static dim3 bwd_grid(int n, int d, int h, int w, int c) {
-    int64_t hw = (int64_t)h * w;
-    int chunks = (int)((hw + kThreads * 4 - 1) / (kThreads * 4));
-    if (chunks < 1) chunks = 1;
-    return dim3(chunks, n * d * (c / 8));
+    const int64_t hw = (int64_t)h * w;
+    const int64_t chunks = (hw + kBwdV * kThreads - 1) / (kBwdV * kThreads);
+    const int64_t items = (int64_t)n * d * chunks;
+    const int c8 = c / 8;
+    int64_t bx = (FPL_NUM_SMS * g_bwd_blocks_per_sm + c8 - 1) / c8;
+    if (bx > items) bx = items;
+    if (bx < 1) bx = 1;
+    return dim3((unsigned)bx, (unsigned)c8);
+}
+
+template <bool APPLY>
+static void bwd_dispatch(const ActBwdParams& P, dim3 grid, cudaStream_t stream) {
+    const bool pool = P.g_pool != nullptr, drop = P.drop_p > 0.0f;
+    if (pool && drop) dsbn_act_bwd_kernel<APPLY, true, true><<<grid, kThreads, 0, stream>>>(P);
+    else if (pool) dsbn_act_bwd_kernel<APPLY, true, false><<<grid, kThreads, 0, stream>>>(P);
+    else if (drop) dsbn_act_bwd_kernel<APPLY, false, true><<<grid, kThreads, 0, stream>>>(P);
+    else dsbn_act_bwd_kernel<APPLY, false, false><<<grid, kThreads, 0, stream>>>(P);
 }
 
 extern "C" int fpl_dsbn_act_bwd_reduce(const void* y, const void* g1, int g1_c8tot, int g1_c8off, const void* g_pool,
@@ -549,9 +624,8 @@ extern "C" int fpl_dsbn_act_bwd_reduce(const void* y, const void* g1, int g1_c8t
     int rc = fill_bwd(P, y, g1, g1_c8tot, g1_c8off, g_pool, gp_c8tot, gp_c8off, pool_idx, pool_kd, scale, shift,
                       save_mean, save_invstd, slope, drop_p, drop_mask, seed, offset, seed_dev, n, d, h, w, c);
     if (rc) return rc;
-    FPL_REQUIRE((int64_t)n * d * (c / 8) <= 65535, "dsbn bwd: too many planes (%lld)", (long long)n * d * (c / 8));
     P.red = red;
-    dsbn_act_bwd_kernel<false><<<bwd_grid(n, d, h, w, c), kThreads, 0, (cudaStream_t)stream>>>(P);
+    bwd_dispatch<false>(P, bwd_grid(n, d, h, w, c), (cudaStream_t)stream);
     FPL_LAUNCH_CHECK();
     return 0;
 }
@@ -567,12 +641,11 @@ static int act_bwd_apply_launch(float* dgamma, float* dbeta, float* dslope, floa
     int rc = fill_bwd(P, y, g1, g1_c8tot, g1_c8off, g_pool, gp_c8tot, gp_c8off, pool_idx, pool_kd, scale, shift,
                       save_mean, save_invstd, slope, drop_p, drop_mask, seed, offset, seed_dev, n, d, h, w, c);
     if (rc) return rc;
-    FPL_REQUIRE((int64_t)n * d * (c / 8) <= 65535, "dsbn bwd: too many planes (%lld)", (long long)n * d * (c / 8));
     P.red = const_cast<double*>(red);
     P.dy = (bf16x8*)dy;
     P.training = training;
     P.fin_dgamma = dgamma; P.fin_dbeta = dbeta; P.fin_dslope = dslope; P.fin_dbias = dbias_conv;
-    dsbn_act_bwd_kernel<true><<<bwd_grid(n, d, h, w, c), kThreads, 0, (cudaStream_t)stream>>>(P);
+    bwd_dispatch<true>(P, bwd_grid(n, d, h, w, c), (cudaStream_t)stream);
     FPL_LAUNCH_CHECK();
     return 0;
 }
