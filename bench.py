@@ -195,6 +195,7 @@ def build_agent(stage, world):
         if world > 1:
             agent.reducer = GradAllReducer()
             agent.net.grad_ready_hook = agent.reducer.hook
+            agent.net.grad_wait_hook = agent.reducer.finish
     return agent
 
 

@@ -672,6 +672,7 @@ class SegmentationAgent(object):
         if self.world > 1:
             self.reducer = GradAllReducer()
             self.net.grad_ready_hook = self.reducer.hook
+            self.net.grad_wait_hook = self.reducer.finish
         ckpt_dir, prefix = self._ckpt_names()
         iter_start, iter_max, iter_valid = tr['iter_start'], tr['iter_max'], tr['iter_valid']
         iter_save = tr.get('iter_save', None)

@@ -173,6 +173,8 @@ class UNet2D5_dsbn(nn.Module):
         self._dfold_cache = {}
         self._unit_depth = {}
         self.grad_ready_hook = None     # callable(flat_grad, start, end, last) fired as buckets complete (DDP)
+        self.grad_wait_hook = None      # callable() that makes the current stream wait for those all-reduces
+        self._master = None             # persistent flat gradient buffer (see _deliver_grads)
         self._head = UNet2D5_dsbn._HeadConv(self.out_conv)
         self._stem = None
         self._head_unit = None
@@ -868,7 +870,58 @@ class UNet2D5_dsbn(nn.Module):
         assert done == len(params)
         flush_fold()
         self._join_aux()
-        return [grads[p].view(p.shape) for p in params]
+        return self._deliver_grads(params, offs, flat, grads)
+
+    # -- gradient delivery --------------------------------------------------------------------
+    def _master_grads(self, device):
+        """Persistent flat fp32 buffer behind every p.grad (all parameters that can receive gradients, both domains),
+        plus one device-resident segment table per domain for fpl_grad_scatter_add."""
+        m = self._master
+        if m is None or m["buf"].device != device:
+            order, off, o = [], {}, 0
+            for d in range(self.num_domains):
+                for p in self._grad_params(d):
+                    if p not in off:
+                        off[p] = o
+                        order.append(p)
+                        o += (p.numel() + 3) // 4 * 4
+            m = self._master = {"buf": torch.zeros(o, dtype=torch.float32, device=device), "off": off, "tables": {},
+                                "event": None}
+        return m
+
+    def _deliver_grads(self, params, offs, flat, grads):
+        """Hands one backward pass's gradients to the optimiser.  Default: ONE fpl_grad_scatter_add launch adds the
+        pass's flat buffer into the master buffer and p.grad is a view of that buffer (autograd gets None: its ~65
+        per-parameter AccumulateGrad adds for the second domain pass disappear).  The first pass after a
+        zero_grad(set_to_none=True) zeroes the master buffer.  FPL_GRAD_DIRECT=0, or a p.grad that is not ours,
+        falls back to returning the gradients to autograd."""
+        views = [grads[p].view(p.shape) for p in params]
+        if os.environ.get("FPL_GRAD_DIRECT", "1") == "0":
+            return views
+        m = self._master_grads(flat.device)
+        base, off = m["buf"].data_ptr(), m["off"]
+        if any(p.grad is not None and p.grad.data_ptr() != base + 4 * off[p] for p in params):
+            return views
+        if self.grad_wait_hook is not None:
+            self.grad_wait_hook()                     # DDP: the asynchronous all-reduces of `flat` must have landed
+        cur = torch.cuda.current_stream()
+        if self.out_conv.weight.grad is None:
+            m["buf"].zero_()
+            m["event"] = torch.cuda.Event()
+            m["event"].record(cur)
+        elif m["event"] is not None:
+            cur.wait_event(m["event"])                # the other pass's stream may have issued the zeroing
+        key = tuple(id(p) for p in params)
+        tab = m["tables"].get(key)
+        if tab is None:
+            rows = [[so, off[p], p.numel()] for p, so in zip(params, offs)]
+            tab = m["tables"][key] = (torch.tensor(rows, dtype=torch.int32, device=flat.device),
+                                      max(p.numel() for p in params))
+        call("fpl_grad_scatter_add", ptr(m["buf"]), ptr(flat), ptr(tab[0]), len(params), tab[1], stream_ptr())
+        for p in params:
+            if p.grad is None:
+                p.grad = m["buf"][off[p]:off[p] + p.numel()].view(p.shape)
+        return [None] * len(params)
 
 
 class _SmallPool(object):

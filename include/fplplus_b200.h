@@ -108,6 +108,13 @@ int fpl_conv3d_wgrad_tc_tapmajor(const void* x, int x_c8tot, int x_c8off, const 
 int fpl_wgrad_tapmajor_to_dw_batch(int count, const float* const* h_scratch, float* const* h_dw, const int* h_cout,
                                    const int* h_cin, const int* h_taps, void* stream);
 
+/* Adds segments of one backward pass's flat gradient buffer into the network's master gradient buffer (the storage
+ * behind every p.grad) in one launch: replaces autograd's per-parameter AccumulateGrad adds when the source and the
+ * target batch of a training_all step (agent_seg.py:459-495) go through the same weights.  d_table is a DEVICE array
+ * [segments][3] = {src offset, dst offset, count} in floats, offsets multiples of 4; the adds are atomic (the two
+ * passes run on two streams).  max_numel = the largest count (grid sizing). */
+int fpl_grad_scatter_add(float* dst, const float* src, const int* d_table, int segments, int max_numel, void* stream);
+
 /* stem: image fp32 NCDHW (in_chns <= 8) -> C8-planar bf16, conv k3 p1 + bias + stats. */
 int fpl_stem_conv_fwd(const float* x, const float* w, const float* bias, void* y, int y_c8tot, int y_c8off,
                       double* stats, int n, int cin, int d, int h, int w_, int cout, int kd, void* stream);

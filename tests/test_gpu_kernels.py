@@ -662,3 +662,56 @@ def test_stem_on_tensor_cores_patch9_k311(cout, shape):
     np.testing.assert_allclose(stats.cpu()[:cout], ref32.double().sum((0, 2, 3, 4)), rtol=2e-5, atol=2e-3)   # fp32-accurate sums
     np.testing.assert_allclose(stats.cpu()[cout:], (ref32.double() ** 2).sum((0, 2, 3, 4)), rtol=2e-5, atol=2e-3)
     assert max_rel(from_c8(y).cpu(), ref32) < 4e-3                                   # only the bf16 output rounding is left
+
+
+@pytest.mark.parametrize("cin,cout,kd,shape", [(16, 16, 3, (2, 4, 16, 32)), (32, 16, 3, (1, 6, 16, 16)), (64, 32, 3, (2, 4, 8, 16)),
+                                               (128, 128, 3, (2, 2, 8, 8)), (16, 16, 1, (1, 3, 16, 16))])
+def test_wgrad_tapmajor_and_fold(cin, cout, kd, shape):
+    """fpl_conv3d_wgrad_tc_tapmajor writes S[tap][cout][cin]; fpl_wgrad_tapmajor_to_dw_batch folds it into the
+    PyTorch layout ACCUMULATING into dw.  Against torch's conv3d weight gradient on bf16-rounded operands."""
+    n, d, h, w = shape
+    x = bf16_round(randn(301, n, cin, d, h, w))
+    wt = torch.zeros(cout, cin, kd, 3, 3, requires_grad=True)
+    y = F.conv3d(x, wt, None, padding=(kd // 2, 1, 1))
+    g = bf16_round(randn(302, *y.shape))
+    y.backward(g)
+    taps = kd * 9
+    scratch = torch.zeros(taps * cout * cin, device=DEV)
+    _call("fpl_conv3d_wgrad_tc_tapmajor", _p(to_c8(x.to(DEV))), cin // 8, 0, _p(to_c8(g.to(DEV))), cout // 8, 0, _p(scratch),
+          n, d, h, w, cin, cout, kd, _st())
+    s = scratch.cpu().view(taps, cout, cin).permute(1, 2, 0).reshape(cout, cin, kd, 3, 3)
+    assert max_rel(s, wt.grad) < 1e-4
+    # fold two layers' worth in one launch, on top of existing content
+    import ctypes
+    pre = randn(303, cout, cin, kd, 3, 3)
+    dw_a, dw_b = pre.to(DEV).contiguous(), torch.zeros(cout, cin, kd, 3, 3, device=DEV)
+    arr_s = (ctypes.c_void_p * 2)(scratch.data_ptr(), scratch.data_ptr())
+    arr_d = (ctypes.c_void_p * 2)(dw_a.data_ptr(), dw_b.data_ptr())
+    ci = (ctypes.c_int * 2)(cout, cout)
+    cj = (ctypes.c_int * 2)(cin, cin)
+    ct = (ctypes.c_int * 2)(taps, taps)
+    _call("fpl_wgrad_tapmajor_to_dw_batch", 2, arr_s, arr_d, ci, cj, ct, _st())
+    assert max_rel(dw_b.cpu(), wt.grad) < 1e-4
+    assert max_rel(dw_a.cpu(), wt.grad + pre) < 1e-4
+
+
+def test_grad_scatter_add():
+    """Segments of a flat gradient buffer are ADDED into the master buffer at other offsets (atomics; odd tails)."""
+    rng = np.random.Generator(np.random.PCG64(311))
+    counts = [1, 3, 4, 5, 16, 1023, 4096, 70001]
+    src_off, dst_off, so, do = [], [], 0, 8
+    for c in counts:
+        src_off.append(so)
+        dst_off.append(do)
+        so += (c + 3) // 4 * 4
+        do += (c + 3) // 4 * 4 + 4
+    src = torch.from_numpy(rng.standard_normal(so).astype(np.float32)).to(DEV)
+    dst0 = torch.from_numpy(rng.standard_normal(do + 8).astype(np.float32))
+    dst = dst0.clone().to(DEV)
+    table = torch.tensor([[a, b, c] for a, b, c in zip(src_off, dst_off, counts)], dtype=torch.int32, device=DEV)
+    for _ in range(2):
+        _call("fpl_grad_scatter_add", _p(dst), _p(src), _p(table), len(counts), max(counts), _st())
+    want = dst0.clone()
+    for a, b, c in zip(src_off, dst_off, counts):
+        want[b:b + c] += 2 * src.cpu()[a:a + c]
+    np.testing.assert_allclose(dst.cpu().numpy(), want.numpy(), rtol=1e-6, atol=1e-6)
