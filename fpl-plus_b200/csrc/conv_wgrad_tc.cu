@@ -37,17 +37,23 @@ struct WgCfg {
     int dy_off;            // offset of the dy tile inside a stage (x bytes rounded up to 128)
     int x_bytes, dy_bytes, stage_bytes, stages, pad_bytes, smem_bytes;
     int tmem_cols;
-    int pair;              // depth-paired mode: 2 dy planes x (2+2) x planes per tile (see the kernel)
-    int ncols;             // UMMA N = nb * (pair ? 2 : 1)
+    int ndy;               // depth-stacked mode: ndy dy planes x (ndy + kd - 1) x planes per tile (see the kernel); 1 = off
+    int ncols;             // UMMA N = nb * ndy
 };
 
 bool make_wg_cfg(int h, int w, int cin, int cout, int kd, int allow_m64, int allow_pair, WgCfg& c) {
-    if (cin % 8 != 0 || cout % 16 != 0 || cin <= 0 || cout <= 0) return false;
+    if (cin % 8 != 0 || (cout % 16 != 0 && cout != 8) || cin <= 0 || cout <= 0) return false;
     c.tw = w >= 32 ? 32 : (w >= 16 ? 16 : 8);
     c.th = h >= 8 ? 8 : ((h + 1) / 2) * 2;
     const int g_all = cin / 8;
-    c.pair = (allow_pair && kd == 3 && g_all <= 4) ? 1 : 0;
-    if (c.pair) { c.nkd = 4; c.c8chunk = g_all; c.mtiles_kd = 1; c.mtiles_c = 1; }
+    // depth stacking: k3 -> 2 dy planes x 4 x planes (3 of the 4 blocks per dy plane are taps); k(1,3,3) -> the diagonal
+    // blocks of ndy x ndy planes (4 planes when the output is one channel group: the head's classes padded to 8)
+    c.ndy = 1;
+    if (allow_pair && kd == 3 && g_all <= 4 && cout % 16 == 0) c.ndy = 2;
+    else if (allow_pair && kd == 1 && cout == 8 && g_all <= 2) c.ndy = 4;
+    else if (allow_pair && kd == 1 && cout == 8 && g_all <= 4) c.ndy = 2;
+    else if (allow_pair && kd == 1 && cout == 16 && g_all <= 8) c.ndy = 2;
+    if (c.ndy > 1) { c.nkd = c.ndy + kd - 1; c.c8chunk = g_all; c.mtiles_kd = 1; c.mtiles_c = 1; }
     else if (kd * g_all <= 16) { c.nkd = kd; c.c8chunk = g_all; c.mtiles_kd = 1; c.mtiles_c = 1; }
     else {
         c.nkd = 1; c.mtiles_kd = kd;
@@ -57,8 +63,9 @@ bool make_wg_cfg(int h, int w, int cin, int cout, int kd, int allow_m64, int all
     }
     const int groups = c.nkd * c.c8chunk;
     c.m = (groups <= 8 && allow_m64) ? 64 : 128;
-    c.nb = (cout % 32 == 0 && !c.pair) ? 32 : 16;
-    c.ncols = c.pair ? 2 * c.nb : c.nb;
+    if (cout == 8 && c.m != 64) return false;          // N = 8 needs the M = 64 shape
+    c.nb = cout == 8 ? 8 : ((cout % 32 == 0 && c.ndy == 1) ? 32 : 16);
+    c.ncols = c.ndy * c.nb;
     c.nchunks = cout / c.nb;
     if (groups > 8 && c.tw == 32 && cin >= 32 && h * w >= 128 * 128) c.tw = 16;   // keep >= 3 stages at full resolution
     if (g_wg_force_tw > 0 && g_wg_force_tw <= w) c.tw = g_wg_force_tw;
@@ -90,7 +97,7 @@ struct WgParams {
     int plane_x, plane_dy, x_bytes, dy_off, stage_bytes, stages, tmem_cols;
     int tiles_h, tiles_w, tiles_total, split;
     int swap_lbo_sbo, m64_quadrant_layout;
-    int pair, ncols, dplanes;      // dplanes: tile index range along depth (D, or ceil(D/2) in pair mode)
+    int ndy, ncols, dplanes;       // dplanes: tile index range along depth, ceil(D / ndy)
     int taps;                      // 9, or 1 = only the centre in-plane tap (k = (kd,1,1))
     int skip_epilogue;             // timing experiments only
     int tapmajor;                  // dW written as [tap][cout][cin] (coalesced atomics; see fpl_wgrad_tapmajor_to_dw_batch)
@@ -158,8 +165,9 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
                 const int th_i = r % P.tiles_h; r /= P.tiles_h;
                 const int dp = r % P.dplanes;
                 const int n = r / P.dplanes;
-                // pair mode: dy planes (2dp, 2dp+1) against x planes 2dp-1 .. 2dp+2 (planes outside the volume: TMA zero fill)
-                const int d = P.pair ? 2 * dp : dp;
+                // stacked mode: dy planes ndy*dp .. ndy*dp+ndy-1 against x planes ndy*dp-pad .. (planes outside the
+                // volume: TMA zero fill)
+                const int d = P.ndy * dp;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* x_dst = ring + (size_t)stage * P.stage_bytes;
                 uint8_t* dy_dst = x_dst + P.dy_off;
@@ -243,22 +251,26 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
 #pragma unroll
                     for (int i = 0; i < 16; ++i) P.dump[((int64_t)t9 * 128 + tlane) * P.ncols + c0 + i] = __uint_as_float(r[i]);
                 }
-                // pair mode: column block dd = c0 / nb is dy plane 2dp+dd, row block kdi is x plane 2dp-1+kdi:
-                // depth tap kd = kdi - dd (the two (kdi, dd) blocks of one tap are summed by the atomics)
-                const int dd = P.pair ? c0 / P.nb : 0;
-                const int kd_tap = P.pair ? kdi - dd : kdi;
-                if (valid && kd_tap >= 0 && kd_tap < P.kd && !P.skip_epilogue) {
+                // stacked mode: column block dd = col / nb is dy plane ndy*dp+dd, row block kdi is x plane ndy*dp-pad+kdi:
+                // depth tap kd = kdi - dd (the (kdi, dd) blocks of one tap are summed by the atomics).  nb is a multiple
+                // of 8, so each half of the 16 loaded columns lies in one block.
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int col = c0 + 8 * half;
+                    const int dd = P.ndy > 1 ? col / P.nb : 0;
+                    const int kd_tap = P.ndy > 1 ? kdi - dd : kdi;
+                    const int co0 = wk.nc * P.nb + (col - dd * P.nb);
+                    if (!(valid && kd_tap >= 0 && kd_tap < P.kd && !P.skip_epilogue)) continue;
                     if (P.tapmajor) {
                         // lanes = consecutive input channels: one 128-byte line per warp instruction
-                        float* base = P.dw + ((int64_t)(kd_tap * P.taps + t9) * P.cout + wk.nc * P.nb + (c0 - dd * P.nb)) * P.cin + ci;
+                        float* base = P.dw + ((int64_t)(kd_tap * P.taps + t9) * P.cout + co0) * P.cin + ci;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) atomicAdd(base + (int64_t)i * P.cin, __uint_as_float(r[i]));
+                        for (int i = 0; i < 8; ++i) atomicAdd(base + (int64_t)i * P.cin, __uint_as_float(r[8 * half + i]));
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int co = wk.nc * P.nb + (c0 - dd * P.nb) + i;
-                            atomicAdd(P.dw + ((int64_t)co * P.cin + ci) * T + kd_tap * P.taps + t9, __uint_as_float(r[i]));
-                        }
+                        for (int i = 0; i < 8; ++i)
+                            atomicAdd(P.dw + ((int64_t)(co0 + i) * P.cin + ci) * T + kd_tap * P.taps + t9,
+                                      __uint_as_float(r[8 * half + i]));
                     }
                 }
             }
@@ -315,7 +327,7 @@ static int wgrad_tc_launch(const void* x, int x_c8tot, int x_c8off, const void* 
     CUtensorMap xmap, dymap;
     CUresult r = encode_5d(encode, &xmap, x, n, d, x_c8tot, h, w, c.tw + 2, c.th + 2, c.c8chunk, c.nkd);
     FPL_REQUIRE(r == CUDA_SUCCESS, "fpl_conv3d_wgrad_tc: tensor map (x) failed (%d)", (int)r);
-    r = encode_5d(encode, &dymap, dy, n, d, dy_c8tot, h, w, c.tw, c.th, c.nb / 8, c.pair ? 2 : 1);
+    r = encode_5d(encode, &dymap, dy, n, d, dy_c8tot, h, w, c.tw, c.th, c.nb / 8, c.ndy);
     FPL_REQUIRE(r == CUDA_SUCCESS, "fpl_conv3d_wgrad_tc: tensor map (dy) failed (%d)", (int)r);
     WgParams P;
     P.dw = dw; P.dump = g_wg_dump;
@@ -325,7 +337,7 @@ static int wgrad_tc_launch(const void* x, int x_c8tot, int x_c8off, const void* 
     P.m = c.m; P.nb = c.nb; P.nchunks = c.nchunks; P.plane_x = c.plane_x; P.plane_dy = c.plane_dy; P.x_bytes = c.x_bytes; P.dy_off = c.dy_off;
     P.stage_bytes = c.stage_bytes; P.stages = c.stages; P.tmem_cols = c.tmem_cols;
     P.tiles_h = (h + c.th - 1) / c.th; P.tiles_w = (w + c.tw - 1) / c.tw;
-    P.pair = c.pair; P.ncols = c.ncols; P.dplanes = c.pair ? (d + 1) / 2 : d;
+    P.ndy = c.ndy; P.ncols = c.ncols; P.dplanes = (d + c.ndy - 1) / c.ndy;
     int64_t tiles = (int64_t)P.tiles_h * P.tiles_w * P.dplanes * n;
     FPL_REQUIRE(tiles < (1ll << 30), "fpl_conv3d_wgrad_tc: too many tiles");
     P.tiles_total = (int)tiles;

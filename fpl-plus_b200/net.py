@@ -813,9 +813,12 @@ class UNet2D5_dsbn(nn.Module):
             call("fpl_pack_ncdhw_to_c8", ptr(dlogits), k, ptr(dl16), 2, 0, 2, ptr(grads[self.out_conv.bias]), n, d, h, w, st)
             img_t = self._weight_image(self._head, 1, True, ws)
             call("fpl_conv3d_tc", ptr(dl16), 2, 0, ptr(img_t), None, *g.args(), None, n, d, h, w, 16, ft[0], 1, st)
-            dw16 = ws.get("dW16", (16, ft[0], 1, 3, 3), torch.float32)
+            # wgrad against the first channel group of dl16 only (classes padded to 8): 4 depth planes are stacked in
+            # M and N, so one MMA set covers 4 planes (csrc/conv_wgrad_tc.cu, ndy = 4)
+            co = 8 if (ft[0] <= 32 and d >= 2) else 16
+            dw16 = ws.get("dW16", (co, ft[0], 1, 3, 3), torch.float32)
             dw16.zero_()
-            call("fpl_conv3d_wgrad_tc", *head_in.args(), ptr(dl16), 2, 0, ptr(dw16), n, d, h, w, ft[0], 16, 1, st)
+            call("fpl_conv3d_wgrad_tc", *head_in.args(), ptr(dl16), 2, 0, ptr(dw16), n, d, h, w, ft[0], co, 1, st)
             grads[self.out_conv.weight].view(k, ft[0], 1, 3, 3).add_(dw16[:k])
         else:
             call("fpl_head_conv_bwd", *head_in.args(), ptr(self.out_conv.weight), ptr(dlogits), *g.args(),

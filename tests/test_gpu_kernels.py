@@ -715,3 +715,21 @@ def test_grad_scatter_add():
     for a, b, c in zip(src_off, dst_off, counts):
         want[b:b + c] += 2 * src.cpu()[a:a + c]
     np.testing.assert_allclose(dst.cpu().numpy(), want.numpy(), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("cin,cout,shape", [(16, 8, (2, 8, 16, 32)), (16, 8, (1, 5, 16, 16)), (32, 8, (1, 6, 8, 16)),
+                                            (16, 16, (2, 5, 16, 16)), (64, 16, (1, 4, 8, 16))])
+def test_conv3d_wgrad_tc_k133_depth_stacked(cin, cout, shape):
+    """k(1,3,3) weight gradient with depth planes stacked in M and N (the head: cout = 8 = one channel group of a wider
+    dy buffer, 4 planes per MMA set; cout = 16: 2 planes); depths that are not multiples of the stack."""
+    n, d, h, w = shape
+    x = bf16_round(randn(321, n, cin, d, h, w))
+    dy = bf16_round(randn(322, n, cout, d, h, w))
+    wt = torch.zeros(cout, cin, 1, 3, 3, requires_grad=True)
+    _conv_ref(x, wt, None, 1).backward(dy)
+    dw = torch.zeros(cout, cin, 1, 3, 3, device=DEV)
+    # dy lives in the first channel groups of a buffer with 2 more (garbage) groups
+    dyb = to_c8(torch.cat([dy, randn(323, n, 16, d, h, w)], 1).to(DEV))
+    _call("fpl_conv3d_wgrad_tc", _p(to_c8(x.to(DEV))), cin // 8, 0, _p(dyb), (cout + 16) // 8, 0, _p(dw), n, d, h, w, cin, cout,
+          1, _st())
+    assert max_rel(dw.cpu(), wt.grad) < 1e-4
