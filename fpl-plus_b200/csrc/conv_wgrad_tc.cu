@@ -381,32 +381,41 @@ constexpr int kMaxFold = 64;
 struct FoldBatch {
     const float* s[kMaxFold];
     float* dw[kMaxFold];
-    int cout[kMaxFold], cin[kMaxFold], taps[kMaxFold];
+    int cout[kMaxFold], cin[kMaxFold], taps[kMaxFold], scout[kMaxFold];
 };
-// dW[co][ci][tap] += S[tap][co][ci]   (blockIdx.y = layer)
+// dW[co][ci][tap] += S[tap][co][ci]   (blockIdx.y = layer; S has scout >= cout rows per tap, the first cout are folded)
 __global__ void __launch_bounds__(256) fold_tapmajor_kernel(const __grid_constant__ FoldBatch B) {
     const int e = blockIdx.y;
     const float* __restrict__ s = B.s[e];
     float* dw = B.dw[e];
-    const int cout = B.cout[e], cin = B.cin[e], T = B.taps[e];
+    const int cout = B.cout[e], cin = B.cin[e];
+    const bool transposed = B.taps[e] < 0;      // nn.ConvTranspose3d weight layout [cin][cout][tap]
+    const int T = transposed ? -B.taps[e] : B.taps[e];
     const int total = cout * cin * T;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int tap = i % T;
-        const int rest = i / T;                 // co * cin + ci
-        dw[i] += __ldg(s + (int64_t)tap * cout * cin + rest);
+        const int rest = i / T;                 // co * cin + ci   (transposed: ci * cout + co)
+        if (transposed) {
+            const int ci = rest / cout, co = rest - ci * cout;
+            dw[i] += __ldg(s + ((int64_t)tap * B.scout[e] + co) * cin + ci);
+        } else {
+            dw[i] += __ldg(s + (int64_t)tap * B.scout[e] * cin + rest);
+        }
     }
 }
 }  // namespace
 
 extern "C" int fpl_wgrad_tapmajor_to_dw_batch(int count, const float* const* h_scratch, float* const* h_dw, const int* h_cout,
-                                              const int* h_cin, const int* h_taps, void* stream) {
+                                              const int* h_cin, const int* h_taps, const int* h_scratch_cout, void* stream) {
     FPL_REQUIRE(count >= 0 && count <= kMaxFold, "fpl_wgrad_tapmajor_to_dw_batch: count %d not in [0,%d]", count, kMaxFold);
     if (count == 0) return 0;
     FoldBatch B;
     int max_total = 0;
     for (int e = 0; e < count; ++e) {
         B.s[e] = h_scratch[e]; B.dw[e] = h_dw[e]; B.cout[e] = h_cout[e]; B.cin[e] = h_cin[e]; B.taps[e] = h_taps[e];
-        const int total = h_cout[e] * h_cin[e] * h_taps[e];
+        B.scout[e] = h_scratch_cout != nullptr ? h_scratch_cout[e] : h_cout[e];
+        FPL_REQUIRE(B.scout[e] >= B.cout[e], "fpl_wgrad_tapmajor_to_dw_batch: scratch rows %d < folded rows %d", B.scout[e], B.cout[e]);
+        const int total = h_cout[e] * h_cin[e] * (h_taps[e] < 0 ? -h_taps[e] : h_taps[e]);
         if (total > max_total) max_total = total;
     }
     int bx = (max_total + 1023) / 1024;

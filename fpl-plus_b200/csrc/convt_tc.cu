@@ -266,6 +266,7 @@ struct CtwParams {
     int mgroups, m, nb, mtiles, nchunks;
     int x_bytes, dy_tile_bytes, stage_bytes, stages, tmem_cols;
     int tiles_h, tiles_w, tiles_total, split;
+    int tapmajor;          // dW written as scratch [tap][cout][cin]
 };
 
 __global__ void __launch_bounds__(kThreadsT) convt_wgrad_tc_kernel(const __grid_constant__ CUtensorMap xmap,
@@ -370,7 +371,8 @@ __global__ void __launch_bounds__(kThreadsT) convt_wgrad_tc_kernel(const __grid_
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int co = nc * P.nb + c0 + i;
-                        atomicAdd(P.dw + ((int64_t)ci * P.cout + co) * P.ntaps + tap, __uint_as_float(r[i]));
+                        if (P.tapmajor) atomicAdd(P.dw + ((int64_t)tap * P.cout + co) * P.cin + ci, __uint_as_float(r[i]));   // lanes = ci: coalesced
+                        else atomicAdd(P.dw + ((int64_t)ci * P.cout + co) * P.ntaps + tap, __uint_as_float(r[i]));
                     }
                 }
             }
@@ -503,15 +505,15 @@ extern "C" int fpl_convt_k2s2_dgrad_tc(const void* dy, int dy_c8tot, int dy_c8of
                              stream);
 }
 
-extern "C" int fpl_convt_k2s2_wgrad_tc(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
-                                       float* dw, int n, int d, int h, int w, int cin, int cout, int kd2, void* stream) {
+static int convt_wgrad_launch(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
+                              float* dw, int n, int d, int h, int w, int cin, int cout, int kd2, void* stream, int tapmajor) {
     FPL_REQUIRE(kd2 == 1 || kd2 == 2, "fpl_convt_k2s2_wgrad_tc: kd2=%d must be 1 or 2", kd2);
     FPL_REQUIRE(cin % 8 == 0 && cout % 16 == 0, "fpl_convt_k2s2_wgrad_tc: unsupported channels (%d -> %d)", cin, cout);
     EncodeTiledFn encode = get_encode_fn();
     FPL_REQUIRE(encode != nullptr, "fpl_convt_k2s2_wgrad_tc: cuTensorMapEncodeTiled not available from the driver");
     CtwParams P;
     P.dw = dw; P.N = n; P.D = d; P.H = h; P.W = w; P.cin = cin; P.cout = cout; P.kd2 = kd2; P.ntaps = 4 * kd2;
-    P.x_c8tot = x_c8tot; P.x_c8off = x_c8off; P.dy_c8tot = dy_c8tot; P.dy_c8off = dy_c8off;
+    P.x_c8tot = x_c8tot; P.x_c8off = x_c8off; P.dy_c8tot = dy_c8tot; P.dy_c8off = dy_c8off; P.tapmajor = tapmajor;
     const int g_all = cin / 8;
     P.mgroups = g_all < 16 ? g_all : 16;
     FPL_REQUIRE(g_all % P.mgroups == 0, "fpl_convt_k2s2_wgrad_tc: cin=%d not tileable", cin);
@@ -550,4 +552,17 @@ extern "C" int fpl_convt_k2s2_wgrad_tc(const void* x, int x_c8tot, int x_c8off, 
     convt_wgrad_tc_kernel<<<pairs * split, kThreadsT, smem_bytes, (cudaStream_t)stream>>>(xmap, dymap, P);
     FPL_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int fpl_convt_k2s2_wgrad_tc(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
+                                       float* dw, int n, int d, int h, int w, int cin, int cout, int kd2, void* stream) {
+    return convt_wgrad_launch(x, x_c8tot, x_c8off, dy, dy_c8tot, dy_c8off, dw, n, d, h, w, cin, cout, kd2, stream, 0);
+}
+
+/* Tap-major variant: scratch S[tap][cout][cin] (fp32, ACCUMULATED into; coalesced epilogue atomics); folded into the
+ * nn.ConvTranspose3d layout [cin][cout][tap] by fpl_wgrad_tapmajor_to_dw_batch with a NEGATIVE tap count. */
+extern "C" int fpl_convt_k2s2_wgrad_tc_tapmajor(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot,
+                                                int dy_c8off, float* scratch, int n, int d, int h, int w, int cin, int cout,
+                                                int kd2, void* stream) {
+    return convt_wgrad_launch(x, x_c8tot, x_c8off, dy, dy_c8tot, dy_c8off, scratch, n, d, h, w, cin, cout, kd2, stream, 1);
 }

@@ -40,7 +40,7 @@ _SIGNATURES = {
     "fpl_conv3d_wgrad_tc": (_I, [_P, _I, _I, _P, _I, _I, _P] + [_I] * 7 + [_P]),
     "fpl_conv3d_wgrad_tc_tapmajor": (_I, [_P, _I, _I, _P, _I, _I, _P] + [_I] * 7 + [_P]),
     "fpl_wgrad_tapmajor_to_dw_batch": (_I, [_I, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.POINTER(_I),
-                                            ctypes.POINTER(_I), ctypes.POINTER(_I), _P]),
+                                            ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_I), _P]),
     "fpl_grad_scatter_add": (_I, [_P, _P, _P, _I, _I, _P]),
     "fpl_stem_conv_fwd": (_I, [_P, _P, _P, _P, _I, _I, _P] + [_I] * 7 + [_P]),
     "fpl_stem_conv_wgrad": (_I, [_P, _P, _I, _I, _P] + [_I] * 7 + [_P]),
@@ -57,6 +57,7 @@ _SIGNATURES = {
     "fpl_convt_k2s2_fwd_tc": (_I, [_P, _I, _I, _P, _P, _P, _I, _I] + [_I] * 7 + [_P]),
     "fpl_convt_k2s2_dgrad_tc": (_I, [_P, _I, _I, _P, _P, _I, _I] + [_I] * 7 + [_P]),
     "fpl_convt_k2s2_wgrad_tc": (_I, [_P, _I, _I, _P, _I, _I, _P] + [_I] * 7 + [_P]),
+    "fpl_convt_k2s2_wgrad_tc_tapmajor": (_I, [_P, _I, _I, _P, _I, _I, _P] + [_I] * 7 + [_P]),
     "fpl_dsbn_finalize": (_I, [_P, _L, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _I, _P]),
     "fpl_dsbn_act_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _F, _P, _U, _U, _P] + [_I] * 5 + [_P]),
     "fpl_dsbn_bn_act_fwd": (_I, [_P, _P, _L, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P,

@@ -766,7 +766,9 @@ class UNet2D5_dsbn(nn.Module):
         fold = None
         if os.environ.get("FPL_WGRAD_TAPMAJOR", "1") != "0" and ops.is_sm100():
             total = sum((u.conv.weight.numel() + 3) // 4 * 4 for pair in self._down_units + self._up_units for u in pair
-                        if not u.is_stem)
+                        if not u.is_stem) + 16 * self.ft_chns[0] * 9 + sum(
+                            (t.weight.numel() + 3) // 4 * 4 for up in (self.up1, self.up2, self.up3, self.up4)
+                            for t in (up.trans3d, up.trans2d) if t is not None)
             scratch = ws.get("wgrad_scratch", (total,), torch.float32)
             scratch.zero_()
             cursor = [0]
@@ -786,7 +788,8 @@ class UNet2D5_dsbn(nn.Module):
             arr_s = (ctypes.c_void_p * m)(*[t[0].data_ptr() for t in part])
             arr_d = (ctypes.c_void_p * m)(*[t[1].data_ptr() for t in part])
             ints = [(ctypes.c_int * m)(*[t[k] for t in part]) for k in (2, 3, 4)]
-            call("fpl_wgrad_tapmajor_to_dw_batch", m, arr_s, arr_d, ints[0], ints[1], ints[2], stream_ptr())
+            scout = (ctypes.c_int * m)(*[t[5] if len(t) > 5 else t[2] for t in part])
+            call("fpl_wgrad_tapmajor_to_dw_batch", m, arr_s, arr_d, ints[0], ints[1], ints[2], scout, stream_ptr())
             fold["pending"] = []
 
         def fire(n_params_done):
@@ -816,10 +819,16 @@ class UNet2D5_dsbn(nn.Module):
             # wgrad against the first channel group of dl16 only (classes padded to 8): 4 depth planes are stacked in
             # M and N, so one MMA set covers 4 planes (csrc/conv_wgrad_tc.cu, ndy = 4)
             co = 8 if (ft[0] <= 32 and d >= 2) else 16
-            dw16 = ws.get("dW16", (co, ft[0], 1, 3, 3), torch.float32)
-            dw16.zero_()
-            call("fpl_conv3d_wgrad_tc", *head_in.args(), ptr(dl16), 2, 0, ptr(dw16), n, d, h, w, ft[0], co, 1, st)
-            grads[self.out_conv.weight].view(k, ft[0], 1, 3, 3).add_(dw16[:k])
+            if fold is not None:
+                # tap-major scratch; only the k real classes are folded into the head's gradient
+                scr = fold["alloc"](co * ft[0] * 9)
+                call("fpl_conv3d_wgrad_tc_tapmajor", *head_in.args(), ptr(dl16), 2, 0, ptr(scr), n, d, h, w, ft[0], co, 1, st)
+                fold["pending"].append((scr, grads[self.out_conv.weight], k, ft[0], 9, co))
+            else:
+                dw16 = ws.get("dW16", (co, ft[0], 1, 3, 3), torch.float32)
+                dw16.zero_()
+                call("fpl_conv3d_wgrad_tc", *head_in.args(), ptr(dl16), 2, 0, ptr(dw16), n, d, h, w, ft[0], co, 1, st)
+                grads[self.out_conv.weight].view(k, ft[0], 1, 3, 3).add_(dw16[:k])
         else:
             call("fpl_head_conv_bwd", *head_in.args(), ptr(self.out_conv.weight), ptr(dlogits), *g.args(),
                  ptr(grads[self.out_conv.weight]), ptr(grads[self.out_conv.bias]), n, d, h, w, ft[0], self.n_class, st)
@@ -844,8 +853,14 @@ class UNet2D5_dsbn(nn.Module):
             if self._convt_tc(c_low, c):
                 call("fpl_convt_k2s2_dgrad_tc", ptr(dcat.buf), 2 * c // 8, c // 8, ptr(self._convt_image(trans, kd2, 1)),
                      *glow.args(), n, dl, hl, wl, c_low, c, kd2, st)
-                call("fpl_convt_k2s2_wgrad_tc", *low.args(), ptr(dcat.buf), 2 * c // 8, c // 8, ptr(grads[trans.weight]),
-                     n, dl, hl, wl, c_low, c, kd2, st)
+                if fold is not None:
+                    scr = fold["alloc"](c_low * c * 4 * kd2)
+                    call("fpl_convt_k2s2_wgrad_tc_tapmajor", *low.args(), ptr(dcat.buf), 2 * c // 8, c // 8, ptr(scr),
+                         n, dl, hl, wl, c_low, c, kd2, st)
+                    fold["pending"].append((scr, grads[trans.weight], c, c_low, -4 * kd2))
+                else:
+                    call("fpl_convt_k2s2_wgrad_tc", *low.args(), ptr(dcat.buf), 2 * c // 8, c // 8, ptr(grads[trans.weight]),
+                         n, dl, hl, wl, c_low, c, kd2, st)
                 call("fpl_convt_k2s2_bwd", *low.args(), ptr(trans.weight), ptr(dcat.buf), 2 * c // 8, c // 8, None, 0, 0,
                      None, ptr(grads[trans.bias]), n, dl, hl, wl, c_low, c, kd2, st)       # bias gradient only
             else:

@@ -102,11 +102,13 @@ int fpl_conv3d_wgrad_tc(const void* x, int x_c8tot, int x_c8off, const void* dy,
 
 /* Tap-major variant: scratch S[kd*9+t9][cout][cin] (fp32, ACCUMULATED into) so that the epilogue's atomics are
  * coalesced; fpl_wgrad_tapmajor_to_dw_batch then folds the scratch of up to 64 layers into the PyTorch layout
- * (dW[co][ci][tap] += S[tap][co][ci]) in one launch; all arrays are HOST arrays of length count. */
+ * (dW[co][ci][tap] += S[tap][co][ci], co < cout) in one launch; all arrays are HOST arrays of length count;
+ * h_scratch_cout (may be NULL = h_cout) is the number of output-channel rows the scratch was computed with (the head:
+ * classes padded to 8, only the real classes are folded). */
 int fpl_conv3d_wgrad_tc_tapmajor(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
                                  float* scratch, int n, int d, int h, int w, int cin, int cout, int kd, void* stream);
 int fpl_wgrad_tapmajor_to_dw_batch(int count, const float* const* h_scratch, float* const* h_dw, const int* h_cout,
-                                   const int* h_cin, const int* h_taps, void* stream);
+                                   const int* h_cin, const int* h_taps, const int* h_scratch_cout, void* stream);
 
 /* Adds segments of one backward pass's flat gradient buffer into the network's master gradient buffer (the storage
  * behind every p.grad) in one launch: replaces autograd's per-parameter AccumulateGrad adds when the source and the
@@ -162,6 +164,10 @@ int fpl_convt_k2s2_dgrad_tc(const void* dy, int dy_c8tot, int dy_c8off, const vo
 /* dW[cin][cout][kd2][2][2] (fp32) ACCUMULATED into. */
 int fpl_convt_k2s2_wgrad_tc(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
                             float* dw, int n, int d, int h, int w, int cin, int cout, int kd2, void* stream);
+/* Tap-major variant: scratch S[tap][cout][cin] (fp32, ACCUMULATED into); fold it into the nn.ConvTranspose3d layout
+ * [cin][cout][kd2][2][2] with fpl_wgrad_tapmajor_to_dw_batch, passing the tap count NEGATED (-4*kd2). */
+int fpl_convt_k2s2_wgrad_tc_tapmajor(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
+                                     float* scratch, int n, int d, int h, int w, int cin, int cout, int kd2, void* stream);
 
 /* ---- (b) DSBN BatchNorm3d + PReLU + Dropout + MaxPool: net_run_dsbn/dsbn.py:54-57,
  *          unet2d5_dsbn.py:76-81,104-106 ---- */

@@ -567,6 +567,14 @@ def test_convt_k2s2_tensor_core_fwd_dgrad_wgrad(cin, cout, kd2, shape):
               kd2, _st())
     assert max_rel(from_c8(dx).cpu(), x.grad) < 6e-3
     assert max_rel(dw.cpu(), 2 * wt.grad) < 1e-4
+    # tap-major scratch + batched fold (negative tap count = ConvTranspose weight layout)
+    ntaps = 4 * kd2
+    scratch = torch.zeros(ntaps * cout * cin, device=DEV)
+    _call("fpl_convt_k2s2_wgrad_tc_tapmajor", _p(xb), cin // 8, 0, _p(gcat), 2 * cout // 8, cout // 8, _p(scratch), n, d, h, w,
+          cin, cout, kd2, _st())
+    _call("fpl_wgrad_tapmajor_to_dw_batch", 1, (ctypes.c_void_p * 1)(scratch.data_ptr()), (ctypes.c_void_p * 1)(dw.data_ptr()),
+          (ctypes.c_int * 1)(cout), (ctypes.c_int * 1)(cin), (ctypes.c_int * 1)(-ntaps), None, _st())
+    assert max_rel(dw.cpu(), 3 * wt.grad) < 1e-4
 
 
 @pytest.mark.parametrize("transpose", [0, 1])
@@ -690,7 +698,12 @@ def test_wgrad_tapmajor_and_fold(cin, cout, kd, shape):
     ci = (ctypes.c_int * 2)(cout, cout)
     cj = (ctypes.c_int * 2)(cin, cin)
     ct = (ctypes.c_int * 2)(taps, taps)
-    _call("fpl_wgrad_tapmajor_to_dw_batch", 2, arr_s, arr_d, ci, cj, ct, _st())
+    _call("fpl_wgrad_tapmajor_to_dw_batch", 2, arr_s, arr_d, ci, cj, ct, None, _st())
+    # only the first rows of a wider scratch
+    half = torch.zeros(cout // 2, cin, kd, 3, 3, device=DEV)
+    _call("fpl_wgrad_tapmajor_to_dw_batch", 1, (ctypes.c_void_p * 1)(scratch.data_ptr()), (ctypes.c_void_p * 1)(half.data_ptr()),
+          (ctypes.c_int * 1)(cout // 2), (ctypes.c_int * 1)(cin), (ctypes.c_int * 1)(taps), (ctypes.c_int * 1)(cout), _st())
+    assert max_rel(half.cpu(), wt.grad[:cout // 2]) < 1e-4
     assert max_rel(dw_b.cpu(), wt.grad) < 1e-4
     assert max_rel(dw_a.cpu(), wt.grad + pre) < 1e-4
 

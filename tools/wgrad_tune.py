@@ -9,7 +9,7 @@ from fplplus_b200 import lib, ops
 
 DEV = "cuda:0"
 L = lib.load()
-SHAPES = [(16, 16, 3, (4, 32, 128, 128)), (32, 16, 3, (4, 32, 128, 128)), (16, 16, 1, (4, 32, 128, 128)),
+SHAPES = [(16, 8, 1, (4, 32, 128, 128)), (16, 16, 3, (4, 32, 128, 128)), (32, 16, 3, (4, 32, 128, 128)), (16, 16, 1, (4, 32, 128, 128)),
           (16, 32, 3, (4, 16, 64, 64)), (32, 32, 3, (4, 16, 64, 64)), (64, 32, 3, (4, 16, 64, 64)),
           (32, 64, 3, (4, 8, 32, 32)), (64, 64, 3, (4, 8, 32, 32)), (128, 64, 3, (4, 8, 32, 32)),
           (64, 128, 3, (4, 4, 16, 16)), (128, 128, 3, (4, 4, 16, 16)), (256, 128, 3, (4, 4, 16, 16)),
@@ -21,21 +21,21 @@ def t(cin, cout, kd, shape, knobs):
     for k, v in knobs.items():
         L.fpl_debug_set(k, v)
     x = torch.randn((n, d, cin // 8, h, w, 8), device=DEV).to(torch.bfloat16)
-    dy = torch.randn((n, d, cout // 8, h, w, 8), device=DEV).to(torch.bfloat16)
+    dy = torch.randn((n, d, max(cout // 8, 2), h, w, 8), device=DEV).to(torch.bfloat16)
     dw = torch.zeros(cout, cin, kd, 3, 3, device=DEV)
     st = ops.stream_ptr()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for it in range(7):
         if it == 2:
             e0.record()
-        ops.call("fpl_conv3d_wgrad_tc", ops.ptr(x), cin // 8, 0, ops.ptr(dy), cout // 8, 0, ops.ptr(dw), n, d, h, w, cin, cout, kd, st)
+        ops.call(FN, ops.ptr(x), cin // 8, 0, ops.ptr(dy), max(cout // 8, 2), 0, ops.ptr(dw), n, d, h, w, cin, cout, kd, st)
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / 5 * 1e3
 
 
-variants = [("tiles4", {15: 0, 16: 4, 17: 0}), ("tiles4-noepi", {15: 0, 16: 4, 17: 1}), ("tiles2", {15: 0, 16: 2, 17: 0}),
-            ("tiles2-noepi", {15: 0, 16: 2, 17: 1}), ("tiles1", {15: 0, 16: 1, 17: 0})]
+variants = [("base", {17: 0, 18: 1}), ("noepi", {17: 1, 18: 1}), ("nodirect", {17: 0, 18: 0})]
+FN = os.environ.get("FN", "fpl_conv3d_wgrad_tc_tapmajor")
 print("%-28s" % "shape" + "".join("%12s" % v[0] for v in variants))
 for cin, cout, kd, shape in SHAPES:
     row = []
