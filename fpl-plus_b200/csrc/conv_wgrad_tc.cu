@@ -383,24 +383,43 @@ struct FoldBatch {
     float* dw[kMaxFold];
     int cout[kMaxFold], cin[kMaxFold], taps[kMaxFold], scout[kMaxFold];
 };
-// dW[co][ci][tap] += S[tap][co][ci]   (blockIdx.y = layer; S has scout >= cout rows per tap, the first cout are folded)
+// dW[row][tap] += S[tap][row]   (blockIdx.y = layer; row = co*cin + ci; S has scout >= cout rows of cin per tap, the first
+// cout are folded).  Both sides are coalesced through a shared-memory transpose: a block owns kFoldRows consecutive
+// rows, reads them tap by tap (consecutive threads = consecutive rows) and writes the [rows][taps] block contiguously.
+// Negative tap count: nn.ConvTranspose3d layout, row = ci*cout + co (small tensors; the gather is left uncoalesced).
+constexpr int kFoldRows = 256;
 __global__ void __launch_bounds__(256) fold_tapmajor_kernel(const __grid_constant__ FoldBatch B) {
+    __shared__ float tile[kFoldRows * 27];
     const int e = blockIdx.y;
     const float* __restrict__ s = B.s[e];
     float* dw = B.dw[e];
     const int cout = B.cout[e], cin = B.cin[e];
-    const bool transposed = B.taps[e] < 0;      // nn.ConvTranspose3d weight layout [cin][cout][tap]
+    const bool transposed = B.taps[e] < 0;
     const int T = transposed ? -B.taps[e] : B.taps[e];
-    const int total = cout * cin * T;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int tap = i % T;
-        const int rest = i / T;                 // co * cin + ci   (transposed: ci * cout + co)
-        if (transposed) {
-            const int ci = rest / cout, co = rest - ci * cout;
-            dw[i] += __ldg(s + ((int64_t)tap * B.scout[e] + co) * cin + ci);
-        } else {
-            dw[i] += __ldg(s + (int64_t)tap * B.scout[e] * cin + rest);
+    const int Tp = T | 1;                                   // odd row pitch: conflict-free transposed writes
+    const uint32_t magic = 0xffffffffu / (uint32_t)T + 1u;  // i / T == umulhi(i, magic) for i < 2^16
+    const int rows = cout * cin;
+    const int64_t tap_stride = (int64_t)B.scout[e] * cin;
+    for (int r0 = blockIdx.x * kFoldRows; r0 < rows; r0 += gridDim.x * kFoldRows) {
+        const int nr = min(kFoldRows, rows - r0);
+        const int r = threadIdx.x;
+        if (r < nr) {
+            int src = r0 + r;
+            if (transposed) {
+                const int ci = src / cout, co = src - ci * cout;
+                src = co * cin + ci;
+            }
+            const float* sp = s + src;
+#pragma unroll 9
+            for (int tap = 0; tap < T; ++tap) tile[r * Tp + tap] = __ldg(sp + tap * tap_stride);
         }
+        __syncthreads();
+        float* out = dw + (int64_t)r0 * T;
+        for (int i = threadIdx.x; i < nr * T; i += blockDim.x) {
+            const int rr = (int)__umulhi((uint32_t)i, magic), tap = i - rr * T;
+            out[i] += tile[rr * Tp + tap];
+        }
+        __syncthreads();
     }
 }
 }  // namespace
@@ -414,12 +433,14 @@ extern "C" int fpl_wgrad_tapmajor_to_dw_batch(int count, const float* const* h_s
     for (int e = 0; e < count; ++e) {
         B.s[e] = h_scratch[e]; B.dw[e] = h_dw[e]; B.cout[e] = h_cout[e]; B.cin[e] = h_cin[e]; B.taps[e] = h_taps[e];
         B.scout[e] = h_scratch_cout != nullptr ? h_scratch_cout[e] : h_cout[e];
+        FPL_REQUIRE((h_taps[e] < 0 ? -h_taps[e] : h_taps[e]) <= 27 && h_taps[e] != 0, "fpl_wgrad_tapmajor_to_dw_batch: tap count %d out of range", h_taps[e]);
         FPL_REQUIRE(B.scout[e] >= B.cout[e], "fpl_wgrad_tapmajor_to_dw_batch: scratch rows %d < folded rows %d", B.scout[e], B.cout[e]);
         const int total = h_cout[e] * h_cin[e] * (h_taps[e] < 0 ? -h_taps[e] : h_taps[e]);
         if (total > max_total) max_total = total;
     }
-    int bx = (max_total + 1023) / 1024;
-    if (bx > 128) bx = 128;
+    int bx = (max_total / 9 + kFoldRows - 1) / kFoldRows;      // ~ blocks of kFoldRows rows for the largest layer
+    if (bx > 296) bx = 296;
+    if (bx < 1) bx = 1;
     fold_tapmajor_kernel<<<dim3(bx, count), 256, 0, (cudaStream_t)stream>>>(B);
     FPL_LAUNCH_CHECK();
     return 0;
