@@ -131,12 +131,29 @@ def _conv_work(a, off):
     return 2.0 * n * d * h * w * cin * cout * kd * 9, float(n * d * h * w * (cin + cout) * 2)
 
 
+def _dfold_work(a):
+    n, d, h, w, cin, cout = a[9:15]
+    return 2.0 * n * d * h * w * cin * cout * 27, float(n * d * h * w * (cin + cout) * 2)
+
+
 WORK = {   # entry point -> (flops, algorithmic bytes) from its argument tuple
     "fpl_conv3d_tc": lambda a: _conv_work(a, 9),
+    "fpl_conv3d_tc_dfold": _dfold_work,
     "fpl_conv3d_direct": lambda a: _conv_work(a, 9),
     "fpl_conv3d_wgrad": lambda a: _conv_work(a, 7),
     "fpl_conv3d_wgrad_tc": lambda a: _conv_work(a, 7),
+    "fpl_conv3d_wgrad_tc_tapmajor": lambda a: _conv_work(a, 7),
 }
+
+
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, averaged over the launches of one train step,
+    from the committed `ncu --set full` capture (profiles/roofline_traffic.json, written by tools/ncu_traffic.py)."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        return json.load(f).get(kernel, {}).get("dram_bytes_per_launch")
 
 
 class KernelTimer(object):
@@ -290,6 +307,10 @@ def run_ours(args):
     timer = KernelTimer()
     lib.set_call_timer(timer)
     agent.use_cuda_graph = False
+    # one stream for this pass: with the domain passes / wgrads on side streams an event bracket would also time the
+    # kernels it overlaps with
+    saved_streams = (agent.dual_stream, agent.net.wgrad_side_stream)
+    agent.dual_stream, agent.net.wgrad_side_stream = False, False
     for _ in range(2):
         step_resident()
     torch.cuda.synchronize()
@@ -299,6 +320,7 @@ def run_ours(args):
     timer.enabled = False
     launches = lib.launch_count()
     agent.use_cuda_graph = True
+    agent.dual_stream, agent.net.wgrad_side_stream = saved_streams
     pk = peaks()
     agg = timer.summary()
     step_ms = ms / args.steps
@@ -312,7 +334,8 @@ def run_ours(args):
         n, tot_ms, fl, by = conv[top]
         ach = fl / (tot_ms / 1e3) / 1e12
         roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"],
-                    "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
+                    "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"], "traffic": measured_traffic(top),
+                    "traffic_note": "bytes per launch (dram read + write, ncu --set full, mean over the launches of one step)",
                     "peak_source": pk["source"] + " (sustained bf16, kernel timed inside a long step)",
                     "launches_per_step": n / args.steps, "avg_launch_ms": tot_ms / n,
                     "algorithmic_gflop_per_launch": fl / n / 1e9, "algorithmic_mb_per_launch": by / n / 1e6,
