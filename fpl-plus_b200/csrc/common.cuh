@@ -148,3 +148,15 @@ __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t offset
     }
     return bits;
 }
+
+// ---- inference epilogue of the conv kernels (BatchNorm in eval mode folded into the conv) -------------------------
+// a = dropout(prelu(acc * scale + shift)):  scale = gamma / sqrt(running_var + eps),
+// shift = beta + (conv bias - running_mean) * scale  (fpl_dsbn_eval_affine_batch).  scale == NULL: plain "+ bias".
+struct EpiAct {
+    const float* scale;
+    const float* shift;
+    const float* slope;
+    float drop_p;
+    uint64_t seed, offset;
+    const unsigned long long* seed_dev;
+};

@@ -64,7 +64,7 @@ bool make_config(int cin, int cout, TcConfig& c) {
     int cols = 2 * c.nb;
     c.tmem_cols = 32;
     while (c.tmem_cols < cols) c.tmem_cols *= 2;
-    c.smem_bytes = c.stages * c.stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + cout * (int)sizeof(float) + 16;
+    c.smem_bytes = c.stages * c.stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + 2 * cout * (int)sizeof(float) + 16;
     return true;
 }
 
@@ -81,6 +81,7 @@ struct TcParams {
     int dbg_swap_lbo_sbo;
     float* logits;        // head mode: fp32 NCDHW output of the first `classes` channels instead of bf16 C8-planar
     int classes;
+    EpiAct act;           // act.scale != NULL: inference epilogue (affine + PReLU + dropout) instead of + bias
 };
 
 struct TileCoord {
@@ -122,7 +123,12 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
-    for (int i = threadIdx.x; i < P.cout; i += kNumThreads) bias_sm[i] = P.bias != nullptr ? P.bias[i] : 0.0f;
+    float* scale_sm = bias_sm + P.cout;
+    const bool fuse_act = P.act.scale != nullptr;
+    for (int i = threadIdx.x; i < P.cout; i += kNumThreads) {
+        bias_sm[i] = fuse_act ? P.act.shift[i] : (P.bias != nullptr ? P.bias[i] : 0.0f);
+        scale_sm[i] = fuse_act ? P.act.scale[i] : 1.0f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -219,6 +225,9 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
         for (int k = 0; k < kMaxChunks; ++k) run[k] = 0.0f;
         const bool want_stats = P.stats != nullptr;
         const int nchunk16 = P.nb / 16;
+        const float act_slope = fuse_act ? __ldg(P.act.slope) : 0.0f;
+        const float act_keep_scale = (fuse_act && P.act.drop_p > 0.0f) ? 1.0f / (1.0f - P.act.drop_p) : 1.0f;
+        const uint64_t act_seed = fuse_act ? P.act.seed + (P.act.seed_dev != nullptr ? (uint64_t)__ldg(P.act.seed_dev) : 0ull) : 0ull;
         for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
             TileCoord c = decode_tile(P, t);
             if (want_stats && c.slice != cur_slice) {
@@ -250,13 +259,39 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
                     tmem_ld_wait();
                     float v[32];
                     const float4* b4 = reinterpret_cast<const float4*>(bias_sm + c.slice * P.nb + c0);
+                    if (!fuse_act) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float4 bb = b4[i];
-                        v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bb.x;
-                        v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
-                        v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z;
-                        v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
+                        for (int i = 0; i < 4; ++i) {
+                            float4 bb = b4[i];
+                            v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bb.x;
+                            v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
+                            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z;
+                            v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
+                        }
+                    } else {
+                        // inference: BatchNorm (running statistics) + PReLU + dropout applied here, the activation kernel
+                        // and its extra pass over the tensor disappear
+                        const float4* s4 = reinterpret_cast<const float4*>(scale_sm + c.slice * P.nb + c0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 bb = b4[i], ss = s4[i];
+                            const float sc[4] = {ss.x, ss.y, ss.z, ss.w}, sh[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float z = fmaf(__uint_as_float(r[4 * i + q]), sc[q], sh[q]);
+                                v[4 * i + q] = z > 0.0f ? z : act_slope * z;
+                            }
+                        }
+                        if (P.act.drop_p > 0.0f && valid) {
+                            const int C8 = P.cout >> 3;
+                            const int64_t vec0 = (((int64_t)c.n * P.D + c.d) * C8 + (c.slice * P.nb + c0) / 8) * HW + (int64_t)h * P.W + w;
+#pragma unroll
+                            for (int g = 0; g < 2; ++g) {
+                                const uint32_t keep = dropout_keep8(act_seed, P.act.offset, (uint64_t)(vec0 + (int64_t)g * HW), P.act.drop_p);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[8 * g + i] = ((keep >> i) & 1u) ? v[8 * g + i] * act_keep_scale : 0.0f;
+                            }
+                        }
                     }
                     if (P.logits != nullptr) {
                         if (valid && k == 0) {
@@ -419,7 +454,7 @@ extern "C" void fpl_debug_set(int key, long long value) {
 
 static int conv3d_tc_launch(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias, void* y,
                             int y_c8tot, int y_c8off, double* stats, int n, int d, int h, int w, int cin, int cout,
-                            int kd, float* logits, int classes, void* stream) {
+                            int kd, float* logits, int classes, void* stream, const EpiAct* act = nullptr) {
     TcConfig c;
     FPL_REQUIRE(make_config(cin, cout, c), "fpl_conv3d_tc: unsupported channels (%d -> %d); need multiples of 16", cin, cout);
     FPL_REQUIRE(kd == 1 || kd == 3, "fpl_conv3d_tc: kd=%d must be 1 or 3", kd);
@@ -449,6 +484,7 @@ static int conv3d_tc_launch(const void* x, int x_c8tot, int x_c8off, const void*
     P.total_tiles = (int)total;
     P.dbg_swap_lbo_sbo = g_dbg_swap;
     P.logits = logits; P.classes = classes;
+    if (act != nullptr) P.act = *act; else { P.act.scale = nullptr; P.act.shift = nullptr; P.act.slope = nullptr; P.act.drop_p = 0.0f; P.act.seed = P.act.offset = 0; P.act.seed_dev = nullptr; }
     FPL_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
     int ctas_per_sm = c.smem_bytes <= 110 * 1024 ? 2 : 1;
     int grid = FPL_NUM_SMS * ctas_per_sm;
@@ -463,6 +499,21 @@ extern "C" int fpl_conv3d_tc(const void* x, int x_c8tot, int x_c8off, const void
                              int kd, void* stream) {
     return conv3d_tc_launch(x, x_c8tot, x_c8off, image, bias, y, y_c8tot, y_c8off, stats, n, d, h, w, cin, cout, kd,
                             nullptr, 0, stream);
+}
+
+/* Inference form of fpl_conv3d_tc: the epilogue applies a = dropout(prelu(acc * scale + shift)) (eval-mode BatchNorm,
+ * nn.PReLU, nn.Dropout of unet2d5_dsbn.py:75-81) and writes the ACTIVATION, so no fpl_dsbn_act_fwd pass follows. */
+extern "C" int fpl_conv3d_tc_act(const void* x, int x_c8tot, int x_c8off, const void* image, void* a, int a_c8tot, int a_c8off,
+                                 int n, int d, int h, int w, int cin, int cout, int kd, const float* scale, const float* shift,
+                                 const float* slope, float drop_p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev,
+                                 void* stream) {
+    FPL_REQUIRE(scale != nullptr && shift != nullptr && slope != nullptr, "fpl_conv3d_tc_act: scale/shift/slope required");
+    FPL_REQUIRE(drop_p >= 0.0f && drop_p < 1.0f, "fpl_conv3d_tc_act: dropout p=%f out of [0,1)", drop_p);
+    EpiAct act;
+    act.scale = scale; act.shift = shift; act.slope = slope; act.drop_p = drop_p; act.seed = seed; act.offset = offset;
+    act.seed_dev = (const unsigned long long*)seed_dev;
+    return conv3d_tc_launch(x, x_c8tot, x_c8off, image, nullptr, a, a_c8tot, a_c8off, nullptr, n, d, h, w, cin, cout, kd,
+                            nullptr, 0, stream, &act);
 }
 
 extern "C" int fpl_head_conv_tc(const void* x, int x_c8tot, int x_c8off, const void* image16, const float* bias16,

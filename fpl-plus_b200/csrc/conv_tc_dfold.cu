@@ -36,6 +36,7 @@ struct DfParams {
     int tiles_h, tiles_w, total_items;
     int taps;                        // 9 (k 3x3x3) or 1 (k 3x1x1: only the centre in-plane tap)
     int a_ksteps;                    // distinct 16-channel K steps of A (B K step j reads A K step j % a_ksteps)
+    EpiAct act;                      // act.scale != NULL: inference epilogue (affine + PReLU) instead of + bias
 };
 
 __device__ __forceinline__ void tmem_st_zero16(uint32_t taddr) {
@@ -89,7 +90,12 @@ __global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
-    for (int i = threadIdx.x; i < P.cout; i += kThreadsD) bias_sm[i] = P.bias != nullptr ? P.bias[i] : 0.0f;
+    float* scale_sm = bias_sm + P.cout;
+    const bool fuse_act = P.act.scale != nullptr;
+    for (int i = threadIdx.x; i < P.cout; i += kThreadsD) {
+        bias_sm[i] = fuse_act ? P.act.shift[i] : (P.bias != nullptr ? P.bias[i] : 0.0f);
+        scale_sm[i] = fuse_act ? P.act.scale[i] : 1.0f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -205,6 +211,7 @@ __global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid
         if (lane == 0) mbar_arrive(acc_free);
         uint32_t item_phase = 0;
         int cur_slice = -1;
+        const float act_slope = fuse_act ? __ldg(P.act.slope) : 0.0f;
         for (int t = blockIdx.x; t < P.total_items; t += gridDim.x) {
             const DfItem c = decode_item(P, t);
             if (want_stats && c.slice != cur_slice) {
@@ -237,13 +244,28 @@ __global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid
                         tmem_st_zero16(taddr);                          // leave the slot clean for the next item
                         float v[32];
                         const float4* b4 = reinterpret_cast<const float4*>(bias_sm + c.slice * P.nb + c0);
+                        if (!fuse_act) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            float4 bb = b4[i];
-                            v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bb.x;
-                            v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
-                            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z;
-                            v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
+                            for (int i = 0; i < 4; ++i) {
+                                float4 bb = b4[i];
+                                v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bb.x;
+                                v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
+                                v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z;
+                                v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
+                            }
+                        } else {
+                            // inference: eval-mode BatchNorm + PReLU applied here (no activation pass follows)
+                            const float4* s4 = reinterpret_cast<const float4*>(scale_sm + c.slice * P.nb + c0);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float4 bb = b4[i], ss = s4[i];
+                                const float sc[4] = {ss.x, ss.y, ss.z, ss.w}, sh[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float z = fmaf(__uint_as_float(r[4 * i + q]), sc[q], sh[q]);
+                                    v[4 * i + q] = z > 0.0f ? z : act_slope * z;
+                                }
+                            }
                         }
                         if (valid) {
                             st_bf16x8(P.y + out_base + (int64_t)(c0 / 8) * HW, v);
@@ -327,7 +349,7 @@ bool make_df_cfg(int cin, int cout, int d, DfCfg& c, int taps = 9, int cin_a = 0
     while (c.tmem_cols < cols) c.tmem_cols *= 2;
     if (c.tmem_cols > 512) return false;
     c.stages = c.b_bytes <= 32 * 1024 ? 6 : 4;
-    c.smem_bytes = c.b_bytes + c.stages * c.a_bytes + 1024 + 512 + cout * (int)sizeof(float) + 16;
+    c.smem_bytes = c.b_bytes + c.stages * c.a_bytes + 1024 + 512 + 2 * cout * (int)sizeof(float) + 16;
     if (c.smem_bytes > 220 * 1024) return false;
     c.ctas_per_sm = (c.smem_bytes <= 110 * 1024 && c.tmem_cols <= 256) ? 2 : 1;
     return true;
@@ -427,7 +449,7 @@ extern "C" int fpl_conv3d_dfold_prep_weight_batch(int count, const float* const*
 
 static int dfold_launch(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias, void* y,
                         int y_c8tot, int y_c8off, double* stats, int n, int d, int h, int w, int cin, int cout, int taps,
-                        int cin_a, void* stream) {
+                        int cin_a, void* stream, const EpiAct* act = nullptr) {
     if (cin_a <= 0) cin_a = cin;
     DfCfg c;
     FPL_REQUIRE(make_df_cfg(cin, cout, d, c, taps, cin_a), "fpl_conv3d_tc_dfold: unsupported shape (%d -> %d, depth %d)", cin, cout, d);
@@ -455,6 +477,7 @@ static int dfold_launch(const void* x, int x_c8tot, int x_c8off, const void* ima
     FPL_REQUIRE(total < (1ll << 30), "fpl_conv3d_tc_dfold: too many items");
     P.total_items = (int)total;
     P.taps = taps; P.a_ksteps = cin_a / 16;
+    if (act != nullptr) P.act = *act; else { P.act.scale = nullptr; P.act.shift = nullptr; P.act.slope = nullptr; P.act.drop_p = 0.0f; P.act.seed = P.act.offset = 0; P.act.seed_dev = nullptr; }
     FPL_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_dfold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
     int grid = FPL_NUM_SMS * c.ctas_per_sm;
     if (grid > P.total_items) grid = P.total_items;
@@ -476,4 +499,25 @@ extern "C" int fpl_conv3d_tc_k311(const void* x, int x_c8tot, int x_c8off, const
                                   int a_channels, void* stream) {
     return dfold_launch(x, x_c8tot, x_c8off, image, bias, y, y_c8tot, y_c8off, stats, n, d, h, w, cin, cout, 1, a_channels,
                         stream);
+}
+
+/* Inference forms (see fpl_conv3d_tc_act): a = prelu(acc * scale + shift) written instead of y; no dropout here (the
+ * levels these kernels serve have p = 0 in every shipped configuration; callers with p > 0 use the two-kernel path). */
+extern "C" int fpl_conv3d_tc_dfold_act(const void* x, int x_c8tot, int x_c8off, const void* image, void* a, int a_c8tot,
+                                       int a_c8off, int n, int d, int h, int w, int cin, int cout, const float* scale,
+                                       const float* shift, const float* slope, void* stream) {
+    FPL_REQUIRE(scale != nullptr && shift != nullptr && slope != nullptr, "fpl_conv3d_tc_dfold_act: scale/shift/slope required");
+    EpiAct act;
+    act.scale = scale; act.shift = shift; act.slope = slope; act.drop_p = 0.0f; act.seed = act.offset = 0; act.seed_dev = nullptr;
+    return dfold_launch(x, x_c8tot, x_c8off, image, nullptr, a, a_c8tot, a_c8off, nullptr, n, d, h, w, cin, cout, 9, 0, stream, &act);
+}
+
+extern "C" int fpl_conv3d_tc_k311_act(const void* x, int x_c8tot, int x_c8off, const void* image, void* a, int a_c8tot,
+                                      int a_c8off, int n, int d, int h, int w, int cin, int cout, int a_channels,
+                                      const float* scale, const float* shift, const float* slope, void* stream) {
+    FPL_REQUIRE(scale != nullptr && shift != nullptr && slope != nullptr, "fpl_conv3d_tc_k311_act: scale/shift/slope required");
+    EpiAct act;
+    act.scale = scale; act.shift = shift; act.slope = slope; act.drop_p = 0.0f; act.seed = act.offset = 0; act.seed_dev = nullptr;
+    return dfold_launch(x, x_c8tot, x_c8off, image, nullptr, a, a_c8tot, a_c8off, nullptr, n, d, h, w, cin, cout, 1, a_channels,
+                        stream, &act);
 }

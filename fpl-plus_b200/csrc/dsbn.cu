@@ -678,3 +678,53 @@ extern "C" int fpl_dsbn_bwd_finalize(const double* red, const float* scale, cons
     FPL_LAUNCH_CHECK();
     return 0;
 }
+
+// ------------------------------------------------------------------------------------
+// eval-mode affine maps of all conv units of a forward pass in ONE launch (inference epilogue of the conv kernels)
+// ------------------------------------------------------------------------------------
+namespace {
+constexpr int kMaxAffine = 48;
+struct AffineBatch {
+    const float* gamma[kMaxAffine];
+    const float* beta[kMaxAffine];
+    const float* mean[kMaxAffine];
+    const float* var[kMaxAffine];
+    const float* bias[kMaxAffine];      // conv bias feeding the BatchNorm (may be NULL)
+    float* scale[kMaxAffine];
+    float* shift[kMaxAffine];
+    int c[kMaxAffine];
+    float eps;
+};
+__global__ void dsbn_eval_affine_batch_kernel(const __grid_constant__ AffineBatch B) {
+    const int e = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B.c[e]; i += gridDim.x * blockDim.x) {
+        const float invstd = 1.0f / sqrtf(B.var[e][i] + B.eps);      // same expression as the eval branch of bn_prologue
+        const float g = B.gamma[e][i] * invstd;
+        const float b = B.bias[e] != nullptr ? B.bias[e][i] : 0.0f;
+        B.scale[e][i] = g;
+        B.shift[e][i] = (B.beta[e][i] - B.mean[e][i] * g) + b * g;
+    }
+}
+}  // namespace
+
+extern "C" int fpl_dsbn_eval_affine_batch(int count, const float* const* h_gamma, const float* const* h_beta,
+                                          const float* const* h_running_mean, const float* const* h_running_var,
+                                          const float* const* h_conv_bias, float* const* h_scale, float* const* h_shift,
+                                          const int* h_c, float eps, void* stream) {
+    FPL_REQUIRE(count >= 0 && count <= kMaxAffine, "fpl_dsbn_eval_affine_batch: count %d not in [0,%d]", count, kMaxAffine);
+    if (count == 0) return 0;
+    AffineBatch B;
+    int cmax = 0;
+    for (int e = 0; e < count; ++e) {
+        FPL_REQUIRE(h_gamma[e] && h_beta[e] && h_running_mean[e] && h_running_var[e] && h_scale[e] && h_shift[e] && h_c[e] > 0,
+                    "fpl_dsbn_eval_affine_batch: NULL array in entry %d", e);
+        B.gamma[e] = h_gamma[e]; B.beta[e] = h_beta[e]; B.mean[e] = h_running_mean[e]; B.var[e] = h_running_var[e];
+        B.bias[e] = h_conv_bias != nullptr ? h_conv_bias[e] : nullptr; B.scale[e] = h_scale[e]; B.shift[e] = h_shift[e];
+        B.c[e] = h_c[e];
+        if (h_c[e] > cmax) cmax = h_c[e];
+    }
+    B.eps = eps;
+    dsbn_eval_affine_batch_kernel<<<dim3((cmax + 127) / 128, count), 128, 0, (cudaStream_t)stream>>>(B);
+    FPL_LAUNCH_CHECK();
+    return 0;
+}

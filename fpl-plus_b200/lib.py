@@ -41,6 +41,10 @@ _SIGNATURES = {
     "fpl_conv3d_wgrad_tc_tapmajor": (_I, [_P, _I, _I, _P, _I, _I, _P] + [_I] * 7 + [_P]),
     "fpl_wgrad_tapmajor_to_dw_batch": (_I, [_I, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.POINTER(_I),
                                             ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_I), _P]),
+    "fpl_dsbn_eval_affine_batch": (_I, [_I] + [ctypes.POINTER(c_void_p)] * 7 + [ctypes.POINTER(_I), _F, _P]),
+    "fpl_conv3d_tc_act": (_I, [_P, _I, _I, _P, _P, _I, _I] + [_I] * 7 + [_P, _P, _P, _F, _U, _U, _P, _P]),
+    "fpl_conv3d_tc_dfold_act": (_I, [_P, _I, _I, _P, _P, _I, _I] + [_I] * 6 + [_P, _P, _P, _P]),
+    "fpl_conv3d_tc_k311_act": (_I, [_P, _I, _I, _P, _P, _I, _I] + [_I] * 7 + [_P, _P, _P, _P]),
     "fpl_grad_scatter_add": (_I, [_P, _P, _P, _I, _I, _P]),
     "fpl_stem_conv_fwd": (_I, [_P, _P, _P, _P, _I, _I, _P] + [_I] * 7 + [_P]),
     "fpl_stem_conv_wgrad": (_I, [_P, _P, _I, _I, _P] + [_I] * 7 + [_P]),

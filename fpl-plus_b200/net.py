@@ -552,10 +552,74 @@ class UNet2D5_dsbn(nn.Module):
             call("fpl_conv3d_direct", *xin.args(), ptr(u.conv.weight), ptr(u.conv.bias), ptr(y), y.shape[2], 0,
                  ptr(stats), n, d, h, w, u.cin, u.cout, u.kd, 0, 0, st)
 
+    def _eval_affine_refresh(self, domain, ws):
+        """Inference epilogue (csrc/common.cuh EpiAct): scale / shift of every conv unit whose BatchNorm is in eval mode,
+        from the CURRENT running statistics, in one launch at the start of a no-grad forward (part of the captured
+        graph, so replays follow the running statistics).  Returns {unit name: (scale, shift)}."""
+        units = [u for pair in self._down_units + self._up_units for u in pair if not u.dsbn.bns[domain].training]
+        if not units or os.environ.get("FPL_EVAL_FUSE", "1") == "0" or not ops.is_sm100():
+            return {}
+        key = "eval_affine:%d" % domain
+        total = sum(2 * u.cout for u in units)
+        buf = ws.get(key, (total,), torch.float32)
+        out, o = {}, 0
+        for u in units:
+            out[u.name] = (buf[o:o + u.cout], buf[o + u.cout:o + 2 * u.cout])
+            o += 2 * u.cout
+        m = len(units)
+        bns = [u.dsbn.bns[domain] for u in units]
+        arr = lambda ts: (ctypes.c_void_p * m)(*[t.data_ptr() for t in ts])
+        call("fpl_dsbn_eval_affine_batch", m, arr([b.weight for b in bns]), arr([b.bias for b in bns]),
+             arr([b.running_mean for b in bns]), arr([b.running_var for b in bns]), arr([u.conv.bias for u in units]),
+             arr([out[u.name][0] for u in units]), arr([out[u.name][1] for u in units]),
+             (ctypes.c_int * m)(*[u.cout for u in units]), float(bns[0].eps), stream_ptr())
+        return out
+
+    def _unit_fwd_fused(self, u, xin, x_img, out, aff, p, seed, offset, seed_dev, n, geo, ws):
+        """Inference: conv with the eval-mode BatchNorm + PReLU (+ dropout) in its epilogue; writes the activation into
+        ``out``.  Returns False when no fused kernel serves this unit (the caller runs the two-kernel path)."""
+        d, h, w = geo
+        st = stream_ptr()
+        scale, shift = aff
+        if u.is_stem:
+            if not self._stem_tc(d) or p > 0.0:
+                return False
+            xs = ws.c8("XS:stem", n, d, 32, h, w)
+            call("fpl_patch9_c8", ptr(x_img), ptr(xs), 1, n, d, h, w, st)
+            call("fpl_conv3d_tc_k311_act", ptr(xs), 4, 0, ptr(self._stem.image), *out.args(), n, d, h, w, 48, u.cout, 32,
+                 ptr(scale), ptr(shift), ptr(u.prelu.weight), st)
+            return True
+        if self._dfold_ok(u.cin, u.cout, u.kd, d):
+            if p > 0.0:
+                return False
+            call("fpl_conv3d_tc_dfold_act", *xin.args(), ptr(self._dfold_image(u.conv, False)), *out.args(), n, d, h, w,
+                 u.cin, u.cout, ptr(scale), ptr(shift), ptr(u.prelu.weight), st)
+            return True
+        if self._use_tc(u.cin, u.cout):
+            img = self._weight_image(u.conv, u.kd, False, ws)
+            call("fpl_conv3d_tc_act", *xin.args(), ptr(img), *out.args(), n, d, h, w, u.cin, u.cout, u.kd, ptr(scale),
+                 ptr(shift), ptr(u.prelu.weight), p, seed, offset, ptr(seed_dev) if p > 0.0 else None, st)
+            return True
+        return False
+
     def _unit_fwd(self, u, domain, xin, x_img, out, pooled, pool_idx, pool_kd, n, geo, ws, small, rec):
         """conv -> finalize -> act.  ``out``/``pooled`` are C8 views."""
         d, h, w = geo
         c = u.cout
+        aff = rec["eval_affine"].get(u.name)
+        if aff is not None and pooled is None:
+            # no-grad forward, BatchNorm in eval mode: one kernel instead of two (dropout keeps the same Philox stream
+            # positions as the two-kernel path)
+            p, seed, offset = 0.0, 0, 0
+            drop = u.dropout is not None and u.dropout.training and u.dropout.p > 0.0
+            explicit = drop and self._dropout_masks is not None and u.name in self._dropout_masks
+            if not explicit:
+                if drop:
+                    p, seed, offset = float(u.dropout.p), rec["seed"], rec["next_offset"]
+                if self._unit_fwd_fused(u, xin, x_img, out, aff, p, seed, offset, rec["seed_dev"], n, geo, ws):
+                    if drop:
+                        rec["next_offset"] += 2 * n * d * (c // 8) * h * w
+                    return
         y = ws.c8("Y:" + u.name, n, d, c, h, w)
         stats = small.f64(2 * c)
         self._conv_fwd(u, xin, x_img, y, stats, n, geo, ws)
@@ -598,6 +662,7 @@ class UNet2D5_dsbn(nn.Module):
         else:
             seed, seed_dev = self._draw_seed(), None
         rec = {"seed": seed, "seed_dev": seed_dev, "next_offset": 0, "geo": geo, "n": n, "x": x}
+        rec["eval_affine"] = {} if torch.is_grad_enabled() else self._eval_affine_refresh(domain, ws)
         cur = None
         for i in range(5):
             u1, u2 = self._down_units[i]

@@ -117,6 +117,27 @@ int fpl_wgrad_tapmajor_to_dw_batch(int count, const float* const* h_scratch, flo
  * passes run on two streams).  max_numel = the largest count (grid sizing). */
 int fpl_grad_scatter_add(float* dst, const float* src, const int* d_table, int segments, int max_numel, void* stream);
 
+/* ---- inference epilogue: eval-mode BatchNorm + PReLU + Dropout folded into the conv kernels --------------------------
+ * In eval mode nn.BatchNorm3d is the per-channel affine map of the running statistics (dsbn.py:54-57), so
+ * conv -> BN -> PReLU -> Dropout (unet2d5_dsbn.py:75-81) is  a = dropout(prelu(acc * scale + shift))  with
+ * scale = gamma / sqrt(running_var + eps), shift = beta + (conv bias - running_mean) * scale: the conv epilogue writes the
+ * activation and the fpl_dsbn_act_fwd pass (4 B/element of HBM traffic per layer) disappears from no-grad forwards.
+ * fpl_dsbn_eval_affine_batch computes scale / shift of up to 48 layers in one launch (HOST arrays of DEVICE pointers). */
+int fpl_dsbn_eval_affine_batch(int count, const float* const* h_gamma, const float* const* h_beta,
+                               const float* const* h_running_mean, const float* const* h_running_var,
+                               const float* const* h_conv_bias, float* const* h_scale, float* const* h_shift,
+                               const int* h_c, float eps, void* stream);
+int fpl_conv3d_tc_act(const void* x, int x_c8tot, int x_c8off, const void* image, void* a, int a_c8tot, int a_c8off,
+                      int n, int d, int h, int w, int cin, int cout, int kd, const float* scale, const float* shift,
+                      const float* slope, float drop_p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev,
+                      void* stream);
+int fpl_conv3d_tc_dfold_act(const void* x, int x_c8tot, int x_c8off, const void* image, void* a, int a_c8tot, int a_c8off,
+                            int n, int d, int h, int w, int cin, int cout, const float* scale, const float* shift,
+                            const float* slope, void* stream);
+int fpl_conv3d_tc_k311_act(const void* x, int x_c8tot, int x_c8off, const void* image, void* a, int a_c8tot, int a_c8off,
+                           int n, int d, int h, int w, int cin, int cout, int a_channels, const float* scale,
+                           const float* shift, const float* slope, void* stream);
+
 /* stem: image fp32 NCDHW (in_chns <= 8) -> C8-planar bf16, conv k3 p1 + bias + stats. */
 int fpl_stem_conv_fwd(const float* x, const float* w, const float* bias, void* y, int y_c8tot, int y_c8off,
                       double* stats, int n, int cin, int d, int h, int w_, int cout, int kd, void* stream);

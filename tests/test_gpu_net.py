@@ -471,3 +471,35 @@ def test_direct_gradient_delivery_equals_autograd_accumulation(monkeypatch):
     _, g2 = run("1", repeats=2)
     k = "out_conv.weight"
     assert float((g2[k] - 2 * g1[k]).abs().max()) <= 2e-2 * float(g1[k].abs().max())
+
+
+@pytest.mark.parametrize("mc_dropout", [False, True])
+@pytest.mark.parametrize("dims", [[3, 3, 3, 3, 3], [2, 2, 3, 3, 3]])
+def test_inference_epilogue_fusion_matches_two_kernel_path(mc_dropout, dims, monkeypatch):
+    """No-grad forwards with BatchNorm in eval mode run conv + BN + PReLU (+ dropout) as ONE kernel (EpiAct).  Same logits
+    as conv -> fpl_dsbn_bn_act_fwd within the bf16 tolerance (the fused form skips one bf16 rounding), the SAME dropout
+    mask (Philox positions), and both within rel 1e-2 of the fp32 oracle."""
+    from oracle import unet_dsbn
+    params = dict(NET_PARAMS, conv_dims=dims, dropout=[0.0, 0.0, 0.3, 0.4, 0.5])
+    shape = (16, 32, 32)
+    x = torch.from_numpy(synth.synth_image(2, 1, shape, seed=77))
+    outs = {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("FPL_EVAL_FUSE", fuse)
+        net = _net(params).eval()
+        net.cuda_graphs = False
+        if mc_dropout:
+            for m in net.modules():
+                if type(m) == torch.nn.Dropout:
+                    m.train()
+        torch.manual_seed(5)
+        with torch.no_grad():
+            outs[fuse] = net(x.to(DEV), domain_label=torch.ones(2, dtype=torch.long)).cpu()
+    err = rel_l2(outs["1"], outs["0"])
+    print("fused vs two-kernel logits rel_l2 %.2e (mc_dropout=%s)" % (err, mc_dropout))
+    assert err < 6e-3
+    if not mc_dropout:
+        sd = synth.synth_state_dict(params["in_chns"], params["feature_chns"], params["class_num"], params["num_domains"], seed=1)
+        ref = unet_dsbn.forward(unet_dsbn.to_torch_state(sd), x, 1, params, bn_training=False).detach()
+        assert rel_l2(outs["1"], ref) < 1e-2 and rel_l2(outs["0"], ref) < 1e-2
+        assert rel_l2(outs["1"], ref) <= rel_l2(outs["0"], ref) * 1.25
