@@ -728,3 +728,67 @@ extern "C" int fpl_dsbn_eval_affine_batch(int count, const float* const* h_gamma
     FPL_LAUNCH_CHECK();
     return 0;
 }
+
+// ------------------------------------------------------------------------------------
+// max-pool only (inference: the activation was already written by the conv epilogue)
+// ------------------------------------------------------------------------------------
+namespace {
+struct PoolParams {
+    const bf16x8* a;
+    int a_c8tot, a_c8off;
+    bf16x8* pooled;
+    int p_c8tot, p_c8off;
+    int kd, N, D, C8, H, W;
+};
+// grid: (chunks of H2*W2, N*D2*C8 pooled planes); one thread per pooled vector
+__global__ void __launch_bounds__(kThreads) maxpool_c8_kernel(PoolParams P) {
+    const int kd = P.kd, D2 = P.D / kd, H2 = P.H / 2, W2 = P.W / 2;
+    const int HW = P.H * P.W, HW2 = H2 * W2;
+    const int pplane = blockIdx.y;
+    const int c8 = pplane % P.C8;
+    const int nd2 = pplane / P.C8;
+    const int d2 = nd2 % D2, n = nd2 / D2;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < HW2; v += gridDim.x * blockDim.x) {
+        const int h2 = v / W2, w2 = v - h2 * W2;
+        int4 raw[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int dd = q >> 2, hh = (q >> 1) & 1, ww = q & 1;
+            if (dd < kd) {
+                const int64_t nd = (int64_t)n * P.D + d2 * kd + dd;
+                raw[q] = ld_stream16(P.a + (nd * P.a_c8tot + P.a_c8off + c8) * HW + (h2 * 2 + hh) * P.W + w2 * 2 + ww);
+            }
+        }
+        float best[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) best[i] = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if ((q >> 2) < kd) {
+                float f[8];
+                bf16x8_to_float(*reinterpret_cast<bf16x8*>(&raw[q]), f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) best[i] = fmaxf(best[i], f[i]);
+            }
+        }
+        st_bf16x8(P.pooled + ((int64_t)nd2 * P.p_c8tot + P.p_c8off + c8) * HW2 + v, best);
+    }
+}
+}  // namespace
+
+extern "C" int fpl_maxpool_c8(const void* a, int a_c8tot, int a_c8off, void* pooled, int p_c8tot, int p_c8off, int pool_kd,
+                              int n, int d, int h, int w, int c, void* stream) {
+    FPL_REQUIRE(c > 0 && c % 8 == 0, "fpl_maxpool_c8: channels (%d) must be a multiple of 8", c);
+    FPL_REQUIRE(pool_kd == 1 || pool_kd == 2, "fpl_maxpool_c8: pool_kd must be 1 or 2");
+    FPL_REQUIRE(h % 2 == 0 && w % 2 == 0 && d % pool_kd == 0, "fpl_maxpool_c8: pooled dims must be even");
+    FPL_REQUIRE(a != nullptr && pooled != nullptr, "fpl_maxpool_c8: NULL buffer");
+    PoolParams P;
+    P.a = (const bf16x8*)a; P.a_c8tot = a_c8tot; P.a_c8off = a_c8off; P.pooled = (bf16x8*)pooled; P.p_c8tot = p_c8tot;
+    P.p_c8off = p_c8off; P.kd = pool_kd; P.N = n; P.D = d; P.C8 = c / 8; P.H = h; P.W = w;
+    const int64_t planes = (int64_t)n * (d / pool_kd) * (c / 8);
+    FPL_REQUIRE(planes <= 65535, "fpl_maxpool_c8: too many planes (%lld)", (long long)planes);
+    const int hw2 = (h / 2) * (w / 2);
+    maxpool_c8_kernel<<<dim3((hw2 + kThreads - 1) / kThreads, (unsigned)planes), kThreads, 0, (cudaStream_t)stream>>>(P);
+    FPL_LAUNCH_CHECK();
+    return 0;
+}

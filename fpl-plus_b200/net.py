@@ -174,6 +174,7 @@ class UNet2D5_dsbn(nn.Module):
         self._unit_depth = {}
         self.grad_ready_hook = None     # callable(flat_grad, start, end, last) fired as buckets complete (DDP)
         self.grad_wait_hook = None      # callable() that makes the current stream wait for those all-reduces
+        self.grad_bucket_bytes = 4 << 20
         self._master = None             # persistent flat gradient buffer (see _deliver_grads)
         self._head = UNet2D5_dsbn._HeadConv(self.out_conv)
         self._stem = None
@@ -607,7 +608,7 @@ class UNet2D5_dsbn(nn.Module):
         d, h, w = geo
         c = u.cout
         aff = rec["eval_affine"].get(u.name)
-        if aff is not None and pooled is None:
+        if aff is not None:
             # no-grad forward, BatchNorm in eval mode: one kernel instead of two (dropout keeps the same Philox stream
             # positions as the two-kernel path)
             p, seed, offset = 0.0, 0, 0
@@ -619,6 +620,8 @@ class UNet2D5_dsbn(nn.Module):
                 if self._unit_fwd_fused(u, xin, x_img, out, aff, p, seed, offset, rec["seed_dev"], n, geo, ws):
                     if drop:
                         rec["next_offset"] += 2 * n * d * (c // 8) * h * w
+                    if pooled is not None:
+                        call("fpl_maxpool_c8", *out.args(), *pooled.args(), pool_kd, n, d, h, w, c, stream_ptr())
                     return
         y = ws.c8("Y:" + u.name, n, d, c, h, w)
         stats = small.f64(2 * c)
@@ -861,7 +864,9 @@ class UNet2D5_dsbn(nn.Module):
             # gradients of params[:n_params_done] are final: hand the new flat range to the hook (DDP all-reduce)
             if self.grad_ready_hook is not None:
                 end = offs[n_params_done - 1] + sizes[n_params_done - 1]
-                if end > fired[0]:
+                last = n_params_done == len(params)
+                # hand over >= grad_bucket_bytes at a time: every hand-over costs a fold launch and an all-reduce launch
+                if end > fired[0] and (last or (end - fired[0]) * 4 >= self.grad_bucket_bytes):
                     flush_fold()
                     self._join_aux()
                     self.grad_ready_hook(flat, fired[0], end, n_params_done == len(params))

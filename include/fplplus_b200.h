@@ -138,6 +138,11 @@ int fpl_conv3d_tc_k311_act(const void* x, int x_c8tot, int x_c8off, const void* 
                            int n, int d, int h, int w, int cin, int cout, int a_channels, const float* scale,
                            const float* shift, const float* slope, void* stream);
 
+/* nn.MaxPool3d((pool_kd,2,2)) (unet2d5_dsbn.py:104-117) of a C8-planar activation that the inference epilogue already
+ * wrote; no argmax codes (no-grad forwards only). */
+int fpl_maxpool_c8(const void* a, int a_c8tot, int a_c8off, void* pooled, int p_c8tot, int p_c8off, int pool_kd,
+                   int n, int d, int h, int w, int c, void* stream);
+
 /* stem: image fp32 NCDHW (in_chns <= 8) -> C8-planar bf16, conv k3 p1 + bias + stats. */
 int fpl_stem_conv_fwd(const float* x, const float* w, const float* bias, void* y, int y_c8tot, int y_c8off,
                       double* stats, int n, int cin, int d, int h, int w_, int cout, int kd, void* stream);
