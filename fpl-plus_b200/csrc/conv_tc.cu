@@ -76,7 +76,8 @@ struct TcParams {
     double* stats;
     int N, D, H, W, cin, cout, kd;
     int x_c8tot, x_c8off;
-    int nb, kc, nslices, nchunks, a_bytes, b_bytes, stages, tmem_cols;
+    int nb, kc, nslices, nchunks, a_bytes, b_bytes, stages, tmem_cols;   // nb / nslices / b_bytes: of THIS launch (after nsub)
+    int nsub, nb_img, b_bytes_img;   // N split of a staged image slice: nb = nb_img / nsub (few-tile layers: more, smaller CTAs)
     int tiles_h, tiles_w, total_tiles;
     int dbg_swap_lbo_sbo;
     float* logits;        // head mode: fp32 NCDHW output of the first `classes` channels instead of bf16 C8-planar
@@ -100,7 +101,8 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int t) {
     return c;
 }
 
-__global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, TcParams P) {
+__global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                                 const __grid_constant__ CUtensorMap imap, TcParams P) {
     extern __shared__ uint8_t smem_raw[];
     // stage ring at 1024-byte alignment, then barriers, the TMEM base slot and the BN partial sums
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -118,6 +120,7 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+        if (P.nsub > 1) asm volatile("prefetch.tensormap [%0];" ::"l"(&imap) : "memory");
         for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
         fence_barrier_init();
@@ -150,9 +153,16 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
                         mbar_expect_tx(&full_bar[stage], (uint32_t)(P.a_bytes + P.b_bytes));
                         tma_load_3d(a_dst, &xmap, &full_bar[stage], (c.w0 - 1) * 8, c.h0 - 1,
                                     (c.n * P.D + dz) * P.x_c8tot + P.x_c8off + q * (P.kc / 8));
-                        const uint8_t* b_src = reinterpret_cast<const uint8_t*>(P.image) +
-                                               ((size_t)(c.slice * P.nchunks + q) * P.kd + kdi) * P.b_bytes;
-                        bulk_load(b_dst, b_src, (uint32_t)P.b_bytes, &full_bar[stage]);
+                        if (P.nsub == 1) {
+                            const uint8_t* b_src = reinterpret_cast<const uint8_t*>(P.image) +
+                                                   ((size_t)(c.slice * P.nchunks + q) * P.kd + kdi) * P.b_bytes;
+                            bulk_load(b_dst, b_src, (uint32_t)P.b_bytes, &full_bar[stage]);
+                        } else {
+                            // this CTA's nb columns out of the nb_img of the staged slice: the image is a 3-D tensor
+                            // {nb_img * 16 B, 9 * kc/8 rows, chunks}; one TMA box lands the packed [rows][nb * 16 B] operand
+                            const int simg = c.slice / P.nsub, sub = c.slice - simg * P.nsub;
+                            tma_load_3d(b_dst, &imap, &full_bar[stage], sub * P.nb * 2, 0, (simg * P.nchunks + q) * P.kd + kdi);
+                        }
                         if (++stage == P.stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -443,11 +453,12 @@ extern "C" int fpl_conv3d_prep_weight_batch(int count, const float* const* h_w, 
     return 0;
 }
 
-static int g_dbg_swap = 0;
+static int g_dbg_swap = 0, g_tc_allow_nsub = 1;
 void fpl_wgrad_debug_set(int key, long long value);
 void fpl_dsbn_debug_set(int key, long long value);
 extern "C" void fpl_debug_set(int key, long long value) {
     if (key == 0) g_dbg_swap = (int)value;
+    if (key == 1) g_tc_allow_nsub = (int)value;
     if (key >= 10 && key < 30) fpl_wgrad_debug_set(key, value);
     if (key >= 30 && key < 40) fpl_dsbn_debug_set(key, value);
 }
@@ -479,7 +490,17 @@ static int conv3d_tc_launch(const void* x, int x_c8tot, int x_c8off, const void*
     P.nb = c.nb; P.kc = c.kc; P.nslices = c.nslices; P.nchunks = c.nchunks; P.a_bytes = c.a_bytes; P.b_bytes = c.b_bytes;
     P.stages = c.stages; P.tmem_cols = c.tmem_cols;
     P.tiles_h = (h + kTileH - 1) / kTileH; P.tiles_w = (w + kTileW - 1) / kTileW;
-    int64_t total = (int64_t)P.tiles_h * P.tiles_w * d * n * c.nslices;
+    // few voxel tiles (levels 3-4): split the N of a staged slice over up to 4 CTAs so that the ~430 serial MMAs of a tile
+    // get shorter and more SMs work; the image layout stays that of nb_img
+    P.nsub = 1; P.nb_img = c.nb; P.b_bytes_img = c.b_bytes;
+    {
+        const int64_t mn = (int64_t)P.tiles_h * P.tiles_w * d * n * c.nslices;
+        while (g_tc_allow_nsub && logits == nullptr && P.nsub < 4 && c.nb % (P.nsub * 2 * 16) == 0 && c.nb / (P.nsub * 2) >= 32 &&
+               mn * P.nsub < 96)
+            P.nsub *= 2;
+    }
+    P.nb = c.nb / P.nsub; P.nslices = c.nslices * P.nsub; P.b_bytes = c.b_bytes / P.nsub;
+    int64_t total = (int64_t)P.tiles_h * P.tiles_w * d * n * P.nslices;
     FPL_REQUIRE(total < (1ll << 30), "fpl_conv3d_tc: too many tiles");
     P.total_tiles = (int)total;
     P.dbg_swap_lbo_sbo = g_dbg_swap;
@@ -489,7 +510,19 @@ static int conv3d_tc_launch(const void* x, int x_c8tot, int x_c8off, const void*
     int ctas_per_sm = c.smem_bytes <= 110 * 1024 ? 2 : 1;
     int grid = FPL_NUM_SMS * ctas_per_sm;
     if (grid > P.total_tiles) grid = P.total_tiles;
-    conv3d_tc_kernel<<<grid, kNumThreads, c.smem_bytes, (cudaStream_t)stream>>>(xmap, P);
+    CUtensorMap imap = xmap;
+    if (P.nsub > 1) {
+        // 8-byte elements: nb * 16 B = nb * 2 elements (<= 256 per box dimension)
+        const int rows = 9 * (c.kc / 8);
+        cuuint64_t idim[3] = {(cuuint64_t)c.nb * 2, (cuuint64_t)rows, (cuuint64_t)c.nslices * c.nchunks * kd};
+        cuuint64_t istride[2] = {(cuuint64_t)c.nb * 16, (cuuint64_t)c.b_bytes};
+        cuuint32_t ibox[3] = {(cuuint32_t)P.nb * 2, (cuuint32_t)rows, 1};
+        r = encode(&imap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(image), idim, istride, ibox, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        FPL_REQUIRE(r == CUDA_SUCCESS, "fpl_conv3d_tc: cuTensorMapEncodeTiled (weight image) failed (%d)", (int)r);
+    }
+    conv3d_tc_kernel<<<grid, kNumThreads, c.smem_bytes, (cudaStream_t)stream>>>(xmap, imap, P);
     FPL_LAUNCH_CHECK();
     return 0;
 }
