@@ -18,13 +18,25 @@ int grid_for(int64_t items) {
     return (int)(blocks < 1 ? 1 : blocks);
 }
 
+// The reference takes the argmax of the fp32 SOFTMAX PROBABILITIES (scipy.special.softmax = exp(x - max) / sum, then
+// np.argmax: agent_seg.py:1049-1050), not of the logits: two logits closer than the fp32 resolution of their
+// probabilities (|dz| < ~6e-8 around p = 0.5) collapse to a tie that the first index wins.  Same arithmetic here
+// (accurate expf, sequential sum, IEEE division), so labels follow the reference through those ties.
 template <int C>
 __device__ __forceinline__ int argmax_c(const float* z) {
-    int am = 0;
-    float best = z[0];
+    float m = z[0];
 #pragma unroll
-    for (int c = 1; c < C; ++c)
-        if (z[c] > best) { best = z[c]; am = c; }
+    for (int c = 1; c < C; ++c) m = fmaxf(m, z[c]);
+    float e[C], s = 0.0f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { e[c] = expf(z[c] - m); s += e[c]; }
+    int am = 0;
+    float best = __fdiv_rn(e[0], s);
+#pragma unroll
+    for (int c = 1; c < C; ++c) {
+        const float p = __fdiv_rn(e[c], s);
+        if (p > best) { best = p; am = c; }
+    }
     return am;
 }
 

@@ -1,0 +1,153 @@
+"""GPU: the BASELINE.json configurations that are not the bench workload, at their FULL named sizes.
+
+  configs[3]  BraTS-style 2-class DSBN U-Net, 1x128x128x128 patches
+  configs[4]  MMWHS 5-class DSBN U-Net, 1x96x160x160 patches
+  configs[1]  48x256x256 volumes through the filter kernels
+
+The oracle is only asked for what it finishes in seconds at these sizes (one fp32 eval forward of one sample on the
+host cores); the rest is checked through size-independent properties: linearity of backward in the loss scale,
+gradients only where the reference has them, bit-exact labels / agreement weights against numpy, window stitching
+identity."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth
+from oracle.gen_golden import NET_PARAMS
+from tests._util import rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+CFG3 = (dict(NET_PARAMS, class_num=2, dropout=[0.0, 0.0, 0.3, 0.4, 0.5]), (128, 128, 128))
+CFG4 = (dict(NET_PARAMS, class_num=5, dropout=[0.0, 0.0, 0.3, 0.4, 0.5]), (96, 160, 160))
+
+
+def _net(params, seed=1):
+    from fplplus_b200.net import UNet2D5_dsbn
+    net = UNet2D5_dsbn(dict(params))
+    sd = synth.synth_state_dict(params["in_chns"], params["feature_chns"], params["class_num"], params["num_domains"], seed=seed)
+    net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+    return net.to(DEV), sd
+
+
+@pytest.mark.parametrize("cfg", [CFG3, CFG4], ids=["brats_128cube", "mmwhs_96x160x160_5class"])
+def test_full_size_eval_forward_matches_oracle(cfg):
+    """One sample, eval mode (running statistics), against the fp32 CPU oracle: logits rel 1e-2, argmax labels >= 99.9 %
+    on the voxels the tolerance can decide (the untrained synthetic net crowds margins around zero)."""
+    from oracle import unet_dsbn
+    params, shape = cfg
+    net, sd = _net(params)
+    net.eval()
+    x = torch.from_numpy(synth.synth_image(1, 1, shape, seed=21))
+    with torch.no_grad():
+        out = net(x.to(DEV), domain_label=torch.zeros(1, dtype=torch.long)).cpu()
+        ref = unet_dsbn.forward(unet_dsbn.to_torch_state(sd), x, 0, params, bn_training=False)
+    assert out.shape == (1, params["class_num"]) + shape
+    err = rel_l2(out, ref)
+    top2 = ref.topk(2, dim=1).values
+    decided = (top2[:, 0] - top2[:, 1]) > 1e-2 * ref.abs().max()
+    agree = float((out.argmax(1) == ref.argmax(1))[decided].float().mean())
+    print("full-size eval logits rel_l2 %.2e, decided-voxel label agreement %.5f (%.2f of the volume)" %
+          (err, agree, float(decided.float().mean())))
+    assert err < 1e-2
+    assert agree >= 0.999
+
+
+@pytest.mark.parametrize("cfg", [CFG3, CFG4], ids=["brats_128cube", "mmwhs_96x160x160_5class"])
+def test_full_size_train_step_properties(cfg):
+    """Batch 2 train-mode forward + weighted Dice+CE + backward at the named patch size.  Properties: finite loss and
+    gradients; exactly the reference's set of parameters receives gradients (3-D convs, the selected domain's BN, PReLU;
+    never the 2-D twins, 1x1 convs or the other domain's BN); backward is linear in the loss scale; running statistics
+    of the selected domain moved, the other domain's did not."""
+    from fplplus_b200.loss import CombinedLoss
+    from fplplus_b200.registry import loss_dict
+    params, shape = cfg
+    c = params["class_num"]
+    net, sd = _net(params)
+    net.train()
+    crit = CombinedLoss({"loss_type": ["DiceLoss", "CrossEntropyLoss"], "loss_weight": [0.5, 0.5]}, loss_dict)
+    x = torch.from_numpy(synth.synth_image(2, 1, shape, seed=31)).to(DEV)
+    lab = synth.synth_label(2, c, shape, seed=31)
+    y = torch.from_numpy(synth.one_hot(lab, c)).to(DEV)
+    pw = torch.from_numpy(synth.synth_pixel_weight(lab, seed=31)[0]).to(DEV)
+    dom = torch.ones(2, dtype=torch.long)
+
+    def grads(scale):
+        for p in net.parameters():
+            p.grad = None
+        torch.manual_seed(3)                     # same dropout stream
+        out = net(x, domain_label=dom)
+        loss = crit({"prediction": out, "ground_truth": y, "pixel_weight": pw})
+        (loss * scale).backward()
+        torch.cuda.synchronize()
+        return float(loss.detach()), {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
+
+    rm_before = {k: v.clone() for k, v in net.state_dict().items() if "running_mean" in k}
+    loss1, g1 = grads(1.0)
+    assert np.isfinite(loss1) and 0.0 < loss1 < 5.0
+    for k, g in g1.items():
+        assert torch.isfinite(g).all(), k
+        assert "2d" not in k and ".bns.0." not in k, k
+        assert not (k.startswith("up") and (".conv3d." in k and k.count(".") == 2)), k     # the 1x1 convs of bilinear mode
+    assert any(".bns.1.weight" in k for k in g1) and "out_conv.weight" in g1 and "block0.conv.conv3d_1.weight" in g1
+    moved = [k for k, v in net.state_dict().items() if "running_mean" in k and not torch.equal(v, rm_before[k])]
+    assert moved and all(".bns.1." in k for k in moved)
+    # BatchNorm uses batch statistics: the second pass sees the same activations, so gradients scale exactly with the loss
+    loss2, g2 = grads(2.0)
+    assert abs(loss2 - loss1) <= 1e-5 * abs(loss1)
+    assert g1.keys() == g2.keys()
+    for k in g1:
+        scale = float(g1[k].abs().max())
+        if scale == 0.0:
+            assert float(g2[k].abs().max()) == 0.0, k
+            continue
+        # bf16 gradients of the scaled loss round differently: relative to the tensor's scale
+        assert float((g2[k] - 2 * g1[k]).abs().max()) <= 4e-2 * 2 * scale, k
+        assert rel_l2(g2[k], 2 * g1[k]) < 2e-2, k
+
+
+def test_full_size_filter_kernels_bit_exact():
+    """configs[1] volume size (48x256x256): argmax pseudo labels, agreement weights (+ image-weight folding) and the
+    disagreement count bit-exact against the numpy oracle; MC uncertainty statistics within fp32 summation error."""
+    from oracle import fpl_filter
+    from fplplus_b200 import fpl
+    r = np.random.Generator(np.random.PCG64(17))
+    shape = (1, 2, 48, 256, 256)
+    za = (r.standard_normal(shape) * 2).astype(np.float32)
+    zb = (za + r.standard_normal(shape) * 0.7).astype(np.float32)
+    za[0, :, 5, 7, :64] = 0.25                                   # ties: first index wins
+    ta, tb = torch.from_numpy(za).to(DEV), torch.from_numpy(zb).to(DEV)
+    la, lb, w, cnt = fpl.agreement_weight(ta, tb, image_weight=0.42)
+    ra, rb = fpl_filter.pseudo_label(za)[0], fpl_filter.pseudo_label(zb)[0]
+    ga, gb = la.cpu().numpy().reshape(ra.shape), lb.cpu().numpy().reshape(rb.shape)
+    # labels are the argmax of fp32 softmax probabilities on both sides; the only freedom left is the last-ulp rounding of
+    # expf (CUDA vs numpy) for logits inside the ~1e-7 band where probabilities collapse to a tie
+    for got, ref, z in ((ga, ra, za), (gb, rb, zb)):
+        bad = got != ref
+        assert bad.sum() <= 2
+        assert np.all(np.abs(z[0, 0] - z[0, 1])[bad] <= 2e-7)
+    np.testing.assert_array_equal(ga, ra)                       # za has no such voxel besides the planted exact ties
+    ref_w = fpl_filter.agreement_weight(ga, gb)
+    np.testing.assert_array_equal(w.cpu().numpy().reshape(ref_w.shape),
+                                  fpl_filter.set_weight_(np.float32(0.42), ref_w.astype(np.float32)))
+    assert int(cnt) == int((ga != gb).sum())
+    assert np.array_equal(ra[5, 7, :64], np.zeros(64, dtype=ra.dtype))
+
+
+def test_full_size_window_stitching_identity():
+    """Inferer over a 48x256x256 volume with a model that returns a fixed function of the window (its own voxels):
+    the stitched, TTA-averaged result must equal that function of the volume, whatever the window overlap."""
+    from fplplus_b200.inferer import Inferer
+
+    class Toy(torch.nn.Module):
+        def forward(self, x, domain_label=None):
+            return torch.cat([x * 2.0 + 1.0, -x], 1)
+
+    vol = torch.from_numpy(synth.synth_image(1, 1, (48, 256, 256), seed=41)).to(DEV)
+    for stride in ([32, 128, 128], [16, 96, 96]):
+        inf = Inferer({"class_num": 2, "sliding_window_enable": True, "sliding_window_size": [32, 128, 128],
+                       "sliding_window_stride": stride, "tta_mode": 1})
+        out = inf.run(Toy(), vol, torch.zeros(1, dtype=torch.long))
+        want = torch.cat([vol * 2.0 + 1.0, -vol], 1)
+        assert float((out - want).abs().max()) <= 1e-5
