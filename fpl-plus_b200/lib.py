@@ -46,6 +46,8 @@ _SIGNATURES = {
     "fpl_conv3d_tc_dfold_act": (_I, [_P, _I, _I, _P, _P, _I, _I] + [_I] * 6 + [_P, _P, _P, _P]),
     "fpl_conv3d_tc_k311_act": (_I, [_P, _I, _I, _P, _P, _I, _I] + [_I] * 7 + [_P, _P, _P, _P]),
     "fpl_maxpool_c8": (_I, [_P, _I, _I, _P, _I, _I, _I] + [_I] * 5 + [_P]),
+    "fpl_head_fwd": (_I, [_P, _I, _I, _P, _P, _P] + [_I] * 6 + [_P]),
+    "fpl_head_dgrad": (_I, [_P, _P, _P, _I, _I, _P, _I, _I, _P] + [_I] * 6 + [_P]),
     "fpl_grad_scatter_add": (_I, [_P, _P, _P, _I, _I, _P]),
     "fpl_stem_conv_fwd": (_I, [_P, _P, _P, _P, _I, _I, _P] + [_I] * 7 + [_P]),
     "fpl_stem_conv_wgrad": (_I, [_P, _P, _I, _I, _P] + [_I] * 7 + [_P]),

@@ -258,6 +258,12 @@ class UNet2D5_dsbn(nn.Module):
         return (u.cin == 1 and u.kd == 3 and depth >= 2 and u.cout in (16, 32, 64) and ops.is_sm100()
                 and _conv_impl() == "tc" and os.environ.get("FPL_STEM_IMPL", "tc") == "tc")
 
+    def _head_cc(self, n, d):
+        """CUDA-core head kernels (csrc/head.cu): the default for the shipped shapes; FPL_HEAD_IMPL=tc selects the
+        zero-padded tensor-core path."""
+        return (self.ft_chns[0] in (16, 32) and self.n_class <= 8 and d >= 2 and n * d <= 65535 and ops.is_sm100()
+                and os.environ.get("FPL_HEAD_IMPL", "cc") == "cc" and os.environ.get("FPL_CONV_IMPL", "tc") == "tc")
+
     def _head_tc(self):
         return self._use_tc(self.ft_chns[0], 16) and self.n_class <= 8 and os.environ.get("FPL_HEAD_IMPL", "tc") == "tc"
 
@@ -711,7 +717,10 @@ class UNet2D5_dsbn(nn.Module):
             low = a2
         d, h, w = geo[0]
         logits = torch.empty((n, self.n_class, d, h, w), dtype=torch.float32, device=x.device)
-        if self._head_tc():
+        if self._head_cc(n, d):
+            call("fpl_head_fwd", *low.args(), ptr(self.out_conv.weight), ptr(self.out_conv.bias), ptr(logits), n, d, h, w,
+                 ft[0], self.n_class, stream_ptr())
+        elif self._head_tc():
             img = self._weight_image(self._head, 1, False, ws)
             call("fpl_head_conv_tc", *low.args(), ptr(img), ptr(self._head.bias), ptr(logits), n, d, h, w, ft[0],
                  self.n_class, stream_ptr())
@@ -878,7 +887,23 @@ class UNet2D5_dsbn(nn.Module):
         head_in = rec["head_in"]
         g = C8(ws.c8("dX:head", n, d, ft[0], h, w))
         dlogits = dlogits.contiguous()
-        if self._head_tc():
+        if self._head_cc(n, d):
+            # CUDA-core head dgrad (csrc/head.cu): one pass reads the fp32 logit gradient and writes the input gradient,
+            # the one-channel-group bf16 copy the tensor-core wgrad consumes and the bias gradient
+            k = self.n_class
+            dl8 = ws.c8("dL8", n, d, 8, h, w)
+            call("fpl_head_dgrad", ptr(dlogits), ptr(self.out_conv.weight), *g.args(), ptr(dl8), 1, 0,
+                 ptr(grads[self.out_conv.bias]), n, d, h, w, ft[0], k, st)
+            if fold is not None:
+                scr = fold["alloc"](8 * ft[0] * 9)
+                call("fpl_conv3d_wgrad_tc_tapmajor", *head_in.args(), ptr(dl8), 1, 0, ptr(scr), n, d, h, w, ft[0], 8, 1, st)
+                fold["pending"].append((scr, grads[self.out_conv.weight], k, ft[0], 9, 8))
+            else:
+                dw8 = ws.get("dW16", (8, ft[0], 1, 3, 3), torch.float32)
+                dw8.zero_()
+                call("fpl_conv3d_wgrad_tc", *head_in.args(), ptr(dl8), 1, 0, ptr(dw8), n, d, h, w, ft[0], 8, 1, st)
+                grads[self.out_conv.weight].view(k, ft[0], 1, 3, 3).add_(dw8[:k])
+        elif self._head_tc():
             # dlogits -> bf16 C8-planar (zero padded to 16 channels) + the bias gradient; then the ordinary
             # tensor-core dgrad / wgrad with the padded head weights
             k = self.n_class

@@ -143,6 +143,17 @@ int fpl_conv3d_tc_k311_act(const void* x, int x_c8tot, int x_c8off, const void* 
 int fpl_maxpool_c8(const void* a, int a_c8tot, int a_c8off, void* pooled, int p_c8tot, int p_c8off, int pool_kd,
                    int n, int d, int h, int w, int c, void* stream);
 
+/* The (1,3,3) output conv (unet2d5_dsbn.py:301-308) on CUDA cores, one thread per voxel (csrc/head.cu); cin = 16 or 32,
+ * class_num <= 8, w fp32 [classes][cin][1][3][3].
+ * fpl_head_fwd  : logits fp32 NCDHW = conv(x) + bias.
+ * fpl_head_dgrad: g = gradient wrt x (C8-planar bf16) from dlogits fp32 NCDHW; the same pass writes dl8 (may be NULL), the
+ *                 bf16 copy of dlogits with the classes padded to one channel group that the tensor-core wgrad reads, and
+ *                 ACCUMULATES the bias gradient dbias[classes] (may be NULL). */
+int fpl_head_fwd(const void* x, int x_c8tot, int x_c8off, const float* w, const float* bias, float* logits, int n, int d,
+                 int h, int w_, int cin, int classes, void* stream);
+int fpl_head_dgrad(const float* dlogits, const float* w, void* g, int g_c8tot, int g_c8off, void* dl8, int dl_c8tot,
+                   int dl_c8off, float* dbias, int n, int d, int h, int w_, int cin, int classes, void* stream);
+
 /* stem: image fp32 NCDHW (in_chns <= 8) -> C8-planar bf16, conv k3 p1 + bias + stats. */
 int fpl_stem_conv_fwd(const float* x, const float* w, const float* bias, void* y, int y_c8tot, int y_c8off,
                       double* stats, int n, int cin, int d, int h, int w_, int cout, int kd, void* stream);

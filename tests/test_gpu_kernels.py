@@ -746,3 +746,33 @@ def test_conv3d_wgrad_tc_k133_depth_stacked(cin, cout, shape):
     _call("fpl_conv3d_wgrad_tc", _p(to_c8(x.to(DEV))), cin // 8, 0, _p(dyb), (cout + 16) // 8, 0, _p(dw), n, d, h, w, cin, cout,
           1, _st())
     assert max_rel(dw.cpu(), wt.grad) < 1e-4
+
+
+@pytest.mark.parametrize("cin,classes,shape", [(16, 2, (2, 3, 12, 40)), (16, 5, (1, 2, 9, 33)), (32, 2, (1, 4, 16, 32)),
+                                               (32, 8, (1, 2, 8, 70)), (16, 3, (1, 2, 5, 7))])
+def test_head_cuda_core_fwd_and_dgrad(cin, classes, shape):
+    """csrc/head.cu against torch's (1,3,3) conv on the bf16-rounded activation: fp32 logits; input gradient (bf16),
+    the one-channel-group bf16 copy of the logit gradient and the ACCUMULATED bias gradient from one dgrad pass."""
+    n, d, h, w = shape
+    x = bf16_round(randn(401, n, cin, d, h, w)).requires_grad_(True)
+    wt = randn(402, classes, cin, 1, 3, 3, scale=0.2).requires_grad_(True)
+    b = randn(403, classes, scale=0.1).requires_grad_(True)
+    ref = F.conv3d(x, wt, b, padding=(0, 1, 1))
+    dl = randn(404, *ref.shape)
+    ref.backward(dl)
+    xb = to_c8(torch.cat([x.detach(), randn(405, n, 8, d, h, w)], 1).to(DEV))            # a slice of a wider buffer
+    logits = torch.empty(ref.shape, device=DEV)
+    _call("fpl_head_fwd", _p(xb), (cin + 8) // 8, 0, _p(wt.detach().to(DEV)), _p(b.detach().to(DEV)), _p(logits), n, d, h, w, cin,
+          classes, _st())
+    np.testing.assert_allclose(logits.cpu().numpy(), ref.detach().numpy(), rtol=2e-5, atol=2e-5)
+    g = torch.zeros((n, d, cin // 8 + 1, h, w, 8), dtype=torch.bfloat16, device=DEV)
+    dl8 = torch.zeros((n, d, 1, h, w, 8), dtype=torch.bfloat16, device=DEV)
+    db = torch.ones(classes, device=DEV)
+    _call("fpl_head_dgrad", _p(dl.to(DEV)), _p(wt.detach().to(DEV)), _p(g), cin // 8 + 1, 1, _p(dl8), 1, 0, _p(db), n, d, h, w, cin,
+          classes, _st())
+    got = from_c8(g).cpu()
+    assert torch.all(got[:, :8] == 0)                                                     # the neighbouring group is untouched
+    assert max_rel(got[:, 8:], x.grad) < 6e-3
+    copy = from_c8(dl8).cpu()
+    assert torch.equal(copy[:, :classes], bf16_round(dl)) and torch.all(copy[:, classes:] == 0)
+    np.testing.assert_allclose(db.cpu().numpy() - 1.0, b.grad.numpy(), rtol=1e-4, atol=1e-4)
