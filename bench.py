@@ -372,7 +372,7 @@ def run_ours(args):
                                     "peak_tflops": pk["bf16_tflops_sustained"]},
                "pl_filter": pl}
         if not args.skip_cpu:
-            out["cpu_baseline"] = cpu_baseline(bounded_steps=2)
+            out["cpu_baseline"] = cpu_baseline(bounded_steps=12)
     if out is not None:
         print(json.dumps(out), flush=True)
     if world > 1:
