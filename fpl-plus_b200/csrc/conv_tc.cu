@@ -446,8 +446,10 @@ extern "C" int fpl_conv3d_prep_weight_batch(int count, const float* const* h_w, 
         B.total[e] = c.nslices * c.nchunks * h_kd[e] * c.b_bytes / 2;
         if (B.total[e] > max_total) max_total = B.total[e];
     }
+    // one thread per 1-7 image elements: the gather from the PyTorch layout is latency bound, so the largest layers
+    // (1.77 M elements) want thousands of threads in flight; blocks beyond a small layer's size exit at once
     int bx = (max_total + 255) / 256;
-    if (bx > 64) bx = 64;
+    if (bx > 512) bx = 512;
     prep_weight_batch_kernel<<<dim3(bx, count), 256, 0, (cudaStream_t)stream>>>(B);
     FPL_LAUNCH_CHECK();
     return 0;
