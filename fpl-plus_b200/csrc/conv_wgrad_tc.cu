@@ -20,7 +20,7 @@
 namespace {
 
 // debug / tuning knobs (fpl_debug_set keys 10..16)
-int g_wg_swap = 0, g_wg_allow_m64 = 1, g_wg_m64_quadrant = 1, g_wg_allow_pair = 1, g_wg_force_tw = 0, g_wg_tiles_per_cta = 4, g_wg_skip_epilogue = 0;
+int g_wg_swap = 0, g_wg_allow_m64 = 1, g_wg_m64_quadrant = 1, g_wg_allow_pair = 1, g_wg_force_tw = 0, g_wg_tiles_per_cta = 2, g_wg_skip_epilogue = 0;
 
 constexpr int kThreadsW = 192;
 constexpr int kMaxStagesW = 8;
@@ -342,7 +342,7 @@ static int wgrad_tc_launch(const void* x, int x_c8tot, int x_c8off, const void* 
     FPL_REQUIRE(tiles < (1ll << 30), "fpl_conv3d_wgrad_tc: too many tiles");
     P.tiles_total = (int)tiles;
     const int pairs = c.mtiles_kd * c.mtiles_c * c.nchunks;
-    // split-K over voxel tiles: every CTA ends with 9*128*N atomics into dW, so a slice should own >= 8 tiles
+    // split-K over voxel tiles: every CTA ends with 9*128*N atomics into dW, so a slice should own >= 2 tiles (measured: tools/wgrad_tune.py)
     // (deep levels: few tiles, many (M,N) pairs -> split 1; full resolution: one CTA per SM)
     int split = FPL_NUM_SMS / pairs;
     if (split > P.tiles_total / g_wg_tiles_per_cta) split = P.tiles_total / g_wg_tiles_per_cta;

@@ -34,7 +34,7 @@ def t(cin, cout, kd, shape, knobs):
     return e0.elapsed_time(e1) / 5 * 1e3
 
 
-variants = [("base", {17: 0, 18: 1}), ("noepi", {17: 1, 18: 1}), ("nodirect", {17: 0, 18: 0})]
+variants = [("tiles4", {16: 4, 17: 0}), ("tiles2", {16: 2, 17: 0}), ("tiles1", {16: 1, 17: 0}), ("tiles8", {16: 8, 17: 0})]
 FN = os.environ.get("FN", "fpl_conv3d_wgrad_tc_tapmajor")
 print("%-28s" % "shape" + "".join("%12s" % v[0] for v in variants))
 for cin, cout, kd, shape in SHAPES:
