@@ -121,6 +121,10 @@ def set_call_timer(fn):
 #: profiling only (tools/marginal_cost.sh): entry points named in FPL_DEBUG_SKIP are not launched, which shows what a
 #: kernel class costs in the overlapped schedule of the real step.  Results are WRONG with it set; never set it otherwise.
 _debug_skip = frozenset(n for n in os.environ.get("FPL_DEBUG_SKIP", "").split(",") if n)
+if _debug_skip:
+    import sys as _sys
+    print("fplplus_b200: FPL_DEBUG_SKIP is set -- %d entry points are NOT launched; results are wrong (profiling only)"
+          % len(_debug_skip), file=_sys.stderr)
 
 
 def call(name, *args):
