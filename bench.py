@@ -146,6 +146,22 @@ WORK = {   # entry point -> (flops, algorithmic bytes) from its argument tuple
 }
 
 
+def _dsbn_work(bytes_per_elem, lo, hi):
+    def f(a):
+        n, d, h, w, c = a[lo:hi]
+        return 0.0, float(n) * d * h * w * c * bytes_per_elem
+    return f
+
+
+# HBM-bound kernels: algorithmic bytes per element of DESIGN.md section 3 (bf16 activations)
+WORK.update({
+    "fpl_dsbn_bn_act_fwd": _dsbn_work(4, -6, -1),            # read y, write a
+    "fpl_dsbn_act_bwd_reduce": _dsbn_work(4, -6, -1),        # read y, g
+    "fpl_dsbn_act_bwd_apply_fin": _dsbn_work(6, -10, -5),    # read y, g, write dy
+})
+HBM_KERNELS = ("fpl_dsbn_bn_act_fwd", "fpl_dsbn_act_bwd_reduce", "fpl_dsbn_act_bwd_apply_fin")
+
+
 def measured_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, averaged over the launches of one train step,
     from the committed `ncu --set full` capture (profiles/roofline_traffic.json, written by tools/ncu_traffic.py)."""
@@ -328,7 +344,7 @@ def run_ours(args):
     kern = {k: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps,
                 "share_of_step": v[1] / args.steps / eager_step_ms} for k, v in agg.items()}
     roofline = None
-    conv = {k: v for k, v in agg.items() if k in WORK and v[1] > 0}
+    conv = {k: v for k, v in agg.items() if k in WORK and v[1] > 0 and v[2] > 0}
     if conv:
         top = max(conv, key=lambda k: conv[k][1])
         n, tot_ms, fl, by = conv[top]
@@ -340,6 +356,17 @@ def run_ours(args):
                     "launches_per_step": n / args.steps, "avg_launch_ms": tot_ms / n,
                     "algorithmic_gflop_per_launch": fl / n / 1e9, "algorithmic_mb_per_launch": by / n / 1e6,
                     "hbm_gbs_at_algorithmic_bytes": by / (tot_ms / 1e3) / 1e9}
+    # HBM-bound kernels: GB/s at the algorithmic bytes, over all layers of the step and for the largest layer alone
+    hbm = {}
+    for name in HBM_KERNELS:
+        recs = [(by, e0.elapsed_time(e1)) for nm, (fl, by), e0, e1 in timer.records if nm == name and by > 0]
+        if recs:
+            big = max(b for b, _ in recs)
+            tb = [t for b, t in recs if b == big]
+            hbm[name] = {"gbs_all_layers": sum(b for b, _ in recs) / (sum(t for _, t in recs) / 1e3) / 1e9,
+                         "gbs_largest_layer": big / (sum(tb) / len(tb) / 1e3) / 1e9,
+                         "frac_of_hbm_peak_largest_layer": big / (sum(tb) / len(tb) / 1e3) / 1e9 / pk["hbm_gbs"],
+                         "largest_layer_mb": big / 1e6}
     lib.set_call_timer(None)
 
     # ---- configs[1]: filtered-pseudo-label pass, volumes sharded over ranks, no communication ----
@@ -367,6 +394,7 @@ def run_ours(args):
                "host_enqueue_ms_per_step": host_ms, "eager_ms_per_step": eager_step_ms,
                "clocks": clk,
                "roofline": roofline,
+               "hbm_kernels": hbm,
                "kernels": kern,
                "conv_tensor_util": {"achieved_tflops_over_step": world * 2 * BATCH * 179.9e9 / (step_ms / 1e3) / 1e12 / world,
                                     "peak_tflops": pk["bf16_tflops_sustained"]},
