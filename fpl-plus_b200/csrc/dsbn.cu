@@ -148,63 +148,76 @@ __device__ __forceinline__ uint32_t keep_bits(const uint2* mask, uint64_t seed, 
     return dropout_keep8(seed, offset, (uint64_t)vec, p);
 }
 
-// grid: (chunks of H*W, N*D*C8 planes): a block stays inside one channel group, so the affine
-// parameters are loaded once and the index math is 32-bit
-__global__ void __launch_bounds__(kThreads) dsbn_act_fwd_kernel(ActParams P) {
+// grid: (blocks per channel group, C8).  A block stays inside one channel group (its affine parameters, derived once in
+// the prologue, live in registers) and walks over work items = (plane (n,d), chunk of 2*256 vectors), two vectors per
+// thread in flight, with stepped plane pointers (same structure as dsbn_act_bwd_kernel below).
+__global__ void __launch_bounds__(kThreads) dsbn_act_fwd_kernel(const __grid_constant__ ActParams P) {
     const int HW = P.H * P.W;
-    const int plane = blockIdx.y;
-    const int c8 = plane % P.C8;
-    const int nd = plane / P.C8;
+    const int c8 = blockIdx.y;
     const float slope = __ldg(P.slope);
     const bool drop = P.drop_p > 0.0f;
     const float keep_scale = drop ? 1.0f / (1.0f - P.drop_p) : 1.0f;
     const uint64_t seed = P.seed + (P.seed_dev != nullptr ? (uint64_t)__ldg(P.seed_dev) : 0ull);
     float sc[8], sh[8];
-    if (P.fin.enabled) bn_prologue(P.fin, P.C8 * 8, c8, blockIdx.x == 0 && nd == 0, sc, sh);
+    if (P.fin.enabled) bn_prologue(P.fin, P.C8 * 8, c8, blockIdx.x == 0, sc, sh);
     else load_affine(P.scale, P.shift, c8, sc, sh);
-    const bf16x8* src = P.y + (int64_t)plane * HW;
-    bf16x8* dst = P.a + ((int64_t)nd * P.a_c8tot + P.a_c8off + c8) * HW;
-    const int stride = gridDim.x * blockDim.x;
-    for (int hw = blockIdx.x * blockDim.x + threadIdx.x; hw < HW; hw += 2 * stride) {
-        const int hw2 = hw + stride;
-        const bool two = hw2 < HW;
-        int4 r0 = ld_stream16(src + hw), r1 = make_int4(0, 0, 0, 0);
-        if (two) r1 = ld_stream16(src + hw2);
+    const int chunks = (HW + 2 * kThreads - 1) / (2 * kThreads);
+    const int items = P.N * P.D * chunks;
+    const int step_nd = gridDim.x / chunks, step_ch = gridDim.x - step_nd * chunks;
+    int nd = blockIdx.x / chunks, ch = blockIdx.x - nd * chunks;
+    const int64_t y_stride = (int64_t)P.C8 * HW, a_stride = (int64_t)P.a_c8tot * HW;
+    const bf16x8* src = P.y + ((int64_t)nd * P.C8 + c8) * HW + threadIdx.x;
+    bf16x8* dst = P.a + ((int64_t)nd * P.a_c8tot + P.a_c8off + c8) * HW + threadIdx.x;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int voff = ch * (2 * kThreads);
+        const int hw = voff + (int)threadIdx.x, hw2 = hw + kThreads;
+        const bool one = hw < HW, two = hw2 < HW;
+        int4 r0 = make_int4(0, 0, 0, 0), r1 = make_int4(0, 0, 0, 0);
+        if (one) r0 = ld_stream16(src + voff);
+        if (two) r1 = ld_stream16(src + voff + kThreads);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            if (k == 1 && !two) break;
-            const int h = k == 0 ? hw : hw2;
+            if (!(k == 0 ? one : two)) continue;
             float f[8];
             bf16x8_to_float(*reinterpret_cast<bf16x8*>(k == 0 ? &r0 : &r1), f);
-            uint32_t keep = drop ? keep_bits(P.drop_mask, seed, P.offset, (int64_t)plane * HW + h, P.drop_p) : 0xffu;
+            uint32_t keep = 0xffu;
+            if (drop) keep = keep_bits(P.drop_mask, seed, P.offset, (src - P.y) + voff + k * kThreads, P.drop_p);   // dense index of this vector
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 float z = fmaf(f[i], sc[i], sh[i]);
                 float a = z > 0.0f ? z : slope * z;
                 f[i] = ((keep >> i) & 1u) ? a * keep_scale : 0.0f;
             }
-            st_bf16x8(dst + h, f);
+            st_bf16x8(dst + voff + k * kThreads, f);
         }
+        int dnd = step_nd;
+        ch += step_ch;
+        if (ch >= chunks) { ch -= chunks; ++dnd; }
+        src += dnd * y_stride;
+        dst += dnd * a_stride;
     }
 }
 
 // one thread per pooled output vector; reads the 2x2x2 (or 1x2x2) window, writes the full
 // resolution activations, the pooled max and the 3-bit argmax code (first max wins, scan
 // order d,h,w as in torch's max_pool3d).
-// grid: (chunks of H2*W2, N*D2*C8 pooled planes)
-__global__ void __launch_bounds__(kThreads) dsbn_act_pool_fwd_kernel(ActParams P) {
+// grid: (blocks per channel group, C8); work items = (pooled plane (n,d2), chunk of 256 pooled vectors)
+__global__ void __launch_bounds__(kThreads) dsbn_act_pool_fwd_kernel(const __grid_constant__ ActParams P) {
     const int kd = P.pool_kd;
     const int D2 = P.D / kd, H2 = P.H / 2, W2 = P.W / 2;
     const int HW = P.H * P.W, HW2 = H2 * W2;
-    const int pplane = blockIdx.y;
-    const int c8 = pplane % P.C8;
-    const int nd2 = pplane / P.C8;
-    const int d2 = nd2 % D2, n = nd2 / D2;
+    const int c8 = blockIdx.y;
     const float slope = __ldg(P.slope);
     float sc[8], sh[8];
-    if (P.fin.enabled) bn_prologue(P.fin, P.C8 * 8, c8, blockIdx.x == 0 && nd2 == 0, sc, sh);
+    if (P.fin.enabled) bn_prologue(P.fin, P.C8 * 8, c8, blockIdx.x == 0, sc, sh);
     else load_affine(P.scale, P.shift, c8, sc, sh);
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < HW2; v += gridDim.x * blockDim.x) {
+    const int chunks = (HW2 + kThreads - 1) / kThreads;
+    const int items = P.N * D2 * chunks;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int nd2 = item / chunks;
+        const int v = (item - nd2 * chunks) * kThreads + (int)threadIdx.x;
+        if (v >= HW2) continue;
+        const int n = nd2 / D2, d2 = nd2 - n * D2;
         const int h2 = v / W2, w2 = v - h2 * W2;
         float best[8];
         uint32_t code[8];
@@ -246,7 +259,7 @@ __global__ void __launch_bounds__(kThreads) dsbn_act_pool_fwd_kernel(ActParams P
         uint2 packed;
         packed.x = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
         packed.y = code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24);
-        P.pool_idx[(int64_t)pplane * HW2 + v] = packed;
+        P.pool_idx[((int64_t)nd2 * P.C8 + c8) * HW2 + v] = packed;
     }
 }
 
@@ -517,22 +530,25 @@ static int act_fwd_launch(const BnFinalize* fin, const void* y, const float* sca
     P.pool_kd = pool_kd; P.drop_p = drop_p; P.drop_mask = (const uint2*)drop_mask; P.seed = seed; P.offset = offset;
     P.seed_dev = (const unsigned long long*)seed_dev;
     P.N = n; P.D = d; P.C8 = c / 8; P.H = h; P.W = w;
+    const int c8 = c / 8;
     if (pooled != nullptr) {
         FPL_REQUIRE(pool_kd == 1 || pool_kd == 2, "fpl_dsbn_act_fwd: pool_kd must be 1 or 2");
         FPL_REQUIRE(h % 2 == 0 && w % 2 == 0 && d % pool_kd == 0, "fpl_dsbn_act_fwd: pooled dims must be even");
         FPL_REQUIRE(drop_p == 0.0f, "fpl_dsbn_act_fwd: dropout is not combined with pooling");
         FPL_REQUIRE(pool_idx != nullptr, "fpl_dsbn_act_fwd: pool_idx required");
-        int64_t planes = (int64_t)n * (d / pool_kd) * (c / 8);
-        FPL_REQUIRE(planes <= 65535, "fpl_dsbn_act_fwd: too many planes (%lld)", (long long)planes);
-        int hw2 = (h / 2) * (w / 2);
-        dim3 grid((hw2 + kThreads - 1) / kThreads, (unsigned)planes);
-        dsbn_act_pool_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(P);
+        const int64_t hw2 = (int64_t)(h / 2) * (w / 2);
+        const int64_t items = (int64_t)n * (d / pool_kd) * ((hw2 + kThreads - 1) / kThreads);
+        int64_t bx = (FPL_NUM_SMS * 8 + c8 - 1) / c8;
+        if (bx > items) bx = items;
+        if (bx < 1) bx = 1;
+        dsbn_act_pool_fwd_kernel<<<dim3((unsigned)bx, (unsigned)c8), kThreads, 0, (cudaStream_t)stream>>>(P);
     } else {
-        int64_t planes = (int64_t)n * d * (c / 8);
-        FPL_REQUIRE(planes <= 65535, "fpl_dsbn_act_fwd: too many planes (%lld)", (long long)planes);
-        int chunks = (h * w + kThreads * 4 - 1) / (kThreads * 4);
-        dim3 grid(chunks < 1 ? 1 : chunks, (unsigned)planes);
-        dsbn_act_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(P);
+        const int64_t hw = (int64_t)h * w;
+        const int64_t items = (int64_t)n * d * ((hw + 2 * kThreads - 1) / (2 * kThreads));
+        int64_t bx = (FPL_NUM_SMS * 8 + c8 - 1) / c8;
+        if (bx > items) bx = items;
+        if (bx < 1) bx = 1;
+        dsbn_act_fwd_kernel<<<dim3((unsigned)bx, (unsigned)c8), kThreads, 0, (cudaStream_t)stream>>>(P);
     }
     FPL_LAUNCH_CHECK();
     return 0;
