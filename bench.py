@@ -446,7 +446,7 @@ def bench_filter(agent, rank, world, barrier, max_over_ranks, args):
             for m in net.modules():
                 if type(m) == nn.Dropout:
                     m.train()
-            passes = [inferer.run(net, tgt, 1 * one) for _ in range(6)]
+            passes = inferer.run(net, tgt, 1 * one, mc_passes=6)
             stats, _ = fpl.mc_uncertainty(passes)
             lab_host = la.cpu()                         # what leaves the GPU: u8 labels, fp32 weights, 2 scalars
             w_host = w.cpu()

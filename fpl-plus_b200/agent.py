@@ -779,7 +779,11 @@ class SegmentationAgent(object):
                 name = names[0] if isinstance(names, (list, tuple)) else names
                 dl = domain * torch.ones(images.shape[0], dtype=torch.long)
                 if self.FPL:
-                    passes = [self.inferer.run(self.net, images, domain_label=dl) for _ in range(k_passes)]
+                    # the K MC-dropout passes in one sweep: their dropout-free encoder levels are computed once
+                    if k_passes > 1 and hasattr(self.net, "forward_mc") and isinstance(self.inferer, Inferer):
+                        passes = self.inferer.run(self.net, images, dl, mc_passes=k_passes)
+                    else:
+                        passes = [self.inferer.run(self.net, images, domain_label=dl) for _ in range(k_passes)]
                     stats, _ = fpl.mc_uncertainty(passes)
                     pending.append((name, stats))          # stays on the device until the loop ends
                 else:

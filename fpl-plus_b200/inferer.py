@@ -51,22 +51,29 @@ class Inferer(object):
                     starts.append((min(d, img_shape[0] - win[0]), h0, w0))
         return starts, win
 
-    def _model(self, x, domain_label, lane=None):
+    def _model(self, x, domain_label, lane=None, repeats=1):
+        """Returns a list of ``repeats`` outputs (MC-dropout passes of the same input share their dropout-free
+        encoder prefix through ``forward_mc`` when the model offers it)."""
+        if repeats > 1:
+            if hasattr(self.model, "forward_mc"):
+                return self.model.forward_mc(x, domain_label, repeats, graph_lane=0 if lane is None else lane)
+            return [self._model(x, domain_label, lane)[0] for _ in range(repeats)]
         if lane is None:
             out = self.model(x, domain_label=domain_label)
         else:
             out = self.model(x, domain_label=domain_label, graph_lane=lane)
         if isinstance(out, (tuple, list)):
             out = out[0]
-        return out
+        return [out]
 
     def _two_lanes(self, model):
         """The fplplus_b200 network accepts ``graph_lane``: two half-batches of windows can then run concurrently
         on two streams (tensor-pipe-bound convolutions of one under the HBM-bound BatchNorm kernels of the other)."""
         return self.config.get('window_two_streams', True) and hasattr(model, "_forward_graphed") and model.cuda_graphs
 
-    def _infer(self, image, domain_label, result, scale, flip_h, flip_w):
-        """result += scale * unflip(sliding_window(model, image))."""
+    def _infer(self, image, domain_label, results, scale, flip_h, flip_w):
+        """results[k] += scale * unflip(sliding_window(model, image)) for each of the len(results) MC passes."""
+        K = len(results)
         b, _cin, vd, vh, vw = image.shape
         class_num = self.config['class_num']
         st = stream_ptr()
@@ -74,11 +81,13 @@ class Inferer(object):
         if self.config.get('sliding_window_enable', False):
             starts, win = self._windows([vd, vh, vw])
         if starts is None:
-            out = self._model(image, domain_label).float().contiguous()
-            call("fpl_window_accumulate", ptr(out), ptr(result), None, b, out.shape[1], vd, vh, vw, 0, 0, 0,
-                 vd, vh, vw, flip_h, flip_w, scale, st)
+            for k, out in enumerate(self._model(image, domain_label, None, K)):
+                out = out.float().contiguous()
+                call("fpl_window_accumulate", ptr(out), ptr(results[k]), None, b, out.shape[1], vd, vh, vw, 0, 0, 0,
+                     vd, vh, vw, flip_h, flip_w, scale, st)
             return
-        acc = torch.zeros((b, class_num, vd, vh, vw), dtype=torch.float32, device=image.device)
+        accs = [torch.zeros((b, class_num, vd, vh, vw), dtype=torch.float32, device=image.device) for _ in range(K)]
+        acc = accs[0]
         cnt = torch.zeros_like(acc)
         batched = _bn_in_eval(self.model)
         group = max(1, self.max_batch // b) if batched else 1
@@ -88,7 +97,7 @@ class Inferer(object):
             if self._side is None:
                 self._side = torch.cuda.Stream()
             # each lane accumulates into its own volume (windows of the two lanes may overlap): deterministic sums
-            acc1, cnt1 = torch.zeros_like(acc), torch.zeros_like(cnt)
+            accs1, cnt1 = [torch.zeros_like(acc) for _ in range(K)], torch.zeros_like(cnt)
             self._side.wait_stream(main)
             group = max(1, group // 2)
         lane = 0
@@ -99,24 +108,30 @@ class Inferer(object):
                 patches = [image[:, :, d0:d0 + win[0], h0:h0 + win[1], w0:w0 + win[2]] for d0, h0, w0 in chunk]
                 x = torch.cat(patches, 0).contiguous() if len(patches) > 1 else patches[0].contiguous()
                 dl = domain_label if len(chunk) == 1 else domain_label.repeat(len(chunk))
-                out = self._model(x, dl, lane if two else None).float().contiguous()
+                outs = self._model(x, dl, lane if two else None, K)
                 sp = ctypes.c_void_p(stream.cuda_stream)
-                a_, c_ = (acc1, cnt1) if (two and lane == 1) else (acc, cnt)
-                for j, (d0, h0, w0) in enumerate(chunk):
-                    call("fpl_window_accumulate", ptr(out[j * b:(j + 1) * b]), ptr(a_), ptr(c_), b, class_num, vd, vh, vw,
-                         d0, h0, w0, win[0], win[1], win[2], 0, 0, 1.0, sp)
+                as_, c_ = (accs1, cnt1) if (two and lane == 1) else (accs, cnt)
+                for k, out in enumerate(outs):
+                    out = out.float().contiguous()
+                    for j, (d0, h0, w0) in enumerate(chunk):
+                        # the visit count is the same for every pass: accumulated with pass 0 only
+                        call("fpl_window_accumulate", ptr(out[j * b:(j + 1) * b]), ptr(as_[k]), ptr(c_) if k == 0 else None, b,
+                             class_num, vd, vh, vw, d0, h0, w0, win[0], win[1], win[2], 0, 0, 1.0, sp)
             if two:
                 lane ^= 1
         if two:
             main.wait_stream(self._side)
-            acc.add_(acc1)
+            for k in range(K):
+                accs[k].add_(accs1[k])
             cnt.add_(cnt1)
-        call("fpl_window_normalize", ptr(acc), ptr(cnt), 1.0, acc.numel(), st)
-        call("fpl_window_accumulate", ptr(acc), ptr(result), None, b, class_num, vd, vh, vw, 0, 0, 0, vd, vh, vw,
-             flip_h, flip_w, scale, st)
+        for k in range(K):
+            call("fpl_window_normalize", ptr(accs[k]), ptr(cnt), 1.0, acc.numel(), st)
+            call("fpl_window_accumulate", ptr(accs[k]), ptr(results[k]), None, b, class_num, vd, vh, vw, 0, 0, 0, vd, vh, vw,
+                 flip_h, flip_w, scale, st)
 
-    def run(self, model, image, domain_label):
-        """Logits [B,class_num,D,H,W] on ``image.device`` (infer_func.py:188-222)."""
+    def run(self, model, image, domain_label, mc_passes=1):
+        """Logits [B,class_num,D,H,W] on ``image.device`` (infer_func.py:188-222).  ``mc_passes`` = K > 1: the K
+        MC-dropout passes of agent_seg.py:897-911 over the same volume in one sweep (a list of K logits volumes)."""
         self.model = model
         tta_mode = self.config.get('tta_mode', 0)
         if tta_mode not in (0, 1):
@@ -124,12 +139,13 @@ class Inferer(object):
         image = image.float()
         b, _c, vd, vh, vw = image.shape
         class_num = self.config['class_num']
-        result = torch.zeros((b, class_num, vd, vh, vw), dtype=torch.float32, device=image.device)
+        results = [torch.zeros((b, class_num, vd, vh, vw), dtype=torch.float32, device=image.device)
+                   for _ in range(max(1, int(mc_passes)))]
         if tta_mode == 0:
-            self._infer(image, domain_label, result, 1.0, 0, 0)
+            self._infer(image, domain_label, results, 1.0, 0, 0)
         else:
-            self._infer(image, domain_label, result, 0.25, 0, 0)
-            self._infer(torch.flip(image, [-2]), domain_label, result, 0.25, 1, 0)
-            self._infer(torch.flip(image, [-1]), domain_label, result, 0.25, 0, 1)
-            self._infer(torch.flip(image, [-2, -1]), domain_label, result, 0.25, 1, 1)
-        return result
+            self._infer(image, domain_label, results, 0.25, 0, 0)
+            self._infer(torch.flip(image, [-2]), domain_label, results, 0.25, 1, 0)
+            self._infer(torch.flip(image, [-1]), domain_label, results, 0.25, 0, 1)
+            self._infer(torch.flip(image, [-2, -1]), domain_label, results, 0.25, 1, 1)
+        return results if mc_passes > 1 else results[0]

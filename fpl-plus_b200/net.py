@@ -287,7 +287,19 @@ class UNet2D5_dsbn(nn.Module):
         return out
 
     # -- public forward ---------------------------------------------------------------------
-    def forward(self, x, domain_label=None, graph_lane=0):
+    def forward_mc(self, x, domain_label, repeats, graph_lane=0):
+        """K = ``repeats`` MC-dropout forwards of the SAME input in one call (no-grad): returns a list of K logits tensors,
+        bit-identical to K consecutive ``forward`` calls (same seeds from torch's CPU generator), with the dropout-free
+        encoder prefix computed once (agent_seg.py:897-911 runs K full passes; their first levels are identical)."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise RuntimeError("forward_mc is an inference call: wrap it in torch.no_grad()")
+        if not 1 <= repeats <= self.kMaxMcRepeats:
+            raise ValueError("repeats must be in [1, %d]" % self.kMaxMcRepeats)
+        if repeats == 1:
+            return [self.forward(x, domain_label, graph_lane)]
+        return self.forward(x, domain_label, graph_lane, _repeats=repeats)
+
+    def forward(self, x, domain_label=None, graph_lane=0, _repeats=1):
         """``graph_lane``: callers that run several no-grad forwards CONCURRENTLY on different streams (the
         Inferer's two half-batches) give each its own lane, i.e. its own captured graph and static buffers."""
         if domain_label is None:
@@ -307,11 +319,11 @@ class UNet2D5_dsbn(nn.Module):
         if need_grad:
             return _UNetFunction.apply(self, domain, x, *params)
         if self.cuda_graphs and not torch.cuda.is_current_stream_capturing():
-            return self._forward_graphed(x, domain, graph_lane)
+            return self._forward_graphed(x, domain, graph_lane, _repeats)
         ws = self._infer_ws
         if ws is None or ws.device != x.device:
             ws = self._infer_ws = _Workspace(x.device)
-        logits, _ = self._run_forward(x, domain, ws)
+        logits, _ = self._run_forward(x, domain, ws, _repeats)
         return logits
 
     # -- no-grad forwards replayed from CUDA graphs (sliding-window inference: 256 forwards / volume) --
@@ -324,12 +336,14 @@ class UNet2D5_dsbn(nn.Module):
                     sig.append(u.dropout.training and u.dropout.p > 0.0)
         return tuple(sig)
 
+    kMaxMcRepeats = 16      # seeds per graph lane: entry 0 is the ordinary dropout seed, 0..K-1 those of forward_mc
+
     def ensure_rng(self, device, lane=0):
         """The device-side dropout seed of a graph lane (must exist BEFORE a capture so that no allocation /
         zero-fill of it is recorded into the graph).  Lane 0 is also ``self._rng_dev`` (training graphs)."""
         t = self._rng_lanes.get(lane)
         if t is None or t.device != torch.device(device):
-            t = self._rng_lanes[lane] = torch.zeros(1, dtype=torch.int64, device=device)
+            t = self._rng_lanes[lane] = torch.zeros(self.kMaxMcRepeats, dtype=torch.int64, device=device)
         if lane == 0:
             self._rng_dev = t
         return t
@@ -338,8 +352,8 @@ class UNet2D5_dsbn(nn.Module):
         # torch's CPU generator, so torch.manual_seed makes MC-dropout passes reproducible
         return int(torch.empty((), dtype=torch.int64).random_().item()) & ((1 << 62) - 1)
 
-    def _forward_graphed(self, x, domain, lane=0):
-        key = (tuple(x.shape), domain, x.device.index, self._mode_signature(domain), lane)
+    def _forward_graphed(self, x, domain, lane=0, repeats=1):
+        key = (tuple(x.shape), domain, x.device.index, self._mode_signature(domain), lane, repeats)
         ent = self._graphs.get(key)
         if ent is None:
             # first sight of this (shape, domain, mode): run eagerly (also warms lazy driver state), capture next time
@@ -349,7 +363,7 @@ class UNet2D5_dsbn(nn.Module):
             ws = self._infer_wss.get(lane)
             if ws is None or ws.device != x.device:
                 ws = self._infer_wss[lane] = _Workspace(x.device)
-            logits, _ = self._run_forward(x, domain, ws)
+            logits, _ = self._run_forward(x, domain, ws, repeats)
             return logits
         rng = self.ensure_rng(x.device, lane)
         self._note_depths(self._geometry(x.shape))
@@ -364,14 +378,20 @@ class UNet2D5_dsbn(nn.Module):
             self._seed_from_device, self._cur_lane = True, lane
             try:
                 with torch.cuda.graph(g):
-                    ent["out"], _ = self._run_forward(ent["x"], domain, ent["ws"])
+                    ent["out"], _ = self._run_forward(ent["x"], domain, ent["ws"], repeats)
             finally:
                 self._seed_from_device, self._cur_lane = False, 0
             ent["graph"] = g
         ent["x"].copy_(x, non_blocking=True)
         if any(key[3][1:]) and self._dropout_masks is None:
-            rng.fill_(self._draw_seed())
+            if repeats == 1:
+                rng[0:1].fill_(self._draw_seed())
+            else:
+                for k in range(repeats):                   # the same draws, in the same order, as K separate forwards
+                    rng[k:k + 1].fill_(self._draw_seed())
         ent["graph"].replay()
+        if repeats > 1:
+            return [o.clone() for o in ent["out"]]
         return ent["out"].clone()
 
     # -- helpers ----------------------------------------------------------------------------
@@ -657,7 +677,19 @@ class UNet2D5_dsbn(nn.Module):
                            seed_dev=rec["seed_dev"] if p > 0.0 and mask is None else None)
 
     # -- whole-network forward --------------------------------------------------------------
-    def _run_forward(self, x, domain, ws):
+    def _first_dropout_level(self):
+        """Index of the first encoder level whose unit-1 dropout is active (5 = none): everything before it is
+        deterministic, hence identical in all MC-dropout passes over the same input."""
+        for i in range(5):
+            dr = self._down_units[i][0].dropout
+            if dr is not None and dr.training and dr.p > 0.0:
+                return i
+        return 5
+
+    def _run_forward(self, x, domain, ws, repeats=1):
+        """``repeats`` > 1 (no-grad only): K MC-dropout passes over the same input in one call -- the encoder levels in
+        front of the first active dropout run ONCE, the rest of the network K times with K dropout seeds; returns a
+        list of K logits tensors (bit-identical to K separate forwards drawing the same seeds)."""
         n = x.shape[0]
         geo = self._geometry(x.shape)
         ft = self.ft_chns
@@ -672,27 +704,53 @@ class UNet2D5_dsbn(nn.Module):
             seed, seed_dev = self._draw_seed(), None
         rec = {"seed": seed, "seed_dev": seed_dev, "next_offset": 0, "geo": geo, "n": n, "x": x}
         rec["eval_affine"] = {} if torch.is_grad_enabled() else self._eval_affine_refresh(domain, ws)
+        if repeats > 1:
+            assert not torch.is_grad_enabled()
+            seeds = [(seed, seed_dev if seed_dev is None else seed_dev[0:1])]
+            for k in range(1, repeats):
+                seeds.append((0, seed_dev[k:k + 1]) if self._seed_from_device else (self._draw_seed(), None))
+            split = self._first_dropout_level()
+            cur = None
+            for i in range(split):
+                cur = self._down_level(i, domain, cur, x, n, geo, ws, small, rec)
+            outs = []
+            for k in range(repeats):
+                rec["seed"], rec["seed_dev"] = seeds[k]
+                rec["next_offset"] = 0
+                c2 = cur
+                for i in range(split, 5):
+                    c2 = self._down_level(i, domain, c2, x, n, geo, ws, small, rec)
+                outs.append(self._up_path_and_head(c2, domain, x, n, geo, ws, small, rec)[0])
+            return outs, rec
         cur = None
         for i in range(5):
-            u1, u2 = self._down_units[i]
-            d, h, w = geo[i]
-            c = ft[i]
-            a1 = C8(ws.c8("A1:block%d" % i, n, d, c, h, w))
-            self._unit_fwd(u1, domain, cur, x, a1, None, None, 0, n, geo[i], ws, small, rec)
-            if i < 4:
-                cat = ws.c8("cat%d" % i, n, d, 2 * c, h, w)
-                d2, h2, w2 = geo[i + 1]
-                pooled = C8(ws.c8("P%d" % i, n, d2, c, h2, w2))
-                idx = ws.get("idx%d" % i, (n, d2, c // 8, h2, w2, 8), torch.uint8)
-                pool_kd = 2 if self.dims[i] == 3 else 1
-                self._unit_fwd(u2, domain, a1, None, C8(cat, 0, c), pooled, idx, pool_kd, n, geo[i], ws, small, rec)
-                rec["idx%d" % i] = (idx, pool_kd)
-                cur = pooled
-            else:
-                a2 = C8(ws.c8("A2:block4", n, d, c, h, w))
-                self._unit_fwd(u2, domain, a1, None, a2, None, None, 0, n, geo[i], ws, small, rec)
-                cur = a2
-        low = cur
+            cur = self._down_level(i, domain, cur, x, n, geo, ws, small, rec)
+        return self._up_path_and_head(cur, domain, x, n, geo, ws, small, rec)
+
+    def _down_level(self, i, domain, cur, x, n, geo, ws, small, rec):
+        ft = self.ft_chns
+        u1, u2 = self._down_units[i]
+        d, h, w = geo[i]
+        c = ft[i]
+        a1 = C8(ws.c8("A1:block%d" % i, n, d, c, h, w))
+        self._unit_fwd(u1, domain, cur, x, a1, None, None, 0, n, geo[i], ws, small, rec)
+        if i < 4:
+            cat = ws.c8("cat%d" % i, n, d, 2 * c, h, w)
+            d2, h2, w2 = geo[i + 1]
+            pooled = C8(ws.c8("P%d" % i, n, d2, c, h2, w2))
+            idx = ws.get("idx%d" % i, (n, d2, c // 8, h2, w2, 8), torch.uint8)
+            pool_kd = 2 if self.dims[i] == 3 else 1
+            self._unit_fwd(u2, domain, a1, None, C8(cat, 0, c), pooled, idx, pool_kd, n, geo[i], ws, small, rec)
+            rec["idx%d" % i] = (idx, pool_kd)
+            cur = pooled
+        else:
+            a2 = C8(ws.c8("A2:block4", n, d, c, h, w))
+            self._unit_fwd(u2, domain, a1, None, a2, None, None, 0, n, geo[i], ws, small, rec)
+            cur = a2
+        return cur
+
+    def _up_path_and_head(self, low, domain, x, n, geo, ws, small, rec):
+        ft = self.ft_chns
         ups = [self.up1, self.up2, self.up3, self.up4]
         for k, lvl in zip(range(4), (3, 2, 1, 0)):
             up = ups[k]

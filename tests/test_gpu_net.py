@@ -503,3 +503,46 @@ def test_inference_epilogue_fusion_matches_two_kernel_path(mc_dropout, dims, mon
         ref = unet_dsbn.forward(unet_dsbn.to_torch_state(sd), x, 1, params, bn_training=False).detach()
         assert rel_l2(outs["1"], ref) < 1e-2 and rel_l2(outs["0"], ref) < 1e-2
         assert rel_l2(outs["1"], ref) <= rel_l2(outs["0"], ref) * 1.25
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_forward_mc_equals_consecutive_mc_dropout_forwards(graphs):
+    """K MC-dropout passes of one input through forward_mc (dropout-free encoder levels computed once) are bit-identical
+    to K consecutive forward calls drawing the same seeds (agent_seg.py:897-911 runs K full passes)."""
+    params = dict(NET_PARAMS, dropout=[0.0, 0.0, 0.3, 0.4, 0.5])
+    net = _net(params).eval()
+    net.cuda_graphs = graphs
+    for m in net.modules():
+        if type(m) == torch.nn.Dropout:
+            m.train()
+    assert net._first_dropout_level() == 2
+    x = torch.from_numpy(synth.synth_image(2, 1, (16, 32, 32), seed=91)).to(DEV)
+    dom = torch.ones(2, dtype=torch.long)
+    K = 4
+    with torch.no_grad():
+        for _ in range(3):                      # eager first sight, capture, replay
+            torch.manual_seed(11)
+            sep = [net(x, domain_label=dom).clone() for _ in range(K)]
+            torch.manual_seed(11)
+            mc = net.forward_mc(x, dom, K)
+            assert len(mc) == K
+            for a, b in zip(sep, mc):
+                assert torch.equal(a, b)
+            assert not torch.equal(mc[0], mc[1])            # different dropout masks per pass
+
+
+def test_inferer_mc_passes_without_dropout_equal_single_run():
+    """Inferer.run(mc_passes=K) with every dropout in eval mode: K identical volumes equal to the plain run (window
+    stitching, visit counts and TTA shared between the passes)."""
+    from fplplus_b200.inferer import Inferer
+    net = _net(dict(NET_PARAMS, dropout=[0.0, 0.0, 0.3, 0.4, 0.5])).eval()
+    vol = torch.from_numpy(synth.synth_image(1, 1, (24, 48, 64), seed=92)).to(DEV)
+    inf = Inferer({"class_num": 2, "sliding_window_enable": True, "sliding_window_size": [16, 32, 32],
+                   "sliding_window_stride": [8, 32, 32], "tta_mode": 1})
+    one = torch.ones(1, dtype=torch.long)
+    with torch.no_grad():
+        single = inf.run(net, vol, one)
+        many = inf.run(net, vol, one, mc_passes=3)
+    assert isinstance(many, list) and len(many) == 3
+    for m in many:
+        assert float((m - single).abs().max()) <= 1e-5 * float(single.abs().max())
