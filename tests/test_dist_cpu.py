@@ -38,6 +38,17 @@ def _worker(rank, world, port, q):
         dist.all_gather(others, mine)
         ref = torch.stack(others).mean(0)
         ok_avg = bool(torch.allclose(flat, ref, rtol=1e-6, atol=1e-7))
+        # ---- the second domain pass of the same step reuses the reducer after finish() (net.grad_wait_hook): the
+        #      network hands over >= grad_bucket_bytes at a time, the last range always ----
+        flat2 = torch.randn(n, generator=g)
+        mine2 = flat2.clone()
+        for a, b, last in ((0, 1_100_000, False), (1_100_000, 2_400_000, False), (2_400_000, n, True)):
+            red.hook(flat2, a, b, last)
+        red.finish()
+        assert not red._pending and red._start is None
+        others2 = [torch.empty_like(mine2) for _ in range(world)]
+        dist.all_gather(others2, mine2)
+        ok_avg = ok_avg and bool(torch.allclose(flat2, torch.stack(others2).mean(0), rtol=1e-6, atol=1e-7))
         # ---- inference: volumes round-robin, gather of (value, name) pairs, host sort ----
         cfg = {"dataset": {"tensor_type": "float"}, "network": {}, "training": {}, "testing": {}}
         ag = A.SegmentationAgent(cfg, "test")
