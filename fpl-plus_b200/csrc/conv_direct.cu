@@ -815,3 +815,18 @@ extern "C" int fpl_convt_k2s2_bwd(const void* x, int x_c8tot, int x_c8off, const
     }
     return 0;
 }
+
+/* per-channel sums of a C8-planar bf16 tensor, ACCUMULATED into out[c] (bias gradient of a conv whose output gradient
+ * is `g`): the 1x1 conv of UpBlock's bilinear mode. */
+extern "C" int fpl_channel_sum_c8(const void* g, int g_c8tot, int g_c8off, float* out, int n, int d, int h, int w, int c,
+                                  void* stream) {
+    FPL_REQUIRE(c > 0 && c % 8 == 0 && g != nullptr && out != nullptr, "fpl_channel_sum_c8: bad arguments");
+    FPL_REQUIRE((int64_t)n * d * (c / 8) <= 65535, "fpl_channel_sum_c8: too many planes");
+    const int HW = h * w;
+    int chunks = (HW + 1023) / 1024;
+    if (chunks < 1) chunks = 1;
+    dim3 grid(chunks, n * d * (c / 8));
+    channel_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16x8*)g, g_c8tot, g_c8off, out, n * d, c / 8, HW);
+    FPL_LAUNCH_CHECK();
+    return 0;
+}

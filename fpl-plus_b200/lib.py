@@ -48,6 +48,9 @@ _SIGNATURES = {
     "fpl_maxpool_c8": (_I, [_P, _I, _I, _P, _I, _I, _I] + [_I] * 5 + [_P]),
     "fpl_head_fwd": (_I, [_P, _I, _I, _P, _P, _P] + [_I] * 6 + [_P]),
     "fpl_head_dgrad": (_I, [_P, _P, _P, _I, _I, _P, _I, _I, _P] + [_I] * 6 + [_P]),
+    "fpl_upsample2x_c8": (_I, [_P, _I, _I, _P, _I, _I] + [_I] * 6 + [_P]),
+    "fpl_upsample2x_c8_bwd": (_I, [_P, _I, _I, _P, _I, _I] + [_I] * 6 + [_P]),
+    "fpl_channel_sum_c8": (_I, [_P, _I, _I, _P] + [_I] * 5 + [_P]),
     "fpl_grad_scatter_add": (_I, [_P, _P, _P, _I, _I, _P]),
     "fpl_stem_conv_fwd": (_I, [_P, _P, _P, _P, _I, _I, _P] + [_I] * 7 + [_P]),
     "fpl_stem_conv_wgrad": (_I, [_P, _P, _I, _I, _P] + [_I] * 7 + [_P]),

@@ -200,6 +200,12 @@ class UNet2D5_dsbn(nn.Module):
             (c1, n1, r1, d1), (c2, n2, r2, _d2) = u.conv.units()
             self._up_units.append((_Unit("up%d.conv#1" % k, c1, n1, r1, d1, kd),
                                    _Unit("up%d.conv#2" % k, c2, n2, r2, None, kd)))
+        # bilinear mode: the 1x1 projection in front of the up-sampling, one adapter per up block
+        self._proj_units = []
+        if self.bilinear:
+            for k, u in enumerate(ups, start=1):
+                conv = u.conv3d if u.dim == 3 else u.conv2d
+                self._proj_units.append(_Unit("up%d.proj" % k, UNet2D5_dsbn._Conv1x1(conv), None, None, None, 1))
 
     class _HeadConv(object):
         """The head's weights zero-padded to 16 output channels (a plain tensor whose ``_version`` drives the
@@ -224,6 +230,31 @@ class UNet2D5_dsbn(nn.Module):
                 self.weight[:k].copy_(w.detach())
                 self.bias[:k].copy_(self.src.bias.detach())
                 self.seen = ver
+
+    class _Conv1x1(object):
+        """UpBlock's 1x1 conv of `bilinear=True` mode (unet2d5_dsbn.py:147-148,171,174) as a (1,3,3) conv whose off-centre
+        taps are zero, so that forward / dgrad / wgrad run on the ordinary tensor-core conv kernels.  ``weight`` is a
+        plain tensor kept in sync with the module (its ``_version`` drives the weight-image cache)."""
+
+        def __init__(self, conv):
+            self.src = conv
+            self.weight = None
+            self.in_channels, self.out_channels = conv.in_channels, conv.out_channels
+            self.seen = None
+
+        @property
+        def bias(self):
+            return self.src.bias
+
+        def sync(self, force):
+            w = self.src.weight
+            co, ci = w.shape[0], w.shape[1]
+            if self.weight is None or self.weight.device != w.device:
+                self.weight = torch.zeros((co, ci, 1, 3, 3), dtype=torch.float32, device=w.device)
+                force = True
+            if force or w._version != self.seen:
+                self.weight[:, :, 0, 1, 1].copy_(w.detach().reshape(co, ci))
+                self.seen = w._version
 
     class _StemConv(object):
         """The 1-channel stem conv k(3,3,3) as a k(3,1,1) conv over the 16 "patch" channels written by
@@ -279,7 +310,10 @@ class UNet2D5_dsbn(nn.Module):
         for k in (3, 2, 1, 0):
             u1, u2 = self._up_units[k]
             out += unit_params(u2) + unit_params(u1)
-            t = ups[k].trans3d if ups[k].dim == 3 else ups[k].trans2d
+            if self.bilinear:
+                t = ups[k].conv3d if ups[k].dim == 3 else ups[k].conv2d
+            else:
+                t = ups[k].trans3d if ups[k].dim == 3 else ups[k].trans2d
             out += [t.weight, t.bias]
         for i in (4, 3, 2, 1, 0):
             u1, u2 = self._down_units[i]
@@ -308,8 +342,8 @@ class UNet2D5_dsbn(nn.Module):
             raise ValueError('expected 5D input (got {}D input)'.format(x.dim()))
         if not x.is_cuda:
             raise RuntimeError("fplplus_b200.UNet2D5_dsbn runs on CUDA (sm_100a) only; got a %s tensor" % x.device)
-        if self.bilinear:
-            raise NotImplementedError("bilinear=True up-sampling is not built yet (SURVEY.md §8f-1)")
+        if self.bilinear and not all(self._use_tc(u.cin, u.cout) for u in self._proj_units):
+            raise NotImplementedError("bilinear=True needs feature_chns that are multiples of 16 (tensor-core 1x1 projection)")
         domain = int(domain_label[0])
         if not 0 <= domain < self.num_domains:
             raise IndexError("domain_label %d out of range" % domain)
@@ -426,12 +460,15 @@ class UNet2D5_dsbn(nn.Module):
             for u in (u1, u2):
                 if not u.is_stem and self._use_tc(u.cin, u.cout):
                     out.append(u)
+        for u in self._proj_units:
+            u.conv.sync(self._head_dirty)
+            out.append(u)
         if self._head_tc():
             if self._head_unit is None:
                 self._head_unit = _Unit("head", self._head, None, None, None, 1)
             self._head.sync(self._head_dirty)
-            self._head_dirty = False
             out.append(self._head_unit)
+        self._head_dirty = False
         return out
 
     def _refresh_weight_images(self, with_dgrad):
@@ -761,7 +798,16 @@ class UNet2D5_dsbn(nn.Module):
             cat = ws.t["cat%d" % lvl]
             trans = up.trans3d if up.dim == 3 else up.trans2d
             kd2 = 2 if up.dim == 3 else 1
-            if self._convt_tc(c_low, c):
+            if self.bilinear:
+                # 1x1 projection at low resolution (a (1,3,3) conv with zero off-centre taps), then trilinear / bilinear
+                # x2 up-sampling (align_corners=True) straight into the second half of the concat buffer
+                pu = self._proj_units[k]
+                t_low = ws.c8("T:up%d" % (k + 1), n, dl, c, hl, wl)
+                call("fpl_conv3d_tc", *low.args(), ptr(self._weight_image(pu.conv, 1, False, ws)), ptr(pu.conv.bias), ptr(t_low),
+                     c // 8, 0, None, n, dl, hl, wl, c_low, c, 1, stream_ptr())
+                call("fpl_upsample2x_c8", ptr(t_low), c // 8, 0, ptr(cat), 2 * c // 8, c // 8, n, dl, hl, wl, c, kd2,
+                     stream_ptr())
+            elif self._convt_tc(c_low, c):
                 call("fpl_convt_k2s2_fwd_tc", *low.args(), ptr(self._convt_image(trans, kd2, 0)), ptr(trans.bias), ptr(cat),
                      2 * c // 8, c // 8, n, dl, hl, wl, c_low, c, kd2, stream_ptr())
             else:
@@ -903,7 +949,8 @@ class UNet2D5_dsbn(nn.Module):
             total = sum((u.conv.weight.numel() + 3) // 4 * 4 for pair in self._down_units + self._up_units for u in pair
                         if not u.is_stem) + 16 * self.ft_chns[0] * 9 + sum(
                             (t.weight.numel() + 3) // 4 * 4 for up in (self.up1, self.up2, self.up3, self.up4)
-                            for t in (up.trans3d, up.trans2d) if t is not None)
+                            for t in (up.trans3d, up.trans2d) if t is not None) + sum(
+                            9 * u.cin * u.cout for u in self._proj_units)
             scratch = ws.get("wgrad_scratch", (total,), torch.float32)
             scratch.zero_()
             cursor = [0]
@@ -1003,7 +1050,25 @@ class UNet2D5_dsbn(nn.Module):
             dl, hl, wl = geo[lvl + 1]
             low = rec["up%d.low" % (k + 1)]
             glow = C8(ws.c8("dlow%d" % lvl, n, dl, c_low, hl, wl))
-            if self._convt_tc(c_low, c):
+            if self.bilinear:
+                pu = self._proj_units[k]
+                proj = up.conv3d if up.dim == 3 else up.conv2d
+                g_t = ws.c8("dT:up%d" % (k + 1), n, dl, c, hl, wl)
+                call("fpl_upsample2x_c8_bwd", ptr(dcat.buf), 2 * c // 8, c // 8, ptr(g_t), c // 8, 0, n, dl, hl, wl, c, kd2, st)
+                call("fpl_channel_sum_c8", ptr(g_t), c // 8, 0, ptr(grads[proj.bias]), n, dl, hl, wl, c, st)
+                # wgrad of the (1,3,3) stand-in: only its centre tap is the 1x1 weight
+                if fold is not None:
+                    scr = fold["alloc"](9 * c * c_low)
+                    call("fpl_conv3d_wgrad_tc_tapmajor", *low.args(), ptr(g_t), c // 8, 0, ptr(scr), n, dl, hl, wl, c_low, c, 1, st)
+                    fold["pending"].append((scr[4 * c * c_low:5 * c * c_low], grads[proj.weight], c, c_low, 1))
+                else:
+                    dw9 = ws.get("dW9:up%d" % (k + 1), (c, c_low, 1, 3, 3), torch.float32)
+                    dw9.zero_()
+                    call("fpl_conv3d_wgrad_tc", *low.args(), ptr(g_t), c // 8, 0, ptr(dw9), n, dl, hl, wl, c_low, c, 1, st)
+                    grads[proj.weight].view(c, c_low).add_(dw9[:, :, 0, 1, 1])
+                call("fpl_conv3d_tc", ptr(g_t), c // 8, 0, ptr(self._weight_image(pu.conv, 1, True, ws)), None, *glow.args(),
+                     None, n, dl, hl, wl, c, c_low, 1, st)
+            elif self._convt_tc(c_low, c):
                 call("fpl_convt_k2s2_dgrad_tc", ptr(dcat.buf), 2 * c // 8, c // 8, ptr(self._convt_image(trans, kd2, 1)),
                      *glow.args(), n, dl, hl, wl, c_low, c, kd2, st)
                 if fold is not None:

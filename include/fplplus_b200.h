@@ -154,6 +154,17 @@ int fpl_head_fwd(const void* x, int x_c8tot, int x_c8off, const float* w, const 
 int fpl_head_dgrad(const float* dlogits, const float* w, void* g, int g_c8tot, int g_c8off, void* dl8, int dl_c8tot,
                    int dl_c8off, float* dbias, int n, int d, int h, int w_, int cin, int classes, void* stream);
 
+/* UpBlock in `bilinear = True` mode (unet2d5_dsbn.py:149-150, 170-176): 1x1 conv (run as a (1,3,3) conv whose off-centre
+ * taps are zero, on the ordinary conv kernels) followed by nn.Upsample(scale_factor=2, trilinear / bilinear,
+ * align_corners=True).  (n, d, h, w) is the LOW-resolution geometry; kd2 = 2 interpolates depth too (3-D blocks),
+ * kd2 = 1 in-plane only (2-D blocks).  The backward form gathers (deterministic). */
+int fpl_upsample2x_c8(const void* x, int x_c8tot, int x_c8off, void* y, int y_c8tot, int y_c8off, int n, int d, int h, int w,
+                      int c, int kd2, void* stream);
+int fpl_upsample2x_c8_bwd(const void* gy, int gy_c8tot, int gy_c8off, void* gx, int gx_c8tot, int gx_c8off, int n, int d,
+                          int h, int w, int c, int kd2, void* stream);
+/* out[c] += sum over voxels of g[., c] (bias gradient from a C8-planar output gradient). */
+int fpl_channel_sum_c8(const void* g, int g_c8tot, int g_c8off, float* out, int n, int d, int h, int w, int c, void* stream);
+
 /* stem: image fp32 NCDHW (in_chns <= 8) -> C8-planar bf16, conv k3 p1 + bias + stats. */
 int fpl_stem_conv_fwd(const float* x, const float* w, const float* bias, void* y, int y_c8tot, int y_c8off,
                       double* stats, int n, int cin, int d, int h, int w_, int cout, int kd, void* stream);

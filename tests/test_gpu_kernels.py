@@ -776,3 +776,31 @@ def test_head_cuda_core_fwd_and_dgrad(cin, classes, shape):
     copy = from_c8(dl8).cpu()
     assert torch.equal(copy[:, :classes], bf16_round(dl)) and torch.all(copy[:, classes:] == 0)
     np.testing.assert_allclose(db.cpu().numpy() - 1.0, b.grad.numpy(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("kd2,shape,c", [(2, (2, 3, 5, 7), 16), (1, (1, 4, 8, 8), 8), (2, (1, 1, 1, 6), 24), (2, (1, 8, 16, 16), 32)])
+def test_upsample2x_align_corners_fwd_bwd(kd2, shape, c):
+    """nn.Upsample(scale_factor=2, trilinear / bilinear, align_corners=True) (UpBlock bilinear mode) against torch, into a
+    channel slice of a wider buffer; the gather backward against autograd."""
+    n, d, h, w = shape
+    x = bf16_round(randn(501, n, c, d, h, w)).requires_grad_(True)
+    if kd2 == 2:
+        ref = F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=True)
+    else:
+        ref = F.interpolate(x.transpose(1, 2).reshape(n * d, c, h, w), scale_factor=2, mode="bilinear", align_corners=True)
+        ref = ref.reshape(n, d, c, 2 * h, 2 * w).transpose(1, 2)
+    g = bf16_round(randn(502, *ref.shape))
+    ref.backward(g)
+    do = d * kd2
+    cat = torch.zeros((n, do, 2 * c // 8, 2 * h, 2 * w, 8), dtype=torch.bfloat16, device=DEV)
+    _call("fpl_upsample2x_c8", _p(to_c8(x.detach().to(DEV))), c // 8, 0, _p(cat), 2 * c // 8, c // 8, n, d, h, w, c, kd2, _st())
+    out = from_c8(cat).cpu()
+    assert torch.all(out[:, :c] == 0)
+    assert max_rel(out[:, c:], ref.detach()) < 6e-3
+    gcat = to_c8(torch.cat([torch.zeros_like(g), g], 1).to(DEV))
+    gx = torch.zeros((n, d, c // 8, h, w, 8), dtype=torch.bfloat16, device=DEV)
+    _call("fpl_upsample2x_c8_bwd", _p(gcat), 2 * c // 8, c // 8, _p(gx), c // 8, 0, n, d, h, w, c, kd2, _st())
+    assert max_rel(from_c8(gx).cpu(), x.grad) < 6e-3
+    s = torch.ones(c, device=DEV)
+    _call("fpl_channel_sum_c8", _p(gcat), 2 * c // 8, c // 8, _p(s), n, do, 2 * h, 2 * w, c, _st())
+    np.testing.assert_allclose(s.cpu().numpy() - 1.0, g.sum((0, 2, 3, 4)).numpy(), rtol=2e-4, atol=2e-3)

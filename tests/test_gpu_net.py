@@ -546,3 +546,52 @@ def test_inferer_mc_passes_without_dropout_equal_single_run():
     assert isinstance(many, list) and len(many) == 3
     for m in many:
         assert float((m - single).abs().max()) <= 1e-5 * float(single.abs().max())
+
+
+@pytest.mark.parametrize("dims", [[3, 3, 3, 3, 3], [2, 2, 3, 3, 3]])
+def test_bilinear_mode_matches_oracle(dims):
+    """`bilinear = True`: 1x1 projection + trilinear / bilinear x2 up-sampling (align_corners) instead of the
+    transposed conv.  Eval logits against the fp32 oracle; one train-mode backward: the 1x1 convs (not the transposed
+    convs) receive gradients that point the same way as the oracle's."""
+    from oracle import unet_dsbn, losses
+    from fplplus_b200.loss import CombinedLoss
+    from fplplus_b200.registry import loss_dict
+    params = dict(NET_PARAMS, conv_dims=dims, bilinear=True, dropout=[0.0] * 5)
+    shape = (16, 32, 32)
+    net = _net(params).eval()
+    x_np = synth.synth_image(2, 1, shape, seed=61)
+    dom = torch.ones(2, dtype=torch.long)
+    sd = synth.synth_state_dict()
+    with torch.no_grad():
+        out = net(torch.from_numpy(x_np).to(DEV), domain_label=dom).cpu()
+        ref = unet_dsbn.forward(unet_dsbn.to_torch_state(sd), torch.from_numpy(x_np), 1, params)
+    err = rel_l2(out, ref)
+    print("bilinear eval rel_l2", err)
+    assert err < 1e-2
+    # train-mode step
+    net.train()
+    lab = synth.synth_label(2, 2, shape, seed=61)
+    y = torch.from_numpy(synth.one_hot(lab, 2))
+    crit = CombinedLoss({"loss_type": ["DiceLoss", "CrossEntropyLoss"], "loss_weight": [0.5, 0.5]}, loss_dict)
+    logits = net(torch.from_numpy(x_np).to(DEV), domain_label=dom)
+    loss = crit({"prediction": logits, "ground_truth": y.to(DEV)})
+    loss.backward()
+    st = unet_dsbn.to_torch_state(sd, requires_grad=True)
+    ref_logits = unet_dsbn.forward(st, torch.from_numpy(x_np), 1, params, bn_training=True)
+    ref_loss = losses.combined_loss(ref_logits, y, None, 0.5, 0.5)
+    ref_loss.backward()
+    assert abs(float(loss.detach()) - float(ref_loss.detach())) <= 1e-2 * abs(float(ref_loss.detach()))
+    named = dict(net.named_parameters())
+    for k in range(1, 5):
+        up_dim3 = dims[4 - k] == 3
+        proj = "up%d.%s" % (k, "conv3d" if up_dim3 else "conv2d")
+        trans = "up%d.%s" % (k, "trans3d" if up_dim3 else "trans2d")
+        assert named[trans + ".weight"].grad is None
+        for leaf in (".weight", ".bias"):
+            ours, want = named[proj + leaf].grad.cpu().flatten(), st[proj + leaf].grad.flatten()
+            cos = float(torch.nn.functional.cosine_similarity(ours, want, dim=0))
+            print(proj + leaf, "cosine", cos, "norm ratio", float(ours.norm() / want.norm()))
+            assert cos > 0.97 and 0.8 < float(ours.norm() / want.norm()) < 1.25
+    cos = float(torch.nn.functional.cosine_similarity(named["out_conv.weight"].grad.cpu().flatten(),
+                                                      st["out_conv.weight"].grad.flatten(), dim=0))
+    assert cos > 0.99
