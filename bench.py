@@ -55,11 +55,11 @@ def peaks():
 
 
 # --------------------------------------------------------------------------------------------
-# synthetic data (oracle/synth.py is the seeded generator shared with the parity tests; it is data
-# generation, not the measured path)
+# synthetic data (synthetic_data.py is the seeded generator shared with the parity tests; it is data
+# generation, not the measured path, and not part of oracle/)
 # --------------------------------------------------------------------------------------------
 def make_batch(seed, n, shape, weighted, pinned):
-    from oracle import synth
+    import synthetic_data as synth
     x = torch.from_numpy(synth.synth_image(n, 1, shape, seed=seed))
     lab = synth.synth_label(n, 2, shape, seed=seed)
     d = {"image": x, "label_prob": torch.from_numpy(synth.one_hot(lab, 2))}
@@ -212,7 +212,7 @@ class KernelTimer(object):
 # --------------------------------------------------------------------------------------------
 def build_agent(stage, world):
     from fplplus_b200.agent import GradAllReducer, SegmentationAgent
-    from oracle import synth
+    import synthetic_data as synth
     cfg = {"dataset": {"tensor_type": "float", "train_batch_size": BATCH}, "network": dict(NET_PARAMS),
            "training": dict(TRAIN_CFG), "testing": dict(TEST_CFG)}
     agent = SegmentationAgent(cfg, stage)
@@ -420,7 +420,7 @@ def bench_filter(agent, rank, world, barrier, max_over_ranks, args):
     (8 windows x 4 flips) = 256 network forwards of 1x32x128x128 per 48x256x256 volume."""
     from fplplus_b200 import fpl
     from fplplus_b200.inferer import Inferer
-    from oracle import synth
+    import synthetic_data as synth
     import torch.nn as nn
     net = agent.net
     net.eval()
@@ -479,7 +479,7 @@ def bench_filter(agent, rank, world, barrier, max_over_ranks, args):
 # be imported without SimpleITK/tensorboardX, see oracle/__init__.py) on the host cores
 # --------------------------------------------------------------------------------------------
 def _oracle_trainer(threads):
-    from oracle import synth
+    import synthetic_data as synth
     from oracle.train_step import OracleTrainer
     torch.set_num_threads(threads)
     params = dict(NET_PARAMS)
