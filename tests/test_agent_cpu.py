@@ -81,3 +81,38 @@ def test_npy_dataset_folds_image_weight_like_set_weight(tmp_path):
     assert s["image"].shape == (1, 4, 6, 8) and s["label_prob"].shape == (2, 4, 6, 8)
     from oracle import fpl_filter
     np.testing.assert_array_equal(s["pixel_weight"][0].numpy(), fpl_filter.set_weight_(np.float32(0.37), w.astype(np.float32)))
+
+
+def test_network_plan_on_cpu_gradient_sets_and_mc_split():
+    """Host-side planning of UNet2D5_dsbn needs no GPU: which parameters receive gradients (3-D convs, the selected
+    domain's BN, PReLU, the transposed convs -- or the 1x1 projections in bilinear mode; never the 2-D twins), and where
+    the MC-dropout sweep splits the network (first encoder level with an active dropout)."""
+    import torch
+    from fplplus_b200.net import UNet2D5_dsbn
+    base = {"in_chns": 1, "feature_chns": [16, 32, 64, 128, 256], "dropout": [0.0, 0.0, 0.3, 0.4, 0.5],
+            "conv_dims": [3, 3, 3, 3, 3], "class_num": 2, "bilinear": False, "num_domains": 2}
+    net = UNet2D5_dsbn(dict(base))
+    names = {id(p): n for n, p in net.named_parameters()}
+    got = [names[id(p)] for p in net._grad_params(1)]
+    assert len(got) == len(set(got)) == 2 + 4 * 12 + 5 * 10
+    assert got[:2] == ["out_conv.weight", "out_conv.bias"] and got[-1] == "block0.conv.relu_1.weight"
+    assert not any("2d" in n or ".bns.0." in n or n.endswith(".conv3d.weight") and n.count(".") == 2 for n in got)
+    assert "up4.trans3d.weight" in got and sum(p.numel() for p in net._grad_params(1)) == 5648148      # SURVEY 8b
+    bil = UNet2D5_dsbn(dict(base, bilinear=True))
+    names = {id(p): n for n, p in bil.named_parameters()}
+    got = [names[id(p)] for p in bil._grad_params(0)]
+    assert "up4.conv3d.weight" in got and not any("trans" in n for n in got)
+    # 2.5-D: the 2-D members of the first two levels take the gradients
+    d25 = UNet2D5_dsbn(dict(base, conv_dims=[2, 2, 3, 3, 3]))
+    names = {id(p): n for n, p in d25.named_parameters()}
+    got = [names[id(p)] for p in d25._grad_params(1)]
+    assert "block0.conv.conv2d_1.weight" in got and "block0.conv.conv3d_1.weight" not in got and "up4.trans2d.weight" in got
+    # MC split: dropout modules in train mode with p > 0 from level 2 on
+    net.eval()
+    assert net._first_dropout_level() == 5
+    for m in net.modules():
+        if type(m) == torch.nn.Dropout:
+            m.train()
+    assert net._first_dropout_level() == 2
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 1, 16, 32, 32), domain_label=torch.zeros(1, dtype=torch.long))      # CPU tensor: no fallback
