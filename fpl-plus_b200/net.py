@@ -1141,12 +1141,16 @@ class UNet2D5_dsbn(nn.Module):
         if self.grad_wait_hook is not None:
             self.grad_wait_hook()                     # DDP: the asynchronous all-reduces of `flat` must have landed
         cur = torch.cuda.current_stream()
+        capturing = torch.cuda.is_current_stream_capturing()
         if self.out_conv.weight.grad is None:
             m["buf"].zero_()
             m["event"] = torch.cuda.Event()
             m["event"].record(cur)
-        elif m["event"] is not None:
-            cur.wait_event(m["event"])                # the other pass's stream may have issued the zeroing
+            m["event_captured"] = capturing
+        elif m["event"] is not None and m.get("event_captured", False) == capturing:
+            # the other pass's stream may have issued the zeroing (an event recorded inside a graph capture cannot be
+            # waited on from eager work; eager work after a replay is ordered by its stream anyway)
+            cur.wait_event(m["event"])
         key = tuple(id(p) for p in params)
         tab = m["tables"].get(key)
         if tab is None:
