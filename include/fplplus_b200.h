@@ -33,8 +33,11 @@ int fpl_version(void);
 long long fpl_launch_count(int reset);
 /* 1 when the running device is sm_100 (tcgen05 kernels usable), else 0. */
 int fpl_device_is_sm100(void);
-/* debugging knobs of the tensor-core kernels (key 0: swap LBO/SBO of the fwd UMMA descriptors;
- * 10: same for wgrad; 11: allow UMMA M=64 in wgrad; 12: M=64 TMEM lane layout; 13: raw-accumulator dump pointer). */
+/* debugging / tuning knobs, used by tools/*_probe.py and tools/*_tune.py only (defaults are the measured optima):
+ *   0  swap LBO/SBO of the fwd UMMA descriptors        1  allow the N split of staged weight slices (conv3d_tc)
+ *  10  swap LBO/SBO in wgrad   11  allow UMMA M=64 in wgrad   12  M=64 TMEM lane layout   13  raw-accumulator dump pointer
+ *  14  allow depth-stacked wgrad tiles   15  force the wgrad tile width   16  minimum voxel tiles per split-K slice
+ *  17  skip the wgrad epilogue (timing only: results are wrong)          30  DSBN backward blocks per SM */
 void fpl_debug_set(int key, long long value);
 
 /* ---- (a) conv3d: PyMIC/pymic/net/net3d/unet2d5_dsbn.py:75,79 (nn.Conv3d k3 p1 / k(1,3,3) p(0,1,1)) ---- */
