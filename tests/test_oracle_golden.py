@@ -5,6 +5,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import fpl_filter, inferer, losses, synth, unet_dsbn
@@ -197,3 +198,32 @@ def test_bf16_emulating_mode_tracks_the_fp32_oracle():
     cos = torch.nn.functional.cosine_similarity(res[True][1]["up4.conv.conv3d_2.weight"].grad.flatten(),
                                                 res[False][1]["up4.conv.conv3d_2.weight"].grad.flatten(), dim=0)
     assert float(cos) > 0.99
+
+
+@pytest.mark.parametrize("tag", ["d25", "bil3d", "bil25"])
+def test_network_modes_against_reference(golden_dir, tag):
+    """The oracle's 2.5-D (`conv_dims` with 2) and `bilinear = True` branches against the REFERENCE network run in those
+    modes (oracle/gen_golden_modes.py): eval logits, train-mode logits / loss, gradient prefixes and norms, and the number
+    of parameters that receive gradients."""
+    from oracle.gen_golden_modes import GRADS, MODES, SHAPE as MSHAPE
+    g = _load(golden_dir, "net_modes.npz")
+    params = dict(NET_PARAMS, dropout=[0.0] * 5, **MODES[tag])
+    x = torch.from_numpy(synth.synth_image(1, 1, MSHAPE, seed=7))
+    y = torch.from_numpy(synth.one_hot(synth.synth_label(1, 2, MSHAPE, seed=7), 2))
+    st = unet_dsbn.to_torch_state(synth.synth_state_dict())
+    with torch.no_grad():
+        out = unet_dsbn.forward(st, x, 1, params, bn_training=False).numpy()
+    np.testing.assert_allclose(out, g[tag + "_eval_logits"], rtol=1e-4, atol=1e-5)
+    st = unet_dsbn.to_torch_state(synth.synth_state_dict(), requires_grad=True)
+    logits = unet_dsbn.forward(st, x, 1, params, bn_training=True)
+    loss = losses.combined_loss(logits, y, None, 0.5, 0.5)
+    loss.backward()
+    np.testing.assert_allclose(logits.detach().numpy(), g[tag + "_train_logits"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(loss.item(), float(g[tag + "_train_loss"]), rtol=1e-6)
+    n_with_grad = sum(v.numel() for v in st.values() if v.requires_grad and v.grad is not None)
+    assert n_with_grad == int(g[tag + "_n_with_grad"])
+    for k in GRADS[tag]:
+        ours = st[k].grad
+        np.testing.assert_allclose(ours.double().norm().item(), float(g[tag + "_gradnorm_" + k]), rtol=1e-4, err_msg=k)
+        np.testing.assert_allclose(ours.numpy().reshape(-1)[:4096], g[tag + "_grad_" + k], rtol=2e-3,
+                                   atol=1e-6 * float(ours.abs().max()), err_msg=k)
