@@ -346,8 +346,16 @@ class SegmentationAgent(object):
         if self.stage == 'train':
             if self.train_loaders[0] is None and self.train_set is not None:
                 sets = self.train_set if isinstance(self.train_set, (list, tuple)) else [self.train_set]
-                self.train_loaders = [torch.utils.data.DataLoader(s, batch_size=bs, shuffle=True, drop_last=True)
-                                      for s in sets] + [None] * (2 - len(sets))
+
+                def train_loader(s):
+                    if self.world > 1:
+                        # one process per GPU: every rank draws a disjoint shard of each epoch's permutation
+                        sampler = torch.utils.data.distributed.DistributedSampler(
+                            s, num_replicas=self.world, rank=self.rank, shuffle=True, seed=int(self.random_seed),
+                            drop_last=True)
+                        return torch.utils.data.DataLoader(s, batch_size=bs, sampler=sampler, drop_last=True)
+                    return torch.utils.data.DataLoader(s, batch_size=bs, shuffle=True, drop_last=True)
+                self.train_loaders = [train_loader(s) for s in sets] + [None] * (2 - len(sets))
             if self.valid_loaders[0] is None and self.valid_set is not None:
                 sets = self.valid_set if isinstance(self.valid_set, (list, tuple)) else [self.valid_set]
                 self.valid_loaders = [torch.utils.data.DataLoader(s, batch_size=1, shuffle=False) for s in sets] \
@@ -472,6 +480,8 @@ class SegmentationAgent(object):
         if self.reducer is not None:
             self.reducer.finish()
         self.optimizer.step()
+        if inval is not None:
+            inval()                 # the staged images now lag the updated masters (validation / infer re-stage)
         return loss.detach(), dices
 
     def train_step(self, batches):
@@ -580,6 +590,11 @@ class SegmentationAgent(object):
         if getattr(self.net, "_rng_dev", None) is not None:
             self.net._rng_dev.fill_(self.net._draw_seed())
         ent["graph"].replay()
+        inval = getattr(self.net, "invalidate_weight_images", None)
+        if inval is not None:
+            # the replay updated the fp32 masters after staging: a no-grad forward that follows (validation, infer)
+            # must not trust the host-side "fresh" marks set while the graph was captured
+            inval()
         return ent["out"]
 
     def _next(self, d, iters):
@@ -605,7 +620,7 @@ class SegmentationAgent(object):
                 if b is None:
                     continue
                 if dices[k] is not None:
-                    dice_acc[d] = dices[k] if dice_acc[d] is None else dice_acc[d] + dices[k]
+                    dice_acc[d] = dices[k].clone() if dice_acc[d] is None else dice_acc[d] + dices[k]
                 k += 1
         # ONE device->host read per round
         train_avg_loss = float(loss_acc) / iter_valid / int(n_dom)
@@ -623,6 +638,7 @@ class SegmentationAgent(object):
             infer_cfg['class_num'] = class_num
             self.inferer = Inferer(infer_cfg)
         res = []
+        self._broadcast_state(buffers_only=True)
         self.net.eval()
         with torch.no_grad():
             for d in range(n_dom):
@@ -650,7 +666,7 @@ class SegmentationAgent(object):
             pick = host
         loss = float(np.mean([h[0] for h in pick]))
         cls = np.mean(np.stack([h[1] for h in pick], 0), 0)
-        scal = {'loss': loss, 'avg_dice': float(cls.mean()), 'class_dice': cls}
+        scal = self._agree_scalars({'loss': loss, 'avg_dice': float(cls.mean()), 'class_dice': cls})
         if isinstance(self.scheduler, lr_scheduler.ReduceLROnPlateau):
             self.scheduler.step(scal['avg_dice'])
         return scal
@@ -691,6 +707,7 @@ class SegmentationAgent(object):
             self.net.load_state_dict(self.checkpoint['model_state_dict'])
             self.max_val_it = iter_start
             self.best_model_wts = self.checkpoint['model_state_dict']
+        self._broadcast_state()
         self.create_optimizer(self.get_parameters_to_update())
         self.create_loss_calculator()
         if self.rank == 0:
@@ -768,7 +785,9 @@ class SegmentationAgent(object):
             infer_cfg = dict(te)
             infer_cfg['class_num'] = self.config['network']['class_num']
             self.inferer = Inferer(infer_cfg)
-        k_passes = te.get('fpl_mc_passes', 6)       # hard-coded 6 in the reference (:898)
+        k_passes = int(te.get('fpl_mc_passes', 6))  # hard-coded 6 in the reference (:898)
+        if self.FPL and not 1 <= k_passes <= fpl.max_mc_passes():
+            raise ValueError("fpl_mc_passes = %d not in [1, %d]" % (k_passes, fpl.max_mc_passes()))
         uncertainty_list, pending = {}, []
         outputs = {}
         volumes = list(self.test_loader)
@@ -802,6 +821,41 @@ class SegmentationAgent(object):
         self.last_outputs = {k: v.cpu().numpy() for k, v in outputs.items()}
         self.save_outputs(self.last_outputs)
         return self.last_outputs
+
+    # -- multi-process agreement (one process per GPU) ------------------------------------------
+    def _broadcast_state(self, buffers_only=False):
+        """Rank 0's parameters / buffers on every rank.  Parameters: once, before the first step (ranks may have been
+        initialised from different seeds).  Buffers (BatchNorm running statistics, rank-local under data parallelism):
+        before every validation, which reproduces nn.DataParallel, whose replica 0 shares its buffers with the wrapped
+        module (agent_seg.py:695) -- and makes the validation score, hence early stopping / ReduceLROnPlateau /
+        best-model choice, identical on all ranks."""
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+        tensors = list(self.net.buffers()) if buffers_only else list(self.net.parameters()) + list(self.net.buffers())
+        for dtype in sorted({t.dtype for t in tensors}, key=str):
+            group = [t for t in tensors if t.dtype == dtype]
+            flat = torch.cat([t.detach().reshape(-1) for t in group])
+            dist.broadcast(flat, src=0)
+            o = 0
+            with torch.no_grad():
+                for t in group:
+                    t.copy_(flat[o:o + t.numel()].view_as(t))
+                    o += t.numel()
+        inval = getattr(self.net, "invalidate_weight_images", None)
+        if inval is not None and not buffers_only:
+            inval()
+
+    def _agree_scalars(self, scal):
+        """Rank 0's validation scalars on every rank (bit-identical control flow: stop_now, scheduler, best model)."""
+        if self.world == 1:
+            return scal
+        import torch.distributed as dist
+        cls = np.asarray(scal['class_dice'], np.float64)
+        t = torch.tensor([scal['loss'], scal['avg_dice']] + cls.tolist(), dtype=torch.float64, device=self.device)
+        dist.broadcast(t, src=0)
+        v = t.tolist()
+        return {'loss': v[0], 'avg_dice': v[1], 'class_dice': np.asarray(v[2:], cls.dtype).reshape(cls.shape)}
 
     def _gather_dict(self, d):
         if self.world == 1:

@@ -9,7 +9,8 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kMaxK = 8;
+constexpr int kMaxK = 8;          // passes held in registers by mc_uncertainty_kernel
+constexpr int kMaxKStream = 16;   // passes the streaming variant accepts (= UNet2D5_dsbn.kMaxMcRepeats)
 
 int grid_for(int64_t items) {
     int64_t blocks = (items + kThreads - 1) / kThreads;
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(kThreads) argmax_label_kernel(const float* __r
 }
 
 struct PassPtrs {
-    const float* p[kMaxK];
+    const float* p[kMaxKStream];
 };
 
 // out[0] += sum over classes and voxels of the population variance across the K passes of the
@@ -116,6 +117,91 @@ __global__ void __launch_bounds__(kThreads) mc_uncertainty_kernel(PassPtrs ptrs,
                 var_acc += m2 * invK;
                 if (c == 1) mean1 = mean;
             }
+            float u = -1.0f * (mean1 * logf(mean1 + 1e-6f));
+            cnt += (u > 0.01f) ? 1u : 0u;
+            reinterpret_cast<float*>(&uo)[j] = u;
+        }
+        if (umap != nullptr) reinterpret_cast<float4*>(umap)[g] = uo;
+    }
+    __shared__ float sv[kThreads / 32];
+    __shared__ unsigned int sc[kThreads / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float v = warp_sum(var_acc);
+    unsigned int c = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) { sv[wid] = v; sc[wid] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tv = 0.0, tc = 0.0;
+        for (int k = 0; k < kThreads / 32; ++k) { tv += (double)sv[k]; tc += (double)sc[k]; }
+        atomicAdd(out, tv);
+        atomicAdd(out + 1, tc);
+    }
+}
+
+// K in (kMaxK, kMaxKStream]: the [K][C][4] register tile of the kernel above would spill, so the probabilities are
+// recomputed: sweep 1 accumulates the per-class means, sweep 2 re-reads the logits (L1/L2 hits: the same thread read
+// them a few hundred cycles earlier) and accumulates the squared deviations.  Same operation order as the register
+// kernel (sum over k ascending, * 1/K, fma of squared deviations over k ascending), so both give identical bits.
+template <int C>
+__device__ __forceinline__ void mc_probs4(const float* base, int64_t S4, int64_t g, float (&prob)[C][4]) {
+    float4 zv[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) zv[c] = __ldg(reinterpret_cast<const float4*>(base) + c * S4 + g);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float m = reinterpret_cast<const float*>(&zv[0])[j];
+#pragma unroll
+        for (int c = 1; c < C; ++c) m = fmaxf(m, reinterpret_cast<const float*>(&zv[c])[j]);
+        float s = 0.0f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float e = expf(reinterpret_cast<const float*>(&zv[c])[j] - m);
+            prob[c][j] = e;
+            s += e;
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) prob[c][j] = prob[c][j] / s;
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kThreads) mc_uncertainty_stream_kernel(PassPtrs ptrs, int K, int64_t S4, double* out,
+                                                                        float* umap) {
+    float var_acc = 0.0f;
+    unsigned int cnt = 0;
+    const float invK = 1.0f / (float)K;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < S4; g += (int64_t)gridDim.x * blockDim.x) {
+        float mean[C][4], m2[C][4], prob[C][4];
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { mean[c][j] = 0.0f; m2[c][j] = 0.0f; }
+        for (int k = 0; k < K; ++k) {
+            mc_probs4<C>(ptrs.p[k], S4, g, prob);
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mean[c][j] += prob[c][j];
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mean[c][j] *= invK;
+        for (int k = 0; k < K; ++k) {
+            mc_probs4<C>(ptrs.p[k], S4, g, prob);
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { float dlt = prob[c][j] - mean[c][j]; m2[c][j] = fmaf(dlt, dlt, m2[c][j]); }
+        }
+        float4 uo;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) var_acc += m2[c][j] * invK;
+            const float mean1 = mean[1][j];
             float u = -1.0f * (mean1 * logf(mean1 + 1e-6f));
             cnt += (u > 0.01f) ? 1u : 0u;
             reinterpret_cast<float*>(&uo)[j] = u;
@@ -233,15 +319,21 @@ extern "C" int fpl_argmax_label(const float* logits, uint8_t* label, int b, int 
 
 extern "C" int fpl_mc_uncertainty(const float* const* h_logits_k, int k, int c, int64_t spatial, double* out,
                                   float* uncertainty_map, void* stream) {
-    FPL_REQUIRE(k >= 1 && k <= kMaxK, "fpl_mc_uncertainty: K=%d passes not in [1,%d]", k, kMaxK);
+    FPL_REQUIRE(k >= 1 && k <= kMaxKStream, "fpl_mc_uncertainty: K=%d passes not in [1,%d]", k, kMaxKStream);
     FPL_REQUIRE(spatial % 4 == 0, "fpl_mc_uncertainty: spatial size %lld must be a multiple of 4", (long long)spatial);
     PassPtrs ptrs;
-    for (int i = 0; i < kMaxK; ++i) ptrs.p[i] = i < k ? h_logits_k[i] : nullptr;
+    for (int i = 0; i < kMaxKStream; ++i) ptrs.p[i] = i < k ? h_logits_k[i] : nullptr;
     int64_t s4 = spatial / 4;
-    FPL_DISPATCH_C(c, (mc_uncertainty_kernel<CC><<<grid_for(s4), kThreads, 0, (cudaStream_t)stream>>>(ptrs, k, s4, out, uncertainty_map)));
+    if (k <= kMaxK) {
+        FPL_DISPATCH_C(c, (mc_uncertainty_kernel<CC><<<grid_for(s4), kThreads, 0, (cudaStream_t)stream>>>(ptrs, k, s4, out, uncertainty_map)));
+    } else {
+        FPL_DISPATCH_C(c, (mc_uncertainty_stream_kernel<CC><<<grid_for(s4), kThreads, 0, (cudaStream_t)stream>>>(ptrs, k, s4, out, uncertainty_map)));
+    }
     FPL_LAUNCH_CHECK();
     return 0;
 }
+
+extern "C" int fpl_mc_uncertainty_max_passes(void) { return kMaxKStream; }
 
 extern "C" int fpl_agree_weight(const float* logits_tgt, const float* logits_src, uint8_t* label_tgt,
                                 uint8_t* label_src, float* weight, int fold_image_weight, float image_weight,

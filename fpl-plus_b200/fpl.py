@@ -24,12 +24,21 @@ def pseudo_label(logits):
     return out
 
 
+def max_mc_passes():
+    """Largest K of ``mc_uncertainty`` (the reference hard-codes 6, agent_seg.py:898); callers validate
+    ``fpl_mc_passes`` against it before running the K forwards."""
+    from . import lib as _lib
+    return int(_lib.load().fpl_mc_uncertainty_max_passes())
+
+
 def mc_uncertainty(logit_passes, want_map=False):
     """K MC-dropout logits maps of one volume (each [1,C,D,H,W] CUDA fp32).
     Returns (stats, umap): stats is a float64 CUDA tensor [2] = (sum of variances, boundary count)
     -- no host sync here; ``finish_uncertainty`` turns it into the reference's ``uncer_one``."""
     passes = [p.float().contiguous() for p in logit_passes]
     k = len(passes)
+    if not 1 <= k <= max_mc_passes():
+        raise ValueError("mc_uncertainty: %d passes not in [1, %d]" % (k, max_mc_passes()))
     _b, c = passes[0].shape[:2]
     if passes[0].shape[0] != 1:
         raise ValueError("mc_uncertainty expects one volume per call (batch 1), as the reference test loader")

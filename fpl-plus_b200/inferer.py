@@ -98,6 +98,11 @@ class Inferer(object):
                 self._side = torch.cuda.Stream()
             # each lane accumulates into its own volume (windows of the two lanes may overlap): deterministic sums
             accs1, cnt1 = [torch.zeros_like(acc) for _ in range(K)], torch.zeros_like(cnt)
+            # stale weight images are re-staged HERE, on the main stream, before the side stream forks: lane 0 would
+            # otherwise stage them lazily after the fork and lane 1 could read half-written images
+            prepare = getattr(self.model, "prepare_inference", None)
+            if prepare is not None:
+                prepare((b,) + tuple(image.shape[1:2]) + tuple(win))
             self._side.wait_stream(main)
             group = max(1, group // 2)
         lane = 0
@@ -133,6 +138,8 @@ class Inferer(object):
         """Logits [B,class_num,D,H,W] on ``image.device`` (infer_func.py:188-222).  ``mc_passes`` = K > 1: the K
         MC-dropout passes of agent_seg.py:897-911 over the same volume in one sweep (a list of K logits volumes)."""
         self.model = model
+        if mc_passes > 1 and hasattr(model, "kMaxMcRepeats") and mc_passes > model.kMaxMcRepeats:
+            raise ValueError("mc_passes = %d exceeds %d" % (mc_passes, model.kMaxMcRepeats))
         tta_mode = self.config.get('tta_mode', 0)
         if tta_mode not in (0, 1):
             raise ValueError("Undefined tta_mode {0:}".format(tta_mode))

@@ -83,6 +83,7 @@ _SIGNATURES = {
     "fpl_dice_ce_grad": (_I, [_P, _P, _P, _P, _F, _F, _F, _P, _P, _P, _I, _I, _L, _P]),
     "fpl_argmax_label": (_I, [_P, _P, _I, _I, _L, _P]),
     "fpl_mc_uncertainty": (_I, [ctypes.POINTER(c_void_p), _I, _I, _L, _P, _P, _P]),
+    "fpl_mc_uncertainty_max_passes": (_I, []),
     "fpl_agree_weight": (_I, [_P, _P, _P, _P, _P, _I, _F, _P, _I, _L, _P]),
     "fpl_window_accumulate": (_I, [_P, _P, _P] + [_I] * 13 + [_F, _P]),
     "fpl_window_normalize": (_I, [_P, _P, _F, _L, _P]),

@@ -454,6 +454,13 @@ class UNet2D5_dsbn(nn.Module):
             ent[0] = -1
         self._head_dirty = True
 
+    def prepare_inference(self, shape):
+        """Stage every stale weight image for no-grad forwards of inputs shaped ``shape`` [N,C,D,H,W] on the CURRENT
+        stream.  Callers that fan no-grad forwards out over several streams (Inferer's two lanes) call this before
+        the fork, so no lane stages lazily while another reads the images."""
+        self._note_depths(self._geometry(tuple(shape)))
+        self._refresh_weight_images(with_dgrad=False)
+
     def _tc_convs(self):
         out = []
         for u1, u2 in self._down_units + self._up_units:

@@ -308,6 +308,9 @@ int fpl_argmax_label(const float* logits, uint8_t* label, int b, int c, int64_t 
  * variance over classes, boundary voxel count), optional uncertainty map fp32[spatial]. */
 int fpl_mc_uncertainty(const float* const* h_logits_k, int k, int c, int64_t spatial,
                        double* out, float* uncertainty_map, void* stream);
+/* Largest K fpl_mc_uncertainty accepts (agent_seg.py:898 hard-codes 6): the host validates
+ * `fpl_mc_passes` against it BEFORE running the K forwards. */
+int fpl_mc_uncertainty_max_passes(void);
 /* Two logits maps (target pass, fake-source pass) -> two uint8 label maps and the
  * agreement weight 1 - 0.5*[a != b]; if fold_image_weight != 0 the weight is folded
  * as set_weight_ does: (w < 1 ? 0 : w) * image_weight.  out_count (int64[1], may be

@@ -116,3 +116,37 @@ def test_network_plan_on_cpu_gradient_sets_and_mc_split():
     assert net._first_dropout_level() == 2
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 1, 16, 32, 32), domain_label=torch.zeros(1, dtype=torch.long))      # CPU tensor: no fallback
+
+
+def test_training_all_copies_the_graphs_static_dice_output():
+    """in CUDA-graph mode train_step returns the graph's STATIC output tensors; training_all must not
+    alias them (the first step of a round used to be replaced by the second).  Host logic only: a fake train_step
+    that rewrites one static buffer per call, like a replay does."""
+    cfg = {"dataset": {"tensor_type": "float"}, "network": {"num_domains": 2, "class_num": 2},
+           "training": {"iter_valid": 3}, "testing": {}}
+    ag = A.SegmentationAgent(cfg, "train")
+    ag.device = torch.device("cpu")
+
+    class _Net(object):
+        def train(self):
+            pass
+    ag.net = _Net()
+    ag.train_loaders = [[{"k": 0}], [{"k": 1}]]
+    static_loss = torch.zeros(())
+    static_dice = [torch.zeros(2, dtype=torch.float64), torch.zeros(2, dtype=torch.float64)]
+    calls = []
+
+    def fake_train_step(batches):
+        i = len(calls)
+        calls.append(batches)
+        static_loss.fill_(1.0 + i)
+        static_dice[0].copy_(torch.tensor([0.1 * (i + 1), 0.2 * (i + 1)], dtype=torch.float64))
+        static_dice[1].copy_(torch.tensor([0.3 * (i + 1), 0.0], dtype=torch.float64))
+        return static_loss, static_dice
+    ag.train_step = fake_train_step
+    out = ag.training_all()
+    assert len(calls) == 3
+    assert abs(out["loss"] - (1 + 2 + 3) / 3 / 2) < 1e-6
+    # mean over the 3 steps, then over the 2 domains
+    expect = (np.array([0.2, 0.4]) + np.array([0.6, 0.0])) / 2
+    np.testing.assert_allclose(out["class_dice"], expect, rtol=1e-12)

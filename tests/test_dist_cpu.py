@@ -57,7 +57,23 @@ def _worker(rank, world, port, q):
         local = {nm: table[nm] for nm in A.shard_round_robin(names, ag.rank, ag.world)}
         merged = ag._gather_dict(local)
         srt = fpl.sort_uncertainty(merged)
-        q.put((rank, ok_avg, n_buckets, len(local), [nm for _v, nm in srt], ag.world))
+        # ---- rank 0's parameters / BatchNorm buffers and validation scalars on every rank ----
+        torch.manual_seed(7 + rank)                          # ranks start from DIFFERENT weights and running statistics
+        ag.device = torch.device("cpu")
+        ag.net = torch.nn.Sequential(torch.nn.Conv3d(1, 4, 3), torch.nn.BatchNorm3d(4))
+        ag.net[1].running_mean.normal_()
+        ag.net[1].num_batches_tracked.fill_(5 + rank)
+        ag._broadcast_state()
+        state = torch.cat([t.detach().double().reshape(-1) for t in list(ag.net.parameters()) + list(ag.net.buffers())])
+        all_states = [torch.empty_like(state) for _ in range(world)]
+        dist.all_gather(all_states, state)
+        ok_bcast = all(torch.equal(s_, all_states[0]) for s_ in all_states) and int(ag.net[1].num_batches_tracked) == 5
+        ag.net[1].running_var.fill_(1.0 + rank)              # rank-local BN statistics diverge again during training
+        ag._broadcast_state(buffers_only=True)
+        ok_bcast = ok_bcast and float(ag.net[1].running_var[0]) == 1.0
+        scal = ag._agree_scalars({"loss": 0.5 + rank, "avg_dice": 0.25 * (rank + 1), "class_dice": np.array([0.1, 0.4]) * (rank + 1)})
+        ok_bcast = ok_bcast and scal["loss"] == 0.5 and scal["avg_dice"] == 0.25 and np.allclose(scal["class_dice"], [0.1, 0.4])
+        q.put((rank, ok_avg and ok_bcast, n_buckets, len(local), [nm for _v, nm in srt], ag.world))
     finally:
         dist.destroy_process_group()
 

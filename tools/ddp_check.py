@@ -18,11 +18,65 @@ def checksum(net):
                        [p.detach().double().abs().sum() for p in net.parameters()])
 
 
+def grads_of(agent, batches):
+    """Gradients (flat fp64 copy) of one training_all forward/backward of `batches`, optimiser untouched."""
+    agent.optimizer.zero_grad(set_to_none=True)
+    total = None
+    for d, data in enumerate(batches):
+        x, y = agent._to_device(data["image"]), agent._to_device(data["label_prob"])
+        out = agent.net(x, domain_label=d * torch.ones(x.shape[0], dtype=torch.long))
+        loss_d = agent.get_loss_value(data, out, y, agent.fpl_uda)
+        total = loss_d if total is None else total + loss_d
+    (total / len(batches)).backward()
+    if agent.reducer is not None:
+        agent.reducer.finish()
+    torch.cuda.synchronize()
+    return {n: p.grad.detach().double().clone() for n, p in agent.net.named_parameters() if p.grad is not None}
+
+
+def grad_mean_check(agent, rank, world):
+    """The all-reduced gradient of this rank's step == mean over ranks of the gradients each rank's batch gives in a
+    single process (same weights everywhere): what nn.DataParallel's gather-then-backward amounts to per sample
+    group (agent_seg.py:695), up to the per-rank Dice normalisation documented in DESIGN.md section 4."""
+    small = (16, 64, 64)
+    per_rank = [[bench.make_batch(500 + r * 2, 2, small, False, False), bench.make_batch(501 + r * 2, 2, small, True, False)]
+                for r in range(world)]
+    reducer, hook, wait = agent.reducer, agent.net.grad_ready_hook, agent.net.grad_wait_hook
+    drops = [m for m in agent.net.modules() if type(m) == torch.nn.Dropout]
+    for m in drops:
+        m.eval()                                                     # identical arithmetic in every pass below
+    averaged = grads_of(agent, per_rank[rank])                       # with the overlapped NCCL all-reduce
+    agent.reducer, agent.net.grad_ready_hook, agent.net.grad_wait_hook = None, None, None
+    singles = [grads_of(agent, per_rank[r]) for r in range(world)]   # no communication: every rank computes all of them
+    agent.reducer, agent.net.grad_ready_hook, agent.net.grad_wait_hook = reducer, hook, wait
+    agent.optimizer.zero_grad(set_to_none=True)
+    for m in drops:
+        m.train()
+    worst = ("", 0.0)
+    for k, g in averaged.items():
+        ref = sum(s[k] for s in singles) / world
+        err = float((g - ref).norm() / (ref.norm() + 1e-30))
+        if err > worst[1]:
+            worst = (k, err)
+    local_vs_avg = float((singles[rank]["out_conv.weight"] - averaged["out_conv.weight"]).norm()
+                         / averaged["out_conv.weight"].norm())
+    if worst[1] > 1e-3:
+        raise SystemExit("rank %d: all-reduced gradient differs from the mean of the per-rank gradients: %s rel %.3e" % (
+            (rank,) + worst))
+    if local_vs_avg < 1e-3:
+        raise SystemExit("rank %d: the averaged gradient equals the local one -- no all-reduce happened" % rank)
+    dist.barrier()
+    if rank == 0:
+        print("GRAD MEAN OK: worst rel_l2 %.2e (%s); local vs averaged %.2e" % (worst[1], worst[0], local_vs_avg), flush=True)
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
     agent = bench.build_agent("train", world)
+    if os.environ.get("GRAD_MEAN", "0") != "0":
+        grad_mean_check(agent, rank, world)
     host = [bench.make_batch(100 + rank * 2, bench.BATCH, bench.PATCH, False, True),
             bench.make_batch(101 + rank * 2, bench.BATCH, bench.PATCH, True, True)]
     steps = int(os.environ.get("STEPS", "7"))
