@@ -109,7 +109,8 @@ def test_full_size_train_step_properties(cfg):
 
 def test_full_size_filter_kernels_bit_exact():
     """configs[1] volume size (48x256x256): argmax pseudo labels, agreement weights (+ image-weight folding) and the
-    disagreement count bit-exact against the numpy oracle; MC uncertainty statistics within fp32 summation error."""
+    disagreement count bit-exact against the numpy oracle (the MC-dropout statistics at this size:
+    test_full_size_mc_uncertainty_and_five_class_filter below)."""
     from oracle import fpl_filter
     from fplplus_b200 import fpl
     r = np.random.Generator(np.random.PCG64(17))
@@ -133,6 +134,44 @@ def test_full_size_filter_kernels_bit_exact():
                                   fpl_filter.set_weight_(np.float32(0.42), ref_w.astype(np.float32)))
     assert int(cnt) == int((ga != gb).sum())
     assert np.array_equal(ra[5, 7, :64], np.zeros(64, dtype=ra.dtype))
+
+
+@pytest.mark.parametrize("c,k,shape", [(2, 6, (48, 256, 256)), (5, 6, (24, 160, 160)), (2, 12, (16, 64, 64)), (5, 16, (8, 32, 32))],
+                         ids=["configs1_K6_C2_48x256x256", "mmwhs_K6_C5", "K12_streaming", "K16_C5_streaming"])
+def test_full_size_mc_uncertainty_and_five_class_filter(c, k, shape):
+    """K MC-dropout logits volumes -> (sum of variances, boundary count, uncertainty map) against the numpy restatement
+    of agent_seg.py:911-929, at the configs[1] volume size with the reference's K = 6, for 5 classes (configs[4]) and
+    for K > 8 (the streaming kernel; ADVICE r1: 9..16 passes used to fail after all forwards had run).  With 5 classes
+    also the argmax labels / multi-class agreement weights (w = 1 - 0.5*[a != b])."""
+    from oracle import fpl_filter
+    from fplplus_b200 import fpl
+    r = np.random.Generator(np.random.PCG64(100 + 10 * c + k))
+    base = (r.standard_normal((1, c) + shape) * 2).astype(np.float32)
+    passes = [(base + 0.6 * r.standard_normal(base.shape)).astype(np.float32) for _ in range(k)]
+    assert k <= fpl.max_mc_passes()
+    stats, umap = fpl.mc_uncertainty([torch.from_numpy(p).to(DEV) for p in passes], want_map=True)
+    ref = fpl_filter.mc_uncertainty(passes)
+    v, b = stats.tolist()
+    ref_map = ref["uncertainty_map"].reshape(shape)
+    near = int((np.abs(ref_map - 0.01) < 1e-6).sum())
+    assert abs(int(b) - ref["boundary"]) <= near
+    np.testing.assert_allclose(v, float(ref["vars"]), rtol=2e-5)
+    np.testing.assert_allclose(umap.cpu().numpy(), ref_map, rtol=1e-4, atol=1e-7)
+    got = fpl.finish_uncertainty(stats)
+    assert abs(float(got) - float(ref["uncer_one"])) <= 3e-5 * abs(float(ref["uncer_one"])) + 1e-12
+    with pytest.raises(ValueError):
+        fpl.mc_uncertainty([torch.from_numpy(passes[0]).to(DEV)] * (fpl.max_mc_passes() + 1))
+    if c > 2:
+        za, zb = passes[0], passes[1]
+        la, lb, w, cnt = fpl.agreement_weight(torch.from_numpy(za).to(DEV), torch.from_numpy(zb).to(DEV))
+        ra, rb = fpl_filter.pseudo_label(za)[0], fpl_filter.pseudo_label(zb)[0]
+        ga, gb = la.cpu().numpy().reshape(ra.shape), lb.cpu().numpy().reshape(rb.shape)
+        assert (ga != ra).sum() <= 2 and (gb != rb).sum() <= 2        # last-ulp expf ties only (see the test above)
+        assert ga.max() == c - 1
+        np.testing.assert_array_equal(w.cpu().numpy().reshape(ra.shape).astype(np.float64),
+                                      fpl_filter.agreement_weight_multiclass(ga, gb))
+        assert int(cnt) == int((ga != gb).sum())
+        np.testing.assert_array_equal(fpl.pseudo_label(torch.from_numpy(za).to(DEV)).cpu().numpy()[0], ga)
 
 
 def test_full_size_window_stitching_identity():
