@@ -137,12 +137,14 @@ def get_optimizer(name, net_params, optim_params, capturable=False):
         return torch.optim.SGD(net_params, lr, momentum=momentum, weight_decay=weight_decay)
     if keyword_match(name, "Adam"):
         params = list(net_params)
-        # same update rule (coupled L2); on CUDA use torch's single-launch multi-tensor implementation
-        fused = len(params) > 0 and all(p.is_cuda for p in params)
-        if fused and capturable:
-            lr = torch.tensor(float(lr), dtype=torch.float32, device=params[0].device)
-            return torch.optim.Adam(params, lr, weight_decay=weight_decay, fused=True, capturable=True)
-        return torch.optim.Adam(params, lr, weight_decay=weight_decay, fused=fused)
+        # same update rule (coupled L2, per-parameter step counters, torch's state_dict layout) as ONE launch of the
+        # library's multi-tensor kernel (optim.FusedAdam, csrc/adam.cu); CPU parameters keep torch's implementation
+        if len(params) > 0 and all(p.is_cuda for p in params):
+            from .optim import FusedAdam
+            if capturable:
+                lr = torch.tensor(float(lr), dtype=torch.float32, device=params[0].device)
+            return FusedAdam(params, lr, weight_decay=weight_decay)
+        return torch.optim.Adam(params, lr, weight_decay=weight_decay)
     if keyword_match(name, "RMSprop"):
         return torch.optim.RMSprop(net_params, lr, momentum=momentum, weight_decay=weight_decay)
     raise ValueError("unsupported optimizer {0:}".format(name))
@@ -386,6 +388,12 @@ class SegmentationAgent(object):
         if getattr(self, 'checkpoint', None) is not None:
             self.optimizer.load_state_dict(self.checkpoint['optimizer_state_dict'])
             last_iter = self.checkpoint['iteration'] - 1
+            if getattr(self, "_graph_capable", False):
+                # a checkpoint written by torch.optim.Adam carries a float learning rate: the captured step reads it
+                # from device memory
+                for gph in self.optimizer.param_groups:
+                    if not torch.is_tensor(gph['lr']):
+                        gph['lr'] = torch.tensor(float(gph['lr']), dtype=torch.float32, device=gph['params'][0].device)
         self._host_it = last_iter + 1
         if self.scheduler is None:
             opt_params["last_iter"] = last_iter

@@ -120,6 +120,18 @@ int fpl_wgrad_tapmajor_to_dw_batch(int count, const float* const* h_scratch, flo
  * passes run on two streams).  max_numel = the largest count (grid sizing). */
 int fpl_grad_scatter_add(float* dst, const float* src, const int* d_table, int segments, int max_numel, void* stream);
 
+/* ---- optimiser: torch.optim.Adam(params, lr, weight_decay=wd) of net_run/get_optimizer.py:16-17 (coupled L2) ----------
+ * ONE launch over all tensors.  d_segs: DEVICE table of nseg rows of 48 bytes
+ *   { float* param; const float* grad; float* exp_avg; float* exp_avg_sq; float* step; int32 numel; int32 pad }
+ * (all pointers 16-byte aligned); d_chunks: DEVICE int32 [nchunks][2] = {row, first element}, one entry per
+ * fpl_adam_chunk_elems() elements of every tensor.  step is torch's per-parameter step counter (fp32, incremented here
+ * after the update); the learning rate is *lr_dev when lr_dev != NULL (CUDA-graph replays under MultiStepLR,
+ * get_optimizer.py:50-54), else lr_host.  d_done_counter: DEVICE uint32 zero-initialised once by the caller. */
+int fpl_adam_multi_tensor(const void* d_segs, int nseg, const int* d_chunks, int nchunks, const float* lr_dev,
+                          float lr_host, float beta1, float beta2, float eps, float weight_decay,
+                          unsigned int* d_done_counter, void* stream);
+int fpl_adam_chunk_elems(void);
+
 /* ---- inference epilogue: eval-mode BatchNorm + PReLU + Dropout folded into the conv kernels --------------------------
  * In eval mode nn.BatchNorm3d is the per-channel affine map of the running statistics (dsbn.py:54-57), so
  * conv -> BN -> PReLU -> Dropout (unet2d5_dsbn.py:75-81) is  a = dropout(prelu(acc * scale + shift))  with
