@@ -405,24 +405,34 @@ struct PrepBatch {
 };
 
 namespace {
+// One thread per (output channel, input channel) PAIR: it reads the pair's kd*9 taps as one contiguous run of the PyTorch
+// layout (108 B for k3: whole sectors) and writes them to the kd*9 tap planes of the image; consecutive threads are
+// consecutive image elements of a tap plane, so every warp store is one 64-byte run.  (The element-per-thread form
+// of prep_weight_kernel costs 7 integer divisions and one 32-byte sector per 4-byte read: 112 us per step for the 36
+// images of the network, at the head of every optimiser step.)
 __global__ void prep_weight_batch_kernel(const __grid_constant__ PrepBatch B) {
     const int e = blockIdx.y;
     const float* __restrict__ w = B.w[e];
     __nv_bfloat16* image = B.image[e];
     const int cin_eff = B.cin_eff[e], cout_eff = B.cout_eff[e], kd = B.kd[e], nb = B.nb[e], kc = B.kc[e];
-    const int T = kd * 9, nchunks = cin_eff / kc, total = B.total[e];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        int t = i;
-        int el = t % 8; t /= 8;
-        int nrow = t % nb; t /= nb;
-        int k8 = t % (kc / 8); t /= (kc / 8);
-        int t9 = t % 9; t /= 9;
-        int kdi = t % kd; t /= kd;
-        int q = t % nchunks;
-        int sl = t / nchunks;
-        int out = sl * nb + nrow, in = q * kc + k8 * 8 + el, tap = kdi * 9 + t9;
-        float v = B.tf[e] ? w[((int64_t)in * cout_eff + out) * T + (T - 1 - tap)] : w[((int64_t)out * cin_eff + in) * T + tap];
-        image[i] = __float2bfloat16_rn(v);
+    const int T = kd * 9, nchunks = cin_eff / kc;
+    const int plane = (kc / 8) * nb * 8;                  // elements of one tap plane of one (slice, chunk)
+    const int pairs = cin_eff * cout_eff;
+    const bool tf = B.tf[e] != 0;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < pairs; r += gridDim.x * blockDim.x) {
+        const int sq = r / plane, rem = r - sq * plane;   // (slice, chunk) and position inside a tap plane
+        const int el = rem & 7, nrow = (rem >> 3) % nb, k8 = (rem >> 3) / nb;
+        const int q = sq % nchunks, sl = sq / nchunks;
+        const int out = sl * nb + nrow, in = q * kc + k8 * 8 + el;
+        const float* src = tf ? w + ((int64_t)in * cout_eff + out) * T : w + ((int64_t)out * cin_eff + in) * T;
+        __nv_bfloat16* dst = image + (int64_t)sq * T * plane + rem;
+        if (kd == 3) {
+#pragma unroll
+            for (int tap = 0; tap < 27; ++tap) dst[(int64_t)tap * plane] = __float2bfloat16_rn(__ldg(src + (tf ? 26 - tap : tap)));
+        } else {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) dst[(int64_t)tap * plane] = __float2bfloat16_rn(__ldg(src + (tf ? 8 - tap : tap)));
+        }
     }
 }
 }  // namespace
@@ -446,10 +456,11 @@ extern "C" int fpl_conv3d_prep_weight_batch(int count, const float* const* h_w, 
         B.total[e] = c.nslices * c.nchunks * h_kd[e] * c.b_bytes / 2;
         if (B.total[e] > max_total) max_total = B.total[e];
     }
-    // one thread per 1-7 image elements: the gather from the PyTorch layout is latency bound, so the largest layers
-    // (1.77 M elements) want thousands of threads in flight; blocks beyond a small layer's size exit at once
-    int bx = (max_total + 255) / 256;
+    // one thread per (out, in) pair of the largest layer (65 536 pairs at 256 -> 256); blocks beyond a small layer's
+    // pair count exit at once
+    int bx = (max_total / 9 + 255) / 256;
     if (bx > 512) bx = 512;
+    if (bx < 1) bx = 1;
     prep_weight_batch_kernel<<<dim3(bx, count), 256, 0, (cudaStream_t)stream>>>(B);
     FPL_LAUNCH_CHECK();
     return 0;

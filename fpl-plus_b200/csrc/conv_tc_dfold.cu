@@ -402,25 +402,27 @@ struct DfPrepBatch {
     int cin_eff[kMaxDfBatch], cout_eff[kMaxDfBatch], total[kMaxDfBatch];
     unsigned char tf[kMaxDfBatch], nb[kMaxDfBatch];
 };
+// one thread per (out, in) pair: 27 contiguous source floats -> 27 image positions (see prep_weight_batch_kernel)
 __global__ void dfold_prep_batch_kernel(const __grid_constant__ DfPrepBatch B) {
     const int e = blockIdx.y;
     const float* __restrict__ w = B.w[e];
     __nv_bfloat16* image = B.image[e];
-    const int cin_eff = B.cin_eff[e], cout_eff = B.cout_eff[e], nb = B.nb[e], total = B.total[e], tf = B.tf[e];
+    const int cin_eff = B.cin_eff[e], cout_eff = B.cout_eff[e], nb = B.nb[e], tf = B.tf[e];
     const int ksteps = cin_eff / 16, n3 = 3 * nb;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        int t = i;
-        const int el = t % 8; t /= 8;
-        const int nn = t % n3; t /= n3;
-        const int k8 = t % 2; t /= 2;
-        const int j = t % ksteps; t /= ksteps;
-        const int t9 = t % 9;
-        const int sl = t / 9;
-        const int in = j * 16 + k8 * 8 + el;
-        const int jj = nn / nb, out = sl * nb + nn % nb;
-        const int tap = (2 - jj) * 9 + t9;
-        const float v = tf ? w[((int64_t)in * cout_eff + out) * 27 + (26 - tap)] : w[((int64_t)out * cin_eff + in) * 27 + tap];
-        image[i] = __float2bfloat16_rn(v);
+    const int pairs = cin_eff * cout_eff;                 // nslices == 1: out == n
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < pairs; r += gridDim.x * blockDim.x) {
+        const int el = r & 7, n = (r >> 3) % nb, jk = (r >> 3) / nb;      // jk = j * 2 + k8
+        const int in = jk * 8 + el, out = n;
+        const float* src = tf ? w + ((int64_t)in * cout_eff + out) * 27 : w + ((int64_t)out * cin_eff + in) * 27;
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj) {
+#pragma unroll
+            for (int t9 = 0; t9 < 9; ++t9) {
+                const int tap = (2 - jj) * 9 + t9;
+                const float v = __ldg(src + (tf ? 26 - tap : tap));
+                image[(((int64_t)t9 * ksteps * 2 + jk) * n3 + jj * nb + n) * 8 + el] = __float2bfloat16_rn(v);
+            }
+        }
     }
 }
 }  // namespace
@@ -440,8 +442,9 @@ extern "C" int fpl_conv3d_dfold_prep_weight_batch(int count, const float* const*
         B.tf[e] = (unsigned char)tf; B.nb[e] = (unsigned char)c.nb; B.total[e] = c.nslices * c.b_bytes / 2;
         if (B.total[e] > max_total) max_total = B.total[e];
     }
-    int bx = (max_total + 255) / 256;
+    int bx = (max_total / 27 + 255) / 256;
     if (bx > 32) bx = 32;
+    if (bx < 1) bx = 1;
     dfold_prep_batch_kernel<<<dim3(bx, count), 256, 0, (cudaStream_t)stream>>>(B);
     FPL_LAUNCH_CHECK();
     return 0;
