@@ -58,22 +58,33 @@ def peaks():
 # synthetic data (synthetic_data.py is the seeded generator shared with the parity tests; it is data
 # generation, not the measured path, and not part of oracle/)
 # --------------------------------------------------------------------------------------------
-def make_batch(seed, n, shape, weighted, pinned):
+def make_batch(seed, n, shape, weighted, pinned, compact=False):
+    """One batch dict.  Default: the PyMIC loader layout (io/nifty_dataset.py:171-218: 'label_prob' fp32 one-hot,
+    'pixel_weight' fp32 already folded with the image weight).  ``compact``: the device data path of SURVEY 8 f-3 --
+    'label' uint8 [N,D,H,W], 'pixel_weight' uint8 agreement code [N,1,D,H,W] (0/1/2 = 0/0.5/1), 'image_weight' fp32 [N];
+    one-hot and NiftyDataset.set_weight_ happen inside the loss kernels.  Same voxels, same weights, bit for bit."""
     import synthetic_data as synth
     x = torch.from_numpy(synth.synth_image(n, 1, shape, seed=seed))
     lab = synth.synth_label(n, 2, shape, seed=seed)
-    d = {"image": x, "label_prob": torch.from_numpy(synth.one_hot(lab, 2))}
+    if compact:
+        d = {"image": x, "label": torch.from_numpy(lab)}
+    else:
+        d = {"image": x, "label_prob": torch.from_numpy(synth.one_hot(lab, 2))}
     if weighted:
         pw, iw = synth.synth_pixel_weight(lab, seed=seed)
-        d["pixel_weight"] = torch.from_numpy(pw)
-        d["image_weight"] = torch.from_numpy(iw)
+        if compact:
+            d["pixel_weight"] = torch.from_numpy(np.where(pw > 0, 2, 1).astype(np.uint8))
+            d["image_weight"] = torch.from_numpy(iw.astype(np.float32))
+        else:
+            d["pixel_weight"] = torch.from_numpy(pw)
+            d["image_weight"] = torch.from_numpy(iw)
     if pinned:
-        d = {k: (v.pin_memory() if v.dtype == torch.float32 else v) for k, v in d.items()}
+        d = {k: (v.pin_memory() if v.dtype in (torch.float32, torch.uint8) else v) for k, v in d.items()}
     return d
 
 
 def batch_bytes(b):
-    return sum(v.numel() * v.element_size() for k, v in b.items() if k != "image_weight")
+    return sum(v.numel() * v.element_size() for k, v in b.items() if k != "image_weight" or v.dtype == torch.float32)
 
 
 # --------------------------------------------------------------------------------------------
@@ -136,6 +147,11 @@ def _dfold_work(a):
     return 2.0 * n * d * h * w * cin * cout * 27, float(n * d * h * w * (cin + cout) * 2)
 
 
+def _k311_work(a, off):
+    n, d, h, w, cin, cout = a[off:off + 6]
+    return 2.0 * n * d * h * w * cin * cout * 3, float(n * d * h * w * (cin + cout) * 2)
+
+
 WORK = {   # entry point -> (flops, algorithmic bytes) from its argument tuple
     "fpl_conv3d_tc": lambda a: _conv_work(a, 9),
     "fpl_conv3d_tc_dfold": _dfold_work,
@@ -143,7 +159,13 @@ WORK = {   # entry point -> (flops, algorithmic bytes) from its argument tuple
     "fpl_conv3d_wgrad": lambda a: _conv_work(a, 7),
     "fpl_conv3d_wgrad_tc": lambda a: _conv_work(a, 7),
     "fpl_conv3d_wgrad_tc_tapmajor": lambda a: _conv_work(a, 7),
+    "fpl_conv3d_wgrad_tc_k311": lambda a: _k311_work(a, 7),
 }
+# entry points that launch the SAME kernel are one roofline population (the ncu capture sees kernel names):
+# conv3d_wgrad_tc_kernel serves the k3 / k(1,3,3) wgrads, the head wgrad and the stem's k(3,1,1) wgrad
+KERNEL_OF = {"fpl_conv3d_wgrad_tc_tapmajor": "conv3d_wgrad_tc_kernel", "fpl_conv3d_wgrad_tc": "conv3d_wgrad_tc_kernel",
+             "fpl_conv3d_wgrad_tc_k311": "conv3d_wgrad_tc_kernel", "fpl_conv3d_tc": "conv3d_tc_kernel",
+             "fpl_conv3d_tc_dfold": "conv3d_tc_dfold_kernel"}
 
 
 def _dsbn_work(bytes_per_elem, lo, hi):
@@ -159,7 +181,29 @@ WORK.update({
     "fpl_dsbn_act_bwd_reduce": _dsbn_work(4, -6, -1),        # read y, g
     "fpl_dsbn_act_bwd_apply_fin": _dsbn_work(6, -10, -5),    # read y, g, write dy
 })
-HBM_KERNELS = ("fpl_dsbn_bn_act_fwd", "fpl_dsbn_act_bwd_reduce", "fpl_dsbn_act_bwd_apply_fin")
+
+
+def _loss_work(reduce):
+    """fpl_dice_ce_{reduce,grad}_ex: logits 4C B/voxel + truth (4C fp32 one-hot or 1 uint8) + weight (4, 1 or 0);
+    the gradient pass also writes 4C (8C+4 / 12C+4 with the PyMIC layout, 4C+2 / 8C+2 with the device one)."""
+    def f(a):
+        soft_y, label, weight, code = a[1], a[2], a[3], a[4]
+        if reduce:
+            n, c, spatial = a[7], a[8], a[9]
+            wr = 0
+        else:
+            n, c, spatial = a[14], a[15], a[16]
+            if a[13] is None:                      # loss-only call (no dlogits): one thread, no streaming
+                return 0.0, 0.0
+            wr = 4 * c
+        per = 4 * c + (4 * c if soft_y is not None else 1) + (4 if weight is not None else (1 if code is not None else 0)) + wr
+        return 0.0, float(n) * spatial * per
+    return f
+
+
+WORK.update({"fpl_dice_ce_reduce_ex": _loss_work(True), "fpl_dice_ce_grad_ex": _loss_work(False)})
+HBM_KERNELS = ("fpl_dsbn_bn_act_fwd", "fpl_dsbn_act_bwd_reduce", "fpl_dsbn_act_bwd_apply_fin", "fpl_dice_ce_reduce_ex",
+               "fpl_dice_ce_grad_ex")
 
 
 def measured_traffic(kernel):
@@ -275,8 +319,10 @@ def run_ours(args):
 
     agent = build_agent("train", world)
     dev = agent.device
-    host = [make_batch(11 + rank * 2, BATCH, PATCH, False, True), make_batch(12 + rank * 2, BATCH, PATCH, True, True)]
-    resident = [{k: (v.to(dev) if torch.is_tensor(v) and v.dtype == torch.float32 else v) for k, v in b.items()}
+    compact = not args.fp32_onehot
+    host = [make_batch(11 + rank * 2, BATCH, PATCH, False, True, compact),
+            make_batch(12 + rank * 2, BATCH, PATCH, True, True, compact)]
+    resident = [{k: (v.to(dev) if torch.is_tensor(v) and v.dtype in (torch.float32, torch.uint8) else v) for k, v in b.items()}
                 for b in host]
     vox_per_step = 2 * BATCH * PATCH[0] * PATCH[1] * PATCH[2]
 
@@ -317,6 +363,21 @@ def run_ours(args):
     ms_e2e = max_over_ranks(ms_e2e)
     e2e_value = world * vox_per_step * args.steps / (ms_e2e / 1e3)
     h2d = sum(batch_bytes(b) for b in host)
+    # the same step fed with the PyMIC loader layout (fp32 one-hot labels + folded fp32 pixel weights): 2.5x the H2D bytes
+    e2e_alt = None
+    if compact and not args.quick:
+        host_alt = [make_batch(11 + rank * 2, BATCH, PATCH, False, True, False),
+                    make_batch(12 + rank * 2, BATCH, PATCH, True, True, False)]
+        state["i"] = 0
+        host_keep, host[:] = list(host), host_alt
+        for _ in range(5):
+            step_e2e()                                  # this batch signature has its own captured graph
+        ms_alt, _, _ = timed(step_e2e, args.steps, 0, barrier)
+        ms_alt = max_over_ranks(ms_alt)
+        e2e_alt = {"value": world * vox_per_step * args.steps / (ms_alt / 1e3), "unit": "voxels/s",
+                   "ms_per_step": ms_alt / args.steps, "h2d_bytes_per_step": sum(batch_bytes(b) for b in host_alt),
+                   "layout": "PyMIC loader layout: 'label_prob' fp32 one-hot + folded fp32 'pixel_weight'"}
+        host[:] = host_keep
 
     # ---- roofline of the dominant kernel: a second timed region of K EAGER steps (a graph replay has no per-kernel
     #      host hook) with CUDA events on the launching stream around every C-ABI call; same kernels, same shapes ----
@@ -344,18 +405,47 @@ def run_ours(args):
     kern = {k: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps,
                 "share_of_step": v[1] / args.steps / eager_step_ms} for k, v in agg.items()}
     roofline = None
-    conv = {k: v for k, v in agg.items() if k in WORK and v[1] > 0 and v[2] > 0}
+    conv = {}
+    for k, v in agg.items():
+        if k in WORK and v[1] > 0 and v[2] > 0:
+            kk = KERNEL_OF.get(k, k)
+            c = conv.setdefault(kk, [0, 0.0, 0.0, 0.0, []])
+            for i in range(4):
+                c[i] += v[i]
+            c[4].append(k)
     if conv:
         top = max(conv, key=lambda k: conv[k][1])
-        n, tot_ms, fl, by = conv[top]
+        n, tot_ms, fl, by, entries = conv[top]
         ach = fl / (tot_ms / 1e3) / 1e12
-        roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"],
-                    "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"], "traffic": measured_traffic(top),
-                    "traffic_note": "bytes per launch (dram read + write, ncu --set full, mean over the launches of one step)",
+        tr = measured_traffic(top)
+        roofline = {"kernel": top, "entry_points": sorted(entries), "bound": "tensor", "achieved": ach,
+                    "peak": pk["bf16_tflops_sustained"],
+                    "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"], "traffic": tr,
+                    "traffic_note": "bytes per launch (dram read + write from ncu --set full), mean over ALL launches of this "
+                                    "kernel in one train step -- the same population as achieved / algorithmic_mb_per_launch",
                     "peak_source": pk["source"] + " (sustained bf16, kernel timed inside a long step)",
                     "launches_per_step": n / args.steps, "avg_launch_ms": tot_ms / n,
                     "algorithmic_gflop_per_launch": fl / n / 1e9, "algorithmic_mb_per_launch": by / n / 1e6,
+                    "traffic_over_algorithmic": (tr / (by / n)) if tr else None,
                     "hbm_gbs_at_algorithmic_bytes": by / (tot_ms / 1e3) / 1e9}
+    # per-layer roofline of every conv launch class: bound = max(tensor time at the sustained bf16 peak, HBM time at the
+    # measured copy bandwidth) -- the C = 16/32 full-resolution layers are HBM-side of the ridge
+    layers = {}
+    for nm, (fl, by), e0, e1 in timer.records:
+        if fl > 0:
+            layers.setdefault((nm, fl, by), []).append(e0.elapsed_time(e1))
+    conv_layers = []
+    for (nm, fl, by), ts in layers.items():
+        t = sum(ts) / len(ts) / 1e3
+        t_tc, t_hbm = fl / (pk["bf16_tflops_sustained"] * 1e12), by / (pk["hbm_gbs"] * 1e9)
+        conv_layers.append({"entry": nm, "gflop": fl / 1e9, "mb": by / 1e6, "launches_per_step": len(ts) / args.steps,
+                            "avg_us": t * 1e6, "tflops": fl / t / 1e12, "gbs": by / t / 1e9,
+                            "bound": "tensor" if t_tc >= t_hbm else "hbm", "frac_of_bound": max(t_tc, t_hbm) / t})
+    conv_layers.sort(key=lambda r: -r["avg_us"] * r["launches_per_step"])
+    big = [r for r in conv_layers if r["gflop"] >= 1.0]
+    tw = sum(r["avg_us"] * r["launches_per_step"] for r in big)
+    conv_summary = {"time_weighted_frac_of_bound": (sum(r["frac_of_bound"] * r["avg_us"] * r["launches_per_step"] for r in big) / tw) if tw else None,
+                    "note": "min(TC, HBM) roofline per conv launch class (>= 1 GFLOP), weighted by its time in the eager step"}
     # HBM-bound kernels: GB/s at the algorithmic bytes, over all layers of the step and for the largest layer alone
     hbm = {}
     for name in HBM_KERNELS:
@@ -394,13 +484,25 @@ def run_ours(args):
                "host_enqueue_ms_per_step": host_ms, "eager_ms_per_step": eager_step_ms,
                "clocks": clk,
                "roofline": roofline,
+               "conv_layers": conv_layers[:24], "conv_layers_summary": conv_summary,
+               "e2e_fp32_onehot": e2e_alt,
                "hbm_kernels": hbm,
                "kernels": kern,
                "conv_tensor_util": {"achieved_tflops_over_step": world * 2 * BATCH * 179.9e9 / (step_ms / 1e3) / 1e12 / world,
                                     "peak_tflops": pk["bf16_tflops_sustained"]},
                "pl_filter": pl}
-        if not args.skip_cpu:
+        if not args.skip_cpu and world == 1:
             out["cpu_baseline"] = cpu_baseline(bounded_steps=12)
+        elif world > 1:
+            out["cpu_baseline"] = None
+            out["cpu_baseline_note"] = ("timed at N=1 only: under torchrun the other ranks would spin in a barrier for the "
+                                        "~15 s of CPU work and OMP_NUM_THREADS=1 starves the CPU arm; see --impl reference")
+        if not args.skip_cpu and world == 1 and pl is not None and not args.quick:
+            pl["cpu_baseline"] = pl_filter_cpu_baseline()
+        if world == 1 and not args.quick and not args.skip_torch:
+            out["torch_cuda_baseline"] = torch_cuda_baseline(dev, args)
+        if not args.skip_filter and not args.quick:
+            out["filter_kernels"] = filter_kernel_rooflines(dev, pk)
     if out is not None:
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -465,13 +567,106 @@ def bench_filter(agent, rank, world, barrier, max_over_ranks, args):
     ms = max_over_ranks(e0.elapsed_time(e1))
     net.train()
     vps = world * nvol / (ms / 1e3)
+    # FLOPs per volume: the reference runs 8 Inferer passes x 8 windows x 4 flips = 256 full forwards of 59.97 GFLOP
+    # (15.35 TFLOP).  forward_mc computes the dropout-free encoder prefix (block0 + block1 = 13.13 GFLOP) once for the
+    # 6 MC passes of a window batch, so 5 x 13.13 GFLOP per window forward set are NOT executed: 13.25 TFLOP.
+    executed_tflop = 32 * (2 * 59.97 + 6 * 59.97 - 5 * 13.13) / 1e3
     return {"metric": "pl_filter_volumes_per_s", "value": vps, "unit": "volumes/s", "ms_per_volume": ms / nvol,
             "volumes_timed_per_gpu": nvol, "forwards_per_volume": 256,
-            "conv_tflops": 15.35 * vps / world,
+            "conv_tflops": executed_tflop * vps / world, "executed_tflop_per_volume": executed_tflop,
+            "reference_equivalent_tflop_per_volume": 15.35, "reference_equivalent_tflops": 15.35 * vps / world,
             "workload": "VS-style 1x48x256x256 volume: dual-domain sliding-window inference (window 32x128x128, "
                         "4-flip TTA) + argmax labels + agreement pixel weights + 6 MC-dropout passes -> image "
                         "uncertainty (BASELINE.json configs[1]); host volumes in, u8 labels + fp32 weights + scalar out",
             "scaling": "weak (volumes sharded round-robin, no collective)"}
+
+
+# --------------------------------------------------------------------------------------------
+# HBM rooflines of the filter / stitching kernels (north_star (c)): CUDA events around every launch, inputs rotated over
+# enough buffers that no launch finds its data in the 126 MB L2
+# --------------------------------------------------------------------------------------------
+def filter_kernel_rooflines(dev, pk, iters=6):
+    from fplplus_b200 import fpl
+    from fplplus_b200.ops import call, ptr, stream_ptr
+    d, h, w = VOLUME
+    S, C, K = d * h * w, 2, 6
+    g = torch.Generator(device="cpu").manual_seed(5)
+    n_sets = 8                                              # 8 x 25 MB logits volumes x K: far beyond L2
+    vols = [torch.randn((1, C, d, h, w), generator=g).to(dev) for _ in range(n_sets + K)]
+    out = {}
+
+    def timeit(name, fn, nbytes):
+        fn(0)
+        torch.cuda.synchronize()
+        ts = []
+        for i in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(i + 1)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t = sorted(ts)[len(ts) // 2] / 1e3
+        out[name] = {"us": t * 1e6, "algorithmic_mb": nbytes / 1e6, "gbs": nbytes / t / 1e9,
+                     "frac_of_hbm_peak": nbytes / t / 1e9 / pk["hbm_gbs"]}
+
+    timeit("fpl_mc_uncertainty_K6_C2", lambda i: fpl.mc_uncertainty([vols[(i + k) % len(vols)] for k in range(K)]),
+           S * (4 * K * C))
+    timeit("fpl_agree_weight_C2", lambda i: fpl.agreement_weight(vols[(2 * i) % len(vols)], vols[(2 * i + 1) % len(vols)]),
+           S * (8 * C + 6))
+    timeit("fpl_argmax_label_C2", lambda i: fpl.pseudo_label(vols[(i * 3) % len(vols)]), S * (4 * C + 1))
+    # window accumulate: one 32x128x128 window of 2-class logits into the volume sums + visit counts (read patch, RMW out + count)
+    win = (32, 128, 128)
+    patches = [torch.randn((1, C) + win, generator=g).to(dev) for _ in range(4)]
+    accs = [torch.zeros((1, C, d, h, w), device=dev) for _ in range(n_sets)]
+    cnts = [torch.zeros((1, C, d, h, w), device=dev) for _ in range(n_sets)]
+    pv = win[0] * win[1] * win[2] * C
+
+    def wa(i):
+        call("fpl_window_accumulate", ptr(patches[i % 4]), ptr(accs[i % n_sets]), ptr(cnts[i % n_sets]), 1, C, d, h, w,
+             16 * (i % 2), 128 * (i % 2), 0, win[0], win[1], win[2], 0, i % 2, 1.0, stream_ptr())
+    timeit("fpl_window_accumulate_32x128x128", wa, pv * 4 * 5)
+    timeit("fpl_window_normalize", lambda i: call("fpl_window_normalize", ptr(accs[i % n_sets]), ptr(cnts[i % n_sets]), 1.0,
+                                                  accs[0].numel(), stream_ptr()), S * C * 12)
+    out["note"] = ("configs[1] sizes (48x256x256, 2 classes, K = 6); median of %d launches, inputs rotated over > 2x L2; "
+                   "peak = MEASURED_PEAKS hbm_gbs (%s)" % (iters, pk["source"]))
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# the same train step on stock torch modules (cuDNN / ATen) on the same GPU: the bar to beat (baseline/torch_cudnn_unet.py)
+# --------------------------------------------------------------------------------------------
+def torch_cuda_baseline(dev, args, steps=8):
+    from baseline.torch_cudnn_unet import TorchTrainer
+    out = {}
+    b0, b1 = make_batch(11, BATCH, PATCH, False, False), make_batch(12, BATCH, PATCH, True, False)
+    batches = [(b0["image"].to(dev), b0["label_prob"].to(dev), None),
+               (b1["image"].to(dev), b1["label_prob"].to(dev), b1["pixel_weight"].to(dev))]
+    vox = 2 * BATCH * PATCH[0] * PATCH[1] * PATCH[2]
+    for mode in ("fp32", "bf16_channels_last"):
+        try:
+            torch.manual_seed(1)
+            tr = TorchTrainer(dev, mode)
+            for _ in range(4):
+                tr.step(batches)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                tr.step(batches)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[mode] = {"ms_per_step": ms, "value": vox / (ms / 1e3), "unit": "voxels/s"}
+            del tr
+            torch.cuda.empty_cache()
+        except Exception as exc:                      # a baseline must never take the product measurement down
+            out[mode] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+    out["note"] = ("BASELINE, not a code path of fplplus_b200: the same DSBN 3-D U-Net + Dice/CE + Adam(fused) step as stock "
+                   "torch.nn modules (cuDNN convs, ATen BatchNorm / PReLU / pooling, eager launches, cudnn.benchmark) on "
+                   "this GPU, inputs resident; fp32 NCDHW is what the reference .cfg runs (tensor_type = float), bf16 "
+                   "autocast + channels_last_3d is the fastest stock configuration")
+    return out
 
 
 # --------------------------------------------------------------------------------------------
@@ -501,6 +696,40 @@ def cpu_baseline(bounded_steps=2, batch=1):
             "sample": "%d training_all steps (1 warm-up) at batch %d/domain of 1x32x128x128 (1/%d of the GPU arm's "
                       "step), fp32 torch CPU (oneDNN), oracle.train_step.OracleTrainer" % (bounded_steps, batch, BATCH // batch),
             "s_per_step": dt}
+
+
+def pl_filter_cpu_baseline():
+    """the oracle Inferer + NumPy filter on ONE 48x256x256 volume with tta_mode = 0 and
+    K = 2 MC passes (agent_seg.py:897-931 loop), extrapolated linearly to the GPU arm's workload (4-flip TTA, K = 6)."""
+    import synthetic_data as synth
+    from oracle import fpl_filter, inferer as oinf, unet_dsbn
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    params = dict(NET_PARAMS)
+    st = unet_dsbn.to_torch_state(synth.synth_state_dict(), requires_grad=False)
+    cfg = dict(TEST_CFG, tta_mode=0)
+    vol = torch.from_numpy(synth.synth_image(1, 1, VOLUME, seed=50))
+    t0 = time.time()
+    with torch.no_grad():
+        z_t = oinf.run(lambda x: unet_dsbn.forward(st, x, 1, params), vol, 2, cfg)
+        z_s = oinf.run(lambda x: unet_dsbn.forward(st, x, 0, params), vol, 2, cfg)
+        passes = [oinf.run(lambda x: unet_dsbn.forward(st, x, 1, params, drop_training=True), vol, 2, cfg).numpy()
+                  for _ in range(2)]
+    t_fwd = time.time() - t0                                # 4 Inferer passes x 8 windows = 32 forwards
+    t0 = time.time()
+    la, lb = fpl_filter.pseudo_label(z_t.numpy()), fpl_filter.pseudo_label(z_s.numpy())
+    fpl_filter.agreement_weight(la, lb)
+    t_lab = time.time() - t0
+    t0 = time.time()
+    fpl_filter.mc_uncertainty(passes)
+    t_mc2 = time.time() - t0
+    # full pass: (2 label passes + 6 MC passes) x 4 flips x 8 windows = 256 forwards; filter: labels once, statistics over 6
+    est = t_fwd / 32 * 256 + t_lab + t_mc2 * 3
+    return {"value": 1.0 / est, "unit": "volumes/s", "cores": threads, "kind": "port",
+            "sample": "1 volume 48x256x256, tta_mode 0, K = 2 (32 window forwards %.1f s + labels/agreement %.2f s + MC "
+                      "statistics %.2f s measured); extrapolated linearly to 256 forwards (4-flip TTA, 2 + 6 passes) and "
+                      "K = 6 statistics: %.1f s per volume" % (t_fwd, t_lab, t_mc2, est),
+            "s_per_volume_estimated": est}
 
 
 def run_reference(args):
@@ -547,6 +776,10 @@ def main():
     ap.add_argument("--volumes", type=int, default=2, help="volumes timed per GPU in the pl_filter leg")
     ap.add_argument("--skip-filter", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-torch", action="store_true", help="skip the stock torch/cuDNN baseline leg")
+    ap.add_argument("--quick", action="store_true", help="headline numbers only (no baselines / kernel rooflines)")
+    ap.add_argument("--fp32-onehot", action="store_true",
+                    help="feed the PyMIC loader layout (fp32 one-hot labels, folded fp32 weights) instead of uint8 labels / codes")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -419,14 +419,25 @@ class SegmentationAgent(object):
     def get_loss_value(self, data, pred, gt, fpl_uda=False):
         loss_input_dict = {'prediction': pred, 'ground_truth': gt}
         if fpl_uda and data.get('pixel_weight', None) is not None:
-            loss_input_dict['pixel_weight'] = data['pixel_weight'].to(pred.device, non_blocking=True)
+            pw = data['pixel_weight']
+            loss_input_dict['pixel_weight'] = pw.to(pred.device, non_blocking=True)
             if data.get('image_weight', None) is not None:
                 loss_input_dict['image_weight'] = data['image_weight']
+                # device data path: a uint8 agreement code (0/1/2 = 0/0.5/1) is NOT yet folded with the image weight;
+                # the loss kernel applies NiftyDataset.set_weight_ (io/nifty_dataset.py:165-168) per voxel
+                loss_input_dict['fold_image_weight'] = pw.dtype == torch.uint8
         return self.loss_calculator(loss_input_dict)
 
     # -- one optimiser step (agent_seg.py:459-495) -------------------------------------------
     def _to_device(self, t):
-        return t.to(self.device, dtype=torch.float32, non_blocking=True)
+        if torch.is_tensor(t) and t.dtype == torch.uint8:       # label maps / agreement codes stay 1 byte per voxel
+            return t.to(self.device, non_blocking=True)
+        return torch.as_tensor(t).to(self.device, dtype=torch.float32, non_blocking=True)
+
+    @staticmethod
+    def _truth_key(data):
+        """'label_prob' (fp32 one-hot/soft, the PyMIC batch layout) or 'label' (uint8 label map, device data path)."""
+        return 'label_prob' if data.get('label_prob', None) is not None else 'label'
 
     def _lr_at(self, it):
         tr = self.config['training']
@@ -472,7 +483,7 @@ class SegmentationAgent(object):
             stream = self._side_stream if (fork and d == present[1]) else main
             with torch.cuda.stream(stream):
                 x = self._to_device(data['image'])
-                y = self._to_device(data['label_prob'])
+                y = self._to_device(data[self._truth_key(data)])
                 out = self.net(x, domain_label=d * torch.ones(x.shape[0], dtype=torch.long))
                 loss_d = self.get_loss_value(data, out, y, self.fpl_uda)
                 hd = getattr(self.loss_calculator, "last_hard_dice", None)
@@ -513,11 +524,26 @@ class SegmentationAgent(object):
             self._set_lr(self._lr_at(self._host_it))
         return out
 
-    _TENSOR_KEYS = ('image', 'label_prob', 'pixel_weight')
+    _TENSOR_KEYS = ('image', 'label_prob', 'label', 'pixel_weight', 'image_weight')
+    _WEIGHT_KEYS = ('pixel_weight', 'image_weight')
+
+    def _graph_keys(self, b):
+        """Tensor entries of a batch dict that the captured step reads (static buffers refreshed before every replay)."""
+        keys = []
+        for k in self._TENSOR_KEYS:
+            v = b.get(k, None)
+            if v is None or (k in self._WEIGHT_KEYS and not self.fpl_uda):
+                continue
+            if k == 'label' and b.get('label_prob', None) is not None:
+                continue
+            if k == 'image_weight' and not (torch.is_tensor(v) and b.get('pixel_weight', None) is not None
+                                            and b['pixel_weight'].dtype == torch.uint8):
+                continue                    # already folded into an fp32 pixel_weight by the loader: the loss ignores it
+            keys.append(k)
+        return keys
 
     def _train_step_graphed(self, batches):
-        key = tuple(None if b is None else tuple((k, tuple(b[k].shape)) for k in self._TENSOR_KEYS
-                                                 if b.get(k, None) is not None and (k != 'pixel_weight' or self.fpl_uda))
+        key = tuple(None if b is None else tuple((k, tuple(b[k].shape), str(b[k].dtype)) for k in self._graph_keys(b))
                     for b in batches)
         ent = self._graphs.get(key)
         if ent is None:
@@ -533,10 +559,7 @@ class SegmentationAgent(object):
                 if b is None:
                     static.append(None)
                     continue
-                sb = {k: self._to_device(b[k]).clone() for k in self._TENSOR_KEYS
-                      if b.get(k, None) is not None and (k != 'pixel_weight' or self.fpl_uda)}
-                if b.get('image_weight', None) is not None:
-                    sb['image_weight'] = b['image_weight']
+                sb = {k: self._to_device(b[k]).clone() for k in self._graph_keys(b)}
                 static.append(sb)
             ent["static"] = static
             if hasattr(self.net, "ensure_rng"):
@@ -653,7 +676,7 @@ class SegmentationAgent(object):
                 losses, dices = [], []
                 loader = self.valid_loaders[d]
                 for data in (loader if loader is not None else []):
-                    x, y = self._to_device(data['image']), self._to_device(data['label_prob'])
+                    x, y = self._to_device(data['image']), self._to_device(data[self._truth_key(data)])
                     out = self.inferer.run(self.net, x, domain_label=d * torch.ones(x.shape[0], dtype=torch.long))
                     losses.append(self.get_loss_value(data, out, y))
                     for i in range(x.shape[0]):        # per-volume hard Dice (agent_seg.py:541-545)

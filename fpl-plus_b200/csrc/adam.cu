@@ -32,9 +32,12 @@ constexpr int kAdamChunk = 4096;    // elements per work item: 256 threads x 4 x
 
 __global__ void __launch_bounds__(kAdamThreads) adam_multi_tensor_kernel(const AdamSeg* __restrict__ segs, int nseg,
                                                                          const int2* __restrict__ chunks, int nchunks,
-                                                                         const float* __restrict__ lr_dev, float lr_host,
-                                                                         float b1, float b2, float eps, float wd,
+                                                                         const float* __restrict__ lr_dev, double lr_host,
+                                                                         double beta1, double beta2, float eps, float wd,
                                                                          unsigned int* done_counter) {
+    // torch evaluates 1 - beta, beta ** step and lr / bias_correction in Python doubles and hands the kernels the fp32
+    // roundings of those: 1.0f - 0.999f differs from float(1 - 0.999) by 1.3e-5 relative
+    const float b2 = (float)beta2, omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
     __shared__ float s_step_size, s_bc2_sqrt;
     __shared__ int s_last;
     for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
@@ -43,13 +46,13 @@ __global__ void __launch_bounds__(kAdamThreads) adam_multi_tensor_kernel(const A
         __syncthreads();
         if (threadIdx.x == 0) {
             const double t = (double)(*sg.step) + 1.0;
-            const double bc1 = 1.0 - pow((double)b1, t), bc2 = 1.0 - pow((double)b2, t);
-            const double lr = lr_dev != nullptr ? (double)__ldg(lr_dev) : (double)lr_host;
+            const double bc1 = 1.0 - pow(beta1, t), bc2 = 1.0 - pow(beta2, t);
+            const double lr = lr_dev != nullptr ? (double)__ldg(lr_dev) : lr_host;
             s_step_size = (float)(lr / bc1);
             s_bc2_sqrt = (float)sqrt(bc2);
         }
         __syncthreads();
-        const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt, omb1 = 1.0f - b1, omb2 = 1.0f - b2;
+        const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
         const int end = min(sg.numel, ch.y + kAdamChunk);
         const int n4_end = ch.y + ((end - ch.y) & ~3);
         for (int i = ch.y + 4 * threadIdx.x; i < n4_end; i += 4 * kAdamThreads) {
@@ -100,19 +103,19 @@ __global__ void __launch_bounds__(kAdamThreads) adam_multi_tensor_kernel(const A
 extern "C" int fpl_adam_chunk_elems(void) { return kAdamChunk; }
 
 extern "C" int fpl_adam_multi_tensor(const void* d_segs, int nseg, const int* d_chunks, int nchunks, const float* lr_dev,
-                                     float lr_host, float beta1, float beta2, float eps, float weight_decay,
+                                     double lr_host, double beta1, double beta2, double eps, double weight_decay,
                                      unsigned int* d_done_counter, void* stream) {
     FPL_REQUIRE(nseg >= 0 && nchunks >= 0, "fpl_adam_multi_tensor: negative counts");
     if (nseg == 0 || nchunks == 0) return 0;
     FPL_REQUIRE(d_segs != nullptr && d_chunks != nullptr && d_done_counter != nullptr, "fpl_adam_multi_tensor: NULL argument");
     FPL_REQUIRE((reinterpret_cast<uintptr_t>(d_segs) & 15) == 0, "fpl_adam_multi_tensor: table must be 16-byte aligned");
-    FPL_REQUIRE(beta1 >= 0.0f && beta1 < 1.0f && beta2 >= 0.0f && beta2 < 1.0f && eps >= 0.0f,
+    FPL_REQUIRE(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps >= 0.0,
                 "fpl_adam_multi_tensor: betas (%g, %g) / eps %g out of range", beta1, beta2, eps);
     int grid = nchunks;
     if (grid > FPL_NUM_SMS * 8) grid = FPL_NUM_SMS * 8;
     adam_multi_tensor_kernel<<<grid, kAdamThreads, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const AdamSeg*>(d_segs), nseg, reinterpret_cast<const int2*>(d_chunks), nchunks, lr_dev, lr_host,
-        beta1, beta2, eps, weight_decay, d_done_counter);
+        beta1, beta2, (float)eps, (float)weight_decay, d_done_counter);
     FPL_LAUNCH_CHECK();
     return 0;
 }

@@ -24,13 +24,57 @@ __device__ __forceinline__ void softmax_c(const float* z, float* p) {
     for (int c = 0; c < C; ++c) p[c] *= inv;
 }
 
-// sums layout (double): I[C], Y[C], P[C], sum_w, sum_w_ce, HI[C], HY[C], HP[C]
+// Where the ground truth and the pixel weight of a voxel come from.  The PyMIC loss API hands fp32 one-hot / soft labels
+// [N,C,D,H,W] and an fp32 weight map [N,1,D,H,W]; the device data path hands a uint8 label map [N,D,H,W]
+// (one-hot built here: LabelToProbability, transform/label_convert.py:82-88) and a uint8 agreement code [N,D,H,W]
+// (0, 1, 2 = weight 0, 0.5, 1 of data/get_pixel_weight.py:21-26) with the per-sample image weight folded in here
+// exactly as NiftyDataset.set_weight_ does (io/nifty_dataset.py:165-168: w < 1 -> 0, else w * image_weight).
+struct LossSrc {
+    const float* soft_y;      // fp32 [N,C,S] or NULL
+    const uint8_t* label;     // u8 [N,S] (used when soft_y == NULL)
+    const float* weight;      // fp32 [N,S] or NULL
+    const uint8_t* wcode;     // u8 [N,S] or NULL (used when weight == NULL)
+    const float* image_w;     // fp32 [N] or NULL: fold the image weight into wcode (set_weight_)
+    int prob_input;           // loss_softmax = False (loss/seg/abstract.py:16-21): `logits` already are probabilities
+};
+
 template <int C>
-__global__ void __launch_bounds__(kThreads) dice_ce_reduce_kernel(const float* __restrict__ logits,
-                                                                 const float* __restrict__ soft_y,
-                                                                 const float* __restrict__ weight, double* sums,
-                                                                 int N, int64_t S4) {
-    constexpr int NV = 6 * C + 2;
+__device__ __forceinline__ void load_truth4(const LossSrc& src, int64_t n, int64_t s4, int64_t S4, float4 (&yv)[C]) {
+    if (src.soft_y != nullptr) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) yv[c] = ld_stream_f4(reinterpret_cast<const float4*>(src.soft_y) + (n * C + c) * S4 + s4);
+    } else {
+        const uint32_t lab = __ldg(reinterpret_cast<const uint32_t*>(src.label) + n * S4 + s4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int l = (int)((lab >> (8 * j)) & 0xffu);
+#pragma unroll
+            for (int c = 0; c < C; ++c) reinterpret_cast<float*>(&yv[c])[j] = (l == c) ? 1.0f : 0.0f;
+        }
+    }
+}
+
+__device__ __forceinline__ float4 load_weight4(const LossSrc& src, int64_t n, int64_t s4, int64_t S4) {
+    if (src.weight != nullptr) return ld_stream_f4(reinterpret_cast<const float4*>(src.weight) + n * S4 + s4);
+    if (src.wcode == nullptr) return make_float4(1.f, 1.f, 1.f, 1.f);
+    const uint32_t code = __ldg(reinterpret_cast<const uint32_t*>(src.wcode) + n * S4 + s4);
+    const bool fold = src.image_w != nullptr;
+    const float iw = fold ? __ldg(src.image_w + n) : 1.0f;
+    float4 w;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float a = 0.5f * (float)((code >> (8 * j)) & 0xffu);
+        reinterpret_cast<float*>(&w)[j] = fold ? (a < 1.0f ? 0.0f : a) * iw : a;
+    }
+    return w;
+}
+
+// sums layout (double): I[C], Y[C], P[C], sum_w, sum_w_ce, HI[C], HY[C], HP[C], sum_c,v p*log2(p + 1e-10)
+template <int C>
+__global__ void __launch_bounds__(kThreads) dice_ce_reduce_kernel(const float* __restrict__ logits, LossSrc src,
+                                                                 double* sums, int N, int64_t S4, int want_entropy) {
+    const bool weighted = src.weight != nullptr || src.wcode != nullptr;
+    constexpr int NV = 6 * C + 3;
     float acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i] = 0.0f;
@@ -39,12 +83,10 @@ __global__ void __launch_bounds__(kThreads) dice_ce_reduce_kernel(const float* _
         int64_t n = g / S4, s4 = g - n * S4;
         float4 zv[C], yv[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            zv[c] = ld_stream_f4(reinterpret_cast<const float4*>(logits) + (n * C + c) * S4 + s4);
-            yv[c] = ld_stream_f4(reinterpret_cast<const float4*>(soft_y) + (n * C + c) * S4 + s4);
-        }
+        for (int c = 0; c < C; ++c) zv[c] = ld_stream_f4(reinterpret_cast<const float4*>(logits) + (n * C + c) * S4 + s4);
+        load_truth4<C>(src, n, s4, S4, yv);
         float4 wv = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (weight != nullptr) wv = ld_stream_f4(reinterpret_cast<const float4*>(weight) + n * S4 + s4);
+        if (weighted) wv = load_weight4(src, n, s4, S4);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float z[C], y[C], p[C];
@@ -54,7 +96,16 @@ __global__ void __launch_bounds__(kThreads) dice_ce_reduce_kernel(const float* _
                 y[c] = reinterpret_cast<const float*>(&yv[c])[j];
             }
             float w = reinterpret_cast<const float*>(&wv)[j];
-            softmax_c<C>(z, p);
+            if (src.prob_input) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) p[c] = z[c];
+            } else {
+                softmax_c<C>(z, p);
+            }
+            if (want_entropy) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[6 * C + 2] = fmaf(p[c], log2f(p[c] + 1e-10f), acc[6 * C + 2]);
+            }
             int am = 0;
             float best = z[0];
             float ce = 0.0f;
@@ -95,13 +146,12 @@ __global__ void __launch_bounds__(kThreads) dice_ce_reduce_kernel(const float* _
 }
 
 template <int C>
-__global__ void __launch_bounds__(kThreads) dice_ce_grad_kernel(const float* __restrict__ logits,
-                                                               const float* __restrict__ soft_y,
-                                                               const float* __restrict__ weight,
+__global__ void __launch_bounds__(kThreads) dice_ce_grad_kernel(const float* __restrict__ logits, LossSrc src,
                                                                const double* __restrict__ sums, float w_dice,
-                                                               float w_ce, float grad_scale,
+                                                               float w_ce, float w_ent, float grad_scale,
                                                                const float* __restrict__ grad_scale_dev, float* loss,
                                                                float* dlogits, int N, int64_t S4) {
+    const bool weighted = src.weight != nullptr || src.wcode != nullptr;
     if (grad_scale_dev != nullptr) grad_scale *= __ldg(grad_scale_dev);
     // per-class constants of dDice/dp:  g_c = -(1/C) * w * (2*y*den - num) / den^2
     float a_c[C], b_c[C];
@@ -117,26 +167,27 @@ __global__ void __launch_bounds__(kThreads) dice_ce_grad_kernel(const float* __r
     dice_mean /= C;
     const double sum_w = sums[3 * C], sum_wce = sums[3 * C + 1];
     const double V = (double)N * (double)S4 * 4.0;
-    const double ce_den = weight != nullptr ? sum_w + 1e-5 : V;
+    const double ce_den = weighted ? sum_w + 1e-5 : V;
     if (loss != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
         double l = 0.0;
         if (w_dice != 0.0f) l += (double)w_dice * (1.0 - dice_mean);
         if (w_ce != 0.0f) l += (double)w_ce * (sum_wce / ce_den);
+        // entropy regulariser of agent_seg.py:353,467: -sum p*log2(p + 1e-10) / (N*D*H*W)
+        if (w_ent != 0.0f) l += (double)w_ent * (-sums[6 * C + 2] / V);
         loss[0] = (float)l;
     }
     if (dlogits == nullptr) return;
     const float ce_k = (float)(-(double)w_ce * 0.999 / ce_den);
+    const float ent_k = (float)(-(double)w_ent / V);
     const int64_t total = (int64_t)N * S4;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
         int64_t n = g / S4, s4 = g - n * S4;
         float4 zv[C], yv[C], ov[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            zv[c] = ld_stream_f4(reinterpret_cast<const float4*>(logits) + (n * C + c) * S4 + s4);
-            yv[c] = ld_stream_f4(reinterpret_cast<const float4*>(soft_y) + (n * C + c) * S4 + s4);
-        }
+        for (int c = 0; c < C; ++c) zv[c] = ld_stream_f4(reinterpret_cast<const float4*>(logits) + (n * C + c) * S4 + s4);
+        load_truth4<C>(src, n, s4, S4, yv);
         float4 wv = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (weight != nullptr) wv = ld_stream_f4(reinterpret_cast<const float4*>(weight) + n * S4 + s4);
+        if (weighted) wv = load_weight4(src, n, s4, S4);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float z[C], y[C], p[C], gp[C];
@@ -146,17 +197,25 @@ __global__ void __launch_bounds__(kThreads) dice_ce_grad_kernel(const float* __r
                 y[c] = reinterpret_cast<const float*>(&yv[c])[j];
             }
             float w = reinterpret_cast<const float*>(&wv)[j];
-            softmax_c<C>(z, p);
+            if (src.prob_input) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) p[c] = z[c];
+            } else {
+                softmax_c<C>(z, p);
+            }
             float dot = 0.0f;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 float gc = w * fmaf(a_c[c], y[c], b_c[c]);
                 if (w_ce != 0.0f) gc += ce_k * w * y[c] / (p[c] * 0.999f + 5e-4f);
+                // d/dp of p*log2(p + eps) = log2(p + eps) + p / ((p + eps) * ln 2)
+                if (w_ent != 0.0f) gc += ent_k * (log2f(p[c] + 1e-10f) + p[c] / ((p[c] + 1e-10f) * 0.69314718056f));
                 gp[c] = gc;
                 dot = fmaf(gc, p[c], dot);
             }
 #pragma unroll
-            for (int c = 0; c < C; ++c) reinterpret_cast<float*>(&ov[c])[j] = grad_scale * p[c] * (gp[c] - dot);
+            for (int c = 0; c < C; ++c)
+                reinterpret_cast<float*>(&ov[c])[j] = src.prob_input ? grad_scale * gp[c] : grad_scale * p[c] * (gp[c] - dot);
         }
 #pragma unroll
         for (int c = 0; c < C; ++c) reinterpret_cast<float4*>(dlogits)[(n * C + c) * S4 + s4] = ov[c];
@@ -184,24 +243,59 @@ int grid_for(int64_t groups) {
         default: fpl_set_error("class_num %d not in [2,8]", C_); return 2;          \
     }
 
-extern "C" int fpl_dice_ce_reduce(const float* logits, const float* soft_y, const float* weight, double* sums, int n,
-                                  int c, int64_t spatial, void* stream) {
+static int dice_ce_reduce_launch(const float* logits, const LossSrc& src, double* sums, int n, int c, int64_t spatial,
+                                 int want_entropy, void* stream) {
     FPL_REQUIRE(spatial % 4 == 0, "fpl_dice_ce_reduce: spatial size %lld must be a multiple of 4", (long long)spatial);
+    FPL_REQUIRE(src.soft_y != nullptr || src.label != nullptr, "fpl_dice_ce_reduce: soft_y or label required");
     int64_t s4 = spatial / 4;
     FPL_DISPATCH_C(c, (dice_ce_reduce_kernel<CC><<<grid_for((int64_t)n * s4), kThreads, 0, (cudaStream_t)stream>>>(
-                          logits, soft_y, weight, sums, n, s4)));
+                          logits, src, sums, n, s4, want_entropy)));
     FPL_LAUNCH_CHECK();
     return 0;
+}
+
+static int dice_ce_grad_launch(const float* logits, const LossSrc& src, const double* sums, float w_dice, float w_ce,
+                               float w_ent, float grad_scale, const float* grad_scale_dev, float* loss, float* dlogits,
+                               int n, int c, int64_t spatial, void* stream) {
+    FPL_REQUIRE(spatial % 4 == 0, "fpl_dice_ce_grad: spatial size %lld must be a multiple of 4", (long long)spatial);
+    FPL_REQUIRE(src.soft_y != nullptr || src.label != nullptr, "fpl_dice_ce_grad: soft_y or label required");
+    int64_t s4 = spatial / 4;
+    int grid = dlogits != nullptr ? grid_for((int64_t)n * s4) : 1;
+    FPL_DISPATCH_C(c, (dice_ce_grad_kernel<CC><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+                          logits, src, sums, w_dice, w_ce, w_ent, grad_scale, grad_scale_dev, loss, dlogits, n, s4)));
+    FPL_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int fpl_dice_ce_reduce(const float* logits, const float* soft_y, const float* weight, double* sums, int n,
+                                  int c, int64_t spatial, void* stream) {
+    LossSrc src = {soft_y, nullptr, weight, nullptr, nullptr, 0};
+    return dice_ce_reduce_launch(logits, src, sums, n, c, spatial, 0, stream);
 }
 
 extern "C" int fpl_dice_ce_grad(const float* logits, const float* soft_y, const float* weight, const double* sums,
                                 float w_dice, float w_ce, float grad_scale, const float* grad_scale_dev, float* loss,
                                 float* dlogits, int n, int c, int64_t spatial, void* stream) {
-    FPL_REQUIRE(spatial % 4 == 0, "fpl_dice_ce_grad: spatial size %lld must be a multiple of 4", (long long)spatial);
-    int64_t s4 = spatial / 4;
-    int grid = dlogits != nullptr ? grid_for((int64_t)n * s4) : 1;
-    FPL_DISPATCH_C(c, (dice_ce_grad_kernel<CC><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
-                          logits, soft_y, weight, sums, w_dice, w_ce, grad_scale, grad_scale_dev, loss, dlogits, n, s4)));
-    FPL_LAUNCH_CHECK();
-    return 0;
+    LossSrc src = {soft_y, nullptr, weight, nullptr, nullptr, 0};
+    return dice_ce_grad_launch(logits, src, sums, w_dice, w_ce, 0.0f, grad_scale, grad_scale_dev, loss, dlogits, n, c,
+                               spatial, stream);
+}
+
+extern "C" int fpl_dice_ce_reduce_ex(const float* logits, const float* soft_y, const uint8_t* label, const float* weight,
+                                     const uint8_t* weight_code, const float* image_weight, double* sums, int n, int c,
+                                     int64_t spatial, int want_entropy, int prob_input, void* stream) {
+    FPL_REQUIRE(!(prob_input && want_entropy), "fpl_dice_ce_reduce_ex: the entropy term is defined on logits");
+    LossSrc src = {soft_y, label, weight, weight_code, image_weight, prob_input};
+    return dice_ce_reduce_launch(logits, src, sums, n, c, spatial, want_entropy, stream);
+}
+
+extern "C" int fpl_dice_ce_grad_ex(const float* logits, const float* soft_y, const uint8_t* label, const float* weight,
+                                   const uint8_t* weight_code, const float* image_weight, const double* sums,
+                                   float w_dice, float w_ce, float w_entropy, float grad_scale,
+                                   const float* grad_scale_dev, float* loss, float* dlogits, int n, int c,
+                                   int64_t spatial, int prob_input, void* stream) {
+    FPL_REQUIRE(!(prob_input && w_entropy != 0.0f), "fpl_dice_ce_grad_ex: the entropy term is defined on logits");
+    LossSrc src = {soft_y, label, weight, weight_code, image_weight, prob_input};
+    return dice_ce_grad_launch(logits, src, sums, w_dice, w_ce, w_entropy, grad_scale, grad_scale_dev, loss, dlogits, n,
+                               c, spatial, stream);
 }

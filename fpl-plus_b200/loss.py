@@ -15,6 +15,9 @@ from .ops import call, ptr, stream_ptr
 
 
 def _prep(loss_input_dict):
+    """Returns (prediction, truth, weight): ``truth`` is fp32 one-hot/soft [N,C,D,H,W] (the PyMIC layout) or a uint8
+    label map [N,D,H,W] / [N,1,D,H,W] (device data path: the one-hot is built inside the kernel); ``weight`` is None,
+    an fp32 map [N,1,D,H,W], or a (uint8 agreement code [N,1,D,H,W], image weight [N] or None) pair."""
     predict = loss_input_dict['prediction']
     soft_y = loss_input_dict['ground_truth']
     pix_w = loss_input_dict.get('pixel_weight', None)
@@ -24,50 +27,81 @@ def _prep(loss_input_dict):
         raise RuntimeError("fplplus_b200 losses run on CUDA only")
     if predict.dim() != 5:
         raise ValueError("{0:}D tensor not supported".format(predict.dim()))
-    soft_y = soft_y.to(device=predict.device, dtype=torch.float32).contiguous()
-    if soft_y.shape != predict.shape:
-        raise ValueError("prediction %s and ground_truth %s differ in shape" % (tuple(predict.shape), tuple(soft_y.shape)))
+    n_vox = predict.numel() // predict.shape[1]
+    if soft_y.dtype == torch.uint8:
+        soft_y = soft_y.to(device=predict.device).contiguous()
+        if soft_y.numel() != n_vox:
+            raise ValueError("uint8 ground_truth must be a label map [N,D,H,W] matching prediction %s" % (tuple(predict.shape),))
+    else:
+        soft_y = soft_y.to(device=predict.device, dtype=torch.float32).contiguous()
+        if soft_y.shape != predict.shape:
+            raise ValueError("prediction %s and ground_truth %s differ in shape" % (tuple(predict.shape), tuple(soft_y.shape)))
     if pix_w is not None:
-        pix_w = pix_w.to(device=predict.device, dtype=torch.float32).contiguous()
-        if pix_w.numel() != predict.numel() // predict.shape[1]:
-            raise ValueError("pixel_weight must be [N,1,D,H,W]")
+        if pix_w.dtype == torch.uint8:
+            code = pix_w.to(device=predict.device).contiguous()
+            if code.numel() != n_vox:
+                raise ValueError("pixel_weight must be [N,1,D,H,W]")
+            iw = loss_input_dict.get('image_weight', None) if loss_input_dict.get('fold_image_weight', False) else None
+            if iw is not None:
+                iw = torch.as_tensor(iw).to(device=predict.device, dtype=torch.float32).reshape(-1).contiguous()
+                if iw.numel() != predict.shape[0]:
+                    raise ValueError("image_weight must hold one value per sample")
+            pix_w = (code, iw)
+        else:
+            pix_w = pix_w.to(device=predict.device, dtype=torch.float32).contiguous()
+            if pix_w.numel() != n_vox:
+                raise ValueError("pixel_weight must be [N,1,D,H,W]")
     return predict, soft_y, pix_w
 
 
 def n_sums(c):
-    return 6 * c + 2
+    return 6 * c + 3
+
+
+def _src_args(truth, weight):
+    """(soft_y, label, weight, weight_code, image_weight) pointers of fpl_dice_ce_*_ex."""
+    soft_y, label = (None, truth) if truth.dtype == torch.uint8 else (truth, None)
+    w, code, iw = None, None, None
+    if isinstance(weight, tuple):
+        code, iw = weight
+    else:
+        w = weight
+    return ptr(soft_y), ptr(label), ptr(w), ptr(code), ptr(iw)
 
 
 class _DiceCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, soft_y, weight, w_dice, w_ce, holder):
+    def forward(ctx, logits, truth, weight, w_dice, w_ce, w_ent, prob_input, holder):
         logits = logits.float().contiguous()
         n, c = logits.shape[:2]
         spatial = logits.numel() // (n * c)
         sums = torch.zeros(n_sums(c), dtype=torch.float64, device=logits.device)
         st = stream_ptr()
-        call("fpl_dice_ce_reduce", ptr(logits), ptr(soft_y), ptr(weight), ptr(sums), n, c, spatial, st)
+        src = _src_args(truth, weight)
+        call("fpl_dice_ce_reduce_ex", ptr(logits), *src, ptr(sums), n, c, spatial, 1 if w_ent != 0.0 else 0, prob_input, st)
+        red = holder.get("sums_allreduce") if holder is not None else None
+        if red is not None:
+            red(sums)            # exact data-parallel Dice: the partial sums of all ranks (SURVEY 8e), see agent.py
         loss = torch.empty((), dtype=torch.float32, device=logits.device)
-        call("fpl_dice_ce_grad", ptr(logits), ptr(soft_y), ptr(weight), ptr(sums), w_dice, w_ce, 1.0, None, ptr(loss),
-             None, n, c, spatial, st)
-        ctx.save_for_backward(logits, soft_y, sums) if weight is None else ctx.save_for_backward(logits, soft_y, sums, weight)
-        ctx.w = (w_dice, w_ce)
+        call("fpl_dice_ce_grad_ex", ptr(logits), *src, ptr(sums), w_dice, w_ce, w_ent, 1.0, None, ptr(loss), None, n, c,
+             spatial, prob_input, st)
+        ctx.saved = (logits, truth, weight, sums)
+        ctx.w = (w_dice, w_ce, w_ent, prob_input)
         if holder is not None:
             holder["sums"] = sums
+            holder["voxels"] = n * spatial
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        saved = ctx.saved_tensors
-        logits, soft_y, sums = saved[:3]
-        weight = saved[3] if len(saved) > 3 else None
+        logits, truth, weight, sums = ctx.saved
         n, c = logits.shape[:2]
         spatial = logits.numel() // (n * c)
         dlogits = torch.empty_like(logits)
         g = grad_out.float().contiguous()
-        call("fpl_dice_ce_grad", ptr(logits), ptr(soft_y), ptr(weight), ptr(sums), ctx.w[0], ctx.w[1], 1.0, ptr(g),
-             None, ptr(dlogits), n, c, spatial, stream_ptr())
-        return dlogits, None, None, None, None, None
+        call("fpl_dice_ce_grad_ex", ptr(logits), *_src_args(truth, weight), ptr(sums), ctx.w[0], ctx.w[1], ctx.w[2], 1.0,
+             ptr(g), None, ptr(dlogits), n, c, spatial, ctx.w[3], stream_ptr())
+        return dlogits, None, None, None, None, None, None, None
 
 
 def hard_dice_from_sums(sums, c):
@@ -84,17 +118,26 @@ class _FusedSegLoss(nn.Module):
     def __init__(self, params=None):
         super().__init__()
         self.softmax = True if params is None else params.get('loss_softmax', True)
+        # optional entropy regulariser -sum p*log2(p+1e-10)/(N*D*H*W) of agent_seg.py:353,467 ([training]
+        # entropy_weight; 0 = the pinned training_all contract, where the term is commented out)
+        self.w_ent = 0.0 if params is None else float(params.get('entropy_weight', 0.0) or 0.0)
         self.last = {}
 
     def forward(self, loss_input_dict):
-        if not self.softmax:
-            raise NotImplementedError("loss_softmax=False is not supported by the fused Dice/CE kernel")
+        if not self.softmax and self.w_ent != 0.0:
+            raise ValueError("entropy_weight needs loss_softmax = True (the term is defined on logits)")
         predict, soft_y, pix_w = _prep(loss_input_dict)
-        return _DiceCE.apply(predict, soft_y, pix_w, float(self.w_dice), float(self.w_ce), self.last)
+        return _DiceCE.apply(predict, soft_y, pix_w, float(self.w_dice), float(self.w_ce), float(self.w_ent),
+                             0 if self.softmax else 1, self.last)
 
     def last_hard_dice(self):
         s = self.last.get("sums")
-        return None if s is None else hard_dice_from_sums(s, (s.numel() - 2) // 6)
+        return None if s is None else hard_dice_from_sums(s, (s.numel() - 3) // 6)
+
+    def last_entropy(self):
+        """-sum p*log2(p + 1e-10) / (N*D*H*W) of the last call (needs entropy_weight != 0); CUDA float64 tensor."""
+        s, v = self.last.get("sums"), self.last.get("voxels")
+        return None if s is None or v is None else -s[-1] / v
 
 
 class DiceLoss(_FusedSegLoss):

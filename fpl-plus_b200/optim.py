@@ -138,7 +138,7 @@ class FusedAdam(torch.optim.Optimizer):
             rows += struct.pack("<5Qii", *ptrs, p.numel(), 0)
             chunks += [(row, c0) for c0 in range(0, p.numel(), chunk)]
         dev = params[0].device
-        segs = torch.frombuffer(bytes(rows), dtype=torch.uint8).to(dev)
+        segs = torch.frombuffer(rows, dtype=torch.uint8).to(dev)
         ch = torch.tensor(chunks, dtype=torch.int32).to(dev)
         return segs, ch, len(active), len(chunks)
 

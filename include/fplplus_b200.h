@@ -126,9 +126,10 @@ int fpl_grad_scatter_add(float* dst, const float* src, const int* d_table, int s
  * (all pointers 16-byte aligned); d_chunks: DEVICE int32 [nchunks][2] = {row, first element}, one entry per
  * fpl_adam_chunk_elems() elements of every tensor.  step is torch's per-parameter step counter (fp32, incremented here
  * after the update); the learning rate is *lr_dev when lr_dev != NULL (CUDA-graph replays under MultiStepLR,
- * get_optimizer.py:50-54), else lr_host.  d_done_counter: DEVICE uint32 zero-initialised once by the caller. */
+ * get_optimizer.py:50-54), else lr_host.  Hyper-parameters are doubles: torch evaluates 1 - beta, beta^step and
+ * lr / bias_correction in double and rounds the results to fp32.  d_done_counter: DEVICE uint32 zero-initialised once by the caller. */
 int fpl_adam_multi_tensor(const void* d_segs, int nseg, const int* d_chunks, int nchunks, const float* lr_dev,
-                          float lr_host, float beta1, float beta2, float eps, float weight_decay,
+                          double lr_host, double beta1, double beta2, double eps, double weight_decay,
                           unsigned int* d_done_counter, void* stream);
 int fpl_adam_chunk_elems(void);
 
@@ -297,9 +298,9 @@ int fpl_dsbn_bwd_finalize(const double* red, const float* scale, const float* sa
 
 /* ---- (d) pixel/image-weighted Dice + CE: loss/seg/dice.py:20-57, ce.py:23-44, util.py:85-107 ---- */
 
-/* sums = double[3C+2+3C]: I_c, Y_c, P_c, sum_w, sum_w_ce, then the hard-Dice
- * counters of agent_seg.py:472-476 (sum onehot(argmax)*y, sum y, sum onehot(argmax)) -- ACCUMULATED into.
- * logits/soft_y fp32 NCDHW, weight fp32 [N,1,D,H,W] or NULL. */
+/* sums = double[6C+3]: I_c, Y_c, P_c, sum_w, sum_w_ce, then the hard-Dice counters of agent_seg.py:472-476
+ * (sum onehot(argmax)*y, sum y, sum onehot(argmax)), then sum_{c,v} p*log2(p + 1e-10) (only filled by the _ex form with
+ * want_entropy) -- ACCUMULATED into.  logits/soft_y fp32 NCDHW, weight fp32 [N,1,D,H,W] or NULL. */
 int fpl_dice_ce_reduce(const float* logits, const float* soft_y, const float* weight,
                        double* sums, int n, int c, int64_t spatial, void* stream);
 /* loss (fp32[1], may be NULL) and dlogits (fp32 NCDHW, may be NULL) from the sums; dlogits =
@@ -309,6 +310,21 @@ int fpl_dice_ce_grad(const float* logits, const float* soft_y, const float* weig
                      const double* sums, float w_dice, float w_ce, float grad_scale,
                      const float* grad_scale_dev, float* loss, float* dlogits,
                      int n, int c, int64_t spatial, void* stream);
+/* Device data path + entropy term.  Ground truth: soft_y (fp32 [N,C,S]) or, when soft_y is NULL,
+ * a uint8 label map [N,S] whose one-hot is built in the kernel (LabelToProbability, transform/label_convert.py:82-88).
+ * Pixel weight: weight (fp32 [N,S]) or, when weight is NULL, a uint8 agreement code [N,S] (0/1/2 = weight 0/0.5/1 of
+ * data/get_pixel_weight.py:21-26); image_weight (fp32 [N], may be NULL) is folded into the code exactly as
+ * NiftyDataset.set_weight_ (io/nifty_dataset.py:165-168): w < 1 -> 0, else w * image_weight[n].  10 instead of 20
+ * bytes/voxel at C = 2 in the reduce pass.  w_entropy weighs the regulariser -sum p*log2(p+1e-10)/(N*D*H*W) of
+ * agent_seg.py:353,467 (value and gradient); want_entropy makes the reduce pass accumulate its sum.  prob_input != 0:
+ * `logits` already hold probabilities (loss_softmax = False, loss/seg/abstract.py:16-21): no softmax, d/dp returned. */
+int fpl_dice_ce_reduce_ex(const float* logits, const float* soft_y, const uint8_t* label, const float* weight,
+                          const uint8_t* weight_code, const float* image_weight, double* sums, int n, int c,
+                          int64_t spatial, int want_entropy, int prob_input, void* stream);
+int fpl_dice_ce_grad_ex(const float* logits, const float* soft_y, const uint8_t* label, const float* weight,
+                        const uint8_t* weight_code, const float* image_weight, const double* sums,
+                        float w_dice, float w_ce, float w_entropy, float grad_scale, const float* grad_scale_dev,
+                        float* loss, float* dlogits, int n, int c, int64_t spatial, int prob_input, void* stream);
 
 /* ---- (c) pseudo-label filter: agent_seg.py:897-931,1045-1050; data/get_pixel_weight.py:21-26;
  *          io/nifty_dataset.py:165-168 ---- */

@@ -804,3 +804,83 @@ def test_upsample2x_align_corners_fwd_bwd(kd2, shape, c):
     s = torch.ones(c, device=DEV)
     _call("fpl_channel_sum_c8", _p(gcat), 2 * c // 8, c // 8, _p(s), n, do, 2 * h, 2 * w, c, _st())
     np.testing.assert_allclose(s.cpu().numpy() - 1.0, g.sum((0, 2, 3, 4)).numpy(), rtol=2e-4, atol=2e-3)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# round 2: device data path of the loss (uint8 labels / agreement codes), entropy term, loss_softmax = False
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("c", [2, 5])
+def test_dice_ce_uint8_labels_and_weight_codes_equal_the_fp32_layout(c):
+    """a uint8 label map + a uint8 agreement code (0/1/2) + per-sample image weights give the SAME loss and
+    gradient as the PyMIC layout (fp32 one-hot + fp32 pixel weight folded by set_weight_ on the host)."""
+    from oracle import fpl_filter, losses, synth
+    from fplplus_b200.loss import CombinedLoss
+    from fplplus_b200.registry import loss_dict
+    shape = (8, 24, 32)
+    lab = synth.synth_label(3, c, shape, seed=5)
+    r = np.random.Generator(np.random.PCG64(8))
+    code = r.integers(0, 3, (3, 1) + shape).astype(np.uint8)
+    iw = r.uniform(0.01, 1.01, 3).astype(np.float32)
+    pw = np.stack([fpl_filter.set_weight_(iw[i], 0.5 * code[i].astype(np.float32)) for i in range(3)], 0).astype(np.float32)
+    z = randn(77, 3, c, *shape, scale=2.0)
+    crit = CombinedLoss({"loss_type": ["DiceLoss", "CrossEntropyLoss"], "loss_weight": [0.4, 0.6]}, loss_dict)
+    out = {}
+    for mode in ("fp32", "u8"):
+        zz = z.clone().to(DEV).requires_grad_(True)
+        if mode == "fp32":
+            d = {"prediction": zz, "ground_truth": torch.from_numpy(synth.one_hot(lab, c)).to(DEV),
+                 "pixel_weight": torch.from_numpy(pw).to(DEV)}
+        else:
+            d = {"prediction": zz, "ground_truth": torch.from_numpy(lab).to(DEV), "pixel_weight": torch.from_numpy(code).to(DEV),
+                 "image_weight": torch.from_numpy(iw), "fold_image_weight": True}
+        loss = crit(d)
+        loss.backward()
+        out[mode] = (float(loss), zz.grad.cpu(), crit.last_hard_dice().cpu())
+    assert abs(out["fp32"][0] - out["u8"][0]) <= 1e-6 * abs(out["fp32"][0])
+    torch.testing.assert_close(out["u8"][1], out["fp32"][1], rtol=1e-5, atol=1e-10)
+    torch.testing.assert_close(out["u8"][2], out["fp32"][2], rtol=1e-9, atol=0)
+    # and against the float64 closed form of the reference losses
+    lv, dz, _ = losses.dice_ce_closed_form(z.numpy(), synth.one_hot(lab, c), pw, 0.4, 0.6)
+    assert abs(out["u8"][0] - lv) <= 1e-5 * abs(lv)
+    assert max_rel(out["u8"][1], torch.from_numpy(dz).float()) < 1e-4
+    # unfolded codes (no image weight): weight = code / 2
+    zz = z.clone().to(DEV).requires_grad_(True)
+    l2 = crit({"prediction": zz, "ground_truth": torch.from_numpy(lab).to(DEV), "pixel_weight": torch.from_numpy(code).to(DEV)})
+    lv2, _, _ = losses.dice_ce_closed_form(z.numpy(), synth.one_hot(lab, c), 0.5 * code.astype(np.float32), 0.4, 0.6)
+    assert abs(float(l2) - lv2) <= 1e-5 * abs(lv2)
+
+
+def test_entropy_term_and_probability_inputs_match_the_oracle():
+    """a12: entropy regulariser -sum p*log2(p+1e-10)/(N*D*H*W) (agent_seg.py:353,467) as a fused term of the loss
+    kernels (value + gradient); loss_softmax = False (loss/seg/abstract.py:16-21): predictions already are probabilities."""
+    from oracle import losses, synth
+    from fplplus_b200.loss import CombinedLoss, DiceLoss
+    from fplplus_b200.registry import loss_dict
+    shape, c = (8, 16, 32), 3
+    lab = synth.synth_label(2, c, shape, seed=9)
+    y = torch.from_numpy(synth.one_hot(lab, c))
+    z = randn(78, 2, c, *shape, scale=2.0)
+    crit = CombinedLoss({"loss_type": ["DiceLoss", "CrossEntropyLoss"], "loss_weight": [0.5, 0.5], "entropy_weight": 0.3}, loss_dict)
+    zz = z.clone().to(DEV).requires_grad_(True)
+    loss = crit({"prediction": zz, "ground_truth": y.to(DEV)})
+    loss.backward()
+    zr = z.clone().requires_grad_(True)
+    ref = losses.combined_loss(zr, y, None, 0.5, 0.5) + 0.3 * losses.entropy_bits(zr)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    assert max_rel(zz.grad.cpu(), zr.grad) < 1e-4
+    assert abs(float(crit.last_entropy()) - float(losses.entropy_bits(z))) <= 1e-5 * float(losses.entropy_bits(z))
+    # probabilities in, no softmax inside
+    p = torch.softmax(z, 1)
+    crit2 = DiceLoss({"loss_softmax": False})
+    pp = p.clone().to(DEV).requires_grad_(True)
+    l2 = crit2({"prediction": pp, "ground_truth": y.to(DEV)})
+    l2.backward()
+    pr = p.clone().requires_grad_(True)
+    r2 = losses.dice_loss(pr, y, None, softmax=False)
+    r2.backward()
+    assert abs(float(l2) - float(r2)) <= 1e-5 * abs(float(r2))
+    assert max_rel(pp.grad.cpu(), pr.grad) < 1e-4
+    with pytest.raises(ValueError):
+        CombinedLoss({"loss_type": ["DiceLoss"], "loss_weight": [1.0], "entropy_weight": 0.1, "loss_softmax": False}, loss_dict)(
+            {"prediction": pp, "ground_truth": y.to(DEV)})
