@@ -585,28 +585,40 @@ def bench_filter(agent, rank, world, barrier, max_over_ranks, args):
 # HBM rooflines of the filter / stitching kernels (north_star (c)): CUDA events around every launch, inputs rotated over
 # enough buffers that no launch finds its data in the 126 MB L2
 # --------------------------------------------------------------------------------------------
-def filter_kernel_rooflines(dev, pk, iters=6):
+def filter_kernel_rooflines(dev, pk, iters=16):
+    """GB/s at the algorithmic bytes of the filter / stitching / loss kernels at the configs[1] / configs[2] sizes.
+    Each kernel is captured `iters` times back to back into a CUDA graph (inputs rotated over more buffers than fit
+    the 126 MB L2) and the replay is timed with CUDA events: the figure is the average launch duration in a busy
+    stream, free of the host's enqueue latency that an event bracket around a single eager launch would include."""
     from fplplus_b200 import fpl
+    from fplplus_b200.loss import CombinedLoss
     from fplplus_b200.ops import call, ptr, stream_ptr
+    from fplplus_b200.registry import loss_dict
     d, h, w = VOLUME
     S, C, K = d * h * w, 2, 6
     g = torch.Generator(device="cpu").manual_seed(5)
-    n_sets = 8                                              # 8 x 25 MB logits volumes x K: far beyond L2
+    n_sets = 8                                              # 8 x 25 MB logits volumes (+ K): far beyond L2
     vols = [torch.randn((1, C, d, h, w), generator=g).to(dev) for _ in range(n_sets + K)]
     out = {}
 
     def timeit(name, fn, nbytes):
-        fn(0)
+        fn(0)                                               # eager warm-up (lazy module state, allocator)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(iters):
+                fn(i + 1)
+        graph.replay()
         torch.cuda.synchronize()
         ts = []
-        for i in range(iters):
+        for _ in range(3):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            fn(i + 1)
+            graph.replay()
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
-        t = sorted(ts)[len(ts) // 2] / 1e3
+        t = sorted(ts)[1] / iters / 1e3
         out[name] = {"us": t * 1e6, "algorithmic_mb": nbytes / 1e6, "gbs": nbytes / t / 1e9,
                      "frac_of_hbm_peak": nbytes / t / 1e9 / pk["hbm_gbs"]}
 
@@ -628,8 +640,44 @@ def filter_kernel_rooflines(dev, pk, iters=6):
     timeit("fpl_window_accumulate_32x128x128", wa, pv * 4 * 5)
     timeit("fpl_window_normalize", lambda i: call("fpl_window_normalize", ptr(accs[i % n_sets]), ptr(cnts[i % n_sets]), 1.0,
                                                   accs[0].numel(), stream_ptr()), S * C * 12)
-    out["note"] = ("configs[1] sizes (48x256x256, 2 classes, K = 6); median of %d launches, inputs rotated over > 2x L2; "
-                   "peak = MEASURED_PEAKS hbm_gbs (%s)" % (iters, pk["source"]))
+    # loss kernels at the train-step size (batch 4 x 32x128x128, 2 classes): device layout (uint8 labels + agreement
+    # codes) and PyMIC layout (fp32 one-hot + fp32 weights); reduce pass and gradient pass separately
+    n, sp = BATCH, PATCH[0] * PATCH[1] * PATCH[2]
+    n_rot = 12
+    zs = [torch.randn((n, C) + PATCH, generator=g).to(dev) for _ in range(n_rot)]
+    labs = [torch.randint(0, C, (n,) + PATCH, generator=g, dtype=torch.uint8).to(dev) for _ in range(n_rot)]
+    codes = [torch.randint(1, 3, (n, 1) + PATCH, generator=g, dtype=torch.uint8).to(dev) for _ in range(n_rot)]
+    onehots = [torch.nn.functional.one_hot(l.long(), C).permute(0, 4, 1, 2, 3).float().contiguous() for l in labs[:6]]
+    pws = [c_.float() * 0.5 for c_ in codes[:6]]
+    iw = torch.rand(n, generator=g).to(dev)
+    sums = torch.zeros(6 * C + 3, dtype=torch.float64, device=dev)
+    dz = torch.empty_like(zs[0])
+    gs = torch.ones((), device=dev)
+
+    def red_u8(i):
+        call("fpl_dice_ce_reduce_ex", ptr(zs[i % n_rot]), None, ptr(labs[i % n_rot]), None, ptr(codes[i % n_rot]), ptr(iw),
+             ptr(sums), n, C, sp, 0, 0, stream_ptr())
+
+    def grad_u8(i):
+        call("fpl_dice_ce_grad_ex", ptr(zs[i % n_rot]), None, ptr(labs[i % n_rot]), None, ptr(codes[i % n_rot]), ptr(iw),
+             ptr(sums), 0.5, 0.5, 0.0, 1.0, ptr(gs), None, ptr(dz), n, C, sp, 0, stream_ptr())
+
+    def red_f32(i):
+        call("fpl_dice_ce_reduce_ex", ptr(zs[i % n_rot]), ptr(onehots[i % 6]), None, ptr(pws[i % 6]), None, None,
+             ptr(sums), n, C, sp, 0, 0, stream_ptr())
+
+    def grad_f32(i):
+        call("fpl_dice_ce_grad_ex", ptr(zs[i % n_rot]), ptr(onehots[i % 6]), None, ptr(pws[i % 6]), None, None,
+             ptr(sums), 0.5, 0.5, 0.0, 1.0, ptr(gs), None, ptr(dz), n, C, sp, 0, stream_ptr())
+    red_u8(0)
+    V = n * sp
+    timeit("fpl_dice_ce_reduce_ex_u8_labels", red_u8, V * (4 * C + 2))
+    timeit("fpl_dice_ce_grad_ex_u8_labels", grad_u8, V * (8 * C + 2))
+    timeit("fpl_dice_ce_reduce_ex_fp32_onehot", red_f32, V * (8 * C + 4))
+    timeit("fpl_dice_ce_grad_ex_fp32_onehot", grad_f32, V * (12 * C + 4))
+    out["note"] = ("filter kernels at configs[1] sizes (48x256x256, 2 classes, K = 6), loss kernels at the configs[2] step "
+                   "size (4 x 32x128x128); %d launches back to back in a CUDA graph, inputs rotated over > L2; peak = "
+                   "MEASURED_PEAKS hbm_gbs (%s)" % (iters, pk["source"]))
     return out
 
 

@@ -35,6 +35,8 @@ __global__ void __launch_bounds__(kAdamThreads) adam_multi_tensor_kernel(const A
                                                                          const float* __restrict__ lr_dev, double lr_host,
                                                                          double beta1, double beta2, float eps, float wd,
                                                                          unsigned int* done_counter) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     // torch evaluates 1 - beta, beta ** step and lr / bias_correction in Python doubles and hands the kernels the fp32
     // roundings of those: 1.0f - 0.999f differs from float(1 - 0.999) by 1.3e-5 relative
     const float b2 = (float)beta2, omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
@@ -113,7 +115,7 @@ extern "C" int fpl_adam_multi_tensor(const void* d_segs, int nseg, const int* d_
                 "fpl_adam_multi_tensor: betas (%g, %g) / eps %g out of range", beta1, beta2, eps);
     int grid = nchunks;
     if (grid > FPL_NUM_SMS * 8) grid = FPL_NUM_SMS * 8;
-    adam_multi_tensor_kernel<<<grid, kAdamThreads, 0, (cudaStream_t)stream>>>(
+    fpl_launch(adam_multi_tensor_kernel, grid, kAdamThreads, 0, (cudaStream_t)stream, 
         reinterpret_cast<const AdamSeg*>(d_segs), nseg, reinterpret_cast<const int2*>(d_chunks), nchunks, lr_dev, lr_host,
         beta1, beta2, (float)eps, (float)weight_decay, d_done_counter);
     FPL_LAUNCH_CHECK();

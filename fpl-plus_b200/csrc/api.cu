@@ -1,5 +1,6 @@
 // Error reporting and device queries for the C ABI (include/fplplus_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "../../include/fplplus_b200.h"
@@ -16,6 +17,13 @@ void fpl_set_error(const char* fmt, ...) {
 extern "C" const char* fpl_last_error(void) { return g_err; }
 
 unsigned long long g_fpl_launches = 0;
+
+// programmatic dependent launch on by default; FPL_PDL=0 falls back to plain stream-ordered launches (A/B measurements)
+static int read_pdl_env() {
+    const char* e = getenv("FPL_PDL");
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
+}
+int g_fpl_pdl = read_pdl_env();
 
 extern "C" long long fpl_launch_count(int reset) {
     unsigned long long v = __atomic_load_n(&g_fpl_launches, __ATOMIC_RELAXED);

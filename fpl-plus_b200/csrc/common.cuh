@@ -36,6 +36,36 @@ extern unsigned long long g_fpl_launches;
         FPL_CHECK_CUDA(cudaGetLastError());                                               \
     } while (0)
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization (fpl_launch): the next
+// kernel of the stream may be SCHEDULED while this one is still running -- its CTAs run their prologue (barrier init,
+// TMEM allocation, tensor-map prefetch, index math) and then block in griddepcontrol.wait until the whole previous grid
+// has completed and flushed its memory.  ~320 dependent launches per train step otherwise pay the full
+// drain-then-launch latency each, also inside a CUDA graph (the edges are captured as programmatic dependencies).
+// Rules: (1) every kernel executes FPL_PDL_WAIT() before its first global read / write of data another kernel of the
+// stream touches (the waits chain, so completion is transitive); (2) FPL_PDL_TRIGGER() lets the dependents be
+// scheduled once every CTA of this grid has executed it (or exited).  Both are no-ops for a normally launched kernel.
+#define FPL_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define FPL_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+
+extern int g_fpl_pdl;     // 1 (default) / 0: FPL_PDL environment variable, read once (api.cu)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t fpl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_fpl_pdl;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- 16-byte bf16x8 vectors ----------------------------------------------------------
 struct __align__(16) bf16x8 {
     __nv_bfloat162 v[4];

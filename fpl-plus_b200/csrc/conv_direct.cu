@@ -27,6 +27,8 @@ struct ConvP {
 };
 
 __global__ void __launch_bounds__(128) conv3d_direct_kernel(ConvP P) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int T = P.kd * 9;
     __shared__ __align__(16) float wsm[27][8][8];   // [tap][ci][co]
     __shared__ float red[4][16];
@@ -115,6 +117,8 @@ struct WgradP {
 
 template <int MODE>
 __global__ void __launch_bounds__(256) wgrad_kernel(WgradP P) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     __shared__ __align__(16) float dys[64][33];
     __shared__ __align__(16) float xs[64][36];
     const int T = MODE == 0 ? P.kd * 9 : P.kd * 4;
@@ -181,6 +185,8 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WgradP P) {
 // per-channel sum of a C8-planar tensor (bias gradients): grid (chunks, planes)
 __global__ void __launch_bounds__(256) channel_sum_kernel(const bf16x8* __restrict__ g, int c8tot, int c8off, float* out,
                                                           int ND, int C8, int HW) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int plane = blockIdx.y, c8 = plane % C8, nd = plane / C8;
     float s[8];
 #pragma unroll
@@ -216,6 +222,8 @@ struct StemP {
 };
 
 __global__ void __launch_bounds__(128) stem_conv_fwd_kernel(StemP P) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     extern __shared__ float wsm_dyn[];   // [ci][tap][8 co] for this co8
     __shared__ float red[4][16];
     const int T = P.kd * 9;
@@ -280,6 +288,8 @@ struct StemWP {
 };
 
 __global__ void __launch_bounds__(256) stem_conv_wgrad_kernel(StemWP P) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     extern __shared__ float sm_dyn[];
     const int T = P.kd * 9;
     const int HW = P.H * P.W;
@@ -352,6 +362,8 @@ struct HeadP {
 };
 
 __global__ void __launch_bounds__(128) head_conv_fwd_kernel(HeadP P) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     extern __shared__ float wsm_dyn[];   // [tap 9][ci][cls]
     const int HW = P.H * P.W;
     for (int e = threadIdx.x; e < 9 * P.cin * P.classes; e += 128) {
@@ -394,6 +406,8 @@ __global__ void __launch_bounds__(128) head_conv_fwd_kernel(HeadP P) {
 
 // dgrad: thread = voxel x 8 input channels
 __global__ void __launch_bounds__(128) head_conv_dgrad_kernel(HeadP P) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     extern __shared__ float wsm_dyn[];   // [tap 9][cls][8 ci] for this ci8
     const int HW = P.H * P.W;
     const int ci8 = blockIdx.z;
@@ -431,6 +445,8 @@ __global__ void __launch_bounds__(128) head_conv_dgrad_kernel(HeadP P) {
 
 // wgrad + bias grad: block = (row group, plane); thread = (cls, ci, tap) element
 __global__ void __launch_bounds__(256) head_conv_wgrad_kernel(HeadP P) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     extern __shared__ float sm_dyn[];
     const int HW = P.H * P.W;
     const int rows = 2;
@@ -502,6 +518,8 @@ struct ConvTP {
 
 // fwd: thread = output voxel x 8 co.  block = 128 consecutive output w of one output row.
 __global__ void __launch_bounds__(128) convt_fwd_kernel(ConvTP P) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     extern __shared__ float wsm_dyn[];   // [ci][c parity 2][8 co]
     const int T = P.kd2 * 4;
     const int Ho = P.H * 2, Wo = P.W * 2, Do = P.D * P.kd2;
@@ -537,6 +555,8 @@ __global__ void __launch_bounds__(128) convt_fwd_kernel(ConvTP P) {
 
 // dgrad: thread = low-res voxel x 8 ci; loops the kd2*4 positions and all co
 __global__ void __launch_bounds__(128) convt_dgrad_kernel(ConvTP P) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     extern __shared__ float wsm_dyn[];   // [pos T][co][8 ci]
     const int T = P.kd2 * 4;
     const int ci8 = blockIdx.z;
@@ -575,6 +595,8 @@ __global__ void __launch_bounds__(128) convt_dgrad_kernel(ConvTP P) {
 // optional per-channel sums (the bias gradient when the tensor is dlogits).  grid: (chunks of H*W, N*D)
 __global__ void __launch_bounds__(256) pack_ncdhw_c8_kernel(const float* __restrict__ x, int C, bf16x8* out, int c8tot,
                                                             int c8off, int groups, float* chan_sum, int D, int HW) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int nd = blockIdx.y, n = nd / D, d = nd - n * D;
     float s[16];
 #pragma unroll
@@ -612,6 +634,8 @@ __global__ void __launch_bounds__(256) pack_ncdhw_c8_kernel(const float* __restr
 // neighbour x[d][h+kh-1][w+kw-1] (zero outside the plane), channels 9..15 are zero.  The stem conv k(3,3,3) then is a
 // k(3,1,1) conv over these 16 channels, which the tensor-core kernels run with ONE in-plane tap.
 __global__ void __launch_bounds__(256) patch9_kernel(const float* __restrict__ x, bf16x8* out, int D, int H, int W, int split) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int nd = blockIdx.y;
     const int HW = H * W;
     const float* plane = x + (int64_t)nd * HW;
@@ -651,7 +675,7 @@ __global__ void __launch_bounds__(256) patch9_kernel(const float* __restrict__ x
 extern "C" int fpl_patch9_c8(const float* x, void* out, int split_hi_lo, int n, int d, int h, int w, void* stream) {
     FPL_REQUIRE((int64_t)n * d <= 65535, "fpl_patch9_c8: too many planes");
     int chunks = (h * w + 1023) / 1024;
-    patch9_kernel<<<dim3(chunks, n * d), 256, 0, (cudaStream_t)stream>>>(x, (bf16x8*)out, d, h, w, split_hi_lo);
+    fpl_launch(patch9_kernel, dim3(chunks, n * d), 256, 0, (cudaStream_t)stream, x, (bf16x8*)out, d, h, w, split_hi_lo);
     FPL_LAUNCH_CHECK();
     return 0;
 }
@@ -662,7 +686,7 @@ extern "C" int fpl_pack_ncdhw_to_c8(const float* x, int c, void* out, int out_c8
     FPL_REQUIRE(chan_sum == nullptr || c <= 16, "fpl_pack_ncdhw_to_c8: channel sums need c <= 16");
     FPL_REQUIRE((int64_t)n * d <= 65535, "fpl_pack_ncdhw_to_c8: too many planes");
     int chunks = (h * w + 1023) / 1024;
-    pack_ncdhw_c8_kernel<<<dim3(chunks, n * d), 256, 0, (cudaStream_t)stream>>>(x, c, (bf16x8*)out, out_c8tot, out_c8off,
+    fpl_launch(pack_ncdhw_c8_kernel, dim3(chunks, n * d), 256, 0, (cudaStream_t)stream, x, c, (bf16x8*)out, out_c8tot, out_c8off,
                                                                                groups, chan_sum, d, h * w);
     FPL_LAUNCH_CHECK();
     return 0;
@@ -677,7 +701,7 @@ extern "C" int fpl_conv3d_direct(const void* x, int x_c8tot, int x_c8off, const 
     ConvP P{(const bf16x8*)x, x_c8tot, x_c8off, w, bias, (bf16x8*)y, y_c8tot, y_c8off, stats,
             n, d, h, w_, cin, cout, kd, transpose_flip, round_w_bf16};
     dim3 grid((h * w_ + 127) / 128, n * d, cout / 8);
-    conv3d_direct_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(P);
+    fpl_launch(conv3d_direct_kernel, grid, 128, 0, (cudaStream_t)stream, P);
     FPL_LAUNCH_CHECK();
     return 0;
 }
@@ -688,7 +712,7 @@ extern "C" int fpl_conv3d_wgrad(const void* x, int x_c8tot, int x_c8off, const v
     FPL_REQUIRE(kd == 1 || kd == 3, "fpl_conv3d_wgrad: kd=%d must be 1 or 3", kd);
     WgradP P{(const bf16x8*)x, x_c8tot, x_c8off, (const bf16x8*)dy, dy_c8tot, dy_c8off, dw, n, d, h, w, cin, cout, kd};
     dim3 grid(n * d, ((cout + 31) / 32) * ((cin + 31) / 32), kd * 9);
-    wgrad_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+    fpl_launch(wgrad_kernel<0>, grid, 256, 0, (cudaStream_t)stream, P);
     FPL_LAUNCH_CHECK();
     return 0;
 }
@@ -701,7 +725,7 @@ extern "C" int fpl_stem_conv_fwd(const float* x, const float* w, const float* bi
     StemP P{x, w, bias, (bf16x8*)y, y_c8tot, y_c8off, stats, n, cin, d, h, w_, cout, kd};
     dim3 grid((h * w_ + 127) / 128, n * d, cout / 8);
     size_t smem = (size_t)cin * kd * 9 * 8 * sizeof(float);
-    stem_conv_fwd_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(P);
+    fpl_launch(stem_conv_fwd_kernel, grid, 128, smem, (cudaStream_t)stream, P);
     FPL_LAUNCH_CHECK();
     return 0;
 }
@@ -717,7 +741,7 @@ extern "C" int fpl_stem_conv_wgrad(const float* x, const void* dy, int dy_c8tot,
     int rows_blocks = (h + 3) / 4;
     if (rows_blocks > 8) rows_blocks = 8;
     dim3 grid(rows_blocks, n * d);
-    stem_conv_wgrad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(P);
+    fpl_launch(stem_conv_wgrad_kernel, grid, 256, smem, (cudaStream_t)stream, P);
     FPL_LAUNCH_CHECK();
     return 0;
 }
@@ -730,7 +754,7 @@ extern "C" int fpl_head_conv_fwd(const void* x, int x_c8tot, int x_c8off, const 
     P.x = (const bf16x8*)x; P.x_c8tot = x_c8tot; P.x_c8off = x_c8off; P.w = w; P.bias = bias; P.logits = logits;
     P.N = n; P.D = d; P.H = h; P.W = w_; P.cin = cin; P.classes = classes;
     dim3 grid((h * w_ + 127) / 128, n * d);
-    head_conv_fwd_kernel<<<grid, 128, (size_t)9 * cin * classes * sizeof(float), (cudaStream_t)stream>>>(P);
+    fpl_launch(head_conv_fwd_kernel, grid, 128, (size_t)9 * cin * classes * sizeof(float), (cudaStream_t)stream, P);
     FPL_LAUNCH_CHECK();
     return 0;
 }
@@ -747,7 +771,7 @@ extern "C" int fpl_head_conv_bwd(const void* x, int x_c8tot, int x_c8off, const 
     P.N = n; P.D = d; P.H = h; P.W = w_; P.cin = cin; P.classes = classes;
     if (dx != nullptr) {
         dim3 grid((h * w_ + 127) / 128, n * d, cin / 8);
-        head_conv_dgrad_kernel<<<grid, 128, (size_t)9 * classes * 8 * sizeof(float), (cudaStream_t)stream>>>(P);
+        fpl_launch(head_conv_dgrad_kernel, grid, 128, (size_t)9 * classes * 8 * sizeof(float), (cudaStream_t)stream, P);
         FPL_LAUNCH_CHECK();
     }
     if (dw != nullptr) {
@@ -757,7 +781,7 @@ extern "C" int fpl_head_conv_bwd(const void* x, int x_c8tot, int x_c8off, const 
         int rb = (h + 1) / 2;
         if (rb > 16) rb = 16;
         dim3 grid(rb, n * d);
-        head_conv_wgrad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(P);
+        fpl_launch(head_conv_wgrad_kernel, grid, 256, smem, (cudaStream_t)stream, P);
         FPL_LAUNCH_CHECK();
     }
     return 0;
@@ -776,7 +800,7 @@ extern "C" int fpl_convt_k2s2_fwd(const void* x, int x_c8tot, int x_c8off, const
     FPL_REQUIRE(rows <= 65535 * 32, "fpl_convt_k2s2_fwd: too many rows");
     FPL_REQUIRE(rows <= 65535, "fpl_convt_k2s2_fwd: too many output rows (%lld)", (long long)rows);
     dim3 grid((w_ * 2 + 127) / 128, (unsigned)rows, cout / 8);
-    convt_fwd_kernel<<<grid, 128, (size_t)cin * 16 * sizeof(float), (cudaStream_t)stream>>>(P);
+    fpl_launch(convt_fwd_kernel, grid, 128, (size_t)cin * 16 * sizeof(float), (cudaStream_t)stream, P);
     FPL_LAUNCH_CHECK();
     return 0;
 }
@@ -796,20 +820,20 @@ extern "C" int fpl_convt_k2s2_bwd(const void* x, int x_c8tot, int x_c8off, const
         FPL_REQUIRE(smem <= 200 * 1024, "fpl_convt_k2s2_bwd: cout=%d too large", cout);
         FPL_CHECK_CUDA(cudaFuncSetAttribute(convt_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((h * w_ + 127) / 128, n * d, cin / 8);
-        convt_dgrad_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(P);
+        fpl_launch(convt_dgrad_kernel, grid, 128, smem, (cudaStream_t)stream, P);
         FPL_LAUNCH_CHECK();
     }
     if (dw != nullptr) {
         WgradP P{(const bf16x8*)x, x_c8tot, x_c8off, (const bf16x8*)dy, dy_c8tot, dy_c8off, dw, n, d, h, w_, cin, cout, kd2};
         dim3 grid(n * d, ((cout + 31) / 32) * ((cin + 31) / 32), T);
-        wgrad_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+        fpl_launch(wgrad_kernel<1>, grid, 256, 0, (cudaStream_t)stream, P);
         FPL_LAUNCH_CHECK();
     }
     if (db != nullptr) {
         int HWo = h * 2 * w_ * 2;
         int chunks = (HWo + 1023) / 1024;
         dim3 grid(chunks, n * d * kd2 * (cout / 8));
-        channel_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16x8*)dy, dy_c8tot, dy_c8off, db, n * d * kd2,
+        fpl_launch(channel_sum_kernel, grid, 256, 0, (cudaStream_t)stream, (const bf16x8*)dy, dy_c8tot, dy_c8off, db, n * d * kd2,
                                                                   cout / 8, HWo);
         FPL_LAUNCH_CHECK();
     }
@@ -826,7 +850,7 @@ extern "C" int fpl_channel_sum_c8(const void* g, int g_c8tot, int g_c8off, float
     int chunks = (HW + 1023) / 1024;
     if (chunks < 1) chunks = 1;
     dim3 grid(chunks, n * d * (c / 8));
-    channel_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16x8*)g, g_c8tot, g_c8off, out, n * d, c / 8, HW);
+    fpl_launch(channel_sum_kernel, grid, 256, 0, (cudaStream_t)stream, (const bf16x8*)g, g_c8tot, g_c8off, out, n * d, c / 8, HW);
     FPL_LAUNCH_CHECK();
     return 0;
 }

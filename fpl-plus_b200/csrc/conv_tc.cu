@@ -103,6 +103,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int t) {
 
 __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap,
                                                                  const __grid_constant__ CUtensorMap imap, TcParams P) {
+    FPL_PDL_TRIGGER();   // dependents may be scheduled; they block in their own FPL_PDL_WAIT
     extern __shared__ uint8_t smem_raw[];
     // stage ring at 1024-byte alignment, then barriers, the TMEM base slot and the BN partial sums
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+    FPL_PDL_WAIT();      // prologue above overlapped the previous kernel's tail; from here on its results are visible
     float* scale_sm = bias_sm + P.cout;
     const bool fuse_act = P.act.scale != nullptr;
     for (int i = threadIdx.x; i < P.cout; i += kNumThreads) {
@@ -350,6 +352,8 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
 // ---------------------------------------------------------------------------------------------
 __global__ void prep_weight_kernel(const float* __restrict__ w, __nv_bfloat16* image, int cin_eff, int cout_eff, int kd,
                                    int transpose_flip, int nb, int kc, int64_t total) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int T = kd * 9;
     const int nchunks = cin_eff / kc;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -386,7 +390,7 @@ extern "C" int fpl_conv3d_prep_weight(const float* w, int cin, int cout, int kd,
     int64_t total = (int64_t)c.nslices * c.nchunks * kd * c.b_bytes / 2;
     int blocks = (int)((total + 255) / 256);
     if (blocks > FPL_NUM_SMS * 8) blocks = FPL_NUM_SMS * 8;
-    prep_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)image, cin_eff, cout_eff, kd,
+    fpl_launch(prep_weight_kernel, blocks, 256, 0, (cudaStream_t)stream, w, (__nv_bfloat16*)image, cin_eff, cout_eff, kd,
                                                                  transpose_flip, c.nb, c.kc, total);
     FPL_LAUNCH_CHECK();
     return 0;
@@ -411,6 +415,8 @@ namespace {
 // of prep_weight_kernel costs 7 integer divisions and one 32-byte sector per 4-byte read: 112 us per step for the 36
 // images of the network, at the head of every optimiser step.)
 __global__ void prep_weight_batch_kernel(const __grid_constant__ PrepBatch B) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int e = blockIdx.y;
     const float* __restrict__ w = B.w[e];
     __nv_bfloat16* image = B.image[e];
@@ -461,7 +467,7 @@ extern "C" int fpl_conv3d_prep_weight_batch(int count, const float* const* h_w, 
     int bx = (max_total / 9 + 255) / 256;
     if (bx > 512) bx = 512;
     if (bx < 1) bx = 1;
-    prep_weight_batch_kernel<<<dim3(bx, count), 256, 0, (cudaStream_t)stream>>>(B);
+    fpl_launch(prep_weight_batch_kernel, dim3(bx, count), 256, 0, (cudaStream_t)stream, B);
     FPL_LAUNCH_CHECK();
     return 0;
 }
@@ -535,7 +541,7 @@ static int conv3d_tc_launch(const void* x, int x_c8tot, int x_c8off, const void*
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         FPL_REQUIRE(r == CUDA_SUCCESS, "fpl_conv3d_tc: cuTensorMapEncodeTiled (weight image) failed (%d)", (int)r);
     }
-    conv3d_tc_kernel<<<grid, kNumThreads, c.smem_bytes, (cudaStream_t)stream>>>(xmap, imap, P);
+    fpl_launch(conv3d_tc_kernel, grid, kNumThreads, c.smem_bytes, (cudaStream_t)stream, xmap, imap, P);
     FPL_LAUNCH_CHECK();
     return 0;
 }

@@ -66,6 +66,7 @@ __device__ __forceinline__ DfItem decode_item(const DfParams& P, int t) {
 }
 
 __global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid_constant__ CUtensorMap xmap, DfParams P) {
+    FPL_PDL_TRIGGER();   // dependents may be scheduled; they block in their own FPL_PDL_WAIT
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     // [resident weights of this CTA's slice][A stage ring][barriers][bias]
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+    FPL_PDL_WAIT();      // prologue above overlapped the previous kernel's tail; from here on its results are visible
     float* scale_sm = bias_sm + P.cout;
     const bool fuse_act = P.act.scale != nullptr;
     for (int i = threadIdx.x; i < P.cout; i += kThreadsD) {
@@ -308,6 +310,8 @@ __global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid
 // z-1+jj of input plane z, i.e. depth tap kd = 2 - jj.  transpose_flip as in fpl_conv3d_prep_weight.
 __global__ void dfold_prep_kernel(const float* __restrict__ w, __nv_bfloat16* image, int cin_eff, int cout_eff, int transpose_flip,
                                   int nb, int total, int taps) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int ksteps = cin_eff / 16, n3 = 3 * nb, T = 3 * taps;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int t = i;
@@ -379,7 +383,7 @@ static int dfold_prep(const float* w, int cin, int cout, int transpose_flip, int
     const int total = c.nslices * c.b_bytes / 2;
     int blocks = (total + 255) / 256;
     if (blocks > FPL_NUM_SMS * 4) blocks = FPL_NUM_SMS * 4;
-    dfold_prep_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)image, cin_eff, cout_eff, transpose_flip, c.nb, total, taps);
+    fpl_launch(dfold_prep_kernel, blocks, 256, 0, (cudaStream_t)stream, w, (__nv_bfloat16*)image, cin_eff, cout_eff, transpose_flip, c.nb, total, taps);
     FPL_LAUNCH_CHECK();
     return 0;
 }
@@ -404,6 +408,8 @@ struct DfPrepBatch {
 };
 // one thread per (out, in) pair: 27 contiguous source floats -> 27 image positions (see prep_weight_batch_kernel)
 __global__ void dfold_prep_batch_kernel(const __grid_constant__ DfPrepBatch B) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int e = blockIdx.y;
     const float* __restrict__ w = B.w[e];
     __nv_bfloat16* image = B.image[e];
@@ -445,7 +451,7 @@ extern "C" int fpl_conv3d_dfold_prep_weight_batch(int count, const float* const*
     int bx = (max_total / 27 + 255) / 256;
     if (bx > 32) bx = 32;
     if (bx < 1) bx = 1;
-    dfold_prep_batch_kernel<<<dim3(bx, count), 256, 0, (cudaStream_t)stream>>>(B);
+    fpl_launch(dfold_prep_batch_kernel, dim3(bx, count), 256, 0, (cudaStream_t)stream, B);
     FPL_LAUNCH_CHECK();
     return 0;
 }
@@ -484,7 +490,7 @@ static int dfold_launch(const void* x, int x_c8tot, int x_c8off, const void* ima
     FPL_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_dfold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
     int grid = FPL_NUM_SMS * c.ctas_per_sm;
     if (grid > P.total_items) grid = P.total_items;
-    conv3d_tc_dfold_kernel<<<grid, kThreadsD, c.smem_bytes, (cudaStream_t)stream>>>(xmap, P);
+    fpl_launch(conv3d_tc_dfold_kernel, grid, kThreadsD, c.smem_bytes, (cudaStream_t)stream, xmap, P);
     FPL_LAUNCH_CHECK();
     return 0;
 }

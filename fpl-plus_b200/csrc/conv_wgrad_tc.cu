@@ -126,6 +126,7 @@ __device__ __forceinline__ WgWork decode_work(const WgParams& P, int b) {
 
 __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid_constant__ CUtensorMap xmap,
                                                                    const __grid_constant__ CUtensorMap dymap, WgParams P) {
+    FPL_PDL_TRIGGER();   // dependents may be scheduled; they block in their own FPL_PDL_WAIT
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     // barriers live in front of the stage ring so that operand over-reads past the last stage stay in the pad
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+    FPL_PDL_WAIT();      // prologue above overlapped the previous kernel's tail; from here on its results are visible
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -351,7 +353,7 @@ static int wgrad_tc_launch(const void* x, int x_c8tot, int x_c8off, const void* 
     P.swap_lbo_sbo = g_wg_swap; P.m64_quadrant_layout = g_wg_m64_quadrant;
     P.taps = taps; P.skip_epilogue = g_wg_skip_epilogue; P.tapmajor = tapmajor;
     FPL_CHECK_CUDA(cudaFuncSetAttribute(conv3d_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
-    conv3d_wgrad_tc_kernel<<<pairs * split, kThreadsW, c.smem_bytes, (cudaStream_t)stream>>>(xmap, dymap, P);
+    fpl_launch(conv3d_wgrad_tc_kernel, pairs * split, kThreadsW, c.smem_bytes, (cudaStream_t)stream, xmap, dymap, P);
     FPL_LAUNCH_CHECK();
     return 0;
 }
@@ -389,6 +391,8 @@ struct FoldBatch {
 // Negative tap count: nn.ConvTranspose3d layout, row = ci*cout + co (small tensors; the gather is left uncoalesced).
 constexpr int kFoldRows = 256;
 __global__ void __launch_bounds__(256) fold_tapmajor_kernel(const __grid_constant__ FoldBatch B) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     __shared__ float tile[kFoldRows * 27];
     const int e = blockIdx.y;
     const float* __restrict__ s = B.s[e];
@@ -441,7 +445,7 @@ extern "C" int fpl_wgrad_tapmajor_to_dw_batch(int count, const float* const* h_s
     int bx = (max_total / 9 + kFoldRows - 1) / kFoldRows;      // ~ blocks of kFoldRows rows for the largest layer
     if (bx > 296) bx = 296;
     if (bx < 1) bx = 1;
-    fold_tapmajor_kernel<<<dim3(bx, count), 256, 0, (cudaStream_t)stream>>>(B);
+    fpl_launch(fold_tapmajor_kernel, dim3(bx, count), 256, 0, (cudaStream_t)stream, B);
     FPL_LAUNCH_CHECK();
     return 0;
 }

@@ -74,6 +74,7 @@ bool make_ct_cfg(int kdim, int ndim, int kc_div, CtCfg& c) {
 }
 
 __global__ void __launch_bounds__(kThreadsT) convt_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, CtParams P) {
+    FPL_PDL_TRIGGER();   // dependents may be scheduled; they block in their own FPL_PDL_WAIT
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stage_bytes = P.a_bytes + P.b_bytes;
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(kThreadsT) convt_gemm_tc_kernel(const __grid_c
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+    FPL_PDL_WAIT();      // prologue above overlapped the previous kernel's tail; from here on its results are visible
     if (P.mode == 0)
         for (int i = threadIdx.x; i < P.ndim; i += kThreadsT) bias_sm[i] = P.bias != nullptr ? P.bias[i % P.cout] : 0.0f;
     tc_fence_before();
@@ -230,6 +232,8 @@ __global__ void __launch_bounds__(kThreadsT) convt_gemm_tc_kernel(const __grid_c
 //   mode 0 (fwd):   B[k = ci][n = tap*cout + co]          mode 1 (dgrad): B[k = tap*cout + co][n = ci]
 __global__ void convt_prep_kernel(const float* __restrict__ w, __nv_bfloat16* image, int cin, int cout, int ntaps, int mode,
                                   int nb, int kc, int nchunks, int total) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int t = i;
         const int el = t % 8; t /= 8;
@@ -271,6 +275,7 @@ struct CtwParams {
 
 __global__ void __launch_bounds__(kThreadsT) convt_wgrad_tc_kernel(const __grid_constant__ CUtensorMap xmap,
                                                                   const __grid_constant__ CUtensorMap dymap, CtwParams P) {
+    FPL_PDL_TRIGGER();   // dependents may be scheduled; they block in their own FPL_PDL_WAIT
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -297,6 +302,7 @@ __global__ void __launch_bounds__(kThreadsT) convt_wgrad_tc_kernel(const __grid_
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+    FPL_PDL_WAIT();      // prologue above overlapped the previous kernel's tail; from here on its results are visible
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -402,7 +408,7 @@ extern "C" int fpl_convt_prep_weight(const float* w, int cin, int cout, int kd2,
     const int total = kdim * ndim;
     int blocks = (total + 255) / 256;
     if (blocks > FPL_NUM_SMS * 4) blocks = FPL_NUM_SMS * 4;
-    convt_prep_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)image, cin, cout, ntaps, mode, c.nb, c.kc,
+    fpl_launch(convt_prep_kernel, blocks, 256, 0, (cudaStream_t)stream, w, (__nv_bfloat16*)image, cin, cout, ntaps, mode, c.nb, c.kc,
                                                                c.nchunks, total);
     FPL_LAUNCH_CHECK();
     return 0;
@@ -417,6 +423,8 @@ struct CtPrepBatch {
         nchunks[kMaxCtBatch], total[kMaxCtBatch];
 };
 __global__ void convt_prep_batch_kernel(const __grid_constant__ CtPrepBatch B) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int e = blockIdx.y;
     const float* __restrict__ w = B.w[e];
     __nv_bfloat16* image = B.image[e];
@@ -454,7 +462,7 @@ extern "C" int fpl_convt_prep_weight_batch(int count, const float* const* h_w, c
     }
     int bx = (max_total + 255) / 256;
     if (bx > 64) bx = 64;
-    convt_prep_batch_kernel<<<dim3(bx, count), 256, 0, (cudaStream_t)stream>>>(B);
+    fpl_launch(convt_prep_batch_kernel, dim3(bx, count), 256, 0, (cudaStream_t)stream, B);
     FPL_LAUNCH_CHECK();
     return 0;
 }
@@ -488,7 +496,7 @@ static int convt_gemm_launch(int mode, const void* a, int a_c8tot, int a_c8off, 
     FPL_CHECK_CUDA(cudaFuncSetAttribute(convt_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
     int grid = FPL_NUM_SMS * 2;
     if (grid > P.total_items) grid = P.total_items;
-    convt_gemm_tc_kernel<<<grid, kThreadsT, c.smem_bytes, (cudaStream_t)stream>>>(amap, P);
+    fpl_launch(convt_gemm_tc_kernel, grid, kThreadsT, c.smem_bytes, (cudaStream_t)stream, amap, P);
     FPL_LAUNCH_CHECK();
     return 0;
 }
@@ -549,7 +557,7 @@ static int convt_wgrad_launch(const void* x, int x_c8tot, int x_c8off, const voi
     P.split = split;
     const int smem_bytes = P.stages * P.stage_bytes + (P.m / 8) * kPlane + 1024 + 256;
     FPL_CHECK_CUDA(cudaFuncSetAttribute(convt_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    convt_wgrad_tc_kernel<<<pairs * split, kThreadsT, smem_bytes, (cudaStream_t)stream>>>(xmap, dymap, P);
+    fpl_launch(convt_wgrad_tc_kernel, pairs * split, kThreadsT, smem_bytes, (cudaStream_t)stream, xmap, dymap, P);
     FPL_LAUNCH_CHECK();
     return 0;
 }

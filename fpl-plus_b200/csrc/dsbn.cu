@@ -23,6 +23,8 @@ __global__ void dsbn_finalize_kernel(const double* __restrict__ stats, double in
                                      float* running_mean, float* running_var, long long* nbt,
                                      float momentum, float eps, int training,
                                      float* scale, float* shift, float* save_mean, float* save_invstd, int C) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < C) {
         float mean, invstd;
@@ -152,6 +154,8 @@ __device__ __forceinline__ uint32_t keep_bits(const uint2* mask, uint64_t seed, 
 // the prologue, live in registers) and walks over work items = (plane (n,d), chunk of 2*256 vectors), two vectors per
 // thread in flight, with stepped plane pointers (same structure as dsbn_act_bwd_kernel below).
 __global__ void __launch_bounds__(kThreads) dsbn_act_fwd_kernel(const __grid_constant__ ActParams P) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int HW = P.H * P.W;
     const int c8 = blockIdx.y;
     const float slope = __ldg(P.slope);
@@ -203,6 +207,8 @@ __global__ void __launch_bounds__(kThreads) dsbn_act_fwd_kernel(const __grid_con
 // order d,h,w as in torch's max_pool3d).
 // grid: (blocks per channel group, C8); work items = (pooled plane (n,d2), chunk of 256 pooled vectors)
 __global__ void __launch_bounds__(kThreads) dsbn_act_pool_fwd_kernel(const __grid_constant__ ActParams P) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int kd = P.pool_kd;
     const int D2 = P.D / kd, H2 = P.H / 2, W2 = P.W / 2;
     const int HW = P.H * P.W, HW2 = H2 * W2;
@@ -306,6 +312,8 @@ constexpr int kBwdV = FPL_BWD_V;          // vectors per thread per work item
 constexpr int kBwdBlocks = FPL_BWD_BLOCKS; // resident blocks per SM the register budget is tuned for
 template <bool APPLY, bool POOL, bool DROP>
 __global__ void __launch_bounds__(kThreads, kBwdBlocks) dsbn_act_bwd_kernel(const __grid_constant__ ActBwdParams P) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int HW = P.H * P.W;
     const int c8 = blockIdx.y;
     const int C = P.C8 * 8;
@@ -481,6 +489,8 @@ __global__ void __launch_bounds__(kThreads, kBwdBlocks) dsbn_act_bwd_kernel(cons
 __global__ void dsbn_bwd_finalize_kernel(const double* __restrict__ red, const float* __restrict__ scale, int training,
                                          float* dgamma, float* dbeta, float* dslope, float* dbias_conv,
                                          const float* __restrict__ invstd, int C) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < C) {
         // dz is the gradient wrt the BN output: dbeta = sum dz, dgamma = sum dz*xhat
@@ -508,7 +518,7 @@ extern "C" int fpl_dsbn_finalize(const double* stats, int64_t count, const float
     FPL_REQUIRE(training ? (stats != nullptr && count > 0) : (running_mean != nullptr && running_var != nullptr),
                 "fpl_dsbn_finalize: missing statistics for training=%d", training);
     double unbias = count > 1 ? (double)count / (double)(count - 1) : 1.0;
-    dsbn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+    fpl_launch(dsbn_finalize_kernel, (c + 127) / 128, 128, 0, (cudaStream_t)stream, 
         stats, 1.0 / (double)(count > 0 ? count : 1), unbias, gamma, beta, running_mean, running_var,
         (long long*)num_batches_tracked, momentum, eps, training, scale, shift, save_mean, save_invstd, c);
     FPL_LAUNCH_CHECK();
@@ -541,14 +551,14 @@ static int act_fwd_launch(const BnFinalize* fin, const void* y, const float* sca
         int64_t bx = (FPL_NUM_SMS * 8 + c8 - 1) / c8;
         if (bx > items) bx = items;
         if (bx < 1) bx = 1;
-        dsbn_act_pool_fwd_kernel<<<dim3((unsigned)bx, (unsigned)c8), kThreads, 0, (cudaStream_t)stream>>>(P);
+        fpl_launch(dsbn_act_pool_fwd_kernel, dim3((unsigned)bx, (unsigned)c8), kThreads, 0, (cudaStream_t)stream, P);
     } else {
         const int64_t hw = (int64_t)h * w;
         const int64_t items = (int64_t)n * d * ((hw + 2 * kThreads - 1) / (2 * kThreads));
         int64_t bx = (FPL_NUM_SMS * 8 + c8 - 1) / c8;
         if (bx > items) bx = items;
         if (bx < 1) bx = 1;
-        dsbn_act_fwd_kernel<<<dim3((unsigned)bx, (unsigned)c8), kThreads, 0, (cudaStream_t)stream>>>(P);
+        fpl_launch(dsbn_act_fwd_kernel, dim3((unsigned)bx, (unsigned)c8), kThreads, 0, (cudaStream_t)stream, P);
     }
     FPL_LAUNCH_CHECK();
     return 0;
@@ -623,10 +633,10 @@ static dim3 bwd_grid(int n, int d, int h, int w, int c) {
 template <bool APPLY>
 static void bwd_dispatch(const ActBwdParams& P, dim3 grid, cudaStream_t stream) {
     const bool pool = P.g_pool != nullptr, drop = P.drop_p > 0.0f;
-    if (pool && drop) dsbn_act_bwd_kernel<APPLY, true, true><<<grid, kThreads, 0, stream>>>(P);
-    else if (pool) dsbn_act_bwd_kernel<APPLY, true, false><<<grid, kThreads, 0, stream>>>(P);
-    else if (drop) dsbn_act_bwd_kernel<APPLY, false, true><<<grid, kThreads, 0, stream>>>(P);
-    else dsbn_act_bwd_kernel<APPLY, false, false><<<grid, kThreads, 0, stream>>>(P);
+    if (pool && drop) fpl_launch(dsbn_act_bwd_kernel<APPLY, true, true>, grid, kThreads, 0, stream, P);
+    else if (pool) fpl_launch(dsbn_act_bwd_kernel<APPLY, true, false>, grid, kThreads, 0, stream, P);
+    else if (drop) fpl_launch(dsbn_act_bwd_kernel<APPLY, false, true>, grid, kThreads, 0, stream, P);
+    else fpl_launch(dsbn_act_bwd_kernel<APPLY, false, false>, grid, kThreads, 0, stream, P);
 }
 
 extern "C" int fpl_dsbn_act_bwd_reduce(const void* y, const void* g1, int g1_c8tot, int g1_c8off, const void* g_pool,
@@ -689,7 +699,7 @@ extern "C" int fpl_dsbn_act_bwd_apply_fin(const void* y, const void* g1, int g1_
 extern "C" int fpl_dsbn_bwd_finalize(const double* red, const float* scale, const float* save_invstd, int training,
                                      float* dgamma, float* dbeta, float* dslope, float* dbias_conv, int c,
                                      void* stream) {
-    dsbn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(red, scale, training, dgamma, dbeta,
+    fpl_launch(dsbn_bwd_finalize_kernel, (c + 127) / 128, 128, 0, (cudaStream_t)stream, red, scale, training, dgamma, dbeta,
                                                                                 dslope, dbias_conv, save_invstd, c);
     FPL_LAUNCH_CHECK();
     return 0;
@@ -712,6 +722,8 @@ struct AffineBatch {
     float eps;
 };
 __global__ void dsbn_eval_affine_batch_kernel(const __grid_constant__ AffineBatch B) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int e = blockIdx.y;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B.c[e]; i += gridDim.x * blockDim.x) {
         const float invstd = 1.0f / sqrtf(B.var[e][i] + B.eps);      // same expression as the eval branch of bn_prologue
@@ -740,7 +752,7 @@ extern "C" int fpl_dsbn_eval_affine_batch(int count, const float* const* h_gamma
         if (h_c[e] > cmax) cmax = h_c[e];
     }
     B.eps = eps;
-    dsbn_eval_affine_batch_kernel<<<dim3((cmax + 127) / 128, count), 128, 0, (cudaStream_t)stream>>>(B);
+    fpl_launch(dsbn_eval_affine_batch_kernel, dim3((cmax + 127) / 128, count), 128, 0, (cudaStream_t)stream, B);
     FPL_LAUNCH_CHECK();
     return 0;
 }
@@ -758,6 +770,8 @@ struct PoolParams {
 };
 // grid: (chunks of H2*W2, N*D2*C8 pooled planes); one thread per pooled vector
 __global__ void __launch_bounds__(kThreads) maxpool_c8_kernel(PoolParams P) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int kd = P.kd, D2 = P.D / kd, H2 = P.H / 2, W2 = P.W / 2;
     const int HW = P.H * P.W, HW2 = H2 * W2;
     const int pplane = blockIdx.y;
@@ -804,7 +818,7 @@ extern "C" int fpl_maxpool_c8(const void* a, int a_c8tot, int a_c8off, void* poo
     const int64_t planes = (int64_t)n * (d / pool_kd) * (c / 8);
     FPL_REQUIRE(planes <= 65535, "fpl_maxpool_c8: too many planes (%lld)", (long long)planes);
     const int hw2 = (h / 2) * (w / 2);
-    maxpool_c8_kernel<<<dim3((hw2 + kThreads - 1) / kThreads, (unsigned)planes), kThreads, 0, (cudaStream_t)stream>>>(P);
+    fpl_launch(maxpool_c8_kernel, dim3((hw2 + kThreads - 1) / kThreads, (unsigned)planes), kThreads, 0, (cudaStream_t)stream, P);
     FPL_LAUNCH_CHECK();
     return 0;
 }

@@ -44,6 +44,8 @@ __device__ __forceinline__ int argmax_c(const float* z) {
 template <int C>
 __global__ void __launch_bounds__(kThreads) argmax_label_kernel(const float* __restrict__ logits, uint8_t* label, int B,
                                                                int64_t S4) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int64_t total = (int64_t)B * S4;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
         int64_t b = g / S4, s4 = g - b * S4;
@@ -71,6 +73,8 @@ struct PassPtrs {
 template <int C>
 __global__ void __launch_bounds__(kThreads) mc_uncertainty_kernel(PassPtrs ptrs, int K, int64_t S4, double* out,
                                                                  float* umap) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     float var_acc = 0.0f;
     unsigned int cnt = 0;
     const float invK = 1.0f / (float)K;
@@ -169,6 +173,8 @@ __device__ __forceinline__ void mc_probs4(const float* base, int64_t S4, int64_t
 template <int C>
 __global__ void __launch_bounds__(kThreads) mc_uncertainty_stream_kernel(PassPtrs ptrs, int K, int64_t S4, double* out,
                                                                         float* umap) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     float var_acc = 0.0f;
     unsigned int cnt = 0;
     const float invK = 1.0f / (float)K;
@@ -230,6 +236,8 @@ __global__ void __launch_bounds__(kThreads) agree_weight_kernel(const float* __r
                                                                uint8_t* lab_t, uint8_t* lab_s, float* weight, int fold,
                                                                float image_weight, unsigned long long* out_count,
                                                                int64_t S4) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     unsigned int diff = 0;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < S4; g += (int64_t)gridDim.x * blockDim.x) {
         float4 a[C], b[C];
@@ -271,6 +279,8 @@ __global__ void __launch_bounds__(kThreads) window_accumulate_kernel(const float
                                                                     float* count, int BC, int vd, int vh, int vw, int d0,
                                                                     int h0, int w0, int pd, int ph, int pw, int flip_h,
                                                                     int flip_w, float scale) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int64_t total = (int64_t)BC * pd * ph * pw;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int k = (int)(i % pw);
@@ -288,6 +298,8 @@ __global__ void __launch_bounds__(kThreads) window_accumulate_kernel(const float
 
 __global__ void __launch_bounds__(kThreads) window_normalize_kernel(float* out, const float* __restrict__ count,
                                                                    float scale, int64_t numel) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x) {
         float v = out[i];
         if (count != nullptr) v = v / count[i];
@@ -312,7 +324,7 @@ __global__ void __launch_bounds__(kThreads) window_normalize_kernel(float* out, 
 extern "C" int fpl_argmax_label(const float* logits, uint8_t* label, int b, int c, int64_t spatial, void* stream) {
     FPL_REQUIRE(spatial % 4 == 0, "fpl_argmax_label: spatial size %lld must be a multiple of 4", (long long)spatial);
     int64_t s4 = spatial / 4;
-    FPL_DISPATCH_C(c, (argmax_label_kernel<CC><<<grid_for((int64_t)b * s4), kThreads, 0, (cudaStream_t)stream>>>(logits, label, b, s4)));
+    FPL_DISPATCH_C(c, (fpl_launch(argmax_label_kernel<CC>, grid_for((int64_t)b * s4), kThreads, 0, (cudaStream_t)stream, logits, label, b, s4)));
     FPL_LAUNCH_CHECK();
     return 0;
 }
@@ -325,9 +337,9 @@ extern "C" int fpl_mc_uncertainty(const float* const* h_logits_k, int k, int c, 
     for (int i = 0; i < kMaxKStream; ++i) ptrs.p[i] = i < k ? h_logits_k[i] : nullptr;
     int64_t s4 = spatial / 4;
     if (k <= kMaxK) {
-        FPL_DISPATCH_C(c, (mc_uncertainty_kernel<CC><<<grid_for(s4), kThreads, 0, (cudaStream_t)stream>>>(ptrs, k, s4, out, uncertainty_map)));
+        FPL_DISPATCH_C(c, (fpl_launch(mc_uncertainty_kernel<CC>, grid_for(s4), kThreads, 0, (cudaStream_t)stream, ptrs, k, s4, out, uncertainty_map)));
     } else {
-        FPL_DISPATCH_C(c, (mc_uncertainty_stream_kernel<CC><<<grid_for(s4), kThreads, 0, (cudaStream_t)stream>>>(ptrs, k, s4, out, uncertainty_map)));
+        FPL_DISPATCH_C(c, (fpl_launch(mc_uncertainty_stream_kernel<CC>, grid_for(s4), kThreads, 0, (cudaStream_t)stream, ptrs, k, s4, out, uncertainty_map)));
     }
     FPL_LAUNCH_CHECK();
     return 0;
@@ -340,7 +352,7 @@ extern "C" int fpl_agree_weight(const float* logits_tgt, const float* logits_src
                                 long long* out_count, int c, int64_t spatial, void* stream) {
     FPL_REQUIRE(spatial % 4 == 0, "fpl_agree_weight: spatial size %lld must be a multiple of 4", (long long)spatial);
     int64_t s4 = spatial / 4;
-    FPL_DISPATCH_C(c, (agree_weight_kernel<CC><<<grid_for(s4), kThreads, 0, (cudaStream_t)stream>>>(
+    FPL_DISPATCH_C(c, (fpl_launch(agree_weight_kernel<CC>, grid_for(s4), kThreads, 0, (cudaStream_t)stream, 
                           logits_tgt, logits_src, label_tgt, label_src, weight, fold_image_weight, image_weight,
                           (unsigned long long*)out_count, s4)));
     FPL_LAUNCH_CHECK();
@@ -354,14 +366,14 @@ extern "C" int fpl_window_accumulate(const float* patch, float* out, float* coun
                 "fpl_window_accumulate: window [%d+%d,%d+%d,%d+%d] outside volume [%d,%d,%d]", d0, pd, h0, ph, w0, pw,
                 vd, vh, vw);
     int64_t total = (int64_t)b * c * pd * ph * pw;
-    window_accumulate_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(
+    fpl_launch(window_accumulate_kernel, grid_for(total), kThreads, 0, (cudaStream_t)stream, 
         patch, out, count, b * c, vd, vh, vw, d0, h0, w0, pd, ph, pw, flip_h, flip_w, scale);
     FPL_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int fpl_window_normalize(float* out, const float* count, float scale, int64_t numel, void* stream) {
-    window_normalize_kernel<<<grid_for(numel), kThreads, 0, (cudaStream_t)stream>>>(out, count, scale, numel);
+    fpl_launch(window_normalize_kernel, grid_for(numel), kThreads, 0, (cudaStream_t)stream, out, count, scale, numel);
     FPL_LAUNCH_CHECK();
     return 0;
 }

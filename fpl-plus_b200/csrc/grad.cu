@@ -11,6 +11,8 @@ namespace {
 // table[3*s + {0,1,2}] = {source offset, destination offset, element count} (all multiples of 4 floats except the count)
 __global__ void __launch_bounds__(256) grad_scatter_add_kernel(float* __restrict__ dst, const float* __restrict__ src,
                                                                const int* __restrict__ table) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int s = blockIdx.y;
     const int so = __ldg(table + 3 * s), dof = __ldg(table + 3 * s + 1), n = __ldg(table + 3 * s + 2);
     const float* sp = src + so;
@@ -35,7 +37,7 @@ extern "C" int fpl_grad_scatter_add(float* dst, const float* src, const int* d_t
     int bx = (max_numel / 4 + 1023) / 1024;
     if (bx < 1) bx = 1;
     if (bx > 64) bx = 64;
-    grad_scatter_add_kernel<<<dim3(bx, segments), 256, 0, (cudaStream_t)stream>>>(dst, src, d_table);
+    fpl_launch(grad_scatter_add_kernel, dim3(bx, segments), 256, 0, (cudaStream_t)stream, dst, src, d_table);
     FPL_LAUNCH_CHECK();
     return 0;
 }

@@ -41,6 +41,8 @@ __device__ __forceinline__ float bf16_lane(const int4& v, int i) {        // cha
 // ---------------------------------------------------------------------------------------------------------------
 template <int CIN, int VPT>
 __global__ void __launch_bounds__(kThreadsH) head_dgrad_kernel(const HeadParams P) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     constexpr int kTW = kTX * VPT, kHW = kTW + 2;
     __shared__ float sdl[kMaxClasses][kHH][kHW + 1];
     __shared__ __align__(16) float sw[9 * kMaxClasses * CIN];      // [tap][k][c]
@@ -154,6 +156,8 @@ __global__ void __launch_bounds__(kThreadsH) head_dgrad_kernel(const HeadParams 
 // ---------------------------------------------------------------------------------------------------------------
 template <int CIN, int KP>                      // KP: classes padded to 2, 4 or 8 accumulators per voxel
 __global__ void __launch_bounds__(kThreadsH) head_fwd_kernel(const HeadParams P) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     constexpr int VPT = 4, kTW = kTX * VPT, kHW = kTW + 2;
     extern __shared__ __align__(16) uint8_t head_smem[];
     int4* sx = reinterpret_cast<int4*>(head_smem);                                        // [CIN/8][kHH][kHW]
@@ -252,7 +256,7 @@ int launch_head_fwd_kp(const HeadParams& P, cudaStream_t st) {
     const int smem = (CIN / 8) * kHH * kHW * 16 + 9 * CIN * KP * 4;
     FPL_CHECK_CUDA(cudaFuncSetAttribute(head_fwd_kernel<CIN, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     dim3 grid((P.W + kTW - 1) / kTW, (P.H + kTH - 1) / kTH, P.N * P.D);
-    head_fwd_kernel<CIN, KP><<<grid, kThreadsH, smem, st>>>(P);
+    fpl_launch(head_fwd_kernel<CIN, KP>, grid, kThreadsH, smem, st, P);
     return 0;
 }
 
@@ -282,10 +286,10 @@ extern "C" int fpl_head_dgrad(const float* dlogits, const float* w, void* g, int
     P.N = n; P.D = d; P.H = h; P.W = w_; P.cin = cin; P.classes = classes;
     if (cin == 16) {
         dim3 grid((w_ + kTX * 4 - 1) / (kTX * 4), (h + kTH - 1) / kTH, n * d);
-        head_dgrad_kernel<16, 4><<<grid, kThreadsH, 0, (cudaStream_t)stream>>>(P);
+        fpl_launch(head_dgrad_kernel<16, 4>, grid, kThreadsH, 0, (cudaStream_t)stream, P);
     } else {
         dim3 grid((w_ + kTX * 2 - 1) / (kTX * 2), (h + kTH - 1) / kTH, n * d);
-        head_dgrad_kernel<32, 2><<<grid, kThreadsH, 0, (cudaStream_t)stream>>>(P);
+        fpl_launch(head_dgrad_kernel<32, 2>, grid, kThreadsH, 0, (cudaStream_t)stream, P);
     }
     FPL_LAUNCH_CHECK();
     return 0;

@@ -73,6 +73,8 @@ __device__ __forceinline__ float4 load_weight4(const LossSrc& src, int64_t n, in
 template <int C>
 __global__ void __launch_bounds__(kThreads) dice_ce_reduce_kernel(const float* __restrict__ logits, LossSrc src,
                                                                  double* sums, int N, int64_t S4, int want_entropy) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const bool weighted = src.weight != nullptr || src.wcode != nullptr;
     constexpr int NV = 6 * C + 3;
     float acc[NV];
@@ -151,6 +153,8 @@ __global__ void __launch_bounds__(kThreads) dice_ce_grad_kernel(const float* __r
                                                                float w_ce, float w_ent, float grad_scale,
                                                                const float* __restrict__ grad_scale_dev, float* loss,
                                                                float* dlogits, int N, int64_t S4) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const bool weighted = src.weight != nullptr || src.wcode != nullptr;
     if (grad_scale_dev != nullptr) grad_scale *= __ldg(grad_scale_dev);
     // per-class constants of dDice/dp:  g_c = -(1/C) * w * (2*y*den - num) / den^2
@@ -248,7 +252,7 @@ static int dice_ce_reduce_launch(const float* logits, const LossSrc& src, double
     FPL_REQUIRE(spatial % 4 == 0, "fpl_dice_ce_reduce: spatial size %lld must be a multiple of 4", (long long)spatial);
     FPL_REQUIRE(src.soft_y != nullptr || src.label != nullptr, "fpl_dice_ce_reduce: soft_y or label required");
     int64_t s4 = spatial / 4;
-    FPL_DISPATCH_C(c, (dice_ce_reduce_kernel<CC><<<grid_for((int64_t)n * s4), kThreads, 0, (cudaStream_t)stream>>>(
+    FPL_DISPATCH_C(c, (fpl_launch(dice_ce_reduce_kernel<CC>, grid_for((int64_t)n * s4), kThreads, 0, (cudaStream_t)stream, 
                           logits, src, sums, n, s4, want_entropy)));
     FPL_LAUNCH_CHECK();
     return 0;
@@ -261,7 +265,7 @@ static int dice_ce_grad_launch(const float* logits, const LossSrc& src, const do
     FPL_REQUIRE(src.soft_y != nullptr || src.label != nullptr, "fpl_dice_ce_grad: soft_y or label required");
     int64_t s4 = spatial / 4;
     int grid = dlogits != nullptr ? grid_for((int64_t)n * s4) : 1;
-    FPL_DISPATCH_C(c, (dice_ce_grad_kernel<CC><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+    FPL_DISPATCH_C(c, (fpl_launch(dice_ce_grad_kernel<CC>, grid, kThreads, 0, (cudaStream_t)stream, 
                           logits, src, sums, w_dice, w_ce, w_ent, grad_scale, grad_scale_dev, loss, dlogits, n, s4)));
     FPL_LAUNCH_CHECK();
     return 0;

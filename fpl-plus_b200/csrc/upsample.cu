@@ -33,6 +33,8 @@ __device__ __forceinline__ void src_index(float scale, int dst, int in, int& i0,
 
 // one thread per OUTPUT vector
 __global__ void __launch_bounds__(kThreadsU) upsample2x_fwd_kernel(const UpParams P) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int Do = P.D * P.kd2, Ho = 2 * P.H, Wo = 2 * P.W;
     const int64_t total = (int64_t)P.N * Do * P.C8 * Ho * Wo;
     const int64_t HW = (int64_t)P.H * P.W, HWo = (int64_t)Ho * Wo;
@@ -75,6 +77,8 @@ __device__ __forceinline__ float axis_weight(float scale, int o, int in, int i) 
 
 // one thread per INPUT (low-res) vector: gathers from the <= 4 output indices per axis that read it
 __global__ void __launch_bounds__(kThreadsU) upsample2x_bwd_kernel(const UpParams P) {
+    FPL_PDL_TRIGGER();
+    FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int Do = P.D * P.kd2, Ho = 2 * P.H, Wo = 2 * P.W;
     const int64_t total = (int64_t)P.N * P.D * P.C8 * P.H * P.W;
     const int64_t HW = (int64_t)P.H * P.W, HWo = (int64_t)Ho * Wo;
@@ -147,7 +151,7 @@ extern "C" int fpl_upsample2x_c8(const void* x, int x_c8tot, int x_c8off, void* 
                                  int h, int w, int c, int kd2, void* stream) {
     UpParams P;
     if (int rc = fill(P, x, x_c8tot, x_c8off, y, y_c8tot, y_c8off, n, d, h, w, c, kd2)) return rc;
-    upsample2x_fwd_kernel<<<grid_u((int64_t)n * d * kd2 * (c / 8) * 4 * h * w), kThreadsU, 0, (cudaStream_t)stream>>>(P);
+    fpl_launch(upsample2x_fwd_kernel, grid_u((int64_t)n * d * kd2 * (c / 8) * 4 * h * w), kThreadsU, 0, (cudaStream_t)stream, P);
     FPL_LAUNCH_CHECK();
     return 0;
 }
@@ -156,7 +160,7 @@ extern "C" int fpl_upsample2x_c8_bwd(const void* gy, int gy_c8tot, int gy_c8off,
                                      int d, int h, int w, int c, int kd2, void* stream) {
     UpParams P;
     if (int rc = fill(P, gy, gy_c8tot, gy_c8off, gx, gx_c8tot, gx_c8off, n, d, h, w, c, kd2)) return rc;
-    upsample2x_bwd_kernel<<<grid_u((int64_t)n * d * (c / 8) * h * w), kThreadsU, 0, (cudaStream_t)stream>>>(P);
+    fpl_launch(upsample2x_bwd_kernel, grid_u((int64_t)n * d * (c / 8) * h * w), kThreadsU, 0, (cudaStream_t)stream, P);
     FPL_LAUNCH_CHECK();
     return 0;
 }
