@@ -35,7 +35,6 @@ __global__ void __launch_bounds__(kAdamThreads) adam_multi_tensor_kernel(const A
                                                                          const float* __restrict__ lr_dev, double lr_host,
                                                                          double beta1, double beta2, float eps, float wd,
                                                                          unsigned int* done_counter) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     // torch evaluates 1 - beta, beta ** step and lr / bias_correction in Python doubles and hands the kernels the fp32
     // roundings of those: 1.0f - 0.999f differs from float(1 - 0.999) by 1.3e-5 relative

@@ -27,7 +27,6 @@ struct ConvP {
 };
 
 __global__ void __launch_bounds__(128) conv3d_direct_kernel(ConvP P) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int T = P.kd * 9;
     __shared__ __align__(16) float wsm[27][8][8];   // [tap][ci][co]
@@ -117,7 +116,6 @@ struct WgradP {
 
 template <int MODE>
 __global__ void __launch_bounds__(256) wgrad_kernel(WgradP P) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     __shared__ __align__(16) float dys[64][33];
     __shared__ __align__(16) float xs[64][36];
@@ -185,7 +183,6 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WgradP P) {
 // per-channel sum of a C8-planar tensor (bias gradients): grid (chunks, planes)
 __global__ void __launch_bounds__(256) channel_sum_kernel(const bf16x8* __restrict__ g, int c8tot, int c8off, float* out,
                                                           int ND, int C8, int HW) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int plane = blockIdx.y, c8 = plane % C8, nd = plane / C8;
     float s[8];
@@ -222,7 +219,6 @@ struct StemP {
 };
 
 __global__ void __launch_bounds__(128) stem_conv_fwd_kernel(StemP P) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     extern __shared__ float wsm_dyn[];   // [ci][tap][8 co] for this co8
     __shared__ float red[4][16];
@@ -288,7 +284,6 @@ struct StemWP {
 };
 
 __global__ void __launch_bounds__(256) stem_conv_wgrad_kernel(StemWP P) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     extern __shared__ float sm_dyn[];
     const int T = P.kd * 9;
@@ -362,7 +357,6 @@ struct HeadP {
 };
 
 __global__ void __launch_bounds__(128) head_conv_fwd_kernel(HeadP P) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     extern __shared__ float wsm_dyn[];   // [tap 9][ci][cls]
     const int HW = P.H * P.W;
@@ -406,7 +400,6 @@ __global__ void __launch_bounds__(128) head_conv_fwd_kernel(HeadP P) {
 
 // dgrad: thread = voxel x 8 input channels
 __global__ void __launch_bounds__(128) head_conv_dgrad_kernel(HeadP P) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     extern __shared__ float wsm_dyn[];   // [tap 9][cls][8 ci] for this ci8
     const int HW = P.H * P.W;
@@ -445,7 +438,6 @@ __global__ void __launch_bounds__(128) head_conv_dgrad_kernel(HeadP P) {
 
 // wgrad + bias grad: block = (row group, plane); thread = (cls, ci, tap) element
 __global__ void __launch_bounds__(256) head_conv_wgrad_kernel(HeadP P) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     extern __shared__ float sm_dyn[];
     const int HW = P.H * P.W;
@@ -518,7 +510,6 @@ struct ConvTP {
 
 // fwd: thread = output voxel x 8 co.  block = 128 consecutive output w of one output row.
 __global__ void __launch_bounds__(128) convt_fwd_kernel(ConvTP P) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     extern __shared__ float wsm_dyn[];   // [ci][c parity 2][8 co]
     const int T = P.kd2 * 4;
@@ -555,7 +546,6 @@ __global__ void __launch_bounds__(128) convt_fwd_kernel(ConvTP P) {
 
 // dgrad: thread = low-res voxel x 8 ci; loops the kd2*4 positions and all co
 __global__ void __launch_bounds__(128) convt_dgrad_kernel(ConvTP P) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     extern __shared__ float wsm_dyn[];   // [pos T][co][8 ci]
     const int T = P.kd2 * 4;
@@ -595,7 +585,6 @@ __global__ void __launch_bounds__(128) convt_dgrad_kernel(ConvTP P) {
 // optional per-channel sums (the bias gradient when the tensor is dlogits).  grid: (chunks of H*W, N*D)
 __global__ void __launch_bounds__(256) pack_ncdhw_c8_kernel(const float* __restrict__ x, int C, bf16x8* out, int c8tot,
                                                             int c8off, int groups, float* chan_sum, int D, int HW) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int nd = blockIdx.y, n = nd / D, d = nd - n * D;
     float s[16];
@@ -634,7 +623,6 @@ __global__ void __launch_bounds__(256) pack_ncdhw_c8_kernel(const float* __restr
 // neighbour x[d][h+kh-1][w+kw-1] (zero outside the plane), channels 9..15 are zero.  The stem conv k(3,3,3) then is a
 // k(3,1,1) conv over these 16 channels, which the tensor-core kernels run with ONE in-plane tap.
 __global__ void __launch_bounds__(256) patch9_kernel(const float* __restrict__ x, bf16x8* out, int D, int H, int W, int split) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int nd = blockIdx.y;
     const int HW = H * W;

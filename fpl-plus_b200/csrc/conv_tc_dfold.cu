@@ -37,6 +37,7 @@ struct DfParams {
     int taps;                        // 9 (k 3x3x3) or 1 (k 3x1x1: only the centre in-plane tap)
     int a_ksteps;                    // distinct 16-channel K steps of A (B K step j reads A K step j % a_ksteps)
     EpiAct act;                      // act.scale != NULL: inference epilogue (affine + PReLU) instead of + bias
+    EpiBwdRed br;                    // br.red != NULL (dgrad): BatchNorm-backward sums of the unit whose activation gradient is written
 };
 
 __device__ __forceinline__ void tmem_st_zero16(uint32_t taddr) {
@@ -66,7 +67,6 @@ __device__ __forceinline__ DfItem decode_item(const DfParams& P, int t) {
 }
 
 __global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid_constant__ CUtensorMap xmap, DfParams P) {
-    FPL_PDL_TRIGGER();   // dependents may be scheduled; they block in their own FPL_PDL_WAIT
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     // [resident weights of this CTA's slice][A stage ring][barriers][bias]
@@ -94,9 +94,13 @@ __global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid
     FPL_PDL_WAIT();      // prologue above overlapped the previous kernel's tail; from here on its results are visible
     float* scale_sm = bias_sm + P.cout;
     const bool fuse_act = P.act.scale != nullptr;
+    float* br_sc = scale_sm + P.cout;
+    float* br_sh = br_sc + P.cout;
+    const bool fuse_br = P.br.red != nullptr;
     for (int i = threadIdx.x; i < P.cout; i += kThreadsD) {
         bias_sm[i] = fuse_act ? P.act.shift[i] : (P.bias != nullptr ? P.bias[i] : 0.0f);
         scale_sm[i] = fuse_act ? P.act.scale[i] : 1.0f;
+        if (fuse_br) { br_sc[i] = P.br.scale[i]; br_sh[i] = P.br.shift[i]; }
     }
     tc_fence_before();
     __syncthreads();
@@ -193,6 +197,7 @@ __global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid
             }
             item_phase ^= 1;
         }
+        FPL_PDL_TRIGGER();   // this CTA has issued its last tile: the next kernel of the stream may be scheduled as SMs drain
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int quarter = warp & 3;
@@ -214,14 +219,21 @@ __global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid
         uint32_t item_phase = 0;
         int cur_slice = -1;
         const float act_slope = fuse_act ? __ldg(P.act.slope) : 0.0f;
+        // fused BatchNorm-backward statistics (dgrad only; exclusive with want_stats, so `run` is shared)
+        const float br_slope = fuse_br ? __ldg(P.br.slope) : 0.0f;
+        const bool br_drop = fuse_br && P.br.drop_p > 0.0f;
+        const float br_keep_scale = br_drop ? 1.0f / (1.0f - P.br.drop_p) : 1.0f;
+        const uint64_t br_seed = br_drop ? P.br.seed + (P.br.seed_dev != nullptr ? (uint64_t)__ldg(P.br.seed_dev) : 0ull) : 0ull;
+        float br_dsl = 0.0f;
         for (int t = blockIdx.x; t < P.total_items; t += gridDim.x) {
             const DfItem c = decode_item(P, t);
-            if (want_stats && c.slice != cur_slice) {
+            if ((want_stats || fuse_br) && c.slice != cur_slice) {
                 if (cur_slice >= 0) {
 #pragma unroll
                     for (int k = 0; k < kMaxChunks; ++k)
                         if (k < nchunk16) {
-                            atomicAdd(P.stats + (lane >> 4) * P.cout + cur_slice * P.nb + k * 16 + (lane & 15), (double)run[k]);
+                            if (want_stats) atomicAdd(P.stats + (lane >> 4) * P.cout + cur_slice * P.nb + k * 16 + (lane & 15), (double)run[k]);
+                            else epi_bwdred_flush(P.br, P.cout, cur_slice * P.nb + k * 16, run[k], lane);
                             run[k] = 0.0f;
                         }
                 }
@@ -281,6 +293,16 @@ __global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid
                             }
                             warp_transpose_sum32(v, lane);
                             run[k] += v[0];
+                        } else if (fuse_br) {
+                            const int C8 = P.cout >> 3;
+                            const int64_t vec0 = (((int64_t)c.n * P.D + c.d0 + p) * C8 + (c.slice * P.nb + c0) / 8) * HW + (int64_t)h * P.W + w;
+                            uint32_t keep0 = 0xffu, keep1 = 0xffu;
+                            if (br_drop && valid) {
+                                keep0 = dropout_keep8(br_seed, P.br.offset, (uint64_t)vec0, P.br.drop_p);
+                                keep1 = dropout_keep8(br_seed, P.br.offset, (uint64_t)(vec0 + HW), P.br.drop_p);
+                            }
+                            epi_bwdred16(v, valid, P.br.y + vec0, P.br.y + vec0 + HW, br_sc + c.slice * P.nb + c0,
+                                         br_sh + c.slice * P.nb + c0, br_slope, br_drop, keep0, keep1, br_keep_scale, lane, run[k], br_dsl);
                         }
                     }
                 }
@@ -297,6 +319,15 @@ __global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid
                 if (k < nchunk16)
                     atomicAdd(P.stats + (lane >> 4) * P.cout + cur_slice * P.nb + k * 16 + (lane & 15), (double)run[k]);
         }
+        if (fuse_br) {
+            if (cur_slice >= 0) {
+#pragma unroll
+                for (int k = 0; k < kMaxChunks; ++k)
+                    if (k < nchunk16) epi_bwdred_flush(P.br, P.cout, cur_slice * P.nb + k * 16, run[k], lane);
+            }
+            br_dsl = warp_sum(br_dsl);
+            if (lane == 0 && br_dsl != 0.0f) atomicAdd(P.br.red + 2 * P.cout, (double)br_dsl);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -310,7 +341,6 @@ __global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid
 // z-1+jj of input plane z, i.e. depth tap kd = 2 - jj.  transpose_flip as in fpl_conv3d_prep_weight.
 __global__ void dfold_prep_kernel(const float* __restrict__ w, __nv_bfloat16* image, int cin_eff, int cout_eff, int transpose_flip,
                                   int nb, int total, int taps) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int ksteps = cin_eff / 16, n3 = 3 * nb, T = 3 * taps;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -353,7 +383,7 @@ bool make_df_cfg(int cin, int cout, int d, DfCfg& c, int taps = 9, int cin_a = 0
     while (c.tmem_cols < cols) c.tmem_cols *= 2;
     if (c.tmem_cols > 512) return false;
     c.stages = c.b_bytes <= 32 * 1024 ? 6 : 4;
-    c.smem_bytes = c.b_bytes + c.stages * c.a_bytes + 1024 + 512 + 2 * cout * (int)sizeof(float) + 16;
+    c.smem_bytes = c.b_bytes + c.stages * c.a_bytes + 1024 + 512 + 4 * cout * (int)sizeof(float) + 16;
     if (c.smem_bytes > 220 * 1024) return false;
     c.ctas_per_sm = (c.smem_bytes <= 110 * 1024 && c.tmem_cols <= 256) ? 2 : 1;
     return true;
@@ -408,7 +438,6 @@ struct DfPrepBatch {
 };
 // one thread per (out, in) pair: 27 contiguous source floats -> 27 image positions (see prep_weight_batch_kernel)
 __global__ void dfold_prep_batch_kernel(const __grid_constant__ DfPrepBatch B) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int e = blockIdx.y;
     const float* __restrict__ w = B.w[e];
@@ -458,7 +487,7 @@ extern "C" int fpl_conv3d_dfold_prep_weight_batch(int count, const float* const*
 
 static int dfold_launch(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias, void* y,
                         int y_c8tot, int y_c8off, double* stats, int n, int d, int h, int w, int cin, int cout, int taps,
-                        int cin_a, void* stream, const EpiAct* act = nullptr) {
+                        int cin_a, void* stream, const EpiAct* act = nullptr, const EpiBwdRed* br = nullptr) {
     if (cin_a <= 0) cin_a = cin;
     DfCfg c;
     FPL_REQUIRE(make_df_cfg(cin, cout, d, c, taps, cin_a), "fpl_conv3d_tc_dfold: unsupported shape (%d -> %d, depth %d)", cin, cout, d);
@@ -486,6 +515,7 @@ static int dfold_launch(const void* x, int x_c8tot, int x_c8off, const void* ima
     FPL_REQUIRE(total < (1ll << 30), "fpl_conv3d_tc_dfold: too many items");
     P.total_items = (int)total;
     P.taps = taps; P.a_ksteps = cin_a / 16;
+    if (br != nullptr) P.br = *br; else { P.br.y = nullptr; P.br.scale = P.br.shift = P.br.mean = P.br.invstd = P.br.slope = nullptr; P.br.drop_p = 0.0f; P.br.seed = P.br.offset = 0; P.br.seed_dev = nullptr; P.br.red = nullptr; }
     if (act != nullptr) P.act = *act; else { P.act.scale = nullptr; P.act.shift = nullptr; P.act.slope = nullptr; P.act.drop_p = 0.0f; P.act.seed = P.act.offset = 0; P.act.seed_dev = nullptr; }
     FPL_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_dfold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
     int grid = FPL_NUM_SMS * c.ctas_per_sm;
@@ -530,3 +560,21 @@ extern "C" int fpl_conv3d_tc_k311_act(const void* x, int x_c8tot, int x_c8off, c
     return dfold_launch(x, x_c8tot, x_c8off, image, nullptr, a, a_c8tot, a_c8off, nullptr, n, d, h, w, cin, cout, 1, a_channels,
                         stream, &act);
 }
+
+/* dgrad form of fpl_conv3d_tc_dfold that also accumulates the BatchNorm-backward sums of the unit whose activation
+ * gradient it writes (fpl_conv3d_tc_bwdred, EpiBwdRed in common.cuh). */
+extern "C" int fpl_conv3d_tc_dfold_bwdred(const void* x, int x_c8tot, int x_c8off, const void* image, void* y, int y_c8tot,
+                                          int y_c8off, int n, int d, int h, int w, int cin, int cout, const void* y_prev,
+                                          const float* scale, const float* shift, const float* mean, const float* invstd,
+                                          const float* slope, float drop_p, uint64_t seed, uint64_t offset,
+                                          const uint64_t* seed_dev, double* red, void* stream) {
+    FPL_REQUIRE(y_prev != nullptr && scale != nullptr && shift != nullptr && mean != nullptr && invstd != nullptr &&
+                slope != nullptr && red != nullptr, "fpl_conv3d_tc_dfold_bwdred: NULL argument");
+    FPL_REQUIRE(drop_p >= 0.0f && drop_p < 1.0f, "fpl_conv3d_tc_dfold_bwdred: dropout p=%f out of [0,1)", drop_p);
+    EpiBwdRed br;
+    br.y = (const bf16x8*)y_prev; br.scale = scale; br.shift = shift; br.mean = mean; br.invstd = invstd; br.slope = slope;
+    br.drop_p = drop_p; br.seed = seed; br.offset = offset; br.seed_dev = (const unsigned long long*)seed_dev; br.red = red;
+    return dfold_launch(x, x_c8tot, x_c8off, image, nullptr, y, y_c8tot, y_c8off, nullptr, n, d, h, w, cin, cout, 9, 0, stream,
+                        nullptr, &br);
+}
+

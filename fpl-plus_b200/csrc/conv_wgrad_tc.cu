@@ -126,7 +126,6 @@ __device__ __forceinline__ WgWork decode_work(const WgParams& P, int b) {
 
 __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid_constant__ CUtensorMap xmap,
                                                                    const __grid_constant__ CUtensorMap dymap, WgParams P) {
-    FPL_PDL_TRIGGER();   // dependents may be scheduled; they block in their own FPL_PDL_WAIT
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     // barriers live in front of the stage ring so that operand over-reads past the last stage stay in the pad
@@ -226,6 +225,7 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
         }
         if (leader) umma_commit(done_bar);
         __syncwarp();
+        FPL_PDL_TRIGGER();   // this CTA has issued its last tile: the next kernel of the stream may be scheduled as SMs drain
     } else if (tile_end > tile_begin) {
         // ===================== epilogue: TMEM -> fp32 atomics into dW =====================
         const int quarter = warp & 3;
@@ -391,7 +391,6 @@ struct FoldBatch {
 // Negative tap count: nn.ConvTranspose3d layout, row = ci*cout + co (small tensors; the gather is left uncoalesced).
 constexpr int kFoldRows = 256;
 __global__ void __launch_bounds__(256) fold_tapmajor_kernel(const __grid_constant__ FoldBatch B) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     __shared__ float tile[kFoldRows * 27];
     const int e = blockIdx.y;

@@ -74,7 +74,6 @@ bool make_ct_cfg(int kdim, int ndim, int kc_div, CtCfg& c) {
 }
 
 __global__ void __launch_bounds__(kThreadsT) convt_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, CtParams P) {
-    FPL_PDL_TRIGGER();   // dependents may be scheduled; they block in their own FPL_PDL_WAIT
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stage_bytes = P.a_bytes + P.b_bytes;
@@ -167,6 +166,7 @@ __global__ void __launch_bounds__(kThreadsT) convt_gemm_tc_kernel(const __grid_c
             __syncwarp();
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        FPL_PDL_TRIGGER();   // this CTA has issued its last tile: the next kernel of the stream may be scheduled as SMs drain
     } else {
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
@@ -232,7 +232,6 @@ __global__ void __launch_bounds__(kThreadsT) convt_gemm_tc_kernel(const __grid_c
 //   mode 0 (fwd):   B[k = ci][n = tap*cout + co]          mode 1 (dgrad): B[k = tap*cout + co][n = ci]
 __global__ void convt_prep_kernel(const float* __restrict__ w, __nv_bfloat16* image, int cin, int cout, int ntaps, int mode,
                                   int nb, int kc, int nchunks, int total) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int t = i;
@@ -275,7 +274,6 @@ struct CtwParams {
 
 __global__ void __launch_bounds__(kThreadsT) convt_wgrad_tc_kernel(const __grid_constant__ CUtensorMap xmap,
                                                                   const __grid_constant__ CUtensorMap dymap, CtwParams P) {
-    FPL_PDL_TRIGGER();   // dependents may be scheduled; they block in their own FPL_PDL_WAIT
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -360,6 +358,7 @@ __global__ void __launch_bounds__(kThreadsT) convt_wgrad_tc_kernel(const __grid_
         }
         if (leader) umma_commit(done_bar);
         __syncwarp();
+        FPL_PDL_TRIGGER();   // this CTA has issued its last tile: the next kernel of the stream may be scheduled as SMs drain
     } else if (tile_end > tile_begin) {
         const int quarter = warp & 3;
         mbar_wait(done_bar, 0);
@@ -423,7 +422,6 @@ struct CtPrepBatch {
         nchunks[kMaxCtBatch], total[kMaxCtBatch];
 };
 __global__ void convt_prep_batch_kernel(const __grid_constant__ CtPrepBatch B) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int e = blockIdx.y;
     const float* __restrict__ w = B.w[e];

@@ -23,7 +23,6 @@ __global__ void dsbn_finalize_kernel(const double* __restrict__ stats, double in
                                      float* running_mean, float* running_var, long long* nbt,
                                      float momentum, float eps, int training,
                                      float* scale, float* shift, float* save_mean, float* save_invstd, int C) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < C) {
@@ -154,7 +153,6 @@ __device__ __forceinline__ uint32_t keep_bits(const uint2* mask, uint64_t seed, 
 // the prologue, live in registers) and walks over work items = (plane (n,d), chunk of 2*256 vectors), two vectors per
 // thread in flight, with stepped plane pointers (same structure as dsbn_act_bwd_kernel below).
 __global__ void __launch_bounds__(kThreads) dsbn_act_fwd_kernel(const __grid_constant__ ActParams P) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int HW = P.H * P.W;
     const int c8 = blockIdx.y;
@@ -207,7 +205,6 @@ __global__ void __launch_bounds__(kThreads) dsbn_act_fwd_kernel(const __grid_con
 // order d,h,w as in torch's max_pool3d).
 // grid: (blocks per channel group, C8); work items = (pooled plane (n,d2), chunk of 256 pooled vectors)
 __global__ void __launch_bounds__(kThreads) dsbn_act_pool_fwd_kernel(const __grid_constant__ ActParams P) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int kd = P.pool_kd;
     const int D2 = P.D / kd, H2 = P.H / 2, W2 = P.W / 2;
@@ -312,7 +309,6 @@ constexpr int kBwdV = FPL_BWD_V;          // vectors per thread per work item
 constexpr int kBwdBlocks = FPL_BWD_BLOCKS; // resident blocks per SM the register budget is tuned for
 template <bool APPLY, bool POOL, bool DROP>
 __global__ void __launch_bounds__(kThreads, kBwdBlocks) dsbn_act_bwd_kernel(const __grid_constant__ ActBwdParams P) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int HW = P.H * P.W;
     const int c8 = blockIdx.y;
@@ -453,6 +449,7 @@ __global__ void __launch_bounds__(kThreads, kBwdBlocks) dsbn_act_bwd_kernel(cons
             while (pd >= P.D) { pd -= P.D; ++pn; }
         }
     }
+    FPL_PDL_TRIGGER();       // main loop done: the next kernel of the stream may be scheduled as blocks drain
     if (!APPLY) {
         __shared__ float sm[kThreads / 32][17];
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -489,7 +486,6 @@ __global__ void __launch_bounds__(kThreads, kBwdBlocks) dsbn_act_bwd_kernel(cons
 __global__ void dsbn_bwd_finalize_kernel(const double* __restrict__ red, const float* __restrict__ scale, int training,
                                          float* dgamma, float* dbeta, float* dslope, float* dbias_conv,
                                          const float* __restrict__ invstd, int C) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < C) {
@@ -722,7 +718,6 @@ struct AffineBatch {
     float eps;
 };
 __global__ void dsbn_eval_affine_batch_kernel(const __grid_constant__ AffineBatch B) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int e = blockIdx.y;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B.c[e]; i += gridDim.x * blockDim.x) {
@@ -770,7 +765,6 @@ struct PoolParams {
 };
 // grid: (chunks of H2*W2, N*D2*C8 pooled planes); one thread per pooled vector
 __global__ void __launch_bounds__(kThreads) maxpool_c8_kernel(PoolParams P) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int kd = P.kd, D2 = P.D / kd, H2 = P.H / 2, W2 = P.W / 2;
     const int HW = P.H * P.W, HW2 = H2 * W2;

@@ -44,7 +44,6 @@ __device__ __forceinline__ int argmax_c(const float* z) {
 template <int C>
 __global__ void __launch_bounds__(kThreads) argmax_label_kernel(const float* __restrict__ logits, uint8_t* label, int B,
                                                                int64_t S4) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int64_t total = (int64_t)B * S4;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
@@ -73,7 +72,6 @@ struct PassPtrs {
 template <int C>
 __global__ void __launch_bounds__(kThreads) mc_uncertainty_kernel(PassPtrs ptrs, int K, int64_t S4, double* out,
                                                                  float* umap) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     float var_acc = 0.0f;
     unsigned int cnt = 0;
@@ -173,7 +171,6 @@ __device__ __forceinline__ void mc_probs4(const float* base, int64_t S4, int64_t
 template <int C>
 __global__ void __launch_bounds__(kThreads) mc_uncertainty_stream_kernel(PassPtrs ptrs, int K, int64_t S4, double* out,
                                                                         float* umap) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     float var_acc = 0.0f;
     unsigned int cnt = 0;
@@ -236,7 +233,6 @@ __global__ void __launch_bounds__(kThreads) agree_weight_kernel(const float* __r
                                                                uint8_t* lab_t, uint8_t* lab_s, float* weight, int fold,
                                                                float image_weight, unsigned long long* out_count,
                                                                int64_t S4) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     unsigned int diff = 0;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < S4; g += (int64_t)gridDim.x * blockDim.x) {
@@ -279,7 +275,6 @@ __global__ void __launch_bounds__(kThreads) window_accumulate_kernel(const float
                                                                     float* count, int BC, int vd, int vh, int vw, int d0,
                                                                     int h0, int w0, int pd, int ph, int pw, int flip_h,
                                                                     int flip_w, float scale) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int64_t total = (int64_t)BC * pd * ph * pw;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -298,7 +293,6 @@ __global__ void __launch_bounds__(kThreads) window_accumulate_kernel(const float
 
 __global__ void __launch_bounds__(kThreads) window_normalize_kernel(float* out, const float* __restrict__ count,
                                                                    float scale, int64_t numel) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x) {
         float v = out[i];

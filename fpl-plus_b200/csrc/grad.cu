@@ -11,7 +11,6 @@ namespace {
 // table[3*s + {0,1,2}] = {source offset, destination offset, element count} (all multiples of 4 floats except the count)
 __global__ void __launch_bounds__(256) grad_scatter_add_kernel(float* __restrict__ dst, const float* __restrict__ src,
                                                                const int* __restrict__ table) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int s = blockIdx.y;
     const int so = __ldg(table + 3 * s), dof = __ldg(table + 3 * s + 1), n = __ldg(table + 3 * s + 2);

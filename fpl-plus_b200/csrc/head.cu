@@ -41,7 +41,6 @@ __device__ __forceinline__ float bf16_lane(const int4& v, int i) {        // cha
 // ---------------------------------------------------------------------------------------------------------------
 template <int CIN, int VPT>
 __global__ void __launch_bounds__(kThreadsH) head_dgrad_kernel(const HeadParams P) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     constexpr int kTW = kTX * VPT, kHW = kTW + 2;
     __shared__ float sdl[kMaxClasses][kHH][kHW + 1];
@@ -156,7 +155,6 @@ __global__ void __launch_bounds__(kThreadsH) head_dgrad_kernel(const HeadParams 
 // ---------------------------------------------------------------------------------------------------------------
 template <int CIN, int KP>                      // KP: classes padded to 2, 4 or 8 accumulators per voxel
 __global__ void __launch_bounds__(kThreadsH) head_fwd_kernel(const HeadParams P) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     constexpr int VPT = 4, kTW = kTX * VPT, kHW = kTW + 2;
     extern __shared__ __align__(16) uint8_t head_smem[];

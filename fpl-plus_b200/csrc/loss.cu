@@ -73,7 +73,6 @@ __device__ __forceinline__ float4 load_weight4(const LossSrc& src, int64_t n, in
 template <int C>
 __global__ void __launch_bounds__(kThreads) dice_ce_reduce_kernel(const float* __restrict__ logits, LossSrc src,
                                                                  double* sums, int N, int64_t S4, int want_entropy) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const bool weighted = src.weight != nullptr || src.wcode != nullptr;
     constexpr int NV = 6 * C + 3;
@@ -153,7 +152,6 @@ __global__ void __launch_bounds__(kThreads) dice_ce_grad_kernel(const float* __r
                                                                float w_ce, float w_ent, float grad_scale,
                                                                const float* __restrict__ grad_scale_dev, float* loss,
                                                                float* dlogits, int N, int64_t S4) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const bool weighted = src.weight != nullptr || src.wcode != nullptr;
     if (grad_scale_dev != nullptr) grad_scale *= __ldg(grad_scale_dev);

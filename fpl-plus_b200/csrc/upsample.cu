@@ -33,7 +33,6 @@ __device__ __forceinline__ void src_index(float scale, int dst, int in, int& i0,
 
 // one thread per OUTPUT vector
 __global__ void __launch_bounds__(kThreadsU) upsample2x_fwd_kernel(const UpParams P) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int Do = P.D * P.kd2, Ho = 2 * P.H, Wo = 2 * P.W;
     const int64_t total = (int64_t)P.N * Do * P.C8 * Ho * Wo;
@@ -77,7 +76,6 @@ __device__ __forceinline__ float axis_weight(float scale, int o, int in, int i) 
 
 // one thread per INPUT (low-res) vector: gathers from the <= 4 output indices per axis that read it
 __global__ void __launch_bounds__(kThreadsU) upsample2x_bwd_kernel(const UpParams P) {
-    FPL_PDL_TRIGGER();
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const int Do = P.D * P.kd2, Ho = 2 * P.H, Wo = 2 * P.W;
     const int64_t total = (int64_t)P.N * P.D * P.C8 * P.H * P.W;

@@ -842,17 +842,27 @@ class UNet2D5_dsbn(nn.Module):
         return logits, rec
 
     # -- whole-network backward -------------------------------------------------------------
-    def _unit_bwd(self, u, r, g1, g_pool, pool_idx, pool_kd, n, ws, small, grads, need_dx, fold=None):
-        """Backward of one conv unit.  Returns the C8 gradient wrt the unit's input (or None)."""
+    def _bwdred_ok(self, u_prev, r_prev):
+        """The BatchNorm-backward sums of ``u_prev`` can be accumulated by the epilogue of the dgrad that writes its
+        activation gradient (csrc/common.cuh EpiBwdRed): Philox dropout (no injected mask), tensor-core dgrad."""
+        return (u_prev is not None and r_prev.get("mask") is None and os.environ.get("FPL_BWD_FUSE", "1") != "0"
+                and ops.is_sm100())
+
+    def _unit_bwd(self, u, r, g1, g_pool, pool_idx, pool_kd, n, ws, small, grads, need_dx, fold=None, prev=None):
+        """Backward of one conv unit.  Returns the C8 gradient wrt the unit's input (or None).
+        ``prev`` = (unit, record) of the unit whose activation is this unit's ONLY consumer-input (unit 1 of the same
+        ConvBlockND): its BatchNorm-backward reduce pass is then folded into this unit's dgrad epilogue."""
         d, h, w = r["geo"]
         c = u.cout
         st = stream_ptr()
-        red = small.f64(2 * c + 1)
         g1a = g1.args() if g1 is not None else (None, 0, 0)
         gpa = g_pool.args() if g_pool is not None else (None, 0, 0)
         common = (ptr(r["y"]), *g1a, *gpa, ptr(pool_idx), pool_kd, ptr(r["scale"]), ptr(r["shift"]), ptr(r["mean"]),
                   ptr(r["invstd"]), ptr(u.prelu.weight), r["p"], ptr(r["mask"]), r["seed"], r["offset"], ptr(r["seed_dev"]))
-        call("fpl_dsbn_act_bwd_reduce", *common, ptr(red), n, d, h, w, c, st)
+        red = r.pop("red_fused", None)
+        if red is None:
+            red = small.f64(2 * c + 1)
+            call("fpl_dsbn_act_bwd_reduce", *common, ptr(red), n, d, h, w, c, st)
         dy = ws.c8("dY:" + u.name, n, d, c, h, w)       # per unit: the side-stream wgrad may still be reading it
         bn = r["bn"]
         call("fpl_dsbn_act_bwd_apply_fin", *common, ptr(red), r["training"], ptr(dy), n, d, h, w, c, st,
@@ -894,13 +904,27 @@ class UNet2D5_dsbn(nn.Module):
         if not need_dx:
             return None
         dx = ws.c8("dX:" + u.name, n, d, u.cin, h, w)
+        br = None
+        if prev is not None and self._bwdred_ok(*prev) and (self._dfold_ok(u.cout, u.cin, u.kd, d) or self._use_tc(u.cout, u.cin)):
+            up, rp = prev
+            rp["red_fused"] = small.f64(2 * up.cout + 1)
+            br = (ptr(rp["y"]), ptr(rp["scale"]), ptr(rp["shift"]), ptr(rp["mean"]), ptr(rp["invstd"]), ptr(up.prelu.weight),
+                  rp["p"], rp["seed"], rp["offset"], ptr(rp["seed_dev"]), ptr(rp["red_fused"]))
         if self._dfold_ok(u.cout, u.cin, u.kd, d):
-            call("fpl_conv3d_tc_dfold", ptr(dy), c // 8, 0, ptr(self._dfold_image(u.conv, True)), None, ptr(dx),
-                 u.cin // 8, 0, None, n, d, h, w, c, u.cin, st)
+            if br is not None:
+                call("fpl_conv3d_tc_dfold_bwdred", ptr(dy), c // 8, 0, ptr(self._dfold_image(u.conv, True)), ptr(dx),
+                     u.cin // 8, 0, n, d, h, w, c, u.cin, *br, st)
+            else:
+                call("fpl_conv3d_tc_dfold", ptr(dy), c // 8, 0, ptr(self._dfold_image(u.conv, True)), None, ptr(dx),
+                     u.cin // 8, 0, None, n, d, h, w, c, u.cin, st)
         elif self._use_tc(u.cout, u.cin):
             img = self._weight_image(u.conv, u.kd, True, ws)
-            call("fpl_conv3d_tc", ptr(dy), c // 8, 0, ptr(img), None, ptr(dx), u.cin // 8, 0, None,
-                 n, d, h, w, c, u.cin, u.kd, st)
+            if br is not None:
+                call("fpl_conv3d_tc_bwdred", ptr(dy), c // 8, 0, ptr(img), ptr(dx), u.cin // 8, 0, n, d, h, w, c, u.cin,
+                     u.kd, *br, st)
+            else:
+                call("fpl_conv3d_tc", ptr(dy), c // 8, 0, ptr(img), None, ptr(dx), u.cin // 8, 0, None,
+                     n, d, h, w, c, u.cin, u.kd, st)
         else:
             call("fpl_conv3d_direct", ptr(dy), c // 8, 0, ptr(u.conv.weight), None, ptr(dx), u.cin // 8, 0, None,
                  n, d, h, w, c, u.cin, u.kd, 1, 0, st)
@@ -1047,9 +1071,9 @@ class UNet2D5_dsbn(nn.Module):
             u1, u2 = self._up_units[k]
             up = ups[k]
             c, c_low = ft[lvl], ft[lvl + 1]
-            g = self._unit_bwd(u2, rec[u2.name], g, None, None, 0, n, ws, small, grads, True, fold)
-            # dgrad of unit 1 produces the gradient of the whole concat buffer; keep it alive per level
             r1 = rec[u1.name]
+            g = self._unit_bwd(u2, rec[u2.name], g, None, None, 0, n, ws, small, grads, True, fold, prev=(u1, r1))
+            # dgrad of unit 1 produces the gradient of the whole concat buffer; keep it alive per level
             dcat = self._unit_bwd(u1, r1, g, None, None, 0, n, ws, small, grads, True, fold)
             skip_grads[lvl] = C8(dcat.buf, 0, c)
             trans = up.trans3d if up.dim == 3 else up.trans2d
@@ -1097,12 +1121,13 @@ class UNet2D5_dsbn(nn.Module):
         g_pool = None
         for i in (4, 3, 2, 1, 0):
             u1, u2 = self._down_units[i]
+            r1 = rec[u1.name]
             if i == 4:
-                g = self._unit_bwd(u2, rec[u2.name], g, None, None, 0, n, ws, small, grads, True, fold)
+                g = self._unit_bwd(u2, rec[u2.name], g, None, None, 0, n, ws, small, grads, True, fold, prev=(u1, r1))
             else:
                 idx, pool_kd = rec["idx%d" % i]
-                g = self._unit_bwd(u2, rec[u2.name], skip_grads[i], g_pool, idx, pool_kd, n, ws, small, grads, True, fold)
-            r1 = rec[u1.name]
+                g = self._unit_bwd(u2, rec[u2.name], skip_grads[i], g_pool, idx, pool_kd, n, ws, small, grads, True, fold,
+                                   prev=(u1, r1))
             r1["x_img"] = rec["x"]
             if i > 0:
                 g_pool = self._unit_bwd(u1, r1, g, None, None, 0, n, ws, small, grads, True, fold)
