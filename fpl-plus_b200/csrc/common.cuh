@@ -212,20 +212,16 @@ struct EpiBwdRed {
 };
 
 // v[0..15]: fp32 gradient of one voxel wrt 16 consecutive channels (the values the caller stores as bf16); v[16..31] scratch.
-// y0 / y1: the voxel's two 16-byte groups of y_k.  Afterwards lane L of the warp holds in acc the warp's sum of dz for
-// channel L (L < 16) or of dz*y for channel L - 16 (L >= 16); dsl accumulates this thread's z*g over z <= 0.
-__device__ __forceinline__ void epi_bwdred16(float (&v)[32], bool valid, const bf16x8* y0, const bf16x8* y1, const float* sc,
+// ya / yb: the voxel's two 16-byte groups of y_k, loaded by the caller (PREFETCHED several steps ahead: the 128 epilogue
+// threads of a CTA cannot hide DRAM latency with loads issued at the point of use).  Afterwards lane L of the warp holds
+// in acc the warp's sum of dz for channel L (L < 16) or of dz*y for channel L - 16 (L >= 16); dsl accumulates this
+// thread's z*g over z <= 0.
+__device__ __forceinline__ void epi_bwdred16(float (&v)[32], bool valid, const int4& ya, const int4& yb, const float* sc,
                                              const float* sh, float slope, bool drop, uint32_t keep0, uint32_t keep1,
                                              float keep_scale, int lane, float& acc, float& dsl) {
     float yf[16];
-    if (valid) {
-        const bf16x8 a = ldg_bf16x8(y0), b = ldg_bf16x8(y1);
-        bf16x8_to_float(a, yf);
-        bf16x8_to_float(b, yf + 8);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) yf[i] = 0.0f;
-    }
+    bf16x8_to_float(*reinterpret_cast<const bf16x8*>(&ya), yf);
+    bf16x8_to_float(*reinterpret_cast<const bf16x8*>(&yb), yf + 8);
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         float g = __bfloat162float(__float2bfloat16_rn(v[i]));          // the stored (rounded) gradient, as the apply pass reads it
@@ -240,6 +236,22 @@ __device__ __forceinline__ void epi_bwdred16(float (&v)[32], bool valid, const b
     warp_transpose_sum32(v, lane);
     acc += v[0];
 }
+
+// the two y_k groups of one (voxel, 16-channel chunk) step; zeros outside the volume
+struct BrPre {
+    int4 a, b;
+};
+__device__ __forceinline__ BrPre epi_bwdred_load(const bf16x8* y, int64_t vec0, int64_t HW, bool valid) {
+    BrPre r;
+    r.a = make_int4(0, 0, 0, 0);
+    r.b = make_int4(0, 0, 0, 0);
+    if (valid) {
+        r.a = ld_stream16(y + vec0);
+        r.b = ld_stream16(y + vec0 + HW);
+    }
+    return r;
+}
+constexpr int kBrPrefetch = 4;      // steps of look-ahead (a step = one 16-channel chunk of one 128-voxel tile / plane)
 
 // end of a slice: lane L < 16 owns sum dz of channel ch0 + L, lane L + 16 the matching sum dz*y
 __device__ __forceinline__ void epi_bwdred_flush(const EpiBwdRed& R, int C, int ch0, float acc, int lane) {

@@ -266,11 +266,20 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
                 }
                 cur_slice = c.slice;
             }
-            mbar_wait(&tmem_full[acc], acc_phase);
-            tc_fence_after();
             const int h = c.h0 + hl, w = c.w0 + wl;
             const bool valid = h < P.H && w < P.W;
             const int64_t HW = (int64_t)P.H * P.W;
+            // fused BatchNorm-backward sums: the tile's y_k chunks are requested BEFORE waiting for the tile's MMAs and
+            // kept kBrPrefetch steps ahead in a rotating register window
+            BrPre br_pre[kBrPrefetch];
+            const int64_t br_vec_tile = (((int64_t)c.n * P.D + c.d) * (P.cout >> 3) + (c.slice * P.nb) / 8) * HW + (int64_t)h * P.W + w;
+            if (fuse_br) {
+#pragma unroll
+                for (int q = 0; q < kBrPrefetch; ++q)
+                    br_pre[q] = epi_bwdred_load(P.br.y, br_vec_tile + (int64_t)(2 * q) * HW, HW, valid && q < nchunk16);
+            }
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
             const int64_t out_base = (((int64_t)c.n * P.D + c.d) * P.y_c8tot + P.y_c8off + (c.slice * P.nb) / 8) * HW +
                                      (int64_t)h * P.W + w;
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P.nb);
@@ -337,15 +346,19 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
                         warp_transpose_sum32(v, lane);
                         run[k] += v[0];
                     } else if (fuse_br) {
-                        const int C8 = P.cout >> 3;
-                        const int64_t vec0 = (((int64_t)c.n * P.D + c.d) * C8 + (c.slice * P.nb + c0) / 8) * HW + (int64_t)h * P.W + w;
+                        const int64_t vec0 = br_vec_tile + (int64_t)(2 * k) * HW;
                         uint32_t keep0 = 0xffu, keep1 = 0xffu;
                         if (br_drop && valid) {
                             keep0 = dropout_keep8(br_seed, P.br.offset, (uint64_t)vec0, P.br.drop_p);
                             keep1 = dropout_keep8(br_seed, P.br.offset, (uint64_t)(vec0 + HW), P.br.drop_p);
                         }
-                        epi_bwdred16(v, valid, P.br.y + vec0, P.br.y + vec0 + HW, br_sc + c.slice * P.nb + c0,
-                                     br_sh + c.slice * P.nb + c0, br_slope, br_drop, keep0, keep1, br_keep_scale, lane, run[k], br_dsl);
+                        const BrPre cur = br_pre[0];
+#pragma unroll
+                        for (int q = 0; q + 1 < kBrPrefetch; ++q) br_pre[q] = br_pre[q + 1];
+                        br_pre[kBrPrefetch - 1] = epi_bwdred_load(P.br.y, br_vec_tile + (int64_t)(2 * (k + kBrPrefetch)) * HW, HW,
+                                                                  valid && k + kBrPrefetch < nchunk16);
+                        epi_bwdred16(v, valid, cur.a, cur.b, br_sc + c.slice * P.nb + c0, br_sh + c.slice * P.nb + c0,
+                                     br_slope, br_drop, keep0, keep1, br_keep_scale, lane, run[k], br_dsl);
                     }
                 }
             }

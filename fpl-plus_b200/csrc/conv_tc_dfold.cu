@@ -242,6 +242,21 @@ __global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid
             const int h = c.h0 + hl, w = c.w0 + wl;
             const bool valid = h < P.H && w < P.W;
             const int64_t HW = (int64_t)P.H * P.W;
+            // fused BatchNorm-backward sums: y_k of step s = (plane p, chunk k), s = p * nchunk16 + k, is loaded
+            // kBrPrefetch steps ahead into a rotating register window
+            BrPre br_pre[kBrPrefetch];
+            const int br_steps = c.dcount * nchunk16;
+            const int64_t br_vec_item = ((int64_t)c.n * P.D + c.d0) * (P.cout >> 3) * HW + (int64_t)(c.slice * P.nb / 8) * HW + (int64_t)h * P.W + w;
+            auto br_vec = [&](int s_) -> int64_t {
+                const int p_ = s_ / nchunk16, k_ = s_ - p_ * nchunk16;
+                return br_vec_item + ((int64_t)p_ * (P.cout >> 3) + 2 * k_) * HW;
+            };
+            if (fuse_br) {
+#pragma unroll
+                for (int q = 0; q < kBrPrefetch; ++q)
+                    br_pre[q] = epi_bwdred_load(P.br.y, br_vec(q), HW, valid && q < br_steps);
+            }
+            int br_step = 0;
             for (int p = 0; p < c.dcount; ++p) {
                 mbar_wait(&done_bar[p], item_phase);
                 tc_fence_after();
@@ -294,15 +309,20 @@ __global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid
                             warp_transpose_sum32(v, lane);
                             run[k] += v[0];
                         } else if (fuse_br) {
-                            const int C8 = P.cout >> 3;
-                            const int64_t vec0 = (((int64_t)c.n * P.D + c.d0 + p) * C8 + (c.slice * P.nb + c0) / 8) * HW + (int64_t)h * P.W + w;
+                            const int64_t vec0 = br_vec(br_step);
                             uint32_t keep0 = 0xffu, keep1 = 0xffu;
                             if (br_drop && valid) {
                                 keep0 = dropout_keep8(br_seed, P.br.offset, (uint64_t)vec0, P.br.drop_p);
                                 keep1 = dropout_keep8(br_seed, P.br.offset, (uint64_t)(vec0 + HW), P.br.drop_p);
                             }
-                            epi_bwdred16(v, valid, P.br.y + vec0, P.br.y + vec0 + HW, br_sc + c.slice * P.nb + c0,
-                                         br_sh + c.slice * P.nb + c0, br_slope, br_drop, keep0, keep1, br_keep_scale, lane, run[k], br_dsl);
+                            const BrPre cur = br_pre[0];
+#pragma unroll
+                            for (int q = 0; q + 1 < kBrPrefetch; ++q) br_pre[q] = br_pre[q + 1];
+                            br_pre[kBrPrefetch - 1] = epi_bwdred_load(P.br.y, br_vec(br_step + kBrPrefetch), HW,
+                                                                      valid && br_step + kBrPrefetch < br_steps);
+                            ++br_step;
+                            epi_bwdred16(v, valid, cur.a, cur.b, br_sc + c.slice * P.nb + c0, br_sh + c.slice * P.nb + c0,
+                                         br_slope, br_drop, keep0, keep1, br_keep_scale, lane, run[k], br_dsl);
                         }
                     }
                 }
