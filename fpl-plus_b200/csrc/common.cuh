@@ -237,6 +237,28 @@ __device__ __forceinline__ void epi_bwdred16(float (&v)[32], bool valid, const i
     acc += v[0];
 }
 
+// Per-thread form: acc32[0..15] += dz, acc32[16..31] += dz*y of THIS thread's voxel; the caller transposes acc32 across
+// the warp (warp_transpose_sum32) once, after its last step.
+__device__ __forceinline__ void epi_bwdred16_acc(const float (&v)[32], bool valid, const int4& ya, const int4& yb, const float* sc,
+                                                 const float* sh, float slope, bool drop, uint32_t keep0, uint32_t keep1,
+                                                 float keep_scale, float (&acc32)[32], float& dsl) {
+    if (!valid) return;
+    float yf[16];
+    bf16x8_to_float(*reinterpret_cast<const bf16x8*>(&ya), yf);
+    bf16x8_to_float(*reinterpret_cast<const bf16x8*>(&yb), yf + 8);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        float g = __bfloat162float(__float2bfloat16_rn(v[i]));
+        if (drop) g = (((i < 8 ? keep0 >> i : keep1 >> (i - 8)) & 1u) != 0u) ? g * keep_scale : 0.0f;
+        const float z = fmaf(yf[i], sc[i], sh[i]);
+        const bool pos = z > 0.0f;
+        const float dz = pos ? g : g * slope;
+        if (!pos) dsl = fmaf(z, g, dsl);
+        acc32[i] += dz;
+        acc32[16 + i] = fmaf(dz, yf[i], acc32[16 + i]);
+    }
+}
+
 // the two y_k groups of one (voxel, 16-channel chunk) step; zeros outside the volume
 struct BrPre {
     int4 a, b;

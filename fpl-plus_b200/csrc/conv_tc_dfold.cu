@@ -66,7 +66,13 @@ __device__ __forceinline__ DfItem decode_item(const DfParams& P, int t) {
     return c;
 }
 
-__global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid_constant__ CUtensorMap xmap, DfParams P) {
+// NCH = nb / 16.  For NCH == 1 (Cout 16: the full-resolution layers, where a CTA walks ~60 planes per launch; 64
+// accumulator registers for Cout 32 would cost the second resident CTA) the per-channel sums of the epilogue (forward BatchNorm statistics or the fused BatchNorm-backward sums) are
+// accumulated PER THREAD (32 registers per chunk) and transposed across the warp once per CTA; the transposing
+// butterfly per plane (31 shuffles + ~90 ALU instructions on warps that have an SM sub-partition to themselves) made
+// the epilogue the pacing stage of the 16 -> 16 layers (52 us without statistics, 65 us with; tools/epi_probe.py).
+template <int NCH>
+__global__ void __launch_bounds__(kThreadsD, 2) conv3d_tc_dfold_kernel(const __grid_constant__ CUtensorMap xmap, DfParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     // [resident weights of this CTA's slice][A stage ring][barriers][bias]
@@ -204,12 +210,18 @@ __global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid
         const int row = quarter * 32 + lane;
         const int hl = row / kTileW, wl = row % kTileW;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        constexpr int kMaxChunks = 4;                                   // nb <= 64
+        constexpr int kMaxChunks = NCH;                                 // nb = 16 * NCH <= 64
+        constexpr bool kThreadAcc = NCH <= 2;
         float run[kMaxChunks];
+        float tacc[kThreadAcc ? NCH : 1][32];
 #pragma unroll
         for (int k = 0; k < kMaxChunks; ++k) run[k] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < (kThreadAcc ? NCH : 1); ++k)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) tacc[k][i] = 0.0f;
         const bool want_stats = P.stats != nullptr;
-        const int nchunk16 = P.nb / 16;
+        constexpr int nchunk16 = NCH;
         // zero every accumulator once, then hand them to the MMA warp
         for (int col = 0; col < P.dc * P.nb; col += 16) tmem_st_zero16(lane_base + (uint32_t)col);
         tmem_st_wait();
@@ -232,6 +244,12 @@ __global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid
 #pragma unroll
                     for (int k = 0; k < kMaxChunks; ++k)
                         if (k < nchunk16) {
+                            if (kThreadAcc) {
+                                warp_transpose_sum32(tacc[k], lane);
+                                run[k] += tacc[k][0];
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) tacc[k][i] = 0.0f;
+                            }
                             if (want_stats) atomicAdd(P.stats + (lane >> 4) * P.cout + cur_slice * P.nb + k * 16 + (lane & 15), (double)run[k]);
                             else epi_bwdred_flush(P.br, P.cout, cur_slice * P.nb + k * 16, run[k], lane);
                             run[k] = 0.0f;
@@ -242,21 +260,7 @@ __global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid
             const int h = c.h0 + hl, w = c.w0 + wl;
             const bool valid = h < P.H && w < P.W;
             const int64_t HW = (int64_t)P.H * P.W;
-            // fused BatchNorm-backward sums: y_k of step s = (plane p, chunk k), s = p * nchunk16 + k, is loaded
-            // kBrPrefetch steps ahead into a rotating register window
-            BrPre br_pre[kBrPrefetch];
-            const int br_steps = c.dcount * nchunk16;
             const int64_t br_vec_item = ((int64_t)c.n * P.D + c.d0) * (P.cout >> 3) * HW + (int64_t)(c.slice * P.nb / 8) * HW + (int64_t)h * P.W + w;
-            auto br_vec = [&](int s_) -> int64_t {
-                const int p_ = s_ / nchunk16, k_ = s_ - p_ * nchunk16;
-                return br_vec_item + ((int64_t)p_ * (P.cout >> 3) + 2 * k_) * HW;
-            };
-            if (fuse_br) {
-#pragma unroll
-                for (int q = 0; q < kBrPrefetch; ++q)
-                    br_pre[q] = epi_bwdred_load(P.br.y, br_vec(q), HW, valid && q < br_steps);
-            }
-            int br_step = 0;
             for (int p = 0; p < c.dcount; ++p) {
                 mbar_wait(&done_bar[p], item_phase);
                 tc_fence_after();
@@ -301,28 +305,36 @@ __global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid
                             st_bf16x8(P.y + out_base + (int64_t)(c0 / 8 + 1) * HW, v + 8);
                         }
                         if (want_stats) {
+                            if (kThreadAcc) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                v[i] = valid ? v[i] : 0.0f;
-                                v[16 + i] = v[i] * v[i];
+                                for (int i = 0; i < 16; ++i) {
+                                    const float xv = valid ? v[i] : 0.0f;
+                                    tacc[k][i] += xv;
+                                    tacc[k][16 + i] = fmaf(xv, xv, tacc[k][16 + i]);
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) {
+                                    v[i] = valid ? v[i] : 0.0f;
+                                    v[16 + i] = v[i] * v[i];
+                                }
+                                warp_transpose_sum32(v, lane);
+                                run[k] += v[0];
                             }
-                            warp_transpose_sum32(v, lane);
-                            run[k] += v[0];
                         } else if (fuse_br) {
-                            const int64_t vec0 = br_vec(br_step);
+                            const int64_t vec0 = br_vec_item + ((int64_t)p * (P.cout >> 3) + 2 * k) * HW;
                             uint32_t keep0 = 0xffu, keep1 = 0xffu;
                             if (br_drop && valid) {
                                 keep0 = dropout_keep8(br_seed, P.br.offset, (uint64_t)vec0, P.br.drop_p);
                                 keep1 = dropout_keep8(br_seed, P.br.offset, (uint64_t)(vec0 + HW), P.br.drop_p);
                             }
-                            const BrPre cur = br_pre[0];
-#pragma unroll
-                            for (int q = 0; q + 1 < kBrPrefetch; ++q) br_pre[q] = br_pre[q + 1];
-                            br_pre[kBrPrefetch - 1] = epi_bwdred_load(P.br.y, br_vec(br_step + kBrPrefetch), HW,
-                                                                      valid && br_step + kBrPrefetch < br_steps);
-                            ++br_step;
-                            epi_bwdred16(v, valid, cur.a, cur.b, br_sc + c.slice * P.nb + c0, br_sh + c.slice * P.nb + c0,
-                                         br_slope, br_drop, keep0, keep1, br_keep_scale, lane, run[k], br_dsl);
+                            const BrPre cur = epi_bwdred_load(P.br.y, vec0, HW, valid);
+                            if (kThreadAcc)
+                                epi_bwdred16_acc(v, valid, cur.a, cur.b, br_sc + c.slice * P.nb + c0, br_sh + c.slice * P.nb + c0,
+                                                 br_slope, br_drop, keep0, keep1, br_keep_scale, tacc[k], br_dsl);
+                            else
+                                epi_bwdred16(v, valid, cur.a, cur.b, br_sc + c.slice * P.nb + c0, br_sh + c.slice * P.nb + c0,
+                                             br_slope, br_drop, keep0, keep1, br_keep_scale, lane, run[k], br_dsl);
                         }
                     }
                 }
@@ -332,6 +344,13 @@ __global__ void __launch_bounds__(kThreadsD) conv3d_tc_dfold_kernel(const __grid
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_free);
             item_phase ^= 1;
+        }
+        if (kThreadAcc && cur_slice >= 0) {
+#pragma unroll
+            for (int k = 0; k < kMaxChunks; ++k) {
+                warp_transpose_sum32(tacc[k], lane);
+                run[k] += tacc[k][0];
+            }
         }
         if (want_stats && cur_slice >= 0) {
 #pragma unroll
@@ -537,10 +556,18 @@ static int dfold_launch(const void* x, int x_c8tot, int x_c8off, const void* ima
     P.taps = taps; P.a_ksteps = cin_a / 16;
     if (br != nullptr) P.br = *br; else { P.br.y = nullptr; P.br.scale = P.br.shift = P.br.mean = P.br.invstd = P.br.slope = nullptr; P.br.drop_p = 0.0f; P.br.seed = P.br.offset = 0; P.br.seed_dev = nullptr; P.br.red = nullptr; }
     if (act != nullptr) P.act = *act; else { P.act.scale = nullptr; P.act.shift = nullptr; P.act.slope = nullptr; P.act.drop_p = 0.0f; P.act.seed = P.act.offset = 0; P.act.seed_dev = nullptr; }
-    FPL_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_dfold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
     int grid = FPL_NUM_SMS * c.ctas_per_sm;
     if (grid > P.total_items) grid = P.total_items;
-    fpl_launch(conv3d_tc_dfold_kernel, grid, kThreadsD, c.smem_bytes, (cudaStream_t)stream, xmap, P);
+    if (c.nb == 16) {
+        FPL_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_dfold_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
+        fpl_launch(conv3d_tc_dfold_kernel<1>, grid, kThreadsD, c.smem_bytes, (cudaStream_t)stream, xmap, P);
+    } else if (c.nb == 32) {
+        FPL_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_dfold_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
+        fpl_launch(conv3d_tc_dfold_kernel<2>, grid, kThreadsD, c.smem_bytes, (cudaStream_t)stream, xmap, P);
+    } else {
+        FPL_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_dfold_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
+        fpl_launch(conv3d_tc_dfold_kernel<4>, grid, kThreadsD, c.smem_bytes, (cudaStream_t)stream, xmap, P);
+    }
     FPL_LAUNCH_CHECK();
     return 0;
 }
