@@ -51,32 +51,19 @@ extern unsigned long long g_fpl_launches;
 extern int g_fpl_pdl;     // 1 (default) / 0: FPL_PDL environment variable, read once (api.cu)
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t fpl_launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                                      unsigned cluster_x, Args&&... args) {
+inline cudaError_t fpl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = g_fpl_pdl;
-    cfg.numAttrs = 1;
-    if (cluster_x > 1) {                       // thread-block cluster of cluster_x CTAs along x (distributed shared memory)
-        attr[1].id = cudaLaunchAttributeClusterDimension;
-        attr[1].val.clusterDim.x = cluster_x;
-        attr[1].val.clusterDim.y = 1;
-        attr[1].val.clusterDim.z = 1;
-        cfg.numAttrs = 2;
-    }
     cfg.attrs = attr;
+    cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-
-template <typename... KArgs, typename... Args>
-inline cudaError_t fpl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                              Args&&... args) {
-    return fpl_launch_cluster(kernel, grid, block, smem, stream, 1u, static_cast<Args&&>(args)...);
 }
 
 // ---- 16-byte bf16x8 vectors ----------------------------------------------------------

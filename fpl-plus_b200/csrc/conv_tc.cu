@@ -78,8 +78,6 @@ struct TcParams {
     int x_c8tot, x_c8off;
     int nb, kc, nslices, nchunks, a_bytes, b_bytes, stages, tmem_cols;   // nb / nslices / b_bytes: of THIS launch (after nsub)
     int nsub, nb_img, b_bytes_img;   // N split of a staged image slice: nb = nb_img / nsub (few-tile layers: more, smaller CTAs)
-    int ksplit;           // > 1: split-K over the cin chunks across a cluster of ksplit CTAs, one tile per cluster (see kernel)
-    int recv_off;         // byte offset of the split-K receive buffer (it ALIASES the stage ring, see the kernel)
     int tiles_h, tiles_w, total_tiles;
     int dbg_swap_lbo_sbo;
     float* logits;        // head mode: fp32 NCDHW output of the first `classes` channels instead of bf16 C8-planar
@@ -104,15 +102,6 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int t) {
     return c;
 }
 
-// Split-K mode (P.ksplit > 1; levels 3-4 of the U-Net: <= 64 voxel tiles of 128 rows, K = 27 * Cin up to 6912): a tile is
-// computed by a CLUSTER of ksplit CTAs, CTA r taking the cin chunks [r, r+1) * nchunks / ksplit (all depth taps), so the
-// ~430 dependent MMAs of a tile become ~54 on each of 4-8 SMs.  Reduction through distributed shared memory as a
-// reduce-scatter: the 16-channel accumulator chunks are dealt out to the ksplit CTAs; every CTA stores the chunks it
-// does not own into the owner's receive buffer (st.shared::cluster), then every CTA runs the ordinary epilogue (bias /
-// BatchNorm statistics / activation / bf16 store) on the chunks it owns, summed with the ksplit-1 partials it received.
-// The receive buffer aliases the stage ring, so two cluster barriers bracket the exchange: the first completes when
-// every CTA of the cluster has seen its MMAs retire (nobody reads a ring any more), the second when all partials have
-// landed.  No scratch tensor, no second kernel, fixed summation order (deterministic).
 __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap,
                                                                  const __grid_constant__ CUtensorMap imap, TcParams P) {
     extern __shared__ uint8_t smem_raw[];
@@ -153,20 +142,14 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // split-K: this CTA's tile and cin-chunk range (plain mode: all chunks, persistent tile loop)
-    const int ksplit = P.ksplit;
-    const int krank = ksplit > 1 ? (int)cluster_ctarank() : 0;
-    const int tile_first = ksplit > 1 ? (int)blockIdx.x / ksplit : (int)blockIdx.x;
-    const int tile_step = ksplit > 1 ? P.total_tiles : (int)gridDim.x;          // split mode: exactly one tile per CTA
-    const int q_begin = (krank * P.nchunks) / ksplit, q_end = ((krank + 1) * P.nchunks) / ksplit;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int t = tile_first; t < P.total_tiles; t += tile_step) {
+            for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
                 TileCoord c = decode_tile(P, t);
-                for (int q = q_begin; q < q_end; ++q) {
+                for (int q = 0; q < P.nchunks; ++q) {
                     for (int kdi = 0; kdi < P.kd; ++kdi) {
                         int dz = c.d + kdi - pad_d;
                         if (dz < 0 || dz >= P.D) continue;
@@ -191,8 +174,6 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
                 }
             }
         }
-        __syncwarp();
-        if (ksplit > 1) { cluster_sync_all(); cluster_sync_all(); }   // every thread of the cluster takes part in both barriers
     } else if (warp == 1) {
         // ===================== MMA issuer: the whole warp runs the loop (uniform), one lane issues =====================
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.nb >> 3) << 17) | (8u << 24);
@@ -209,13 +190,13 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
         const bool leader = elect_one();
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int t = tile_first; t < P.total_tiles; t += tile_step) {
+        for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
             TileCoord c = decode_tile(P, t);
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.nb);
             uint32_t accumulate = 0;
-            for (int q = q_begin; q < q_end; ++q) {
+            for (int q = 0; q < P.nchunks; ++q) {
                 for (int kdi = 0; kdi < P.kd; ++kdi) {
                     int dz = c.d + kdi - pad_d;
                     if (dz < 0 || dz >= P.D) continue;
@@ -244,7 +225,6 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         FPL_PDL_TRIGGER();   // this CTA has issued its last tile: the next kernel of the stream may be scheduled as SMs drain
-        if (ksplit > 1) { cluster_sync_all(); cluster_sync_all(); }
     } else {
         // ===================== epilogue (warps 2..5) =====================
         // thread = one output voxel (TMEM lane); per 16-channel chunk: +bias, one 2 x 128-bit bf16 store,
@@ -271,10 +251,7 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
         const float act_slope = fuse_act ? __ldg(P.act.slope) : 0.0f;
         const float act_keep_scale = (fuse_act && P.act.drop_p > 0.0f) ? 1.0f / (1.0f - P.act.drop_p) : 1.0f;
         const uint64_t act_seed = fuse_act ? P.act.seed + (P.act.seed_dev != nullptr ? (uint64_t)__ldg(P.act.seed_dev) : 0ull) : 0ull;
-        // split-K: chunk k of the tile is finished by CTA k / cpo of the cluster
-        const int cpo = ksplit > 1 ? nchunk16 / ksplit : nchunk16;
-        float* recv = reinterpret_cast<float*>(smem + P.recv_off);       // [src rank][owned chunk][128 rows][16]
-        for (int t = tile_first; t < P.total_tiles; t += tile_step) {
+        for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
             TileCoord c = decode_tile(P, t);
             if ((want_stats || fuse_br) && c.slice != cur_slice) {
                 if (cur_slice >= 0) {
@@ -292,54 +269,27 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
             const int h = c.h0 + hl, w = c.w0 + wl;
             const bool valid = h < P.H && w < P.W;
             const int64_t HW = (int64_t)P.H * P.W;
+            // fused BatchNorm-backward sums: the tile's y_k chunks are requested BEFORE waiting for the tile's MMAs and
+            // kept kBrPrefetch steps ahead in a rotating register window
+            BrPre br_pre[kBrPrefetch];
             const int64_t br_vec_tile = (((int64_t)c.n * P.D + c.d) * (P.cout >> 3) + (c.slice * P.nb) / 8) * HW + (int64_t)h * P.W + w;
+            if (fuse_br) {
+#pragma unroll
+                for (int q = 0; q < kBrPrefetch; ++q)
+                    br_pre[q] = epi_bwdred_load(P.br.y, br_vec_tile + (int64_t)(2 * q) * HW, HW, valid && q < nchunk16);
+            }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            if (ksplit > 1) {
-                cluster_sync_all();          // all MMAs of all CTAs of the cluster have retired: the rings are free
-                // reduce-scatter, send half: partial accumulators of the chunks other CTAs own -> their receive buffers
-                const uint32_t t_row0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P.nb);
-                const uint32_t recv_u = smem_u32(recv);
-#pragma unroll
-                for (int k = 0; k < kMaxChunks; ++k) {
-                    if (k < nchunk16 && k / cpo != krank) {
-                        uint32_t r[16];
-                        tmem_ld16(t_row0 + (uint32_t)(k * 16), r);
-                        tmem_ld_wait();
-                        const uint32_t dst = dsmem_addr(recv_u + (uint32_t)((((krank * cpo) + (k % cpo)) * 128 + row) * 64), (uint32_t)(k / cpo));
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            dsmem_st_f4(dst + 16u * i, __uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                        __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-                    }
-                }
-                cluster_sync_all();
-            }
             const int64_t out_base = (((int64_t)c.n * P.D + c.d) * P.y_c8tot + P.y_c8off + (c.slice * P.nb) / 8) * HW +
                                      (int64_t)h * P.W + w;
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P.nb);
 #pragma unroll
             for (int k = 0; k < kMaxChunks; ++k) {
-                if (k < nchunk16 && (ksplit == 1 || k / cpo == krank)) {
+                if (k < nchunk16) {
                     const int c0 = k * 16;
                     uint32_t r[16];
                     tmem_ld16(t_row + (uint32_t)c0, r);
                     tmem_ld_wait();
-                    if (ksplit > 1) {
-                        // receive half: + the partials of the other ksplit-1 CTAs, in rank order (deterministic)
-                        for (int src = 0; src < ksplit; ++src) {
-                            if (src == krank) continue;
-                            const float4* pr = reinterpret_cast<const float4*>(recv + (((src * cpo) + (k % cpo)) * 128 + row) * 16);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float4 q4 = pr[i];
-                                r[4 * i + 0] = __float_as_uint(__uint_as_float(r[4 * i + 0]) + q4.x);
-                                r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + q4.y);
-                                r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + q4.z);
-                                r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + q4.w);
-                            }
-                        }
-                    }
                     float v[32];
                     const float4* b4 = reinterpret_cast<const float4*>(bias_sm + c.slice * P.nb + c0);
                     if (!fuse_act) {
@@ -402,7 +352,11 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
                             keep0 = dropout_keep8(br_seed, P.br.offset, (uint64_t)vec0, P.br.drop_p);
                             keep1 = dropout_keep8(br_seed, P.br.offset, (uint64_t)(vec0 + HW), P.br.drop_p);
                         }
-                        const BrPre cur = epi_bwdred_load(P.br.y, vec0, HW, valid);
+                        const BrPre cur = br_pre[0];
+#pragma unroll
+                        for (int q = 0; q + 1 < kBrPrefetch; ++q) br_pre[q] = br_pre[q + 1];
+                        br_pre[kBrPrefetch - 1] = epi_bwdred_load(P.br.y, br_vec_tile + (int64_t)(2 * (k + kBrPrefetch)) * HW, HW,
+                                                                  valid && k + kBrPrefetch < nchunk16);
                         epi_bwdred16(v, valid, cur.a, cur.b, br_sc + c.slice * P.nb + c0, br_sh + c.slice * P.nb + c0,
                                      br_slope, br_drop, keep0, keep1, br_keep_scale, lane, run[k], br_dsl);
                     }
@@ -560,13 +514,12 @@ extern "C" int fpl_conv3d_prep_weight_batch(int count, const float* const* h_w, 
     return 0;
 }
 
-static int g_dbg_swap = 0, g_tc_allow_nsub = 1, g_tc_allow_ksplit = 1;
+static int g_dbg_swap = 0, g_tc_allow_nsub = 1;
 void fpl_wgrad_debug_set(int key, long long value);
 void fpl_dsbn_debug_set(int key, long long value);
 extern "C" void fpl_debug_set(int key, long long value) {
     if (key == 0) g_dbg_swap = (int)value;
     if (key == 1) g_tc_allow_nsub = (int)value;
-    if (key == 2) g_tc_allow_ksplit = (int)value;
     if (key >= 10 && key < 30) fpl_wgrad_debug_set(key, value);
     if (key >= 30 && key < 40) fpl_dsbn_debug_set(key, value);
 }
@@ -602,19 +555,9 @@ static int conv3d_tc_launch(const void* x, int x_c8tot, int x_c8off, const void*
     // few voxel tiles (levels 3-4): split the N of a staged slice over up to 4 CTAs so that the ~430 serial MMAs of a tile
     // get shorter and more SMs work; the image layout stays that of nb_img
     P.nsub = 1; P.nb_img = c.nb; P.b_bytes_img = c.b_bytes;
-    // few voxel tiles and a long K loop (levels 3-4): split K over a cluster of up to 8 CTAs with a DSMEM reduce-scatter
-    P.ksplit = 1; P.recv_off = 0;
     {
         const int64_t mn = (int64_t)P.tiles_h * P.tiles_w * d * n * c.nslices;
-        int ks = 8;
-        while (ks > 1 && !(c.nchunks % ks == 0 && (c.nb / 16) % ks == 0 && mn * ks <= FPL_NUM_SMS)) ks /= 2;
-        if (g_tc_allow_ksplit && logits == nullptr && ks > 1 && c.nchunks * kd >= 6 &&
-            (int64_t)c.stages * c.stage_bytes >= (int64_t)(c.nb / 16) * 8192)
-            P.ksplit = ks;
-    }
-    {
-        const int64_t mn = (int64_t)P.tiles_h * P.tiles_w * d * n * c.nslices;
-        while (g_tc_allow_nsub && P.ksplit == 1 && logits == nullptr && P.nsub < 4 && c.nb % (P.nsub * 2 * 16) == 0 && c.nb / (P.nsub * 2) >= 32 &&
+        while (g_tc_allow_nsub && logits == nullptr && P.nsub < 4 && c.nb % (P.nsub * 2 * 16) == 0 && c.nb / (P.nsub * 2) >= 32 &&
                mn * P.nsub < 96)
             P.nsub *= 2;
     }
@@ -630,7 +573,6 @@ static int conv3d_tc_launch(const void* x, int x_c8tot, int x_c8off, const void*
     int ctas_per_sm = c.smem_bytes <= 110 * 1024 ? 2 : 1;
     int grid = FPL_NUM_SMS * ctas_per_sm;
     if (grid > P.total_tiles) grid = P.total_tiles;
-    if (P.ksplit > 1) grid = P.total_tiles * P.ksplit;         // one tile per cluster, all CTAs resident (<= 148)
     CUtensorMap imap = xmap;
     if (P.nsub > 1) {
         // 8-byte elements: nb * 16 B = nb * 2 elements (<= 256 per box dimension)
@@ -643,7 +585,7 @@ static int conv3d_tc_launch(const void* x, int x_c8tot, int x_c8off, const void*
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         FPL_REQUIRE(r == CUDA_SUCCESS, "fpl_conv3d_tc: cuTensorMapEncodeTiled (weight image) failed (%d)", (int)r);
     }
-    fpl_launch_cluster(conv3d_tc_kernel, grid, kNumThreads, c.smem_bytes, (cudaStream_t)stream, (unsigned)P.ksplit, xmap, imap, P);
+    fpl_launch(conv3d_tc_kernel, grid, kNumThreads, c.smem_bytes, (cudaStream_t)stream, xmap, imap, P);
     FPL_LAUNCH_CHECK();
     return 0;
 }

@@ -80,27 +80,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// ---- thread-block clusters: distributed shared memory + cluster barrier (split-K reduction of the deep conv levels) ----
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-// shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_smem_addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void dsmem_st_f4(uint32_t cluster_addr, float a, float b, float c, float d) {
-    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-// all threads of all CTAs of the cluster; release / acquire: remote shared-memory writes issued before are visible after
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
 // true in exactly one lane of a converged warp (the MMA issue loops run warp-uniform so that the
 // descriptors live in uniform registers; only the tcgen05 instructions themselves are predicated)
 __device__ __forceinline__ bool elect_one() {

@@ -928,44 +928,3 @@ def test_dgrad_epilogue_accumulates_the_dsbn_backward_sums(kernel, cin, cout, sh
     tol = 2e-5 * float(b.abs().max()) + 1e-6
     assert float((a - b).abs().max()) <= tol, (float((a - b).abs().max()), tol)
     assert float(b[:c_prev].abs().max()) > 0 and float(b[-1].abs()) > 0
-
-
-@pytest.mark.parametrize("cin,cout,shape,transpose", [
-    (128, 128, (4, 4, 16, 16), 0), (256, 256, (4, 2, 8, 8), 0), (256, 128, (4, 4, 16, 16), 0), (128, 256, (4, 2, 8, 8), 0),
-    (64, 128, (4, 4, 16, 16), 0), (256, 128, (4, 4, 16, 16), 1), (256, 256, (2, 2, 8, 8), 1), (128, 128, (1, 3, 20, 12), 0)])
-def test_conv3d_tc_cluster_split_k(cin, cout, shape, transpose):
-    """Round 2: levels 3-4 run split-K over a thread-block cluster (4-8 CTAs per voxel tile, DSMEM reduce-scatter).  Same
-    result as the single-CTA path up to fp32 summation order, bit-identical from run to run (fixed reduction order),
-    BatchNorm statistics included; forward and dgrad images."""
-    from fplplus_b200 import lib as L
-    n, d, h, w = shape
-    wt = bf16_round(randn(41, cout, cin, 3, 3, 3, scale=0.05))
-    ci, co = (cout, cin) if transpose else (cin, cout)        # channels of the launch (dgrad: cout -> cin)
-    x = bf16_round(randn(42, n, ci, d, h, w))
-    if transpose:
-        xx = torch.zeros(n, cin, d, h, w, requires_grad=True)
-        F.conv3d(xx, wt, None, padding=1).backward(x)
-        ref = xx.grad
-    else:
-        ref = F.conv3d(x, wt, None, padding=1)
-    xb = to_c8(x.to(DEV))
-    img = torch.empty(L.load().fpl_conv3d_weight_image_bytes(ci, co, 3) // 2, dtype=torch.bfloat16, device=DEV)
-    _call("fpl_conv3d_prep_weight", _p(wt.to(DEV)), cin, cout, 3, transpose, _p(img), _st())
-    outs, stats_all = [], []
-    try:
-        for allow in (1, 1, 0):
-            L.load().fpl_debug_set(2, allow)
-            y = torch.zeros((n, d, co // 8, h, w, 8), dtype=torch.bfloat16, device=DEV)
-            stats = torch.zeros(2 * co, dtype=torch.float64, device=DEV)
-            _call("fpl_conv3d_tc", _p(xb), ci // 8, 0, _p(img), None, _p(y), co // 8, 0, _p(stats), n, d, h, w, ci, co, 3, _st())
-            torch.cuda.synchronize()
-            outs.append(from_c8(y).cpu())
-            stats_all.append(stats.cpu())
-    finally:
-        L.load().fpl_debug_set(2, 1)
-    assert torch.equal(outs[0], outs[1])                                   # deterministic
-    assert max_rel(outs[0], ref.detach()) < 6e-3
-    assert max_rel(outs[0], outs[2]) < 5e-3 and float((outs[0] != outs[2]).float().mean()) < 0.05
-    rd = ref.detach().double()
-    np.testing.assert_allclose(stats_all[0][:co], rd.sum((0, 2, 3, 4)), rtol=1e-4, atol=2e-3)
-    np.testing.assert_allclose(stats_all[0][co:], (rd ** 2).sum((0, 2, 3, 4)), rtol=1e-4, atol=2e-3)
