@@ -845,7 +845,10 @@ class UNet2D5_dsbn(nn.Module):
     def _bwdred_ok(self, u_prev, r_prev):
         """The BatchNorm-backward sums of ``u_prev`` can be accumulated by the epilogue of the dgrad that writes its
         activation gradient (csrc/common.cuh EpiBwdRed): Philox dropout (no injected mask), tensor-core dgrad."""
-        return (u_prev is not None and r_prev.get("mask") is None and os.environ.get("FPL_BWD_FUSE", "1") != "0"
+        # default OFF: measured (tools/epi_probe.py, profiles/README.md round 2) the 128 epilogue threads of a CTA pay more
+        # for the extra y_k loads and arithmetic (+23..+50 us on the full-resolution dfold layers, +2.5..3.5 us on the deep
+        # ones) than the standalone HBM-streaming reduce costs (30 / 3..5 us); FPL_BWD_FUSE=1 enables it for A/B runs
+        return (u_prev is not None and r_prev.get("mask") is None and os.environ.get("FPL_BWD_FUSE", "0") != "0"
                 and ops.is_sm100())
 
     def _unit_bwd(self, u, r, g1, g_pool, pool_idx, pool_kd, n, ws, small, grads, need_dx, fold=None, prev=None):
