@@ -303,7 +303,10 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    nccl_ctas = 0
     if world > 1:
+        from fplplus_b200.agent import reserve_sms_for_nccl
+        nccl_ctas = reserve_sms_for_nccl()          # before the communicator exists (NCCL_MAX_CTAS) + grid budget
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -473,6 +476,7 @@ def run_ours(args):
                                       "2 classes, batch 4/domain/GPU x 1x32x128x128, source batch + pixel/image-"
                                       "weighted target batch, 0.5 Dice + 0.5 CE, Adam (BASELINE.json configs[2])",
                           "voxels_per_step_per_gpu": vox_per_step, "parallelism": "dp%d" % world,
+                          "nccl_max_ctas": nccl_ctas or None,
                           "l2": "activation working set per step >> 126 MB L2 (inputs larger than L2)",
                           "conv_gflop_per_step_per_gpu": 2 * BATCH * 179.9},
                "e2e": {"value": e2e_value, "unit": "voxels/s", "ms_per_step": ms_e2e / args.steps,

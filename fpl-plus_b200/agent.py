@@ -209,6 +209,24 @@ class GradAllReducer(object):
         self._start = None
 
 
+def reserve_sms_for_nccl(ctas=None):
+    """Data-parallel runs: cap the CTAs NCCL's all-reduce kernels may hold (NCCL_MAX_CTAS, read by NCCL when the
+    communicator is created -- call this BEFORE ``init_process_group``) and size the library's persistent kernels for the
+    remaining SMs (fpl_set_sm_budget).  Without it the all-reduce kernels that overlap backward occupy a varying number of
+    SMs and every statically tiled 148-CTA conv grid that meets them runs a second wave (wgrad +22 % at 4-8 GPUs in
+    round 1).  ``ctas`` defaults to $FPL_NCCL_CTAS or 8; 0 leaves NCCL and the grids alone."""
+    if ctas is None:
+        ctas = int(os.environ.get("FPL_NCCL_CTAS", "8"))
+    if ctas <= 0:
+        return 0
+    os.environ.setdefault("NCCL_MAX_CTAS", str(ctas))
+    os.environ.setdefault("NCCL_MIN_CTAS", str(min(ctas, 4)))
+    held = int(os.environ["NCCL_MAX_CTAS"])
+    from . import lib as _lib
+    _lib.call("fpl_set_sm_budget", 148 - held)
+    return held
+
+
 def shard_round_robin(items, rank, world):
     """Volumes are independent (agent_seg.py:881 loop): rank r takes items r, r+world, ..."""
     return [it for i, it in enumerate(items) if i % world == rank]

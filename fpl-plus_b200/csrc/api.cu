@@ -31,7 +31,18 @@ extern "C" long long fpl_launch_count(int reset) {
     return (long long)v;
 }
 
-extern "C" int fpl_version(void) { return 100; }
+int g_fpl_num_sms = 148;
+
+extern "C" int fpl_set_sm_budget(int sms) {
+    if (sms < 16 || sms > 148) {
+        fpl_set_error("fpl_set_sm_budget: %d not in [16, 148]", sms);
+        return 2;
+    }
+    g_fpl_num_sms = sms;
+    return 0;
+}
+
+extern "C" int fpl_version(void) { return 200; }
 
 extern "C" int fpl_device_is_sm100(void) {
     int dev = 0, major = 0;

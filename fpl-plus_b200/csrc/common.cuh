@@ -5,7 +5,11 @@
 #include <stdint.h>
 #include <stdio.h>
 
-#define FPL_NUM_SMS 148
+// SMs the persistent / one-CTA-per-SM kernels size their grids for.  148 on a B200; a data-parallel run lowers it by the
+// CTAs the NCCL all-reduce kernels hold while they overlap backward (fpl_set_sm_budget): a statically tiled 148-CTA grid
+// that finds 8 SMs occupied runs its last 8 CTAs as a second wave, i.e. takes twice as long.
+extern int g_fpl_num_sms;
+#define FPL_NUM_SMS g_fpl_num_sms
 
 void fpl_set_error(const char* fmt, ...);
 

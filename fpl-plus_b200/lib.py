@@ -18,6 +18,7 @@ _U = c_uint64
 _SIGNATURES = {
     "fpl_last_error": (c_char_p, []),
     "fpl_version": (_I, []),
+    "fpl_set_sm_budget": (_I, [_I]),
     "fpl_launch_count": (c_longlong, [_I]),
     "fpl_device_is_sm100": (_I, []),
     "fpl_debug_set": (None, [_I, c_longlong]),

@@ -28,6 +28,10 @@ extern "C" {
 
 const char* fpl_last_error(void);
 int fpl_version(void);
+/* Number of SMs the persistent kernels size their grids for (default 148).  One process per GPU with overlapped NCCL
+ * all-reduces (agent_seg.py:695 is nn.DataParallel in the reference) sets 148 - NCCL_MAX_CTAS so that the communication
+ * kernels and the statically tiled conv kernels never queue behind each other. */
+int fpl_set_sm_budget(int sms);
 /* Number of kernels this library has launched in the process so far (reset != 0 zeroes it).
  * Instrumentation only (bench.py reports it as "gpu_launches"); no reference counterpart. */
 long long fpl_launch_count(int reset);

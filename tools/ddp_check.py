@@ -73,6 +73,8 @@ def grad_mean_check(agent, rank, world):
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    from fplplus_b200.agent import reserve_sms_for_nccl
+    reserve_sms_for_nccl()
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
     agent = bench.build_agent("train", world)
     if os.environ.get("GRAD_MEAN", "0") != "0":
