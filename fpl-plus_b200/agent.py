@@ -735,6 +735,9 @@ class SegmentationAgent(object):
         self._pick_device('training')
         self.net.to(self.device)
         if self.world > 1:
+            if os.environ.get("NCCL_MAX_CTAS"):        # reserve_sms_for_nccl() ran before init_process_group
+                from . import lib as _lib
+                _lib.call("fpl_set_sm_budget", 148 - int(os.environ["NCCL_MAX_CTAS"]))
             self.reducer = GradAllReducer()
             self.net.grad_ready_hook = self.reducer.hook
             self.net.grad_wait_hook = self.reducer.finish
