@@ -186,7 +186,9 @@ class GradAllReducer(object):
     outstanding handles and applies the 1/world scale.  Parameters without gradients (2-D twins,
     1x1 convs, the other domain's BN) are never touched: no unused-parameter search."""
 
-    def __init__(self, bucket_bytes=4 << 20, group=None):
+    def __init__(self, bucket_bytes=0, group=None):
+        # bucket_bytes = 0: every range the network hands over is reduced at once (UNet2D5_dsbn already coalesces its
+        # hand-overs to >= grad_bucket_bytes and keeps the LAST one small, see net.py fire())
         self.bucket_bytes = bucket_bytes
         self.group = group
         self._pending = []
@@ -198,8 +200,12 @@ class GradAllReducer(object):
             self._start = start
         if (end - self._start) * 4 >= self.bucket_bytes or last:
             seg = flat[self._start:end]
-            seg.mul_(1.0 / dist.get_world_size(self.group))
-            self._pending.append(dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            if seg.is_cuda:
+                # NCCL averages inside the collective: no separate 1/world scaling kernel per bucket
+                self._pending.append(dist.all_reduce(seg, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+            else:                   # gloo (CPU tests) has no AVG
+                seg.mul_(1.0 / dist.get_world_size(self.group))
+                self._pending.append(dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
             self._start = None
 
     def finish(self):
@@ -236,7 +242,8 @@ def shard_round_robin(items, rank, world):
 # minimal built-in dataset (file formats are out of scope; this covers .npy volumes)
 # ------------------------------------------------------------------------------------------
 class NpyVolumeDataset(torch.utils.data.Dataset):
-    """Rows of (image.npy[, label.npy[, pixel_weight.npy[, image_weight]]]) -> the batch-dict keys
+    """Rows of (image[, label[, pixel_weight[, image_weight]]]) file names (.npy, or .nii / .nii.gz through
+    artefacts.py -- the 4 columns of config_dual/data_vs/train_vs_t1s_wi+wp.csv) -> the batch-dict keys
     the agent consumes (io/nifty_dataset.py:171-218): 'image' [C,D,H,W] fp32, 'label_prob'
     [class,D,H,W] fp32, 'pixel_weight' [1,D,H,W] folded by set_weight_ (:165-168), 'image_weight',
     'names'."""
@@ -247,18 +254,25 @@ class NpyVolumeDataset(torch.utils.data.Dataset):
     def __len__(self):
         return len(self.rows)
 
+    def _load(self, rel):
+        path = os.path.join(self.root, rel)
+        if path.endswith(('.nii.gz', '.nii')):
+            from . import artefacts
+            return artefacts.load_nifty_volume_as_4d_array(path)['data_array'][0]
+        return np.load(path)
+
     def __getitem__(self, i):
         row = self.rows[i]
-        img = np.load(os.path.join(self.root, row[0])).astype(np.float32)
+        img = np.asarray(self._load(row[0])).astype(np.float32)
         if img.ndim == 3:
             img = img[None]
         sample = {'image': torch.from_numpy(img), 'names': row[0]}
         if len(row) > 1 and row[1]:
-            lab = np.load(os.path.join(self.root, row[1]))
+            lab = np.asarray(self._load(row[1]))
             sample['label_prob'] = torch.from_numpy(
                 np.stack([lab == c for c in range(self.class_num)], 0).astype(np.float32))
         if len(row) > 2 and row[2]:
-            w = np.load(os.path.join(self.root, row[2])).astype(np.float32)[None]
+            w = np.asarray(self._load(row[2])).astype(np.float32)[None]
             iw = float(row[3]) if len(row) > 3 else 1.0
             w = np.where(w < 1, 0, w).astype(np.float32) * np.float32(iw)      # set_weight_
             sample['pixel_weight'] = torch.from_numpy(w)
@@ -921,14 +935,23 @@ class SegmentationAgent(object):
         return merged
 
     def save_outputs(self, outputs):
-        """uint8 label volumes -> ``output_dir/<name>.npy`` (NIfTI writing needs SimpleITK: out of scope)."""
+        """uint8 label volumes -> ``output_dir/<name>`` (agent_seg.py:1022-1065): NIfTI in, NIfTI out with the input
+        volume's geometry (artefacts.py writes NIfTI-1 without SimpleITK); other names are saved as ``.npy``."""
         out_dir = self.config['testing'].get('output_dir', None)
         if not out_dir:
             return
+        from . import artefacts
         os.makedirs(out_dir, exist_ok=True)
+        root = self.config.get('dataset', {}).get('root_dir', '') or ''
         for name, lab in outputs.items():
             base = os.path.basename(str(name))
-            for ext in ('.nii.gz', '.nii', '.npy'):
+            vol = np.asarray(lab)
+            vol = vol[0] if vol.ndim == 4 else vol
+            if base.endswith(('.nii.gz', '.nii')):
+                src = os.path.join(root, str(name))
+                artefacts.save_array_as_nifty_volume(vol, os.path.join(out_dir, base), src if os.path.isfile(src) else None)
+                continue
+            for ext in ('.npy',):
                 if base.endswith(ext):
                     base = base[:-len(ext)]
             np.save(os.path.join(out_dir, base + '.npy'), lab)

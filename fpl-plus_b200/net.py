@@ -175,6 +175,7 @@ class UNet2D5_dsbn(nn.Module):
         self.grad_ready_hook = None     # callable(flat_grad, start, end, last) fired as buckets complete (DDP)
         self.grad_wait_hook = None      # callable() that makes the current stream wait for those all-reduces
         self.grad_bucket_bytes = 4 << 20
+        self.grad_tail_bytes = 3 << 19      # 1.5 MB: the hand-over that cannot overlap anything stays below this
         self._master = None             # persistent flat gradient buffer (see _deliver_grads)
         self._head = UNet2D5_dsbn._HeadConv(self.out_conv)
         self._stem = None
@@ -1013,8 +1014,12 @@ class UNet2D5_dsbn(nn.Module):
             if self.grad_ready_hook is not None:
                 end = offs[n_params_done - 1] + sizes[n_params_done - 1]
                 last = n_params_done == len(params)
-                # hand over >= grad_bucket_bytes at a time: every hand-over costs a fold launch and an all-reduce launch
-                if end > fired[0] and (last or (end - fired[0]) * 4 >= self.grad_bucket_bytes):
+                # hand over >= grad_bucket_bytes at a time: every hand-over costs a fold launch and an all-reduce launch.
+                # The all-reduce of the LAST hand-over has nothing left to hide under, so it is kept small: once less
+                # than grad_tail_bytes remain, whatever has accumulated (>= 1 MB) goes out early.
+                pending_b, remaining_b = (end - fired[0]) * 4, (len(flat) - end) * 4
+                if end > fired[0] and (last or pending_b >= self.grad_bucket_bytes
+                                       or (remaining_b <= self.grad_tail_bytes and pending_b >= (1 << 20))):
                     flush_fold()
                     self._join_aux()
                     self.grad_ready_hook(flat, fired[0], end, n_params_done == len(params))

@@ -78,7 +78,10 @@ def test_train_valid_checkpoints_resume_and_infer(tmp_path):
     out = ag3.run()
     lab = out["vol_a.nii.gz"]
     assert lab.dtype == np.uint8 and lab.shape == (1, 24, 48, 48)
-    assert os.path.exists(os.path.join(cfg3["testing"]["output_dir"], "vol_a.npy"))
+    # NIfTI name in -> NIfTI label volume out (artefacts.py, no SimpleITK), same voxels
+    from fplplus_b200 import artefacts
+    saved = artefacts.read_nifti(os.path.join(cfg3["testing"]["output_dir"], "vol_a.nii.gz"))
+    assert saved["data"].dtype == np.uint8 and np.array_equal(saved["data"], lab[0])
     ck = torch.load(os.path.join(d, "vs_S_12.pt"), map_location="cpu", weights_only=False)
     st = {k: v.float() if v.is_floating_point() else v for k, v in ck["model_state_dict"].items()}
     params = dict(NET_PARAMS)
@@ -112,3 +115,51 @@ def test_fpl_branch_sorts_uncertainties(tmp_path):
     assert saved.shape == (3, 2)                                          # the reference's object-array layout
     # MC dropout was live (K passes differ) -> a non-sentinel uncertainty somewhere on an untrained net
     assert any(v != 1 for v in vals)
+
+
+def test_validation_loss_and_dice_match_the_oracle(tmp_path):
+    """a19 (agent_seg.py:509-604): per domain, Inferer pass over every validation volume, unweighted loss of the batch and
+    per-volume hard Dice; model selection by val_t1 / val_t2.  Against the oracle Inferer + losses on the same weights."""
+    from oracle import losses
+    from fplplus_b200.agent import SegmentationAgent
+    cfg = _config(tmp_path)
+    ag = SegmentationAgent(cfg, "train")
+    ag.create_network()
+    sd = synth.synth_state_dict()
+    ag.net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+    ag._pick_device("training")
+    ag.net.to(ag.device)
+    ag.create_loss_calculator()
+    shape = (24, 48, 48)
+
+    def vols(seed, n):
+        out = []
+        for i in range(n):
+            lab = synth.synth_label(1, 2, shape, seed=seed + i)
+            x = synth.synth_image(1, 1, shape, seed=seed + i) * 0.5 + (lab[:, None] > 0) * 2.0
+            out.append({"image": torch.from_numpy(x.astype(np.float32)), "label_prob": torch.from_numpy(synth.one_hot(lab, 2)),
+                        "names": ["v%d" % (seed + i)]})
+        return out
+    valid = [vols(300, 2), vols(400, 3)]
+    ag.set_loaders(valid=valid)
+    st = unet_dsbn.to_torch_state(sd, requires_grad=False)
+    params = dict(NET_PARAMS)
+    ref = []
+    for d in (0, 1):
+        ls, ds = [], []
+        for b in valid[d]:
+            with torch.no_grad():
+                z = oracle_inferer.run(lambda x: unet_dsbn.forward(st, x, d, params), b["image"], 2, cfg["testing"])
+            ls.append(float(losses.combined_loss(z, b["label_prob"], None, 0.5, 0.5)))
+            ds.append(losses.hard_dice(z, b["label_prob"]).numpy())
+        ref.append((np.mean(ls), np.mean(np.stack(ds, 0), 0)))
+    for key, pick in ((None, (0, 1)), ("val_t1", (0,)), ("val_t2", (1,))):
+        cfg["training"]["val_t1"], cfg["training"]["val_t2"] = key == "val_t1", key == "val_t2"
+        got = ag.validation()
+        exp_loss = float(np.mean([ref[d][0] for d in pick]))
+        exp_dice = np.mean(np.stack([ref[d][1] for d in pick], 0), 0)
+        print(key, "validation loss %.5f oracle %.5f; class dice %s oracle %s" % (got["loss"], exp_loss, got["class_dice"], exp_dice))
+        assert abs(got["loss"] - exp_loss) <= 1e-2 * abs(exp_loss)
+        np.testing.assert_allclose(got["class_dice"], exp_dice, atol=2e-2)
+        assert abs(got["avg_dice"] - float(exp_dice.mean())) <= 2e-2
+    assert ag.net.training                                    # validation() hands the network back in train mode
