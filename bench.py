@@ -44,6 +44,32 @@ TEST_CFG = {"fpl": True, "gpus": [0], "domian_label": 1, "ae": False, "ckpt_mode
             "sliding_window_size": [32, 128, 128], "sliding_window_stride": [32, 128, 128]}
 
 
+def conv_gflop(params=None, patch=None):
+    """Algorithmic conv GFLOP of ONE sample: (forward, train = fwd + dgrad + wgrad, forward of the dropout-free encoder
+    prefix).  2 * taps * Cin * Cout per output voxel; the stem has no dgrad; bilinear = False."""
+    params, patch = params or NET_PARAMS, patch or PATCH
+    ft, dims, cls = params["feature_chns"], params["conv_dims"], params["class_num"]
+    vox = [float(patch[0] * patch[1] * patch[2])]
+    for i in range(4):
+        vox.append(vox[-1] / (8 if dims[i] == 3 else 4))
+    taps = [27 if d == 3 else 9 for d in dims]
+    fwd, stem = 0.0, 2.0 * taps[0] * params["in_chns"] * ft[0] * vox[0]
+    chans = [params["in_chns"]] + list(ft)
+    per_level = []
+    for i in range(5):
+        lv = 2.0 * taps[i] * (chans[i] * ft[i] + ft[i] * ft[i]) * vox[i]
+        per_level.append(lv)
+        fwd += lv
+    for lvl in (3, 2, 1, 0):
+        up_taps = 8 if dims[lvl] == 3 else 4
+        fwd += 2.0 * up_taps * ft[lvl + 1] * ft[lvl] * vox[lvl + 1]                       # transposed conv k2s2
+        fwd += 2.0 * taps[lvl] * (2 * ft[lvl] * ft[lvl] + ft[lvl] * ft[lvl]) * vox[lvl]
+    fwd += 2.0 * 9 * ft[0] * cls * vox[0]                                                   # (1,3,3) head
+    drop = params["dropout"]
+    first = next((i for i in range(5) if drop[i] > 0), 5)
+    return fwd / 1e9, (3 * fwd - stem) / 1e9, sum(per_level[:first]) / 1e9
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -261,7 +287,7 @@ def build_agent(stage, world):
            "training": dict(TRAIN_CFG), "testing": dict(TEST_CFG)}
     agent = SegmentationAgent(cfg, stage)
     agent.create_network()
-    sd = synth.synth_state_dict()
+    sd = synth.synth_state_dict(NET_PARAMS["in_chns"], NET_PARAMS["feature_chns"], NET_PARAMS["class_num"], NET_PARAMS["num_domains"])
     agent.net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
     agent._pick_device("training" if stage == "train" else "testing")
     agent.net.to(agent.device)
@@ -478,7 +504,7 @@ def run_ours(args):
                           "voxels_per_step_per_gpu": vox_per_step, "parallelism": "dp%d" % world,
                           "nccl_max_ctas": nccl_ctas or None,
                           "l2": "activation working set per step >> 126 MB L2 (inputs larger than L2)",
-                          "conv_gflop_per_step_per_gpu": 2 * BATCH * 179.9},
+                          "conv_gflop_per_step_per_gpu": 2 * BATCH * conv_gflop()[1], "config_name": args.config},
                "e2e": {"value": e2e_value, "unit": "voxels/s", "ms_per_step": ms_e2e / args.steps,
                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                        "api": "fplplus_b200.agent.SegmentationAgent.train_step(host batch dicts); every step's loss is read "
@@ -492,7 +518,7 @@ def run_ours(args):
                "e2e_fp32_onehot": e2e_alt,
                "hbm_kernels": hbm,
                "kernels": kern,
-               "conv_tensor_util": {"achieved_tflops_over_step": world * 2 * BATCH * 179.9e9 / (step_ms / 1e3) / 1e12 / world,
+               "conv_tensor_util": {"achieved_tflops_over_step": 2 * BATCH * conv_gflop()[1] * 1e9 / (step_ms / 1e3) / 1e12,
                                     "peak_tflops": pk["bf16_tflops_sustained"]},
                "pl_filter": pl}
         if not args.skip_cpu and world == 1:
@@ -503,7 +529,7 @@ def run_ours(args):
                                         "~15 s of CPU work and OMP_NUM_THREADS=1 starves the CPU arm; see --impl reference")
         if not args.skip_cpu and world == 1 and pl is not None and not args.quick:
             pl["cpu_baseline"] = pl_filter_cpu_baseline()
-        if world == 1 and not args.quick and not args.skip_torch:
+        if world == 1 and not args.quick and not args.skip_torch and args.config == "configs2":
             out["torch_cuda_baseline"] = torch_cuda_baseline(dev, args)
         if not args.skip_filter and not args.quick:
             out["filter_kernels"] = filter_kernel_rooflines(dev, pk)
@@ -574,11 +600,14 @@ def bench_filter(agent, rank, world, barrier, max_over_ranks, args):
     # FLOPs per volume: the reference runs 8 Inferer passes x 8 windows x 4 flips = 256 full forwards of 59.97 GFLOP
     # (15.35 TFLOP).  forward_mc computes the dropout-free encoder prefix (block0 + block1 = 13.13 GFLOP) once for the
     # 6 MC passes of a window batch, so 5 x 13.13 GFLOP per window forward set are NOT executed: 13.25 TFLOP.
-    executed_tflop = 32 * (2 * 59.97 + 6 * 59.97 - 5 * 13.13) / 1e3
+    g_fwd, _g_train, g_prefix = conv_gflop(NET_PARAMS, tuple(TEST_CFG["sliding_window_size"]))
+    n_win = 4 * int(np.prod([-(-VOLUME[i] // TEST_CFG["sliding_window_stride"][i]) for i in range(3)]))    # windows x 4 flips
+    executed_tflop = n_win * (2 * g_fwd + 6 * g_fwd - 5 * g_prefix) / 1e3
+    reference_tflop = n_win * 8 * g_fwd / 1e3
     return {"metric": "pl_filter_volumes_per_s", "value": vps, "unit": "volumes/s", "ms_per_volume": ms / nvol,
-            "volumes_timed_per_gpu": nvol, "forwards_per_volume": 256,
+            "volumes_timed_per_gpu": nvol, "forwards_per_volume": 8 * n_win,
             "conv_tflops": executed_tflop * vps / world, "executed_tflop_per_volume": executed_tflop,
-            "reference_equivalent_tflop_per_volume": 15.35, "reference_equivalent_tflops": 15.35 * vps / world,
+            "reference_equivalent_tflop_per_volume": reference_tflop, "reference_equivalent_tflops": reference_tflop * vps / world,
             "workload": "VS-style 1x48x256x256 volume: dual-domain sliding-window inference (window 32x128x128, "
                         "4-flip TTA) + argmax labels + agreement pixel weights + 6 MC-dropout passes -> image "
                         "uncertainty (BASELINE.json configs[1]); host volumes in, u8 labels + fp32 weights + scalar out",
@@ -730,7 +759,8 @@ def _oracle_trainer(threads):
     from oracle.train_step import OracleTrainer
     torch.set_num_threads(threads)
     params = dict(NET_PARAMS)
-    return OracleTrainer(synth.synth_state_dict(), params, lr=1e-4, weight_decay=1e-5, w_dice=0.5, w_ce=0.5)
+    sd = synth.synth_state_dict(params["in_chns"], params["feature_chns"], params["class_num"], params["num_domains"])
+    return OracleTrainer(sd, params, lr=1e-4, weight_decay=1e-5, w_dice=0.5, w_ce=0.5)
 
 
 def cpu_baseline(bounded_steps=2, batch=1):
@@ -758,7 +788,8 @@ def pl_filter_cpu_baseline():
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     params = dict(NET_PARAMS)
-    st = unet_dsbn.to_torch_state(synth.synth_state_dict(), requires_grad=False)
+    st = unet_dsbn.to_torch_state(synth.synth_state_dict(params["in_chns"], params["feature_chns"], params["class_num"],
+                                                         params["num_domains"]), requires_grad=False)
     cfg = dict(TEST_CFG, tta_mode=0)
     vol = torch.from_numpy(synth.synth_image(1, 1, VOLUME, seed=50))
     t0 = time.time()
@@ -815,6 +846,20 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+def apply_workload(name):
+    """--config vs_shipped: the authors' own VS configuration (config_dual/data_vs/vs_t1s_S.cfg): feature_chns
+    32-64-128-256-512, conv_dims [2,2,3,3,3], batch 4 x 28x128x128 patches, windows 28x128x128 -- the shape of the
+    checkpoints users actually load.  The default workload stays BASELINE.json configs[2]."""
+    global PATCH, VOLUME
+    if name == "vs_shipped":
+        NET_PARAMS.update(feature_chns=[32, 64, 128, 256, 512], conv_dims=[2, 2, 3, 3, 3])
+        PATCH = (28, 128, 128)
+        VOLUME = (56, 256, 256)
+        TEST_CFG.update(sliding_window_size=[28, 128, 128], sliding_window_stride=[28, 128, 128])
+    elif name != "configs2":
+        raise SystemExit("unknown --config %s" % name)
+
+
 def main():
     wd = int(os.environ.get("FPL_BENCH_WATCHDOG", "0"))
     if wd > 0:                       # debugging aid: dump every thread's stack and exit if the run wedges
@@ -832,7 +877,10 @@ def main():
     ap.add_argument("--quick", action="store_true", help="headline numbers only (no baselines / kernel rooflines)")
     ap.add_argument("--fp32-onehot", action="store_true",
                     help="feed the PyMIC loader layout (fp32 one-hot labels, folded fp32 weights) instead of uint8 labels / codes")
+    ap.add_argument("--config", default="configs2", choices=["configs2", "vs_shipped"],
+                    help="configs2 = BASELINE.json configs[2] (default, the headline); vs_shipped = the authors' VS .cfg")
     args = ap.parse_args()
+    apply_workload(args.config)
     if args.impl == "reference":
         run_reference(args)
         return

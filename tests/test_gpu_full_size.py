@@ -190,3 +190,58 @@ def test_full_size_window_stitching_identity():
         out = inf.run(Toy(), vol, torch.zeros(1, dtype=torch.long))
         want = torch.cat([vol * 2.0 + 1.0, -vol], 1)
         assert float((out - want).abs().max()) <= 1e-5
+
+
+def test_shipped_vs_config_eval_logits_and_train_step():
+    """SURVEY 8 f-1 at the authors' REAL configuration (config_dual/data_vs/vs_t1s_g.cfg:61-64,115-117): feature_chns
+    32-64-128-256-512, conv_dims [2,2,3,3,3] (2.5-D: (1,3,3) convs, (1,2,2) pools / transposed convs on the first two
+    levels), patches / windows 28x128x128.  Eval logits and one weighted Dice+CE train step against the oracle."""
+    from oracle import losses, unet_dsbn
+    from fplplus_b200.loss import CombinedLoss
+    from fplplus_b200.registry import loss_dict
+    params = dict(NET_PARAMS, feature_chns=[32, 64, 128, 256, 512], conv_dims=[2, 2, 3, 3, 3], dropout=[0.0] * 5)
+    shape = (28, 128, 128)
+    net = _net(params)
+    sd = synth.synth_state_dict(1, params["feature_chns"], 2, 2)
+    x = torch.from_numpy(synth.synth_image(1, 1, shape, seed=21))
+    # eval, both domains
+    net.eval()
+    st = unet_dsbn.to_torch_state(sd, requires_grad=False)
+    for dmn in (0, 1):
+        with torch.no_grad():
+            z = net(x.to(DEV), domain_label=dmn * torch.ones(1, dtype=torch.long)).cpu()
+            ref = unet_dsbn.forward(st, x, dmn, params)
+        e = rel_l2(z, ref)
+        print("shipped VS config, domain %d: eval logits rel_l2 %.2e" % (dmn, e))
+        assert e < 1e-2
+    # one train step (batch 2, target domain, pixel-weighted 0.5 Dice + 0.5 CE)
+    net.train()
+    xb = torch.from_numpy(synth.synth_image(2, 1, shape, seed=22))
+    lab = synth.synth_label(2, 2, shape, seed=22)
+    y = torch.from_numpy(synth.one_hot(lab, 2))
+    pw = torch.from_numpy(synth.synth_pixel_weight(lab, seed=22)[0])
+    crit = CombinedLoss({"loss_type": ["DiceLoss", "CrossEntropyLoss"], "loss_weight": [0.5, 0.5]}, loss_dict)
+    out = net(xb.to(DEV), domain_label=torch.ones(2, dtype=torch.long))
+    loss = crit({"prediction": out, "ground_truth": y.to(DEV), "pixel_weight": pw.to(DEV)})
+    loss.backward()
+    st = unet_dsbn.to_torch_state(sd, requires_grad=True)
+    ref_out = unet_dsbn.forward(st, xb, 1, params, bn_training=True)
+    ref_loss = losses.combined_loss(ref_out, y, pw, 0.5, 0.5)
+    ref_loss.backward()
+    print("shipped VS config train step: logits rel_l2 %.2e loss %.6f oracle %.6f" % (
+        rel_l2(out.detach().cpu(), ref_out.detach()), float(loss), float(ref_loss)))
+    assert rel_l2(out.detach().cpu(), ref_out.detach()) < 1.5e-2
+    assert abs(float(loss) - float(ref_loss)) <= 1e-2 * abs(float(ref_loss))
+    named = dict(net.named_parameters())
+    got_keys = {k for k, p in named.items() if p.grad is not None}
+    ref_keys = {k for k, v in st.items() if v.requires_grad and v.grad is not None}
+    assert got_keys == ref_keys                                  # 2-D members on levels 0-1, 3-D members below
+    assert "block0.conv.conv2d_1.weight" in got_keys and "block2.conv.conv3d_1.weight" in got_keys
+    for key in ("out_conv.weight", "out_conv.bias", "up4.conv.conv2d_2.weight", "up4.trans2d.weight"):
+        e = rel_l2(named[key].grad.cpu(), st[key].grad)
+        print("  d%-28s rel_l2 %.2e" % (key, e))
+        assert e < 8e-2, (key, e)
+    # running statistics of the selected domain
+    sdn = net.state_dict()
+    for key in ("block0.conv.bn2d1.bns.1.running_mean", "up4.conv.bn2d2.bns.1.running_var"):
+        assert rel_l2(sdn[key].cpu(), st[key].detach()) < 2e-2, key
