@@ -69,7 +69,7 @@ bool make_ct_cfg(int kdim, int ndim, int kc_div, CtCfg& c) {
     int cols = 2 * c.nb;
     c.tmem_cols = 32;
     while (c.tmem_cols < cols) c.tmem_cols *= 2;
-    c.smem_bytes = c.stages * stage + 1024 + 256 + 1024 * (int)sizeof(float) + 16;
+    c.smem_bytes = c.stages * stage + 1024 + 256 + (ndim > 1024 ? ndim : 1024) * (int)sizeof(float) + 16;   // + the tiled bias [ndim]
     return true;
 }
 
@@ -473,7 +473,7 @@ static int convt_gemm_launch(int mode, const void* a, int a_c8tot, int a_c8off, 
     const int kdim = mode == 0 ? cin : ntaps * cout, ndim = mode == 0 ? ntaps * cout : cin;
     CtCfg c;
     FPL_REQUIRE(make_ct_cfg(kdim, ndim, mode == 0 ? cin : cout, c), "fpl_convt_k2s2_tc: unsupported channels (%d -> %d)", cin, cout);
-    FPL_REQUIRE(ndim <= 1024, "fpl_convt_k2s2_tc: GEMM N = %d too large", ndim);
+    FPL_REQUIRE(ndim <= 8192, "fpl_convt_k2s2_tc: GEMM N = %d too large", ndim);      // 8 taps x 1024 output channels
     EncodeTiledFn encode = get_encode_fn();
     FPL_REQUIRE(encode != nullptr, "fpl_convt_k2s2_tc: cuTensorMapEncodeTiled not available from the driver");
     CUtensorMap amap;

@@ -201,8 +201,7 @@ def test_shipped_vs_config_eval_logits_and_train_step():
     from fplplus_b200.registry import loss_dict
     params = dict(NET_PARAMS, feature_chns=[32, 64, 128, 256, 512], conv_dims=[2, 2, 3, 3, 3], dropout=[0.0] * 5)
     shape = (28, 128, 128)
-    net = _net(params)
-    sd = synth.synth_state_dict(1, params["feature_chns"], 2, 2)
+    net, sd = _net(params)
     x = torch.from_numpy(synth.synth_image(1, 1, shape, seed=21))
     # eval, both domains
     net.eval()

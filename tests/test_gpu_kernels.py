@@ -532,7 +532,8 @@ def test_dsbn_fused_finalize_entry_points_equal_the_two_step_ones(training, pool
 
 
 @pytest.mark.parametrize("cin,cout,kd2,shape", [(32, 16, 2, (2, 2, 16, 8)), (64, 32, 1, (1, 3, 20, 12)),
-                                                (256, 128, 2, (1, 1, 4, 6)), (128, 64, 2, (1, 2, 8, 8))])
+                                                (256, 128, 2, (1, 1, 4, 6)), (128, 64, 2, (1, 2, 8, 8)),
+                                                (512, 256, 2, (1, 2, 4, 8))])      # the shipped VS widths: GEMM N = 2048
 def test_convt_k2s2_tensor_core_fwd_dgrad_wgrad(cin, cout, kd2, shape):
     """ConvTranspose3d k2 s2 on tcgen05 (strided TMA sub-lattices) against torch on bf16-rounded operands."""
     from fplplus_b200 import lib as L
