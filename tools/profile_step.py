@@ -23,7 +23,7 @@ def main():
     agent.use_cuda_graph = False
     agent.dual_stream = False
     agent.net.wgrad_side_stream = False
-    host = [bench.make_batch(11, bench.BATCH, bench.PATCH, False, True), bench.make_batch(12, bench.BATCH, bench.PATCH, True, True)]
+    host = [bench.make_batch(11, bench.BATCH, bench.PATCH, False, True, True), bench.make_batch(12, bench.BATCH, bench.PATCH, True, True, True)]
     dev = [{k: (v.to(agent.device) if torch.is_tensor(v) else v) for k, v in b.items()} for b in host]
     for _ in range(int(os.environ.get("WARM", "2"))):
         agent.train_step(dev)
