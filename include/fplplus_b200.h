@@ -142,6 +142,17 @@ int fpl_conv3d_tc_dfold_bwdred(const void* x, int x_c8tot, int x_c8off, const vo
                                const float* slope, float drop_p, uint64_t seed, uint64_t offset,
                                const uint64_t* seed_dev, double* red, void* stream);
 
+/* ---- device data path of the training inputs: RandomCrop + RandomFlip (transform/crop.py:170-244, flip.py:14-62) -----
+ * d_rows: DEVICE table of n rows of 64 bytes
+ *   { const float* image [C][D][H][W]; const uint8_t* label [D][H][W] or NULL; const uint8_t* code [D][H][W] or NULL;
+ *     int32 D, H, W; int32 d0, h0, w0 (crop origin); int32 flip (bit 0 depth, 1 height, 2 width); int32 pad[3] }
+ * of volumes resident in HBM.  Writes the batch: out_image fp32 [n][C][pd][ph][pw], out_label uint8 [n][pd][ph][pw]
+ * (may be NULL), out_code uint8 [n][pd][ph][pw] (may be NULL; a sample without a code map gets 2 = weight 1).
+ * out[d,h,w] = volume[d0 + (flip_d ? pd-1-d : d), h0 + (flip_h ? ph-1-h : h), w0 + (flip_w ? pw-1-w : w)].
+ * LabelToProbability and set_weight_ follow inside fpl_dice_ce_*_ex. */
+int fpl_gather_patches(const void* d_rows, int n, int c, int pd, int ph, int pw, float* out_image,
+                       uint8_t* out_label, uint8_t* out_code, void* stream);
+
 /* ---- optimiser: torch.optim.Adam(params, lr, weight_decay=wd) of net_run/get_optimizer.py:16-17 (coupled L2) ----------
  * ONE launch over all tensors.  d_segs: DEVICE table of nseg rows of 48 bytes
  *   { float* param; const float* grad; float* exp_avg; float* exp_avg_sq; float* step; int32 numel; int32 pad }
