@@ -693,7 +693,7 @@ def filter_kernel_rooflines(dev, pk, iters=16):
 
     def grad_u8(i):
         call("fpl_dice_ce_grad_ex", ptr(zs[i % n_rot]), None, ptr(labs[i % n_rot]), None, ptr(codes[i % n_rot]), ptr(iw),
-             ptr(sums), 0.5, 0.5, 0.0, 1.0, ptr(gs), None, ptr(dz), n, C, sp, 0, stream_ptr())
+             ptr(sums), 0.5, 0.5, 0.0, 1.0, ptr(gs), None, ptr(dz), n, C, sp, 0, 0, stream_ptr())
 
     def red_f32(i):
         call("fpl_dice_ce_reduce_ex", ptr(zs[i % n_rot]), ptr(onehots[i % 6]), None, ptr(pws[i % 6]), None, None,
@@ -701,7 +701,7 @@ def filter_kernel_rooflines(dev, pk, iters=16):
 
     def grad_f32(i):
         call("fpl_dice_ce_grad_ex", ptr(zs[i % n_rot]), ptr(onehots[i % 6]), None, ptr(pws[i % 6]), None, None,
-             ptr(sums), 0.5, 0.5, 0.0, 1.0, ptr(gs), None, ptr(dz), n, C, sp, 0, stream_ptr())
+             ptr(sums), 0.5, 0.5, 0.0, 1.0, ptr(gs), None, ptr(dz), n, C, sp, 0, 0, stream_ptr())
     red_u8(0)
     V = n * sp
     timeit("fpl_dice_ce_reduce_ex_u8_labels", red_u8, V * (4 * C + 2))

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kThreads) dice_ce_grad_kernel(const float* __r
                                                                const double* __restrict__ sums, float w_dice,
                                                                float w_ce, float w_ent, float grad_scale,
                                                                const float* __restrict__ grad_scale_dev, float* loss,
-                                                               float* dlogits, int N, int64_t S4) {
+                                                               float* dlogits, int N, int64_t S4, int n_global) {
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const bool weighted = src.weight != nullptr || src.wcode != nullptr;
     if (grad_scale_dev != nullptr) grad_scale *= __ldg(grad_scale_dev);
@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(kThreads) dice_ce_grad_kernel(const float* __r
     }
     dice_mean /= C;
     const double sum_w = sums[3 * C], sum_wce = sums[3 * C + 1];
-    const double V = (double)N * (double)S4 * 4.0;
+    // voxels the sums cover: the local batch, or the GLOBAL batch when the sums were all-reduced (exact data-parallel mode)
+    const double V = (double)(n_global > 0 ? n_global : N) * (double)S4 * 4.0;
     const double ce_den = weighted ? sum_w + 1e-5 : V;
     if (loss != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
         double l = 0.0;
@@ -258,13 +259,14 @@ static int dice_ce_reduce_launch(const float* logits, const LossSrc& src, double
 
 static int dice_ce_grad_launch(const float* logits, const LossSrc& src, const double* sums, float w_dice, float w_ce,
                                float w_ent, float grad_scale, const float* grad_scale_dev, float* loss, float* dlogits,
-                               int n, int c, int64_t spatial, void* stream) {
+                               int n, int c, int64_t spatial, void* stream, int n_global = 0) {
+    FPL_REQUIRE(n_global == 0 || n_global >= n, "fpl_dice_ce_grad: n_global %d < n %d", n_global, n);
     FPL_REQUIRE(spatial % 4 == 0, "fpl_dice_ce_grad: spatial size %lld must be a multiple of 4", (long long)spatial);
     FPL_REQUIRE(src.soft_y != nullptr || src.label != nullptr, "fpl_dice_ce_grad: soft_y or label required");
     int64_t s4 = spatial / 4;
     int grid = dlogits != nullptr ? grid_for((int64_t)n * s4) : 1;
     FPL_DISPATCH_C(c, (fpl_launch(dice_ce_grad_kernel<CC>, grid, kThreads, 0, (cudaStream_t)stream, 
-                          logits, src, sums, w_dice, w_ce, w_ent, grad_scale, grad_scale_dev, loss, dlogits, n, s4)));
+                          logits, src, sums, w_dice, w_ce, w_ent, grad_scale, grad_scale_dev, loss, dlogits, n, s4, n_global)));
     FPL_LAUNCH_CHECK();
     return 0;
 }
@@ -295,9 +297,9 @@ extern "C" int fpl_dice_ce_grad_ex(const float* logits, const float* soft_y, con
                                    const uint8_t* weight_code, const float* image_weight, const double* sums,
                                    float w_dice, float w_ce, float w_entropy, float grad_scale,
                                    const float* grad_scale_dev, float* loss, float* dlogits, int n, int c,
-                                   int64_t spatial, int prob_input, void* stream) {
+                                   int64_t spatial, int prob_input, int n_global, void* stream) {
     FPL_REQUIRE(!(prob_input && w_entropy != 0.0f), "fpl_dice_ce_grad_ex: the entropy term is defined on logits");
     LossSrc src = {soft_y, label, weight, weight_code, image_weight, prob_input};
     return dice_ce_grad_launch(logits, src, sums, w_dice, w_ce, w_entropy, grad_scale, grad_scale_dev, loss, dlogits, n,
-                               c, spatial, stream);
+                               c, spatial, stream, n_global);
 }

@@ -79,14 +79,18 @@ class _DiceCE(torch.autograd.Function):
         st = stream_ptr()
         src = _src_args(truth, weight)
         call("fpl_dice_ce_reduce_ex", ptr(logits), *src, ptr(sums), n, c, spatial, 1 if w_ent != 0.0 else 0, prob_input, st)
+        # exact data-parallel mode: the (6C+3) partial sums of all ranks are summed between the two passes,
+        # so Dice / CE are those of the GLOBAL batch as under nn.DataParallel (agent_seg.py:695, dice.py:29-35); the
+        # gradient is scaled by the world size because the parameter gradients are AVERAGED over ranks afterwards
+        world = 1
         red = holder.get("sums_allreduce") if holder is not None else None
         if red is not None:
-            red(sums)            # exact data-parallel Dice: the partial sums of all ranks, see agent.py
+            world = int(red(sums))
         loss = torch.empty((), dtype=torch.float32, device=logits.device)
         call("fpl_dice_ce_grad_ex", ptr(logits), *src, ptr(sums), w_dice, w_ce, w_ent, 1.0, None, ptr(loss), None, n, c,
-             spatial, prob_input, st)
+             spatial, prob_input, n * world if world > 1 else 0, st)
         ctx.saved = (logits, truth, weight, sums)
-        ctx.w = (w_dice, w_ce, w_ent, prob_input)
+        ctx.w = (w_dice, w_ce, w_ent, prob_input, world)
         if holder is not None:
             holder["sums"] = sums
             holder["voxels"] = n * spatial
@@ -99,8 +103,9 @@ class _DiceCE(torch.autograd.Function):
         spatial = logits.numel() // (n * c)
         dlogits = torch.empty_like(logits)
         g = grad_out.float().contiguous()
-        call("fpl_dice_ce_grad_ex", ptr(logits), *_src_args(truth, weight), ptr(sums), ctx.w[0], ctx.w[1], ctx.w[2], 1.0,
-             ptr(g), None, ptr(dlogits), n, c, spatial, ctx.w[3], stream_ptr())
+        world = ctx.w[4]
+        call("fpl_dice_ce_grad_ex", ptr(logits), *_src_args(truth, weight), ptr(sums), ctx.w[0], ctx.w[1], ctx.w[2],
+             float(world), ptr(g), None, ptr(dlogits), n, c, spatial, ctx.w[3], n * world if world > 1 else 0, stream_ptr())
         return dlogits, None, None, None, None, None, None, None
 
 

@@ -350,14 +350,18 @@ int fpl_dice_ce_grad(const float* logits, const float* soft_y, const float* weig
  * NiftyDataset.set_weight_ (io/nifty_dataset.py:165-168): w < 1 -> 0, else w * image_weight[n].  10 instead of 20
  * bytes/voxel at C = 2 in the reduce pass.  w_entropy weighs the regulariser -sum p*log2(p+1e-10)/(N*D*H*W) of
  * agent_seg.py:353,467 (value and gradient); want_entropy makes the reduce pass accumulate its sum.  prob_input != 0:
- * `logits` already hold probabilities (loss_softmax = False, loss/seg/abstract.py:16-21): no softmax, d/dp returned. */
+ * `logits` already hold probabilities (loss_softmax = False, loss/seg/abstract.py:16-21): no softmax, d/dp returned.
+ * n_global (grad form; 0 = n): number of samples the sums cover when the caller all-reduced them over data-parallel ranks
+ * between the two calls -- Dice and CE are then those of the GLOBAL batch, as nn.DataParallel computes them
+ * (agent_seg.py:695, loss/seg/dice.py:29-35). */
 int fpl_dice_ce_reduce_ex(const float* logits, const float* soft_y, const uint8_t* label, const float* weight,
                           const uint8_t* weight_code, const float* image_weight, double* sums, int n, int c,
                           int64_t spatial, int want_entropy, int prob_input, void* stream);
 int fpl_dice_ce_grad_ex(const float* logits, const float* soft_y, const uint8_t* label, const float* weight,
                         const uint8_t* weight_code, const float* image_weight, const double* sums,
                         float w_dice, float w_ce, float w_entropy, float grad_scale, const float* grad_scale_dev,
-                        float* loss, float* dlogits, int n, int c, int64_t spatial, int prob_input, void* stream);
+                        float* loss, float* dlogits, int n, int c, int64_t spatial, int prob_input, int n_global,
+                        void* stream);
 
 /* ---- (c) pseudo-label filter: agent_seg.py:897-931,1045-1050; data/get_pixel_weight.py:21-26;
  *          io/nifty_dataset.py:165-168 ---- */

@@ -7,8 +7,10 @@ import json
 import subprocess
 import sys
 
-ENTRY = {"conv3d_wgrad_tc_kernel": "fpl_conv3d_wgrad_tc_tapmajor", "conv3d_tc_dfold_kernel": "fpl_conv3d_tc_dfold",
-         "conv3d_tc_kernel": "fpl_conv3d_tc"}
+# keyed by KERNEL name: bench.py aggregates every entry point that launches the same kernel into one roofline population
+# (conv3d_wgrad_tc_kernel = the k3 / k(1,3,3) wgrads + head wgrad + the stem's k(3,1,1) wgrad: all its launches of one step)
+ENTRY = {"conv3d_wgrad_tc_kernel": "conv3d_wgrad_tc_kernel", "conv3d_tc_dfold_kernel": "conv3d_tc_dfold_kernel",
+         "conv3d_tc_kernel": "conv3d_tc_kernel"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 

@@ -42,10 +42,10 @@ def main():
         call("fpl_window_normalize", ptr(acc), ptr(cnt), 1.0, acc.numel(), stream_ptr())
         call("fpl_dice_ce_reduce_ex", ptr(z), None, ptr(lab), None, ptr(code), ptr(iw), ptr(sums), n, C, sp, 0, 0, stream_ptr())
         call("fpl_dice_ce_grad_ex", ptr(z), None, ptr(lab), None, ptr(code), ptr(iw), ptr(sums), 0.5, 0.5, 0.0, 1.0, ptr(gs), None,
-             ptr(dz), n, C, sp, 0, stream_ptr())
+             ptr(dz), n, C, sp, 0, 0, stream_ptr())
         call("fpl_dice_ce_reduce_ex", ptr(z), ptr(onehot), None, ptr(pw), None, None, ptr(sums), n, C, sp, 0, 0, stream_ptr())
         call("fpl_dice_ce_grad_ex", ptr(z), ptr(onehot), None, ptr(pw), None, None, ptr(sums), 0.5, 0.5, 0.0, 1.0, ptr(gs), None,
-             ptr(dz), n, C, sp, 0, stream_ptr())
+             ptr(dz), n, C, sp, 0, 0, stream_ptr())
     run()
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
