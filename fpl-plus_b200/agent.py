@@ -702,6 +702,8 @@ class SegmentationAgent(object):
             self.inferer = Inferer(infer_cfg)
         res = []
         self._broadcast_state(buffers_only=True)
+        hold = getattr(self.loss_calculator, "last", None)
+        exact = hold.pop("sums_allreduce", None) if isinstance(hold, dict) else None     # every rank validates ALL volumes
         self.net.eval()
         with torch.no_grad():
             for d in range(n_dom):
@@ -717,6 +719,8 @@ class SegmentationAgent(object):
                 if losses:
                     res.append((torch.stack(losses).mean(), torch.stack(dices).mean(0)))
         self.net.train()
+        if exact is not None:
+            hold["sums_allreduce"] = exact
         if not res:
             return {'loss': 0.0, 'avg_dice': 0.0, 'class_dice': np.zeros(class_num)}
         host = [(float(l), c.cpu().numpy()) for l, c in res]
@@ -776,6 +780,7 @@ class SegmentationAgent(object):
         self._broadcast_state()
         self.create_optimizer(self.get_parameters_to_update())
         self.create_loss_calculator()
+        self._install_exact_dp_dice()
         if self.rank == 0:
             os.makedirs(ckpt_dir, exist_ok=True)
         self.glob_it = iter_start
@@ -911,6 +916,23 @@ class SegmentationAgent(object):
         inval = getattr(self.net, "invalidate_weight_images", None)
         if inval is not None and not buffers_only:
             inval()
+
+    def _install_exact_dp_dice(self):
+        """[training] exact_dp_dice = True (optional): nn.DataParallel (agent_seg.py:695) evaluates Dice / CE over
+        the gathered GLOBAL batch (loss/seg/dice.py:29-35); one process per GPU evaluates them per rank, which is a
+        different gradient because Dice is a ratio of sums.  With this key the (6C+3) partial sums of the fused loss
+        are all-reduced between its reduce and gradient passes (120 bytes per domain pass), which restores the
+        reference's multi-GPU loss exactly; the default keeps the per-rank loss (no extra collective)."""
+        hold = getattr(self.loss_calculator, "last", None)
+        if self.world == 1 or hold is None or not self.config['training'].get('exact_dp_dice', False):
+            return
+        import torch.distributed as dist
+        world = self.world
+
+        def allreduce(sums):
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+            return world
+        hold["sums_allreduce"] = allreduce
 
     def _agree_scalars(self, scal):
         """Rank 0's validation scalars on every rank (bit-identical control flow: stop_now, scheduler, best model)."""

@@ -929,3 +929,49 @@ def test_dgrad_epilogue_accumulates_the_dsbn_backward_sums(kernel, cin, cout, sh
     tol = 2e-5 * float(b.abs().max()) + 1e-6
     assert float((a - b).abs().max()) <= tol, (float((a - b).abs().max()), tol)
     assert float(b[:c_prev].abs().max()) > 0 and float(b[-1].abs()) > 0
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_exact_data_parallel_dice_equals_the_global_batch_loss(weighted):
+    """nn.DataParallel evaluates Dice / CE over the gathered global batch.  Emulation of two ranks on one
+    GPU: per-rank reduce passes, the (6C+3) sums added (what the all-reduce does), per-rank gradient passes with
+    n_global = 2n and gradient scale 2 (the parameter gradients are averaged over ranks afterwards).  The loss equals the
+    loss of ONE call on the concatenated batch and each rank's dlogits equal 2x its slice of that call's dlogits."""
+    from oracle import synth
+    shape, c, n = (8, 16, 32), 2, 2
+    lab = synth.synth_label(2 * n, c, shape, seed=31)
+    y = torch.from_numpy(synth.one_hot(lab, c)).to(DEV)
+    z = randn(32, 2 * n, c, *shape, scale=2.0).to(DEV)
+    w = torch.from_numpy(synth.synth_pixel_weight(lab, seed=31)[0]).to(DEV) if weighted else None
+    sp = shape[0] * shape[1] * shape[2]
+    one = torch.ones((), device=DEV)
+
+    def reduce_(zz, yy, ww, sums, nn_):
+        _call("fpl_dice_ce_reduce_ex", _p(zz), _p(yy), None, _p(ww), None, None, _p(sums), nn_, c, sp, 0, 0, _st())
+
+    def grad_(zz, yy, ww, sums, nn_, scale, n_global):
+        loss = torch.zeros((), device=DEV)
+        dz = torch.empty_like(zz)
+        _call("fpl_dice_ce_grad_ex", _p(zz), _p(yy), None, _p(ww), None, None, _p(sums), 0.5, 0.5, 0.0, scale, _p(one),
+              _p(loss), _p(dz), nn_, c, sp, 0, n_global, _st())
+        return float(loss), dz
+
+    full = torch.zeros(6 * c + 3, dtype=torch.float64, device=DEV)
+    reduce_(z, y, w, full, 2 * n)
+    loss_full, dz_full = grad_(z, y, w, full, 2 * n, 1.0, 0)
+    halves = [(z[:n].contiguous(), y[:n].contiguous(), None if w is None else w[:n].contiguous()),
+              (z[n:].contiguous(), y[n:].contiguous(), None if w is None else w[n:].contiguous())]
+    parts = []
+    for zz, yy, ww in halves:
+        s_ = torch.zeros(6 * c + 3, dtype=torch.float64, device=DEV)
+        reduce_(zz, yy, ww, s_, n)
+        parts.append(s_)
+    total = parts[0] + parts[1]                                  # the all-reduce
+    torch.testing.assert_close(total, full, rtol=1e-12, atol=1e-9)
+    for r, (zz, yy, ww) in enumerate(halves):
+        loss_r, dz_r = grad_(zz, yy, ww, total, n, 2.0, 2 * n)
+        assert abs(loss_r - loss_full) <= 1e-6 * abs(loss_full)
+        torch.testing.assert_close(dz_r, 2.0 * dz_full[r * n:(r + 1) * n], rtol=1e-5, atol=1e-10)
+        # and it is NOT the per-rank loss (Dice is a ratio of sums)
+        loss_local, _ = grad_(zz, yy, ww, parts[r], n, 1.0, 0)
+        assert abs(loss_local - loss_full) > 1e-5 * abs(loss_full)

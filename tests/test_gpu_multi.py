@@ -31,3 +31,16 @@ def test_two_rank_gradient_mean_and_parameter_agreement():
     print(r.stderr[-4000:])
     assert r.returncode == 0
     assert "GRAD MEAN OK" in r.stdout and "DDP CHECK OK" in r.stdout
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_exact_data_parallel_dice():
+    """[training] exact_dp_dice: the loss sums are all-reduced inside the (graph-captured) step; every rank reports the
+    same GLOBAL loss and the parameters stay bit-identical across ranks."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "ddp_check.py")]
+    env = dict(os.environ, STEPS="6", EXACT_DP="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    print(r.stdout[-3000:])
+    print(r.stderr[-3000:])
+    assert r.returncode == 0 and "DDP CHECK OK" in r.stdout

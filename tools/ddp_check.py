@@ -79,6 +79,11 @@ def main():
     agent = bench.build_agent("train", world)
     if os.environ.get("GRAD_MEAN", "0") != "0":
         grad_mean_check(agent, rank, world)
+    exact = os.environ.get("EXACT_DP", "0") != "0"
+    if exact:
+        agent.config["training"]["exact_dp_dice"] = True
+        agent.world = world
+        agent._install_exact_dp_dice()
     host = [bench.make_batch(100 + rank * 2, bench.BATCH, bench.PATCH, False, True),
             bench.make_batch(101 + rank * 2, bench.BATCH, bench.PATCH, True, True)]
     steps = int(os.environ.get("STEPS", "7"))
@@ -97,7 +102,10 @@ def main():
         if rank == 0:
             print("step %d (%s): parameters identical on %d ranks; local losses %s" % (
                 it, "graph" if it >= 4 else "eager", world, [round(float(l), 5) for l in losses]), flush=True)
-    assert len({round(float(l), 7) for l in losses}) > 1, "ranks saw the same data: the check proves nothing"
+    if exact:
+        assert len({round(float(l), 6) for l in losses}) == 1, "exact-DP Dice: every rank must report the GLOBAL loss"
+    else:
+        assert len({round(float(l), 7) for l in losses}) > 1, "ranks saw the same data: the check proves nothing"
     dist.barrier()
     if rank == 0:
         print("DDP CHECK OK")
