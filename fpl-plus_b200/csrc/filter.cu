@@ -86,6 +86,18 @@ __global__ void __launch_bounds__(kThreads) mc_uncertainty_kernel(PassPtrs ptrs,
                 for (int c = 0; c < C; ++c) zv[c] = ld_stream_f4(reinterpret_cast<const float4*>(ptrs.p[k]) + c * S4 + g);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
+                    if (C == 2) {
+                        // two classes: exp(z_max - z_max) is exactly 1, so one expf per voxel gives the same bits as
+                        // the general form below (12 expf per voxel at K = 6 were the pacing cost of this kernel)
+                        const float z0 = reinterpret_cast<const float*>(&zv[0])[j], z1 = reinterpret_cast<const float*>(&zv[1])[j];
+                        const bool first = z0 >= z1;
+                        const float e = expf(first ? z1 - z0 : z0 - z1);
+                        const float e0 = first ? 1.0f : e, e1 = first ? e : 1.0f;
+                        const float s = e0 + e1;
+                        prob[k][0][j] = e0 / s;
+                        prob[k][1][j] = e1 / s;
+                        continue;
+                    }
                     float m = reinterpret_cast<const float*>(&zv[0])[j];
 #pragma unroll
                     for (int c = 1; c < C; ++c) m = fmaxf(m, reinterpret_cast<const float*>(&zv[c])[j]);

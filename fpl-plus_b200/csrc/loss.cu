@@ -13,6 +13,15 @@ constexpr int kThreads = 256;
 
 template <int C>
 __device__ __forceinline__ void softmax_c(const float* z, float* p) {
+    if (C == 2) {
+        // exp(z_max - z_max) is exactly 1: one expf instead of two, same bits as the general form below
+        const bool first = z[0] >= z[1];
+        const float e = expf(first ? z[1] - z[0] : z[0] - z[1]);
+        const float inv = 1.0f / (1.0f + e);
+        p[0] = first ? inv : e * inv;
+        p[1] = first ? e * inv : inv;
+        return;
+    }
     float m = z[0];
 #pragma unroll
     for (int c = 1; c < C; ++c) m = fmaxf(m, z[c]);
@@ -116,7 +125,7 @@ __global__ void __launch_bounds__(kThreads) dice_ce_reduce_kernel(const float* _
                 acc[c] = fmaf(w * y[c], p[c], acc[c]);
                 acc[C + c] = fmaf(w, y[c], acc[C + c]);
                 acc[2 * C + c] = fmaf(w, p[c], acc[2 * C + c]);
-                ce -= y[c] * logf(p[c] * 0.999f + 5e-4f);
+                if (y[c] != 0.0f) ce -= y[c] * logf(p[c] * 0.999f + 5e-4f);     // one-hot labels: one logf per voxel
                 acc[3 * C + 2 + C + c] += y[c];
             }
             acc[3 * C] += w;
