@@ -161,11 +161,15 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int t = tile_begin; t < tile_end; ++t) {
+                // depth runs fastest: consecutive tiles of a CTA are the same (h, w) window in consecutive depth steps, so
+                // the x planes two neighbouring steps share (kd halo; 2 of 4 planes in the depth-stacked mode) are
+                // re-fetched by the SAME SM right after their first use and hit L2 (w-fastest order: 293 MB of DRAM
+                // reads for the 201 MB of up4.conv1, profiles/r02a_prof_wgrad_summary.md)
                 int r = t;
+                const int dp = r % P.dplanes; r /= P.dplanes;
                 const int tw_i = r % P.tiles_w; r /= P.tiles_w;
-                const int th_i = r % P.tiles_h; r /= P.tiles_h;
-                const int dp = r % P.dplanes;
-                const int n = r / P.dplanes;
+                const int th_i = r % P.tiles_h;
+                const int n = r / P.tiles_h;
                 // stacked mode: dy planes ndy*dp .. ndy*dp+ndy-1 against x planes ndy*dp-pad .. (planes outside the
                 // volume: TMA zero fill)
                 const int d = P.ndy * dp;
