@@ -69,21 +69,36 @@ struct PassPtrs {
 
 // out[0] += sum over classes and voxels of the population variance across the K passes of the
 // softmax probabilities; out[1] += #voxels with -m*ln(m+1e-6) > 0.01, m = mean class-1 probability.
-template <int C>
-__global__ void __launch_bounds__(kThreads) mc_uncertainty_kernel(PassPtrs ptrs, int K, int64_t S4, double* out,
+// KT > 0: the pass count is a compile-time constant (KT = 6 is the reference's hard-coded value, agent_seg.py:898) and,
+// when KT * C <= 16, ALL K * C 16-byte loads of a voxel group are issued before the first use: with the runtime-K form
+// the `k < K` predicate kept ~2 loads in flight per thread and the kernel ran at 2.0 TB/s, latency bound at 24 %
+// occupancy (profiles/r02a_prof_filter_loss_summary.md).
+template <int C, int KT>
+__global__ void __launch_bounds__(kThreads) mc_uncertainty_kernel(PassPtrs ptrs, int K_rt, int64_t S4, double* out,
                                                                  float* umap) {
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
+    constexpr int KK = KT > 0 ? KT : kMaxK;
+    constexpr bool kPreload = KT > 0 && KT * C <= 16;
+    const int K = KT > 0 ? KT : K_rt;
     float var_acc = 0.0f;
     unsigned int cnt = 0;
     const float invK = 1.0f / (float)K;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < S4; g += (int64_t)gridDim.x * blockDim.x) {
-        float prob[kMaxK][C][4];
+        float prob[KK][C][4];
+        float4 zall[kPreload ? KK : 1][C];
+        if (kPreload) {
 #pragma unroll
-        for (int k = 0; k < kMaxK; ++k) {
+            for (int k = 0; k < KK; ++k)
+#pragma unroll
+                for (int c = 0; c < C; ++c) zall[k][c] = ld_stream_f4(reinterpret_cast<const float4*>(ptrs.p[k]) + c * S4 + g);
+        }
+#pragma unroll
+        for (int k = 0; k < KK; ++k) {
             if (k < K) {
                 float4 zv[C];
 #pragma unroll
-                for (int c = 0; c < C; ++c) zv[c] = ld_stream_f4(reinterpret_cast<const float4*>(ptrs.p[k]) + c * S4 + g);
+                for (int c = 0; c < C; ++c)
+                    zv[c] = kPreload ? zall[kPreload ? k : 0][c] : ld_stream_f4(reinterpret_cast<const float4*>(ptrs.p[k]) + c * S4 + g);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (C == 2) {
@@ -121,12 +136,12 @@ __global__ void __launch_bounds__(kThreads) mc_uncertainty_kernel(PassPtrs ptrs,
             for (int c = 0; c < C; ++c) {
                 float mean = 0.0f;
 #pragma unroll
-                for (int k = 0; k < kMaxK; ++k)
+                for (int k = 0; k < KK; ++k)
                     if (k < K) mean += prob[k][c][j];
                 mean *= invK;
                 float m2 = 0.0f;
 #pragma unroll
-                for (int k = 0; k < kMaxK; ++k)
+                for (int k = 0; k < KK; ++k)
                     if (k < K) { float dlt = prob[k][c][j] - mean; m2 = fmaf(dlt, dlt, m2); }
                 var_acc += m2 * invK;
                 if (c == 1) mean1 = mean;
@@ -343,7 +358,11 @@ extern "C" int fpl_mc_uncertainty(const float* const* h_logits_k, int k, int c, 
     for (int i = 0; i < kMaxKStream; ++i) ptrs.p[i] = i < k ? h_logits_k[i] : nullptr;
     int64_t s4 = spatial / 4;
     if (k <= kMaxK) {
-        FPL_DISPATCH_C(c, (fpl_launch(mc_uncertainty_kernel<CC>, grid_for(s4), kThreads, 0, (cudaStream_t)stream, ptrs, k, s4, out, uncertainty_map)));
+        if (k == 6) {
+            FPL_DISPATCH_C(c, (fpl_launch(mc_uncertainty_kernel<CC, 6>, grid_for(s4), kThreads, 0, (cudaStream_t)stream, ptrs, k, s4, out, uncertainty_map)));
+        } else {
+            FPL_DISPATCH_C(c, (fpl_launch(mc_uncertainty_kernel<CC, 0>, grid_for(s4), kThreads, 0, (cudaStream_t)stream, ptrs, k, s4, out, uncertainty_map)));
+        }
     } else {
         FPL_DISPATCH_C(c, (fpl_launch(mc_uncertainty_stream_kernel<CC>, grid_for(s4), kThreads, 0, (cudaStream_t)stream, ptrs, k, s4, out, uncertainty_map)));
     }

@@ -260,7 +260,11 @@ static int dice_ce_reduce_launch(const float* logits, const LossSrc& src, double
     FPL_REQUIRE(spatial % 4 == 0, "fpl_dice_ce_reduce: spatial size %lld must be a multiple of 4", (long long)spatial);
     FPL_REQUIRE(src.soft_y != nullptr || src.label != nullptr, "fpl_dice_ce_reduce: soft_y or label required");
     int64_t s4 = spatial / 4;
-    FPL_DISPATCH_C(c, (fpl_launch(dice_ce_reduce_kernel<CC>, grid_for((int64_t)n * s4), kThreads, 0, (cudaStream_t)stream, 
+    // 4 blocks per SM: every block ends with 6C+3 same-address double atomics, which serialise in L2 (1184 blocks cost
+    // ~5 us of a 15 us launch at the configs[2] batch)
+    int rgrid = grid_for((int64_t)n * s4);
+    if (rgrid > FPL_NUM_SMS * 4) rgrid = FPL_NUM_SMS * 4;
+    FPL_DISPATCH_C(c, (fpl_launch(dice_ce_reduce_kernel<CC>, rgrid, kThreads, 0, (cudaStream_t)stream, 
                           logits, src, sums, n, s4, want_entropy)));
     FPL_LAUNCH_CHECK();
     return 0;
