@@ -229,7 +229,8 @@ def reserve_sms_for_nccl(ctas=None):
     os.environ.setdefault("NCCL_MIN_CTAS", str(min(ctas, 4)))
     held = int(os.environ["NCCL_MAX_CTAS"])
     from . import lib as _lib
-    _lib.call("fpl_set_sm_budget", 148 - held)
+    # $FPL_SM_BUDGET overrides the grid size (A/B runs: cap NCCL but keep 148-CTA grids, or the reverse)
+    _lib.call("fpl_set_sm_budget", int(os.environ.get("FPL_SM_BUDGET", 148 - held)))
     return held
 
 
