@@ -215,22 +215,26 @@ class GradAllReducer(object):
         self._start = None
 
 
-def reserve_sms_for_nccl(ctas=None):
-    """Data-parallel runs: cap the CTAs NCCL's all-reduce kernels may hold (NCCL_MAX_CTAS, read by NCCL when the
-    communicator is created -- call this BEFORE ``init_process_group``) and size the library's persistent kernels for the
-    remaining SMs (fpl_set_sm_budget).  Without it the all-reduce kernels that overlap backward occupy a varying number of
-    SMs and every statically tiled 148-CTA conv grid that meets them runs a second wave (wgrad +22 % at 4-8 GPUs in
-    round 1).  ``ctas`` defaults to $FPL_NCCL_CTAS or 8; 0 leaves NCCL and the grids alone."""
+def reserve_sms_for_nccl(ctas=None, sm_budget=None):
+    """Data-parallel runs: how the SMs are shared between NCCL's all-reduce kernels (which overlap backward) and the
+    library's persistent one-CTA-per-SM kernels.  Call BEFORE ``init_process_group`` (NCCL reads NCCL_MAX_CTAS when the
+    communicator is created).
+
+    ``ctas`` ($FPL_NCCL_CTAS, default 0 = leave NCCL alone) caps NCCL's CTAs; ``sm_budget`` ($FPL_SM_BUDGET, default 148
+    minus the cap) is the SM count every persistent grid is sized for (fpl_set_sm_budget).  Measured on 8 B200
+    (profiles/README.md): capping NCCL slows the all-reduce more than the freed SMs gain (5.06 ms uncapped, 5.15 at
+    16 CTAs / 132 SMs, 5.31 at 8 / 140), so the default leaves both alone; the knobs stay for other topologies."""
     if ctas is None:
-        ctas = int(os.environ.get("FPL_NCCL_CTAS", "8"))
-    if ctas <= 0:
-        return 0
-    os.environ.setdefault("NCCL_MAX_CTAS", str(ctas))
-    os.environ.setdefault("NCCL_MIN_CTAS", str(min(ctas, 4)))
-    held = int(os.environ["NCCL_MAX_CTAS"])
-    from . import lib as _lib
-    # $FPL_SM_BUDGET overrides the grid size (A/B runs: cap NCCL but keep 148-CTA grids, or the reverse)
-    _lib.call("fpl_set_sm_budget", int(os.environ.get("FPL_SM_BUDGET", 148 - held)))
+        ctas = int(os.environ.get("FPL_NCCL_CTAS", "0"))
+    if ctas > 0:
+        os.environ.setdefault("NCCL_MAX_CTAS", str(ctas))
+        os.environ.setdefault("NCCL_MIN_CTAS", str(min(ctas, 4)))
+    held = int(os.environ.get("NCCL_MAX_CTAS", "0") or 0)
+    if sm_budget is None:
+        sm_budget = int(os.environ.get("FPL_SM_BUDGET", 148 - held))
+    if sm_budget != 148:
+        from . import lib as _lib
+        _lib.call("fpl_set_sm_budget", int(sm_budget))
     return held
 
 
@@ -754,9 +758,8 @@ class SegmentationAgent(object):
         self._pick_device('training')
         self.net.to(self.device)
         if self.world > 1:
-            if os.environ.get("NCCL_MAX_CTAS"):        # reserve_sms_for_nccl() ran before init_process_group
-                from . import lib as _lib
-                _lib.call("fpl_set_sm_budget", 148 - int(os.environ["NCCL_MAX_CTAS"]))
+            if os.environ.get("NCCL_MAX_CTAS") or os.environ.get("FPL_SM_BUDGET"):
+                reserve_sms_for_nccl()                 # the communicator exists already: only the grid budget applies
             self.reducer = GradAllReducer()
             self.net.grad_ready_hook = self.reducer.hook
             self.net.grad_wait_hook = self.reducer.finish

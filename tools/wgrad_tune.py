@@ -34,8 +34,11 @@ def t(cin, cout, kd, shape, knobs):
     return e0.elapsed_time(e1) / 5 * 1e3
 
 
-variants = [("tiles4", {16: 4, 17: 0}), ("tiles2", {16: 2, 17: 0}), ("tiles1", {16: 1, 17: 0}), ("tiles8", {16: 8, 17: 0})]
+variants = [("tiles2", {16: 2, 17: 0}), ("t2-noepi", {16: 2, 17: 1}), ("tiles4", {16: 4, 17: 0}), ("tiles8", {16: 8, 17: 0}),
+            ("tiles32", {16: 32, 17: 0}), ("t32-noepi", {16: 32, 17: 1})]
 FN = os.environ.get("FN", "fpl_conv3d_wgrad_tc_tapmajor")
+if os.environ.get("DEEP_ONLY"):
+    SHAPES = [s_ for s_ in SHAPES if s_[3][2] <= 32]
 print("%-28s" % "shape" + "".join("%12s" % v[0] for v in variants))
 for cin, cout, kd, shape in SHAPES:
     row = []
@@ -45,3 +48,5 @@ for cin, cout, kd, shape in SHAPES:
         except Exception as ex:
             row.append("%12s" % "n/a")
     print("%-28s" % ("%d->%d k%d %s" % (cin, cout, kd, "x".join(map(str, shape[1:])))) + "".join(row), flush=True)
+L.fpl_debug_set(16, 2)
+L.fpl_debug_set(17, 0)
