@@ -116,6 +116,11 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
+        # A/B switches of the tuning knobs (fpl_debug_set): FPL_DEBUG_SET="18=0,16=4" ...
+        for item in os.environ.get("FPL_DEBUG_SET", "").split(","):
+            if "=" in item:
+                k, v = item.split("=", 1)
+                lib.fpl_debug_set(int(k), int(v))
         _lib = lib
     return _lib
 
