@@ -224,10 +224,12 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
                     for (int i = 0; i <= P.pairs; ++i) P.counters[i] = 0u;
                 }
             }
-            // end marker: the MMA warp leaves its loop
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            stage_live[stage] = 0;
-            mbar_arrive(&full_bar[stage]);
+            if (P.counters != nullptr) {
+                // end marker: the MMA warp leaves its loop
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                stage_live[stage] = 0;
+                mbar_arrive(&full_bar[stage]);
+            }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer: the whole warp runs the loop (uniform), one lane issues =====================
@@ -248,9 +250,18 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
         const bool leader = elect_one();
         int stage = 0; uint32_t phase = 0;
         uint32_t accumulate = 0;
+        // static slices: a known tile count; dynamic scheduling: until the producer's end marker.  Both loop conditions are
+        // warp-UNIFORM values (a kernel parameter / a vote result): the descriptor arithmetic below must stay in uniform
+        // registers (a plain shared-memory flag test made the loop "possibly divergent" and cost 10-20 us per launch)
+        int remaining = P.counters == nullptr ? tile_end - tile_begin : -1;
         for (;;) {
+            if (remaining == 0) break;
             mbar_wait(&full_bar[stage], phase);
-            if (stage_live[stage] == 0) break;               // end marker of the producer (warp-uniform)
+            if (remaining < 0) {
+                if (__ballot_sync(0xffffffffu, stage_live[stage] != 0) == 0u) break;
+            } else {
+                --remaining;
+            }
             tc_fence_after();
             const uint32_t x_base = (ring_u + (uint32_t)stage * (uint32_t)P.stage_bytes) >> 4;
             const uint32_t dy_base = x_base + ((uint32_t)P.dy_off >> 4);
