@@ -20,7 +20,6 @@
 namespace {
 
 // debug / tuning knobs (fpl_debug_set keys 10..16)
-int g_wg_dynamic = 1;   // fpl_debug_set key 18
 int g_wg_swap = 0, g_wg_allow_m64 = 1, g_wg_m64_quadrant = 1, g_wg_allow_pair = 1, g_wg_force_tw = 0, g_wg_tiles_per_cta = 2, g_wg_skip_epilogue = 0;
 
 constexpr int kThreadsW = 192;
@@ -102,36 +101,7 @@ struct WgParams {
     int taps;                      // 9, or 1 = only the centre in-plane tap (k = (kd,1,1))
     int skip_epilogue;             // timing experiments only
     int tapmajor;                  // dW written as [tap][cout][cin] (coalesced atomics; see fpl_wgrad_tapmajor_to_dw_batch)
-    unsigned int* counters;        // dynamic tile scheduling: [pairs] next-tile counters + [1] finished-CTA ticket (NULL: static slices)
-    int pairs;
 };
-
-// Dynamic tile scheduling.  The split-K slices of an (M, N) pair used to be fixed tile ranges, one CTA per SM: when NCCL's
-// all-reduce kernels (or the other domain's stream) hold a few SMs, the CTAs that find no SM run as a second wave and the
-// launch takes up to twice as long (+22 % on average at 8 GPUs).  Now every CTA takes tile `slice` first and then fetches
-// chunks of kDynChunk tiles from its pair's counter until the pair is exhausted, so late CTAs simply do less; any CTA may
-// take any tile because the partial sums are combined by the atomics of the epilogue anyway.  The counters live in a
-// pool of slots (one per launch, round robin), zero at rest: the last CTA of a launch to finish resets its slot.
-constexpr int kDynChunk = 4;            // consecutive tiles = consecutive depth steps of one (h, w) window (L2 reuse)
-constexpr int kDynMaxPairs = 512;
-constexpr int kDynSlots = 256;
-__device__ unsigned int g_wg_counters[kDynSlots][kDynMaxPairs + 1];
-
-struct WgTile {
-    int tw_i, th_i, dp, n;
-};
-__device__ __forceinline__ WgTile decode_wg_tile(const WgParams& P, int t) {
-    // depth runs fastest: consecutive tiles are the same (h, w) window in consecutive depth steps, so the x planes two
-    // neighbouring steps share (kd halo; 2 of 4 planes in the depth-stacked mode) are re-fetched right after their first
-    // use and hit L2 (w-fastest order: 293 MB of DRAM reads for the 201 MB of up4.conv1, profiles/r02a_prof_wgrad_summary.md)
-    WgTile c;
-    int r = t;
-    c.dp = r % P.dplanes; r /= P.dplanes;
-    c.tw_i = r % P.tiles_w; r /= P.tiles_w;
-    c.th_i = r % P.tiles_h;
-    c.n = r / P.tiles_h;
-    return c;
-}
 
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
                                             int c4) {
@@ -164,7 +134,6 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
     uint64_t* empty_bar = bars + kMaxStagesW;
     uint64_t* done_bar = bars + 2 * kMaxStagesW;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStagesW + 1);
-    volatile int* stage_live = reinterpret_cast<volatile int*>(bars + 2 * kMaxStagesW + 2);   // [kMaxStagesW] 1 = tile, 0 = end marker
     uint8_t* ring = smem + 256;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -191,44 +160,28 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            auto issue_tile = [&](int t) {
-                const WgTile c = decode_wg_tile(P, t);
+            for (int t = tile_begin; t < tile_end; ++t) {
+                // depth runs fastest: consecutive tiles of a CTA are the same (h, w) window in consecutive depth steps, so
+                // the x planes two neighbouring steps share (kd halo; 2 of 4 planes in the depth-stacked mode) are
+                // re-fetched by the SAME SM right after their first use and hit L2 (w-fastest order: 293 MB of DRAM
+                // reads for the 201 MB of up4.conv1, profiles/r02a_prof_wgrad_summary.md)
+                int r = t;
+                const int dp = r % P.dplanes; r /= P.dplanes;
+                const int tw_i = r % P.tiles_w; r /= P.tiles_w;
+                const int th_i = r % P.tiles_h;
+                const int n = r / P.tiles_h;
                 // stacked mode: dy planes ndy*dp .. ndy*dp+ndy-1 against x planes ndy*dp-pad .. (planes outside the
                 // volume: TMA zero fill)
-                const int d = P.ndy * c.dp;
+                const int d = P.ndy * dp;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* x_dst = ring + (size_t)stage * P.stage_bytes;
                 uint8_t* dy_dst = x_dst + P.dy_off;
-                stage_live[stage] = 1;
                 mbar_expect_tx(&full_bar[stage], (uint32_t)(P.x_bytes + (P.ncols / 8) * P.plane_dy));
-                tma_load_5d(x_dst, &xmap, &full_bar[stage], 2 * (c.tw_i * P.tw - 1), c.th_i * P.th - 1,
-                            P.x_c8off + wk.mt_c * P.c8chunk, d + kd0 - pad_d, c.n);
-                tma_load_5d(dy_dst, &dymap, &full_bar[stage], 2 * (c.tw_i * P.tw), c.th_i * P.th,
-                            P.dy_c8off + wk.nc * (P.nb / 8), d, c.n);
+                tma_load_5d(x_dst, &xmap, &full_bar[stage], 2 * (tw_i * P.tw - 1), th_i * P.th - 1,
+                            P.x_c8off + wk.mt_c * P.c8chunk, d + kd0 - pad_d, n);
+                tma_load_5d(dy_dst, &dymap, &full_bar[stage], 2 * (tw_i * P.tw), th_i * P.th,
+                            P.dy_c8off + wk.nc * (P.nb / 8), d, n);
                 if (++stage == P.stages) { stage = 0; phase ^= 1; }
-            };
-            if (P.counters == nullptr) {
-                for (int t = tile_begin; t < tile_end; ++t) issue_tile(t);
-            } else {
-                unsigned int* ctr = P.counters + blockIdx.x / P.split;
-                issue_tile(wk.slice);                                   // every CTA owns one tile: its accumulators are defined
-                for (;;) {
-                    const int base = P.split + (int)atomicAdd(ctr, (unsigned int)kDynChunk);
-                    if (base >= P.tiles_total) break;
-                    const int lim = min(base + kDynChunk, P.tiles_total);
-                    for (int t = base; t < lim; ++t) issue_tile(t);
-                }
-                // the last CTA of the launch to stop fetching puts the slot back to zero for its next user
-                __threadfence();
-                if (atomicAdd(P.counters + P.pairs, 1u) == gridDim.x - 1) {
-                    for (int i = 0; i <= P.pairs; ++i) P.counters[i] = 0u;
-                }
-            }
-            if (P.counters != nullptr) {
-                // end marker: the MMA warp leaves its loop
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                stage_live[stage] = 0;
-                mbar_arrive(&full_bar[stage]);
             }
         }
     } else if (warp == 1) {
@@ -250,18 +203,8 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
         const bool leader = elect_one();
         int stage = 0; uint32_t phase = 0;
         uint32_t accumulate = 0;
-        // static slices: a known tile count; dynamic scheduling: until the producer's end marker.  Both loop conditions are
-        // warp-UNIFORM values (a kernel parameter / a vote result): the descriptor arithmetic below must stay in uniform
-        // registers (a plain shared-memory flag test made the loop "possibly divergent" and cost 10-20 us per launch)
-        int remaining = P.counters == nullptr ? tile_end - tile_begin : -1;
-        for (;;) {
-            if (remaining == 0) break;
+        for (int t = tile_begin; t < tile_end; ++t) {
             mbar_wait(&full_bar[stage], phase);
-            if (remaining < 0) {
-                if (__ballot_sync(0xffffffffu, stage_live[stage] != 0) == 0u) break;
-            } else {
-                --remaining;
-            }
             tc_fence_after();
             const uint32_t x_base = (ring_u + (uint32_t)stage * (uint32_t)P.stage_bytes) >> 4;
             const uint32_t dy_base = x_base + ((uint32_t)P.dy_off >> 4);
@@ -287,7 +230,7 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
         if (leader) umma_commit(done_bar);
         __syncwarp();
         FPL_PDL_TRIGGER();   // this CTA has issued its last tile: the next kernel of the stream may be scheduled as SMs drain
-    } else if (P.counters != nullptr || tile_end > tile_begin) {
+    } else if (tile_end > tile_begin) {
         // ===================== epilogue: TMEM -> fp32 atomics into dW =====================
         const int quarter = warp & 3;
         mbar_wait(done_bar, 0);
@@ -374,7 +317,6 @@ void fpl_wgrad_debug_set(int key, long long value) {
     if (key == 15) g_wg_force_tw = (int)value;
     if (key == 16) g_wg_tiles_per_cta = (int)value;
     if (key == 17) g_wg_skip_epilogue = (int)value;
-    if (key == 18) g_wg_dynamic = (int)value;
 }
 
 static int wgrad_tc_launch(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
@@ -414,13 +356,6 @@ static int wgrad_tc_launch(const void* x, int x_c8tot, int x_c8off, const void* 
     P.split = split;
     P.swap_lbo_sbo = g_wg_swap; P.m64_quadrant_layout = g_wg_m64_quadrant;
     P.taps = taps; P.skip_epilogue = g_wg_skip_epilogue; P.tapmajor = tapmajor;
-    P.pairs = pairs; P.counters = nullptr;
-    if (g_wg_dynamic && pairs <= kDynMaxPairs && split <= P.tiles_total) {
-        static unsigned int* pool = nullptr;
-        static unsigned int seq = 0;
-        if (pool == nullptr) FPL_CHECK_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&pool), g_wg_counters));
-        P.counters = pool + (size_t)(seq++ % kDynSlots) * (kDynMaxPairs + 1);
-    }
     FPL_CHECK_CUDA(cudaFuncSetAttribute(conv3d_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
     fpl_launch(conv3d_wgrad_tc_kernel, pairs * split, kThreadsW, c.smem_bytes, (cudaStream_t)stream, xmap, dymap, P);
     FPL_LAUNCH_CHECK();
