@@ -86,6 +86,11 @@ def test_agent_train_step_graph_replay_matches_oracle(batch):
     for key, ref in oracle.state.items():
         if key not in named or ref.grad is None:
             continue
+        if ".conv.conv" in key and key.endswith(".bias"):
+            # a conv bias in front of a training-mode BatchNorm has an identically zero gradient (BN removes the mean):
+            # fp32 autograd leaves ~1e-9 of rounding noise, this library writes exact zeros, and Adam normalises either
+            # (plus the 1e-5 weight decay) into +-lr steps -- two unrelated random walks, excluded from the comparison
+            continue
         ours, ref = named[key].detach().cpu().double(), ref.detach().double()
         d_rms = float((ours - ref).pow(2).mean().sqrt())
         if d_rms / lr_sum > worst[1]:
