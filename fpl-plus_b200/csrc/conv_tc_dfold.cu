@@ -33,11 +33,14 @@ struct DfParams {
     int x_c8tot, x_c8off;
     int nb, nslices, dc, ndc;        // dc: output planes per depth chunk; ndc = ceil(D/dc)
     int a_bytes, b_bytes, stages, tmem_cols;
+    int pb;                          // input planes per TMA box (= per pipeline stage)
     int tiles_h, tiles_w, total_items;
     int taps;                        // 9 (k 3x3x3) or 1 (k 3x1x1: only the centre in-plane tap)
     int a_ksteps;                    // distinct 16-channel K steps of A (B K step j reads A K step j % a_ksteps)
     EpiAct act;                      // act.scale != NULL: inference epilogue (affine + PReLU) instead of + bias
     EpiBwdRed br;                    // br.red != NULL (dgrad): BatchNorm-backward sums of the unit whose activation gradient is written
+    int dbg_epi, dbg_nomma, dbg_tma;
+    long long* dbg_trace;            // fpl_debug_set 47: CTA 0 logs clock64() per role and plane ([role][4096] entries)          // timing experiments only (fpl_debug_set 42 / 44): results are wrong when set
 };
 
 __device__ __forceinline__ void tmem_st_zero16(uint32_t taddr) {
@@ -78,7 +81,8 @@ __global__ void __launch_bounds__(kThreadsD, 2) conv3d_tc_dfold_kernel(const __g
     // [resident weights of this CTA's slice][A stage ring][barriers][bias]
     uint8_t* b_sm = smem;
     uint8_t* ring = smem + P.b_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)P.stages * P.a_bytes);
+    const uint32_t stage_bytes = (uint32_t)(P.pb * P.a_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)P.stages * stage_bytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kMaxStagesD;
     uint64_t* done_bar = bars + 2 * kMaxStagesD;                  // [kMaxDC] output plane complete
@@ -88,6 +92,7 @@ __global__ void __launch_bounds__(kThreadsD, 2) conv3d_tc_dfold_kernel(const __g
     float* bias_sm = reinterpret_cast<float*>(bars + 2 * kMaxStagesD + kMaxDC + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool trace = P.dbg_trace != nullptr && blockIdx.x == 0;
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
         for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -118,6 +123,7 @@ __global__ void __launch_bounds__(kThreadsD, 2) conv3d_tc_dfold_kernel(const __g
         if (lane == 0) {
             int cur_slice = -1;
             int stage = 0; uint32_t phase = 0;
+            int ntr0 = 0, ntr5 = 0;
             for (int t = blockIdx.x; t < P.total_items; t += gridDim.x) {
                 const DfItem c = decode_item(P, t);
                 if (c.slice != cur_slice) {
@@ -131,12 +137,34 @@ __global__ void __launch_bounds__(kThreadsD, 2) conv3d_tc_dfold_kernel(const __g
                         bulk_load(b_sm + off, src + off, (uint32_t)nbytes, w_bar);
                     }
                 }
-                for (int z = c.d0 - 1; z <= c.d0 + c.dcount; ++z) {
-                    if (z < 0 || z >= P.D) continue;
+                // ONE box per stage = pb consecutive input planes (planes outside the volume: TMA zero fill).  A box costs
+                // the TMA unit ~400 cycles of fixed overhead + ~8 per row per CTA whatever its size (tools/dfold_knob_probe.py:
+                // the load pipeline alone took 28 us of the 47 us of the 16 -> 16 layer with one 5.8 KB box per plane)
+                for (int z = c.d0 - 1; z <= c.d0 + c.dcount; z += P.pb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], (uint32_t)P.a_bytes);
-                    tma_load_3d(ring + (size_t)stage * P.a_bytes, &xmap, &full_bar[stage], (c.w0 - 1) * 8, c.h0 - 1,
-                                (c.n * P.D + z) * P.x_c8tot + P.x_c8off);
+                    if (trace) { P.dbg_trace[0 * 4096 + (ntr0++ & 4095)] = clock64(); }
+                    if (P.dbg_tma == 0) {
+                        mbar_expect_tx(&full_bar[stage], stage_bytes);
+                        tma_load_5d(ring + (size_t)stage * stage_bytes, &xmap, &full_bar[stage], (c.w0 - 1) * 8, c.h0 - 1, P.x_c8off, z, c.n);
+                    } else {     // timing experiments: narrower boxes / other element size (see dfold_launch)
+                        const int bw = (P.dbg_tma & 1) ? kTileW : kBoxW, bh = (P.dbg_tma & 8) ? kTileH : kBoxH;
+                        mbar_expect_tx(&full_bar[stage], (uint32_t)(bw * bh * 16 * (P.a_bytes / kPlaneBytes) * P.pb));
+                        tma_load_5d(ring + (size_t)stage * stage_bytes, &xmap, &full_bar[stage],
+                                    ((P.dbg_tma & 1) ? c.w0 : c.w0 - 1) * ((P.dbg_tma & 2) ? 2 : 8), (P.dbg_tma & 8) ? c.h0 : c.h0 - 1,
+                                    P.x_c8off, z, c.n);
+                    }
+                    if (trace) { P.dbg_trace[5 * 4096 + (ntr5++ & 4095)] = clock64(); }
+                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (lane == 1 && trace) {
+            // trace only: watches the boxes land (the MMA warp may look at a full barrier late)
+            int stage = 0, ntr6 = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < P.total_items; t += gridDim.x) {
+                const DfItem c = decode_item(P, t);
+                for (int z = c.d0 - 1; z <= c.d0 + c.dcount; z += P.pb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    P.dbg_trace[6 * 4096 + (ntr6++ & 4095)] = clock64();
                     if (++stage == P.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -154,6 +182,7 @@ __global__ void __launch_bounds__(kThreadsD, 2) conv3d_tc_dfold_kernel(const __g
         int stage = 0; uint32_t phase = 0;
         uint32_t item_phase = 0, w_phase = 0;
         int cur_slice = -1;
+        int ntr1 = 0, ntr2 = 0, ntr4 = 0;
         for (int t = blockIdx.x; t < P.total_items; t += gridDim.x) {
             const DfItem c = decode_item(P, t);
             if (c.slice != cur_slice) {
@@ -163,38 +192,44 @@ __global__ void __launch_bounds__(kThreadsD, 2) conv3d_tc_dfold_kernel(const __g
             }
             mbar_wait(acc_free, item_phase);                            // accumulators drained + zeroed
             tc_fence_after();
-            for (int r = -1; r <= c.dcount; ++r) {                      // input plane z = d0 + r
-                const int z = c.d0 + r;
-                if (z >= 0 && z < P.D) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    // output planes r-1+j, j in [jlo, jhi], clipped to the chunk
-                    const int jlo = r < 1 ? 1 - r : 0;
-                    const int jhi = r > c.dcount - 2 ? c.dcount - r : 2;
-                    const uint32_t ncols = (uint32_t)(jhi - jlo + 1) * (uint32_t)P.nb;
-                    const uint32_t idesc = idesc0 | ((ncols >> 3) << 17);
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(r - 1 + jlo) * (uint32_t)P.nb;
-                    const uint32_t a_base = ring_u + (uint32_t)(((size_t)stage * P.a_bytes) >> 4);
-                    const uint32_t b_base = b_u + (uint32_t)(jlo * P.nb);
-                    for (int j = 0; j < ksteps; ++j) {
-                        const uint32_t a_j = a_base + (uint32_t)(j % P.a_ksteps) * (2 * kPlaneBytes / 16);
-                        const uint32_t b_j = b_base + (uint32_t)j * b_kstep;
+            if (trace && leader) { P.dbg_trace[4 * 4096 + (ntr4++ & 4095)] = clock64(); }
+            for (int r0 = -1; r0 <= c.dcount; r0 += P.pb) {             // one box = input planes z = d0 + r0 .. + pb - 1
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (trace && leader) { P.dbg_trace[1 * 4096 + (ntr1++ & 4095)] = clock64(); }
+                for (int q = 0; q < P.pb; ++q) {
+                    const int r = r0 + q, z = c.d0 + r;
+                    if (r > c.dcount) break;
+                    if (z >= 0 && z < P.D) {
+                        // output planes r-1+j, j in [jlo, jhi], clipped to the chunk
+                        const int jlo = r < 1 ? 1 - r : 0;
+                        const int jhi = r > c.dcount - 2 ? c.dcount - r : 2;
+                        const uint32_t ncols = (uint32_t)(jhi - jlo + 1) * (uint32_t)P.nb;
+                        const uint32_t idesc = idesc0 | ((ncols >> 3) << 17);
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(r - 1 + jlo) * (uint32_t)P.nb;
+                        const uint32_t a_base = ring_u + (((uint32_t)stage * stage_bytes + (uint32_t)(q * P.a_bytes)) >> 4);
+                        const uint32_t b_base = b_u + (uint32_t)(jlo * P.nb);
+                        for (int j = 0; j < ksteps; ++j) {
+                            const uint32_t a_j = a_base + (uint32_t)(j % P.a_ksteps) * (2 * kPlaneBytes / 16);
+                            const uint32_t b_j = b_base + (uint32_t)j * b_kstep;
 #pragma unroll
-                        for (int t9 = 0; t9 < 9; ++t9) {
-                            if (P.taps == 1 && t9 != 4) continue;
-                            const uint64_t adesc = a_hi | (uint64_t)(a_j + (uint32_t)((t9 / 3) * kBoxW + (t9 % 3)));
-                            const uint64_t bdesc = b_hi | (uint64_t)(b_j + (uint32_t)(P.taps == 1 ? 0 : t9) * b_tap);
-                            if (leader) umma_bf16(d_tmem, adesc, bdesc, idesc, 1u);
+                            for (int t9 = 0; t9 < 9; ++t9) {
+                                if (P.taps == 1 && t9 != 4) continue;
+                                const uint64_t adesc = a_hi | (uint64_t)(a_j + (uint32_t)((t9 / 3) * kBoxW + (t9 % 3)));
+                                const uint64_t bdesc = b_hi | (uint64_t)(b_j + (uint32_t)(P.taps == 1 ? 0 : t9) * b_tap);
+                                if (leader && !P.dbg_nomma) umma_bf16(d_tmem, adesc, bdesc, idesc, 1u);
+                            }
                         }
                     }
-                    if (leader) umma_commit(&empty_bar[stage]);
-                    __syncwarp();
-                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                    if (r >= 1) {                                       // output plane r-1 has all its contributions
+                        if (leader) umma_commit(&done_bar[r - 1]);
+                        __syncwarp();
+                    }
                 }
-                if (r >= 1) {                                           // output plane r-1 has all its contributions
-                    if (leader) umma_commit(&done_bar[r - 1]);
-                    __syncwarp();
-                }
+                if (leader) umma_commit(&empty_bar[stage]);
+                __syncwarp();
+                if (trace && leader) { P.dbg_trace[2 * 4096 + (ntr2++ & 4095)] = clock64(); }
+                if (++stage == P.stages) { stage = 0; phase ^= 1; }
             }
             // a short last chunk: complete the unused plane barriers too, so that every barrier flips once per item
             for (int p = c.dcount; p < P.dc; ++p) {
@@ -230,6 +265,7 @@ __global__ void __launch_bounds__(kThreadsD, 2) conv3d_tc_dfold_kernel(const __g
         if (lane == 0) mbar_arrive(acc_free);
         uint32_t item_phase = 0;
         int cur_slice = -1;
+        int ntr3 = 0;
         const float act_slope = fuse_act ? __ldg(P.act.slope) : 0.0f;
         // fused BatchNorm-backward statistics (dgrad only; exclusive with want_stats, so `run` is shared)
         const float br_slope = fuse_br ? __ldg(P.br.slope) : 0.0f;
@@ -264,6 +300,7 @@ __global__ void __launch_bounds__(kThreadsD, 2) conv3d_tc_dfold_kernel(const __g
             for (int p = 0; p < c.dcount; ++p) {
                 mbar_wait(&done_bar[p], item_phase);
                 tc_fence_after();
+                if (trace && warp == 2 && lane == 0) { P.dbg_trace[3 * 4096 + (ntr3++ & 4095)] = clock64(); }
                 const int64_t out_base = (((int64_t)c.n * P.D + c.d0 + p) * P.y_c8tot + P.y_c8off + (c.slice * P.nb) / 8) * HW +
                                          (int64_t)h * P.W + w;
 #pragma unroll
@@ -272,6 +309,7 @@ __global__ void __launch_bounds__(kThreadsD, 2) conv3d_tc_dfold_kernel(const __g
                         const int c0 = k * 16;
                         const uint32_t taddr = lane_base + (uint32_t)(p * P.nb + c0);
                         uint32_t r[16];
+                        if (P.dbg_epi >= 2) continue;
                         tmem_ld16(taddr, r);
                         tmem_ld_wait();
                         tmem_st_zero16(taddr);                          // leave the slot clean for the next item
@@ -300,7 +338,7 @@ __global__ void __launch_bounds__(kThreadsD, 2) conv3d_tc_dfold_kernel(const __g
                                 }
                             }
                         }
-                        if (valid) {
+                        if (valid && P.dbg_epi == 0) {
                             st_bf16x8(P.y + out_base + (int64_t)(c0 / 8) * HW, v);
                             st_bf16x8(P.y + out_base + (int64_t)(c0 / 8 + 1) * HW, v + 8);
                         }
@@ -400,8 +438,11 @@ __global__ void dfold_prep_kernel(const float* __restrict__ w, __nv_bfloat16* im
     }
 }
 
+int g_df_ctas = 0, g_df_dc = 0, g_df_epi = 0, g_df_stages = 0, g_df_nomma = 0, g_df_tma = 0, g_df_pb = 0;   // fpl_debug_set 40..47
+long long* g_df_trace = nullptr;
+
 struct DfCfg {
-    int nb, nslices, dc, stages, a_bytes, b_bytes, tmem_cols, smem_bytes, ctas_per_sm;
+    int nb, nslices, dc, stages, a_bytes, b_bytes, tmem_cols, smem_bytes, ctas_per_sm, pb;
 };
 
 bool make_df_cfg(int cin, int cout, int d, DfCfg& c, int taps = 9, int cin_a = 0) {
@@ -415,16 +456,27 @@ bool make_df_cfg(int cin, int cout, int d, DfCfg& c, int taps = 9, int cin_a = 0
     if (c.b_bytes > 112 * 1024) return false;
     c.a_bytes = (cin_a / 8) * kPlaneBytes;
     c.dc = c.nb == 16 ? 16 : 8;
+    if (g_df_dc > 0 && g_df_dc * c.nb <= 512) c.dc = g_df_dc;
     if (c.dc > d) c.dc = d;
     if (c.dc < 2) return false;
     int cols = c.dc * c.nb;
     c.tmem_cols = 32;
     while (c.tmem_cols < cols) c.tmem_cols *= 2;
     if (c.tmem_cols > 512) return false;
-    c.stages = c.b_bytes <= 32 * 1024 ? 6 : 4;
-    c.smem_bytes = c.b_bytes + c.stages * c.a_bytes + 1024 + 512 + 4 * cout * (int)sizeof(float) + 16;
+    // pb input planes per TMA box / pipeline stage; as many stages (2..4) as keep two CTAs per SM, else what fits one
+    c.pb = g_df_pb > 0 ? g_df_pb : 2;
+    const int fixed = c.b_bytes + 1024 + 512 + 4 * cout * (int)sizeof(float) + 16;
+    c.stages = 0;
+    for (int s = c.pb == 1 ? 6 : 4; s >= 2 && c.stages == 0; --s)
+        if (fixed + s * c.pb * c.a_bytes <= 110 * 1024) c.stages = s;
+    for (int s = 4; s >= 2 && c.stages == 0; --s)
+        if (fixed + s * c.pb * c.a_bytes <= 220 * 1024) c.stages = s;
+    if (g_df_stages > 0 && g_df_stages <= kMaxStagesD) c.stages = g_df_stages;
+    if (c.stages == 0) return false;
+    c.smem_bytes = fixed + c.stages * c.pb * c.a_bytes;
     if (c.smem_bytes > 220 * 1024) return false;
     c.ctas_per_sm = (c.smem_bytes <= 110 * 1024 && c.tmem_cols <= 256) ? 2 : 1;
+    if (g_df_ctas > 0 && g_df_ctas <= c.ctas_per_sm) c.ctas_per_sm = g_df_ctas;
     return true;
 }
 
@@ -433,6 +485,16 @@ int g_dfold_enable = 1;
 }  // namespace
 
 void fpl_dfold_debug_set(int value) { g_dfold_enable = value; }
+void fpl_dfold_debug_knob(int key, long long value) {
+    if (key == 40) g_df_ctas = (int)value;
+    if (key == 41) g_df_dc = (int)value;
+    if (key == 42) g_df_epi = (int)value;
+    if (key == 43) g_df_stages = (int)value;
+    if (key == 44) g_df_nomma = (int)value;
+    if (key == 45) g_df_tma = (int)value;
+    if (key == 46) g_df_pb = (int)value;
+    if (key == 47) g_df_trace = reinterpret_cast<long long*>(value);
+}
 
 bool fpl_dfold_eligible(int cin, int cout, int kd, int d) {
     DfCfg c;
@@ -535,12 +597,18 @@ static int dfold_launch(const void* x, int x_c8tot, int x_c8off, const void* ima
     EncodeTiledFn encode = get_encode_fn();
     FPL_REQUIRE(encode != nullptr, "fpl_conv3d_tc_dfold: cuTensorMapEncodeTiled not available from the driver");
     CUtensorMap xmap;
-    cuuint64_t gdim[3] = {(cuuint64_t)w * 8, (cuuint64_t)h, (cuuint64_t)n * d * x_c8tot};
-    cuuint64_t gstride[2] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16};
-    cuuint32_t box[3] = {(cuuint32_t)kBoxW * 8, (cuuint32_t)kBoxH, (cuuint32_t)(cin_a / 8)};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(x), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    // timing experiments (fpl_debug_set 45, bit mask; wrong results): 1 = box without the W halo (one aligned 128-byte
+    // line per row), 2 = 8-byte elements, 4 = 256-byte L2 promotion, 8 = box without the H halo
+    const int bw = (g_df_tma & 1) ? kTileW : kBoxW, bh = (g_df_tma & 8) ? kTileH : kBoxH;
+    const int esz = (g_df_tma & 2) ? 8 : 2;
+    cuuint64_t gdim[5] = {(cuuint64_t)w * 16 / esz, (cuuint64_t)h, (cuuint64_t)x_c8tot, (cuuint64_t)d, (cuuint64_t)n};
+    cuuint64_t gstride[4] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16, (cuuint64_t)x_c8tot * h * w * 16,
+                             (cuuint64_t)d * x_c8tot * h * w * 16};
+    cuuint32_t box[5] = {(cuuint32_t)bw * 16 / esz, (cuuint32_t)bh, (cuuint32_t)(cin_a / 8), (cuuint32_t)c.pb, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&xmap, esz == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim,
+                        gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        (g_df_tma & 4) ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     FPL_REQUIRE(r == CUDA_SUCCESS, "fpl_conv3d_tc_dfold: cuTensorMapEncodeTiled failed (%d)", (int)r);
     DfParams P;
@@ -548,12 +616,13 @@ static int dfold_launch(const void* x, int x_c8tot, int x_c8off, const void* ima
     P.stats = stats; P.N = n; P.D = d; P.H = h; P.W = w; P.cin = cin; P.cout = cout;
     P.x_c8tot = x_c8tot; P.x_c8off = x_c8off;
     P.nb = c.nb; P.nslices = c.nslices; P.dc = c.dc; P.ndc = (d + c.dc - 1) / c.dc;
-    P.a_bytes = c.a_bytes; P.b_bytes = c.b_bytes; P.stages = c.stages; P.tmem_cols = c.tmem_cols;
+    P.a_bytes = c.a_bytes; P.b_bytes = c.b_bytes; P.stages = c.stages; P.tmem_cols = c.tmem_cols; P.pb = c.pb;
     P.tiles_h = (h + kTileH - 1) / kTileH; P.tiles_w = (w + kTileW - 1) / kTileW;
     int64_t total = (int64_t)P.tiles_h * P.tiles_w * P.ndc * n * c.nslices;
     FPL_REQUIRE(total < (1ll << 30), "fpl_conv3d_tc_dfold: too many items");
     P.total_items = (int)total;
     P.taps = taps; P.a_ksteps = cin_a / 16;
+    P.dbg_epi = g_df_epi; P.dbg_nomma = g_df_nomma; P.dbg_tma = g_df_tma; P.dbg_trace = g_df_trace;
     if (br != nullptr) P.br = *br; else { P.br.y = nullptr; P.br.scale = P.br.shift = P.br.mean = P.br.invstd = P.br.slope = nullptr; P.br.drop_p = 0.0f; P.br.seed = P.br.offset = 0; P.br.seed_dev = nullptr; P.br.red = nullptr; }
     if (act != nullptr) P.act = *act; else { P.act.scale = nullptr; P.act.shift = nullptr; P.act.slope = nullptr; P.act.drop_p = 0.0f; P.act.seed = P.act.offset = 0; P.act.seed_dev = nullptr; }
     int grid = FPL_NUM_SMS * c.ctas_per_sm;

@@ -103,14 +103,6 @@ struct WgParams {
     int tapmajor;                  // dW written as [tap][cout][cin] (coalesced atomics; see fpl_wgrad_tapmajor_to_dw_batch)
 };
 
-__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
-                                            int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-}
-
 struct WgWork {
     int mt_kd, mt_c, nc, slice;
 };
