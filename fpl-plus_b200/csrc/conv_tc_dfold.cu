@@ -464,7 +464,7 @@ bool make_df_cfg(int cin, int cout, int d, DfCfg& c, int taps = 9, int cin_a = 0
     while (c.tmem_cols < cols) c.tmem_cols *= 2;
     if (c.tmem_cols > 512) return false;
     // pb input planes per TMA box / pipeline stage; as many stages (2..4) as keep two CTAs per SM, else what fits one
-    c.pb = g_df_pb > 0 ? g_df_pb : 2;
+    c.pb = g_df_pb > 0 ? g_df_pb : (c.a_bytes <= 2 * kPlaneBytes ? 3 : 2);      // measured: tools/dfold_knob_probe.py pb
     const int fixed = c.b_bytes + 1024 + 512 + 4 * cout * (int)sizeof(float) + 16;
     c.stages = 0;
     for (int s = c.pb == 1 ? 6 : 4; s >= 2 && c.stages == 0; --s)

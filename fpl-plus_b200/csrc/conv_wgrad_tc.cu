@@ -20,6 +20,8 @@
 namespace {
 
 // debug / tuning knobs (fpl_debug_set keys 10..16)
+int g_wg_hs_dbg = 0;      // key 19: timing experiments of the h-stacked kernel
+int g_wg_hs = 1;          // key 18: h-stacked kernel for Cin 16 / 32 (conv_wgrad_hs.cu)
 int g_wg_swap = 0, g_wg_allow_m64 = 1, g_wg_m64_quadrant = 1, g_wg_allow_pair = 1, g_wg_force_tw = 0, g_wg_tiles_per_cta = 2, g_wg_skip_epilogue = 0;
 
 constexpr int kThreadsW = 192;
@@ -299,7 +301,11 @@ CUresult encode_5d(EncodeTiledFn encode, CUtensorMap* map, const void* base, int
 
 }  // namespace
 
-// debug knobs (keys 10..13), see fpl_debug_set
+bool fpl_wgrad_hs_eligible(int d, int h, int w, int cin, int cout, int kd, int taps);
+int fpl_wgrad_hs_launch(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off, float* dw, int n,
+                        int d, int h, int w, int cin, int cout, void* stream, int tapmajor, int skip_epilogue, int force_tw, int dbg);
+
+// debug knobs (keys 10..18), see fpl_debug_set
 void fpl_wgrad_debug_set(int key, long long value) {
     if (key == 10) g_wg_swap = (int)value;
     if (key == 11) g_wg_allow_m64 = (int)value;
@@ -309,12 +315,17 @@ void fpl_wgrad_debug_set(int key, long long value) {
     if (key == 15) g_wg_force_tw = (int)value;
     if (key == 16) g_wg_tiles_per_cta = (int)value;
     if (key == 17) g_wg_skip_epilogue = (int)value;
+    if (key == 18) g_wg_hs = (int)value;
+    if (key == 19) g_wg_hs_dbg = (int)value;
 }
 
 static int wgrad_tc_launch(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off,
                            float* dw, int n, int d, int h, int w, int cin, int cout, int kd, int taps, void* stream,
                            int tapmajor = 0) {
     FPL_REQUIRE(kd == 1 || kd == 3, "fpl_conv3d_wgrad_tc: kd=%d must be 1 or 3", kd);
+    if (g_wg_hs && fpl_wgrad_hs_eligible(d, h, w, cin, cout, kd, taps))
+        return fpl_wgrad_hs_launch(x, x_c8tot, x_c8off, dy, dy_c8tot, dy_c8off, dw, n, d, h, w, cin, cout, stream, tapmajor,
+                                   g_wg_skip_epilogue, g_wg_force_tw, g_wg_hs_dbg);
     WgCfg c;
     FPL_REQUIRE(make_wg_cfg(h, w, cin, cout, kd, g_wg_allow_m64, g_wg_allow_pair && d >= 2, c),
                 "fpl_conv3d_wgrad_tc: unsupported shape (cin %d, cout %d, %dx%d)", cin, cout, h, w);

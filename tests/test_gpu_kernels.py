@@ -154,7 +154,12 @@ def test_conv3d_dgrad(impl, cin, cout, kd, shape):
 
 @pytest.mark.parametrize("name", ["fpl_conv3d_wgrad", "fpl_conv3d_wgrad_tc"])
 @pytest.mark.parametrize("cin,cout,kd,shape", [(16, 16, 3, (2, 3, 16, 12)), (32, 16, 3, (1, 2, 8, 8)),
-                                               (16, 32, 1, (1, 2, 16, 16)), (64, 48, 3, (1, 2, 6, 10))])
+                                               (16, 32, 1, (1, 2, 16, 16)), (64, 48, 3, (1, 2, 6, 10)),
+                                               # Cin 16 / 32, W >= 16: the h-stacked kernel (conv_wgrad_hs.cu); ragged tiles,
+                                               # odd depth / height, several output-channel chunks, batch > 1
+                                               (16, 16, 3, (2, 3, 16, 32)), (32, 16, 3, (1, 5, 12, 16)), (16, 32, 3, (1, 4, 10, 48)),
+                                               (32, 32, 3, (2, 2, 6, 16)), (16, 16, 3, (1, 3, 7, 20)), (32, 48, 3, (1, 3, 9, 40)),
+                                               (16, 16, 3, (1, 9, 24, 80))])
 def test_conv3d_wgrad(name, cin, cout, kd, shape):
     from fplplus_b200 import lib as L
     if not hasattr(L.load(), name):
@@ -674,7 +679,8 @@ def test_stem_on_tensor_cores_patch9_k311(cout, shape):
 
 
 @pytest.mark.parametrize("cin,cout,kd,shape", [(16, 16, 3, (2, 4, 16, 32)), (32, 16, 3, (1, 6, 16, 16)), (64, 32, 3, (2, 4, 8, 16)),
-                                               (128, 128, 3, (2, 2, 8, 8)), (16, 16, 1, (1, 3, 16, 16))])
+                                               (128, 128, 3, (2, 2, 8, 8)), (16, 16, 1, (1, 3, 16, 16)), (16, 32, 3, (1, 5, 20, 36)),
+                                               (32, 32, 3, (2, 3, 10, 24))])
 def test_wgrad_tapmajor_and_fold(cin, cout, kd, shape):
     """fpl_conv3d_wgrad_tc_tapmajor writes S[tap][cout][cin]; fpl_wgrad_tapmajor_to_dw_batch folds it into the
     PyTorch layout ACCUMULATING into dw.  Against torch's conv3d weight gradient on bf16-rounded operands."""

@@ -190,6 +190,24 @@ int main() {
     cfgs.push_back(k_cfg("K  nosw M64  N64", 64, 64, 0, 8, 0));
     cfgs.push_back(k_cfg("K  sw128 M64  N64", 64, 64, 2, 8, 0));
 
+    {   // the exact operand geometry of conv3d_wgrad_hs_kernel (Cin 16, tw 32): slabs one row pitch apart, K along the row
+        auto hs = [](const char* name, uint32_t sx, uint32_t sdy, uint32_t lbo) {
+            Cfg c = {};
+            c.name = name; c.m = 128; c.n = 64; c.a_mn = 1; c.b_mn = 1; c.swz = 0;
+            c.a_lbo = lbo; c.a_sbo = sx; c.b_lbo = lbo; c.b_sbo = sdy;
+            for (int i = 0; i < 6; ++i) c.a_off[i] = (uint32_t)(i / 2) * 16 + (uint32_t)(i % 2) * 2 * 8 * sx;
+            c.nmma = 6; c.a_step = 256; c.b_step = 256; c.steps_wrap = 2;
+            return c;
+        };
+        cfgs.push_back(hs("hs  M128 N64  sx 544 sdy 512 (kernel)", 544, 512, 128));
+        cfgs.push_back(hs("hs  M128 N64  sx 576 sdy 512", 576, 512, 128));
+        cfgs.push_back(hs("hs  M128 N64  sx 544 sdy 528", 544, 528, 128));
+        cfgs.push_back(hs("hs  M128 N64  sx 576 sdy 576", 576, 576, 128));
+        cfgs.push_back(hs("hs  M128 N64  sx 560 sdy 560", 560, 560, 128));
+        cfgs.push_back(hs("hs  M128 N64  sx 640 sdy 640", 640, 640, 128));
+        cfgs.push_back(hs("hs  M128 N64  sx 288 sdy 256 (tw 16)", 288, 256, 128));
+        cfgs.push_back(hs("hs  M128 N64  sx 272 sdy 272", 272, 272, 128));
+    }
     for (int nm : {1, 3, 9}) {
         for (int every : {0, 1, 2, 4}) {
             static char nm2[24][64];

@@ -16,6 +16,8 @@ SHAPES = [(16, 16, 3, (4, 32, 128, 128), 2), (32, 16, 3, (4, 32, 128, 128), 1),
           (32, 64, 3, (4, 8, 32, 32), 1), (64, 64, 3, (4, 8, 32, 32), 2), (128, 64, 3, (4, 8, 32, 32), 1),
           (64, 128, 3, (4, 4, 16, 16), 1), (128, 128, 3, (4, 4, 16, 16), 2), (256, 128, 3, (4, 4, 16, 16), 1),
           (128, 256, 3, (4, 2, 8, 8), 1), (256, 256, 3, (4, 2, 8, 8), 1)]
+if os.environ.get("SMALLC"):
+    SHAPES = SHAPES[:4]
 
 
 def graph_time(fn, iters=10):
@@ -39,9 +41,12 @@ def graph_time(fn, iters=10):
 
 
 def main():
-    fn_name = sys.argv[1] if len(sys.argv) > 1 else "fpl_conv3d_wgrad_tc_tapmajor"
+    fn_name = "fpl_conv3d_wgrad_tc_tapmajor"
+    for kv in sys.argv[1:]:          # debug knobs as key=value (fpl_debug_set), e.g. 18=0 (old kernel), 15=16, 17=1
+        k, v = kv.split("=")
+        L.fpl_debug_set(int(k), int(v))
     total = 0.0
-    print("%-30s %9s %9s %9s  (%s)" % ("layer", "us", "TFLOP/s", "x/pass", fn_name))
+    print("%-30s %9s %9s %9s  (%s %s)" % ("layer", "us", "TFLOP/s", "x/pass", fn_name, " ".join(sys.argv[1:])))
     for cin, cout, kd, shape, count in SHAPES:
         n, d, h, w = shape
         x = torch.randn((n, d, cin // 8, h, w, 8), device=DEV).to(torch.bfloat16)
@@ -52,7 +57,7 @@ def main():
         us = graph_time(call)
         gf = 2.0 * n * d * h * w * 27 * cin * cout / 1e9
         total += us * count
-        print("%-30s %9.1f %9.0f %9d" % ("%d->%d %s" % (cin, cout, "x".join(map(str, shape))), us, gf / us / 1e3, count), flush=True)
+        print("%-30s %9.1f %9.0f %9d" % ("%d->%d %s" % (cin, cout, "x".join(map(str, shape))), us, gf / us * 1e-3, count), flush=True)
     print("sum over one backward pass (k3 layers only): %.0f us" % total)
 
 
