@@ -35,6 +35,7 @@ struct DfParams {
     int a_bytes, b_bytes, stages, tmem_cols;
     int pb;                          // input planes per TMA box (= per pipeline stage)
     int tiles_h, tiles_w, total_items;
+    int full_items;                  // items [0, full_items) own dc output planes; the rest are HALF chunks (tail balance)
     int taps;                        // 9 (k 3x3x3) or 1 (k 3x1x1: only the centre in-plane tap)
     int a_ksteps;                    // distinct 16-channel K steps of A (B K step j reads A K step j % a_ksteps)
     EpiAct act;                      // act.scale != NULL: inference epilogue (affine + PReLU) instead of + bias
@@ -57,6 +58,14 @@ struct DfItem {
 
 __device__ __forceinline__ DfItem decode_item(const DfParams& P, int t) {
     DfItem c;
+    // the last (items mod grid) chunks are cut into two half-depth items each, so that the CTAs that would have walked one
+    // more full chunk than the others walk half a chunk more (1024 chunks on 296 CTAs: 3.5 instead of 4 chunk times)
+    int half = -1;
+    if (t >= P.full_items) {
+        const int u = t - P.full_items;
+        half = u & 1;
+        t = P.full_items + (u >> 1);
+    }
     int tw = t % P.tiles_w; t /= P.tiles_w;
     int th = t % P.tiles_h; t /= P.tiles_h;
     int ch = t % P.ndc; t /= P.ndc;
@@ -66,6 +75,11 @@ __device__ __forceinline__ DfItem decode_item(const DfParams& P, int t) {
     c.w0 = tw * kTileW;
     c.d0 = ch * P.dc;
     c.dcount = min(P.dc, P.D - c.d0);
+    if (half >= 0) {
+        const int hd = P.dc / 2;
+        c.d0 += half * hd;
+        c.dcount = max(0, min(hd, c.dcount - half * hd));
+    }
     return c;
 }
 
@@ -126,6 +140,7 @@ __global__ void __launch_bounds__(kThreadsD, 2) conv3d_tc_dfold_kernel(const __g
             int ntr0 = 0, ntr5 = 0;
             for (int t = blockIdx.x; t < P.total_items; t += gridDim.x) {
                 const DfItem c = decode_item(P, t);
+                if (c.dcount == 0) continue;
                 if (c.slice != cur_slice) {
                     // items are ordered slice-major, so a CTA (re)loads the resident weights at most nslices times;
                     // the MMA warp has drained every earlier stage before it waits on w_bar again (see below)
@@ -185,6 +200,7 @@ __global__ void __launch_bounds__(kThreadsD, 2) conv3d_tc_dfold_kernel(const __g
         int ntr1 = 0, ntr2 = 0, ntr4 = 0;
         for (int t = blockIdx.x; t < P.total_items; t += gridDim.x) {
             const DfItem c = decode_item(P, t);
+            if (c.dcount == 0) continue;
             if (c.slice != cur_slice) {
                 cur_slice = c.slice;
                 mbar_wait(w_bar, w_phase);
@@ -275,6 +291,7 @@ __global__ void __launch_bounds__(kThreadsD, 2) conv3d_tc_dfold_kernel(const __g
         float br_dsl = 0.0f;
         for (int t = blockIdx.x; t < P.total_items; t += gridDim.x) {
             const DfItem c = decode_item(P, t);
+            if (c.dcount == 0) continue;
             if ((want_stats || fuse_br) && c.slice != cur_slice) {
                 if (cur_slice >= 0) {
 #pragma unroll
@@ -438,7 +455,7 @@ __global__ void dfold_prep_kernel(const float* __restrict__ w, __nv_bfloat16* im
     }
 }
 
-int g_df_ctas = 0, g_df_dc = 0, g_df_epi = 0, g_df_stages = 0, g_df_nomma = 0, g_df_tma = 0, g_df_pb = 0;   // fpl_debug_set 40..47
+int g_df_ctas = 0, g_df_dc = 0, g_df_epi = 0, g_df_stages = 0, g_df_nomma = 0, g_df_tma = 0, g_df_pb = 0, g_df_split_tail = 1;   // fpl_debug_set 40..48
 long long* g_df_trace = nullptr;
 
 struct DfCfg {
@@ -465,6 +482,8 @@ bool make_df_cfg(int cin, int cout, int d, DfCfg& c, int taps = 9, int cin_a = 0
     if (c.tmem_cols > 512) return false;
     // pb input planes per TMA box / pipeline stage; as many stages (2..4) as keep two CTAs per SM, else what fits one
     c.pb = g_df_pb > 0 ? g_df_pb : (c.a_bytes <= 2 * kPlaneBytes ? 3 : 2);      // measured: tools/dfold_knob_probe.py pb
+    // (ONE commit per box -- the producer waiting on the epilogue's plane barriers instead of its own empty barriers --
+    //  was measured SLOWER for the Cin 16 layers: 16 -> 16 41.5 -> 46.3 us, pb 1: 47.0 -> 55.7 us; kept two barriers)
     const int fixed = c.b_bytes + 1024 + 512 + 4 * cout * (int)sizeof(float) + 16;
     c.stages = 0;
     for (int s = c.pb == 1 ? 6 : 4; s >= 2 && c.stages == 0; --s)
@@ -493,6 +512,7 @@ void fpl_dfold_debug_knob(int key, long long value) {
     if (key == 44) g_df_nomma = (int)value;
     if (key == 45) g_df_tma = (int)value;
     if (key == 46) g_df_pb = (int)value;
+    if (key == 48) g_df_split_tail = (int)value;
     if (key == 47) g_df_trace = reinterpret_cast<long long*>(value);
 }
 
@@ -619,14 +639,19 @@ static int dfold_launch(const void* x, int x_c8tot, int x_c8off, const void* ima
     P.a_bytes = c.a_bytes; P.b_bytes = c.b_bytes; P.stages = c.stages; P.tmem_cols = c.tmem_cols; P.pb = c.pb;
     P.tiles_h = (h + kTileH - 1) / kTileH; P.tiles_w = (w + kTileW - 1) / kTileW;
     int64_t total = (int64_t)P.tiles_h * P.tiles_w * P.ndc * n * c.nslices;
-    FPL_REQUIRE(total < (1ll << 30), "fpl_conv3d_tc_dfold: too many items");
-    P.total_items = (int)total;
+    FPL_REQUIRE(total < (1ll << 29), "fpl_conv3d_tc_dfold: too many items");
+    int grid = FPL_NUM_SMS * c.ctas_per_sm;
+    if (grid > total) grid = (int)total;
+    // tail balance: when the chunks do not divide over the CTAs, the last (chunks mod grid) chunks become two half-depth
+    // items each if both halves still fit one extra round (see decode_item); single-slice layers only
+    P.full_items = (int)total;
+    const int rem = (int)(total % grid);
+    if (g_df_split_tail && rem > 0 && 2 * rem <= grid && c.dc >= 8 && c.dc % 2 == 0 && d % c.dc == 0 && c.nslices == 1) P.full_items = (int)total - rem;
+    P.total_items = P.full_items + 2 * ((int)total - P.full_items);
     P.taps = taps; P.a_ksteps = cin_a / 16;
     P.dbg_epi = g_df_epi; P.dbg_nomma = g_df_nomma; P.dbg_tma = g_df_tma; P.dbg_trace = g_df_trace;
     if (br != nullptr) P.br = *br; else { P.br.y = nullptr; P.br.scale = P.br.shift = P.br.mean = P.br.invstd = P.br.slope = nullptr; P.br.drop_p = 0.0f; P.br.seed = P.br.offset = 0; P.br.seed_dev = nullptr; P.br.red = nullptr; }
     if (act != nullptr) P.act = *act; else { P.act.scale = nullptr; P.act.shift = nullptr; P.act.slope = nullptr; P.act.drop_p = 0.0f; P.act.seed = P.act.offset = 0; P.act.seed_dev = nullptr; }
-    int grid = FPL_NUM_SMS * c.ctas_per_sm;
-    if (grid > P.total_items) grid = P.total_items;
     if (c.nb == 16) {
         FPL_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_dfold_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
         fpl_launch(conv3d_tc_dfold_kernel<1>, grid, kThreadsD, c.smem_bytes, (cudaStream_t)stream, xmap, P);

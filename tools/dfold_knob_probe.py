@@ -27,6 +27,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "stages":
 if len(sys.argv) > 1 and sys.argv[1] == "pb":
     VARIANTS = [("pb%d" % k, {46: k}) for k in (1, 2, 3, 6)] + [("lo pb%d" % k, {**LOADONLY, 46: k}) for k in (1, 2, 3, 6)] + \
                [("pb2 s%d" % k, {46: 2, 43: k}) for k in (2, 3, 4)] + [("pb3 s%d" % k, {46: 3, 43: k}) for k in (2, 3)] + [("noepi pb2", {42: 2, 46: 2})]
+if len(sys.argv) > 1 and sys.argv[1] == "tail":
+    VARIANTS = [("split tail", {}), ("no split", {48: 0}), ("pb2", {46: 2}), ("pb2 no split", {46: 2, 48: 0}), ("pb1 no split", {46: 1, 48: 0})]
 if len(sys.argv) > 1 and sys.argv[1] == "round1":
     VARIANTS = [("base", {}), ("1cta", {40: 1}), ("dc8", {41: 8}), ("nostore", {42: 1}), ("noepi", {42: 2}), ("nomma", {44: 1}),
                 ("nomma+noepi", {44: 1, 42: 2}), ("stages8", {43: 8}), ("stages3", {43: 3}), ("1cta+noepi", {40: 1, 42: 2})]
@@ -46,6 +48,7 @@ def probe(cin, cout, shape, with_stats):
     for name, knobs in VARIANTS:
         for k in (40, 41, 42, 43, 44, 45, 46):
             L.fpl_debug_set(k, 0)
+        L.fpl_debug_set(48, 1)
         for k, v in knobs.items():
             L.fpl_debug_set(k, v)
         try:
