@@ -188,9 +188,11 @@ WORK = {   # entry point -> (flops, algorithmic bytes) from its argument tuple
     "fpl_conv3d_wgrad_tc_k311": lambda a: _k311_work(a, 7),
 }
 # entry points that launch the SAME kernel are one roofline population (the ncu capture sees kernel names):
-# conv3d_wgrad_tc_kernel serves the k3 / k(1,3,3) wgrads, the head wgrad and the stem's k(3,1,1) wgrad
-KERNEL_OF = {"fpl_conv3d_wgrad_tc_tapmajor": "conv3d_wgrad_tc_kernel", "fpl_conv3d_wgrad_tc": "conv3d_wgrad_tc_kernel",
-             "fpl_conv3d_wgrad_tc_k311": "conv3d_wgrad_tc_kernel", "fpl_conv3d_tc": "conv3d_tc_kernel",
+# the wgrad entry points launch conv3d_wgrad_hs_kernel (k3, Cin 16 / 32: levels 0-1) or conv3d_wgrad_tc_kernel (the other
+# k3 / k(1,3,3) wgrads, the head wgrad and the stem's k(3,1,1) wgrad): ONE population, the weight-gradient kernels
+WGRAD_KERNELS = "conv3d_wgrad_hs_kernel+conv3d_wgrad_tc_kernel"
+KERNEL_OF = {"fpl_conv3d_wgrad_tc_tapmajor": WGRAD_KERNELS, "fpl_conv3d_wgrad_tc": WGRAD_KERNELS,
+             "fpl_conv3d_wgrad_tc_k311": WGRAD_KERNELS, "fpl_conv3d_tc": "conv3d_tc_kernel",
              "fpl_conv3d_tc_dfold": "conv3d_tc_dfold_kernel"}
 
 

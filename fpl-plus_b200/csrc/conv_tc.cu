@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
         // descriptors = constant high part + (smem byte address >> 4) in the low 14 bits
         const uint64_t a_hi = make_desc(0, a_lbo, a_sbo), b_hi = make_desc(0, b_lbo, b_sbo);
         const uint32_t smem_u = smem_u32(smem) >> 4;
-        const uint32_t b_tap_step = (uint32_t)((P.kc / 8) * P.nb);        // 16-byte units between taps of B
-        const uint32_t b_k_step = (uint32_t)(2 * P.nb);                   // ... between 16-channel K steps
+        const uint64_t b_tap_step = (uint64_t)((P.kc / 8) * P.nb);        // 16-byte units between taps of B
+        const uint64_t b_k_step = (uint64_t)(2 * P.nb);                   // ... between 16-channel K steps
         const int ksteps = P.kc / 16;
         const bool leader = elect_one();
         int stage = 0; uint32_t phase = 0;
@@ -204,16 +204,20 @@ __global__ void __launch_bounds__(kNumThreads) conv3d_tc_kernel(const __grid_con
                     tc_fence_after();
                     const uint32_t a_base = smem_u + (uint32_t)(((size_t)stage * stage_bytes) >> 4);
                     const uint32_t b_base = a_base + (uint32_t)(P.a_bytes >> 4);
+                    // descriptor arithmetic as 64-bit adds of warp-uniform values (the 14-bit start-address field never
+                    // carries): stays on the uniform datapath instead of per-thread IMAD / LOP3 + R2UR moves per MMA
+                    uint64_t a_j = a_hi + (uint64_t)a_base, b_j = b_hi + (uint64_t)b_base;
                     for (int j = 0; j < ksteps; ++j) {
-                        const uint32_t a_j = a_base + (uint32_t)j * (2 * kPlaneBytes / 16);
-                        const uint32_t b_j = b_base + (uint32_t)j * b_k_step;
+                        uint64_t bdesc = b_j;
 #pragma unroll
                         for (int t9 = 0; t9 < 9; ++t9) {
-                            const uint64_t adesc = a_hi | (uint64_t)(a_j + (uint32_t)((t9 / 3) * kBoxW + (t9 % 3)));
-                            const uint64_t bdesc = b_hi | (uint64_t)(b_j + (uint32_t)t9 * b_tap_step);
+                            const uint64_t adesc = a_j + (uint64_t)((t9 / 3) * kBoxW + (t9 % 3));
                             if (leader) umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
                             accumulate = 1;
+                            bdesc += b_tap_step;
                         }
+                        a_j += 2 * kPlaneBytes / 16;
+                        b_j += b_k_step;
                     }
                     if (leader) umma_commit(&empty_bar[stage]);      // smem slot reusable once these MMAs retire
                     __syncwarp();

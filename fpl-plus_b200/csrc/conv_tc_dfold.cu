@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(kThreadsD, 2) conv3d_tc_dfold_kernel(const __g
         const uint64_t b_hi = make_desc(0, (uint32_t)(3 * P.nb) * 16, 128);
         const uint32_t b_u = smem_u32(b_sm) >> 4, ring_u = smem_u32(ring) >> 4;
         const int ksteps = P.cin / 16;
-        const uint32_t b_kstep = (uint32_t)(2 * 3 * P.nb);             // 16-byte units per 16-channel K step
-        const uint32_t b_tap = (uint32_t)ksteps * b_kstep;
+        const uint64_t b_kstep = (uint64_t)(2 * 3 * P.nb);             // 16-byte units per 16-channel K step
+        const uint64_t b_tap = (uint64_t)ksteps * b_kstep;
         const bool leader = elect_one();
         int stage = 0; uint32_t phase = 0;
         uint32_t item_phase = 0, w_phase = 0;
@@ -225,15 +225,20 @@ __global__ void __launch_bounds__(kThreadsD, 2) conv3d_tc_dfold_kernel(const __g
                         const uint32_t d_tmem = tmem_base + (uint32_t)(r - 1 + jlo) * (uint32_t)P.nb;
                         const uint32_t a_base = ring_u + (((uint32_t)stage * stage_bytes + (uint32_t)(q * P.a_bytes)) >> 4);
                         const uint32_t b_base = b_u + (uint32_t)(jlo * P.nb);
-                        for (int j = 0; j < ksteps; ++j) {
-                            const uint32_t a_j = a_base + (uint32_t)(j % P.a_ksteps) * (2 * kPlaneBytes / 16);
-                            const uint32_t b_j = b_base + (uint32_t)j * b_kstep;
+                        // 64-bit adds of warp-uniform values (the 14-bit start-address field never carries): the descriptor
+                        // arithmetic stays on the uniform datapath (hi | uint32 expressions cost ~10 instructions per MMA)
+                        uint64_t b_j = b_hi + (uint64_t)b_base;
+                        for (int j = 0; j < ksteps; ++j, b_j += b_kstep) {
+                            const uint64_t a_j = a_hi + (uint64_t)(a_base + (uint32_t)(j % P.a_ksteps) * (2 * kPlaneBytes / 16));
+                            if (P.taps == 1) {
+                                if (leader && !P.dbg_nomma) umma_bf16(d_tmem, a_j + (uint64_t)(kBoxW + 1), b_j, idesc, 1u);
+                            } else {
+                                uint64_t bdesc = b_j;
 #pragma unroll
-                            for (int t9 = 0; t9 < 9; ++t9) {
-                                if (P.taps == 1 && t9 != 4) continue;
-                                const uint64_t adesc = a_hi | (uint64_t)(a_j + (uint32_t)((t9 / 3) * kBoxW + (t9 % 3)));
-                                const uint64_t bdesc = b_hi | (uint64_t)(b_j + (uint32_t)(P.taps == 1 ? 0 : t9) * b_tap);
-                                if (leader && !P.dbg_nomma) umma_bf16(d_tmem, adesc, bdesc, idesc, 1u);
+                                for (int t9 = 0; t9 < 9; ++t9, bdesc += b_tap) {
+                                    const uint64_t adesc = a_j + (uint64_t)((t9 / 3) * kBoxW + (t9 % 3));
+                                    if (leader && !P.dbg_nomma) umma_bf16(d_tmem, adesc, bdesc, idesc, 1u);
+                                }
                             }
                         }
                     }

@@ -113,48 +113,61 @@ __global__ void __launch_bounds__(kThreadsH) conv3d_wgrad_hs_kernel(const __grid
         const uint32_t idesc64 = idesc0 | ((uint32_t)(64 >> 3) << 17), idesc32 = idesc0 | ((uint32_t)(32 >> 3) << 17);
         // LBO = stride of the two 8-voxel core matrices of a K step (contiguous in the row), SBO = slab stride
         const uint64_t a_hi = make_desc(0, 128u, (uint32_t)P.sx), b_hi = make_desc(0, 128u, (uint32_t)P.sdy);
-        const uint32_t xrow = (uint32_t)(4 * P.G * P.sx) >> 4, dyrow = (uint32_t)(4 * P.sdy) >> 4;   // row pitch, 16-byte units
+        // All descriptor arithmetic below is 64-bit ADDs of warp-uniform values (the start-address field is the low 14
+        // bits and never carries): the compiler keeps it on the uniform datapath, 2-3 instructions per MMA.  Building each
+        // descriptor as hi | (uint32 expression) cost ~12 per-thread instructions + R2UR moves per MMA and made the issuing
+        // warp, not the tensor pipe, the limit (67-78 cycles per 48-cycle MMA).
+        const uint64_t xrow = (uint64_t)((uint32_t)(4 * P.G * P.sx) >> 4), dyrow = (uint64_t)((uint32_t)(4 * P.sdy) >> 4);   // row pitch, 16-byte units
         const uint32_t ring_u = smem_u32(ring);
         const bool leader = elect_one() && !(P.dbg & 1);
         const bool committer = elect_one();
+        // per-MMA constants of a K step
+        uint64_t a_off[12];
+        uint32_t d_col[12];
+        if (P.G == 2) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { a_off[k] = (uint64_t)(k & 1) * 2 * xrow + (uint64_t)(k >> 1); d_col[k] = tmem_base + (uint32_t)(k * 64); }
+#pragma unroll
+            for (int k = 6; k < 12; ++k) { a_off[k] = 0; d_col[k] = 0; }
+        } else {
+            // x row 2i-1+q (tile row 2i+q) against dy rows {2i, 2i+1}: row tap kh = q - b_h; column block = 2 - kh
+            //   q=0: kh 0 of row 2i (N 32, block 2) | q=1: kh 1 | kh 0 (N 64, blocks 1-2) | q=2: kh 2 | kh 1 (N 64, blocks 0-1)
+            //   q=3: kh 2 of row 2i+1 (N 32, block 0, B = dy row 2i+1)
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const int kw = k >> 2, q = k & 3;
+                a_off[k] = (uint64_t)q * xrow + (uint64_t)kw;
+                d_col[k] = tmem_base + (uint32_t)(kw * 96 + (q == 0 ? 64 : (q == 1 ? 32 : 0)));
+            }
+        }
         int stage = 0; uint32_t phase = 0;
         mbar_wait(zero_bar, 0);
         tc_fence_after();
+        const int nsteps_s = P.tw / 16, nsteps_i = P.th / 2;
         for (int t = tile_begin; t < tile_end; ++t) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t x_u = (ring_u + (uint32_t)stage * (uint32_t)P.stage_bytes) >> 4;
-            const uint32_t dy_u = x_u + ((uint32_t)P.dy_off >> 4);
-            for (int i = 0; i < P.th / 2; ++i) {
-                for (int s = 0; s < P.tw / 16; ++s) {
-                    const uint32_t b_addr = dy_u + (uint32_t)(2 * i) * dyrow + (uint32_t)s * 16;
-                    const uint64_t bdesc = b_hi | (uint64_t)b_addr;
-                    const uint32_t a_seg = x_u + (uint32_t)s * 16;
+            uint64_t a_i = a_hi + (uint64_t)x_u;
+            uint64_t b_i = b_hi + (uint64_t)(x_u + ((uint32_t)P.dy_off >> 4));
+            for (int i = 0; i < nsteps_i; ++i) {
+                uint64_t a_s = a_i, b_s = b_i;
+                for (int s = 0; s < nsteps_s; ++s) {
                     if (P.G == 2) {
 #pragma unroll
-                        for (int kw = 0; kw < 3; ++kw) {
-#pragma unroll
-                            for (int j = 0; j < 2; ++j) {
-                                const uint64_t adesc = a_hi | (uint64_t)(a_seg + (uint32_t)(2 * i + 2 * j) * xrow + (uint32_t)kw);
-                                if (leader) umma_bf16(tmem_base + (uint32_t)((kw * 2 + j) * 64), adesc, bdesc, idesc64, 1u);
-                            }
-                        }
+                        for (int k = 0; k < 6; ++k)
+                            if (leader) umma_bf16(d_col[k], a_s + a_off[k], b_s, idesc64, 1u);
                     } else {
-                        const uint64_t bdesc1 = b_hi | (uint64_t)(b_addr + dyrow);          // dy row 2i+1 alone
+                        const uint64_t b_s1 = b_s + dyrow;                                  // dy row 2i+1 alone
 #pragma unroll
-                        for (int kw = 0; kw < 3; ++kw) {
-                            const uint32_t a0 = a_seg + (uint32_t)(2 * i) * xrow + (uint32_t)kw;
-                            const uint32_t d0 = tmem_base + (uint32_t)(kw * 96);
-                            if (leader) {
-                                // x row 2i-1+q (tile row 2i+q) against dy rows {2i, 2i+1}: row tap kh = q - b_h; column block = 2 - kh
-                                umma_bf16(d0 + 64, a_hi | (uint64_t)a0, bdesc, idesc32, 1u);                 // q=0: kh 0 of row 2i
-                                umma_bf16(d0 + 32, a_hi | (uint64_t)(a0 + xrow), bdesc, idesc64, 1u);        // q=1: kh 1 | kh 0
-                                umma_bf16(d0, a_hi | (uint64_t)(a0 + 2 * xrow), bdesc, idesc64, 1u);         // q=2: kh 2 | kh 1
-                                umma_bf16(d0, a_hi | (uint64_t)(a0 + 3 * xrow), bdesc1, idesc32, 1u);        // q=3: kh 2 of row 2i+1
-                            }
+                        for (int k = 0; k < 12; ++k) {
+                            const int q = k & 3;
+                            if (leader) umma_bf16(d_col[k], a_s + a_off[k], q == 3 ? b_s1 : b_s, (q == 0 || q == 3) ? idesc32 : idesc64, 1u);
                         }
                     }
+                    a_s += 16; b_s += 16;
                 }
+                a_i += 2 * xrow; b_i += 2 * dyrow;
             }
             if (committer) umma_commit(&empty_bar[stage]);
             __syncwarp();

@@ -193,6 +193,9 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
         uint32_t tap_off[9];                                  // (kh*pitch + kw*16) >> 4
 #pragma unroll
         for (int t9 = 0; t9 < 9; ++t9) tap_off[t9] = ((uint32_t)(t9 / 3) * pitch_x + (uint32_t)(t9 % 3) * 16) >> 4;
+        uint32_t d_tap[9];
+#pragma unroll
+        for (int t9 = 0; t9 < 9; ++t9) d_tap[t9] = tmem_base + (uint32_t)(t9 * P.ncols);
         const uint32_t ring_u = smem_u32(ring);
         const bool leader = elect_one();
         int stage = 0; uint32_t phase = 0;
@@ -205,14 +208,15 @@ __global__ void __launch_bounds__(kThreadsW) conv3d_wgrad_tc_kernel(const __grid
             for (int hp = 0; hp < P.th / 2; ++hp) {
                 const uint32_t a_row = x_base + (((uint32_t)(2 * hp) * pitch_x) >> 4);
                 const uint32_t b_row = dy_base + (((uint32_t)(2 * hp) * pitch_dy) >> 4);
-                for (int j = 0; j < P.tw / 8; ++j) {
-                    const uint64_t bdesc = b_hi | (uint64_t)(b_row + (uint32_t)j * 8);
-                    const uint32_t a_col = a_row + (uint32_t)j * 8;
+                // 64-bit adds of warp-uniform values (the 14-bit start-address field never carries): uniform datapath
+                uint64_t bdesc = b_hi + (uint64_t)b_row, a_col = a_hi + (uint64_t)a_row;
+                for (int j = 0; j < P.tw / 8; ++j, bdesc += 8, a_col += 8) {
+                    if (P.taps == 1) {
+                        if (leader) umma_bf16(tmem_base, a_col + (uint64_t)tap_off[4], bdesc, idesc, accumulate);
+                    } else {
 #pragma unroll
-                    for (int t9 = 0; t9 < 9; ++t9) {
-                        if (P.taps == 1 && t9 != 4) continue;
-                        const uint64_t adesc = a_hi | (uint64_t)(a_col + tap_off[t9]);
-                        if (leader) umma_bf16(tmem_base + (uint32_t)((P.taps == 1 ? 0 : t9) * P.ncols), adesc, bdesc, idesc, accumulate);
+                        for (int t9 = 0; t9 < 9; ++t9)
+                            if (leader) umma_bf16(d_tap[t9], a_col + (uint64_t)tap_off[t9], bdesc, idesc, accumulate);
                     }
                     accumulate = 1;
                 }

@@ -152,9 +152,10 @@ __global__ void __launch_bounds__(kThreadsT) convt_gemm_tc_kernel(const __grid_c
                 tc_fence_after();
                 const uint32_t a_base = smem_u + (uint32_t)(((size_t)stage * stage_bytes) >> 4);
                 const uint32_t b_base = a_base + (uint32_t)(P.a_bytes >> 4);
-                for (int j = 0; j < ksteps; ++j) {
-                    const uint64_t adesc = a_hi | (uint64_t)(a_base + (uint32_t)j * (2 * kPlane / 16));
-                    const uint64_t bdesc = b_hi | (uint64_t)(b_base + (uint32_t)j * (uint32_t)(2 * P.nb));
+                // 64-bit adds of warp-uniform values (the 14-bit start-address field never carries): uniform datapath
+                uint64_t adesc = a_hi + (uint64_t)a_base, bdesc = b_hi + (uint64_t)b_base;
+                const uint64_t b_step = (uint64_t)(2 * P.nb);
+                for (int j = 0; j < ksteps; ++j, adesc += 2 * kPlane / 16, bdesc += b_step) {
                     if (leader) umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
                     accumulate = 1;
                 }
@@ -343,12 +344,14 @@ __global__ void __launch_bounds__(kThreadsT) convt_wgrad_tc_kernel(const __grid_
             tc_fence_after();
             const uint32_t x_base = (ring_u + (uint32_t)stage * (uint32_t)P.stage_bytes) >> 4;
             const uint32_t dy_base = x_base + ((uint32_t)P.x_bytes >> 4);
-            for (int hp = 0; hp < kTH / 2; ++hp) {
-                const uint64_t adesc = hi | (uint64_t)(x_base + (uint32_t)hp * (2 * kTW * 16 / 16));
-                for (int tap = 0; tap < P.ntaps; ++tap) {
-                    const uint64_t bdesc = hi | (uint64_t)(dy_base + (uint32_t)tap * ((uint32_t)P.dy_tile_bytes >> 4) +
-                                                           (uint32_t)hp * (2 * kTW * 16 / 16));
-                    if (leader) umma_bf16(tmem_base + (uint32_t)(tap * P.nb), adesc, bdesc, idesc, accumulate);
+            // 64-bit adds of warp-uniform values (the 14-bit start-address field never carries): uniform datapath
+            uint64_t adesc = hi + (uint64_t)x_base, b_hp = hi + (uint64_t)dy_base;
+            const uint64_t dy_tile16 = (uint64_t)((uint32_t)P.dy_tile_bytes >> 4);
+            for (int hp = 0; hp < kTH / 2; ++hp, adesc += 2 * kTW * 16 / 16, b_hp += 2 * kTW * 16 / 16) {
+                uint64_t bdesc = b_hp;
+                uint32_t d_tap = tmem_base;
+                for (int tap = 0; tap < P.ntaps; ++tap, bdesc += dy_tile16, d_tap += (uint32_t)P.nb) {
+                    if (leader) umma_bf16(d_tap, adesc, bdesc, idesc, accumulate);
                 }
                 accumulate = 1;
             }
