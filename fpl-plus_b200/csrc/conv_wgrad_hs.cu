@@ -267,6 +267,179 @@ __global__ void __launch_bounds__(kThreadsH) conv3d_wgrad_hs_kernel(const __grid
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Row-stacked weight gradient of the k(1,3,3) HEAD conv (Cin 16, the classes padded to one channel group of 8): no depth
+// taps, so the ROWS are stacked instead of the planes.  Tiles land as [plane][row][channel group][voxel] (tensor-map
+// dimensions (w, c8, h, d, n)); per K step of 16 voxels one MMA per column tap kw:
+//   A = x rows R..R+7 (M = 128 = 8 rows x 16 ci), B = dy rows R..R+5 (N = 48 = 6 rows x 8 co): block (q, b) is row tap
+//   kh = q - b, 18 of the 48 blocks are taps; 3 MMAs of 44 cycles per 96 voxels (the plane-stacked form of
+//   conv3d_wgrad_tc_kernel: 9 MMAs of 30.5 cycles per 64 voxels, 4 of 16 blocks useful).  The planes of a tile are more K.
+struct RsParams {
+    float* dw;
+    int N, D, H, W, x_c8off, dy_c8off;
+    int th, tw, planes;            // tile rows (multiple of 6), columns (16 / 32), planes per tile
+    int sx, sdy, x_plane, dy_plane, dy_off, stage_bytes, stages;
+    int tiles_h, tiles_w, dsteps, tiles_total, split;
+    int tapmajor, skip_epilogue;
+};
+
+__global__ void __launch_bounds__(kThreadsH) conv3d_wgrad_rs_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                                   const __grid_constant__ CUtensorMap dymap, RsParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kMaxStagesH;
+    uint64_t* done_bar = bars + 2 * kMaxStagesH;
+    uint64_t* zero_bar = bars + 2 * kMaxStagesH + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStagesH + 2);
+    uint8_t* ring = smem + 256;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slice = blockIdx.x;
+    const int tile_begin = (int)(((int64_t)P.tiles_total * slice) / P.split);
+    const int tile_end = (int)(((int64_t)P.tiles_total * (slice + 1)) / P.split);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&dymap) : "memory");
+        for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(done_bar, 1);
+        mbar_init(zero_bar, 4);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 256u);
+    FPL_PDL_WAIT();      // prologue above overlapped the previous kernel's tail; from here on its results are visible
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = tile_begin; t < tile_end; ++t) {
+                int r = t;
+                const int dp = r % P.dsteps; r /= P.dsteps;
+                const int tw_i = r % P.tiles_w; r /= P.tiles_w;
+                const int th_i = r % P.tiles_h;
+                const int n = r / P.tiles_h;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* x_dst = ring + (size_t)stage * P.stage_bytes;
+                mbar_expect_tx(&full_bar[stage], (uint32_t)(P.planes * (P.x_plane + P.dy_plane)));
+                // map dimensions (w in 8-byte units, c8, h, d, n); rows / columns / planes outside the volume: zero fill
+                tma_load_5d(x_dst, &xmap, &full_bar[stage], 2 * (tw_i * P.tw - 1), P.x_c8off, th_i * P.th - 1, dp * P.planes, n);
+                tma_load_5d(x_dst + P.dy_off, &dymap, &full_bar[stage], 2 * (tw_i * P.tw), P.dy_c8off, th_i * P.th, dp * P.planes, n);
+                if (++stage == P.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // kind::f16, bf16 x bf16 -> fp32, A and B MN-major, M = 128, N = 48
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(48 >> 3) << 17) |
+                               ((uint32_t)(128 >> 4) << 24);
+        const uint64_t a_hi = make_desc(0, 128u, (uint32_t)P.sx), b_hi = make_desc(0, 128u, (uint32_t)P.sdy);
+        const uint64_t xrow6 = (uint64_t)((uint32_t)(6 * 2 * P.sx) >> 4), dyrow6 = (uint64_t)((uint32_t)(6 * P.sdy) >> 4);
+        const uint64_t xpl = (uint64_t)((uint32_t)P.x_plane >> 4), dypl = (uint64_t)((uint32_t)P.dy_plane >> 4);
+        const uint32_t ring_u = smem_u32(ring);
+        const bool leader = elect_one();
+        int stage = 0; uint32_t phase = 0;
+        mbar_wait(zero_bar, 0);
+        tc_fence_after();
+        const int nsteps_s = P.tw / 16, nsteps_r = P.th / 6;
+        for (int t = tile_begin; t < tile_end; ++t) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t x_u = (ring_u + (uint32_t)stage * (uint32_t)P.stage_bytes) >> 4;
+            uint64_t a_p = a_hi + (uint64_t)x_u;
+            uint64_t b_p = b_hi + (uint64_t)(x_u + ((uint32_t)P.dy_off >> 4));
+            for (int p = 0; p < P.planes; ++p, a_p += xpl, b_p += dypl) {
+                uint64_t a_r = a_p, b_r = b_p;
+                for (int r6 = 0; r6 < nsteps_r; ++r6, a_r += xrow6, b_r += dyrow6) {
+                    uint64_t a_s = a_r, b_s = b_r;
+                    for (int s = 0; s < nsteps_s; ++s, a_s += 16, b_s += 16) {
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw)
+                            if (leader) umma_bf16(tmem_base + (uint32_t)(kw * 48), a_s + (uint64_t)kw, b_s, idesc, 1u);
+                    }
+                }
+            }
+            if (leader) umma_commit(&empty_bar[stage]);
+            __syncwarp();
+            if (++stage == P.stages) { stage = 0; phase ^= 1; }
+        }
+        if (leader) umma_commit(done_bar);
+        __syncwarp();
+        FPL_PDL_TRIGGER();
+    } else {
+        const int quarter = warp & 3;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        for (int col = 0; col < 144; col += 16) tmem_st_zero16_hs(lane_base + (uint32_t)col);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(zero_bar);
+        if (tile_end > tile_begin) {
+            mbar_wait(done_bar, 0);
+            tc_fence_after();
+            float* acc_sm = reinterpret_cast<float*>(ring);                   // [9 taps][8 co][16 ci]; the ring is free now
+            const int et = threadIdx.x - 64;
+            for (int e = et; e < 1152; e += 128) acc_sm[e] = 0.0f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int L = quarter * 32 + lane;
+            const int q = L >> 4, ci = L & 15;                                 // x row of the stack, input channel
+            // one phase per dy row b of the stack: for a fixed b every (lane, kw) is a different tap
+#pragma unroll 1
+            for (int m = 0; m < 3; ++m) {
+                uint32_t r[3][16];
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) tmem_ld16(lane_base + (uint32_t)(kw * 48 + m * 16), r[kw]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int kh = q - (2 * m + half);
+                    if (kh >= 0 && kh <= 2) {
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw) {
+                            float* dst = acc_sm + ((kh * 3 + kw) * 8) * 16 + ci;
+#pragma unroll
+                            for (int co = 0; co < 8; ++co) dst[co * 16] += __uint_as_float(r[kw][half * 8 + co]);
+                        }
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+            }
+            if (!P.skip_epilogue) {
+                for (int e = et; e < 1152; e += 128) {
+                    if (P.tapmajor) atomicAdd(P.dw + e, acc_sm[e]);            // S[tap][8][16]
+                    else {
+                        const int tap = e >> 7, co = (e >> 4) & 7, c = e & 15;
+                        atomicAdd(P.dw + (co * 16 + c) * 9 + tap, acc_sm[e]);   // [8][16][1][3][3]
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256u);
+    }
+}
+
+// tensor map with dimensions ordered (w [8-byte units], c8, h, d, n): a box lands as [plane][row][channel group][voxel]
+CUresult encode_rs(EncodeTiledFn encode, CUtensorMap* map, const void* base, int n, int d, int c8tot, int h, int w, int box_w,
+                   int box_c8, int box_h, int box_d) {
+    cuuint64_t gdim[5] = {(cuuint64_t)w * 2, (cuuint64_t)c8tot, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
+    cuuint64_t gstr[4] = {(cuuint64_t)h * w * 16, (cuuint64_t)w * 16, (cuuint64_t)c8tot * h * w * 16,
+                          (cuuint64_t)d * c8tot * h * w * 16};
+    cuuint32_t box[5] = {(cuuint32_t)box_w * 2, (cuuint32_t)box_c8, (cuuint32_t)box_h, (cuuint32_t)box_d, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
 // tensor map over the C8-planar activation with dimensions ordered (w [8-byte units], c8, d, h, n): a box lands as
 // [row][plane][channel group][voxel]
 CUresult encode_hs(EncodeTiledFn encode, CUtensorMap* map, const void* base, int n, int d, int c8tot, int h, int w, int box_w,
@@ -327,6 +500,49 @@ int fpl_wgrad_hs_launch(const void* x, int x_c8tot, int x_c8off, const void* dy,
     FPL_REQUIRE(r == CUDA_SUCCESS, "fpl_conv3d_wgrad_tc: tensor map (dy, h-stacked) failed (%d)", (int)r);
     FPL_CHECK_CUDA(cudaFuncSetAttribute(conv3d_wgrad_hs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     fpl_launch(conv3d_wgrad_hs_kernel, P.nchunks * split, kThreadsH, smem_bytes, (cudaStream_t)stream, xmap, dymap, P);
+    FPL_LAUNCH_CHECK();
+    return 0;
+}
+
+bool fpl_wgrad_rs_eligible(int d, int h, int w, int cin, int cout, int kd, int taps) {
+    return kd == 1 && taps == 9 && cin == 16 && cout == 8 && h >= 6 && w >= 16 && d >= 1;
+}
+
+/* k(1,3,3), Cin 16, Cout 8 (the head); dw = S[9][8][16] (tapmajor) or [8][16][1][3][3], ACCUMULATED into */
+int fpl_wgrad_rs_launch(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off, float* dw, int n,
+                        int d, int h, int w, void* stream, int tapmajor, int skip_epilogue) {
+    RsParams P;
+    P.dw = dw; P.N = n; P.D = d; P.H = h; P.W = w; P.x_c8off = x_c8off; P.dy_c8off = dy_c8off;
+    P.th = h >= 12 ? 12 : 6;
+    P.tw = w >= 32 ? 32 : 16;
+    P.planes = d >= 2 ? 2 : 1;
+    P.sx = (P.tw + 2) * 16; P.sdy = P.tw * 16;
+    P.x_plane = (P.th + 2) * 2 * P.sx; P.dy_plane = P.th * P.sdy;
+    P.dy_off = ((P.planes * P.x_plane + 127) / 128) * 128;
+    P.stage_bytes = ((P.dy_off + P.planes * P.dy_plane + 127) / 128) * 128;
+    P.stages = (kSmemBudgetH - 2048) / P.stage_bytes;
+    if (P.stages > kMaxStagesH) P.stages = kMaxStagesH;
+    FPL_REQUIRE(P.stages >= 2, "fpl_conv3d_wgrad_tc: row-stacked tile does not fit (%d bytes per stage)", P.stage_bytes);
+    const int smem_bytes = P.stages * P.stage_bytes + 1024 + 256;
+    P.tiles_h = (h + P.th - 1) / P.th; P.tiles_w = (w + P.tw - 1) / P.tw; P.dsteps = (d + P.planes - 1) / P.planes;
+    const int64_t tiles = (int64_t)P.tiles_h * P.tiles_w * P.dsteps * n;
+    FPL_REQUIRE(tiles < (1ll << 30), "fpl_conv3d_wgrad_tc: too many tiles");
+    P.tiles_total = (int)tiles;
+    int split = FPL_NUM_SMS;
+    if (split > P.tiles_total) split = P.tiles_total;
+    P.split = split;
+    P.tapmajor = tapmajor; P.skip_epilogue = skip_epilogue;
+    FPL_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0,
+                "fpl_conv3d_wgrad_tc: x/dy must be 16-byte aligned");
+    EncodeTiledFn encode = get_encode_fn();
+    FPL_REQUIRE(encode != nullptr, "fpl_conv3d_wgrad_tc: cuTensorMapEncodeTiled not available from the driver");
+    CUtensorMap xmap, dymap;
+    CUresult r = encode_rs(encode, &xmap, x, n, d, x_c8tot, h, w, P.tw + 2, 2, P.th + 2, P.planes);
+    FPL_REQUIRE(r == CUDA_SUCCESS, "fpl_conv3d_wgrad_tc: tensor map (x, row-stacked) failed (%d)", (int)r);
+    r = encode_rs(encode, &dymap, dy, n, d, dy_c8tot, h, w, P.tw, 1, P.th, P.planes);
+    FPL_REQUIRE(r == CUDA_SUCCESS, "fpl_conv3d_wgrad_tc: tensor map (dy, row-stacked) failed (%d)", (int)r);
+    FPL_CHECK_CUDA(cudaFuncSetAttribute(conv3d_wgrad_rs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    fpl_launch(conv3d_wgrad_rs_kernel, split, kThreadsH, smem_bytes, (cudaStream_t)stream, xmap, dymap, P);
     FPL_LAUNCH_CHECK();
     return 0;
 }

@@ -308,6 +308,9 @@ CUresult encode_5d(EncodeTiledFn encode, CUtensorMap* map, const void* base, int
 bool fpl_wgrad_hs_eligible(int d, int h, int w, int cin, int cout, int kd, int taps);
 int fpl_wgrad_hs_launch(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off, float* dw, int n,
                         int d, int h, int w, int cin, int cout, void* stream, int tapmajor, int skip_epilogue, int force_tw, int dbg);
+bool fpl_wgrad_rs_eligible(int d, int h, int w, int cin, int cout, int kd, int taps);
+int fpl_wgrad_rs_launch(const void* x, int x_c8tot, int x_c8off, const void* dy, int dy_c8tot, int dy_c8off, float* dw, int n,
+                        int d, int h, int w, void* stream, int tapmajor, int skip_epilogue);
 
 // debug knobs (keys 10..18), see fpl_debug_set
 void fpl_wgrad_debug_set(int key, long long value) {
@@ -330,6 +333,8 @@ static int wgrad_tc_launch(const void* x, int x_c8tot, int x_c8off, const void* 
     if (g_wg_hs && fpl_wgrad_hs_eligible(d, h, w, cin, cout, kd, taps))
         return fpl_wgrad_hs_launch(x, x_c8tot, x_c8off, dy, dy_c8tot, dy_c8off, dw, n, d, h, w, cin, cout, stream, tapmajor,
                                    g_wg_skip_epilogue, g_wg_force_tw, g_wg_hs_dbg);
+    if (g_wg_hs && fpl_wgrad_rs_eligible(d, h, w, cin, cout, kd, taps))
+        return fpl_wgrad_rs_launch(x, x_c8tot, x_c8off, dy, dy_c8tot, dy_c8off, dw, n, d, h, w, stream, tapmajor, g_wg_skip_epilogue);
     WgCfg c;
     FPL_REQUIRE(make_wg_cfg(h, w, cin, cout, kd, g_wg_allow_m64, g_wg_allow_pair && d >= 2, c),
                 "fpl_conv3d_wgrad_tc: unsupported shape (cin %d, cout %d, %dx%d)", cin, cout, h, w);

@@ -680,7 +680,7 @@ def test_stem_on_tensor_cores_patch9_k311(cout, shape):
 
 @pytest.mark.parametrize("cin,cout,kd,shape", [(16, 16, 3, (2, 4, 16, 32)), (32, 16, 3, (1, 6, 16, 16)), (64, 32, 3, (2, 4, 8, 16)),
                                                (128, 128, 3, (2, 2, 8, 8)), (16, 16, 1, (1, 3, 16, 16)), (16, 32, 3, (1, 5, 20, 36)),
-                                               (32, 32, 3, (2, 3, 10, 24))])
+                                               (32, 32, 3, (2, 3, 10, 24)), (16, 8, 1, (2, 3, 14, 40))])
 def test_wgrad_tapmajor_and_fold(cin, cout, kd, shape):
     """fpl_conv3d_wgrad_tc_tapmajor writes S[tap][cout][cin]; fpl_wgrad_tapmajor_to_dw_batch folds it into the
     PyTorch layout ACCUMULATING into dw.  Against torch's conv3d weight gradient on bf16-rounded operands."""
@@ -738,7 +738,9 @@ def test_grad_scatter_add():
 
 
 @pytest.mark.parametrize("cin,cout,shape", [(16, 8, (2, 8, 16, 32)), (16, 8, (1, 5, 16, 16)), (32, 8, (1, 6, 8, 16)),
-                                            (16, 16, (2, 5, 16, 16)), (64, 16, (1, 4, 8, 16))])
+                                            (16, 16, (2, 5, 16, 16)), (64, 16, (1, 4, 8, 16)),
+                                            # Cin 16, Cout 8, H >= 6, W >= 16: the row-stacked kernel (conv3d_wgrad_rs_kernel)
+                                            (16, 8, (1, 3, 7, 20)), (16, 8, (2, 1, 12, 32)), (16, 8, (1, 4, 30, 70))])
 def test_conv3d_wgrad_tc_k133_depth_stacked(cin, cout, shape):
     """k(1,3,3) weight gradient with depth planes stacked in M and N (the head: cout = 8 = one channel group of a wider
     dy buffer, 4 planes per MMA set; cout = 16: 2 planes); depths that are not multiples of the stack."""

@@ -11,13 +11,13 @@ from fplplus_b200 import lib, ops
 
 DEV = "cuda:0"
 L = lib.load()
-SHAPES = [(16, 16, 3, (4, 32, 128, 128), 2), (32, 16, 3, (4, 32, 128, 128), 1),
+SHAPES = [(16, 8, 1, (4, 32, 128, 128), 1), (16, 16, 3, (4, 32, 128, 128), 2), (32, 16, 3, (4, 32, 128, 128), 1),
           (16, 32, 3, (4, 16, 64, 64), 1), (32, 32, 3, (4, 16, 64, 64), 2), (64, 32, 3, (4, 16, 64, 64), 1),
           (32, 64, 3, (4, 8, 32, 32), 1), (64, 64, 3, (4, 8, 32, 32), 2), (128, 64, 3, (4, 8, 32, 32), 1),
           (64, 128, 3, (4, 4, 16, 16), 1), (128, 128, 3, (4, 4, 16, 16), 2), (256, 128, 3, (4, 4, 16, 16), 1),
           (128, 256, 3, (4, 2, 8, 8), 1), (256, 256, 3, (4, 2, 8, 8), 1)]
 if os.environ.get("SMALLC"):
-    SHAPES = SHAPES[:4]
+    SHAPES = SHAPES[:5]
 
 
 def graph_time(fn, iters=10):
@@ -50,12 +50,12 @@ def main():
     for cin, cout, kd, shape, count in SHAPES:
         n, d, h, w = shape
         x = torch.randn((n, d, cin // 8, h, w, 8), device=DEV).to(torch.bfloat16)
-        dy = torch.randn((n, d, cout // 8, h, w, 8), device=DEV).to(torch.bfloat16)
+        dy = torch.randn((n, d, max(cout // 8, 1), h, w, 8), device=DEV).to(torch.bfloat16)
         dw = torch.zeros(cout * cin * kd * 9, device=DEV)
-        call = lambda: ops.call(fn_name, ops.ptr(x), cin // 8, 0, ops.ptr(dy), cout // 8, 0, ops.ptr(dw), n, d, h, w, cin, cout, kd,
+        call = lambda: ops.call(fn_name, ops.ptr(x), cin // 8, 0, ops.ptr(dy), max(cout // 8, 1), 0, ops.ptr(dw), n, d, h, w, cin, cout, kd,
                                 ops.stream_ptr())
         us = graph_time(call)
-        gf = 2.0 * n * d * h * w * 27 * cin * cout / 1e9
+        gf = 2.0 * n * d * h * w * 9 * kd * cin * cout / 1e9
         total += us * count
         print("%-30s %9.1f %9.0f %9d" % ("%d->%d %s" % (cin, cout, "x".join(map(str, shape))), us, gf / us * 1e-3, count), flush=True)
     print("sum over one backward pass (k3 layers only): %.0f us" % total)
