@@ -25,7 +25,7 @@ def main():
                                              "gpu__time_duration.sum"))
     agg = {}
     for r in rows[2:]:
-        name = r[ki].split("(")[0].split("<")[0].replace("<unnamed>::", "").replace("void ", "")
+        name = r[ki].split("(")[0].replace("<unnamed>::", "").replace("void ", "").split("<")[0]
         if name not in ENTRY:
             continue
         b = float(r[ri].replace(",", "")) * UNIT[units[ri]] + float(r[wi].replace(",", "")) * UNIT[units[wi]]
