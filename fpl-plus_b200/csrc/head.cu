@@ -293,10 +293,19 @@ extern "C" int fpl_head_dgrad(const float* dlogits, const float* w, void* g, int
     return 0;
 }
 
+bool fpl_head_fwd_tc_eligible(int h, int w, int cin, int classes);
+int fpl_head_fwd_tc_launch(const void* x, int x_c8tot, int x_c8off, const float* w, const float* bias, float* logits, int n, int d,
+                           int h, int w_, int cin, int classes, void* stream);
+
 extern "C" int fpl_head_fwd(const void* x, int x_c8tot, int x_c8off, const float* w, const float* bias, float* logits, int n,
                             int d, int h, int w_, int cin, int classes, void* stream) {
     if (int rc = check_common("fpl_head_fwd", n, d, h, w_, cin, classes)) return rc;
     FPL_REQUIRE(x != nullptr && w != nullptr && bias != nullptr && logits != nullptr, "fpl_head_fwd: NULL buffer");
+    if (fpl_head_fwd_tc_eligible(h, w_, cin, classes)) {       // tensor-core "scatter" form (head_tc.cu)
+        if (int rc = fpl_head_fwd_tc_launch(x, x_c8tot, x_c8off, w, bias, logits, n, d, h, w_, cin, classes, stream)) return rc;
+        FPL_LAUNCH_CHECK();
+        return 0;
+    }
     HeadParams P = {};
     P.x = (const bf16x8*)x; P.x_c8tot = x_c8tot; P.x_c8off = x_c8off; P.w = w; P.bias = bias; P.logits = logits;
     P.N = n; P.D = d; P.H = h; P.W = w_; P.cin = cin; P.classes = classes;

@@ -758,9 +758,11 @@ def test_conv3d_wgrad_tc_k133_depth_stacked(cin, cout, shape):
 
 
 @pytest.mark.parametrize("cin,classes,shape", [(16, 2, (2, 3, 12, 40)), (16, 5, (1, 2, 9, 33)), (32, 2, (1, 4, 16, 32)),
-                                               (32, 8, (1, 2, 8, 70)), (16, 3, (1, 2, 5, 7))])
+                                               (32, 8, (1, 2, 8, 70)), (16, 3, (1, 2, 5, 7)), (16, 2, (2, 3, 45, 100)),
+                                               (16, 7, (1, 2, 30, 64)), (32, 4, (1, 1, 17, 35))])
 def test_head_cuda_core_fwd_and_dgrad(cin, classes, shape):
-    """csrc/head.cu against torch's (1,3,3) conv on the bf16-rounded activation: fp32 logits; input gradient (bf16),
+    """csrc/head.cu / head_tc.cu (forward, W >= 32 and <= 7 classes: the tensor-core scatter form with three-term bf16
+    weights) against torch's (1,3,3) conv on the bf16-rounded activation: fp32 logits; input gradient (bf16),
     the one-channel-group bf16 copy of the logit gradient and the ACCUMULATED bias gradient from one dgrad pass."""
     n, d, h, w = shape
     x = bf16_round(randn(401, n, cin, d, h, w)).requires_grad_(True)
