@@ -274,10 +274,23 @@ int check_common(const char* who, int n, int d, int h, int w, int cin, int class
 
 }  // namespace
 
+bool fpl_head_fwd_tc_eligible(int h, int w, int cin, int classes);
+bool fpl_head_dgrad_tc_eligible(int h, int w, int cin, int classes);
+int fpl_head_dgrad_tc_launch(const float* dlogits, const float* w, void* g, int g_c8tot, int g_c8off, void* dl8, int dl_c8tot,
+                             int dl_c8off, float* dbias, int n, int d, int h, int w_, int cin, int classes, void* stream);
+int fpl_head_fwd_tc_launch(const void* x, int x_c8tot, int x_c8off, const float* w, const float* bias, float* logits, int n, int d,
+                           int h, int w_, int cin, int classes, void* stream);
+
 extern "C" int fpl_head_dgrad(const float* dlogits, const float* w, void* g, int g_c8tot, int g_c8off, void* dl8, int dl_c8tot,
                               int dl_c8off, float* dbias, int n, int d, int h, int w_, int cin, int classes, void* stream) {
     if (int rc = check_common("fpl_head_dgrad", n, d, h, w_, cin, classes)) return rc;
     FPL_REQUIRE(dlogits != nullptr && w != nullptr && g != nullptr, "fpl_head_dgrad: NULL buffer");
+    if (fpl_head_dgrad_tc_eligible(h, w_, cin, classes)) {     // tensor-core form with the operand built in shared memory (head_tc.cu)
+        if (int rc = fpl_head_dgrad_tc_launch(dlogits, w, g, g_c8tot, g_c8off, dl8, dl_c8tot, dl_c8off, dbias, n, d, h, w_, cin, classes,
+                                              stream)) return rc;
+        FPL_LAUNCH_CHECK();
+        return 0;
+    }
     HeadParams P = {};
     P.w = w; P.dlogits = dlogits; P.g = (bf16x8*)g; P.g_c8tot = g_c8tot; P.g_c8off = g_c8off;
     P.dl8 = (bf16x8*)dl8; P.dl_c8tot = dl_c8tot; P.dl_c8off = dl_c8off; P.dbias = dbias;
@@ -292,10 +305,6 @@ extern "C" int fpl_head_dgrad(const float* dlogits, const float* w, void* g, int
     FPL_LAUNCH_CHECK();
     return 0;
 }
-
-bool fpl_head_fwd_tc_eligible(int h, int w, int cin, int classes);
-int fpl_head_fwd_tc_launch(const void* x, int x_c8tot, int x_c8off, const float* w, const float* bias, float* logits, int n, int d,
-                           int h, int w_, int cin, int classes, void* stream);
 
 extern "C" int fpl_head_fwd(const void* x, int x_c8tot, int x_c8off, const float* w, const float* bias, float* logits, int n,
                             int d, int h, int w_, int cin, int classes, void* stream) {
