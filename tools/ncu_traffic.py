@@ -9,8 +9,9 @@ import sys
 
 # keyed by KERNEL name: bench.py aggregates every entry point that launches the same kernel into one roofline population
 # (conv3d_wgrad_tc_kernel = the k3 / k(1,3,3) wgrads + head wgrad + the stem's k(3,1,1) wgrad: all its launches of one step)
-WG = "conv3d_wgrad_hs_kernel+conv3d_wgrad_tc_kernel"      # bench.py WGRAD_KERNELS: the weight-gradient kernels, one population
-ENTRY = {"conv3d_wgrad_tc_kernel": WG, "conv3d_wgrad_hs_kernel": WG, "conv3d_tc_dfold_kernel": "conv3d_tc_dfold_kernel",
+WG = "conv3d_wgrad_hs_kernel+conv3d_wgrad_tc_kernel"      # (+ conv3d_wgrad_rs_kernel, the head)
+_WG_DOC = WG      # bench.py WGRAD_KERNELS: the weight-gradient kernels, one population
+ENTRY = {"conv3d_wgrad_tc_kernel": WG, "conv3d_wgrad_hs_kernel": WG, "conv3d_wgrad_rs_kernel": WG, "conv3d_tc_dfold_kernel": "conv3d_tc_dfold_kernel",
          "conv3d_tc_kernel": "conv3d_tc_kernel"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
