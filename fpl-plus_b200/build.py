@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfplplus_b200.so")
-SOURCES = ["api.cu", "dsbn.cu", "loss.cu", "filter.cu", "conv_direct.cu", "conv_tc.cu", "conv_wgrad_tc.cu", "conv_wgrad_hs.cu", "convt_tc.cu", "conv_tc_dfold.cu", "grad.cu", "adam.cu", "datapath.cu", "head.cu", "head_tc.cu", "upsample.cu"]
+SOURCES = ["api.cu", "dsbn.cu", "loss.cu", "filter.cu", "conv_direct.cu", "conv_tc.cu", "conv_wgrad_tc.cu", "conv_wgrad_hs.cu", "convt_tc.cu", "conv_tc_dfold.cu", "grad.cu", "adam.cu", "datapath.cu", "head.cu", "head_tc.cu", "stem_tc.cu", "upsample.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

@@ -705,11 +705,22 @@ extern "C" int fpl_conv3d_wgrad(const void* x, int x_c8tot, int x_c8off, const v
     return 0;
 }
 
+bool fpl_stem_tc_eligible(int n, int cin, int d, int h, int w, int cout, int kd);
+int fpl_stem_fwd_tc_launch(const float* x, const float* w, const float* bias, void* y, int y_c8tot, int y_c8off, double* stats, int n,
+                           int d, int h, int w_, void* stream);
+int fpl_stem_wgrad_tc_launch(const float* x, const void* dy, int dy_c8tot, int dy_c8off, float* dw, int n, int d, int h, int w_,
+                             void* stream);
+
 extern "C" int fpl_stem_conv_fwd(const float* x, const float* w, const float* bias, void* y, int y_c8tot, int y_c8off,
                                  double* stats, int n, int cin, int d, int h, int w_, int cout, int kd, void* stream) {
     FPL_REQUIRE(cin >= 1 && cin <= 8, "fpl_stem_conv_fwd: in_chns=%d not in [1,8]", cin);
     FPL_REQUIRE(cout % 8 == 0, "fpl_stem_conv_fwd: cout=%d must be a multiple of 8", cout);
     FPL_REQUIRE(kd == 1 || kd == 3, "fpl_stem_conv_fwd: kd=%d must be 1 or 3", kd);
+    if (fpl_stem_tc_eligible(n, cin, d, h, w_, cout, kd) && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {   // tensor cores (stem_tc.cu)
+        if (int rc = fpl_stem_fwd_tc_launch(x, w, bias, y, y_c8tot, y_c8off, stats, n, d, h, w_, stream)) return rc;
+        FPL_LAUNCH_CHECK();
+        return 0;
+    }
     StemP P{x, w, bias, (bf16x8*)y, y_c8tot, y_c8off, stats, n, cin, d, h, w_, cout, kd};
     dim3 grid((h * w_ + 127) / 128, n * d, cout / 8);
     size_t smem = (size_t)cin * kd * 9 * 8 * sizeof(float);
@@ -722,6 +733,11 @@ extern "C" int fpl_stem_conv_wgrad(const float* x, const void* dy, int dy_c8tot,
                                    int cin, int d, int h, int w_, int cout, int kd, void* stream) {
     FPL_REQUIRE(cin >= 1 && cin <= 8 && cout % 8 == 0, "fpl_stem_conv_wgrad: bad channels (%d,%d)", cin, cout);
     FPL_REQUIRE(cout * cin * kd * 9 <= 256 * 8, "fpl_stem_conv_wgrad: %d weights exceed the per-block budget", cout * cin * kd * 9);
+    if (fpl_stem_tc_eligible(n, cin, d, h, w_, cout, kd)) {                                                    // tensor cores (stem_tc.cu)
+        if (int rc = fpl_stem_wgrad_tc_launch(x, dy, dy_c8tot, dy_c8off, dw, n, d, h, w_, stream)) return rc;
+        FPL_LAUNCH_CHECK();
+        return 0;
+    }
     StemWP P{x, (const bf16x8*)dy, dy_c8tot, dy_c8off, dw, n, cin, d, h, w_, cout, kd};
     size_t smem = ((size_t)4 * w_ * (cout + 1) + (size_t)cin * kd * 6 * (w_ + 2)) * sizeof(float);
     FPL_REQUIRE(smem <= 200 * 1024, "fpl_stem_conv_wgrad: row tile needs %zu B of shared memory", smem);

@@ -523,13 +523,14 @@ void fpl_wgrad_debug_set(int key, long long value);
 void fpl_dsbn_debug_set(int key, long long value);
 void fpl_dfold_debug_knob(int key, long long value);
 void fpl_head_tc_debug_set(int key, long long value);
+void fpl_stem_tc_debug_set(int key, long long value);
 extern "C" void fpl_debug_set(int key, long long value) {
     if (key == 0) g_dbg_swap = (int)value;
     if (key == 1) g_tc_allow_nsub = (int)value;
     if (key >= 10 && key < 30) fpl_wgrad_debug_set(key, value);
     if (key >= 30 && key < 40) fpl_dsbn_debug_set(key, value);
     if (key >= 40 && key < 50) fpl_dfold_debug_knob(key, value);
-    if (key >= 50 && key < 60) fpl_head_tc_debug_set(key, value);
+    if (key >= 50 && key < 60) { fpl_head_tc_debug_set(key, value); fpl_stem_tc_debug_set(key, value); }
 }
 
 static int conv3d_tc_launch(const void* x, int x_c8tot, int x_c8off, const void* image, const float* bias, void* y,

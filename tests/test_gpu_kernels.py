@@ -180,9 +180,12 @@ def test_conv3d_wgrad(name, cin, cout, kd, shape):
     assert max_rel(dw.cpu(), 2 * ref) < 1e-4
 
 
-@pytest.mark.parametrize("cin,kd", [(1, 3), (3, 3), (1, 1)])
-def test_stem_conv_fwd_and_wgrad(cin, kd):
-    n, d, h, w, cout = 2, 3, 12, 20, 16
+@pytest.mark.parametrize("cin,kd,shape", [(1, 3, (2, 3, 12, 20)), (3, 3, (2, 3, 12, 20)), (1, 1, (2, 3, 12, 20)),
+                                          # 1 channel, k3, W >= 32: the tensor-core kernels that build their operand from
+                                          # the image in shared memory (stem_tc.cu); ragged tiles in H and W, depth 1 and 5
+                                          (1, 3, (2, 5, 20, 70)), (1, 3, (1, 1, 33, 32)), (1, 3, (1, 4, 16, 96))])
+def test_stem_conv_fwd_and_wgrad(cin, kd, shape):
+    (n, d, h, w), cout = shape, 16
     x = randn(51, n, cin, d, h, w)
     wt = randn(52, cout, cin, kd, 3, 3, scale=0.2).requires_grad_(True)
     b = randn(53, cout, scale=0.1)
