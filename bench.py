@@ -336,7 +336,7 @@ class KernelTimer(object):
 # our arm
 # --------------------------------------------------------------------------------------------
 def build_agent(stage, world):
-    from fplplus_b200.agent import GradAllReducer, SegmentationAgent
+    from fplplus_b200.agent import SegmentationAgent
     import synthetic_data as synth
     cfg = {"dataset": {"tensor_type": "float", "train_batch_size": BATCH}, "network": dict(NET_PARAMS),
            "training": dict(TRAIN_CFG), "testing": dict(TEST_CFG)}
@@ -351,9 +351,7 @@ def build_agent(stage, world):
         agent.create_loss_calculator()
         agent.net.train()
         if world > 1:
-            agent.reducer = GradAllReducer()
-            agent.net.grad_ready_hook = agent.reducer.hook
-            agent.net.grad_wait_hook = agent.reducer.finish
+            agent.enable_data_parallel()
     return agent
 
 
@@ -571,6 +569,7 @@ def run_ours(args):
                                       "2 classes, batch 4/domain/GPU x 1x32x128x128, source batch + pixel/image-"
                                       "weighted target batch, 0.5 Dice + 0.5 CE, Adam (BASELINE.json configs[2])",
                           "voxels_per_step_per_gpu": vox_per_step, "parallelism": "dp%d" % world,
+                          "grad_allreduce": (type(agent.reducer).__name__ if world > 1 else None),
                           "nccl_max_ctas": nccl_ctas or None,
                           "l2": "activation working set per step >> 126 MB L2 (inputs larger than L2)",
                           "conv_gflop_per_step_per_gpu": 2 * BATCH * conv_gflop()[1], "config_name": args.config},

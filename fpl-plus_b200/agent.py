@@ -215,6 +215,42 @@ class GradAllReducer(object):
         self._start = None
 
 
+class DeferredGradAllReducer(object):
+    """ONE all-reduce per optimiser step, after both domain passes: the master gradient buffer behind every ``p.grad``
+    (``UNet2D5_dsbn._deliver_grads``: both passes of ``training_all`` are scatter-added into it) is averaged over the
+    ranks in a single NCCL call just before the optimiser update.
+
+    Against ``GradAllReducer`` (bucketed all-reduces of EACH pass's flat buffer under the remaining backward kernels)
+    this moves half the bytes (the two domain passes share every conv weight: 22.6 MB once instead of twice), needs no
+    per-bucket fold launches, and no NCCL kernel runs while the one-CTA-per-SM persistent conv kernels do (measured in
+    round 2: every weight-gradient launch ~10 us slower under a concurrent all-reduce, +0.4 ms per step at 8 GPUs for
+    a ~0.1 ms collective).  The cost is that the collective is exposed; profiles/README.md has the A/B."""
+
+    def __init__(self, net, group=None):
+        self.net, self.group = net, group
+
+    def _reduce(self, t):
+        import torch.distributed as dist
+        if t.is_cuda:
+            dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+        else:                       # gloo (CPU tests) has no AVG
+            t.mul_(1.0 / dist.get_world_size(self.group))
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def finish(self):
+        m = getattr(self.net, "_master", None)
+        grads = [p.grad for p in self.net.parameters() if p.grad is not None]
+        if not grads:
+            return
+        if m is not None:
+            lo, hi = m["buf"].data_ptr(), m["buf"].data_ptr() + 4 * m["buf"].numel()
+            if all(lo <= g.data_ptr() < hi for g in grads):
+                self._reduce(m["buf"])
+                return
+        for g in grads:             # gradients delivered through autograd (FPL_GRAD_DIRECT=0, foreign p.grad)
+            self._reduce(g)
+
+
 def reserve_sms_for_nccl(ctas=None, sm_budget=None):
     """Data-parallel runs: how the SMs are shared between NCCL's all-reduce kernels (which overlap backward) and the
     library's persistent one-CTA-per-SM kernels.  Call BEFORE ``init_process_group`` (NCCL reads NCCL_MAX_CTAS when the
@@ -496,6 +532,24 @@ class SegmentationAgent(object):
         lr = self.optimizer.param_groups[0]['lr']
         return self._lr_now if torch.is_tensor(lr) else lr
 
+    def enable_data_parallel(self, mode=None, group=None):
+        """Gradient averaging over the ranks of ``torch.distributed`` (one process per GPU; agent_seg.py:695 wraps the
+        net in nn.DataParallel instead).  ``mode`` ([training] grad_allreduce / $FPL_GRAD_ALLREDUCE): 'deferred'
+        (default) = one all-reduce of the master gradient buffer per step, 'overlapped' = bucketed all-reduces of each
+        domain pass under its backward (round 1)."""
+        if mode is None:
+            mode = os.environ.get("FPL_GRAD_ALLREDUCE", self.config.get('training', {}).get('grad_allreduce', 'deferred'))
+        if mode == 'overlapped':
+            self.reducer = GradAllReducer(group=group)
+            self.net.grad_ready_hook = self.reducer.hook
+            self.net.grad_wait_hook = self.reducer.finish
+        elif mode == 'deferred':
+            self.reducer = DeferredGradAllReducer(self.net, group=group)
+            self.net.grad_ready_hook = self.net.grad_wait_hook = None
+        else:
+            raise ValueError("grad_allreduce must be 'deferred' or 'overlapped', got %r" % (mode,))
+        return self.reducer
+
     def _step_body(self, batches):
         """forward(s) + loss + backward (+ overlapped gradient all-reduce) + optimiser update; device work only."""
         inval = getattr(self.net, "invalidate_weight_images", None)
@@ -760,9 +814,7 @@ class SegmentationAgent(object):
         if self.world > 1:
             if os.environ.get("NCCL_MAX_CTAS") or os.environ.get("FPL_SM_BUDGET"):
                 reserve_sms_for_nccl()                 # the communicator exists already: only the grid budget applies
-            self.reducer = GradAllReducer()
-            self.net.grad_ready_hook = self.reducer.hook
-            self.net.grad_wait_hook = self.reducer.finish
+            self.enable_data_parallel()
         ckpt_dir, prefix = self._ckpt_names()
         iter_start, iter_max, iter_valid = tr['iter_start'], tr['iter_max'], tr['iter_valid']
         iter_save = tr.get('iter_save', None)

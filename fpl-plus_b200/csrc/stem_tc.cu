@@ -43,59 +43,97 @@ __device__ __forceinline__ StemTile stem_tile(const StemGeo& G, int t) {
     return c;
 }
 
+// the next tile in depth-fastest order (the tiles a CTA walks are consecutive: no divisions in the loops)
+__device__ __forceinline__ void stem_tile_next(const StemGeo& G, StemTile& c) {
+    if (++c.z == G.D) {
+        c.z = 0;
+        c.w0 += kSC;
+        if (c.w0 >= G.tiles_w * kSC) {
+            c.w0 = 0;
+            c.h0 += kSR;
+            if (c.h0 >= G.tiles_h * kSR) { c.h0 = 0; ++c.n; }
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // builder thread b: the image floats b, b + 512, ... of the halo tile.  The (plane, row, column) of each of them is the
-// same for every tile: decoded ONCE into packed offsets (the divisions cost as much as the build itself otherwise).
+// same for every tile: decoded ONCE (the divisions cost as much as the build itself otherwise) into one packed word
+// (plane + 1) | (row + 1) << 2 | (column + 1) << 8 (negative = beyond the tile) and the element offset from the tile origin.
 struct StemHaloIdx {
-    int pz[kSLoads], rh[kSLoads], cw[kSLoads];
+    int code[kSLoads], off[kSLoads];
 };
 
-__device__ __forceinline__ void stem_halo_idx(int b, StemHaloIdx& I) {
+__device__ __forceinline__ void stem_halo_idx(int b, const StemGeo& G, StemHaloIdx& I) {
 #pragma unroll
     for (int u = 0; u < kSLoads; ++u) {
         const int i = b + u * 32 * kSBuild;
-        I.cw[u] = i % kSHaloC - 1;
-        I.rh[u] = (i / kSHaloC) % kSHaloR - 1;
-        I.pz[u] = i < kSHalo ? i / (kSHaloC * kSHaloR) - 1 : 1 << 20;          // beyond the tile: never in range
+        const int cw = i % kSHaloC - 1, rh = (i / kSHaloC) % kSHaloR - 1, pz = i / (kSHaloC * kSHaloR) - 1;
+        I.code[u] = i < kSHalo ? (pz + 1) | ((rh + 1) << 2) | ((cw + 1) << 8) : -1;
+        I.off[u] = i < kSHalo ? (pz * G.H + rh) * G.W + cw : 0;
     }
 }
 
 __device__ __forceinline__ void stem_load_halo(const float* __restrict__ img, const StemGeo& G, const StemTile& c, const StemHaloIdx& I,
                                                float* regs) {
-    const int64_t HW = (int64_t)G.H * G.W;
-    const float* base = img + ((int64_t)c.n * G.D + c.z) * HW + (int64_t)c.h0 * G.W + c.w0;
+    const float* base = img + (((int64_t)c.n * G.D + c.z) * G.H + c.h0) * (int64_t)G.W + c.w0;
 #pragma unroll
     for (int u = 0; u < kSLoads; ++u) {
-        const int z = c.z + I.pz[u], h = c.h0 + I.rh[u], w = c.w0 + I.cw[u];
+        const int code = I.code[u];
+        const int z = c.z + (code & 3) - 1, h = c.h0 + ((code >> 2) & 63) - 1, w = c.w0 + (code >> 8) - 1;
         float v = 0.0f;
-        if (z >= 0 && z < G.D && h >= 0 && h < G.H && w >= 0 && w < G.W) v = __ldg(base + (int64_t)I.pz[u] * HW + I.rh[u] * G.W + I.cw[u]);
+        if (code >= 0 && (unsigned)z < (unsigned)G.D && (unsigned)h < (unsigned)G.H && (unsigned)w < (unsigned)G.W) v = __ldg(base + I.off[u]);
         regs[u] = v;
     }
 }
 
-// the 8 tap vectors (4 hi, 4 lo) of the voxel builder thread b owns: (row b / 32, col b % 32).  hi = the fp32 value
-// TRUNCATED to bf16 (one AND), lo = bf16(value - hi): hi + lo carries 16 mantissa bits, like round-to-nearest halves
-__device__ __forceinline__ void stem_build(const float* __restrict__ halo, uint8_t* stage, int b) {
-    const int row = b >> 5, col = b & 31;
-    uint32_t hi[16], lo[16];                                   // packed bf16 pairs, taps 2i and 2i+1
-    const float* src = halo + row * kSHaloC + col;
+// The staged image tile holds one 32-bit word per image value: low half = the fp32 value TRUNCATED to bf16 (hi), high half
+// = bf16(value - hi) (lo): hi + lo carries 16 mantissa bits, like round-to-nearest halves.  Splitting once per image value
+// (instead of once per tap: 27x) leaves the builders two byte permutes per tap pair.
+__device__ __forceinline__ uint32_t stem_split(float v) {
+    const uint32_t h = __float_as_uint(v) & 0xffff0000u;
+    const __nv_bfloat162 l = __floats2bfloat162_rn(0.0f, v - __uint_as_float(h));        // .x (low half) = 0, .y (high half) = lo
+    return (h >> 16) | *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__device__ __forceinline__ void stem_stage_halo(uint32_t halo_addr, int b, const float* regs) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        float v[2];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int k = 2 * i + q;
-            v[q] = k < 27 ? src[((k / 9) * kSHaloR + (k / 3) % 3) * kSHaloC + k % 3] : 0.0f;
-        }
-        const uint32_t h0 = __float_as_uint(v[0]) & 0xffff0000u, h1 = __float_as_uint(v[1]) & 0xffff0000u;
-        hi[i] = (h0 >> 16) | h1;
-        const __nv_bfloat162 l = __floats2bfloat162_rn(v[0] - __uint_as_float(h0), v[1] - __uint_as_float(h1));
-        lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+    for (int u = 0; u < kSLoads; ++u) {
+        const int i = b + u * 32 * kSBuild;
+        if (i < kSHalo) sts_u32(halo_addr + 4u * (uint32_t)i, stem_split(regs[u]));
     }
-    uint4* dst = reinterpret_cast<uint4*>(stage) + row * kSC + col;
+}
+
+// the 8 tap vectors (4 hi, 4 lo) of the voxel builder thread b owns: (row b / 32, col b % 32); shared-state-space
+// addresses (generic pointers into the dynamic array cost a descriptor move per access here)
+__device__ __forceinline__ void stem_build(uint32_t halo_addr, uint32_t stage_addr, int b) {
+    const int row = b >> 5, col = b & 31;
+    const uint32_t src = halo_addr + 4u * (uint32_t)(row * kSHaloC + col);
+    uint32_t t[28];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) t[k] = lds_u32(src + 4u * (uint32_t)(((k / 9) * kSHaloR + (k / 3) % 3) * kSHaloC + k % 3));
+    t[27] = 0u;
+    uint32_t hi[16], lo[16];                                   // packed bf16 pairs, taps 2i and 2i+1
+#pragma unroll
+    for (int i = 0; i < 14; ++i) {
+        hi[i] = __byte_perm(t[2 * i], t[2 * i + 1], 0x5410);
+        lo[i] = __byte_perm(t[2 * i], t[2 * i + 1], 0x7632);
+    }
+    hi[14] = hi[15] = lo[14] = lo[15] = 0u;
+    const uint32_t dst = stage_addr + 16u * (uint32_t)(row * kSC + col);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-        dst[g * (kSGroup / 16)] = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
-        dst[(4 + g) * (kSGroup / 16)] = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
+        sts_v4(dst + (uint32_t)(g * kSGroup), hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
+        sts_v4(dst + (uint32_t)((4 + g) * kSGroup), lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
     }
 }
 

@@ -181,6 +181,9 @@ class UNet2D5_dsbn(nn.Module):
         self._stem = None
         self._head_unit = None
         self._head_dirty = True
+        self._stem_dirty = True
+        self._geo0 = (0, 0, 0)
+        self._grad_pass = False         # inside _UNetFunction.forward (autograd disables grad mode there)
         self._build_plan()
 
     # -- plan -------------------------------------------------------------------------------
@@ -289,6 +292,18 @@ class UNet2D5_dsbn(nn.Module):
         u = self._down_units[0][0]
         return (u.cin == 1 and u.kd == 3 and depth >= 2 and u.cout in (16, 32, 64) and ops.is_sm100()
                 and _conv_impl() == "tc" and os.environ.get("FPL_STEM_IMPL", "tc") == "tc")
+
+    def _stem_direct(self, geo):
+        """Training step, FPL_STEM_TRAIN=direct: the stem forward / weight gradient straight from the fp32 image
+        (csrc/stem_tc.cu: the 27-tap operand is built in shared memory) instead of patch tensor + k(3,1,1) kernels:
+        66 + 50 us against 81 + 40 us per launch pair at 4x32x128x128 and no 134 MB patch tensor kept until backward,
+        but 0.3 % SLOWER in the overlapped step (same-box A/B 4.358 vs 4.344 ms: the 800-thread one-CTA-per-SM builder
+        kernels share an SM with nothing, patch9 is pure HBM streaming under the other domain's convs), so the default
+        stays 'patch'."""
+        u = self._down_units[0][0]
+        d, h, w = geo
+        return (u.cin == 1 and u.kd == 3 and u.cout == 16 and w >= 32 and h >= 4 and ops.is_sm100()
+                and _conv_impl() == "tc" and os.environ.get("FPL_STEM_TRAIN", "patch") == "direct")
 
     def _head_cc(self, n, d):
         """CUDA-core head kernels (csrc/head.cu): the default for the shipped shapes; FPL_HEAD_IMPL=tc selects the
@@ -454,6 +469,7 @@ class UNet2D5_dsbn(nn.Module):
         for ent in self._img_cache.values():
             ent[0] = -1
         self._head_dirty = True
+        self._stem_dirty = True
 
     def prepare_inference(self, shape):
         """Stage every stale weight image for no-grad forwards of inputs shaped ``shape`` [N,C,D,H,W] on the CURRENT
@@ -482,10 +498,13 @@ class UNet2D5_dsbn(nn.Module):
     def _refresh_weight_images(self, with_dgrad):
         """(Re)stage every stale weight image with ONE batched launch."""
         lib = ops._lib.load()
-        if self._stem_tc(self._unit_depth.get("block0.conv#1", 0)):
+        if self._stem_tc(self._unit_depth.get("block0.conv#1", 0)) and not (with_dgrad and self._stem_direct(self._geo0)):
+            # the patch-tensor stem serves the no-grad forwards (activation in its epilogue); the training step builds
+            # the stem operand in shared memory and needs no staged image
             if self._stem is None:
                 self._stem = UNet2D5_dsbn._StemConv(self._down_units[0][0].conv)
-            self._stem.sync(self._head_dirty)
+            self._stem.sync(self._stem_dirty)
+            self._stem_dirty = False
         todo, todo_df, todo_ct = [], [], []
         for u in self._tc_convs():
             w = u.conv.weight
@@ -543,6 +562,7 @@ class UNet2D5_dsbn(nn.Module):
 
     def _note_depths(self, geo):
         """Depth of every conv unit for the current input geometry (kernel selection of the weight staging)."""
+        self._geo0 = tuple(geo[0])
         for i in range(5):
             for u in self._down_units[i]:
                 self._unit_depth[u.name] = geo[i][0]
@@ -605,7 +625,7 @@ class UNet2D5_dsbn(nn.Module):
     def _conv_fwd(self, u, xin, x_img, y, stats, n, geo, ws):
         d, h, w = geo
         st = stream_ptr()
-        if u.is_stem and self._stem_tc(d):
+        if u.is_stem and self._stem_tc(d) and not (self._grad_pass and self._stem_direct(geo)):
             xs = ws.c8("XS:stem", n, d, 32, h, w)
             call("fpl_patch9_c8", ptr(x_img), ptr(xs), 1, n, d, h, w, st)
             call("fpl_conv3d_tc_k311", ptr(xs), 4, 0, ptr(self._stem.image), ptr(u.conv.bias), ptr(y), y.shape[2], 0,
@@ -719,7 +739,8 @@ class UNet2D5_dsbn(nn.Module):
              n, d, h, w, c, stream_ptr())
         rec[u.name] = dict(y=y, xin=xin, scale=scale, shift=shift, mean=mean, invstd=invstd, training=training,
                            p=p, mask=mask, seed=seed, offset=offset, geo=geo, bn=bn,
-                           seed_dev=rec["seed_dev"] if p > 0.0 and mask is None else None)
+                           seed_dev=rec["seed_dev"] if p > 0.0 and mask is None else None,
+                           stem_direct=u.is_stem and self._grad_pass and self._stem_direct(geo))
 
     # -- whole-network forward --------------------------------------------------------------
     def _first_dropout_level(self):
@@ -740,7 +761,7 @@ class UNet2D5_dsbn(nn.Module):
         ft = self.ft_chns
         small = _SmallPool(ws, "fwd", x.device)
         self._note_depths(geo)
-        self._refresh_weight_images(with_dgrad=torch.is_grad_enabled())
+        self._refresh_weight_images(with_dgrad=self._grad_pass)
         # dropout stream: (seed, per-layer offset) drawn from torch's CPU generator, so torch.manual_seed
         # makes MC-dropout passes reproducible; backward regenerates the same Philox stream
         if self._seed_from_device:
@@ -748,7 +769,7 @@ class UNet2D5_dsbn(nn.Module):
         else:
             seed, seed_dev = self._draw_seed(), None
         rec = {"seed": seed, "seed_dev": seed_dev, "next_offset": 0, "geo": geo, "n": n, "x": x}
-        rec["eval_affine"] = {} if torch.is_grad_enabled() else self._eval_affine_refresh(domain, ws)
+        rec["eval_affine"] = {} if self._grad_pass else self._eval_affine_refresh(domain, ws)
         if repeats > 1:
             assert not torch.is_grad_enabled()
             seeds = [(seed, seed_dev if seed_dev is None else seed_dev[0:1])]
@@ -872,6 +893,9 @@ class UNet2D5_dsbn(nn.Module):
         call("fpl_dsbn_act_bwd_apply_fin", *common, ptr(red), r["training"], ptr(dy), n, d, h, w, c, st,
              ptr(grads[bn.weight]), ptr(grads[bn.bias]), ptr(grads[u.prelu.weight]), ptr(grads[u.conv.bias]))
         dw = grads[u.conv.weight]
+        if u.is_stem and r.get("stem_direct"):
+            call("fpl_stem_conv_wgrad", ptr(r["x_img"]), ptr(dy), c // 8, 0, ptr(dw), n, u.cin, d, h, w, c, u.kd, st)
+            return None
         if u.is_stem and self._stem_tc(d):
             # the patch tensor of the forward is still in the workspace: k(3,1,1) wgrad, one MMA per K step
             xs = ws.c8("XS:stem", n, d, 32, h, w)
@@ -1241,7 +1265,11 @@ class _UNetFunction(torch.autograd.Function):
             ws, home = (net._pool.pop() if net._pool else _Workspace(x.device)), net._pool
             if ws.device != x.device:
                 ws = _Workspace(x.device)
-        logits, rec = net._run_forward(x, domain, ws)
+        net._grad_pass = True
+        try:
+            logits, rec = net._run_forward(x, domain, ws)
+        finally:
+            net._grad_pass = False
         ctx.net, ctx.domain, ctx.rec = net, domain, rec
         ctx.lease = _Lease(home, ws)
         return logits

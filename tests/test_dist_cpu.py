@@ -49,6 +49,28 @@ def _worker(rank, world, port, q):
         others2 = [torch.empty_like(mine2) for _ in range(world)]
         dist.all_gather(others2, mine2)
         ok_avg = ok_avg and bool(torch.allclose(flat2, torch.stack(others2).mean(0), rtol=1e-6, atol=1e-7))
+        # ---- deferred mode: ONE all-reduce of the master gradient buffer behind every p.grad (both domain passes already
+        #      summed into it), and the per-parameter fallback when the gradients came through autograd ----
+        class _Net(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.a = torch.nn.Parameter(torch.zeros(5, 3))
+                self.b = torch.nn.Parameter(torch.zeros(7))
+                self.frozen = torch.nn.Parameter(torch.zeros(2))            # never receives a gradient
+        net = _Net()
+        buf = torch.randn(24, generator=g)
+        mine3 = buf.clone()
+        net._master = {"buf": buf}
+        net.a.grad, net.b.grad = buf[0:15].view(5, 3), buf[16:23]
+        A.DeferredGradAllReducer(net).finish()
+        others3 = [torch.empty_like(mine3) for _ in range(world)]
+        dist.all_gather(others3, mine3)
+        ok_avg = ok_avg and bool(torch.allclose(buf, torch.stack(others3).mean(0), rtol=1e-6, atol=1e-7))
+        ok_avg = ok_avg and net.a.grad.data_ptr() == buf.data_ptr() and net.frozen.grad is None
+        net._master = None
+        net.a.grad, net.b.grad = mine3[0:15].clone().view(5, 3), mine3[16:23].clone()
+        A.DeferredGradAllReducer(net).finish()
+        ok_avg = ok_avg and bool(torch.allclose(net.b.grad, buf[16:23], rtol=1e-6, atol=1e-7))
         # ---- inference: volumes round-robin, gather of (value, name) pairs, host sort ----
         cfg = {"dataset": {"tensor_type": "float"}, "network": {}, "training": {}, "testing": {}}
         ag = A.SegmentationAgent(cfg, "test")
