@@ -2,14 +2,19 @@
 // (PyMIC/pymic/net/net3d/unet2d5_dsbn.py:75 with in_chns = 1, and its autograd), WITHOUT a materialised patch tensor.
 //
 // A 1-channel input has no channel dimension to reduce over, so the GEMM's K is the 27 taps: builder warps gather, per
-// voxel, the 27 neighbours of the image from a staged 3-plane halo tile and write them as four 16-byte vectors of 8 taps
-// (bf16 value) + four more (bf16 residual): [hi g0..g3 | lo g0..g3][16 rows][32 voxels][8 taps].  That ONE layout is
+// voxel, the 27 neighbours of the image from a rolling window of staged halo planes (every image value split ONCE into a
+// bf16 value + bf16 residual word) and write them as four 16-byte vectors of 8 taps (value) + four more (residual):
+// [hi g0..g3 | lo g0..g3][16 rows][32 voxels][8 taps].  That ONE layout is
 //   * the K-major A operand of the forward:  y[v][co] = sum_k A[v][k] W[k][co]   (M = 128 voxels = 4 rows, six K steps:
 //     hi x w_hi, lo x w_hi, hi x w_lo: fp32-accurate although every operand is bf16), and
 //   * the MN-major A operand of the weight gradient:  dW[k][co] = sum_v A[v][k] dy[v][co]   (M = 64 = hi | lo taps,
 //     K = 16 voxels of a row, B = the dy tile straight from TMA), hi and lo rows summed by the final atomics.
 // Before: fpl_patch9_c8 wrote a 64 B/voxel patch tensor (24 us), a k(3,1,1) tensor-core conv read it (50 us) and so did
 // the k(3,1,1) wgrad (40 us): 343 + 201 MB of traffic per pass for 75 + 75 MB of algorithmic bytes.
+// A CTA walks CONSECUTIVE tiles, depth fastest: tile coordinates are stepped, not divided, and a tile that continues its
+// column loads one new image plane instead of three.  41 us forward / 35 us weight gradient at 4x32x128x128 (first version:
+// 66 / 50 us with a per-tap split, generic shared-memory addressing, three divisions per tile and role, a spilling epilogue;
+// ncu: 640 instructions per voxel-warp, 60 % issue slots busy -- profiles/README.md round 2e).
 // Warp roles: forward: warp 0 MMA issuer, warps 1..8 epilogue (+bias, bf16 store, BatchNorm sums), warps 9..24 builders;
 //             wgrad:   warp 0 MMA issuer, warp 1 TMA producer (dy), warps 2..5 final epilogue, warps 6..21 builders.
 #include "common.cuh"
@@ -23,7 +28,6 @@ constexpr int kSGroup = kSR * kSC * 16;                 // one 8-tap group plane
 constexpr int kSStage = 8 * kSGroup;                    // hi g0..3 | lo g0..3
 constexpr int kSHaloR = kSR + 2, kSHaloC = kSC + 2, kSHalo = 3 * kSHaloR * kSHaloC;     // staged image tile (floats)
 constexpr int kSBuild = 16;                             // builder warps: one voxel of the tile per builder thread
-constexpr int kSLoads = (kSHalo + 32 * kSBuild - 1) / (32 * kSBuild);                   // image floats per builder thread
 
 struct StemTile {
     int n, z, h0, w0;
@@ -56,6 +60,11 @@ __device__ __forceinline__ void stem_tile_next(const StemGeo& G, StemTile& c) {
     }
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -66,61 +75,84 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, ui
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// builder thread b: the image floats b, b + 512, ... of the halo tile.  The (plane, row, column) of each of them is the
-// same for every tile: decoded ONCE (the divisions cost as much as the build itself otherwise) into one packed word
-// (plane + 1) | (row + 1) << 2 | (column + 1) << 8 (negative = beyond the tile) and the element offset from the tile origin.
+// The builders keep a ROLLING window of image planes in shared memory: a ring of four (18 x 34) halo planes, plane z in
+// slot (z + 1) & 3.  The tiles a CTA walks are consecutive in depth, so a tile that continues its column needs ONE new plane
+// (z + 1); the first tile of a column (or of the CTA) loads all three.  Builder thread b owns the plane elements b and
+// b + 512 (< 612): their (row, column) is the same for every plane and tile: decoded ONCE into a packed word
+// (row + 1) | (column + 1) << 8 (negative = beyond the plane) and the element offset from the tile origin.
+constexpr int kSPlane = kSHaloR * kSHaloC;                                                // 612 values
+constexpr int kSLoadsP = (kSPlane + 32 * kSBuild - 1) / (32 * kSBuild);                   // 2 per thread and plane
+static_assert(4 * kSPlane <= 2 * kSHalo, "the plane ring fits the staged-tile allocation");
+
 struct StemHaloIdx {
-    int code[kSLoads], off[kSLoads];
+    int code[kSLoadsP], off[kSLoadsP];
 };
 
 __device__ __forceinline__ void stem_halo_idx(int b, const StemGeo& G, StemHaloIdx& I) {
 #pragma unroll
-    for (int u = 0; u < kSLoads; ++u) {
+    for (int u = 0; u < kSLoadsP; ++u) {
         const int i = b + u * 32 * kSBuild;
-        const int cw = i % kSHaloC - 1, rh = (i / kSHaloC) % kSHaloR - 1, pz = i / (kSHaloC * kSHaloR) - 1;
-        I.code[u] = i < kSHalo ? (pz + 1) | ((rh + 1) << 2) | ((cw + 1) << 8) : -1;
-        I.off[u] = i < kSHalo ? (pz * G.H + rh) * G.W + cw : 0;
+        const int cw = i % kSHaloC - 1, rh = i / kSHaloC - 1;
+        I.code[u] = i < kSPlane ? (rh + 1) | ((cw + 1) << 8) : -1;
+        I.off[u] = i < kSPlane ? rh * G.W + cw : 0;
     }
 }
 
-__device__ __forceinline__ void stem_load_halo(const float* __restrict__ img, const StemGeo& G, const StemTile& c, const StemHaloIdx& I,
-                                               float* regs) {
-    const float* base = img + (((int64_t)c.n * G.D + c.z) * G.H + c.h0) * (int64_t)G.W + c.w0;
+// image planes c.z - 1 .. c.z + 1 (full) or c.z + 1 only, into regs[plane][u]
+__device__ __forceinline__ void stem_load_planes(const float* __restrict__ img, const StemGeo& G, const StemTile& c, const StemHaloIdx& I,
+                                                 bool full, float* regs) {
+    const int64_t HW = (int64_t)G.H * G.W;
+    const float* base = img + ((int64_t)c.n * G.D + c.z) * HW + (int64_t)c.h0 * G.W + c.w0;
 #pragma unroll
-    for (int u = 0; u < kSLoads; ++u) {
-        const int code = I.code[u];
-        const int z = c.z + (code & 3) - 1, h = c.h0 + ((code >> 2) & 63) - 1, w = c.w0 + (code >> 8) - 1;
-        float v = 0.0f;
-        if (code >= 0 && (unsigned)z < (unsigned)G.D && (unsigned)h < (unsigned)G.H && (unsigned)w < (unsigned)G.W) v = __ldg(base + I.off[u]);
-        regs[u] = v;
+    for (int p = 0; p < 3; ++p) {
+        if (p < 2 && !full) continue;
+        const bool zok = (unsigned)(c.z + p - 1) < (unsigned)G.D;
+        const float* pb = base + (int64_t)(p - 1) * HW;
+#pragma unroll
+        for (int u = 0; u < kSLoadsP; ++u) {
+            const int code = I.code[u];
+            const int h = c.h0 + (code & 255) - 1, w = c.w0 + (code >> 8) - 1;
+            float v = 0.0f;
+            if (code >= 0 && zok && (unsigned)h < (unsigned)G.H && (unsigned)w < (unsigned)G.W) v = __ldg(pb + I.off[u]);
+            regs[p * kSLoadsP + u] = v;
+        }
     }
 }
 
-// The staged image tile holds one 32-bit word per image value: low half = the fp32 value TRUNCATED to bf16 (hi), high half
-// = bf16(value - hi) (lo): hi + lo carries 16 mantissa bits, like round-to-nearest halves.  Splitting once per image value
-// (instead of once per tap: 27x) leaves the builders two byte permutes per tap pair.
+// The staged image tile holds one 32-bit word per image value: low half = bf16(value) (hi), high half = bf16(value - hi)
+// (lo): hi + lo carries 16 mantissa bits -- the same split as fpl_patch9_c8, so the products the tensor pipe forms are
+// those of the patch-tensor path.  Splitting once per image value (instead of once per tap: 27x) leaves the builders two
+// byte permutes per tap pair.
 __device__ __forceinline__ uint32_t stem_split(float v) {
-    const uint32_t h = __float_as_uint(v) & 0xffff0000u;
-    const __nv_bfloat162 l = __floats2bfloat162_rn(0.0f, v - __uint_as_float(h));        // .x (low half) = 0, .y (high half) = lo
-    return (h >> 16) | *reinterpret_cast<const uint32_t*>(&l);
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    return (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16);
 }
 
-__device__ __forceinline__ void stem_stage_halo(uint32_t halo_addr, int b, const float* regs) {
+__device__ __forceinline__ void stem_stage_planes(uint32_t halo_addr, int b, int z, bool full, const float* regs) {
 #pragma unroll
-    for (int u = 0; u < kSLoads; ++u) {
-        const int i = b + u * 32 * kSBuild;
-        if (i < kSHalo) sts_u32(halo_addr + 4u * (uint32_t)i, stem_split(regs[u]));
+    for (int p = 0; p < 3; ++p) {
+        if (p < 2 && !full) continue;
+        const uint32_t slot = halo_addr + 4u * (uint32_t)(((z + p) & 3) * kSPlane);
+#pragma unroll
+        for (int u = 0; u < kSLoadsP; ++u) {
+            const int i = b + u * 32 * kSBuild;
+            if (i < kSPlane) sts_u32(slot + 4u * (uint32_t)i, stem_split(regs[p * kSLoadsP + u]));
+        }
     }
 }
 
-// the 8 tap vectors (4 hi, 4 lo) of the voxel builder thread b owns: (row b / 32, col b % 32); shared-state-space
-// addresses (generic pointers into the dynamic array cost a descriptor move per access here)
-__device__ __forceinline__ void stem_build(uint32_t halo_addr, uint32_t stage_addr, int b) {
+// the 8 tap vectors (4 hi, 4 lo) of the voxel builder thread b owns: (row b / 32, col b % 32) of the tile at depth z;
+// shared-state-space addresses (generic pointers into the dynamic array cost a descriptor move per access here)
+__device__ __forceinline__ void stem_build(uint32_t halo_addr, uint32_t stage_addr, int b, int z) {
     const int row = b >> 5, col = b & 31;
-    const uint32_t src = halo_addr + 4u * (uint32_t)(row * kSHaloC + col);
     uint32_t t[28];
 #pragma unroll
-    for (int k = 0; k < 27; ++k) t[k] = lds_u32(src + 4u * (uint32_t)(((k / 9) * kSHaloR + (k / 3) % 3) * kSHaloC + k % 3));
+    for (int kd = 0; kd < 3; ++kd) {
+        const uint32_t src = halo_addr + 4u * (uint32_t)(((z + kd) & 3) * kSPlane + row * kSHaloC + col);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) t[kd * 9 + k] = lds_u32(src + 4u * (uint32_t)((k / 3) * kSHaloC + k % 3));
+    }
     t[27] = 0u;
     uint32_t hi[16], lo[16];                                   // packed bf16 pairs, taps 2i and 2i+1
 #pragma unroll
@@ -136,6 +168,37 @@ __device__ __forceinline__ void stem_build(uint32_t halo_addr, uint32_t stage_ad
         sts_v4(dst + (uint32_t)((4 + g) * kSGroup), lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
     }
 }
+
+// one builder iteration protocol shared by the forward and the weight gradient (see the kernels): returns nothing; the
+// caller owns the stage ring and its barriers
+#define STEM_BUILDER_LOOP(STAGE_ADDR, FULL_BAR, N_STAGES)                                                              \
+    float regs[3 * kSLoadsP];                                                                                          \
+    StemHaloIdx I;                                                                                                     \
+    stem_halo_idx(b, G, I);                                                                                            \
+    const uint32_t halo_u = smem_u32(halo), ring_a = smem_u32(ring);                                                   \
+    int stage = 0; uint32_t phase = 0;                                                                                 \
+    StemTile c = stem_tile(G, tile_begin);                                                                             \
+    bool full = true;                                                                                                  \
+    if (tile_begin < tile_end) stem_load_planes(P.img, G, c, I, true, regs);                                           \
+    for (int t = tile_begin; t < tile_end; ++t) {                                                                      \
+        /* a new column overwrites ring slots the previous column's last tile may still be read from */               \
+        if (full && t != tile_begin) asm volatile("bar.sync 2, %0;" ::"n"(32 * kSBuild) : "memory");                   \
+        stem_stage_planes(halo_u, b, c.z, full, regs);                                                                 \
+        /* the next tile's image floats travel while this tile is built */                                            \
+        StemTile nx = c;                                                                                               \
+        stem_tile_next(G, nx);                                                                                         \
+        const bool nfull = nx.z == 0;                                                                                  \
+        if (t + 1 < tile_end) stem_load_planes(P.img, G, nx, I, nfull, regs);                                          \
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * kSBuild) : "memory");                                                \
+        mbar_wait(&empty_bar[stage], phase ^ 1);                                                                       \
+        stem_build(halo_u, ring_a + (uint32_t)(STAGE_ADDR), b, c.z);                                                   \
+        fence_proxy_async();                                                                                           \
+        __syncwarp();                                                                                                  \
+        if (lane == 0) mbar_arrive(&FULL_BAR[stage]);                                                                  \
+        if (++stage == N_STAGES) { stage = 0; phase ^= 1; }                                                            \
+        c = nx;                                                                                                        \
+        full = nfull;                                                                                                  \
+    }
 
 // ------------------------------------------------------------------------------------------------------------------
 // forward
@@ -158,7 +221,7 @@ __global__ void __launch_bounds__(kSfThreads) stem_fwd_tc_kernel(StemFwdParams P
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* ring = smem;                                                    // [stage][8 groups][16][32][16 B]
     uint8_t* b_sm = ring + kSfStages * kSStage;                              // [6 K steps][2 groups][16 co][8 taps] bf16
-    float* halo = reinterpret_cast<float*>(b_sm + 6 * 512);                  // [2][3][18][34]
+    float* halo = reinterpret_cast<float*>(b_sm + 6 * 512);                  // ring of 4 halo planes [18][34], split words (stem_split)
     uint64_t* bars = reinterpret_cast<uint64_t*>(halo + 2 * kSHalo);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kSfStages;
@@ -196,6 +259,10 @@ __global__ void __launch_bounds__(kSfThreads) stem_fwd_tc_kernel(StemFwdParams P
     const uint32_t tmem_base = *tmem_slot;
     const StemGeo G = P.G;
     const int64_t HW = (int64_t)G.H * G.W;
+    // consecutive tiles per CTA (depth fastest): the loops step the tile coordinates instead of dividing, and a CTA's
+    // next tile shares two of its three image planes with the current one (L1)
+    const int tile_begin = (int)(((int64_t)G.total_tiles * blockIdx.x) / gridDim.x);
+    const int tile_end = (int)(((int64_t)G.total_tiles * (blockIdx.x + 1)) / gridDim.x);
 
     if (warp == 0) {
         // ===================== MMA issuer =====================
@@ -206,7 +273,7 @@ __global__ void __launch_bounds__(kSfThreads) stem_fwd_tc_kernel(StemFwdParams P
         const bool leader = elect_one();
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < G.total_tiles; t += gridDim.x) {
+        for (int t = tile_begin; t < tile_end; ++t) {
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
@@ -228,36 +295,37 @@ __global__ void __launch_bounds__(kSfThreads) stem_fwd_tc_kernel(StemFwdParams P
         FPL_PDL_TRIGGER();
     } else if (warp <= 8) {
         // ===================== epilogue: + bias, bf16 C8-planar store, BatchNorm sums =====================
-        const int quarter = warp & 3, pair = (warp - 1) >> 2;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        float tacc[32];
+        // two warps per TMEM lane quadrant, one per channel group (8 of the 16 accumulator columns): 16 statistics
+        // accumulators + 8 values per thread keep the 800-thread CTA inside 80 registers without spills
+        const int quarter = warp & 3, half = (warp - 1) >> 2;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 8);
+        float tacc[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) tacc[i] = 0.0f;
-        float bias_r[16];
+        for (int i = 0; i < 16; ++i) tacc[i] = 0.0f;
+        float bias_r[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) bias_r[i] = bias_sm[i];
+        for (int i = 0; i < 8; ++i) bias_r[i] = bias_sm[half * 8 + i];
         int acc = 0; uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < G.total_tiles; t += gridDim.x) {
-            const StemTile c = stem_tile(G, t);
+        StemTile c = stem_tile(G, tile_begin);
+        for (int t = tile_begin; t < tile_end; ++t, stem_tile_next(G, c)) {
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const int w = c.w0 + lane;
-#pragma unroll 1
-            for (int m = pair; m < 4; m += 2) {
+            bf16x8* out0 = P.y + (((int64_t)c.n * G.D + c.z) * P.y_c8tot + P.y_c8off + half) * HW + w;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
                 const int h = c.h0 + 4 * m + quarter;
                 const bool valid = h < G.H && w < G.W;
-                uint32_t r[16];
-                tmem_ld16(lane_base + (uint32_t)(acc * 64 + m * 16), r);
+                uint32_t r[8];
+                tmem_ld8(lane_base + (uint32_t)(acc * 64 + m * 16), r);
                 tmem_ld_wait();
-                float v[16];
+                float v[8];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + bias_r[i];
+                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]) + bias_r[i];
                 if (valid) {
-                    bf16x8* out = P.y + (((int64_t)c.n * G.D + c.z) * P.y_c8tot + P.y_c8off) * HW + (int64_t)h * G.W + w;
-                    st_bf16x8(out, v);
-                    st_bf16x8(out + HW, v + 8);
+                    st_bf16x8(out0 + (int64_t)h * G.W, v);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) { tacc[i] += v[i]; tacc[16 + i] = fmaf(v[i], v[i], tacc[16 + i]); }
+                    for (int i = 0; i < 8; ++i) { tacc[i] += v[i]; tacc[8 + i] = fmaf(v[i], v[i], tacc[8 + i]); }
                 }
             }
             tc_fence_before();
@@ -268,46 +336,31 @@ __global__ void __launch_bounds__(kSfThreads) stem_fwd_tc_kernel(StemFwdParams P
         if (P.stats != nullptr) {
             // one double atomic per channel and CTA: the 8 epilogue warps are first summed in shared memory (1184 warps
             // adding to the same 32 addresses serialise in the L2 atomic unit)
-            warp_transpose_sum32(tacc, lane);                     // lane L: sum over the warp of entry L
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) tacc[i] += __shfl_xor_sync(0xffffffffu, tacc[i], o);
+            }
+            float mine = 0.0f;                                    // lane e < 16: entry e = [sum | sum of squares][8 channels]
+#pragma unroll
+            for (int i = 0; i < 16; ++i) mine = lane == i ? tacc[i] : mine;
             float* red = halo;                                    // the builders are done with the image tiles: see the barrier
             asm volatile("bar.sync 3, 256;" ::: "memory");        // (all epilogue warps past their last tile; builders finish
                                                                   //  before the last tmem_full, which the epilogue has consumed)
-            red[(warp - 1) * 32 + lane] = tacc[0];
+            if (lane < 16) red[(warp - 1) * 16 + lane] = mine;
             asm volatile("bar.sync 3, 256;" ::: "memory");
             if (warp == 1) {
+                const int stat = lane >> 4, ch = lane & 15, e = stat * 8 + (ch & 7), w0 = (ch >> 3) * 4;
                 double s = 0.0;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) s += (double)red[k * 32 + lane];
-                atomicAdd(P.stats + (lane >> 4) * 16 + (lane & 15), s);
+                for (int k = 0; k < 4; ++k) s += (double)red[(w0 + k) * 16 + e];
+                atomicAdd(P.stats + stat * 16 + ch, s);
             }
         }
     } else {
         // ===================== builders =====================
         const int b = threadIdx.x - 32 * 9;
-        float regs[kSLoads];
-        StemHaloIdx I;
-        stem_halo_idx(b, I);
-        int stage = 0; uint32_t phase = 0;
-        int buf = 0;
-        if ((int)blockIdx.x < G.total_tiles) stem_load_halo(P.img, G, stem_tile(G, blockIdx.x), I, regs);
-        for (int t = blockIdx.x; t < G.total_tiles; t += gridDim.x) {
-            float* hb = halo + buf * kSHalo;
-#pragma unroll
-            for (int u = 0; u < kSLoads; ++u) {
-                const int i = b + u * 32 * kSBuild;
-                if (i < kSHalo) hb[i] = regs[u];
-            }
-            // the next tile's image floats travel while this tile is built
-            if (t + (int)gridDim.x < G.total_tiles) stem_load_halo(P.img, G, stem_tile(G, t + gridDim.x), I, regs);
-            asm volatile("bar.sync 2, %0;" ::"n"(32 * kSBuild) : "memory");
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            stem_build(hb, ring + stage * kSStage, b);
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full_bar[stage]);
-            if (++stage == kSfStages) { stage = 0; phase ^= 1; }
-            buf ^= 1;
-        }
+        STEM_BUILDER_LOOP(stage * kSStage, full_bar, kSfStages)
     }
     tc_fence_before();
     __syncthreads();
@@ -393,8 +446,8 @@ __global__ void __launch_bounds__(kSwThreads) stem_wgrad_tc_kernel(const __grid_
         // ===================== TMA producer: dy tile [2 groups][16 rows][32 voxels] =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int t = tile_begin; t < tile_end; ++t) {
-                const StemTile c = stem_tile(G, t);
+            StemTile c = stem_tile(G, tile_begin);
+            for (int t = tile_begin; t < tile_end; ++t, stem_tile_next(G, c)) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 mbar_expect_tx(&full_b[stage], (uint32_t)kSwDy);
                 tma_load_5d(ring + stage * (kSStage + kSwDy) + kSStage, &dymap, &full_b[stage], c.w0 * 8, c.h0, P.dy_c8off, c.z, c.n);
@@ -420,29 +473,7 @@ __global__ void __launch_bounds__(kSwThreads) stem_wgrad_tc_kernel(const __grid_
     } else {
         // ===================== builders =====================
         const int b = threadIdx.x - 32 * 6;
-        float regs[kSLoads];
-        StemHaloIdx I;
-        stem_halo_idx(b, I);
-        int stage = 0; uint32_t phase = 0;
-        int buf = 0;
-        if (tile_begin < tile_end) stem_load_halo(P.img, G, stem_tile(G, tile_begin), I, regs);
-        for (int t = tile_begin; t < tile_end; ++t) {
-            float* hb = halo + buf * kSHalo;
-#pragma unroll
-            for (int u = 0; u < kSLoads; ++u) {
-                const int i = b + u * 32 * kSBuild;
-                if (i < kSHalo) hb[i] = regs[u];
-            }
-            if (t + 1 < tile_end) stem_load_halo(P.img, G, stem_tile(G, t + 1), I, regs);
-            asm volatile("bar.sync 2, %0;" ::"n"(32 * kSBuild) : "memory");
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            stem_build(hb, ring + stage * (kSStage + kSwDy), b);
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full_a[stage]);
-            if (++stage == kSwStages) { stage = 0; phase ^= 1; }
-            buf ^= 1;
-        }
+        STEM_BUILDER_LOOP(stage * (kSStage + kSwDy), full_a, kSwStages)
     }
     tc_fence_before();
     __syncthreads();

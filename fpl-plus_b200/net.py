@@ -294,16 +294,15 @@ class UNet2D5_dsbn(nn.Module):
                 and _conv_impl() == "tc" and os.environ.get("FPL_STEM_IMPL", "tc") == "tc")
 
     def _stem_direct(self, geo):
-        """Training step, FPL_STEM_TRAIN=direct: the stem forward / weight gradient straight from the fp32 image
-        (csrc/stem_tc.cu: the 27-tap operand is built in shared memory) instead of patch tensor + k(3,1,1) kernels:
-        66 + 50 us against 81 + 40 us per launch pair at 4x32x128x128 and no 134 MB patch tensor kept until backward,
-        but 0.3 % SLOWER in the overlapped step (same-box A/B 4.358 vs 4.344 ms: the 800-thread one-CTA-per-SM builder
-        kernels share an SM with nothing, patch9 is pure HBM streaming under the other domain's convs), so the default
-        stays 'patch'."""
+        """Training step: the stem forward / weight gradient straight from the fp32 image (csrc/stem_tc.cu: the 27-tap
+        operand is built in shared memory from a rolling window of image planes) instead of patch tensor + k(3,1,1)
+        kernels: 41 + 35 us against 81 + 40 us per launch pair at 4x32x128x128, no 134 MB patch tensor kept until
+        backward; same-box A/B of the step 4.348 -> 4.283 ms.  FPL_STEM_TRAIN=patch restores the patch-tensor path
+        (which no-grad forwards keep: its conv carries the activation in the epilogue)."""
         u = self._down_units[0][0]
         d, h, w = geo
         return (u.cin == 1 and u.kd == 3 and u.cout == 16 and w >= 32 and h >= 4 and ops.is_sm100()
-                and _conv_impl() == "tc" and os.environ.get("FPL_STEM_TRAIN", "patch") == "direct")
+                and _conv_impl() == "tc" and os.environ.get("FPL_STEM_TRAIN", "direct") == "direct")
 
     def _head_cc(self, n, d):
         """CUDA-core head kernels (csrc/head.cu): the default for the shipped shapes; FPL_HEAD_IMPL=tc selects the
