@@ -47,40 +47,78 @@ struct LossSrc {
     int prob_input;           // loss_softmax = False (loss/seg/abstract.py:16-21): `logits` already are probabilities
 };
 
+// One float4 group (4 voxels) of inputs as it comes from memory.  Loading and decoding are separate so that a thread can
+// issue the loads of U groups back to back (one DRAM round trip per batch) before the first use stalls it.
+template <int C, bool LEAN>
+struct RawGroup {
+    float4 z[C];
+    float4 y[C];              // soft_y layout
+    float4 wf;                // fp32 weight layout
+    uint32_t lab, code;       // uint8 layouts
+};
 template <int C>
-__device__ __forceinline__ void load_truth4(const LossSrc& src, int64_t n, int64_t s4, int64_t S4, float4 (&yv)[C]) {
-    if (src.soft_y != nullptr) {
+struct RawGroup<C, true> {    // uint8 labels, uint8 weight codes or no weights: 4C + 2 registers per group
+    float4 z[C];
+    uint32_t lab, code;
+};
+
+template <int C, bool LEAN>
+__device__ __forceinline__ void load_raw(const float* __restrict__ logits, const LossSrc& src, int64_t n, int64_t s4, int64_t S4,
+                                         RawGroup<C, LEAN>& r) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) yv[c] = ld_stream_f4(reinterpret_cast<const float4*>(src.soft_y) + (n * C + c) * S4 + s4);
-    } else {
-        const uint32_t lab = __ldg(reinterpret_cast<const uint32_t*>(src.label) + n * S4 + s4);
+    for (int c = 0; c < C; ++c) r.z[c] = ld_stream_f4(reinterpret_cast<const float4*>(logits) + (n * C + c) * S4 + s4);
+    if constexpr (!LEAN) {
+        if (src.soft_y != nullptr) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) r.y[c] = ld_stream_f4(reinterpret_cast<const float4*>(src.soft_y) + (n * C + c) * S4 + s4);
+        }
+        if (src.weight != nullptr) r.wf = ld_stream_f4(reinterpret_cast<const float4*>(src.weight) + n * S4 + s4);
+    }
+    if (LEAN || src.soft_y == nullptr) r.lab = __ldg(reinterpret_cast<const uint32_t*>(src.label) + n * S4 + s4);
+    if ((LEAN || src.weight == nullptr) && src.wcode != nullptr) r.code = __ldg(reinterpret_cast<const uint32_t*>(src.wcode) + n * S4 + s4);
+}
+
+template <int C, bool LEAN>
+__device__ __forceinline__ void decode_truth4(const LossSrc& src, const RawGroup<C, LEAN>& r, float4 (&yv)[C]) {
+    bool soft = false;
+    if constexpr (!LEAN) {
+        soft = src.soft_y != nullptr;
+        if (soft) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) yv[c] = r.y[c];
+        }
+    }
+    if (!soft) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int l = (int)((lab >> (8 * j)) & 0xffu);
+            const int l = (int)((r.lab >> (8 * j)) & 0xffu);
 #pragma unroll
             for (int c = 0; c < C; ++c) reinterpret_cast<float*>(&yv[c])[j] = (l == c) ? 1.0f : 0.0f;
         }
     }
 }
 
-__device__ __forceinline__ float4 load_weight4(const LossSrc& src, int64_t n, int64_t s4, int64_t S4) {
-    if (src.weight != nullptr) return ld_stream_f4(reinterpret_cast<const float4*>(src.weight) + n * S4 + s4);
+template <int C, bool LEAN>
+__device__ __forceinline__ float4 decode_weight4(const LossSrc& src, const RawGroup<C, LEAN>& r, float iw) {
+    if constexpr (!LEAN) {
+        if (src.weight != nullptr) return r.wf;
+    }
     if (src.wcode == nullptr) return make_float4(1.f, 1.f, 1.f, 1.f);
-    const uint32_t code = __ldg(reinterpret_cast<const uint32_t*>(src.wcode) + n * S4 + s4);
     const bool fold = src.image_w != nullptr;
-    const float iw = fold ? __ldg(src.image_w + n) : 1.0f;
     float4 w;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float a = 0.5f * (float)((code >> (8 * j)) & 0xffu);
+        const float a = 0.5f * (float)((r.code >> (8 * j)) & 0xffu);
         reinterpret_cast<float*>(&w)[j] = fold ? (a < 1.0f ? 0.0f : a) * iw : a;
     }
     return w;
 }
 
 // sums layout (double): I[C], Y[C], P[C], sum_w, sum_w_ce, HI[C], HY[C], HP[C], sum_c,v p*log2(p + 1e-10)
-template <int C>
-__global__ void __launch_bounds__(kThreads) dice_ce_reduce_kernel(const float* __restrict__ logits, LossSrc src,
+// grid = (blocks per sample, N): the sample index is blockIdx.y (no 64-bit division per group); a thread walks its groups
+// in batches of U whose loads are all issued before the first is used.
+template <int C, int U, bool LEAN>
+__global__ void __launch_bounds__(kThreads, LEAN ? (C <= 3 ? 3 : 2) : 1) dice_ce_reduce_kernel(const float* __restrict__ logits, LossSrc src,
                                                                  double* sums, int N, int64_t S4, int want_entropy) {
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const bool weighted = src.weight != nullptr || src.wcode != nullptr;
@@ -88,15 +126,22 @@ __global__ void __launch_bounds__(kThreads) dice_ce_reduce_kernel(const float* _
     float acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i] = 0.0f;
-    const int64_t total = (int64_t)N * S4;   // float4 groups
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-        int64_t n = g / S4, s4 = g - n * S4;
-        float4 zv[C], yv[C];
+    const int64_t n = blockIdx.y;
+    const float iw = src.image_w != nullptr && src.wcode != nullptr && src.weight == nullptr ? __ldg(src.image_w + n) : 1.0f;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g0 < S4; g0 += U * stride) {
+        RawGroup<C, LEAN> raw[U];
 #pragma unroll
-        for (int c = 0; c < C; ++c) zv[c] = ld_stream_f4(reinterpret_cast<const float4*>(logits) + (n * C + c) * S4 + s4);
-        load_truth4<C>(src, n, s4, S4, yv);
+        for (int u = 0; u < U; ++u)
+            if (g0 + u * stride < S4) load_raw<C, LEAN>(logits, src, n, g0 + u * stride, S4, raw[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+        if (g0 + u * stride >= S4) break;
+        float4 yv[C];
+        decode_truth4<C, LEAN>(src, raw[u], yv);
         float4 wv = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (weighted) wv = load_weight4(src, n, s4, S4);
+        if (weighted) wv = decode_weight4<C, LEAN>(src, raw[u], iw);
+        const float4 (&zv)[C] = raw[u].z;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float z[C], y[C], p[C];
@@ -138,6 +183,7 @@ __global__ void __launch_bounds__(kThreads) dice_ce_reduce_kernel(const float* _
                 }
             }
         }
+        }
     }
     __shared__ float sm[kThreads / 32][NV];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -155,8 +201,8 @@ __global__ void __launch_bounds__(kThreads) dice_ce_reduce_kernel(const float* _
     }
 }
 
-template <int C>
-__global__ void __launch_bounds__(kThreads) dice_ce_grad_kernel(const float* __restrict__ logits, LossSrc src,
+template <int C, int U, bool LEAN>
+__global__ void __launch_bounds__(kThreads, LEAN ? (C <= 3 ? 3 : 2) : 1) dice_ce_grad_kernel(const float* __restrict__ logits, LossSrc src,
                                                                const double* __restrict__ sums, float w_dice,
                                                                float w_ce, float w_ent, float grad_scale,
                                                                const float* __restrict__ grad_scale_dev, float* loss,
@@ -191,15 +237,23 @@ __global__ void __launch_bounds__(kThreads) dice_ce_grad_kernel(const float* __r
     if (dlogits == nullptr) return;
     const float ce_k = (float)(-(double)w_ce * 0.999 / ce_den);
     const float ent_k = (float)(-(double)w_ent / V);
-    const int64_t total = (int64_t)N * S4;
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-        int64_t n = g / S4, s4 = g - n * S4;
-        float4 zv[C], yv[C], ov[C];
+    const int64_t n = blockIdx.y;
+    const float iw = src.image_w != nullptr && src.wcode != nullptr && src.weight == nullptr ? __ldg(src.image_w + n) : 1.0f;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g0 < S4; g0 += U * stride) {
+        RawGroup<C, LEAN> raw[U];
 #pragma unroll
-        for (int c = 0; c < C; ++c) zv[c] = ld_stream_f4(reinterpret_cast<const float4*>(logits) + (n * C + c) * S4 + s4);
-        load_truth4<C>(src, n, s4, S4, yv);
+        for (int u = 0; u < U; ++u)
+            if (g0 + u * stride < S4) load_raw<C, LEAN>(logits, src, n, g0 + u * stride, S4, raw[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+        const int64_t s4 = g0 + u * stride;
+        if (s4 >= S4) break;
+        float4 yv[C], ov[C];
+        decode_truth4<C, LEAN>(src, raw[u], yv);
         float4 wv = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (weighted) wv = load_weight4(src, n, s4, S4);
+        if (weighted) wv = decode_weight4<C, LEAN>(src, raw[u], iw);
+        const float4 (&zv)[C] = raw[u].z;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float z[C], y[C], p[C], gp[C];
@@ -231,14 +285,16 @@ __global__ void __launch_bounds__(kThreads) dice_ce_grad_kernel(const float* __r
         }
 #pragma unroll
         for (int c = 0; c < C; ++c) reinterpret_cast<float4*>(dlogits)[(n * C + c) * S4 + s4] = ov[c];
+        }
     }
 }
 
-int grid_for(int64_t groups) {
-    int64_t blocks = (groups + kThreads - 1) / kThreads;
-    int64_t cap = (int64_t)FPL_NUM_SMS * 8;
-    if (blocks > cap) blocks = cap;
-    return (int)(blocks < 1 ? 1 : blocks);
+// blocks per sample: every thread one batch of U groups, capped at `per_sm` resident blocks per SM over the whole grid
+int grid_x_for(int64_t s4, int n, int u, int per_sm) {
+    int64_t bx = (s4 + (int64_t)kThreads * u - 1) / ((int64_t)kThreads * u);
+    int64_t cap = ((int64_t)FPL_NUM_SMS * per_sm + n - 1) / n;
+    if (bx > cap) bx = cap;
+    return (int)(bx < 1 ? 1 : bx);
 }
 
 }  // namespace
@@ -260,12 +316,22 @@ static int dice_ce_reduce_launch(const float* logits, const LossSrc& src, double
     FPL_REQUIRE(spatial % 4 == 0, "fpl_dice_ce_reduce: spatial size %lld must be a multiple of 4", (long long)spatial);
     FPL_REQUIRE(src.soft_y != nullptr || src.label != nullptr, "fpl_dice_ce_reduce: soft_y or label required");
     int64_t s4 = spatial / 4;
+    FPL_REQUIRE(n >= 1 && n <= 65535, "fpl_dice_ce_reduce: batch %d not in [1,65535]", n);
     // 4 blocks per SM: every block ends with 6C+3 same-address double atomics, which serialise in L2 (1184 blocks cost
-    // ~5 us of a 15 us launch at the configs[2] batch)
-    int rgrid = grid_for((int64_t)n * s4);
-    if (rgrid > FPL_NUM_SMS * 4) rgrid = FPL_NUM_SMS * 4;
-    FPL_DISPATCH_C(c, (fpl_launch(dice_ce_reduce_kernel<CC>, rgrid, kThreads, 0, (cudaStream_t)stream, 
-                          logits, src, sums, n, s4, want_entropy)));
+    // ~5 us of a 15 us launch at the configs[2] batch); two classes with uint8 labels: batches of 4 groups per thread
+    const bool lean = src.soft_y == nullptr && src.weight == nullptr;
+    if (c == 2 && lean) {
+        fpl_launch(dice_ce_reduce_kernel<2, 4, true>, dim3(grid_x_for(s4, n, 4, 4), n), kThreads, 0, (cudaStream_t)stream, logits,
+                   src, sums, n, s4, want_entropy);
+    } else if (lean) {
+        const dim3 rgrid(grid_x_for(s4, n, c <= 5 ? 2 : 1, 4), n);
+        FPL_DISPATCH_C(c, (fpl_launch(dice_ce_reduce_kernel<CC, (CC <= 5 ? 2 : 1), true>, rgrid, kThreads, 0, (cudaStream_t)stream,
+                              logits, src, sums, n, s4, want_entropy)));
+    } else {
+        const dim3 rgrid(grid_x_for(s4, n, 1, 4), n);
+        FPL_DISPATCH_C(c, (fpl_launch(dice_ce_reduce_kernel<CC, 1, false>, rgrid, kThreads, 0, (cudaStream_t)stream,
+                              logits, src, sums, n, s4, want_entropy)));
+    }
     FPL_LAUNCH_CHECK();
     return 0;
 }
@@ -277,9 +343,22 @@ static int dice_ce_grad_launch(const float* logits, const LossSrc& src, const do
     FPL_REQUIRE(spatial % 4 == 0, "fpl_dice_ce_grad: spatial size %lld must be a multiple of 4", (long long)spatial);
     FPL_REQUIRE(src.soft_y != nullptr || src.label != nullptr, "fpl_dice_ce_grad: soft_y or label required");
     int64_t s4 = spatial / 4;
-    int grid = dlogits != nullptr ? grid_for((int64_t)n * s4) : 1;
-    FPL_DISPATCH_C(c, (fpl_launch(dice_ce_grad_kernel<CC>, grid, kThreads, 0, (cudaStream_t)stream, 
-                          logits, src, sums, w_dice, w_ce, w_ent, grad_scale, grad_scale_dev, loss, dlogits, n, s4, n_global)));
+    FPL_REQUIRE(n >= 1 && n <= 65535, "fpl_dice_ce_grad: batch %d not in [1,65535]", n);
+    const bool lean = src.soft_y == nullptr && src.weight == nullptr;
+    const int gy = dlogits != nullptr ? n : 1;
+    if (c == 2 && lean) {
+        const dim3 grid(dlogits != nullptr ? grid_x_for(s4, n, 4, 4) : 1, gy);
+        fpl_launch(dice_ce_grad_kernel<2, 4, true>, grid, kThreads, 0, (cudaStream_t)stream, logits, src, sums, w_dice, w_ce, w_ent,
+                   grad_scale, grad_scale_dev, loss, dlogits, n, s4, n_global);
+    } else if (lean) {
+        const dim3 grid(dlogits != nullptr ? grid_x_for(s4, n, c <= 5 ? 2 : 1, 4) : 1, gy);
+        FPL_DISPATCH_C(c, (fpl_launch(dice_ce_grad_kernel<CC, (CC <= 5 ? 2 : 1), true>, grid, kThreads, 0, (cudaStream_t)stream,
+                              logits, src, sums, w_dice, w_ce, w_ent, grad_scale, grad_scale_dev, loss, dlogits, n, s4, n_global)));
+    } else {
+        const dim3 grid(dlogits != nullptr ? grid_x_for(s4, n, 1, 8) : 1, gy);
+        FPL_DISPATCH_C(c, (fpl_launch(dice_ce_grad_kernel<CC, 1, false>, grid, kThreads, 0, (cudaStream_t)stream,
+                              logits, src, sums, w_dice, w_ce, w_ent, grad_scale, grad_scale_dev, loss, dlogits, n, s4, n_global)));
+    }
     FPL_LAUNCH_CHECK();
     return 0;
 }
