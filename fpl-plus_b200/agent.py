@@ -568,7 +568,7 @@ class SegmentationAgent(object):
             if self._side_stream is None:
                 self._side_stream = torch.cuda.Stream()
             self._side_stream.wait_stream(main)
-        total, n_dom, dices = None, 0, []
+        losses, dices = [], []
         for d in present:
             data = batches[d]
             stream = self._side_stream if (fork and d == present[1]) else main
@@ -581,9 +581,12 @@ class SegmentationAgent(object):
                 dices.append(hd() if hd is not None else None)
             if fork and stream is not main:
                 main.wait_stream(stream)
-            total = loss_d if total is None else total + loss_d
-            n_dom += 1
-        loss = total / n_dom if n_dom > 1 else total
+            losses.append(loss_d)
+        n_dom = len(losses)
+        # L = mean_d L_d (agent_seg.py:467).  (Making every domain loss its own backward root with a constant upstream
+        # gradient, so that no scalar kernels sit between forward and backward, measured neutral and moved the reported
+        # value's two kernels into the tail of the step: not kept.)
+        loss = losses[0] if n_dom == 1 else (losses[0] + losses[1]) / n_dom if n_dom == 2 else sum(losses) / n_dom
         loss.backward()
         if fork:
             main.wait_stream(self._side_stream)

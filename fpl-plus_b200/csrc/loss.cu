@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(kThreads, LEAN ? (C <= 3 ? 3 : 2) : 1) dice_ce
                                                                const double* __restrict__ sums, float w_dice,
                                                                float w_ce, float w_ent, float grad_scale,
                                                                const float* __restrict__ grad_scale_dev, float* loss,
-                                                               float* dlogits, int N, int64_t S4, int n_global) {
+                                                               float* dlogits, int N, int64_t S4, int n_global,
+                                                               double* hard_dice) {
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const bool weighted = src.weight != nullptr || src.wcode != nullptr;
     if (grad_scale_dev != nullptr) grad_scale *= __ldg(grad_scale_dev);
@@ -233,6 +234,12 @@ __global__ void __launch_bounds__(kThreads, LEAN ? (C <= 3 ? 3 : 2) : 1) dice_ce
         // entropy regulariser of agent_seg.py:353,467: -sum p*log2(p + 1e-10) / (N*D*H*W)
         if (w_ent != 0.0f) l += (double)w_ent * (-sums[6 * C + 2] / V);
         loss[0] = (float)l;
+        // class-wise Dice of the argmax one-hot against the ground truth (agent_seg.py:472-476) from the hard counters
+        if (hard_dice != nullptr) {
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                hard_dice[c] = (2.0 * sums[3 * C + 2 + c] + 1e-5) / (sums[3 * C + 2 + C + c] + sums[3 * C + 2 + 2 * C + c] + 1e-5);
+        }
     }
     if (dlogits == nullptr) return;
     const float ce_k = (float)(-(double)w_ce * 0.999 / ce_den);
@@ -338,7 +345,7 @@ static int dice_ce_reduce_launch(const float* logits, const LossSrc& src, double
 
 static int dice_ce_grad_launch(const float* logits, const LossSrc& src, const double* sums, float w_dice, float w_ce,
                                float w_ent, float grad_scale, const float* grad_scale_dev, float* loss, float* dlogits,
-                               int n, int c, int64_t spatial, void* stream, int n_global = 0) {
+                               int n, int c, int64_t spatial, void* stream, int n_global = 0, double* hard_dice = nullptr) {
     FPL_REQUIRE(n_global == 0 || n_global >= n, "fpl_dice_ce_grad: n_global %d < n %d", n_global, n);
     FPL_REQUIRE(spatial % 4 == 0, "fpl_dice_ce_grad: spatial size %lld must be a multiple of 4", (long long)spatial);
     FPL_REQUIRE(src.soft_y != nullptr || src.label != nullptr, "fpl_dice_ce_grad: soft_y or label required");
@@ -349,15 +356,15 @@ static int dice_ce_grad_launch(const float* logits, const LossSrc& src, const do
     if (c == 2 && lean) {
         const dim3 grid(dlogits != nullptr ? grid_x_for(s4, n, 4, 4) : 1, gy);
         fpl_launch(dice_ce_grad_kernel<2, 4, true>, grid, kThreads, 0, (cudaStream_t)stream, logits, src, sums, w_dice, w_ce, w_ent,
-                   grad_scale, grad_scale_dev, loss, dlogits, n, s4, n_global);
+                   grad_scale, grad_scale_dev, loss, dlogits, n, s4, n_global, hard_dice);
     } else if (lean) {
         const dim3 grid(dlogits != nullptr ? grid_x_for(s4, n, c <= 5 ? 2 : 1, 4) : 1, gy);
         FPL_DISPATCH_C(c, (fpl_launch(dice_ce_grad_kernel<CC, (CC <= 5 ? 2 : 1), true>, grid, kThreads, 0, (cudaStream_t)stream,
-                              logits, src, sums, w_dice, w_ce, w_ent, grad_scale, grad_scale_dev, loss, dlogits, n, s4, n_global)));
+                              logits, src, sums, w_dice, w_ce, w_ent, grad_scale, grad_scale_dev, loss, dlogits, n, s4, n_global, hard_dice)));
     } else {
         const dim3 grid(dlogits != nullptr ? grid_x_for(s4, n, 1, 8) : 1, gy);
         FPL_DISPATCH_C(c, (fpl_launch(dice_ce_grad_kernel<CC, 1, false>, grid, kThreads, 0, (cudaStream_t)stream,
-                              logits, src, sums, w_dice, w_ce, w_ent, grad_scale, grad_scale_dev, loss, dlogits, n, s4, n_global)));
+                              logits, src, sums, w_dice, w_ce, w_ent, grad_scale, grad_scale_dev, loss, dlogits, n, s4, n_global, hard_dice)));
     }
     FPL_LAUNCH_CHECK();
     return 0;
@@ -394,4 +401,14 @@ extern "C" int fpl_dice_ce_grad_ex(const float* logits, const float* soft_y, con
     LossSrc src = {soft_y, label, weight, weight_code, image_weight, prob_input};
     return dice_ce_grad_launch(logits, src, sums, w_dice, w_ce, w_entropy, grad_scale, grad_scale_dev, loss, dlogits, n,
                                c, spatial, stream, n_global);
+}
+
+extern "C" int fpl_dice_ce_loss_ex(const float* logits, const float* soft_y, const uint8_t* label, const float* weight,
+                                   const uint8_t* weight_code, const float* image_weight, const double* sums,
+                                   float w_dice, float w_ce, float w_entropy, float* loss, double* hard_dice, int n, int c,
+                                   int64_t spatial, int prob_input, int n_global, void* stream) {
+    FPL_REQUIRE(loss != nullptr, "fpl_dice_ce_loss_ex: loss must not be NULL");
+    LossSrc src = {soft_y, label, weight, weight_code, image_weight, prob_input};
+    return dice_ce_grad_launch(logits, src, sums, w_dice, w_ce, w_entropy, 1.0f, nullptr, loss, nullptr, n, c, spatial, stream,
+                               n_global, hard_dice);
 }

@@ -89,6 +89,7 @@ _SIGNATURES = {
     "fpl_dice_ce_grad": (_I, [_P, _P, _P, _P, _F, _F, _F, _P, _P, _P, _I, _I, _L, _P]),
     "fpl_dice_ce_reduce_ex": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _I, _I, _P]),
     "fpl_dice_ce_grad_ex": (_I, [_P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _P, _P, _P, _I, _I, _L, _I, _I, _P]),
+    "fpl_dice_ce_loss_ex": (_I, [_P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _P, _P, _I, _I, _L, _I, _I, _P]),
     "fpl_argmax_label": (_I, [_P, _P, _I, _I, _L, _P]),
     "fpl_mc_uncertainty": (_I, [ctypes.POINTER(c_void_p), _I, _I, _L, _P, _P, _P]),
     "fpl_mc_uncertainty_max_passes": (_I, []),

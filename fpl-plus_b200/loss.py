@@ -87,12 +87,14 @@ class _DiceCE(torch.autograd.Function):
         if red is not None:
             world = int(red(sums))
         loss = torch.empty((), dtype=torch.float32, device=logits.device)
-        call("fpl_dice_ce_grad_ex", ptr(logits), *src, ptr(sums), w_dice, w_ce, w_ent, 1.0, None, ptr(loss), None, n, c,
+        hard = torch.empty(c, dtype=torch.float64, device=logits.device)
+        call("fpl_dice_ce_loss_ex", ptr(logits), *src, ptr(sums), w_dice, w_ce, w_ent, ptr(loss), ptr(hard), n, c,
              spatial, prob_input, n * world if world > 1 else 0, st)
         ctx.saved = (logits, truth, weight, sums)
         ctx.w = (w_dice, w_ce, w_ent, prob_input, world)
         if holder is not None:
             holder["sums"] = sums
+            holder["hard_dice"] = hard
             holder["voxels"] = n * spatial
         return loss
 
@@ -136,6 +138,10 @@ class _FusedSegLoss(nn.Module):
                              0 if self.softmax else 1, self.last)
 
     def last_hard_dice(self):
+        """Class-wise hard Dice of the last call (agent_seg.py:472-476), written by the loss-value launch."""
+        h = self.last.get("hard_dice")
+        if h is not None:
+            return h
         s = self.last.get("sums")
         return None if s is None else hard_dice_from_sums(s, (s.numel() - 3) // 6)
 

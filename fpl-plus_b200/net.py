@@ -1010,7 +1010,19 @@ class UNet2D5_dsbn(nn.Module):
                             for t in (up.trans3d, up.trans2d) if t is not None) + sum(
                             9 * u.cin * u.cout for u in self._proj_units)
             scratch = ws.get("wgrad_scratch", (total,), torch.float32)
-            scratch.zero_()
+            aux0 = self._aux_stream()
+            if aux0 is not None:
+                # 20+ MB zero fill: on the weight-gradient side stream, under the head dgrad (whose bias gradient needs
+                # `flat`, not the scratch); the main stream picks the event up before its first scratch user
+                cur0 = torch.cuda.current_stream()
+                aux0.wait_stream(cur0)
+                with torch.cuda.stream(aux0):
+                    scratch.zero_()
+                scratch_zeroed = torch.cuda.Event()
+                scratch_zeroed.record(aux0)
+            else:
+                scratch.zero_()
+                scratch_zeroed = None
             cursor = [0]
 
             def alloc(numel):
@@ -1052,6 +1064,10 @@ class UNet2D5_dsbn(nn.Module):
         st = stream_ptr()
         d, h, w = geo[0]
         head_in = rec["head_in"]
+
+        def scratch_ready():
+            if fold is not None and scratch_zeroed is not None:
+                torch.cuda.current_stream().wait_event(scratch_zeroed)
         g = C8(ws.c8("dX:head", n, d, ft[0], h, w))
         dlogits = dlogits.contiguous()
         if self._head_cc(n, d):
@@ -1061,6 +1077,7 @@ class UNet2D5_dsbn(nn.Module):
             dl8 = ws.c8("dL8", n, d, 8, h, w)
             call("fpl_head_dgrad", ptr(dlogits), ptr(self.out_conv.weight), *g.args(), ptr(dl8), 1, 0,
                  ptr(grads[self.out_conv.bias]), n, d, h, w, ft[0], k, st)
+            scratch_ready()
             if fold is not None:
                 scr = fold["alloc"](8 * ft[0] * 9)
                 call("fpl_conv3d_wgrad_tc_tapmajor", *head_in.args(), ptr(dl8), 1, 0, ptr(scr), n, d, h, w, ft[0], 8, 1, st)
@@ -1081,6 +1098,7 @@ class UNet2D5_dsbn(nn.Module):
             # wgrad against the first channel group of dl16 only (classes padded to 8): 4 depth planes are stacked in
             # M and N, so one MMA set covers 4 planes (csrc/conv_wgrad_tc.cu, ndy = 4)
             co = 8 if (ft[0] <= 32 and d >= 2) else 16
+            scratch_ready()
             if fold is not None:
                 # tap-major scratch; only the k real classes are folded into the head's gradient
                 scr = fold["alloc"](co * ft[0] * 9)
@@ -1094,6 +1112,7 @@ class UNet2D5_dsbn(nn.Module):
         else:
             call("fpl_head_conv_bwd", *head_in.args(), ptr(self.out_conv.weight), ptr(dlogits), *g.args(),
                  ptr(grads[self.out_conv.weight]), ptr(grads[self.out_conv.bias]), n, d, h, w, ft[0], self.n_class, st)
+        scratch_ready()
         ups = [self.up1, self.up2, self.up3, self.up4]
         skip_grads = {}
         done = 2

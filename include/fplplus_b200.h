@@ -366,6 +366,14 @@ int fpl_dice_ce_grad_ex(const float* logits, const float* soft_y, const uint8_t*
                         float w_dice, float w_ce, float w_entropy, float grad_scale, const float* grad_scale_dev,
                         float* loss, float* dlogits, int n, int c, int64_t spatial, int prob_input, int n_global,
                         void* stream);
+/* Loss value only (one small launch, no gradient pass): loss[0] as fpl_dice_ce_grad_ex writes it, and -- when hard_dice
+ * is not NULL -- hard_dice[c] = (2*HI_c + 1e-5) / (HY_c + HP_c + 1e-5), the class-wise Dice of the argmax one-hot
+ * against the ground truth that training_all logs every iteration (agent_seg.py:472-476, loss/seg/util.py:85-107), from
+ * the hard counters of the same sums (replaces five element-wise torch kernels per domain pass). */
+int fpl_dice_ce_loss_ex(const float* logits, const float* soft_y, const uint8_t* label, const float* weight,
+                        const uint8_t* weight_code, const float* image_weight, const double* sums,
+                        float w_dice, float w_ce, float w_entropy, float* loss, double* hard_dice, int n, int c,
+                        int64_t spatial, int prob_input, int n_global, void* stream);
 
 /* ---- (c) pseudo-label filter: agent_seg.py:897-931,1045-1050; data/get_pixel_weight.py:21-26;
  *          io/nifty_dataset.py:165-168 ---- */
