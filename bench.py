@@ -178,6 +178,11 @@ def _k311_work(a, off):
     return 2.0 * n * d * h * w * cin * cout * 3, float(n * d * h * w * (cin + cout) * 2)
 
 
+def _stem_work(a, off):
+    n, cin, d, h, w, cout, kd = a[off:off + 7]
+    return 2.0 * n * d * h * w * cin * cout * kd * 9, float(n * d * h * w * (4 * cin + 2 * cout))
+
+
 WORK = {   # entry point -> (flops, algorithmic bytes) from its argument tuple
     "fpl_conv3d_tc": lambda a: _conv_work(a, 9),
     "fpl_conv3d_tc_dfold": _dfold_work,
@@ -186,10 +191,13 @@ WORK = {   # entry point -> (flops, algorithmic bytes) from its argument tuple
     "fpl_conv3d_wgrad_tc": lambda a: _conv_work(a, 7),
     "fpl_conv3d_wgrad_tc_tapmajor": lambda a: _conv_work(a, 7),
     "fpl_conv3d_wgrad_tc_k311": lambda a: _k311_work(a, 7),
+    # the 1-channel stem straight from the fp32 image (csrc/stem_tc.cu): n, cin, d, h, w, cout, kd
+    "fpl_stem_conv_fwd": lambda a: _stem_work(a, 7),
+    "fpl_stem_conv_wgrad": lambda a: _stem_work(a, 5),
 }
 # entry points that launch the SAME kernel are one roofline population (the ncu capture sees kernel names):
 # the wgrad entry points launch conv3d_wgrad_hs_kernel (k3, Cin 16 / 32: levels 0-1) or conv3d_wgrad_tc_kernel (the other
-# k3 / k(1,3,3) wgrads, the head wgrad and the stem's k(3,1,1) wgrad): ONE population, the weight-gradient kernels
+# k3 / k(1,3,3) wgrads, the head wgrad; the stem's k(3,1,1) wgrad when FPL_STEM_TRAIN=patch): ONE population, the weight-gradient kernels
 WGRAD_KERNELS = "conv3d_wgrad_hs_kernel+conv3d_wgrad_tc_kernel"
 KERNEL_OF = {"fpl_conv3d_wgrad_tc_tapmajor": WGRAD_KERNELS, "fpl_conv3d_wgrad_tc": WGRAD_KERNELS,
              "fpl_conv3d_wgrad_tc_k311": WGRAD_KERNELS, "fpl_conv3d_tc": "conv3d_tc_kernel",

@@ -17,10 +17,21 @@ __global__ void __launch_bounds__(256) grad_scatter_add_kernel(float* __restrict
     const float* sp = src + so;
     float* dp = dst + dof;
     const int n4 = n >> 2;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
-        const float4 v = ld_stream_f4(sp + 4 * i);
-        float* d = dp + 4 * i;
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    // batches of 4 loads per thread before the first reduction is issued (one load -> red per iteration made the largest
+    // segments, 1.8 M floats on 64 blocks, 27 memory round trips long)
+    const int stride = gridDim.x * blockDim.x;
+    for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += 4 * stride) {
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i0 + k * stride < n4) v[k] = ld_stream_f4(sp + 4 * (int64_t)(i0 + k * stride));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i0 + k * stride < n4) {
+                float* d = dp + 4 * (int64_t)(i0 + k * stride);
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(v[k].x), "f"(v[k].y), "f"(v[k].z), "f"(v[k].w) : "memory");
+            }
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) atomicAdd(dp + 4 * n4 + threadIdx.x, __ldg(sp + 4 * n4 + threadIdx.x));
 }
@@ -35,7 +46,7 @@ extern "C" int fpl_grad_scatter_add(float* dst, const float* src, const int* d_t
                 "fpl_grad_scatter_add: buffers must be 16-byte aligned");
     int bx = (max_numel / 4 + 1023) / 1024;
     if (bx < 1) bx = 1;
-    if (bx > 64) bx = 64;
+    if (bx > 128) bx = 128;
     fpl_launch(grad_scatter_add_kernel, dim3(bx, segments), 256, 0, (cudaStream_t)stream, dst, src, d_table);
     FPL_LAUNCH_CHECK();
     return 0;

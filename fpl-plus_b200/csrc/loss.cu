@@ -118,7 +118,7 @@ __device__ __forceinline__ float4 decode_weight4(const LossSrc& src, const RawGr
 // grid = (blocks per sample, N): the sample index is blockIdx.y (no 64-bit division per group); a thread walks its groups
 // in batches of U whose loads are all issued before the first is used.
 template <int C, int U, bool LEAN>
-__global__ void __launch_bounds__(kThreads, LEAN ? (C <= 3 ? 3 : 2) : 1) dice_ce_reduce_kernel(const float* __restrict__ logits, LossSrc src,
+__global__ void __launch_bounds__(kThreads, LEAN ? (C == 2 && U == 8 ? 2 : (C <= 3 ? 3 : 2)) : 1) dice_ce_reduce_kernel(const float* __restrict__ logits, LossSrc src,
                                                                  double* sums, int N, int64_t S4, int want_entropy) {
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const bool weighted = src.weight != nullptr || src.wcode != nullptr;
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, LEAN ? (C <= 3 ? 3 : 2) : 1) dice_ce
 }
 
 template <int C, int U, bool LEAN>
-__global__ void __launch_bounds__(kThreads, LEAN ? (C <= 3 ? 3 : 2) : 1) dice_ce_grad_kernel(const float* __restrict__ logits, LossSrc src,
+__global__ void __launch_bounds__(kThreads, LEAN ? (C == 2 && U == 8 ? 2 : (C <= 3 ? 3 : 2)) : 1) dice_ce_grad_kernel(const float* __restrict__ logits, LossSrc src,
                                                                const double* __restrict__ sums, float w_dice,
                                                                float w_ce, float w_ent, float grad_scale,
                                                                const float* __restrict__ grad_scale_dev, float* loss,
@@ -296,6 +296,21 @@ __global__ void __launch_bounds__(kThreads, LEAN ? (C <= 3 ? 3 : 2) : 1) dice_ce
     }
 }
 
+// resident blocks per SM of a kernel instantiation (registers decide: 2..4), so that a grid is exactly one wave
+template <typename K>
+int resident_blocks(K kernel) {
+    // all instantiations of one kernel template share a function TYPE, hence this cache: keyed by the function pointer
+    static int cached = 0;
+    static const void* cached_for = nullptr;
+    if (cached == 0 || cached_for != (const void*)kernel) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kThreads, 0) != cudaSuccess || nb < 1) nb = 1;
+        cached = nb > 4 ? 4 : nb;    // every block ends with 6C+3 same-address double atomics: no more than 4 per SM
+        cached_for = (const void*)kernel;
+    }
+    return cached;
+}
+
 // blocks per sample: every thread one batch of U groups, capped at `per_sm` resident blocks per SM over the whole grid
 int grid_x_for(int64_t s4, int n, int u, int per_sm) {
     int64_t bx = (s4 + (int64_t)kThreads * u - 1) / ((int64_t)kThreads * u);
@@ -325,19 +340,21 @@ static int dice_ce_reduce_launch(const float* logits, const LossSrc& src, double
     int64_t s4 = spatial / 4;
     FPL_REQUIRE(n >= 1 && n <= 65535, "fpl_dice_ce_reduce: batch %d not in [1,65535]", n);
     // 4 blocks per SM: every block ends with 6C+3 same-address double atomics, which serialise in L2 (1184 blocks cost
-    // ~5 us of a 15 us launch at the configs[2] batch); two classes with uint8 labels: batches of 4 groups per thread
+    // ~5 us of a 15 us launch at the configs[2] batch)
     const bool lean = src.soft_y == nullptr && src.weight == nullptr;
     if (c == 2 && lean) {
-        fpl_launch(dice_ce_reduce_kernel<2, 4, true>, dim3(grid_x_for(s4, n, 4, 4), n), kThreads, 0, (cudaStream_t)stream, logits,
-                   src, sums, n, s4, want_entropy);
+        // two classes, uint8 inputs: ONE wave of two 256-thread blocks per SM, every thread one batch of up to 8 groups
+        // (~140 KB of loads in flight per SM = the bandwidth-delay product: one DRAM round trip per launch)
+        fpl_launch(dice_ce_reduce_kernel<2, 8, true>, dim3(grid_x_for(s4, n, 8, resident_blocks(dice_ce_reduce_kernel<2, 8, true>)), n), kThreads, 0,
+                   (cudaStream_t)stream, logits, src, sums, n, s4, want_entropy);
     } else if (lean) {
-        const dim3 rgrid(grid_x_for(s4, n, c <= 5 ? 2 : 1, 4), n);
-        FPL_DISPATCH_C(c, (fpl_launch(dice_ce_reduce_kernel<CC, (CC <= 5 ? 2 : 1), true>, rgrid, kThreads, 0, (cudaStream_t)stream,
-                              logits, src, sums, n, s4, want_entropy)));
+        FPL_DISPATCH_C(c, (fpl_launch(dice_ce_reduce_kernel<CC, (CC <= 5 ? 2 : 1), true>,
+                              dim3(grid_x_for(s4, n, CC <= 5 ? 2 : 1, resident_blocks(dice_ce_reduce_kernel<CC, (CC <= 5 ? 2 : 1), true>)), n),
+                              kThreads, 0, (cudaStream_t)stream, logits, src, sums, n, s4, want_entropy)));
     } else {
-        const dim3 rgrid(grid_x_for(s4, n, 1, 4), n);
-        FPL_DISPATCH_C(c, (fpl_launch(dice_ce_reduce_kernel<CC, 1, false>, rgrid, kThreads, 0, (cudaStream_t)stream,
-                              logits, src, sums, n, s4, want_entropy)));
+        FPL_DISPATCH_C(c, (fpl_launch(dice_ce_reduce_kernel<CC, 1, false>,
+                              dim3(grid_x_for(s4, n, 1, resident_blocks(dice_ce_reduce_kernel<CC, 1, false>)), n),
+                              kThreads, 0, (cudaStream_t)stream, logits, src, sums, n, s4, want_entropy)));
     }
     FPL_LAUNCH_CHECK();
     return 0;
@@ -354,16 +371,18 @@ static int dice_ce_grad_launch(const float* logits, const LossSrc& src, const do
     const bool lean = src.soft_y == nullptr && src.weight == nullptr;
     const int gy = dlogits != nullptr ? n : 1;
     if (c == 2 && lean) {
-        const dim3 grid(dlogits != nullptr ? grid_x_for(s4, n, 4, 4) : 1, gy);
-        fpl_launch(dice_ce_grad_kernel<2, 4, true>, grid, kThreads, 0, (cudaStream_t)stream, logits, src, sums, w_dice, w_ce, w_ent,
+        const dim3 grid(dlogits != nullptr ? grid_x_for(s4, n, 8, resident_blocks(dice_ce_grad_kernel<2, 8, true>)) : 1, gy);
+        fpl_launch(dice_ce_grad_kernel<2, 8, true>, grid, kThreads, 0, (cudaStream_t)stream, logits, src, sums, w_dice, w_ce, w_ent,
                    grad_scale, grad_scale_dev, loss, dlogits, n, s4, n_global, hard_dice);
     } else if (lean) {
-        const dim3 grid(dlogits != nullptr ? grid_x_for(s4, n, c <= 5 ? 2 : 1, 4) : 1, gy);
-        FPL_DISPATCH_C(c, (fpl_launch(dice_ce_grad_kernel<CC, (CC <= 5 ? 2 : 1), true>, grid, kThreads, 0, (cudaStream_t)stream,
+        FPL_DISPATCH_C(c, (fpl_launch(dice_ce_grad_kernel<CC, (CC <= 5 ? 2 : 1), true>,
+                              dim3(dlogits != nullptr ? grid_x_for(s4, n, CC <= 5 ? 2 : 1, 2 * resident_blocks(dice_ce_grad_kernel<CC, (CC <= 5 ? 2 : 1), true>)) : 1, gy),
+                              kThreads, 0, (cudaStream_t)stream,
                               logits, src, sums, w_dice, w_ce, w_ent, grad_scale, grad_scale_dev, loss, dlogits, n, s4, n_global, hard_dice)));
     } else {
-        const dim3 grid(dlogits != nullptr ? grid_x_for(s4, n, 1, 8) : 1, gy);
-        FPL_DISPATCH_C(c, (fpl_launch(dice_ce_grad_kernel<CC, 1, false>, grid, kThreads, 0, (cudaStream_t)stream,
+        FPL_DISPATCH_C(c, (fpl_launch(dice_ce_grad_kernel<CC, 1, false>,
+                              dim3(dlogits != nullptr ? grid_x_for(s4, n, 1, 2 * resident_blocks(dice_ce_grad_kernel<CC, 1, false>)) : 1, gy),
+                              kThreads, 0, (cudaStream_t)stream,
                               logits, src, sums, w_dice, w_ce, w_ent, grad_scale, grad_scale_dev, loss, dlogits, n, s4, n_global, hard_dice)));
     }
     FPL_LAUNCH_CHECK();
