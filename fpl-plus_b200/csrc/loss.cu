@@ -4,6 +4,7 @@
 // (loss/seg/combined.py:34-39) and the training-time hard-Dice metric
 // (net_run_dsbn/agent_seg.py:472-476).  Pure HBM streaming over NCDHW fp32 (the layout the
 // PyMIC loss API hands over): 8C+4 bytes/voxel in the reduce pass, 12C+4 in the grad pass.
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/fplplus_b200.h"
 
@@ -118,7 +119,7 @@ __device__ __forceinline__ float4 decode_weight4(const LossSrc& src, const RawGr
 // grid = (blocks per sample, N): the sample index is blockIdx.y (no 64-bit division per group); a thread walks its groups
 // in batches of U whose loads are all issued before the first is used.
 template <int C, int U, bool LEAN>
-__global__ void __launch_bounds__(kThreads, LEAN ? (C == 2 && U == 8 ? 2 : (C <= 3 ? 3 : 2)) : 1) dice_ce_reduce_kernel(const float* __restrict__ logits, LossSrc src,
+__global__ void __launch_bounds__(kThreads, LEAN ? (C == 2 ? (U == 8 ? 2 : (U == 2 ? 4 : 3)) : (C <= 3 ? 3 : 2)) : 1) dice_ce_reduce_kernel(const float* __restrict__ logits, LossSrc src,
                                                                  double* sums, int N, int64_t S4, int want_entropy) {
     FPL_PDL_WAIT();      // everything below may read what earlier kernels of the stream wrote
     const bool weighted = src.weight != nullptr || src.wcode != nullptr;
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, LEAN ? (C == 2 && U == 8 ? 2 : (C <=
 }
 
 template <int C, int U, bool LEAN>
-__global__ void __launch_bounds__(kThreads, LEAN ? (C == 2 && U == 8 ? 2 : (C <= 3 ? 3 : 2)) : 1) dice_ce_grad_kernel(const float* __restrict__ logits, LossSrc src,
+__global__ void __launch_bounds__(kThreads, LEAN ? (C == 2 ? (U == 8 ? 2 : (U == 2 ? 4 : 3)) : (C <= 3 ? 3 : 2)) : 1) dice_ce_grad_kernel(const float* __restrict__ logits, LossSrc src,
                                                                const double* __restrict__ sums, float w_dice,
                                                                float w_ce, float w_ent, float grad_scale,
                                                                const float* __restrict__ grad_scale_dev, float* loss,
@@ -311,6 +312,17 @@ int resident_blocks(K kernel) {
     return cached;
 }
 
+// groups per thread and batch of the two-class uint8 kernels: 8 (one wave of two register-heavy blocks per SM, one DRAM
+// round trip) or, FPL_LOSS_BATCH=2, 2 (four blocks per SM, two round trips, more warps to hide the exp / log chains)
+int loss_batch() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("FPL_LOSS_BATCH");
+        v = (e != nullptr && atoi(e) == 2) ? 2 : 8;
+    }
+    return v;
+}
+
 // blocks per sample: every thread one batch of U groups, capped at `per_sm` resident blocks per SM over the whole grid
 int grid_x_for(int64_t s4, int n, int u, int per_sm) {
     int64_t bx = (s4 + (int64_t)kThreads * u - 1) / ((int64_t)kThreads * u);
@@ -345,6 +357,10 @@ static int dice_ce_reduce_launch(const float* logits, const LossSrc& src, double
     if (c == 2 && lean) {
         // two classes, uint8 inputs: ONE wave of two 256-thread blocks per SM, every thread one batch of up to 8 groups
         // (~140 KB of loads in flight per SM = the bandwidth-delay product: one DRAM round trip per launch)
+        if (loss_batch() == 2)
+            fpl_launch(dice_ce_reduce_kernel<2, 2, true>, dim3(grid_x_for(s4, n, 2, resident_blocks(dice_ce_reduce_kernel<2, 2, true>)), n), kThreads, 0,
+                       (cudaStream_t)stream, logits, src, sums, n, s4, want_entropy);
+        else
         fpl_launch(dice_ce_reduce_kernel<2, 8, true>, dim3(grid_x_for(s4, n, 8, resident_blocks(dice_ce_reduce_kernel<2, 8, true>)), n), kThreads, 0,
                    (cudaStream_t)stream, logits, src, sums, n, s4, want_entropy);
     } else if (lean) {
@@ -371,6 +387,13 @@ static int dice_ce_grad_launch(const float* logits, const LossSrc& src, const do
     const bool lean = src.soft_y == nullptr && src.weight == nullptr;
     const int gy = dlogits != nullptr ? n : 1;
     if (c == 2 && lean) {
+        if (loss_batch() == 2) {
+            const dim3 grid2(dlogits != nullptr ? grid_x_for(s4, n, 2, resident_blocks(dice_ce_grad_kernel<2, 2, true>)) : 1, gy);
+            fpl_launch(dice_ce_grad_kernel<2, 2, true>, grid2, kThreads, 0, (cudaStream_t)stream, logits, src, sums, w_dice, w_ce, w_ent,
+                       grad_scale, grad_scale_dev, loss, dlogits, n, s4, n_global, hard_dice);
+            FPL_LAUNCH_CHECK();
+            return 0;
+        }
         const dim3 grid(dlogits != nullptr ? grid_x_for(s4, n, 8, resident_blocks(dice_ce_grad_kernel<2, 8, true>)) : 1, gy);
         fpl_launch(dice_ce_grad_kernel<2, 8, true>, grid, kThreads, 0, (cudaStream_t)stream, logits, src, sums, w_dice, w_ce, w_ent,
                    grad_scale, grad_scale_dev, loss, dlogits, n, s4, n_global, hard_dice);
