@@ -150,3 +150,28 @@ def test_training_all_copies_the_graphs_static_dice_output():
     # mean over the 3 steps, then over the 2 domains
     expect = (np.array([0.2, 0.4]) + np.array([0.6, 0.0])) / 2
     np.testing.assert_allclose(out["class_dice"], expect, rtol=1e-12)
+
+
+def test_data_parallel_mode_selection(monkeypatch):
+    """enable_data_parallel: 'deferred' (default) = one all-reduce of the master gradient buffer per step, no hooks inside
+    backward; 'overlapped' = the bucketed hook protocol; [training] grad_allreduce and $FPL_GRAD_ALLREDUCE select it."""
+    class _Net(torch.nn.Module):
+        grad_ready_hook = grad_wait_hook = "stale"
+
+    cfg = {"dataset": {"tensor_type": "float"}, "network": {}, "training": {}, "testing": {}}
+    monkeypatch.delenv("FPL_GRAD_ALLREDUCE", raising=False)
+    ag = A.SegmentationAgent(cfg, "train")
+    ag.net = _Net()
+    red = ag.enable_data_parallel()
+    assert isinstance(red, A.DeferredGradAllReducer) and ag.reducer is red
+    assert ag.net.grad_ready_hook is None and ag.net.grad_wait_hook is None
+    red = ag.enable_data_parallel("overlapped")
+    assert isinstance(red, A.GradAllReducer) and ag.net.grad_ready_hook == red.hook and ag.net.grad_wait_hook == red.finish
+    ag.config["training"]["grad_allreduce"] = "overlapped"
+    assert isinstance(ag.enable_data_parallel(), A.GradAllReducer)
+    monkeypatch.setenv("FPL_GRAD_ALLREDUCE", "deferred")
+    assert isinstance(ag.enable_data_parallel(), A.DeferredGradAllReducer)
+    with pytest.raises(ValueError):
+        ag.enable_data_parallel("ring")
+    # nothing to reduce: a step without gradients is a no-op (no process group needed)
+    A.DeferredGradAllReducer(_Net()).finish()
